@@ -1,0 +1,235 @@
+"""Generate tests/golden/*.npz from the LIVE, UNMODIFIED reference (build container only).
+
+    python -m oracle.gen_golden          # needs /root/reference (read-only)
+
+Every fixture stores the inputs, the explicit random numbers that the reference
+consumed from its global generators (replayed from the seed)
+and the reference's outputs.  ``tests/test_oracle_golden.py`` checks the oracle
+restatement against them (CPU) and ``tests/test_gpu_*.py`` check the CUDA path.
+The reference ships no golden vectors of its own.
+"""
+import os
+import warnings
+
+import numpy as np
+import pandas as pd
+import torch
+from torch.utils.data import DataLoader
+
+from oracle import ref_harness
+from oracle import ynet_oracle as O
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+SMALL_ENC = [8, 8, 16, 16, 16]
+SMALL_DEC = [16, 16, 16, 8, 8]
+
+
+def build_ref_model(ns, obs, pred, n_wp, enc=SMALL_ENC, dec=SMALL_DEC, train_net='mosa_1',
+                    position=(0, 1, 2, 3, 4), network='original', n_fusion=None, seed=0, peaky=1.0):
+    torch.manual_seed(seed)
+    m = ns.ynet.YNet(obs_len=obs, pred_len=pred, segmentation_model_fp=None,
+                     encoder_channels=list(enc), decoder_channels=list(dec), n_waypoints=n_wp,
+                     train_net=train_net, position=list(position), network=network, n_fusion=n_fusion)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if 'lora_B' in n:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+        for d in (m.goal_decoder, m.traj_decoder):
+            d.predictor.weight.mul_(peaky)
+    return m
+
+
+def make_df(tracks, scene='s0'):
+    B, T, _ = tracks.shape
+    rows = [dict(frame=t, trackId=b, x=float(tracks[b, t, 0]), y=float(tracks[b, t, 1]),
+                 sceneId=scene, metaId=b) for b in range(B) for t in range(T)]
+    return pd.DataFrame(rows)
+
+
+def save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + '.npz')
+    np.savez_compressed(path, **arrays)
+    print(f'{name}: {os.path.getsize(path) / 1024:.1f} KiB')
+
+
+def gen_templates(ns):
+    for size in (1050, 1386):
+        d = ns.image_utils.create_dist_mat(size)
+        t = torch.Tensor(d).numpy()
+        # strided sample + exact checksums of the float32 bit patterns
+        save(f'dist_template_{size}', sample=t[::97, ::89], rows=t[[0, size // 2, size - 1]],
+             xor=np.bitwise_xor.reduce(t.view(np.uint32).ravel()),
+             sum64=np.float64(t.astype(np.float64).sum()))
+    g = ns.image_utils.create_gaussian_heatmap_template(1050, kernlen=31, nsig=4, normalize=False)
+    gt = torch.Tensor(g).numpy()
+    save('gauss_template_1050', centre=gt[525 - 16:525 + 16, 525 - 16:525 + 16],
+         sum64=np.float64(gt.astype(np.float64).sum()))
+
+
+def gen_patch(ns):
+    tmpl = torch.Tensor(ns.image_utils.create_dist_mat(130))
+    traj = np.array([[10.5, 20.5], [0.5, 1.5], [47.49, 31.0], [11.5, 7.0], [0.0, 0.0], [2.5, 3.5]],
+                    dtype=np.float32)
+    out = torch.stack(ns.image_utils.get_patch(tmpl, traj, 32, 48)).numpy()
+    save('get_patch', template=tmpl.numpy(), traj=traj, out=out, H=32, W=48)
+
+
+def gen_sampling(ns):
+    torch.manual_seed(3)
+    p = torch.sigmoid(torch.randn(3, 1, 16, 24) * 3)
+    cases = {}
+    torch.manual_seed(11)
+    cases['repl_out'] = ns.image_utils.sampling(p, 500, rel_threshold=0.3, replacement=True).numpy()
+    torch.manual_seed(11)
+    cases['repl_uniforms'] = O.HostRng.uniforms(3, 500)
+    torch.manual_seed(12)
+    cases['norepl_out'] = ns.image_utils.sampling(p, 20).numpy()
+    torch.manual_seed(12)
+    cases['norepl_expo'] = O.HostRng.exponentials(3, 16 * 24)
+    torch.manual_seed(13)
+    cases['one_out'] = ns.image_utils.sampling(p, 1, rel_threshold=0.05).numpy()
+    torch.manual_seed(13)
+    cases['one_expo'] = O.HostRng.exponentials(3, 16 * 24)
+    torch.manual_seed(14)
+    cases['repl_nothr_out'] = ns.image_utils.sampling(p, 64, replacement=True).numpy()
+    torch.manual_seed(14)
+    cases['repl_nothr_uniforms'] = O.HostRng.uniforms(3, 64)
+    save('sampling', prob=p.numpy(), **cases)
+
+
+def gen_softargmax(ns):
+    torch.manual_seed(4)
+    x = torch.randn(2, 3, 32, 48) * 4
+    sa = ns.softargmax.SoftArgmax2D(normalized_coordinates=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        out = sa(x).numpy()
+        sm = torch.softmax(x.view(2, 3, -1), 2).view_as(x)
+        m = ns.ynet.YNet.softargmax_on_softmax_map(None, sm).numpy()
+        smx = ns.ynet.YNet.softmax(None, x).numpy()
+    save('softargmax', x=x.numpy(), out=out, softmax=smx, on_softmax_map=m)
+
+
+def gen_kmeans(ns):
+    torch.manual_seed(5)
+    X = torch.stack([torch.randint(0, 96, (2000,)), torch.randint(0, 64, (2000,))], 1).float()
+    np.random.seed(7)
+    ids, cen = ns.kmeans.kmeans(X=X.clone(), num_clusters=7, distance='euclidean',
+                                device=torch.device('cpu'), tqdm_flag=False, tol=0.001, iter_limit=1000)
+    np.random.seed(7)
+    init = O.HostRng.kmeans_init(2000, 7)
+    # crafted duplicate points -> an empty cluster -> reseed path (kmeans.py:82-83)
+    X2 = torch.cat([torch.tensor([[5., 5.]] * 6), X[:200]], 0)
+    perm = np.arange(206)
+
+    class _Fixed:
+        pass
+    orig_choice = np.random.choice
+    np.random.choice = lambda n, k, replace=False: np.array([0, 1, 2, 50, 100])
+    try:
+        torch.manual_seed(21)
+        ids2, cen2 = ns.kmeans.kmeans(X=X2.clone(), num_clusters=5, distance='euclidean',
+                                      device=torch.device('cpu'), tqdm_flag=False, tol=0.001, iter_limit=1000)
+    finally:
+        np.random.choice = orig_choice
+    torch.manual_seed(21)
+    reseeds = np.array([int(torch.randint(206, (1,))) for _ in range(16)])
+    save('kmeans', X=X.numpy(), init=init, ids=ids.numpy(), centres=cen.numpy(),
+         X2=X2.numpy(), init2=np.array([0, 1, 2, 50, 100]), ids2=ids2.numpy(), centres2=cen2.numpy(),
+         reseeds2=reseeds)
+
+
+def gen_cws(ns):
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        g1 = ns.evaluate.torch_multivariate_gaussian_heatmap(
+            torch.tensor([40.3, 20.2]), 32, 48, torch.tensor([13.0, -7.5]), 6, 2, 'cpu', True)
+        g2 = ns.evaluate.torch_multivariate_gaussian_heatmap(
+            torch.tensor([10.0, 30.0]), 32, 48, torch.tensor([-3.0, 4.0]), 5, 2, 'cpu', False)
+    save('cws_gaussian', g1=g1.numpy(), g2=g2.numpy())
+
+
+def gen_network(ns):
+    """Per-module forward of the reference model: features, goal logits, traj logits."""
+    for tag, kw in (('ynet', dict(network='original')),
+                    ('ynetmod', dict(network='fusion', n_fusion=2, position=('scene', 'motion', 'fusion')))):
+        m = build_ref_model(ns, 5, 6, 2, seed=2, **kw).eval()
+        torch.manual_seed(9)
+        scene = torch.softmax(torch.randn(1, 6, 64, 96), 1).expand(2, -1, -1, -1)
+        motion = torch.rand(2, 5, 64, 96) * 2
+        wp = torch.rand(2, 2, 64, 96) * 2
+        with torch.no_grad():
+            feats = m.pred_features(scene, motion)
+            goal = m.pred_goal(feats)
+            pyr = O.avgpool_pyramid(wp, len(feats))
+            traj = m.pred_traj([torch.cat([f, g], 1) for f, g in zip(feats, pyr)])
+        sd = {k: v.detach().numpy() for k, v in m.state_dict().items()}
+        save(f'network_{tag}', scene=scene[:1].numpy(), motion=motion.numpy(), wp=wp.numpy(),
+             goal=goal.numpy(), traj=traj.numpy(),
+             **{f'feat{i}': f.numpy() for i, f in enumerate(feats)},
+             **{'sd/' + k: v for k, v in sd.items()})
+
+
+def gen_evaluate(ns):
+    cfgs = [
+        dict(name='eval_sdd_short', H=64, W=96, obs=8, pred=12, wps=[11], B=3, resize=0.25, n_goal=20,
+             n_traj=1, T=1.0, ttst=False, cws=False, thr=0.01, cwsp=None, peaky=1.0),
+        dict(name='eval_ind_long_ttst_cws', H=64, W=96, obs=5, pred=30, wps=[14, 29], B=3, resize=0.33,
+             n_goal=20, n_traj=1, T=1.8, ttst=True, cws=True, thr=0.002,
+             cwsp=dict(sigma_factor=6, ratio=2, rot=True), peaky=30.0),
+    ]
+    for c in cfgs:
+        m = build_ref_model(ns, c['obs'], c['pred'], len(c['wps']), peaky=c['peaky'])
+        scene = O.synthetic_scene(c['H'], c['W'], seed=0)
+        tracks = O.synthetic_tracks(c['B'], c['obs'] + c['pred'], c['H'], c['W'], seed=1)
+        df = make_df(tracks / c['resize'])
+        ds = ns.dataloader.SceneDataset(df, resize=c['resize'], total_len=c['obs'] + c['pred'])
+        dl = DataLoader(ds, batch_size=1, collate_fn=ns.dataloader.scene_collate)
+        size = int(4200 * c['resize'])
+        tmpl = torch.Tensor(ns.image_utils.create_dist_mat(size))
+        torch.manual_seed(100)
+        np.random.seed(200)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            ade, fde, dfo, td = ns.evaluate.evaluate(
+                m, dl, {'s0': scene}, 'cpu', 'sdd', None, tmpl, c['wps'], 'test', c['n_goal'], c['n_traj'],
+                c['obs'], c['B'], c['resize'], c['T'], c['ttst'], c['cws'], c['thr'], c['cwsp'],
+                return_preds=True, return_samples=True, network='original')
+            traj = next(iter(dl))[0]
+        # replay the randoms the reference consumed (after the DataLoader's base_seed draw)
+        torch.manual_seed(100)
+        np.random.seed(200)
+        torch.empty((), dtype=torch.int64).random_()
+        rnd = {}
+        if c['ttst']:
+            rnd['uniforms'] = O.HostRng.uniforms(c['B'], 10000)
+            rnd['kmeans_init'] = np.stack([O.HostRng.kmeans_init(10000, c['n_goal'] - 1) for _ in range(c['B'])])
+        else:
+            rnd['expo'] = O.HostRng.exponentials(c['B'], c['H'] * c['W'])
+        sd = {k: v.detach().numpy() for k, v in m.state_dict().items()}
+        save(c['name'], scene=scene.numpy(), trajectory=traj.numpy(), template_size=size,
+             ade=dfo.ade.values.astype(np.float32), fde=dfo.fde.values.astype(np.float32),
+             goal_map=td['goal_map'], goal_sigmoid_map=td['goal_sigmoid_map'],
+             waypoint_sample=td['waypoint_sample'], prediction=td['prediction'],
+             cfg=np.array(repr({k: v for k, v in c.items()})),
+             **rnd, **{'sd/' + k: v for k, v in sd.items()})
+
+
+def main():
+    torch.set_num_threads(1)     # reference's global-sum quirk depends on thread count
+    ns = ref_harness.load()
+    gen_templates(ns)
+    gen_patch(ns)
+    gen_sampling(ns)
+    gen_softargmax(ns)
+    gen_kmeans(ns)
+    gen_cws(ns)
+    gen_network(ns)
+    gen_evaluate(ns)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,75 @@
+"""Import the UNMODIFIED reference from /root/reference (test infrastructure only).
+
+Only usable in the build container: /root/reference does not exist on the GPU
+box, so nothing that runs there (``-m gpu`` tests, ``smoke()``, ``bench.py``) may
+call into this module.  It is used by ``oracle/gen_golden.py`` to produce the
+committed fixtures under ``tests/golden/`` and by the ``not gpu`` tests that pin
+the restatement in ``oracle/ynet_oracle.py`` against the live reference.
+
+Recipe follows SURVEY.md Appendix A:
+  * ``loralib`` -> ``oracle/loralib_restatement.py`` (package not installed);
+  * empty ``seaborn`` / ``matplotlib`` stubs (imported at module top by
+    /root/reference/utils/data_utils.py:8-11, never called on the path).
+"""
+import importlib
+import os
+import sys
+import types
+
+REF_PATH = os.environ.get('REF_PATH', '/root/reference')
+
+_loaded = {}
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_PATH, 'models'))
+
+
+def _stub(name, **attrs):
+    if name in sys.modules:
+        return sys.modules[name]
+    m = types.ModuleType(name)
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    sys.modules[name] = m
+    return m
+
+
+def load():
+    """Return a namespace with the reference's modules (imported once).
+
+    The reference uses top-level package names ``models`` and ``utils``; they are
+    imported with REF_PATH temporarily at the front of sys.path and then kept in
+    sys.modules under their own names (the product package uses the distinct
+    name ``motion_style_transfer_b200`` so there is no clash).
+    """
+    if _loaded:
+        return _loaded['ns']
+    if not available():
+        raise RuntimeError(f'reference tree not found at {REF_PATH}')
+    from oracle import loralib_restatement
+    loralib_restatement.install_as_loralib()
+    mpl = _stub('matplotlib', rcParams={})
+    _stub('matplotlib.pyplot')
+    mpl.pyplot = sys.modules['matplotlib.pyplot']
+    _stub('seaborn')
+    sys.path.insert(0, REF_PATH)
+    try:
+        ns = types.SimpleNamespace()
+        ns.image_utils = importlib.import_module('utils.image_utils')
+        ns.softargmax = importlib.import_module('utils.softargmax')
+        ns.kmeans = importlib.import_module('utils.kmeans')
+        ns.evaluate = importlib.import_module('utils.evaluate')
+        ns.dataloader = importlib.import_module('utils.dataloader')
+        ns.ynet = importlib.import_module('models.ynet')
+        try:
+            ns.train_epoch = importlib.import_module('utils.train_epoch')
+            ns.trainer = importlib.import_module('models.trainer')
+        except Exception as e:  # pragma: no cover - depends on optional deps
+            ns.train_epoch = None
+            ns.trainer = None
+            ns.trainer_error = repr(e)
+    finally:
+        sys.path.remove(REF_PATH)
+    _loaded['ns'] = ns
+    return ns
