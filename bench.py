@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- agent-trajectories/sec of the Y-Net+MoSA forecasting hot path (TTST + CWS) on B200.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+
+A "step" = one pass of the evaluate() batch body (rasterise -> encoder -> goal decoder -> sigmoid ->
+TTST 10k multinomial + k-means(19) -> CWS -> 20 trajectory-decoder passes -> soft-argmax -> ADE/FDE)
+over one batch of `--agents` synthetic agents per GPU on a 416x416 synthetic semantic map.  Agents are
+independent, so ranks shard them with no data-path collective (weak scaling).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[2] shape: inD long-term eval with TTST + CWS (config/inD_longterm_eval.yaml)
+    'ind_long_ttst_cws': dict(obs=5, pred=30, wps=[14, 29], resize=0.33, T=1.8, thr=0.002, ttst=True, cws=True,
+                              cwsp=dict(sigma_factor=6, ratio=2, rot=True), n_goal=20, n_traj=1),
+    # BASELINE.json configs[0] shape: SDD short-term eval (config/sdd_shortterm_eval.yaml)
+    'sdd_short': dict(obs=8, pred=12, wps=[11], resize=0.25, T=1.0, thr=0.01, ttst=False, cws=False, cwsp=None,
+                      n_goal=20, n_traj=1),
+}
+ENC, DEC = [32, 32, 64, 64, 64], [64, 64, 64, 32, 32]
+H = W = 416
+GF_PER_AGENT = {'ind_long_ttst_cws': 371.6, 'sdd_short': 364.7}    # reference-executed GFLOP
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d['hbm_gbs'], bf16_tflops=d['bf16_tflops'], src='measured')
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, src='fallback')
+
+
+def build_model_state(cfg, seed=0):
+    """Random-init Y-Net + MoSA r=1 on encoder stages 0-4 (reference default init, LoRA B ~ N(0, 0.02),
+    predictors x50 so that the heat maps are peaky: SURVEY 8d)."""
+    from motion_style_transfer_b200.models.ynet import YNet
+    torch.manual_seed(seed)
+    m = YNet(obs_len=cfg['obs'], pred_len=cfg['pred'], segmentation_model_fp=None, encoder_channels=ENC,
+             decoder_channels=DEC, n_waypoints=len(cfg['wps']), train_net='mosa_1', position=[0, 1, 2, 3, 4],
+             network='original')
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if 'lora_B' in n:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+        m.goal_decoder.predictor.weight.mul_(50.0)
+        m.traj_decoder.predictor.weight.mul_(50.0)
+    return m
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={index}', f'--query-gpu={q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(',')]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def run_reference(args, cfg, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path = the oracle port
+    (oracle/ynet_oracle.py, pinned bit-for-bit against the live reference), on all host threads."""
+    if rank != 0:
+        return
+    from oracle import ynet_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    m = build_model_state(cfg)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    scene = O.synthetic_scene(H, W, seed=0)[None]
+    tmpl = O.create_dist_mat(int(4200 * cfg['resize'])).astype(np.float32)
+    B = args.ref_agents
+    times = []
+    for it in range(args.warmup + args.steps):
+        traj = O.synthetic_tracks(B, cfg['obs'] + cfg['pred'], H, W, seed=100 + it)
+        torch.manual_seed(1000 + it)
+        np.random.seed(2000 + it)
+        t0 = time.perf_counter()
+        O.evaluate_batch(sd, scene, traj, tmpl, cfg['wps'], cfg['n_goal'], cfg['n_traj'], cfg['obs'], cfg['resize'],
+                         cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'], cfg['cwsp'])
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1000 * sum(times) / len(times)
+    val = B * cfg['n_goal'] * cfg['n_traj'] / (ms / 1000)
+    sample = f'{B} agents x {cfg["n_goal"] * cfg["n_traj"]} trajectories per step, {args.steps} steps, 416x416'
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'agent-trajectories/sec', 'value': val, 'unit': 'agent-trajectories/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(args, cfg), 'agents_per_step': B},
+        'cpu_baseline': {'value': val, 'unit': 'agent-trajectories/s', 'cores': threads, 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': val, 'unit': 'agent-trajectories/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def workload_name(args, cfg):
+    return (f'Y-Net+MoSA(mosa_1, encoder stages 0-4) {args.workload} eval, obs {cfg["obs"]}/pred {cfg["pred"]}, '
+            f'{cfg["n_goal"]} goals, TTST={cfg["ttst"]} (10k samples + k-means 19), CWS={cfg["cws"]}, '
+            f'synthetic {H}x{W} semantic map, random-init weights')
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='ind_long_ttst_cws', choices=sorted(WORKLOADS))
+    ap.add_argument('--agents', type=int, default=64, help='agents per GPU per step')
+    ap.add_argument('--ref-agents', type=int, default=2, help='agents per step of the CPU reference arm')
+    ap.add_argument('--cpu-agents', type=int, default=4, help='agents of the bounded cpu_baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-layers', default=None, help='write a per-layer timing table to this path')
+    args = ap.parse_args()
+    cfg = WORKLOADS[args.workload]
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+
+    if args.impl == 'reference':
+        return run_reference(args, cfg, rank, world)
+
+    import torch.distributed as dist
+    from motion_style_transfer_b200 import ops, _lib
+    from motion_style_transfer_b200.utils.evaluate import forecast_batch
+    from motion_style_transfer_b200.utils.image_utils import DeviceRng
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.load()
+
+    model = build_model_state(cfg).to(dev).eval()
+    from oracle import ynet_oracle as O          # synthetic-input generators only (test infrastructure)
+    scene_host = O.synthetic_scene(H, W, seed=0)[None].contiguous().pin_memory()
+    tmpl = ops.create_dist_template(int(4200 * cfg['resize']), dev)
+    B = args.agents
+    n_iter = args.warmup + args.steps
+    total_len = cfg['obs'] + cfg['pred']
+    traj_host = [O.synthetic_tracks(B, total_len, H, W, seed=1 + rank * 1000 + it).pin_memory() for it in range(n_iter)]
+    traj_dev = [t.to(dev) for t in traj_host]
+    scene_dev = scene_host.to(dev)
+    rng = DeviceRng(seed=1234 + rank)
+
+    def step(scene, traj):
+        return forecast_batch(model, scene, traj, tmpl, cfg['wps'], cfg['n_goal'], cfg['n_traj'], cfg['obs'],
+                              cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'], cfg['cwsp'], rng=rng)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident throughput (`value`): inputs already in HBM ------------------------------------
+    for it in range(args.warmup):
+        step(scene_dev, traj_dev[it])
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ops.launch_count
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(args.warmup, n_iter):
+        res = step(scene_dev, traj_dev[it])
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = ops.launch_count - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    ms_step = ms_total / args.steps
+    traj_per_step = world * B * cfg['n_goal'] * cfg['n_traj']
+    value = traj_per_step / (ms_step / 1000)
+
+    # ---- end to end through the public call with HOST buffers (H2D of inputs + D2H of metrics inside) -----
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for it in range(args.warmup, n_iter):
+        sc = scene_host.to(dev, non_blocking=True)
+        tr = traj_host[it].to(dev, non_blocking=True)
+        r = step(sc, tr)
+        ade_h, fde_h = r['ade'].cpu(), r['fde'].cpu()
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3)) / args.steps
+    e2e_value = traj_per_step / (ms_e2e / 1000)
+    h2d = scene_host.numel() * 4 + traj_host[0].numel() * 4
+    d2h = 2 * B * 4
+
+    # ---- roofline of the dominant kernel: per-launch CUDA-event timing of one extra step -----------------
+    roofline, layer_table = None, None
+    if rank == 0:
+        peaks = load_peaks()
+        ops.profile_begin()
+        step(scene_dev, traj_dev[-1])
+        prof = ops.profile_end()
+        layer_table = prof
+        if prof:
+            by_kernel = {}
+            for p in prof:
+                k = by_kernel.setdefault(p['kernel'], dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
+                k['ms'] += p['ms']
+                k['flops'] += p['flops']
+                k['bytes'] += p['bytes']
+                k['n'] += 1
+            top_name, top = max(by_kernel.items(), key=lambda kv: kv[1]['ms'])
+            step_ms = sum(p['ms'] for p in prof)
+            if top['flops'] > 0:
+                ach = top['flops'] / (top['ms'] / 1000) / 1e12
+                roofline = dict(bound='tensor', kernel=top_name, achieved=ach, peak=peaks['bf16_tflops'],
+                                unit='TFLOP/s', frac=ach / peaks['bf16_tflops'], traffic=None,
+                                launches=top['n'], avg_launch_ms=top['ms'] / top['n'],
+                                share_of_step=top['ms'] / step_ms, peak_source=peaks['src'] + ' (burst bf16 cuBLAS)')
+            else:
+                ach = top['bytes'] / (top['ms'] / 1000) / 1e9
+                roofline = dict(bound='hbm', kernel=top_name, achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s',
+                                frac=ach / peaks['hbm_gbs'], traffic=None, launches=top['n'],
+                                avg_launch_ms=top['ms'] / top['n'], share_of_step=top['ms'] / step_ms,
+                                peak_source=peaks['src'])
+        if args.profile_layers:
+            with open(args.profile_layers, 'w') as f:
+                json.dump(dict(step_ms=sum(p['ms'] for p in prof), launches=prof), f, indent=1)
+
+    # ---- bounded CPU baseline (oracle port) on this host, rank 0 at N=1 only ------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        Bc = args.cpu_agents
+        traj = O.synthetic_tracks(Bc, total_len, H, W, seed=77)
+        tm = O.create_dist_mat(int(4200 * cfg['resize'])).astype(np.float32)
+        torch.manual_seed(1)
+        np.random.seed(2)
+        t0 = time.perf_counter()
+        O.evaluate_batch(sd, scene_host, traj, tm, cfg['wps'], cfg['n_goal'], cfg['n_traj'], cfg['obs'],
+                         cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'], cfg['cwsp'])
+        dt = time.perf_counter() - t0
+        cpu_baseline = dict(value=Bc * cfg['n_goal'] * cfg['n_traj'] / dt, unit='agent-trajectories/s', cores=threads,
+                            kind='port', sample=f'{Bc} agents x {cfg["n_goal"]} trajectories, one batch, '
+                                                f'{dt:.1f} s, torch CPU fp32 with {threads} threads')
+
+    if rank == 0:
+        out = {
+            'metric': 'agent-trajectories/sec', 'value': value, 'unit': 'agent-trajectories/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': model.engine.backend_dtype(), 'data': 'synthetic',
+            'config': {'workload': workload_name(args, cfg), 'agents_per_gpu_per_step': B,
+                       'global_agents_per_step': world * B, 'parallelism': f'dp{world} (agents sharded, no collective)',
+                       'l2': 'inputs + activations per step >> 126 MB L2 (fresh synthetic tracks every step)',
+                       'gflop_per_agent_reference_executed': GF_PER_AGENT[args.workload]},
+            'e2e': {'value': e2e_value, 'unit': 'agent-trajectories/s', 'ms_per_step': ms_e2e,
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+            'effective_tflops_reference_normalised': value / (cfg['n_goal'] * cfg['n_traj']) *
+                                                      GF_PER_AGENT[args.workload] / 1e3,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

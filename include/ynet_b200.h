@@ -1,0 +1,252 @@
+/*
+ * ynet_b200.h -- C ABI of libynet_b200.so: the B200 (sm_100a) implementation of the Y-Net
+ * scene-heatmap forecasting hot path of vita-epfl/motion-style-transfer.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; its seam for this path is the
+ * method set of models/ynet.py::YNet (ynet.py:551-600) plus the free functions get_patch, sampling,
+ * kmeans, SoftArgmax2D and torch_multivariate_gaussian_heatmap.  Each entry point below cites the
+ * reference lines it replaces (paths relative to the reference tree).  INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns all buffers, including workspaces (sizes via the *_workspace_bytes queries);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous w.r.t. the host;
+ *   - return value: 0 = success, negative = YNET_E_* (message via ynet_last_error_string());
+ *   - activations are float32 NCHW unless a function says otherwise; weights are float32 OIHW
+ *     exactly as stored in the reference's state_dict.
+ */
+#ifndef YNET_B200_H_
+#define YNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YNET_OK 0
+#define YNET_E_INVALID (-1)   /* bad shape / argument                                        */
+#define YNET_E_ALIGN (-2)     /* pointer or extent not aligned as required                   */
+#define YNET_E_ARCH (-3)      /* device is not sm_100                                         */
+#define YNET_E_CUDA (-4)      /* CUDA runtime / driver error (see ynet_last_error_string)    */
+#define YNET_E_WORKSPACE (-5) /* workspace too small                                          */
+#define YNET_E_UNSUPPORTED (-6)
+
+#define YNET_MAX_SOURCES 4
+
+/* How a conv source is read (fuses nn.MaxPool2d / F.interpolate / torch.cat into the loader). */
+#define YNET_SRC_DIRECT 0 /* source has the conv's spatial size                               */
+#define YNET_SRC_POOL2 1  /* source is 2H x 2W; loader takes the 2x2 max   (ynet.py:202,215)  */
+#define YNET_SRC_UP2 2    /* source is H/2 x W/2; loader does bilinear x2, align_corners=False
+                             (ynet.py:463)                                                     */
+
+typedef struct ynet_conv_src {
+  const void* ptr;      /* float32 NCHW                                                       */
+  int32_t channels;     /* channels contributed by this source (concat order = array order)   */
+  int32_t mode;         /* YNET_SRC_*                                                          */
+  int64_t batch_stride; /* elements between consecutive images; 0 = broadcast (Tensor.expand,
+                           evaluate.py:117)                                                    */
+  int64_t batch_mod;    /* > 0: image n reads source image n % batch_mod (the encoder features
+                           are shared by the n_goal trajectory-decoder passes, evaluate.py:259) */
+} ynet_conv_src;
+
+int ynet_version(void);
+const char* ynet_last_error_string(void);
+/* Fills sm count / compute capability of the current device; YNET_E_ARCH if it is not sm_100. */
+int ynet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * a3  rasterisation: get_patch + torch.stack  (utils/image_utils.py:40-63, evaluate.py:112-114,
+ *     250-253, train_epoch.py:63-78).  out[n,i,j] = tmpl[mid_y - y_n + i, mid_x - x_n + j] with
+ *     (x_n, y_n) = round-half-even(coords[n]).  Bit-exact copy of template values.
+ *     coords: (n, 2) float32 (x, y).  out: (n, H, W) float32.  oob_flag (optional int32): set to 1
+ *     if any window leaves the template (the reference would silently mis-slice).
+ * ------------------------------------------------------------------------------------------- */
+int ynet_rasterize_patches(const float* tmpl, int32_t tmpl_h, int32_t tmpl_w, const float* coords,
+                           int32_t n, float* out, int32_t H, int32_t W, int32_t* oob_flag, void* stream);
+
+/* Analytic variant for the distance template of create_dist_mat(size) (image_utils.py:30-37):
+ * float32(sqrt(double(di^2+dj^2)) / sqrt(double(2 mid^2)) * 2), bit-identical to the gather. */
+int ynet_rasterize_dist_analytic(int32_t tmpl_size, const float* coords, int32_t n, float* out, int32_t H,
+                                 int32_t W, void* stream);
+
+/* a1  create_dist_mat(size) as float32 (trainer.py:209,326). out: (size, size). */
+int ynet_create_dist_template(int32_t size, float* out, void* stream);
+
+/* a9  waypoint pyramid: nn.AvgPool2d(2^i), i = 1..n_levels-1, of the full-resolution map
+ *     (evaluate.py:255-257, train_epoch.py:97-100).  in: (n, H, W); outs_host[i-1]: (n, H>>i, W>>i). */
+int ynet_avgpool_pyramid(const float* in, int32_t n, int32_t H, int32_t W, int32_t n_levels,
+                         float* const* outs_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a12 SoftArgmax2D.forward (utils/softargmax.py:55-81): rows = B*C maps of H x W ->
+ *     out (rows, 2) = (x, y); eps = 1e-6 added to the exp-sum after max subtraction.
+ *     row r starts at x + r * row_stride (row_stride = H*W for a dense (B*C, H, W) block; C*H*W
+ *     to read one channel of every image, evaluate.py:142-143).
+ *     workspace: ynet_softargmax2d_workspace_bytes(rows, H, W).
+ * a13 YNet.softmax (ynet.py:578-579) and softargmax_on_softmax_map (ynet.py:588-600).
+ * ------------------------------------------------------------------------------------------- */
+int64_t ynet_softargmax2d_workspace_bytes(int32_t rows, int32_t H, int32_t W);
+int ynet_softargmax2d(const float* x, int32_t rows, int64_t row_stride, int32_t H, int32_t W, float* out,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+int ynet_spatial_softmax(const float* x, int32_t rows, int64_t S, float* out, void* stream);
+int ynet_expectation2d(const float* p, int32_t rows, int32_t H, int32_t W, float* out, void* stream);
+
+/* a10 YNet.sigmoid with temperature on selected channels (evaluate.py:128-131):
+ *     out[b, k] = sigmoid(logits[b, ch[k]] / T).  logits (B, C, S); ch_host: n_ch host ints. */
+int ynet_sigmoid_select(const float* logits, int32_t B, int32_t C, int64_t S, const int32_t* ch_host,
+                        int32_t n_ch, float temperature, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a11 sampling (utils/image_utils.py:110-135) = threshold/normalise + torch.multinomial + unravel.
+ *
+ * ynet_sampling_prepare: per-row max and the masked GLOBAL sum (image_utils.py:114-119); the sum
+ *     is float64-accumulated in a fixed order, rounded to float32.  rowmax (rows), gsum (1 float).
+ * ynet_multinomial_replacement: ATen CPU multinomial, replacement=True: sequential float32 CDF,
+ *     c /= c[S-1], c[S-1] = 1, idx = first j with double(c[j]) >= u.  Bit-exact.
+ *     prob (rows, S); rel_threshold < 0 disables the mask/normalise step (then rowmax/gsum unused);
+ *     uniforms (rows, n) float64; cdf_ws (rows, S) float32 scratch; idx (rows, n) int64;
+ *     xy (rows, n, 2) float32 = (idx % W, floor(idx / W)) or NULL.
+ * ynet_multinomial_topk: replacement=False or n == 1: top-n of p / q by descending value
+ *     (q ~ Exp(1) supplied, float32 (rows, S)); ties -> lowest index.  Bit-exact.
+ * ------------------------------------------------------------------------------------------- */
+int64_t ynet_sampling_prepare_workspace_bytes(int32_t rows, int64_t S);
+int ynet_sampling_prepare(const float* prob, int32_t rows, int64_t S, float rel_threshold, float* rowmax,
+                          float* gsum, void* workspace, int64_t workspace_bytes, void* stream);
+int ynet_multinomial_replacement(const float* prob, int32_t rows, int64_t S, float rel_threshold,
+                                 const float* rowmax, const float* gsum, const double* uniforms, int32_t n,
+                                 float* cdf_ws, int64_t* idx, float* xy, int32_t W, void* stream);
+int ynet_multinomial_topk(const float* prob, const float* expo, int32_t rows, int64_t S, float rel_threshold,
+                          const float* rowmax, const float* gsum, int32_t n, int64_t* idx, float* xy,
+                          int32_t W, void* stream);
+/* Counter-based device generators for the production path (the parity path supplies randoms). */
+int ynet_rng_uniform_f64(uint64_t seed, uint64_t offset, int64_t n, double* out, void* stream);
+int ynet_rng_exponential_f32(uint64_t seed, uint64_t offset, int64_t n, float* out, void* stream);
+/* K distinct indices in [0, N) per row: device analogue of np.random.choice(N, K, replace=False)
+ * (utils/kmeans.py:17).  out (rows, K) int32. */
+int ynet_rng_choice(uint64_t seed, uint64_t offset, int32_t rows, int32_t N, int32_t K, int32_t* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a14 kmeans (utils/kmeans.py:22-108, euclidean), batched over agents (the reference loops in
+ *     Python, evaluate.py:147-155).  X (B, N, 2) float32; init_idx (B, K) int32 (np.random.choice,
+ *     kmeans.py:17); reseed_idx (B, R) int32 consumed in (iteration, cluster) order for empty
+ *     clusters (torch.randint, kmeans.py:83) or NULL; stop when shift^2 < tol or iter_limit.
+ *     centres (B, K, 2); assign (B, N) int32 or NULL; iters (B) int32 or NULL;
+ *     status (B) int32 or NULL: bit0 = reseed stream exhausted.
+ * ------------------------------------------------------------------------------------------- */
+int ynet_kmeans_batched(const float* X, int32_t B, int32_t N, int32_t K, const int32_t* init_idx,
+                        const int32_t* reseed_idx, int32_t R, float tol, int32_t iter_limit, float* centres,
+                        int32_t* assign, int32_t* iters, int32_t* status, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a16 CWS (utils/evaluate.py:9-34, 172-224), one waypoint level for all goals and agents:
+ *     prior_g,b = oriented Gaussian of torch_multivariate_gaussian_heatmap; returns the
+ *     softargmax_on_softmax_map of sigmoid_map[b] * prior (first trajectory per goal).
+ *     sig (B, H, W) = sigmoid map of this waypoint; wp_in (G, B, 2) current waypoint (x, y);
+ *     last_obs (B, 2); length_ratio = 1/(waypoint_num+2); sigma_factor (G) float per goal
+ *     (sigma_factor - traj_idx); out (G, B, 2).
+ * ------------------------------------------------------------------------------------------- */
+int ynet_cws_waypoint(const float* sig, int32_t B, int32_t H, int32_t W, const float* wp_in, int32_t G,
+                      const float* last_obs, float length_ratio, const float* sigma_factor, float ratio,
+                      int32_t rot, float* out, void* stream);
+/* Materialises the normalised waypoint map (for the n_traj > 1 re-sampling, evaluate.py:213-216):
+ *     out (B, H, W) for ONE goal g. */
+int ynet_cws_waypoint_map(const float* sig, int32_t B, int32_t H, int32_t W, const float* wp_in_g,
+                          const float* last_obs, float length_ratio, float sigma_factor, float ratio,
+                          int32_t rot, float* out, void* stream);
+
+/* a17 ADE / FDE (evaluate.py:276-277, 290-291): gt (B, T, 2); trajs (K, B, T, 2); wps (K, B, n_wp, 2).
+ *     ade (B), fde (B): min over K of mean_t ||.||/resize and ||gt_goal - wp_last||/resize. */
+int ynet_ade_fde(const float* gt, const float* trajs, const float* wps, int32_t K, int32_t B, int32_t T,
+                 int32_t n_wp, float resize_factor, float* ade, float* fde, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a4-a8 network, reference-grade float32 engine (CUDA cores, fp32 accumulate).
+ *
+ * ynet_conv3x3_f32: F.conv2d(cat(sources), W, b, padding=1) [+ ReLU]  (ynet.py:192-211, 419-447)
+ *     with the producer ops fused into the loader (YNET_SRC_*).  weight_packed is the layout-1
+ *     output of ynet_lora_fold: [sum C_s][3*3][C_out] (OIHW transposed so that CTAs stage it coalesced).
+ * ynet_conv1x1_f32: the predictor (ynet.py:450-451,469).
+ * ynet_predictor_softargmax_f32: predictor + SoftArgmax2D in one pass (ynet.py:469 + 582-583):
+ *     x (N, C_in, H, W) -> out (N, C_out, 2); logits are never written to HBM.
+ * ynet_lora_fold: loralib 0.1.1 Conv2d.forward weight (ynet.py:143): W + (B @ A).view(W.shape)/r
+ *     (lora_A / lora_B may be NULL = plain conv).  out_layout 0 = OIHW, 1 = packed [C_in][k*k][C_out].
+ * ------------------------------------------------------------------------------------------- */
+int ynet_conv3x3_f32(const ynet_conv_src* srcs_host, int32_t n_src, int32_t N, int32_t H, int32_t W,
+                     const float* weight_packed, const float* bias, int32_t C_out, int32_t relu, float* out,
+                     void* stream);
+int ynet_conv1x1_f32(const float* x, int32_t N, int32_t C_in, int64_t S, const float* weight,
+                     const float* bias, int32_t C_out, float* out, void* stream);
+int64_t ynet_predictor_softargmax_workspace_bytes(int32_t N, int32_t C_out, int32_t H, int32_t W);
+int ynet_predictor_softargmax_f32(const float* x, int32_t N, int32_t C_in, int32_t H, int32_t W,
+                                  const float* weight, const float* bias, int32_t C_out, float* out,
+                                  void* workspace, int64_t workspace_bytes, void* stream);
+int ynet_maxpool2x2_f32(const float* x, int64_t planes, int32_t H, int32_t W, float* out, void* stream);
+int ynet_upsample_bilinear2x_f32(const float* x, int64_t planes, int32_t H, int32_t W, float* out,
+                                 void* stream);
+int ynet_lora_fold(const float* weight, const float* lora_A, const float* lora_B, int32_t C_out, int32_t C_in,
+                   int32_t ksize, int32_t rank, int32_t out_layout, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a4-a8 network, tensor-core engine (tcgen05.mma kind::f16, bf16 operands, fp32 TMEM accumulate).
+ *
+ * Activations live in HBM as bf16 "C8" planes: [N][C/8][H][W][8] (C padded to a multiple of 16),
+ * so that a TMA box of pixels is directly a no-swizzle K-major UMMA operand.
+ * ynet_tc_pack_weights: OIHW fp32 -> the per-CTA shared-memory image (bf16 core matrices).
+ * ynet_tc_conv3x3: one 3x3 conv (+bias, +ReLU) over up to YNET_MAX_SOURCES C8 sources.
+ * See DESIGN.md "Tensor-core conv engine".
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ynet_tc_src {
+  const void* ptr;      /* bf16 C8 planes                                                     */
+  int32_t channels_pad; /* multiple of 16                                                     */
+  int32_t reserved;
+  int64_t batch_stride; /* elements (bf16); 0 = broadcast                                     */
+} ynet_tc_src;
+
+int ynet_tc_supported(void);
+int ynet_tc_pack_f32_to_c8(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, int64_t batch_stride,
+                           void* out_c8, int32_t C_pad, void* stream);
+int ynet_tc_unpack_c8_to_f32(const void* x_c8, int32_t N, int32_t C, int32_t C_pad, int32_t H, int32_t W,
+                             float* out, void* stream);
+int64_t ynet_tc_packed_weight_bytes(int32_t C_out, int32_t n_src, const int32_t* src_channels_pad_host);
+int ynet_tc_pack_weights(const float* weight, int32_t C_out, int32_t n_src, const int32_t* src_channels_host,
+                         const int32_t* src_channels_pad_host, void* packed, void* stream);
+int ynet_tc_conv3x3(const ynet_tc_src* srcs_host, int32_t n_src, int32_t N, int32_t H, int32_t W,
+                    const void* packed_weight, const float* bias, int32_t C_out, int32_t relu, void* out_c8,
+                    int32_t C_out_pad, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a18 fine-tuning step pieces (utils/train_epoch.py:86-115, models/trainer.py:197-206).
+ * ------------------------------------------------------------------------------------------- */
+/* BCEWithLogitsLoss(mean) forward + d(loss*scale)/dlogits in one pass.  loss_out: 1 float (mean,
+ * unscaled).  grad may be NULL.  workspace: ynet_bce_workspace_bytes(n). */
+int64_t ynet_bce_workspace_bytes(int64_t n);
+int ynet_bce_logits_fwd_bwd(const float* logits, const float* target, int64_t n, float grad_scale,
+                            float* loss_out, float* grad, void* workspace, int64_t workspace_bytes,
+                            void* stream);
+/* dgrad of conv3x3 (padding 1): dx (N, C_in, H, W) = conv3x3(dy, flip/transpose(W)); dy is first
+ * masked by (y > 0) when relu_out != NULL (ReLU backward fused in the loader). */
+int ynet_conv3x3_dgrad_f32(const float* dy, const float* relu_out, int32_t N, int32_t H, int32_t W,
+                           const float* weight, int32_t C_out, int32_t C_in, float* dx, void* stream);
+/* wgrad: dW (C_out, C_in, 3, 3) = sum_n,pixels x (*) dy ; db (C_out). */
+int64_t ynet_conv3x3_wgrad_workspace_bytes(int32_t N, int32_t H, int32_t W, int32_t C_out, int32_t C_in);
+int ynet_conv3x3_wgrad_f32(const float* x, const float* dy, const float* relu_out, int32_t N, int32_t H,
+                           int32_t W, int32_t C_in, int32_t C_out, float* dW, float* db, void* workspace,
+                           int64_t workspace_bytes, void* stream);
+int ynet_maxpool2x2_bwd_f32(const float* x, const float* dy, int64_t planes, int32_t H, int32_t W, float* dx,
+                            void* stream);
+int ynet_upsample_bilinear2x_bwd_f32(const float* dy, int64_t planes, int32_t H, int32_t W, float* dx,
+                                     void* stream);
+/* dA = s * B^T dM, dB = s * dM A^T with dM = dW.view(C_out*k, C_in*k)  (SURVEY 3.2). */
+int ynet_lora_grad(const float* dW, const float* lora_A, const float* lora_B, int32_t C_out, int32_t C_in,
+                   int32_t ksize, int32_t rank, float* dA, float* dB, void* stream);
+/* torch.optim.Adam defaults on one flat buffer; grad_scale folds the 1/world_size average. */
+int ynet_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   int32_t step, float lr, float beta1, float beta2, float eps, float grad_scale,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YNET_B200_H_ */

@@ -1,0 +1,150 @@
+"""Device executor of the Y-Net encoder / decoders (models/ynet.py:170-471 of the reference).
+
+The nn.Module tree in ``models/ynet.py`` only holds parameters (so that checkpoints stay
+byte-compatible); this class walks that tree and issues the CUDA kernels.  Producer ops are fused
+into each conv's loader -- channel concat (torch.cat), 2x2 max-pool, bilinear x2 -- and batch-1
+sources are broadcast (the semantic map is shared by all agents of a scene, evaluate.py:117).
+
+Two back ends behind the same walk:
+  * ``fp32``  -- CUDA-core fp32 kernels (conv_f32.cu): the <=1e-3 parity mode;
+  * ``bf16``  -- tcgen05/TMEM implicit-GEMM kernels (conv_tc.cu): the throughput mode.
+"""
+import torch
+
+from . import ops
+from .ops import SRC_DIRECT, SRC_POOL2, SRC_UP2
+
+
+class ChannelCat(tuple):
+    """A lazily concatenated feature map: tuple of (N|1, C_i, H, W) tensors, concat along C.
+
+    The reference materialises ``torch.cat([feature, waypoint_map], dim=1)`` (evaluate.py:259,
+    ynet.py:387,466); the conv loader here walks the parts instead.
+    """
+
+    @property
+    def shape(self):
+        n = max(p.shape[0] for p in self)
+        return torch.Size((n, sum(p.shape[1] for p in self)) + tuple(self[0].shape[2:]))
+
+    def materialize(self):
+        n = self.shape[0]
+        return torch.cat([p.expand(n, -1, -1, -1) for p in self], dim=1)
+
+
+def _parts(x):
+    """Normalise a feature (tensor | ChannelCat | tuple) to a list of batch-broadcastable tensors."""
+    if isinstance(x, torch.Tensor):
+        x = (x,)
+    out = []
+    for t in x:
+        if t.dim() != 4:
+            raise ValueError(f'expected NCHW feature maps, got shape {tuple(t.shape)}')
+        if t.shape[0] > 1 and t.stride(0) == 0:       # Tensor.expand over the batch
+            t = t[:1]
+        out.append(t)
+    return out
+
+
+class YNetEngine:
+    def __init__(self, model, backend='fp32'):
+        self.model = model
+        self.backend = backend
+        self._wcache = {}
+
+    def backend_dtype(self):
+        """Arithmetic type of the conv path (bench.py `dtype`)."""
+        return 'f32' if self.backend == 'fp32' else 'bf16'
+
+    # ---------------------------------------------------------------- weights
+    def _conv_params(self, module, key):
+        """(packed effective weight, bias) of a conv module; LoRA folded on device, cached by version."""
+        A = getattr(module, 'lora_A', None)
+        Bm = getattr(module, 'lora_B', None)
+        ver = (module.weight._version, module.weight.data_ptr(),
+               None if A is None else (A._version, A.data_ptr()),
+               None if Bm is None else (Bm._version, Bm.data_ptr()))
+        hit = self._wcache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1], hit[2]
+        w = module.weight.detach()
+        packed = ops.lora_fold(w, None if A is None else A.detach(), None if Bm is None else Bm.detach(), packed=True)
+        bias = None if module.bias is None else module.bias.detach()
+        self._wcache[key] = (ver, packed, bias)
+        return packed, bias
+
+    def _conv(self, module, key, sources, relu, H, W):
+        packed, bias = self._conv_params(module, key)
+        N = max(t.shape[0] for t, _ in sources)
+        return ops.conv3x3_f32(sources, packed, bias, relu, N, H, W)
+
+    # ---------------------------------------------------------------- encoder
+    def _run_stages(self, stages, key, x_parts, first_mode):
+        """Walk an nn.ModuleList of Sequential stages ([conv,relu] | [pool,conv,relu,conv,relu] | [pool])."""
+        feats = []
+        cur = x_parts
+        mode = first_mode
+        for si, stage in enumerate(stages):
+            mods = list(stage)
+            convs = [(j, m) for j, m in enumerate(mods) if isinstance(m, torch.nn.Conv2d)]
+            has_pool = any(isinstance(m, torch.nn.MaxPool2d) for m in mods)
+            H, W = cur[0].shape[2], cur[0].shape[3]
+            if has_pool:
+                H, W = H // 2, W // 2
+            if not convs:                                   # trailing pool-only stage
+                if len(cur) != 1:
+                    cur = [ChannelCat(cur).materialize()]
+                y = ops.maxpool2x2(cur[0])
+                feats.append(y)
+                cur = [y]
+                continue
+            m_in = SRC_POOL2 if has_pool else mode
+            for ci, (j, conv) in enumerate(convs):
+                srcs = [(t, m_in if ci == 0 else SRC_DIRECT) for t in cur]
+                y = self._conv(conv, f'{key}.{si}.{j}', srcs, True, H, W)
+                cur = [y]
+            feats.append(cur[0])
+        return feats, cur
+
+    def pred_features(self, scene_map, motion_map):
+        enc = self.model.encoder
+        scene = _parts(scene_map)
+        motion = _parts(motion_map)
+        if self.model.network == 'fusion':
+            sf, _ = self._run_stages(enc.scene_stages, 'encoder.scene_stages', scene, SRC_DIRECT)
+            mf, _ = self._run_stages(enc.motion_stages, 'encoder.motion_stages', motion, SRC_DIRECT)
+            feats = [ChannelCat((a, b)) for a, b in zip(sf, mf)]
+            ff, _ = self._run_stages(enc.fusion_stages, 'encoder.fusion_stages', list(feats[-1]), SRC_DIRECT)
+            return feats + ff
+        feats, _ = self._run_stages(enc.stages, 'encoder.stages', scene + motion, SRC_DIRECT)
+        return feats
+
+    # ---------------------------------------------------------------- decoders
+    def decoder_trunk(self, decoder, key, features):
+        """Everything of YNetDecoder.forward (ynet.py:453-468) up to (not including) the predictor."""
+        feats = [_parts(f) for f in features][::-1]
+        c = feats[0]
+        H, W = c[0].shape[2], c[0].shape[3]
+        x = self._conv(decoder.center[0], f'{key}.center.0', [(t, SRC_DIRECT) for t in c], True, H, W)
+        x = self._conv(decoder.center[2], f'{key}.center.2', [(x, SRC_DIRECT)], True, H, W)
+        for i, skip in enumerate(feats[1:]):
+            H, W = skip[0].shape[2], skip[0].shape[3]
+            up = self._conv(decoder.upsample_conv[i], f'{key}.upsample_conv.{i}', [(x, SRC_UP2)], False, H, W)
+            srcs = [(up, SRC_DIRECT)] + [(t, SRC_DIRECT) for t in skip]
+            x = self._conv(decoder.decoder[i][0], f'{key}.decoder.{i}.0', srcs, True, H, W)
+            x = self._conv(decoder.decoder[i][2], f'{key}.decoder.{i}.2', [(x, SRC_DIRECT)], True, H, W)
+        return x
+
+    def decoder_logits(self, decoder, key, features):
+        x = self.decoder_trunk(decoder, key, features)
+        p = decoder.predictor
+        return ops.conv1x1_f32(x, p.weight.detach().reshape(p.weight.shape[0], -1), p.bias.detach())
+
+    def decoder_softargmax(self, decoder, key, features):
+        """predictor + SoftArgmax2D fused (ynet.py:469 + 582-583): the logits never reach HBM."""
+        x = self.decoder_trunk(decoder, key, features)
+        p = decoder.predictor
+        if p.weight.shape[0] > 32 or p.weight.shape[1] > 32:
+            return ops.softargmax2d(ops.conv1x1_f32(x, p.weight.detach().reshape(p.weight.shape[0], -1),
+                                                    p.bias.detach()))
+        return ops.predictor_softargmax_f32(x, p.weight.detach().reshape(p.weight.shape[0], -1), p.bias.detach())

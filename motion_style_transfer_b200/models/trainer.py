@@ -1,0 +1,353 @@
+"""Drop-in ``YNetTrainer`` for the reference's models/trainer.py:45-614.
+
+Constructor arguments, attributes, the train/test/load/save methods, the freeze-policy DSL
+(``train_net`` / ``position`` / ``ynet_bias``), the checkpoint layout and the stdout formats scraped
+by the reference's log tools are preserved; the compute runs through libynet_b200.so.
+Data preparation (pandas / cv2 / segmentation preprocessing, trainer.py:518-584) is outside the hot
+path: ``prepare_data`` delegates to the reference's own ``utils.data_utils`` when it is importable,
+and ``train_prepared`` / ``test_prepared`` accept ready-made (images dict, DataLoader) pairs.
+"""
+import pathlib
+import re
+from collections import OrderedDict, deque
+from copy import deepcopy
+
+import torch
+import torch.distributed as dist
+from torch.utils.data import DataLoader
+from tqdm import tqdm
+
+from .. import ops
+from ..autograd_engine import BCEWithLogitsLoss
+from ..utils.dataloader import SceneDataset, scene_collate
+from ..utils.evaluate import evaluate
+from ..utils.image_utils import create_dist_mat, create_gaussian_heatmap_template
+from ..utils.train_epoch import train_epoch
+from .ynet import YNet
+
+
+def _mark_bias(module):
+    for name, p in module.named_parameters():
+        if 'bias' in name:
+            p.requires_grad = True
+
+
+def mark_encoder_bias_trainable(model):
+    _mark_bias(model.encoder)
+    return model
+
+
+def mark_goal_bias_trainable(model):
+    _mark_bias(model.goal_decoder)
+    return model
+
+
+def mark_traj_bias_trainable(model):
+    _mark_bias(model.traj_decoder)
+    return model
+
+
+def mark_ynet_bias_trainable(model):
+    return mark_traj_bias_trainable(mark_goal_bias_trainable(mark_encoder_bias_trainable(model)))
+
+
+def apply_freeze_policy(model, train_net, position, network, ynet_bias=False):
+    """trainer.py:112-195: which parameters train for a given ``train_net`` / ``position``."""
+    for p in model.semantic_segmentation.parameters():
+        p.requires_grad = False
+    if train_net in ('all', 'train'):
+        return model
+    for p in model.parameters():
+        p.requires_grad = False
+    position = [str(i) for i in position]
+    enc = model.encoder
+    fusion_sets = {
+        'scene': ('scene_stages',), 'motion': ('motion_stages',), 'fusion': ('fusion_stages',),
+        'scene_fusion': ('scene_stages', 'fusion_stages'), 'motion_fusion': ('motion_stages', 'fusion_stages'),
+        'scene_motion': ('scene_stages', 'motion_stages'),
+        'scene_motion_fusion': ('scene_stages', 'motion_stages', 'fusion_stages'),
+    }
+    if train_net == 'encoder' and len(position) == 0:
+        for p in enc.parameters():
+            p.requires_grad = True
+    elif train_net == 'encoder':
+        for name, p in enc.named_parameters():
+            if name.split('.')[1] in position:
+                p.requires_grad = True
+    elif 'serial' in train_net or 'parallel' in train_net:
+        key = 'serial' if 'serial' in train_net else 'parallel'
+        for name, p in enc.named_parameters():
+            if key in name:
+                p.requires_grad = True
+    elif 'mosa' in train_net:
+        for name, p in enc.named_parameters():
+            if 'lora' in name:
+                p.requires_grad = True
+    elif 'semantic' in train_net:
+        for name, p in model.named_parameters():
+            if 'semantic_adapter' in name:
+                p.requires_grad = True
+    elif network == 'fusion' and train_net in fusion_sets:
+        for attr in fusion_sets[train_net]:
+            for p in getattr(enc, attr).parameters():
+                p.requires_grad = True
+    elif train_net == 'biasEncoder':
+        mark_encoder_bias_trainable(model)
+    elif train_net == 'biasGoal':
+        mark_goal_bias_trainable(model)
+    elif train_net == 'biasTraj':
+        mark_traj_bias_trainable(model)
+    elif train_net == 'bias':
+        mark_ynet_bias_trainable(model)
+    elif 'segmentation' in train_net:
+        layer = train_net.split('_')[1]
+        for name, p in model.semantic_segmentation.named_parameters():
+            if (layer in ['head', 'bias', 'bn'] and layer in name) or \
+                    re.search(rf'decoder.blocks.\d.{layer}', name) is not None:
+                p.requires_grad = True
+    else:
+        raise NotImplementedError
+    if ynet_bias:
+        mark_ynet_bias_trainable(model)
+    return model
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam defaults (trainer.py:197) with the update done by ``ynet_adam_step``.
+
+    Under torch.distributed (one process per GPU, agents sharded across ranks) the gradients of all
+    trainable tensors -- 8 190 floats for Y-Net mosa_1 -- are flattened into one buffer, summed with a
+    single NCCL all-reduce over NVLink and averaged inside the Adam kernel (grad_scale = 1/world).
+    """
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        for group in self.param_groups:
+            ps = [p for p in group['params'] if p.requires_grad and p.grad is not None]
+            if not ps:
+                continue
+            flat = torch.cat([p.grad.reshape(-1) for p in ps]) if (world > 1 or len(ps) > 1) else ps[0].grad.reshape(-1)
+            if world > 1:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            off = 0
+            for p in ps:
+                n = p.numel()
+                st = self.state[p]
+                if not st:
+                    st['step'] = 0
+                    st['exp_avg'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st['step'] += 1
+                ops.adam_step(p.data, flat[off:off + n], st['exp_avg'], st['exp_avg_sq'], st['step'], group['lr'],
+                              group['betas'][0], group['betas'][1], group['eps'], 1.0 / world)
+                off += n
+                # the kernel wrote through a raw pointer: bump the version so cached folded weights refresh
+                if hasattr(torch.autograd.graph, 'increment_version'):
+                    torch.autograd.graph.increment_version(p)
+                else:  # pragma: no cover
+                    p.add_(0)
+        return None
+
+
+class YNetTrainer:
+    def __init__(self, params, device=None):
+        self.params = params
+        self.device = device if device else torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+        print(f'Working on {self.device}')
+        self.division_factor = 2 ** len(params['encoder_channels'])
+        self.template_size = int(4200 * params['resize_factor'])
+        self.model = YNet(
+            obs_len=params['obs_len'], pred_len=params['pred_len'],
+            segmentation_model_fp=params['segmentation_model_fp'],
+            use_features_only=params['use_features_only'],
+            n_semantic_classes=params['n_semantic_classes'],
+            encoder_channels=params['encoder_channels'], decoder_channels=params['decoder_channels'],
+            n_waypoints=len(params['waypoints']), train_net=params['train_net'], position=params['position'],
+            network=params['network'], n_fusion=params['n_fusion'])
+        self.homo_mat = None
+
+    # ------------------------------------------------------------------------------------------ train
+    def train(self, df_train, df_val, train_image_path, val_image_path, experiment_name):
+        p = self.params
+        train_images, train_loader, self.homo_mat = self.prepare_data(
+            df_train, train_image_path, p['dataset_name'], 'train', p['obs_len'], p['pred_len'], p['resize_factor'],
+            p.get('use_raw_data', False), p.get('augment', False))
+        val_images, val_loader, _ = self.prepare_data(
+            df_val, val_image_path, p['dataset_name'], 'val', p['obs_len'], p['pred_len'], p['resize_factor'],
+            p.get('use_raw_data', False), False)
+        return self.train_prepared(train_images, train_loader, val_images, val_loader, experiment_name)
+
+    def train_prepared(self, train_images, train_loader, val_images, val_loader, experiment_name):
+        return self._train(train_images, train_loader, val_images, val_loader, experiment_name, **self.params)
+
+    def _train(self, train_images, train_loader, val_images, val_loader, experiment_name, ckpt_path, dataset_name,
+               resize_factor, obs_len, pred_len, batch_size, lr, n_epoch, waypoints, n_goal, n_traj, kernlen, nsig,
+               e_unfreeze, loss_scale, temperature, use_raw_data=False, save_every_n=10, train_net='all', position=[],
+               fine_tune=False, augment=False, ynet_bias=False, use_CWS=False, resl_thresh=0.002, CWS_params=None,
+               n_early_stop=5, steps=[20], lr_decay_ratio=0.1, network=None, swap_semantic=False, window_size=9,
+               smooth_val=False, **kwargs):
+        model = self.model.to(self.device)
+        apply_freeze_policy(model, train_net, position, network, ynet_bias)
+        optimizer = FusedAdam(model.parameters(), lr=lr)
+        if fine_tune:
+            print('LR Schedular because finetuning')
+            lr_scheduler = torch.optim.lr_scheduler.MultiStepLR(optimizer, milestones=steps, gamma=lr_decay_ratio)
+        print('The number of trainable parameters: {:d}'.format(
+            sum(param.numel() for param in model.parameters() if param.requires_grad)))
+        criterion = BCEWithLogitsLoss()
+        input_template = torch.Tensor(create_dist_mat(size=self.template_size)).to(self.device)
+        gt_template = torch.Tensor(create_gaussian_heatmap_template(
+            size=self.template_size, kernlen=kernlen, nsig=nsig, normalize=False)).to(self.device)
+
+        best_val_ADE, best_epoch = 99999999999999, 0
+        self.val_ADE, self.val_FDE = [], []
+        state_dicts = deque()
+        half_window_size = (window_size // 2) + 1
+        curr_model_dict = best_state_dict = None
+        print('Start training')
+        for e in tqdm(range(n_epoch), desc='Epoch'):
+            train_ADE, train_FDE, train_loss = train_epoch(
+                model, train_loader, train_images, optimizer, criterion, loss_scale, self.device, dataset_name,
+                self.homo_mat, gt_template, input_template, waypoints, e, obs_len, pred_len, batch_size, e_unfreeze,
+                resize_factor, network, swap_semantic)
+            # like the reference, validation skips TTST (trainer.py:229-235)
+            val_ADE, val_FDE, _, _ = evaluate(
+                model, val_loader, val_images, self.device, dataset_name, self.homo_mat, input_template, waypoints,
+                'val', n_goal, n_traj, obs_len, batch_size, resize_factor, temperature, False, use_CWS, resl_thresh,
+                CWS_params, network=network, swap_semantic=swap_semantic)
+            if fine_tune:
+                print(f'Epoch {e}: \tTrain (Top-1) ADE: {train_ADE:.2f} FDE: {train_FDE:.2f} \t\tVal (Top-k) ADE: '
+                      f'{val_ADE:.2f} FDE: {val_FDE:.2f}   lr={lr_scheduler.get_last_lr()[0]}')
+            else:
+                print(f'Epoch {e}: \tTrain (Top-1) ADE: {train_ADE:.2f} FDE: {train_FDE:.2f} \t\tVal (Top-k) ADE: '
+                      f'{val_ADE:.2f} FDE: {val_FDE:.2f}')
+            self.val_ADE.append(val_ADE)
+            self.val_FDE.append(val_FDE)
+            if fine_tune:
+                lr_scheduler.step()
+            if smooth_val:
+                print('Length: ', len(state_dicts))
+                if len(state_dicts) == half_window_size:
+                    curr_model_dict = state_dicts.popleft()
+                state_dicts.append(deepcopy(model.state_dict()))
+                val_ADE = best_val_ADE + 1 if e < window_size else sum(self.val_ADE[-window_size:]) / window_size
+            else:
+                curr_model_dict = deepcopy(model.state_dict())
+            if val_ADE < best_val_ADE:
+                best_val_ADE = val_ADE
+                best_epoch = e - half_window_size + 1 if smooth_val else e
+                best_state_dict = curr_model_dict
+                if not fine_tune:
+                    print(f'Best Epoch {e}: \nVal ADE: {val_ADE} \nVal FDE: {val_FDE}')
+                    pathlib.Path(ckpt_path).mkdir(parents=True, exist_ok=True)
+                    torch.save(model.state_dict(), f'{ckpt_path}/{experiment_name}_weights.pt')
+            if (e + 1) % save_every_n == 0:
+                pathlib.Path(ckpt_path).mkdir(parents=True, exist_ok=True)
+                self.save_params(f'{ckpt_path}/{experiment_name}__epoch_{e}.pt', train_net)
+            if fine_tune and (best_val_ADE < min(self.val_ADE[-n_early_stop:])):
+                print(f'Early stop at epoch {e}')
+                break
+        print(f'Best epoch at {best_epoch}')
+        if best_epoch != 0 and best_state_dict is not None:
+            model.load_state_dict(best_state_dict, strict=True)
+        pathlib.Path(ckpt_path).mkdir(parents=True, exist_ok=True)
+        self.save_params(f'{ckpt_path}/{experiment_name}.pt', train_net)
+        return self.val_ADE, self.val_FDE
+
+    # ------------------------------------------------------------------------------------------ test
+    def test(self, df_test, image_path, return_preds=False, return_samples=False):
+        p = self.params
+        test_images, test_loader, self.homo_mat = self.prepare_data(
+            df_test, image_path, p['dataset_name'], 'test', p['obs_len'], p['pred_len'], p['resize_factor'],
+            p.get('use_raw_data', False))
+        return self.test_prepared(test_images, test_loader, return_preds, return_samples)
+
+    def test_prepared(self, test_images, test_loader, return_preds=False, return_samples=False):
+        return self._test(test_images, test_loader, return_preds=return_preds, return_samples=return_samples,
+                          **self.params)
+
+    def _test(self, test_images, test_loader, dataset_name, resize_factor, batch_size, n_round, obs_len, pred_len,
+              waypoints, n_goal, n_traj, temperature, rel_threshold, use_TTST, use_CWS, CWS_params,
+              use_raw_data=False, return_preds=False, return_samples=False, network=None, swap_semantic=False,
+              **kwargs):
+        model = self.model.to(self.device)
+        input_template = torch.Tensor(create_dist_mat(size=self.template_size)).to(self.device)
+        self.eval_ADE, self.eval_FDE = [], []
+        list_metrics, list_trajs = [], []
+        print('TTST setting:', use_TTST)
+        print('Start testing')
+        for e in tqdm(range(n_round), desc='Round'):
+            test_ADE, test_FDE, df_metrics, trajs_dict = evaluate(
+                model, test_loader, test_images, self.device, dataset_name, self.homo_mat, input_template, waypoints,
+                'test', n_goal, n_traj, obs_len, batch_size, resize_factor, temperature, use_TTST, use_CWS,
+                rel_threshold, CWS_params, return_preds=return_preds, return_samples=return_samples, network=network,
+                swap_semantic=swap_semantic)
+            list_metrics.append(df_metrics)
+            list_trajs.append(trajs_dict)
+            print(f'Round {e}: \nTest ADE: {test_ADE} \nTest FDE: {test_FDE}')
+            self.eval_ADE.append(test_ADE)
+            self.eval_FDE.append(test_FDE)
+        avg_ade = sum(self.eval_ADE) / len(self.eval_ADE)
+        avg_fde = sum(self.eval_FDE) / len(self.eval_FDE)
+        print(f'\nAverage performance (by {n_round}): \nTest ADE: {avg_ade} \nTest FDE: {avg_fde}')
+        return avg_ade, avg_fde, list_metrics, list_trajs
+
+    def forward_test(self, df_test, image_path, set_input, noisy_std_frac):
+        raise NotImplementedError('forward_test (saliency tooling, trainer.py:354-516) is outside the B200 hot path')
+
+    # ------------------------------------------------------------------------------------------ data
+    def prepare_data(self, df, image_path, dataset_name, mode, obs_len, pred_len, resize_factor, use_raw_data,
+                     augment=False):
+        """trainer.py:518-584.  Image loading / cv2 resize+pad / segmentation preprocessing are host-side,
+        once per scene and outside the hot path: they are taken from the reference's own modules."""
+        try:
+            from utils.data_utils import augment_data, create_images_dict
+            from utils.image_utils import preprocess_image_for_segmentation, pad, resize
+        except Exception as e:  # pragma: no cover - needs the reference tree on sys.path
+            raise RuntimeError('prepare_data needs the reference\'s utils.data_utils / utils.image_utils (data '
+                               'pipeline is out of scope here); use train_prepared / test_prepared with ready '
+                               f'images + DataLoader instead ({e!r})')
+        dataset_name = dataset_name.lower()
+        names = {'sdd': 'reference.jpg', 'ind-dataset-v1.0': 'reference.png', 'eth': 'oracle.png'}
+        if dataset_name not in names:
+            raise ValueError(f'{dataset_name} dataset is not supported')
+        if dataset_name == 'eth':
+            raise NotImplementedError('ETH/UCY homography path is outside the B200 hot path')
+        if not augment:
+            images_dict = create_images_dict(df.sceneId.unique(), image_path=image_path,
+                                             image_file=names[dataset_name], use_raw_data=use_raw_data)
+            print('No data and images augmentation')
+        else:
+            df, images_dict = augment_data(df, image_path=image_path, image_file=names[dataset_name], seg_mask=False,
+                                           use_raw_data=use_raw_data)
+            print('Augmented data and images')
+        dataset = SceneDataset(df, resize=resize_factor, total_len=obs_len + pred_len)
+        dataloader = DataLoader(dataset, batch_size=1, collate_fn=scene_collate, shuffle=(mode == 'train'))
+        resize(images_dict, factor=resize_factor, seg_mask=False)
+        pad(images_dict, division_factor=self.division_factor)
+        preprocess_image_for_segmentation(images_dict, seg_mask=False)
+        return images_dict, dataloader, None
+
+    # ------------------------------------------------------------------------------------------ checkpoints
+    def load_params(self, path):
+        self.model.load_state_dict(torch.load(path, map_location=self.device), strict=False)
+        print(f'Loaded ynet model to {"GPU" if torch.device(self.device).type == "cuda" else "CPU"}')
+
+    def save_params(self, path, train_net):
+        if train_net == 'all' or train_net == 'train':
+            state_dict = {k: v for k, v in self.model.state_dict().items() if 'segmentation' not in k}
+        else:
+            state_dict = OrderedDict()
+            for name, param in self.model.named_parameters():
+                if param.requires_grad:
+                    state_dict[name] = param
+        torch.save(state_dict, path)
+
+    def load_separated_params(self, pretrained_path, tuned_path):
+        self.model.load_state_dict(torch.load(pretrained_path, map_location=self.device), strict=False)
+        self.model.load_state_dict(torch.load(tuned_path, map_location=self.device), strict=False)
+        print(f'Loaded ynet model to {"GPU" if torch.device(self.device).type == "cuda" else "CPU"}')

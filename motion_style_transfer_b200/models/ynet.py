@@ -1,0 +1,246 @@
+"""Drop-in ``YNet`` for the reference's models/ynet.py (Y-Net + MoSA / Y-Net-Mod).
+
+Same constructor, attributes, method set and -- module for module -- the same parameter names,
+shapes, creation order (hence identical default initialisation under a given seed) as
+/root/reference/models/ynet.py:474-600, so ``state_dict`` files are interchangeable.  The modules
+are parameter containers: all arithmetic is done by ``YNetEngine`` through libynet_b200.so.
+
+Supported on the hot path: ``network in {'original', 'fusion'}`` with plain convs or MoSA/LoRA
+convs (``train_net`` containing ``mosa``; ``position`` = stage ids or scene/motion/fusion).
+The serial/parallel adapter baselines, the ``embed`` network and the ``semantic`` adapter
+(ynet.py:15-131,154-167,513-519) are out of this round's scope and raise.
+"""
+import torch
+import torch.nn as nn
+
+from . import lora
+from .. import ops
+from ..engine import YNetEngine, ChannelCat
+from ..utils.softargmax import SoftArgmax2D
+
+
+def get_conv2d(train_net, l, position, kernel_size, in_channels, out_channels=None, rank=None, stride=1,
+               padding=None):
+    """Adapter factory (ynet.py:134-151): LoRA conv on adapted positions, plain conv elsewhere."""
+    out_channels = in_channels if out_channels is None else out_channels
+    padding = kernel_size // 2 if padding is None else padding
+    pos = [str(i) for i in (position or [])]
+    if 'mosa' in train_net and str(l) in pos:
+        assert rank != 0 and rank is not None
+        return lora.Conv2d(in_channels, out_channels, kernel_size=kernel_size, r=rank, stride=stride,
+                           padding=padding)
+    if 'Layer' in train_net and str(l) in pos:
+        raise NotImplementedError('AdapterLayer baselines (ynet.py:69-131) are outside the B200 hot path')
+    return nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding)
+
+
+def _mosa_rank(train_net):
+    if 'mosa' not in train_net:
+        return None
+    parts = train_net.split('_')
+    return int(parts[1]) if len(parts) > 1 else 1
+
+
+def _pool():
+    return nn.MaxPool2d(kernel_size=2, stride=2, padding=0, dilation=1, ceil_mode=False)
+
+
+def _double_conv_stage(train_net, l, position, cin, cout, rank):
+    return nn.Sequential(
+        _pool(),
+        get_conv2d(train_net, l, position, 3, cin, cout, rank), nn.ReLU(inplace=False),
+        get_conv2d(train_net, l, position, 3, cout, cout, rank), nn.ReLU(inplace=False))
+
+
+class YNetEncoder(nn.Module):
+    """ynet.py:170-215: stage 0 = conv+ReLU; stages 1..n-1 = pool, 2 x (conv+ReLU); last = pool."""
+
+    def __init__(self, in_channels, channels=(64, 128, 256, 512, 512), train_net=None, position=[]):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = channels
+        self.train_net = train_net
+        self.position = position
+        self.rank = _mosa_rank(train_net)
+        self.stages = nn.ModuleList()
+        self.stages.append(nn.Sequential(
+            get_conv2d(train_net, 0, position, 3, in_channels, channels[0], self.rank), nn.ReLU(inplace=False)))
+        for i in range(len(channels) - 1):
+            self.stages.append(_double_conv_stage(train_net, i + 1, position, channels[i], channels[i + 1], self.rank))
+        self.stages.append(nn.Sequential(_pool()))
+
+
+class YNetEncoderL(YNetEncoder):
+    pass
+
+
+class YNetEncoderB(YNetEncoder):
+    """ynet.py:237-283 without the serial/parallel adapter blocks (not on the hot path)."""
+
+    def __init__(self, in_channels, channels=(64, 128, 256, 512, 512), train_net=None, position=[]):
+        if 'serial' in train_net or 'parallel' in train_net:
+            raise NotImplementedError('serial/parallel adapter baselines are outside the B200 hot path')
+        pos = []
+        for i in position:
+            try:
+                pos.append(int(i))
+            except (TypeError, ValueError):
+                pos.append(i)
+        super().__init__(in_channels, channels, train_net, pos)
+
+
+class YNetEncoderFusion(nn.Module):
+    """Y-Net-Mod encoder (ynet.py:286-395): separate scene / motion branches, then fusion stages."""
+
+    def __init__(self, scene_channel, motion_channel, channels, train_net=None, position=[], n_fusion=2):
+        super().__init__()
+        self.scene_channel = scene_channel
+        self.motion_channel = motion_channel
+        self.channels = channels
+        self.train_net = train_net
+        self.position = position
+        self.rank = _mosa_rank(train_net)
+        assert not any([i % 2 for i in channels]), f'Odd value in channels={channels}'
+        assert n_fusion <= len(channels) - 1, 'The number of fusion exceeds the total number of layer in encoder'
+        r = self.rank
+        self.scene_stages = nn.ModuleList([nn.Sequential(
+            get_conv2d(train_net, 'scene', position, 3, scene_channel, channels[0] // 2, r), nn.ReLU(inplace=False))])
+        self.motion_stages = nn.ModuleList([nn.Sequential(
+            get_conv2d(train_net, 'motion', position, 3, motion_channel, channels[0] // 2, r), nn.ReLU(inplace=False))])
+        self.fusion_stages = nn.ModuleList()
+        n_sep = len(channels) - n_fusion - 1
+        for i in range(n_sep):
+            self.scene_stages.append(
+                _double_conv_stage(train_net, 'scene', position, channels[i] // 2, channels[i + 1] // 2, r))
+        for i in range(n_sep):
+            self.motion_stages.append(
+                _double_conv_stage(train_net, 'motion', position, channels[i] // 2, channels[i + 1] // 2, r))
+        for i in range(n_sep, len(channels) - 1):
+            self.fusion_stages.append(
+                _double_conv_stage(train_net, 'fusion', position, channels[i], channels[i + 1], r))
+        self.fusion_stages.append(nn.Sequential(_pool()))
+
+
+class YNetDecoder(nn.Module):
+    """ynet.py:398-451: center (2 convs), 5 x [bilinear x2, upsample_conv, cat skip, 2 convs], 1x1 predictor."""
+
+    def __init__(self, encoder_channels, decoder_channels, output_len, traj=False):
+        super().__init__()
+        if traj:
+            encoder_channels = [c + traj for c in encoder_channels]
+        encoder_channels = encoder_channels[::-1]
+        center = encoder_channels[0]
+
+        def c3(i, o):
+            return nn.Conv2d(i, o, kernel_size=(3, 3), stride=(1, 1), padding=(1, 1))
+
+        self.center = nn.Sequential(c3(center, center * 2), nn.ReLU(inplace=False),
+                                    c3(center * 2, center * 2), nn.ReLU(inplace=False))
+        up_in = [center * 2] + decoder_channels[:-1]
+        up_out = [c // 2 for c in up_in]
+        self.upsample_conv = nn.ModuleList([c3(i, o) for i, o in zip(up_in, up_out)])
+        dec_in = [e + d for e, d in zip(encoder_channels, up_out)]
+        self.decoder = nn.ModuleList([
+            nn.Sequential(c3(i, o), nn.ReLU(inplace=False), c3(o, o), nn.ReLU(inplace=False))
+            for i, o in zip(dec_in, decoder_channels)])
+        self.predictor = nn.Conv2d(in_channels=decoder_channels[-1], out_channels=output_len, kernel_size=1,
+                                   stride=1, padding=0)
+
+
+class YNet(nn.Module):
+    def __init__(self, obs_len, pred_len, segmentation_model_fp, use_features_only=False, n_semantic_classes=6,
+                 encoder_channels=[], decoder_channels=[], n_waypoints=1, train_net=None, position=[],
+                 network=None, n_fusion=None):
+        super().__init__()
+        self.train_net = train_net
+        if segmentation_model_fp is not None:
+            # third-party pickled smp U-Net, runs once per scene (ynet.py:495-507): kept as a torch module
+            map_location = None if torch.cuda.is_available() else torch.device('cpu')
+            self.semantic_segmentation = torch.load(segmentation_model_fp, map_location=map_location,
+                                                    weights_only=False)
+            if use_features_only:
+                self.semantic_segmentation.segmentation_head = nn.Identity()
+                n_semantic_classes = 16
+        else:
+            self.semantic_segmentation = nn.Identity()
+        self.feature_channels = n_semantic_classes + obs_len
+        self.network = network
+        if 'semantic' in train_net:
+            raise NotImplementedError('semantic adapter (ynet.py:513-519) is outside the B200 hot path')
+        if network == 'fusion':
+            assert n_fusion is not None
+            self.encoder = YNetEncoderFusion(n_semantic_classes, obs_len, encoder_channels, train_net=train_net,
+                                             position=position, n_fusion=n_fusion)
+        elif network == 'original':
+            if 'mosa' in train_net or 'Layer' in train_net:
+                self.encoder = YNetEncoderL(self.feature_channels, encoder_channels, train_net, position)
+            else:
+                self.encoder = YNetEncoderB(self.feature_channels, encoder_channels, train_net, position)
+        elif network == 'embed':
+            raise NotImplementedError("network='embed' (ynet.py:154-167) is outside the B200 hot path")
+        else:
+            raise ValueError('No network parameter is provided')
+        self.goal_decoder = YNetDecoder(encoder_channels, decoder_channels, output_len=pred_len)
+        self.traj_decoder = YNetDecoder(encoder_channels, decoder_channels, output_len=pred_len, traj=n_waypoints)
+        self.softargmax_ = SoftArgmax2D(normalized_coordinates=False)
+        self.encoder_channels = encoder_channels
+        self._engine = None
+
+    # ---- engine plumbing -------------------------------------------------------------------------
+    @property
+    def engine(self):
+        if self._engine is None:
+            object.__setattr__(self, '_engine', YNetEngine(self))
+        return self._engine
+
+    def _training_graph(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    # ---- reference method set (ynet.py:551-600) ---------------------------------------------------
+    def segmentation(self, image):
+        return self.semantic_segmentation(image)
+
+    def adapt_semantic(self, semantic_img):
+        return semantic_img
+
+    def pred_features(self, scene_map, motion_map):
+        if self._training_graph():
+            from .. import autograd_engine
+            return autograd_engine.pred_features(self, scene_map, motion_map)
+        return self.engine.pred_features(scene_map, motion_map)
+
+    def pred_goal(self, features):
+        if self._training_graph():
+            from .. import autograd_engine
+            return autograd_engine.decoder_logits(self, self.goal_decoder, 'goal_decoder', features)
+        return self.engine.decoder_logits(self.goal_decoder, 'goal_decoder', features)
+
+    def pred_traj(self, features):
+        if self._training_graph():
+            from .. import autograd_engine
+            return autograd_engine.decoder_logits(self, self.traj_decoder, 'traj_decoder', features)
+        return self.engine.decoder_logits(self.traj_decoder, 'traj_decoder', features)
+
+    def pred_traj_softargmax(self, features):
+        """pred_traj followed by softargmax (evaluate.py:263-264) without materialising the logits."""
+        return self.engine.decoder_softargmax(self.traj_decoder, 'traj_decoder', features)
+
+    def softmax(self, x):
+        return ops.spatial_softmax(x)
+
+    def softargmax(self, output):
+        return self.softargmax_(output)
+
+    def sigmoid(self, output):
+        B, C = output.shape[:2]
+        return ops.sigmoid_select(output, list(range(C)), 1.0)
+
+    def softargmax_on_softmax_map(self, x):
+        return ops.expectation2d(x)
+
+    def forward(self, *a, **k):  # the reference defines no forward either
+        raise NotImplementedError('use pred_features / pred_goal / pred_traj')
+
+
+__all__ = ['YNet', 'YNetEncoder', 'YNetEncoderL', 'YNetEncoderB', 'YNetEncoderFusion', 'YNetDecoder',
+           'get_conv2d', 'ChannelCat']

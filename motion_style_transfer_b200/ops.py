@@ -1,0 +1,536 @@
+"""torch-tensor front end of the C ABI (include/ynet_b200.h).
+
+torch is plumbing only: it owns device memory and the stream; every computation below is a call
+into libynet_b200.so with raw pointers.  Nothing here runs on the CPU -- CPU tensors are rejected.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvSrc, SRC_DIRECT, SRC_POOL2, SRC_UP2, check  # noqa: F401
+
+
+def _L():
+    return _lib.load()
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _req(t, dtype=torch.float32, name='tensor'):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f'{name}: expected a torch.Tensor, got {type(t)}')
+    if not t.is_cuda:
+        raise RuntimeError(f'{name}: motion_style_transfer_b200 runs on CUDA only (no CPU fallback); got {t.device}')
+    if t.dtype != dtype:
+        raise TypeError(f'{name}: expected dtype {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        t = t.contiguous()
+    return t
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device, tag):
+    """Caller-owned scratch, grown on demand and reused per (device, tag)."""
+    key = (device, tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+launch_count = 0      # kernels-launching C calls issued (bench.py reports it)
+_profile = None       # list of per-launch records while profile_begin() is active
+
+
+def profile_begin():
+    global _profile
+    _profile = []
+
+
+def profile_end():
+    """Per-launch device times (CUDA events on the launching stream) with algorithmic flops / bytes."""
+    global _profile
+    rec, _profile = _profile, None
+    torch.cuda.synchronize()
+    out = []
+    for r in rec or []:
+        out.append(dict(kernel=r['kernel'], tag=r['tag'], ms=r['e0'].elapsed_time(r['e1']), flops=r['flops'],
+                        bytes=r['bytes']))
+    return out
+
+
+class _timed:
+    def __init__(self, kernel, flops=0.0, nbytes=0.0, tag=''):
+        self.kernel, self.flops, self.nbytes, self.tag = kernel, float(flops), float(nbytes), tag
+
+    def __enter__(self):
+        if _profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _profile is not None and exc[0] is None:
+            self.e1.record()
+            _profile.append(dict(kernel=self.kernel, tag=self.tag, e0=self.e0, e1=self.e1, flops=self.flops,
+                                 bytes=self.nbytes))
+        return False
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+# ------------------------------------------------------------------------------------------------ a1/a3/a9
+def create_dist_template(size, device):
+    out = torch.empty(size, size, dtype=torch.float32, device=device)
+    check(_L().ynet_create_dist_template(size, _ptr(out), _stream()), 'create_dist_template')
+    _count()
+    return out
+
+
+def rasterize_patches(template, coords, H, W, check_bounds=False):
+    """get_patch + stack: template (th, tw) f32, coords (n, 2) f32 (x, y) -> (n, H, W)."""
+    template = _req(template, name='template')
+    coords = _req(coords.reshape(-1, 2), name='coords')
+    n = coords.shape[0]
+    out = torch.empty(n, H, W, dtype=torch.float32, device=template.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=template.device) if check_bounds else None
+    with _timed('rasterize_gather_kernel', 0, 4.0 * n * H * W):
+        check(_L().ynet_rasterize_patches(_ptr(template), template.shape[0], template.shape[1], _ptr(coords), n,
+                                          _ptr(out), H, W, _ptr(flag), _stream()), 'rasterize_patches')
+    _count()
+    if check_bounds and int(flag.item()):
+        raise ValueError('get_patch: window leaves the template (coordinate outside the image)')
+    return out
+
+
+def rasterize_dist_analytic(template_size, coords, H, W):
+    coords = _req(coords.reshape(-1, 2), name='coords')
+    n = coords.shape[0]
+    out = torch.empty(n, H, W, dtype=torch.float32, device=coords.device)
+    check(_L().ynet_rasterize_dist_analytic(template_size, _ptr(coords), n, _ptr(out), H, W, _stream()),
+          'rasterize_dist_analytic')
+    _count()
+    return out
+
+
+def avgpool_pyramid(maps, n_levels):
+    """maps (B, C, H, W) -> [maps, AvgPool2d(2)(maps), ..., AvgPool2d(2^(n_levels-1))(maps)]."""
+    maps = _req(maps, name='maps')
+    B, C, H, W = maps.shape
+    outs = [torch.empty(B, C, H >> i, W >> i, dtype=torch.float32, device=maps.device) for i in range(1, n_levels)]
+    arr = (ctypes.c_void_p * max(1, len(outs)))(*[o.data_ptr() for o in outs])
+    if n_levels >= 2:
+        with _timed('avgpool_pyramid_kernel', 0, 4.0 * B * C * H * W * 4 / 3):
+            check(_L().ynet_avgpool_pyramid(_ptr(maps), B * C, H, W, n_levels, arr, _stream()), 'avgpool_pyramid')
+        _count()
+    return [maps] + outs
+
+
+# ------------------------------------------------------------------------------------------------ a10/a12/a13
+def softargmax2d(x, channel=None):
+    """(B, C, H, W) -> (B, C, 2); with `channel` only that channel of every image -> (B, 1, 2)."""
+    x = _req(x, name='input')
+    B, C, H, W = x.shape
+    if channel is None:
+        rows, stride, base, oc = B * C, H * W, x.data_ptr(), C
+    else:
+        rows, stride, base, oc = B, C * H * W, x.data_ptr() + (int(channel) % C) * H * W * 4, 1
+    out = torch.empty(B, oc, 2, dtype=torch.float32, device=x.device)
+    nb = _L().ynet_softargmax2d_workspace_bytes(rows, H, W)
+    ws = _workspace(nb, x.device, 'softargmax')
+    with _timed('softargmax_partial_kernel', 0, 4.0 * rows * H * W):
+        check(_L().ynet_softargmax2d(ctypes.c_void_p(base), rows, stride, H, W, _ptr(out), _ptr(ws), ws.numel(),
+                                     _stream()), 'softargmax2d')
+    _count(2)
+    return out
+
+
+def spatial_softmax(x):
+    x = _req(x, name='input')
+    B, C, H, W = x.shape
+    out = torch.empty_like(x)
+    check(_L().ynet_spatial_softmax(_ptr(x), B * C, H * W, _ptr(out), _stream()), 'spatial_softmax')
+    _count()
+    return out
+
+
+def expectation2d(p):
+    p = _req(p, name='input')
+    B, C, H, W = p.shape
+    out = torch.empty(B, C, 2, dtype=torch.float32, device=p.device)
+    check(_L().ynet_expectation2d(_ptr(p), B * C, H, W, _ptr(out), _stream()), 'expectation2d')
+    _count()
+    return out
+
+
+def sigmoid_select(logits, channels, temperature):
+    logits = _req(logits, name='logits')
+    B, C, H, W = logits.shape
+    ch = (ctypes.c_int32 * len(channels))(*[int(c) % C for c in channels])
+    out = torch.empty(B, len(channels), H, W, dtype=torch.float32, device=logits.device)
+    with _timed('sigmoid_select_kernel', 0, 8.0 * B * len(channels) * H * W):
+        check(_L().ynet_sigmoid_select(_ptr(logits), B, C, H * W, ch, len(channels), float(temperature), _ptr(out),
+                                       _stream()), 'sigmoid_select')
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ a11
+def _prepare(p2d, rel_threshold):
+    rows, S = p2d.shape
+    rowmax = torch.empty(rows, dtype=torch.float32, device=p2d.device)
+    gsum = torch.empty(1, dtype=torch.float32, device=p2d.device)
+    nb = _L().ynet_sampling_prepare_workspace_bytes(rows, S)
+    ws = _workspace(nb, p2d.device, 'sampling_prepare')
+    check(_L().ynet_sampling_prepare(_ptr(p2d), rows, S, float(rel_threshold), _ptr(rowmax), _ptr(gsum), _ptr(ws),
+                                     ws.numel(), _stream()), 'sampling_prepare')
+    _count(3)
+    return rowmax, gsum
+
+
+def multinomial_replacement(prob_map, uniforms, rel_threshold=None):
+    """prob_map (B, C, H, W) f32, uniforms (B*C, n) f64 -> idx (B*C, n) int64, xy (B, C, n, 2) f32."""
+    prob_map = _req(prob_map, name='probability_map')
+    B, C, H, W = prob_map.shape
+    rows, S = B * C, H * W
+    p2d = prob_map.view(rows, S)
+    uniforms = _req(uniforms, torch.float64, 'uniforms').view(rows, -1)
+    n = uniforms.shape[1]
+    rowmax = gsum = None
+    if rel_threshold is not None:
+        rowmax, gsum = _prepare(p2d, rel_threshold)
+    cdf = _workspace(rows * S * 4, prob_map.device, 'cdf')
+    idx = torch.empty(rows, n, dtype=torch.int64, device=prob_map.device)
+    xy = torch.empty(B, C, n, 2, dtype=torch.float32, device=prob_map.device)
+    with _timed('cdf_sequential_kernel+cdf_search_kernel', 0, 4.0 * rows * S + 8.0 * rows * n):
+        check(_L().ynet_multinomial_replacement(_ptr(p2d), rows, S,
+                                                -1.0 if rel_threshold is None else float(rel_threshold),
+                                                _ptr(rowmax), _ptr(gsum), _ptr(uniforms), n, _ptr(cdf), _ptr(idx),
+                                                _ptr(xy), W, _stream()), 'multinomial_replacement')
+    _count(2)
+    return idx, xy
+
+
+def multinomial_topk(prob_map, expo, n, rel_threshold=None):
+    """replacement=False (or n == 1): top-n of p / q.  expo (B*C, H*W) f32 ~ Exp(1)."""
+    prob_map = _req(prob_map, name='probability_map')
+    B, C, H, W = prob_map.shape
+    rows, S = B * C, H * W
+    p2d = prob_map.view(rows, S)
+    expo = _req(expo, name='exponentials').view(rows, S)
+    rowmax = gsum = None
+    if rel_threshold is not None:
+        rowmax, gsum = _prepare(p2d, rel_threshold)
+    idx = torch.empty(rows, n, dtype=torch.int64, device=prob_map.device)
+    xy = torch.empty(B, C, n, 2, dtype=torch.float32, device=prob_map.device)
+    check(_L().ynet_multinomial_topk(_ptr(p2d), _ptr(expo), rows, S, -1.0 if rel_threshold is None else float(rel_threshold),
+                                     _ptr(rowmax), _ptr(gsum), n, _ptr(idx), _ptr(xy), W, _stream()),
+          'multinomial_topk')
+    _count()
+    return idx, xy
+
+
+def rng_uniform_f64(seed, offset, n, device):
+    out = torch.empty(n, dtype=torch.float64, device=device)
+    check(_L().ynet_rng_uniform_f64(seed, offset, n, _ptr(out), _stream()), 'rng_uniform_f64')
+    _count()
+    return out
+
+
+def rng_exponential_f32(seed, offset, n, device):
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    check(_L().ynet_rng_exponential_f32(seed, offset, n, _ptr(out), _stream()), 'rng_exponential_f32')
+    _count()
+    return out
+
+
+def rng_choice(seed, offset, rows, N, K, device):
+    out = torch.empty(rows, K, dtype=torch.int32, device=device)
+    check(_L().ynet_rng_choice(seed, offset, rows, N, K, _ptr(out), _stream()), 'rng_choice')
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ a14
+def kmeans_batched(X, init_idx, reseed_idx=None, tol=1e-4, iter_limit=0, want_assign=False):
+    """X (B, N, 2) f32, init_idx (B, K) int32 -> centres (B, K, 2), assign (B, N)|None, iters (B), status (B)."""
+    X = _req(X, name='X')
+    B, N, D = X.shape
+    if D != 2:
+        raise NotImplementedError('kmeans_batched: only 2-D points (pixel coordinates) are supported')
+    init_idx = _req(init_idx, torch.int32, 'init_idx')
+    K = init_idx.shape[1]
+    R = 0
+    if reseed_idx is not None:
+        reseed_idx = _req(reseed_idx, torch.int32, 'reseed_idx')
+        R = reseed_idx.shape[1]
+    centres = torch.empty(B, K, 2, dtype=torch.float32, device=X.device)
+    assign = torch.empty(B, N, dtype=torch.int32, device=X.device) if want_assign else None
+    iters = torch.empty(B, dtype=torch.int32, device=X.device)
+    status = torch.empty(B, dtype=torch.int32, device=X.device)
+    with _timed('kmeans_kernel', 0, 8.0 * B * N):
+        check(_L().ynet_kmeans_batched(_ptr(X), B, N, K, _ptr(init_idx), _ptr(reseed_idx), R, float(tol),
+                                       int(iter_limit), _ptr(centres), _ptr(assign), _ptr(iters), _ptr(status),
+                                       _stream()), 'kmeans_batched')
+    _count()
+    return centres, assign, iters, status
+
+
+# ------------------------------------------------------------------------------------------------ a16/a17
+def cws_waypoint(sig, wp_in, last_obs, length_ratio, sigma_factor, ratio, rot):
+    """sig (B, H, W); wp_in (G, B, 2); last_obs (B, 2); sigma_factor (G,) -> (G, B, 2)."""
+    sig = _req(sig, name='sig')
+    B, H, W = sig.shape
+    wp_in = _req(wp_in, name='wp_in')
+    G = wp_in.shape[0]
+    last_obs = _req(last_obs, name='last_obs')
+    sigma_factor = _req(sigma_factor, name='sigma_factor')
+    out = torch.empty(G, B, 2, dtype=torch.float32, device=sig.device)
+    for g0 in range(0, G, 32):
+        g1 = min(G, g0 + 32)
+        check(_L().ynet_cws_waypoint(_ptr(sig), B, H, W, _ptr(wp_in[g0:g1]), g1 - g0, _ptr(last_obs),
+                                     float(length_ratio), _ptr(sigma_factor[g0:g1]), float(ratio), int(bool(rot)),
+                                     _ptr(out[g0:g1]), _stream()), 'cws_waypoint')
+        _count(2)
+    return out
+
+
+def cws_waypoint_map(sig, wp_in_g, last_obs, length_ratio, sigma_factor, ratio, rot):
+    sig = _req(sig, name='sig')
+    B, H, W = sig.shape
+    out = torch.empty(B, H, W, dtype=torch.float32, device=sig.device)
+    check(_L().ynet_cws_waypoint_map(_ptr(sig), B, H, W, _ptr(_req(wp_in_g, name='wp_in_g')),
+                                     _ptr(_req(last_obs, name='last_obs')), float(length_ratio), float(sigma_factor),
+                                     float(ratio), int(bool(rot)), _ptr(out), _stream()), 'cws_waypoint_map')
+    _count()
+    return out
+
+
+def ade_fde(gt_future, trajs, wps, resize_factor):
+    gt_future = _req(gt_future, name='gt_future')
+    trajs = _req(trajs, name='trajs')
+    wps = _req(wps, name='waypoints')
+    K, B, T, _ = trajs.shape
+    n_wp = wps.shape[2]
+    ade = torch.empty(B, dtype=torch.float32, device=trajs.device)
+    fde = torch.empty(B, dtype=torch.float32, device=trajs.device)
+    check(_L().ynet_ade_fde(_ptr(gt_future), _ptr(trajs), _ptr(wps), K, B, T, n_wp, float(resize_factor), _ptr(ade),
+                            _ptr(fde), _stream()), 'ade_fde')
+    _count()
+    return ade, fde
+
+
+# ------------------------------------------------------------------------------------------------ a4-a8 fp32 engine
+def lora_fold(weight, lora_A=None, lora_B=None, packed=True):
+    """W + (B @ A).view(W.shape) / r  ->  OIHW (packed=False) or [C_in][k*k][C_out] (packed=True)."""
+    weight = _req(weight, name='weight')
+    C_out, C_in, k, _ = weight.shape
+    rank = 0
+    if lora_A is not None:
+        lora_A = _req(lora_A, name='lora_A')
+        lora_B = _req(lora_B, name='lora_B')
+        rank = lora_A.shape[0] // k
+    out = torch.empty(C_in * k * k * C_out, dtype=torch.float32, device=weight.device)
+    check(_L().ynet_lora_fold(_ptr(weight), _ptr(lora_A), _ptr(lora_B), C_out, C_in, k, rank, 1 if packed else 0,
+                              _ptr(out), _stream()), 'lora_fold')
+    _count()
+    return out.view(C_in, k * k, C_out) if packed else out.view(C_out, C_in, k, k)
+
+
+def conv3x3_f32(sources, weight_packed, bias, relu, N, H, W):
+    """sources: list of (tensor NCHW f32, mode); weight_packed [C_in][9][C_out]; -> (N, C_out, H, W).
+
+    A source whose batch is 1 is broadcast; a source whose batch B divides N is read as n % B
+    (features shared by stacked goal passes)."""
+    C_out = weight_packed.shape[2]
+    arr = (ConvSrc * len(sources))()
+    keep = []
+    cin = 0
+    for i, (t, mode) in enumerate(sources):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise RuntimeError('conv3x3_f32: sources must be float32 CUDA tensors')
+        if t.dim() != 4:
+            raise ValueError('conv3x3_f32: sources must be 4-D')
+        bs = t.stride(0)
+        if t.shape[0] == 1 and N > 1:
+            bs = 0                                   # broadcast over the batch (Tensor.expand)
+        if not t[0].is_contiguous():
+            t = t.contiguous()
+            bs = 0 if (t.shape[0] == 1 and N > 1) else t.stride(0)
+        keep.append(t)
+        arr[i].ptr = t.data_ptr()
+        arr[i].channels = t.shape[1]
+        arr[i].mode = mode
+        arr[i].batch_stride = bs
+        arr[i].batch_mod = t.shape[0] if (1 < t.shape[0] < N and N % t.shape[0] == 0 and bs != 0) else 0
+        if 1 < t.shape[0] < N and arr[i].batch_mod == 0:
+            raise ValueError(f'conv3x3_f32: source batch {t.shape[0]} does not divide N={N}')
+        cin += t.shape[1]
+    if cin != weight_packed.shape[0]:
+        raise ValueError(f'conv3x3_f32: sources give {cin} channels, weight expects {weight_packed.shape[0]}')
+    out = torch.empty(N, C_out, H, W, dtype=torch.float32, device=weight_packed.device)
+    co_blocks = (C_out + 31) // 32
+    per = max(1, 65535 // co_blocks)
+    for n0 in range(0, N, per):
+        nn = min(per, N - n0)
+        if n0:
+            for i, t in enumerate(keep):
+                if arr[i].batch_mod:
+                    raise ValueError('conv3x3_f32: modulo-batched sources need N * ceil(C_out/32) <= 65535')
+                arr[i].ptr = t.data_ptr() + n0 * arr[i].batch_stride * 4
+        with _timed('conv3x3_f32_kernel', 2.0 * 9 * cin * C_out * H * W * nn, 4.0 * (cin + C_out) * H * W * nn,
+                    tag=f'{cin}->{C_out}@{H}x{W} N={nn}'):
+            check(_L().ynet_conv3x3_f32(arr, len(sources), nn, H, W, _ptr(weight_packed), _ptr(bias), C_out,
+                                        1 if relu else 0, _ptr(out[n0:]), _stream()), 'conv3x3_f32')
+        _count()
+    return out
+
+
+def conv1x1_f32(x, weight, bias):
+    x = _req(x, name='x')
+    N, C_in, H, W = x.shape
+    weight = _req(weight, name='weight')
+    C_out = weight.shape[0]
+    out = torch.empty(N, C_out, H, W, dtype=torch.float32, device=x.device)
+    with _timed('conv1x1_f32_kernel', 2.0 * C_in * C_out * H * W * N, 4.0 * (C_in + C_out) * H * W * N):
+        check(_L().ynet_conv1x1_f32(_ptr(x), N, C_in, H * W, _ptr(weight), _ptr(bias), C_out, _ptr(out), _stream()),
+              'conv1x1_f32')
+    _count()
+    return out
+
+
+def predictor_softargmax_f32(x, weight, bias):
+    """1x1 predictor + SoftArgmax2D fused: x (N, C_in, H, W) -> (N, C_out, 2)."""
+    x = _req(x, name='x')
+    N, C_in, H, W = x.shape
+    weight = _req(weight, name='weight')
+    C_out = weight.shape[0]
+    out = torch.empty(N, C_out, 2, dtype=torch.float32, device=x.device)
+    nb = _L().ynet_predictor_softargmax_workspace_bytes(N, C_out, H, W)
+    ws = _workspace(nb, x.device, 'pred_softargmax')
+    with _timed('predictor_softargmax_kernel', 0, 4.0 * C_in * H * W * N):
+        check(_L().ynet_predictor_softargmax_f32(_ptr(x), N, C_in, H, W, _ptr(weight), _ptr(bias), C_out, _ptr(out),
+                                                 _ptr(ws), ws.numel(), _stream()), 'predictor_softargmax_f32')
+    _count(2)
+    return out
+
+
+def maxpool2x2(x):
+    x = _req(x, name='x')
+    N, C, H, W = x.shape
+    out = torch.empty(N, C, H // 2, W // 2, dtype=torch.float32, device=x.device)
+    check(_L().ynet_maxpool2x2_f32(_ptr(x), N * C, H, W, _ptr(out), _stream()), 'maxpool2x2')
+    _count()
+    return out
+
+
+def upsample_bilinear2x(x):
+    x = _req(x, name='x')
+    N, C, H, W = x.shape
+    out = torch.empty(N, C, 2 * H, 2 * W, dtype=torch.float32, device=x.device)
+    check(_L().ynet_upsample_bilinear2x_f32(_ptr(x), N * C, H, W, _ptr(out), _stream()), 'upsample_bilinear2x')
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ a18 training pieces
+def bce_logits_fwd_bwd(logits, target, grad_scale, want_grad=True):
+    logits = _req(logits, name='logits')
+    target = _req(target, name='target')
+    n = logits.numel()
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    grad = torch.empty_like(logits) if want_grad else None
+    ws = _workspace(_L().ynet_bce_workspace_bytes(n), logits.device, 'bce')
+    check(_L().ynet_bce_logits_fwd_bwd(_ptr(logits), _ptr(target), n, float(grad_scale), _ptr(loss), _ptr(grad),
+                                       _ptr(ws), ws.numel(), _stream()), 'bce_logits_fwd_bwd')
+    _count(2)
+    return loss, grad
+
+
+def conv3x3_dgrad_f32(dy, relu_out, weight_oihw):
+    dy = _req(dy, name='dy')
+    N, C_out, H, W = dy.shape
+    weight_oihw = _req(weight_oihw, name='weight')
+    C_in = weight_oihw.shape[1]
+    if relu_out is not None:
+        relu_out = _req(relu_out, name='relu_out')
+    dx = torch.empty(N, C_in, H, W, dtype=torch.float32, device=dy.device)
+    check(_L().ynet_conv3x3_dgrad_f32(_ptr(dy), _ptr(relu_out), N, H, W, _ptr(weight_oihw), C_out, C_in, _ptr(dx),
+                                      _stream()), 'conv3x3_dgrad_f32')
+    _count(3)
+    return dx
+
+
+def conv3x3_wgrad_f32(x, dy, relu_out, want_bias=True):
+    x = _req(x, name='x')
+    dy = _req(dy, name='dy')
+    N, C_in, H, W = x.shape
+    C_out = dy.shape[1]
+    if relu_out is not None:
+        relu_out = _req(relu_out, name='relu_out')
+    dW = torch.empty(C_out, C_in, 3, 3, dtype=torch.float32, device=x.device)
+    db = torch.empty(C_out, dtype=torch.float32, device=x.device) if want_bias else None
+    nb = _L().ynet_conv3x3_wgrad_workspace_bytes(N, H, W, C_out, C_in)
+    ws = _workspace(nb, x.device, 'wgrad')
+    check(_L().ynet_conv3x3_wgrad_f32(_ptr(x), _ptr(dy), _ptr(relu_out), N, H, W, C_in, C_out, _ptr(dW), _ptr(db),
+                                      _ptr(ws), ws.numel(), _stream()), 'conv3x3_wgrad_f32')
+    _count(3)
+    return dW, db
+
+
+def maxpool2x2_bwd(x, dy):
+    x = _req(x, name='x')
+    dy = _req(dy, name='dy')
+    N, C, H, W = x.shape
+    dx = torch.empty_like(x)
+    check(_L().ynet_maxpool2x2_bwd_f32(_ptr(x), _ptr(dy), N * C, H, W, _ptr(dx), _stream()), 'maxpool2x2_bwd')
+    _count()
+    return dx
+
+
+def upsample_bilinear2x_bwd(dy):
+    dy = _req(dy, name='dy')
+    N, C, OH, OW = dy.shape
+    dx = torch.empty(N, C, OH // 2, OW // 2, dtype=torch.float32, device=dy.device)
+    check(_L().ynet_upsample_bilinear2x_bwd_f32(_ptr(dy), N * C, OH // 2, OW // 2, _ptr(dx), _stream()),
+          'upsample_bilinear2x_bwd')
+    _count()
+    return dx
+
+
+def lora_grad(dW, lora_A, lora_B):
+    dW = _req(dW, name='dW')
+    C_out, C_in, k, _ = dW.shape
+    lora_A = _req(lora_A, name='lora_A')
+    lora_B = _req(lora_B, name='lora_B')
+    rank = lora_A.shape[0] // k
+    dA = torch.empty_like(lora_A)
+    dB = torch.empty_like(lora_B)
+    check(_L().ynet_lora_grad(_ptr(dW), _ptr(lora_A), _ptr(lora_B), C_out, C_in, k, rank, _ptr(dA), _ptr(dB),
+                              _stream()), 'lora_grad')
+    _count()
+    return dA, dB
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    for t, nme in ((param, 'param'), (grad, 'grad'), (exp_avg, 'exp_avg'), (exp_avg_sq, 'exp_avg_sq')):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise RuntimeError(f'adam_step: {nme} must be a contiguous float32 CUDA tensor')
+    check(_L().ynet_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), int(step),
+                              float(lr), float(beta1), float(beta2), float(eps), float(grad_scale), _stream()),
+          'adam_step')
+    _count()

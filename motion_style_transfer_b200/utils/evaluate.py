@@ -1,0 +1,207 @@
+"""Drop-in for the reference's utils/evaluate.py: TTST / CWS evaluation, device-resident.
+
+``evaluate(...)`` keeps the 23-argument signature and return value of evaluate.py:37-315.  The body of
+its batch loop lives in ``forecast_batch`` (also what bench.py times): coordinates never leave the
+GPU (the reference round-trips them through numpy at evaluate.py:112,251), the per-agent k-means
+loop (147-155) and the per-(goal, agent) CWS loop (172-224) are single batched kernels, and the
+n_goal trajectory-decoder passes (249-266) are stacked along the batch axis.
+"""
+import numpy as np
+import pandas as pd
+import torch
+
+from .. import ops
+from ..engine import ChannelCat
+from .image_utils import HostRng, sampling
+from .kmeans import kmeans_batched
+
+TTST_SAMPLES = 10000          # evaluate.py:138
+MAX_STACKED_PASSES = 256      # agent x goal decoder passes per launch (bounds activation memory)
+
+
+def torch_multivariate_gaussian_heatmap(coordinates, H, W, dist, sigma_factor, ratio, device, rot=False):
+    """evaluate.py:9-34 for ONE (goal, agent): normalised oriented Gaussian (H, W).
+
+    The batched path (``ops.cws_waypoint``) never materialises this map; this entry point exists for
+    API parity and tests.  Implemented with the device kernel on an all-ones sigmoid map.
+    """
+    coordinates = torch.as_tensor(coordinates, dtype=torch.float32, device=device).reshape(1, 2)
+    dist = torch.as_tensor(dist, dtype=torch.float32, device=device).reshape(1, 2)
+    ones = torch.ones(1, H, W, dtype=torch.float32, device=device)
+    # mean = wp + dist * ratio with ratio 0 -> mean = wp = coordinates; last_obs = wp + dist
+    return ops.cws_waypoint_map(ones, coordinates, coordinates + dist, 0.0, sigma_factor, ratio, rot)[0]
+
+
+def _goal_samples_ttst(model, pred_goal_map, sig_goal, waypoints, n_goal, rel_thresh, rng, kmeans_init=None):
+    """evaluate.py:134-161.  Returns (n_goal, B, 1, 2)."""
+    B = pred_goal_map.shape[0]
+    xy = sampling(sig_goal, num_samples=TTST_SAMPLES, replacement=True, rel_threshold=rel_thresh, rng=rng)
+    X = xy[:, 0]                                                     # (B, S, 2)
+    soft = ops.softargmax2d(pred_goal_map, channel=waypoints[-1])   # (B, 1, 2) first sample = softargmax
+    if kmeans_init is None and hasattr(rng, 'kmeans_init'):         # device generator: no host round trip
+        kmeans_init = rng.kmeans_init(B, X.shape[1], n_goal - 1, X.device)
+    _, centres = kmeans_batched(X, n_goal - 1, init_idx=kmeans_init, tol=0.001, iter_limit=1000)
+    return torch.cat([soft.unsqueeze(0), centres.permute(1, 0, 2).unsqueeze(2)], dim=0)
+
+
+def _cws(model, sig_maps, goal_samples, last_observed, n_goal, n_traj, n_wp, CWS_params, rng):
+    """evaluate.py:172-224.  sig_maps: list of (B, 1, H, W) per waypoint; returns (G, B, n_wp, 2)."""
+    sigma_factor, ratio, rot = CWS_params['sigma_factor'], CWS_params['ratio'], CWS_params['rot']
+    goal_samples = goal_samples.repeat(n_traj, 1, 1, 1)
+    G, B = goal_samples.shape[0], goal_samples.shape[1]
+    dev = goal_samples.device
+    traj_idx = torch.arange(G, device=dev) // n_goal
+    sf = (sigma_factor - traj_idx).float()
+    first = [g for g in range(G) if g // n_goal == 0]
+    rest = [g for g in range(G) if g // n_goal > 0]
+    out = torch.empty(G, B, n_wp, 2, dtype=torch.float32, device=dev)
+    out[:, :, n_wp - 1] = goal_samples[:, :, 0]
+    # trajectories 0 of every goal: expectation of sigmoid * prior, all goals in one pass per level
+    cur = goal_samples[first, :, 0].contiguous()
+    for wnum in reversed(range(n_wp - 1)):
+        cur = ops.cws_waypoint(sig_maps[wnum][:, 0], cur, last_observed, 1.0 / (wnum + 2), sf[first].contiguous(),
+                               ratio, rot)
+        out[first, :, wnum] = cur
+    # further trajectories per goal re-sample from the thresholded map (evaluate.py:213-216); RNG is
+    # consumed goal-major / level-minor exactly like the reference loop
+    for g in rest:
+        cur = goal_samples[g, :, 0].contiguous()
+        for wnum in reversed(range(n_wp - 1)):
+            wmap = ops.cws_waypoint_map(sig_maps[wnum][:, 0], cur, last_observed, 1.0 / (wnum + 2),
+                                        float(sigma_factor - g // n_goal), ratio, rot)
+            cur = sampling(wmap.unsqueeze(1), num_samples=1, rel_threshold=0.05, rng=rng)[:, 0, 0].contiguous()
+            out[g, :, wnum] = cur
+    return out, goal_samples
+
+
+def forecast_batch(model, scene_image, trajectory, input_template, waypoints, n_goal, n_traj, obs_len,
+                   resize_factor=0.25, temperature=1.0, use_TTST=False, use_CWS=False, rel_thresh=0.002,
+                   CWS_params=None, rng=None, kmeans_init=None, want_maps=False):
+    """One iteration of the reference's batch loop (evaluate.py:109-291), everything on the device.
+
+    scene_image (1, n_cls, H, W) semantic map; trajectory (B, obs+pred, 2) float32 device tensor in
+    resized-image pixels.  Returns dict(ade (B,), fde (B,), trajs (G, B, pred, 2),
+    waypoint_samples (G, B, n_wp, 2)[, goal_map, sig]).
+    """
+    rng = rng or HostRng
+    _, _, H, W = scene_image.shape
+    B = trajectory.shape[0]
+    n_wp = len(waypoints)
+    with torch.no_grad():
+        observed = trajectory[:, :obs_len].reshape(-1, 2)
+        observed_map = ops.rasterize_patches(input_template, observed, H, W).view(B, obs_len, H, W)
+        gt_future = trajectory[:, obs_len:].contiguous()
+        feats = model.pred_features(scene_image, observed_map)
+        pred_goal_map = model.pred_goal(feats)
+        sig = [ops.sigmoid_select(pred_goal_map, [w], temperature) for w in waypoints]   # n_wp x (B, 1, H, W)
+
+        if use_TTST:
+            goal_samples = _goal_samples_ttst(model, pred_goal_map, sig[-1], waypoints, n_goal, rel_thresh, rng,
+                                              kmeans_init)
+        else:
+            goal_samples = sampling(sig[-1], num_samples=n_goal, rng=rng).permute(2, 0, 1, 3)   # (n_goal, B, 1, 2)
+
+        if use_CWS and n_wp > 1:
+            last_observed = trajectory[:, obs_len - 1].contiguous()
+            waypoint_samples, goal_samples = _cws(model, sig, goal_samples, last_observed, n_goal, n_traj, n_wp,
+                                                  CWS_params, rng)
+        elif not use_CWS and n_wp > 1:
+            # evaluate.py:227-231 samples all earlier waypoints with ONE multinomial over (B*(n_wp-1)) rows
+            sig_early = torch.cat(sig[:-1], dim=1)
+            ws = sampling(sig_early, num_samples=n_goal * n_traj, rng=rng).permute(2, 0, 1, 3)
+            goal_samples = goal_samples.repeat(n_traj, 1, 1, 1)
+            waypoint_samples = torch.cat([ws, goal_samples], dim=2)
+        else:
+            waypoint_samples = goal_samples
+        waypoint_samples = waypoint_samples.contiguous()
+        G = waypoint_samples.shape[0]
+
+        # trajectory decoder: goals stacked along the batch axis; features are read modulo B
+        trajs = torch.empty(G, B, gt_future.shape[1], 2, dtype=torch.float32, device=trajectory.device)
+        gc = max(1, min(G, MAX_STACKED_PASSES // max(B, 1)))
+        for g0 in range(0, G, gc):
+            g1 = min(G, g0 + gc)
+            wp = waypoint_samples[g0:g1].reshape(-1, 2)                      # ((g1-g0)*B*n_wp, 2)
+            wmap = ops.rasterize_patches(input_template, wp, H, W).view((g1 - g0) * B, n_wp, H, W)
+            pyr = ops.avgpool_pyramid(wmap, len(feats))
+            traj_input = [ChannelCat(tuple(f) + (p,)) if isinstance(f, tuple) else ChannelCat((f, p))
+                          for f, p in zip(feats, pyr)]
+            trajs[g0:g1] = model.pred_traj_softargmax(traj_input).view(g1 - g0, B, -1, 2)
+        ade, fde = ops.ade_fde(gt_future, trajs, waypoint_samples, resize_factor)
+    out = dict(ade=ade, fde=fde, trajs=trajs, waypoint_samples=waypoint_samples)
+    if want_maps:
+        out['goal_map'] = pred_goal_map
+        out['sig'] = sig
+    return out
+
+
+def evaluate(model, val_loader, val_images, device, dataset_name, homo_mat, input_template, waypoints, mode,
+             n_goal, n_traj, obs_len, batch_size, resize_factor=0.25, temperature=1, use_TTST=False, use_CWS=False,
+             rel_thresh=0.002, CWS_params=None, return_preds=False, return_samples=False, network=None,
+             swap_semantic=False):
+    """Reference signature (evaluate.py:37-42) -> (ade, fde, DataFrame[metaId, sceneId, ade, fde], dict|None)."""
+    if str(dataset_name).lower() == 'eth':
+        raise NotImplementedError('ETH/UCY homography path (image2world) is outside the B200 hot path')
+    if network == 'embed':
+        raise NotImplementedError("network='embed' is outside the B200 hot path")
+    if swap_semantic:
+        raise NotImplementedError('swap_semantic is outside the B200 hot path')
+    model.eval()
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise RuntimeError('motion_style_transfer_b200.evaluate runs on CUDA only (no CPU fallback)')
+    input_template = input_template.to(device=device, dtype=torch.float32)
+    ade_list, fde_list, meta_id_list, scene_id_list = [], [], [], []
+    if return_preds:
+        trajs_dict = {'groundtruth': [], 'prediction': []}
+        if return_samples:
+            trajs_dict.update({'waypoint_sample': [], 'goal_map': [], 'goal_sigmoid_map': []})
+    else:
+        trajs_dict = None
+
+    with torch.no_grad():
+        for trajectory, df_batch, scene_id in val_loader:
+            scene_image = val_images[scene_id].to(device).unsqueeze(0)
+            scene_image = model.segmentation(scene_image)
+            scene_image = model.adapt_semantic(scene_image).float().contiguous()
+            meta_ids = df_batch[0].metaId.unique()
+            n_data = trajectory.shape[0]
+            trajectory = trajectory.to(device=device, dtype=torch.float32)
+            for b in range(0, n_data, batch_size):
+                res = forecast_batch(model, scene_image, trajectory[b:b + batch_size].contiguous(), input_template,
+                                     waypoints, n_goal, n_traj, obs_len, resize_factor, temperature, use_TTST,
+                                     use_CWS, rel_thresh, CWS_params, want_maps=return_samples)
+                ade_list.append(res['ade'])
+                fde_list.append(res['fde'])
+                if return_preds:
+                    if b == 0:
+                        trajs_dict['groundtruth'].append(trajectory.cpu().numpy() / resize_factor)
+                    trajs, gt_future = res['trajs'], trajectory[b:b + batch_size, obs_len:]
+                    ade_batch = ((((gt_future - trajs) / resize_factor) ** 2).sum(dim=3) ** 0.5).mean(dim=2)
+                    best = ade_batch.argmin(dim=0)
+                    trajs_dict['prediction'].append(
+                        (trajs[best, torch.arange(trajs.shape[1], device=device)] / resize_factor).cpu().numpy())
+                    if return_samples:
+                        trajs_dict['goal_map'].append(res['goal_map'].cpu().numpy())
+                        trajs_dict['goal_sigmoid_map'].append(
+                            ops.sigmoid_select(res['goal_map'], list(range(res['goal_map'].shape[1])),
+                                               temperature).cpu().numpy())
+                        trajs_dict['waypoint_sample'].append(res['waypoint_samples'].permute(1, 2, 0, 3).cpu().numpy())
+            meta_id_list.append(meta_ids)
+            scene_id_list.append([scene_id] * n_data)
+
+    val_ade_arr = torch.cat(ade_list).cpu().numpy()
+    val_fde_arr = torch.cat(fde_list).cpu().numpy()
+    df_out = pd.DataFrame()
+    meta_id_ready = np.concatenate(meta_id_list)
+    scene_id_ready = sum(scene_id_list, [])
+    df_out.loc[:, 'metaId'] = meta_id_ready
+    df_out.loc[:, 'sceneId'] = scene_id_ready
+    df_out.loc[:, 'ade'] = val_ade_arr
+    df_out.loc[:, 'fde'] = val_fde_arr
+    if return_preds:
+        for key, value in trajs_dict.items():
+            trajs_dict[key] = np.concatenate(value, axis=0)
+        trajs_dict['metaId'] = meta_id_ready
+        trajs_dict['sceneId'] = scene_id_ready
+    return val_ade_arr.mean(), val_fde_arr.mean(), df_out, trajs_dict

@@ -1,0 +1,73 @@
+"""Drop-in for the reference's utils/train_epoch.py (one fine-tuning epoch), device-resident.
+
+Same 20-argument signature and return value as train_epoch.py:8-12.  Heat maps are rasterised on the
+device from device coordinates (no numpy round trip), the forward/backward of every layer and the
+BCE run in libynet_b200.so kernels through ``autograd_engine``; ``optimizer.step()`` is whatever the
+trainer passes (``FusedAdam`` = Adam kernel + optional NCCL all-reduce of the LoRA gradients).
+"""
+import torch
+
+from .. import ops
+from ..engine import ChannelCat
+
+
+def train_epoch(model, train_loader, train_images, optimizer, criterion, loss_scale, device, dataset_name, homo_mat,
+                gt_template, input_template, waypoints, epoch, obs_len, pred_len, batch_size, e_unfreeze,
+                resize_factor, network=None, swap_semantic=False):
+    if network == 'embed' or swap_semantic:
+        raise NotImplementedError("network='embed' / swap_semantic are outside the B200 hot path")
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise RuntimeError('motion_style_transfer_b200.train_epoch runs on CUDA only (no CPU fallback)')
+    train_loss = torch.zeros((), device=device)
+    train_ADE, train_FDE = [], []
+    model.train()
+    input_template = input_template.to(device=device, dtype=torch.float32)
+    gt_template = gt_template.to(device=device, dtype=torch.float32)
+
+    for batch, (trajectory, meta, scene) in enumerate(train_loader):
+        model.eval()
+        with torch.no_grad():
+            scene_image = train_images[scene].to(device).unsqueeze(0)
+            scene_image = model.segmentation(scene_image).float().contiguous()
+        model.train()
+        trajectory = trajectory.to(device=device, dtype=torch.float32)
+        for i in range(0, len(trajectory), batch_size):
+            semantic_img = model.adapt_semantic(scene_image)
+            _, _, H, W = scene_image.shape
+            traj = trajectory[i:i + batch_size]
+            B = traj.shape[0]
+            observed_map = ops.rasterize_patches(input_template, traj[:, :obs_len].reshape(-1, 2), H, W)
+            observed_map = observed_map.view(B, obs_len, H, W)
+            gt_future = traj[:, obs_len:].contiguous()
+            gt_future_map = ops.rasterize_patches(gt_template, gt_future.reshape(-1, 2), H, W).view(B, pred_len, H, W)
+            gt_waypoints = gt_future[:, waypoints]
+            gt_waypoint_map = ops.rasterize_patches(input_template, gt_waypoints.reshape(-1, 2), H, W)
+            gt_waypoint_map = gt_waypoint_map.view(B, gt_waypoints.shape[1], H, W)
+
+            features = model.pred_features(semantic_img, observed_map)            # scene broadcast over B
+            pred_goal_map = model.pred_goal(features)
+            goal_loss = criterion(pred_goal_map, gt_future_map) * loss_scale
+
+            pyr = ops.avgpool_pyramid(gt_waypoint_map, len(features))
+            traj_input = [ChannelCat(tuple(f) + (g,)) if isinstance(f, tuple) else ChannelCat((f, g))
+                          for f, g in zip(features, pyr)]
+            pred_traj_map = model.pred_traj(traj_input)
+            traj_loss = criterion(pred_traj_map, gt_future_map) * loss_scale
+
+            loss = goal_loss + traj_loss
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
+
+            with torch.no_grad():
+                train_loss += loss.detach()
+                pred_traj = model.softargmax(pred_traj_map.detach())
+                pred_goal = ops.softargmax2d(pred_goal_map.detach(), channel=-1)
+                train_ADE.append(((((gt_future - pred_traj) / resize_factor) ** 2).sum(dim=2) ** 0.5).mean(dim=1))
+                train_FDE.append(((((gt_future[:, -1:] - pred_goal[:, -1:]) / resize_factor) ** 2).sum(dim=2) ** 0.5)
+                                 .mean(dim=1))
+
+    train_ADE = torch.cat(train_ADE).mean()
+    train_FDE = torch.cat(train_FDE).mean()
+    return train_ADE.item(), train_FDE.item(), train_loss.item()

@@ -1,0 +1,43 @@
+"""Shared helpers for the parity tests (CPU side: oracle; GPU side: product through the C ABI)."""
+import ast
+
+import numpy as np
+import torch
+
+from conftest import load_golden, golden_state_dict
+
+SMALL_ENC = [8, 8, 16, 16, 16]
+SMALL_DEC = [16, 16, 16, 8, 8]
+
+
+def build_product_model(sd, obs, pred, n_wp, network='original', position=(0, 1, 2, 3, 4), n_fusion=None,
+                        train_net='mosa_1', enc=SMALL_ENC, dec=SMALL_DEC, device='cuda'):
+    from motion_style_transfer_b200.models.ynet import YNet
+    m = YNet(obs_len=obs, pred_len=pred, segmentation_model_fp=None, encoder_channels=list(enc),
+             decoder_channels=list(dec), n_waypoints=n_wp, train_net=train_net, position=list(position),
+             network=network, n_fusion=n_fusion)
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    return m.to(device).eval()
+
+
+class ReplayRng:
+    """Feeds randoms recorded in a fixture (the ones the live reference consumed)."""
+
+    def __init__(self, g):
+        self.g = g
+
+    def uniforms(self, rows, n, device):
+        return torch.from_numpy(self.g['uniforms']).to(device)
+
+    def exponentials(self, rows, S, device):
+        return torch.from_numpy(self.g['expo']).to(device)
+
+
+def eval_cfg(g):
+    return ast.literal_eval(str(g['cfg']))
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
