@@ -144,9 +144,9 @@ extern "C" {
 
 int ynet_rasterize_patches(const float* tmpl, int32_t th, int32_t tw, const float* coords, int32_t n, float* out,
                            int32_t H, int32_t W, int32_t* oob_flag, void* stream) {
-  YNET_CHECK_ARG(tmpl && coords && out, "null pointer");
   YNET_CHECK_ARG(n >= 0 && H > 0 && W > 0 && th >= H && tw >= W, "bad shape (template smaller than window?)");
   if (n == 0) return YNET_OK;
+  YNET_CHECK_ARG(tmpl && coords && out, "null pointer");
   const bool vec = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
   const int work = vec ? H * (W / 4) : H * W;
   int gx = ceil_div(work, 256 * 4);
