@@ -200,7 +200,7 @@ int ynet_lora_fold(const float* weight, const float* lora_A, const float* lora_B
 typedef struct ynet_tc_src {
   const void* ptr;      /* bf16 C8 planes                                                     */
   int32_t channels_pad; /* multiple of 16                                                     */
-  int32_t reserved;
+  int32_t batch_mod;    /* > 0: image n reads source image n % batch_mod                      */
   int64_t batch_stride; /* elements (bf16); 0 = broadcast                                     */
 } ynet_tc_src;
 
@@ -209,6 +209,12 @@ int ynet_tc_pack_f32_to_c8(const float* x, int32_t N, int32_t C, int32_t H, int3
                            void* out_c8, int32_t C_pad, void* stream);
 int ynet_tc_unpack_c8_to_f32(const void* x_c8, int32_t N, int32_t C, int32_t C_pad, int32_t H, int32_t W,
                              float* out, void* stream);
+/* nn.MaxPool2d(2,2) / bilinear x2 (align_corners=False) on C8 planes; (H, W) = input size. */
+int ynet_tc_maxpool2x2(const void* x_c8, int32_t N, int32_t C_pad, int32_t H, int32_t W, void* out_c8, void* stream);
+int ynet_tc_upsample2x(const void* x_c8, int32_t N, int32_t C_pad, int32_t H, int32_t W, void* out_c8, void* stream);
+/* 1x1 predictor (ynet.py:450-451,469) reading C8 bf16, writing float32 NCHW logits (fp32 FMA). */
+int ynet_tc_predictor_f32(const void* x_c8, int32_t N, int32_t C_pad, int32_t C_in, int32_t H, int32_t W,
+                          const float* weight, const float* bias, int32_t C_out, float* out, void* stream);
 int64_t ynet_tc_packed_weight_bytes(int32_t C_out, int32_t n_src, const int32_t* src_channels_pad_host);
 int ynet_tc_pack_weights(const float* weight, int32_t C_out, int32_t n_src, const int32_t* src_channels_host,
                          const int32_t* src_channels_pad_host, void* packed, void* stream);

@@ -22,7 +22,7 @@ class ConvSrc(Structure):
 
 
 class TcSrc(Structure):
-    _fields_ = [('ptr', c_void_p), ('channels_pad', c_int32), ('reserved', c_int32), ('batch_stride', c_int64)]
+    _fields_ = [('ptr', c_void_p), ('channels_pad', c_int32), ('batch_mod', c_int32), ('batch_stride', c_int64)]
 
 
 class YnetError(RuntimeError):
@@ -68,6 +68,9 @@ _PROTOS = {
     'ynet_tc_supported': (c_int, []),
     'ynet_tc_pack_f32_to_c8': (c_int, [_P, _I, _I, _I, _I, _L, _P, _I, _P]),
     'ynet_tc_unpack_c8_to_f32': (c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    'ynet_tc_maxpool2x2': (c_int, [_P, _I, _I, _I, _I, _P, _P]),
+    'ynet_tc_upsample2x': (c_int, [_P, _I, _I, _I, _I, _P, _P]),
+    'ynet_tc_predictor_f32': (c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
     'ynet_tc_packed_weight_bytes': (_L, [_I, _I, POINTER(c_int32)]),
     'ynet_tc_pack_weights': (c_int, [_P, _I, _I, POINTER(c_int32), POINTER(c_int32), _P, _P]),
     'ynet_tc_conv3x3': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),

@@ -148,3 +148,89 @@ class YNetEngine:
             return ops.softargmax2d(ops.conv1x1_f32(x, p.weight.detach().reshape(p.weight.shape[0], -1),
                                                     p.bias.detach()))
         return ops.predictor_softargmax_f32(x, p.weight.detach().reshape(p.weight.shape[0], -1), p.bias.detach())
+
+
+class YNetEngineTC(YNetEngine):
+    """Throughput back end: tcgen05 implicit-GEMM convs on bf16 C8 planes (conv_tc.cu).
+
+    Same layer walk; activations are ``ops.C8`` objects.  float32 NCHW inputs (rasterised maps, the
+    semantic map, waypoint pyramids) are converted on entry with ``tc_pack``; the 1x1 predictor reads
+    bf16 and writes float32 logits so that sigmoid / sampling / soft-argmax stay in fp32.
+    """
+
+    def __init__(self, model):
+        super().__init__(model, backend='bf16')
+
+    def _c8(self, t):
+        return t if isinstance(t, ops.C8) else ops.tc_pack(t)
+
+    def _c8_parts(self, x):
+        if isinstance(x, (ops.C8, torch.Tensor)):
+            x = (x,)
+        return [self._c8(t) for t in x]
+
+    def _tc_params(self, module, key, src_channels):
+        A = getattr(module, 'lora_A', None)
+        Bm = getattr(module, 'lora_B', None)
+        ver = (module.weight._version, module.weight.data_ptr(),
+               None if A is None else (A._version, A.data_ptr()),
+               None if Bm is None else (Bm._version, Bm.data_ptr()), tuple(src_channels))
+        hit = self._wcache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1], hit[2]
+        w_eff = ops.lora_fold(module.weight.detach(), None if A is None else A.detach(),
+                              None if Bm is None else Bm.detach(), packed=False)
+        packed = ops.tc_pack_weights(w_eff, list(src_channels))
+        C_out = module.weight.shape[0]
+        bias = torch.zeros(ops._pad16(C_out), dtype=torch.float32, device=module.weight.device)
+        if module.bias is not None:
+            bias[:C_out] = module.bias.detach()
+        self._wcache[key] = (ver, packed, bias)
+        return packed, bias
+
+    def _tconv(self, module, key, sources, relu):
+        packed, bias = self._tc_params(module, key, [s.C for s in sources])
+        return ops.tc_conv3x3(sources, packed, bias, module.weight.shape[0], relu)
+
+    def _run_stages_tc(self, stages, key, cur):
+        feats = []
+        for si, stage in enumerate(stages):
+            mods = list(stage)
+            convs = [(j, m) for j, m in enumerate(mods) if isinstance(m, torch.nn.Conv2d)]
+            if any(isinstance(m, torch.nn.MaxPool2d) for m in mods):
+                cur = [ops.tc_maxpool(c) for c in cur]
+            if not convs:
+                feats.append(cur[0] if len(cur) == 1 else ChannelCat(cur))
+                continue
+            for j, conv in convs:
+                cur = [self._tconv(conv, f'{key}.{si}.{j}', cur, True)]
+            feats.append(cur[0])
+        return feats
+
+    def pred_features(self, scene_map, motion_map):
+        enc = self.model.encoder
+        scene, motion = self._c8_parts(scene_map), self._c8_parts(motion_map)
+        if self.model.network == 'fusion':
+            sf = self._run_stages_tc(enc.scene_stages, 'encoder.scene_stages', scene)
+            mf = self._run_stages_tc(enc.motion_stages, 'encoder.motion_stages', motion)
+            feats = [ChannelCat((a, b)) for a, b in zip(sf, mf)]
+            return feats + self._run_stages_tc(enc.fusion_stages, 'encoder.fusion_stages', list(feats[-1]))
+        return self._run_stages_tc(enc.stages, 'encoder.stages', scene + motion)
+
+    def decoder_trunk(self, decoder, key, features):
+        feats = [self._c8_parts(f) for f in features][::-1]
+        x = self._tconv(decoder.center[0], f'{key}.center.0', feats[0], True)
+        x = self._tconv(decoder.center[2], f'{key}.center.2', [x], True)
+        for i, skip in enumerate(feats[1:]):
+            up = self._tconv(decoder.upsample_conv[i], f'{key}.upsample_conv.{i}', [ops.tc_upsample(x)], False)
+            x = self._tconv(decoder.decoder[i][0], f'{key}.decoder.{i}.0', [up] + skip, True)
+            x = self._tconv(decoder.decoder[i][2], f'{key}.decoder.{i}.2', [x], True)
+        return x
+
+    def decoder_logits(self, decoder, key, features):
+        x = self.decoder_trunk(decoder, key, features)
+        p = decoder.predictor
+        return ops.tc_predictor_f32(x, p.weight.detach().reshape(p.weight.shape[0], -1), p.bias.detach())
+
+    def decoder_softargmax(self, decoder, key, features):
+        return ops.softargmax2d(self.decoder_logits(decoder, key, features))

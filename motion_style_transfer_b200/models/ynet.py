@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from . import lora
 from .. import ops
-from ..engine import YNetEngine, ChannelCat
+from ..engine import YNetEngine, YNetEngineTC, ChannelCat
 from ..utils.softargmax import SoftArgmax2D
 
 
@@ -185,12 +185,22 @@ class YNet(nn.Module):
         self.softargmax_ = SoftArgmax2D(normalized_coordinates=False)
         self.encoder_channels = encoder_channels
         self._engine = None
+        self._backend = 'fp32'
 
     # ---- engine plumbing -------------------------------------------------------------------------
+    def set_backend(self, backend):
+        """'fp32' = CUDA-core reference-grade engine (<= 1e-3 parity); 'bf16' = tcgen05 tensor-core engine."""
+        if backend not in ('fp32', 'bf16'):
+            raise ValueError(f'unknown backend {backend!r}')
+        object.__setattr__(self, '_backend', backend)
+        object.__setattr__(self, '_engine', None)
+        return self
+
     @property
     def engine(self):
         if self._engine is None:
-            object.__setattr__(self, '_engine', YNetEngine(self))
+            eng = YNetEngineTC(self) if self._backend == 'bf16' else YNetEngine(self)
+            object.__setattr__(self, '_engine', eng)
         return self._engine
 
     def _training_graph(self):

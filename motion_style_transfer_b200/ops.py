@@ -534,3 +534,130 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999
                               float(lr), float(beta1), float(beta2), float(eps), float(grad_scale), _stream()),
           'adam_step')
     _count()
+
+
+# ------------------------------------------------------------------------------------------------ a4-a8 tensor-core engine
+class C8:
+    """bf16 activation in C8 planes: data (N, C_pad/8, H, W, 8) bfloat16, logical channel count C."""
+
+    __slots__ = ('data', 'C')
+
+    def __init__(self, data, C):
+        self.data, self.C = data, C
+
+    @property
+    def N(self):
+        return self.data.shape[0]
+
+    @property
+    def C_pad(self):
+        return self.data.shape[1] * 8
+
+    @property
+    def H(self):
+        return self.data.shape[2]
+
+    @property
+    def W(self):
+        return self.data.shape[3]
+
+
+def _pad16(c):
+    return (c + 15) // 16 * 16
+
+
+def tc_supported():
+    return bool(_L().ynet_tc_supported())
+
+
+def tc_pack(x):
+    """NCHW float32 (batch may be broadcast: stride 0 or N == 1) -> C8 bf16."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
+        raise RuntimeError('tc_pack: expected a 4-D float32 CUDA tensor')
+    if x.shape[0] > 1 and x.stride(0) == 0:
+        x = x[:1]
+    if not x[0].is_contiguous():
+        x = x.contiguous()
+    N, C, H, W = x.shape
+    cp = _pad16(C)
+    out = torch.empty(N, cp // 8, H, W, 8, dtype=torch.bfloat16, device=x.device)
+    with _timed('pack_c8_kernel', 0, (4.0 * C + 2.0 * cp) * N * H * W):
+        check(_L().ynet_tc_pack_f32_to_c8(_ptr(x), N, C, H, W, x.stride(0) if N > 1 else C * H * W, _ptr(out), cp,
+                                          _stream()), 'tc_pack_f32_to_c8')
+    _count()
+    return C8(out, C)
+
+
+def tc_unpack(a):
+    out = torch.empty(a.N, a.C, a.H, a.W, dtype=torch.float32, device=a.data.device)
+    check(_L().ynet_tc_unpack_c8_to_f32(_ptr(a.data), a.N, a.C, a.C_pad, a.H, a.W, _ptr(out), _stream()),
+          'tc_unpack_c8_to_f32')
+    _count()
+    return out
+
+
+def tc_maxpool(a):
+    out = torch.empty(a.N, a.C_pad // 8, a.H // 2, a.W // 2, 8, dtype=torch.bfloat16, device=a.data.device)
+    with _timed('c8_maxpool_kernel', 0, 2.5 * a.C_pad * a.N * a.H * a.W):
+        check(_L().ynet_tc_maxpool2x2(_ptr(a.data), a.N, a.C_pad, a.H, a.W, _ptr(out), _stream()), 'tc_maxpool2x2')
+    _count()
+    return C8(out, a.C)
+
+
+def tc_upsample(a):
+    out = torch.empty(a.N, a.C_pad // 8, a.H * 2, a.W * 2, 8, dtype=torch.bfloat16, device=a.data.device)
+    with _timed('c8_upsample_kernel', 0, 10.0 * a.C_pad * a.N * a.H * a.W):
+        check(_L().ynet_tc_upsample2x(_ptr(a.data), a.N, a.C_pad, a.H, a.W, _ptr(out), _stream()), 'tc_upsample2x')
+    _count()
+    return C8(out, a.C)
+
+
+def tc_pack_weights(weight_oihw, src_channels):
+    """Effective OIHW float32 weight -> bf16 [kb][tap][2][C_out_pad][8] over per-source padded channels."""
+    weight_oihw = _req(weight_oihw, name='weight')
+    C_out = weight_oihw.shape[0]
+    n = len(src_channels)
+    real = (ctypes.c_int32 * n)(*src_channels)
+    pad = (ctypes.c_int32 * n)(*[_pad16(c) for c in src_channels])
+    nbytes = _L().ynet_tc_packed_weight_bytes(C_out, n, pad)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=weight_oihw.device)
+    check(_L().ynet_tc_pack_weights(_ptr(weight_oihw), C_out, n, real, pad, _ptr(packed), _stream()), 'tc_pack_weights')
+    _count()
+    return packed
+
+
+def tc_conv3x3(sources, packed_weight, bias_pad, C_out, relu):
+    """sources: list of C8 (batch N, 1 = broadcast, or a divisor of N = modulo).  Returns C8 (N, C_out)."""
+    N = max(s.N for s in sources)
+    H, W = sources[0].H, sources[0].W
+    arr = (_lib.TcSrc * len(sources))()
+    for i, s in enumerate(sources):
+        if s.H != H or s.W != W:
+            raise ValueError('tc_conv3x3: sources must share the spatial size')
+        arr[i].ptr = s.data.data_ptr()
+        arr[i].channels_pad = s.C_pad
+        arr[i].batch_stride = 0 if (s.N == 1 and N > 1) else s.data.stride(0)
+        arr[i].batch_mod = s.N if (1 < s.N < N) else 0
+        if 1 < s.N < N and N % s.N != 0:
+            raise ValueError(f'tc_conv3x3: source batch {s.N} does not divide N={N}')
+    cp = _pad16(C_out)
+    out = torch.empty(N, cp // 8, H, W, 8, dtype=torch.bfloat16, device=sources[0].data.device)
+    cin_pad = sum(s.C_pad for s in sources)
+    with _timed('tc_conv3x3_kernel', 2.0 * 9 * sum(s.C for s in sources) * C_out * H * W * N,
+                2.0 * (cin_pad + cp) * H * W * N, tag=f'{cin_pad}->{cp}@{H}x{W} N={N}'):
+        check(_L().ynet_tc_conv3x3(arr, len(sources), N, H, W, _ptr(packed_weight), _ptr(bias_pad), C_out,
+                                   1 if relu else 0, _ptr(out), cp, _stream()), 'tc_conv3x3')
+    _count()
+    return C8(out, C_out)
+
+
+def tc_predictor_f32(a, weight, bias):
+    """1x1 predictor on a C8 activation -> float32 NCHW logits."""
+    weight = _req(weight, name='weight')
+    C_out, C_in = weight.shape
+    out = torch.empty(a.N, C_out, a.H, a.W, dtype=torch.float32, device=a.data.device)
+    with _timed('c8_predictor_kernel', 2.0 * C_in * C_out * a.H * a.W * a.N, (2.0 * a.C_pad + 4.0 * C_out) * a.H * a.W * a.N):
+        check(_L().ynet_tc_predictor_f32(_ptr(a.data), a.N, a.C_pad, C_in, a.H, a.W, _ptr(weight), _ptr(bias), C_out,
+                                         _ptr(out), _stream()), 'tc_predictor_f32')
+    _count()
+    return out

