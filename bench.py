@@ -164,6 +164,8 @@ def main():
     ap.add_argument('--cpu-agents', type=int, default=4, help='agents of the bounded cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-layers', default=None, help='write a per-layer timing table to this path')
+    ap.add_argument('--backend', default='bf16', choices=['bf16', 'fp32'],
+                    help='bf16 = tcgen05 tensor-core engine (default), fp32 = CUDA-core reference-grade engine')
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', 0))
@@ -185,7 +187,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     _lib.load()
 
-    model = build_model_state(cfg).to(dev).eval()
+    model = build_model_state(cfg).to(dev).eval().set_backend(args.backend)
     from oracle import ynet_oracle as O          # synthetic-input generators only (test infrastructure)
     scene_host = O.synthetic_scene(H, W, seed=0)[None].contiguous().pin_memory()
     tmpl = ops.create_dist_template(int(4200 * cfg['resize']), dev)

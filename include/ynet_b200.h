@@ -215,12 +215,29 @@ int ynet_tc_upsample2x(const void* x_c8, int32_t N, int32_t C_pad, int32_t H, in
 /* 1x1 predictor (ynet.py:450-451,469) reading C8 bf16, writing float32 NCHW logits (fp32 FMA). */
 int ynet_tc_predictor_f32(const void* x_c8, int32_t N, int32_t C_pad, int32_t C_in, int32_t H, int32_t W,
                           const float* weight, const float* bias, int32_t C_out, float* out, void* stream);
-int64_t ynet_tc_packed_weight_bytes(int32_t C_out, int32_t n_src, const int32_t* src_channels_pad_host);
+/* ksize = 3 (3x3 conv) or 1 (the 1x1 predictor). */
+int64_t ynet_tc_packed_weight_bytes(int32_t C_out, int32_t n_src, const int32_t* src_channels_pad_host,
+                                    int32_t ksize);
 int ynet_tc_pack_weights(const float* weight, int32_t C_out, int32_t n_src, const int32_t* src_channels_host,
-                         const int32_t* src_channels_pad_host, void* packed, void* stream);
+                         const int32_t* src_channels_pad_host, int32_t ksize, void* packed, void* stream);
+/* tune: 0 = built-in heuristics; else (accumulators per tile J in bits 0-3) | (max CTAs per SM in bits 4-7) |
+ * (pipeline stages in bits 8-15) -- the host side autotunes these per layer shape. */
 int ynet_tc_conv3x3(const ynet_tc_src* srcs_host, int32_t n_src, int32_t N, int32_t H, int32_t W,
                     const void* packed_weight, const float* bias, int32_t C_out, int32_t relu, void* out_c8,
-                    int32_t C_out_pad, void* stream);
+                    int32_t C_out_pad, int32_t tune, void* stream);
+
+/* The 1x1 predictor (ynet.py:450-451,469) on the tensor cores, same kernel with one tap:
+ *   ynet_tc_conv1x1_f32        -> float32 NCHW logits (goal decoder: sigmoid / sampling need the map);
+ *   ynet_tc_conv1x1_softargmax -> predictor + SoftArgmax2D (ynet.py:582-583) fused in the epilogue: the
+ *       logits go TMEM -> registers -> shared memory -> per-channel online soft-max partials, never to HBM.
+ *       out (N, C_out, 2) = (x, y); C_out <= 32. */
+int ynet_tc_conv1x1_f32(const ynet_tc_src* srcs_host, int32_t n_src, int32_t N, int32_t H, int32_t W,
+                        const void* packed_weight, const float* bias, int32_t C_out, float* out, int32_t tune,
+                        void* stream);
+int64_t ynet_tc_conv1x1_softargmax_workspace_bytes(int32_t N, int32_t C_out);
+int ynet_tc_conv1x1_softargmax(const ynet_tc_src* srcs_host, int32_t n_src, int32_t N, int32_t H, int32_t W,
+                               const void* packed_weight, const float* bias, int32_t C_out, float* out,
+                               void* workspace, int64_t workspace_bytes, int32_t tune, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a18 fine-tuning step pieces (utils/train_epoch.py:86-115, models/trainer.py:197-206).

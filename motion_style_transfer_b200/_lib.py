@@ -71,9 +71,12 @@ _PROTOS = {
     'ynet_tc_maxpool2x2': (c_int, [_P, _I, _I, _I, _I, _P, _P]),
     'ynet_tc_upsample2x': (c_int, [_P, _I, _I, _I, _I, _P, _P]),
     'ynet_tc_predictor_f32': (c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
-    'ynet_tc_packed_weight_bytes': (_L, [_I, _I, POINTER(c_int32)]),
-    'ynet_tc_pack_weights': (c_int, [_P, _I, _I, POINTER(c_int32), POINTER(c_int32), _P, _P]),
-    'ynet_tc_conv3x3': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
+    'ynet_tc_packed_weight_bytes': (_L, [_I, _I, POINTER(c_int32), _I]),
+    'ynet_tc_pack_weights': (c_int, [_P, _I, _I, POINTER(c_int32), POINTER(c_int32), _I, _P, _P]),
+    'ynet_tc_conv1x1_f32': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
+    'ynet_tc_conv1x1_softargmax_workspace_bytes': (_L, [_I, _I]),
+    'ynet_tc_conv1x1_softargmax': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _P, _P, _L, _I, _P]),
+    'ynet_tc_conv3x3': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _I, _P]),
     'ynet_bce_workspace_bytes': (_L, [_L]),
     'ynet_bce_logits_fwd_bwd': (c_int, [_P, _P, _L, _F, _P, _P, _P, _L, _P]),
     'ynet_conv3x3_dgrad_f32': (c_int, [_P, _P, _I, _I, _I, _P, _I, _I, _P, _P]),

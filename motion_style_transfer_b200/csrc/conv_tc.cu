@@ -22,14 +22,12 @@
 
 namespace ynet {
 
-constexpr int TC_TH = 16, TC_TW = 8;                 // output tile (pixels)
-constexpr int TC_BH = TC_TH + 2, TC_BW = TC_TW + 2;  // halo box
+constexpr int TC_TH = 16;                            // output tile height; width = 8 * J pixels (J accumulators)
+constexpr int TC_BH = TC_TH + 2;                     // halo box height; width = 8 * J + 2
 constexpr int TC_KB = 16;                            // channels per pipeline stage (one UMMA K step)
-constexpr int TC_A_BYTES = TC_BH * TC_BW * TC_KB * 2;            // 5760
-constexpr int TC_A_LBO = TC_BH * TC_BW * 16;                     // 2880: chunk (8 ch) stride
-constexpr int TC_A_SBO = TC_BW * 16;                             // 160: image-row stride = 8-pixel-group stride
+constexpr int TC_MAX_J = 3;                          // 4-D TMA box: (8J+2)*8 elements <= 256
 constexpr int TC_THREADS = 192;
-constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_MAX_STAGES = 32;
 constexpr unsigned TC_SPIN_LIMIT = 4u * 1000u * 1000u;             // bounded waits: trap instead of hanging
 
 struct TcSrcDev {
@@ -47,11 +45,20 @@ struct TcParams {
   int kb_total;           // sum of kblocks
   int resident;           // weights resident in smem
   int stages, stage_bytes, wres_bytes, tmem_cols;
+  int j;                  // accumulators (8-pixel column blocks) per tile: consecutive MMAs hit different ones
+  int bw;                 // halo box width in pixels = 8 j + 2
+  int a_bytes, a_lbo, a_sbo;   // A stage bytes, chunk stride, image-row stride (= 8-pixel-group stride)
   const unsigned char* wpacked;   // [kb][tap][2][n_pad][8] bf16
   const float* bias;              // n_pad floats (pad = 0)
-  __nv_bfloat16* out;             // C8 planes, n_pad channels
+  __nv_bfloat16* out;             // EPI 0: C8 planes, n_pad channels
+  float* out_f32;                 // EPI 1: NCHW float32, c_out channels
+  float4* partial;                // EPI 2: soft-argmax partials (m, s, sx, sy) [(n * c_out + c) * gridDim.x + cta]
+  int c_out;                      // real output channels
   int* err;
 };
+
+constexpr int EPI_C8 = 0, EPI_NCHW_F32 = 1, EPI_SOFTARGMAX = 2;
+constexpr int TC_LOGIT_PITCH = 33;
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -88,6 +95,13 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -133,8 +147,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 // ---- the conv kernel -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tc_conv3x3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+template <int J, int TAPS, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                   const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
                   const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -151,6 +166,8 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* w_bar = tempty_bar + 2;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(w_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(w_bar + 2);
+  for (int i = threadIdx.x; i < p.n_pad; i += TC_THREADS) s_bias[i] = p.bias[i];
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -176,7 +193,9 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
   const uint32_t tmem_base = *s_tmem;
 
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int wblk_bytes = 9 * 2 * p.n_pad * 16;  // weights of one 16-channel K block: [tap][2][n_pad][8] bf16
+  constexpr int HALO = (TAPS == 9) ? 1 : 0;
+  constexpr int BW = 8 * J + 2 * HALO, BH = TC_TH + 2 * HALO;   // TMA box (pixels)
+  const int wblk_bytes = TAPS * 2 * p.n_pad * 16;  // weights of one 16-channel K block: [tap][2][n_pad][8] bf16
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -194,7 +213,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n = (int)(tile / tiles_per_img);
         const int r = (int)(tile - (long long)n * tiles_per_img);
-        const int y0 = (r / p.tiles_x) * TC_TH, x0 = (r % p.tiles_x) * TC_TW;
+        const int y0 = (r / p.tiles_x) * TC_TH, x0 = (r % p.tiles_x) * 8 * J;
         int kb = 0;
         for (int s = 0; s < p.n_src; ++s) {
           const CUtensorMap* map = (s == 0) ? &map0 : (s == 1) ? &map1 : (s == 2) ? &map2 : &map3;
@@ -203,9 +222,9 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err);
             unsigned char* st = s_stage + (size_t)stage * p.stage_bytes;
             const uint32_t fb = smem_u32(&full_bar[stage]);
-            mbar_expect_tx(fb, TC_A_BYTES + (p.resident ? 0 : wblk_bytes));
-            tma_load_5d(smem_u32(st), map, fb, 0, x0 - 1, y0 - 1, 2 * b, ns);
-            if (!p.resident) bulk_load(smem_u32(st + TC_A_BYTES), p.wpacked + (size_t)kb * wblk_bytes, wblk_bytes, fb);
+            mbar_expect_tx(fb, p.a_bytes + (p.resident ? 0 : wblk_bytes));
+            tma_load_4d(smem_u32(st), map, fb, 8 * (x0 - HALO), y0 - HALO, 2 * b, ns);
+            if (!p.resident) bulk_load(smem_u32(st + p.a_bytes), p.wpacked + (size_t)kb * wblk_bytes, wblk_bytes, fb);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -228,19 +247,34 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
         const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.err);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_pad);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * J * p.n_pad);
+        // The issuing lane is a scalar instruction stream: keep it to ~3 instructions per MMA.  Descriptors
+        // differ only in the start-address field (16-byte units, low word): tap (kh, kw) and column block jj
+        // are compile-time offsets into the halo tile, the weight tap advances by a fixed stride.
+        constexpr uint32_t A_HI = (uint32_t)((BW * 16) >> 4) | (1u << 14);                 // SBO | version
+        constexpr uint32_t A_LBO_FIELD = (uint32_t)((BH * BW * 16) >> 4) << 16;             // LBO
+        const uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);
+        const uint32_t b_lbo_field = (uint32_t)((p.n_pad * 16) >> 4) << 16;
+        const uint32_t b_tap_step = (uint32_t)(2 * p.n_pad);                                // 16-byte units per tap
         for (int kb = 0; kb < p.kb_total; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase, p.err);
           tc_fence_after();
           unsigned char* st = s_stage + (size_t)stage * p.stage_bytes;
-          const uint32_t a_base = smem_u32(st);
-          const uint32_t b_base = p.resident ? smem_u32(s_w + (size_t)kb * wblk_bytes) : smem_u32(st + TC_A_BYTES);
+          const uint32_t a_lo0 = ((smem_u32(st) >> 4) & 0x3FFF) | A_LBO_FIELD;
+          const uint32_t b_base = p.resident ? smem_u32(s_w + (size_t)kb * wblk_bytes) : smem_u32(st + p.a_bytes);
+          uint32_t b_lo = ((b_base >> 4) & 0x3FFF) | b_lbo_field;
+          const uint32_t acc_first = (kb > 0) ? 1u : 0u;
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int kh = tap / 3, kw = tap - kh * 3;
-            const uint64_t adesc = make_desc(a_base + (uint32_t)(kh * TC_BW + kw) * 16, TC_A_LBO, TC_A_SBO);
-            const uint64_t bdesc = make_desc(b_base + (uint32_t)tap * 2 * p.n_pad * 16, (uint32_t)p.n_pad * 16, 128);
-            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > 0 || tap > 0) ? 1u : 0u);
+          for (int tap = 0; tap < TAPS; ++tap) {
+            const uint64_t bdesc = ((uint64_t)b_hi << 32) | b_lo;
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj) {
+              // consecutive MMAs target different accumulators (column blocks of the tile)
+              const uint64_t adesc =
+                  ((uint64_t)A_HI << 32) | (a_lo0 + (uint32_t)((TAPS == 9 ? (tap / 3) * BW + (tap % 3) : 0) + 8 * jj));
+              tc_mma_bf16(d_tmem + (uint32_t)(jj * p.n_pad), adesc, bdesc, idesc, tap == 0 ? acc_first : 1u);
+            }
+            b_lo += b_tap_step;
           }
           tc_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when these MMAs retire
           if (++stage == p.stages) {
@@ -257,44 +291,124 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     const int m = q * 32 + lane;         // accumulator row = pixel of the tile
     const int py = m >> 3, px = m & 7;
     const int n_chunks = p.n_pad >> 3;
+    // EPI_SOFTARGMAX: thread t reduces channel (t & 31) over pixel group (t >> 5) of every accumulator
+    const int et = threadIdx.x - 64;
+    const int ec = et & 31, eg = et >> 5;
+    float* s_logit = s_bias + 256;       // [128][TC_LOGIT_PITCH]
+    float st_m = -3.402823466e+38f, st_s = 0.f, st_sx = 0.f, st_sy = 0.f;
+    int cur_n = -1;
+    auto flush = [&](int n_img) {
+      // combine the 4 pixel groups of each channel and publish one partial per (image, channel, CTA)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float4* s_comb = reinterpret_cast<float4*>(s_logit);
+      s_comb[eg * 32 + ec] = make_float4(st_m, st_s, st_sx, st_sy);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (eg == 0 && ec < p.c_out) {
+        float M = -3.402823466e+38f;
+        for (int g = 0; g < 4; ++g) M = fmaxf(M, s_comb[g * 32 + ec].x);
+        float S = 0.f, SX = 0.f, SY = 0.f;
+        for (int g = 0; g < 4; ++g) {
+          const float4 v = s_comb[g * 32 + ec];
+          const float f = (v.x == -3.402823466e+38f) ? 0.f : __expf(v.x - M);
+          S += v.y * f;
+          SX += v.z * f;
+          SY += v.w * f;
+        }
+        p.partial[((size_t)n_img * p.c_out + ec) * gridDim.x + blockIdx.x] = make_float4(M, S, SX, SY);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
     long long it = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int n = (int)(tile / tiles_per_img);
       const int r = (int)(tile - (long long)n * tiles_per_img);
-      const int y = (r / p.tiles_x) * TC_TH + py, x = (r % p.tiles_x) * TC_TW + px;
+      const int y0 = (r / p.tiles_x) * TC_TH, x0 = (r % p.tiles_x) * 8 * J;
+      const int y = y0 + py, xb = x0 + px;
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      if (EPI == EPI_SOFTARGMAX && n != cur_n) {
+        if (cur_n >= 0) flush(cur_n);
+        st_m = -3.402823466e+38f;
+        st_s = st_sx = st_sy = 0.f;
+        cur_n = n;
+      }
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_pad);
-      const bool inb = (y < p.H) && (x < p.W);
-      for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_row + (uint32_t)c0, v);
-        float f[16];
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * J * p.n_pad);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          f[k] = __uint_as_float(v[k]) + __ldg(p.bias + c0 + k);
-          if (p.relu) f[k] = fmaxf(f[k], 0.f);
-        }
-        if (inb) {
+      for (int jj = 0; jj < J; ++jj) {
+        const int x = xb + 8 * jj;
+        const bool inb = (y < p.H) && (x < p.W);
+        for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_row + (uint32_t)(jj * p.n_pad + c0), v);
+          float f[16];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int chunk = (c0 >> 3) + h;
-            uint4 o;
-            o.x = pack_bf16(f[8 * h + 0], f[8 * h + 1]);
-            o.y = pack_bf16(f[8 * h + 2], f[8 * h + 3]);
-            o.z = pack_bf16(f[8 * h + 4], f[8 * h + 5]);
-            o.w = pack_bf16(f[8 * h + 6], f[8 * h + 7]);
-            __nv_bfloat16* dst = p.out + ((((size_t)n * n_chunks + chunk) * p.H + y) * p.W + x) * 8;
-            *reinterpret_cast<uint4*>(dst) = o;
+          for (int k = 0; k < 16; ++k) {
+            f[k] = __uint_as_float(v[k]) + s_bias[c0 + k];
+            if (p.relu) f[k] = fmaxf(f[k], 0.f);
           }
+          if (EPI == EPI_C8) {
+            if (inb) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int chunk = (c0 >> 3) + h;
+                uint4 o;
+                o.x = pack_bf16(f[8 * h + 0], f[8 * h + 1]);
+                o.y = pack_bf16(f[8 * h + 2], f[8 * h + 3]);
+                o.z = pack_bf16(f[8 * h + 4], f[8 * h + 5]);
+                o.w = pack_bf16(f[8 * h + 6], f[8 * h + 7]);
+                __nv_bfloat16* dst = p.out + ((((size_t)n * n_chunks + chunk) * p.H + y) * p.W + x) * 8;
+                *reinterpret_cast<uint4*>(dst) = o;
+              }
+            }
+          } else if (EPI == EPI_NCHW_F32) {
+            if (inb) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k)
+                if (c0 + k < p.c_out) p.out_f32[(((size_t)n * p.c_out + c0 + k) * p.H + y) * p.W + x] = f[k];
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) s_logit[m * TC_LOGIT_PITCH + c0 + k] = f[k];
+          }
+        }
+        if (EPI == EPI_SOFTARGMAX) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (ec < p.c_out) {
+            float vals[32];
+            float mx = -3.402823466e+38f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int pp = eg * 32 + i;
+              const bool ok = (y0 + (pp >> 3) < p.H) && (x0 + 8 * jj + (pp & 7) < p.W);
+              vals[i] = ok ? s_logit[pp * TC_LOGIT_PITCH + ec] : -3.402823466e+38f;
+              mx = fmaxf(mx, vals[i]);
+            }
+            if (mx > st_m) {
+              const float sc = (st_m == -3.402823466e+38f) ? 0.f : __expf(st_m - mx);
+              st_s *= sc;
+              st_sx *= sc;
+              st_sy *= sc;
+              st_m = mx;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int pp = eg * 32 + i;
+              const float e = (vals[i] == -3.402823466e+38f) ? 0.f : __expf(vals[i] - st_m);
+              st_s += e;
+              st_sx = fmaf(e, (float)(x0 + 8 * jj + (pp & 7)), st_sx);
+              st_sy = fmaf(e, (float)(y0 + (pp >> 3)), st_sy);
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
     }
+    if (EPI == EPI_SOFTARGMAX && cur_n >= 0) flush(cur_n);
   }
 
   tc_fence_before();
@@ -416,9 +530,9 @@ struct PackSrc {
   int n_src;
 };
 __global__ void __launch_bounds__(256)
-tc_pack_weights_kernel(const float* __restrict__ w, int C_out, int C_in, int n_pad, PackSrc ps, int kb_total,
+tc_pack_weights_kernel(const float* __restrict__ w, int C_out, int C_in, int n_pad, PackSrc ps, int kb_total, int taps,
                        __nv_bfloat16* __restrict__ out) {
-  const long long total = (long long)kb_total * 9 * 2 * n_pad * 8;
+  const long long total = (long long)kb_total * taps * 2 * n_pad * 8;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int k8 = (int)(t & 7);
     long long r = t >> 3;
@@ -426,8 +540,8 @@ tc_pack_weights_kernel(const float* __restrict__ w, int C_out, int C_in, int n_p
     r /= n_pad;
     const int c = (int)(r & 1);
     r >>= 1;
-    const int tap = (int)(r % 9);
-    const int kb = (int)(r / 9);
+    const int tap = (int)(r % taps);
+    const int kb = (int)(r / taps);
     int kpad = kb * 16 + c * 8 + k8;     // index in the padded concatenation
     int ci = -1, off_real = 0;
     for (int s = 0; s < ps.n_src; ++s) {
@@ -439,7 +553,7 @@ tc_pack_weights_kernel(const float* __restrict__ w, int C_out, int C_in, int n_p
       off_real += ps.real[s];
     }
     float v = 0.f;
-    if (ci >= 0 && n < C_out) v = w[((size_t)n * C_in + ci) * 9 + tap];
+    if (ci >= 0 && n < C_out) v = w[((size_t)n * C_in + ci) * taps + tap];
     out[t] = __float2bfloat16_rn(v);
   }
 }
@@ -474,6 +588,47 @@ c8_predictor_kernel(const uint4* __restrict__ x, int chunks, int C_in, long long
       }
     }
     for (int b = 0; b < C_out; ++b) out[((size_t)n * C_out + b) * S + i] = acc[b];
+  }
+}
+
+__global__ void __launch_bounds__(256) tc_partial_init_kernel(float4* __restrict__ part, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    part[i] = make_float4(-3.402823466e+38f, 0.f, 0.f, 0.f);
+}
+
+// one warp per (image, channel): combine the per-CTA partials, apply 1/(sum + 1e-6)  (softargmax.py:68)
+__global__ void __launch_bounds__(256)
+tc_partial_finalize_kernel(const float4* __restrict__ part, int rows, int slots, float* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float m = -3.402823466e+38f, sm = 0.f, sx = 0.f, sy = 0.f;
+  for (int i = lane; i < slots; i += 32) {
+    const float4 v = part[(size_t)row * slots + i];
+    const float M = fmaxf(m, v.x);
+    const float fa = (m == -3.402823466e+38f) ? 0.f : __expf(m - M);
+    const float fb = (v.x == -3.402823466e+38f) ? 0.f : __expf(v.x - M);
+    sm = sm * fa + v.y * fb;
+    sx = sx * fa + v.z * fb;
+    sy = sy * fa + v.w * fb;
+    m = M;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, sm, o);
+    const float x2 = __shfl_xor_sync(0xffffffffu, sx, o), y2 = __shfl_xor_sync(0xffffffffu, sy, o);
+    const float M = fmaxf(m, m2);
+    const float fa = (m == -3.402823466e+38f) ? 0.f : __expf(m - M);
+    const float fb = (m2 == -3.402823466e+38f) ? 0.f : __expf(m2 - M);
+    sm = sm * fa + s2 * fb;
+    sx = sx * fa + x2 * fb;
+    sy = sy * fa + y2 * fb;
+    m = M;
+  }
+  if (lane == 0) {
+    const float inv = 1.0f / (sm + 1e-6f);
+    out[2 * row + 0] = sx * inv;
+    out[2 * row + 1] = sy * inv;
   }
 }
 
@@ -573,18 +728,19 @@ int ynet_tc_predictor_f32(const void* x_c8, int32_t N, int32_t C_pad, int32_t C_
   return YNET_OK;
 }
 
-int64_t ynet_tc_packed_weight_bytes(int32_t C_out, int32_t n_src, const int32_t* src_channels_pad_host) {
-  if (C_out <= 0 || n_src <= 0 || n_src > YNET_MAX_SOURCES || !src_channels_pad_host) return 0;
+int64_t ynet_tc_packed_weight_bytes(int32_t C_out, int32_t n_src, const int32_t* src_channels_pad_host, int32_t ksize) {
+  if (C_out <= 0 || n_src <= 0 || n_src > YNET_MAX_SOURCES || !src_channels_pad_host || (ksize != 1 && ksize != 3))
+    return 0;
   const int n_pad = ceil_div(C_out, 16) * 16;
   long long kb = 0;
   for (int i = 0; i < n_src; ++i) kb += src_channels_pad_host[i] / 16;
-  return kb * 9 * 2 * n_pad * 16;
+  return kb * ksize * ksize * 2 * n_pad * 16;
 }
 
 int ynet_tc_pack_weights(const float* weight, int32_t C_out, int32_t n_src, const int32_t* src_channels_host,
-                         const int32_t* src_channels_pad_host, void* packed, void* stream) {
+                         const int32_t* src_channels_pad_host, int32_t ksize, void* packed, void* stream) {
   YNET_CHECK_ARG(weight && packed && src_channels_host && src_channels_pad_host, "null pointer");
-  YNET_CHECK_ARG(C_out > 0 && n_src >= 1 && n_src <= YNET_MAX_SOURCES, "bad shape");
+  YNET_CHECK_ARG(C_out > 0 && n_src >= 1 && n_src <= YNET_MAX_SOURCES && (ksize == 1 || ksize == 3), "bad shape");
   PackSrc ps;
   memset(&ps, 0, sizeof(ps));
   ps.n_src = n_src;
@@ -599,48 +755,109 @@ int ynet_tc_pack_weights(const float* weight, int32_t C_out, int32_t n_src, cons
     kb += src_channels_pad_host[i] / 16;
   }
   const int n_pad = ceil_div(C_out, 16) * 16;
-  const long long total = (long long)kb * 9 * 2 * n_pad * 8;
-  tc_pack_weights_kernel<<<grid_1d(total), 256, 0, as_stream(stream)>>>(weight, C_out, cin, n_pad, ps, kb,
+  const int taps = ksize * ksize;
+  const long long total = (long long)kb * taps * 2 * n_pad * 8;
+  tc_pack_weights_kernel<<<grid_1d(total), 256, 0, as_stream(stream)>>>(weight, C_out, cin, n_pad, ps, kb, taps,
                                                                         reinterpret_cast<__nv_bfloat16*>(packed));
   YNET_LAUNCH_CHECK();
   return YNET_OK;
 }
 
-int ynet_tc_conv3x3(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int32_t H, int32_t W, const void* packed_weight,
-                    const float* bias, int32_t C_out, int32_t relu, void* out_c8, int32_t C_out_pad, void* stream) {
-  YNET_CHECK_ARG(srcs && packed_weight && bias && out_c8, "null pointer");
-  YNET_CHECK_ARG(n_src >= 1 && n_src <= YNET_MAX_SOURCES && N >= 0 && H > 0 && W > 0, "bad shape");
-  YNET_CHECK_ARG(C_out > 0 && C_out_pad % 16 == 0 && C_out_pad >= C_out && C_out_pad <= 256, "C_out_pad must be a multiple of 16, <= 256");
-  YNET_CHECK_ALIGN(out_c8, 16);
-  YNET_CHECK_ALIGN(packed_weight, 16);
+}  // extern "C"
+
+namespace ynet {
+
+struct TcOut {
+  void* c8;
+  float* f32;
+  float4* partial;
+};
+
+template <int TAPS, int EPI>
+static cudaError_t tc_configure() {
+  cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<1, TAPS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tc_conv_kernel<2, TAPS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tc_conv_kernel<3, TAPS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  return e;
+}
+
+template <int TAPS, int EPI>
+static void tc_dispatch(int j, unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap* maps, const TcParams& p) {
+  if (j == 1)
+    tc_conv_kernel<1, TAPS, EPI><<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  else if (j == 2)
+    tc_conv_kernel<2, TAPS, EPI><<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  else
+    tc_conv_kernel<3, TAPS, EPI><<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+}
+
+// Shared launcher of the tcgen05 conv kernel.  taps = 9 (3x3, padding 1) or 1 (1x1); epi = EPI_*.
+static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N, int H, int W, const void* packed_weight,
+                     const float* bias, int C_out, int relu, int C_out_pad, int tune, int taps, int epi, TcOut out,
+                     int* grid_out, void* stream) {
+  if (!(srcs && packed_weight && bias)) {
+    set_error("%s: null pointer", who);
+    return YNET_E_INVALID;
+  }
+  if (!(n_src >= 1 && n_src <= YNET_MAX_SOURCES && N >= 0 && H > 0 && W > 0 && C_out > 0 && C_out_pad % 16 == 0 &&
+        C_out_pad >= C_out && C_out_pad <= 256)) {
+    set_error("%s: bad shape (C_out_pad must be a multiple of 16, <= 256)", who);
+    return YNET_E_INVALID;
+  }
+  if (reinterpret_cast<uintptr_t>(packed_weight) % 16 != 0) {
+    set_error("%s: packed_weight not 16-byte aligned", who);
+    return YNET_E_ALIGN;
+  }
   if (N == 0) return YNET_OK;
   EncodeTiledFn encode = get_encode();
   if (encode == nullptr) {
-    set_error("ynet_tc_conv3x3: cuTensorMapEncodeTiled is not available from the driver");
+    set_error("%s: cuTensorMapEncodeTiled is not available from the driver", who);
     return YNET_E_UNSUPPORTED;
   }
   TcParams p;
   memset(&p, 0, sizeof(p));
+  const int halo = (taps == 9) ? 1 : 0;
+  // accumulators per tile: independent MMA chains, bounded by double-buffered TMEM (512 columns)
+  const int j_cap = tmax(1, tmin(TC_MAX_J, 512 / (2 * C_out_pad)));
+  int j = tmin(j_cap, ceil_div(W, 8));
+  if (const char* e = getenv("YNET_TC_J")) j = tmin(j_cap, atoi(e));
+  if (tune & 0xF) j = tmin(j_cap, tune & 0xF);
+  j = tmax(1, j);
+  p.j = j;
+  p.bw = 8 * j + 2 * halo;
+  const int bh = TC_TH + 2 * halo;
+  p.a_bytes = bh * p.bw * TC_KB * 2;
+  p.a_lbo = bh * p.bw * 16;
+  p.a_sbo = p.bw * 16;
   CUtensorMap maps[YNET_MAX_SOURCES];
   memset(maps, 0, sizeof(maps));
   int kb_total = 0;
   for (int i = 0; i < n_src; ++i) {
     const int cp = srcs[i].channels_pad;
-    YNET_CHECK_ARG(srcs[i].ptr && cp > 0 && cp % 16 == 0, "source channels_pad must be a positive multiple of 16");
-    YNET_CHECK_ALIGN(srcs[i].ptr, 16);
+    if (!(srcs[i].ptr && cp > 0 && cp % 16 == 0) || reinterpret_cast<uintptr_t>(srcs[i].ptr) % 16 != 0) {
+      set_error("%s: source %d must be 16-byte aligned with channels_pad a positive multiple of 16", who, i);
+      return YNET_E_INVALID;
+    }
     const bool bcast = srcs[i].batch_stride == 0;
     const int nsrc = bcast ? 1 : (srcs[i].batch_mod > 0 ? srcs[i].batch_mod : N);
-    const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(cp / 8), (cuuint64_t)nsrc};
+    // A pixel row of one 8-channel chunk is W*8 contiguous bf16: that is the innermost TMA dimension, so one
+    // box row is ONE (8J+2)*16-byte request instead of 8J+2 sixteen-byte ones.
+    const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)(cp / 8), (cuuint64_t)nsrc};
     const cuuint64_t bs = bcast ? (cuuint64_t)(cp / 8) * H * W * 16 : (cuuint64_t)srcs[i].batch_stride * 2;
-    YNET_CHECK_ARG(bs % 16 == 0, "batch stride must be a multiple of 8 elements");
-    const cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, bs};
-    const cuuint32_t box[5] = {8, TC_BW, TC_BH, 2, 1};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(srcs[i].ptr), dims, strides, box,
+    if (bs % 16 != 0) {
+      set_error("%s: batch stride must be a multiple of 8 elements", who);
+      return YNET_E_ALIGN;
+    }
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, bs};
+    const cuuint32_t box[4] = {(cuuint32_t)p.bw * 8, (cuuint32_t)bh, 2, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(srcs[i].ptr), dims, strides, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-      set_error("ynet_tc_conv3x3: cuTensorMapEncodeTiled failed (%d) for source %d (W=%d H=%d C=%d)", (int)r, i, W, H, cp);
+      set_error("%s: cuTensorMapEncodeTiled failed (%d) for source %d (W=%d H=%d C=%d)", who, (int)r, i, W, H, cp);
       return YNET_E_CUDA;
     }
     p.src[i].kblocks = cp / 16;
@@ -654,42 +871,122 @@ int ynet_tc_conv3x3(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int32_t H
   p.H = H;
   p.W = W;
   p.n_pad = C_out_pad;
+  p.c_out = C_out;
   p.relu = relu;
-  p.tiles_x = ceil_div(W, TC_TW);
+  p.tiles_x = ceil_div(W, 8 * p.j);
   p.tiles_y = ceil_div(H, TC_TH);
   p.total_tiles = (long long)N * p.tiles_x * p.tiles_y;
   p.kb_total = kb_total;
   p.wpacked = reinterpret_cast<const unsigned char*>(packed_weight);
   p.bias = bias;
-  p.out = reinterpret_cast<__nv_bfloat16*>(out_c8);
+  p.out = reinterpret_cast<__nv_bfloat16*>(out.c8);
+  p.out_f32 = out.f32;
+  p.partial = out.partial;
   p.err = nullptr;
 
-  const int wblk = 9 * 2 * C_out_pad * 16;
+  const int wblk = taps * 2 * C_out_pad * 16;
   const long long wall = (long long)kb_total * wblk;
   const int budget = 200 * 1024;
-  const int tail = (2 * TC_MAX_STAGES + 5) * 8 + 16;
+  const int tail = (2 * TC_MAX_STAGES + 5) * 8 + 16 + 256 * 4 + (epi == EPI_SOFTARGMAX ? 128 * TC_LOGIT_PITCH * 4 : 0);
   const char* force_stream = getenv("YNET_TC_FORCE_STREAMED");
-  p.resident = (wall + 4 * TC_A_BYTES + tail <= budget) && !(force_stream && force_stream[0] == '1');
+  p.resident = (wall + 4 * p.a_bytes + tail <= budget) && !(force_stream && force_stream[0] == '1');
   p.wres_bytes = p.resident ? (int)ceil_div<long long>(wall, 1024) * 1024 : 0;
-  p.stage_bytes = ceil_div(TC_A_BYTES + (p.resident ? 0 : wblk), 128) * 128;
-  p.stages = tmin(TC_MAX_STAGES, (budget - p.wres_bytes - tail) / p.stage_bytes);
+  p.stage_bytes = ceil_div(p.a_bytes + (p.resident ? 0 : wblk), 128) * 128;
+  int max_stages = 6;   // measured: depth beyond ~4 does not matter; small rings let two CTAs share an SM
+  if (const char* e = getenv("YNET_TC_STAGES")) max_stages = tmax(2, tmin(TC_MAX_STAGES, atoi(e)));
+  if ((tune >> 8) & 0xFF) max_stages = tmax(2, tmin(TC_MAX_STAGES, (tune >> 8) & 0xFF));
+  p.stages = tmin(max_stages, (budget - p.wres_bytes - tail) / p.stage_bytes);
   if (p.stages < 2) {
-    set_error("ynet_tc_conv3x3: layer does not fit shared memory (C_out_pad=%d)", C_out_pad);
+    set_error("%s: layer does not fit shared memory (C_out_pad=%d)", who, C_out_pad);
     return YNET_E_UNSUPPORTED;
   }
   int cols = 32;
-  while (cols < 2 * C_out_pad) cols *= 2;
+  while (cols < 2 * p.j * C_out_pad) cols *= 2;
   p.tmem_cols = cols;
   const size_t smem_bytes = (size_t)p.wres_bytes + (size_t)p.stages * p.stage_bytes + tail + 1024;
 
-  static size_t configured = 0;
-  if (smem_bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return cuda_fail(e, "ynet_tc_conv3x3(cudaFuncSetAttribute)");
-    configured = 227 * 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = tc_configure<9, EPI_C8>();
+    if (e == cudaSuccess) e = tc_configure<1, EPI_NCHW_F32>();
+    if (e == cudaSuccess) e = tc_configure<1, EPI_SOFTARGMAX>();
+    if (e != cudaSuccess) return cuda_fail(e, "tc_launch(cudaFuncSetAttribute)");
+    configured = true;
   }
-  const long long grid = tmin<long long>(p.total_tiles, sm_count());
-  tc_conv3x3_kernel<<<(unsigned)grid, TC_THREADS, smem_bytes, as_stream(stream)>>>(maps[0], maps[1], maps[2], maps[3], p);
+  int ctas_per_sm = (smem_bytes <= 110 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
+  if (const char* e = getenv("YNET_TC_CTAS_PER_SM")) ctas_per_sm = tmax(1, tmin(2, atoi(e)));
+  if ((tune >> 4) & 0xF) ctas_per_sm = tmin(ctas_per_sm, tmax(1, (tune >> 4) & 0xF));
+  long long grid = tmin<long long>(p.total_tiles, (long long)sm_count() * ctas_per_sm);
+  if (grid_out != nullptr) {
+    if (*grid_out > 0) grid = tmin<long long>(grid, *grid_out);   // caller sized its partial buffer for this many CTAs
+    *grid_out = (int)grid;
+  }
+  cudaStream_t st = as_stream(stream);
+  if (taps == 9 && epi == EPI_C8)
+    tc_dispatch<9, EPI_C8>(p.j, (unsigned)grid, smem_bytes, st, maps, p);
+  else if (taps == 1 && epi == EPI_NCHW_F32)
+    tc_dispatch<1, EPI_NCHW_F32>(p.j, (unsigned)grid, smem_bytes, st, maps, p);
+  else if (taps == 1 && epi == EPI_SOFTARGMAX)
+    tc_dispatch<1, EPI_SOFTARGMAX>(p.j, (unsigned)grid, smem_bytes, st, maps, p);
+  else {
+    set_error("%s: unsupported (taps, epilogue) combination", who);
+    return YNET_E_UNSUPPORTED;
+  }
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) return cuda_fail(le, who);
+  return YNET_OK;
+}
+
+}  // namespace ynet
+
+extern "C" {
+
+int ynet_tc_conv3x3(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int32_t H, int32_t W, const void* packed_weight,
+                    const float* bias, int32_t C_out, int32_t relu, void* out_c8, int32_t C_out_pad, int32_t tune,
+                    void* stream) {
+  YNET_CHECK_ARG(out_c8 != nullptr || N == 0, "null output");
+  YNET_CHECK_ALIGN(out_c8, 16);
+  TcOut o{out_c8, nullptr, nullptr};
+  return tc_launch("ynet_tc_conv3x3", srcs, n_src, N, H, W, packed_weight, bias, C_out, relu, C_out_pad, tune, 9, EPI_C8, o,
+                   nullptr, stream);
+}
+
+int ynet_tc_conv1x1_f32(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int32_t H, int32_t W, const void* packed_weight,
+                        const float* bias, int32_t C_out, float* out, int32_t tune, void* stream) {
+  YNET_CHECK_ARG(out != nullptr || N == 0, "null output");
+  TcOut o{nullptr, out, nullptr};
+  return tc_launch("ynet_tc_conv1x1_f32", srcs, n_src, N, H, W, packed_weight, bias, C_out, 0, ceil_div(C_out, 16) * 16, tune,
+                   1, EPI_NCHW_F32, o, nullptr, stream);
+}
+
+int64_t ynet_tc_conv1x1_softargmax_workspace_bytes(int32_t N, int32_t C_out) {
+  return (int64_t)N * C_out * 2 * sm_count() * (int64_t)sizeof(float4);
+}
+
+int ynet_tc_conv1x1_softargmax(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int32_t H, int32_t W,
+                               const void* packed_weight, const float* bias, int32_t C_out, float* out, void* workspace,
+                               int64_t workspace_bytes, int32_t tune, void* stream) {
+  YNET_CHECK_ARG(out != nullptr || N == 0, "null output");
+  YNET_CHECK_ARG(C_out > 0 && C_out <= 32, "C_out must be <= 32 for the fused soft-argmax epilogue");
+  if (N == 0) return YNET_OK;
+  if (workspace == nullptr || workspace_bytes < ynet_tc_conv1x1_softargmax_workspace_bytes(N, C_out)) {
+    set_error("ynet_tc_conv1x1_softargmax: workspace too small");
+    return YNET_E_WORKSPACE;
+  }
+  YNET_CHECK_ALIGN(workspace, 16);
+  float4* part = reinterpret_cast<float4*>(workspace);
+  const int slots = 2 * sm_count();
+  const long long n_part = (long long)N * C_out * slots;
+  tc_partial_init_kernel<<<grid_1d(n_part), 256, 0, as_stream(stream)>>>(part, n_part);
+  YNET_LAUNCH_CHECK();
+  // the kernel indexes partials with gridDim.x slots per (image, channel): pin the slot count
+  int grid = slots;
+  TcOut o{nullptr, nullptr, part};
+  // run with exactly `grid` (<= slots) CTAs; the finalize pass reads `grid` slots per row
+  int rc = tc_launch("ynet_tc_conv1x1_softargmax", srcs, n_src, N, H, W, packed_weight, bias, C_out, 0,
+                     ceil_div(C_out, 16) * 16, tune, 1, EPI_SOFTARGMAX, o, &grid, stream);
+  if (rc != YNET_OK) return rc;
+  tc_partial_finalize_kernel<<<ceil_div(N * C_out, 8), 256, 0, as_stream(stream)>>>(part, N * C_out, grid, out);
   YNET_LAUNCH_CHECK();
   return YNET_OK;
 }

@@ -229,8 +229,14 @@ class YNetEngineTC(YNetEngine):
 
     def decoder_logits(self, decoder, key, features):
         x = self.decoder_trunk(decoder, key, features)
-        p = decoder.predictor
-        return ops.tc_predictor_f32(x, p.weight.detach().reshape(p.weight.shape[0], -1), p.bias.detach())
+        packed, bias = self._tc_params(decoder.predictor, f'{key}.predictor', [x.C])
+        return ops.tc_conv1x1_f32(x, packed, bias, decoder.predictor.weight.shape[0])
 
     def decoder_softargmax(self, decoder, key, features):
-        return ops.softargmax2d(self.decoder_logits(decoder, key, features))
+        """predictor + SoftArgmax2D fused into the tensor-core kernel's epilogue (logits never reach HBM)."""
+        x = self.decoder_trunk(decoder, key, features)
+        p = decoder.predictor
+        if p.weight.shape[0] > 32:
+            return ops.softargmax2d(self.decoder_logits(decoder, key, features))
+        packed, bias = self._tc_params(p, f'{key}.predictor', [x.C])
+        return ops.tc_conv1x1_softargmax(x, packed, bias, p.weight.shape[0])

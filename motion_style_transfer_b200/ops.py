@@ -4,6 +4,7 @@ torch is plumbing only: it owns device memory and the stream; every computation 
 into libynet_b200.so with raw pointers.  Nothing here runs on the CPU -- CPU tensors are rejected.
 """
 import ctypes
+import os
 
 import torch
 
@@ -613,17 +614,53 @@ def tc_upsample(a):
 
 
 def tc_pack_weights(weight_oihw, src_channels):
-    """Effective OIHW float32 weight -> bf16 [kb][tap][2][C_out_pad][8] over per-source padded channels."""
+    """Effective OIHW float32 weight (3x3 or 1x1) -> bf16 [kb][tap][2][C_out_pad][8] over per-source padded channels."""
     weight_oihw = _req(weight_oihw, name='weight')
-    C_out = weight_oihw.shape[0]
+    C_out, ksize = weight_oihw.shape[0], weight_oihw.shape[2]
     n = len(src_channels)
     real = (ctypes.c_int32 * n)(*src_channels)
     pad = (ctypes.c_int32 * n)(*[_pad16(c) for c in src_channels])
-    nbytes = _L().ynet_tc_packed_weight_bytes(C_out, n, pad)
+    nbytes = _L().ynet_tc_packed_weight_bytes(C_out, n, pad, ksize)
     packed = torch.empty(nbytes, dtype=torch.uint8, device=weight_oihw.device)
-    check(_L().ynet_tc_pack_weights(_ptr(weight_oihw), C_out, n, real, pad, _ptr(packed), _stream()), 'tc_pack_weights')
+    check(_L().ynet_tc_pack_weights(_ptr(weight_oihw), C_out, n, real, pad, ksize, _ptr(packed), _stream()),
+          'tc_pack_weights')
     _count()
     return packed
+
+
+def _tc_src_array(sources, N):
+    arr = (_lib.TcSrc * len(sources))()
+    for i, s in enumerate(sources):
+        arr[i].ptr = s.data.data_ptr()
+        arr[i].channels_pad = s.C_pad
+        arr[i].batch_stride = 0 if (s.N == 1 and N > 1) else s.data.stride(0)
+        arr[i].batch_mod = s.N if (1 < s.N < N) else 0
+    return arr
+
+
+def tc_conv1x1_f32(a, packed_weight, bias_pad, C_out):
+    """1x1 predictor on the tensor cores -> float32 NCHW logits."""
+    out = torch.empty(a.N, C_out, a.H, a.W, dtype=torch.float32, device=a.data.device)
+    arr = _tc_src_array([a], a.N)
+    with _timed('tc_conv_kernel<1x1,f32>', 2.0 * a.C * C_out * a.H * a.W * a.N,
+                (2.0 * a.C_pad + 4.0 * C_out) * a.H * a.W * a.N):
+        check(_L().ynet_tc_conv1x1_f32(arr, 1, a.N, a.H, a.W, _ptr(packed_weight), _ptr(bias_pad), C_out, _ptr(out), 0,
+                                       _stream()), 'tc_conv1x1_f32')
+    _count()
+    return out
+
+
+def tc_conv1x1_softargmax(a, packed_weight, bias_pad, C_out):
+    """1x1 predictor + SoftArgmax2D fused on the tensor-core kernel: C8 activation -> (N, C_out, 2)."""
+    out = torch.empty(a.N, C_out, 2, dtype=torch.float32, device=a.data.device)
+    nb = _L().ynet_tc_conv1x1_softargmax_workspace_bytes(a.N, C_out)
+    ws = _workspace(nb, a.data.device, 'tc_softargmax')
+    arr = _tc_src_array([a], a.N)
+    with _timed('tc_conv_kernel<1x1,softargmax>', 2.0 * a.C * C_out * a.H * a.W * a.N, 2.0 * a.C_pad * a.H * a.W * a.N):
+        check(_L().ynet_tc_conv1x1_softargmax(arr, 1, a.N, a.H, a.W, _ptr(packed_weight), _ptr(bias_pad), C_out,
+                                              _ptr(out), _ptr(ws), ws.numel(), 0, _stream()), 'tc_conv1x1_softargmax')
+    _count(3)
+    return out
 
 
 def tc_conv3x3(sources, packed_weight, bias_pad, C_out, relu):
@@ -643,12 +680,48 @@ def tc_conv3x3(sources, packed_weight, bias_pad, C_out, relu):
     cp = _pad16(C_out)
     out = torch.empty(N, cp // 8, H, W, 8, dtype=torch.bfloat16, device=sources[0].data.device)
     cin_pad = sum(s.C_pad for s in sources)
+    args = (arr, len(sources), N, H, W, _ptr(packed_weight), _ptr(bias_pad), C_out, 1 if relu else 0, _ptr(out), cp)
+    key = (tuple(s.C_pad for s in sources), cp, H, W, min(N, 64))
+    tune = _tc_tune.get(key)
+    if tune is None:
+        tune = _tc_autotune(key, args) if (tc_autotune_enabled and not torch.cuda.is_current_stream_capturing()) else 0
     with _timed('tc_conv3x3_kernel', 2.0 * 9 * sum(s.C for s in sources) * C_out * H * W * N,
                 2.0 * (cin_pad + cp) * H * W * N, tag=f'{cin_pad}->{cp}@{H}x{W} N={N}'):
-        check(_L().ynet_tc_conv3x3(arr, len(sources), N, H, W, _ptr(packed_weight), _ptr(bias_pad), C_out,
-                                   1 if relu else 0, _ptr(out), cp, _stream()), 'tc_conv3x3')
+        check(_L().ynet_tc_conv3x3(*args, tune, _stream()), 'tc_conv3x3')
     _count()
     return C8(out, C_out)
+
+
+tc_autotune_enabled = os.environ.get('YNET_TC_AUTOTUNE', '1') != '0'
+_tc_tune = {}
+
+
+def _tc_autotune(key, args):
+    """Pick (accumulators per tile, CTAs per SM, stages) for one layer shape by timing the candidates once."""
+    cp = key[1]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cands = [j | (ctas << 4) | (stages << 8) for j in (1, 2, 3) if j <= max(1, 512 // (2 * cp))
+             for ctas in (2, 1) for stages in (6, 3)]
+
+    def run(tune, reps):
+        e0.record()
+        for _ in range(reps):
+            check(_L().ynet_tc_conv3x3(*args, tune, _stream()), 'tc_conv3x3(autotune)')
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # bring the SM clocks up first: timing the first candidates on an idle GPU would bias the choice
+    spent = 0.0
+    while spent < 40.0:
+        spent += run(0, 4) * 4
+    times = {t: float('inf') for t in cands}
+    for _ in range(2):
+        for t in cands:
+            times[t] = min(times[t], run(t, 3))
+    best = min(times, key=times.get)
+    _tc_tune[key] = best
+    return best
 
 
 def tc_predictor_f32(a, weight, bias):

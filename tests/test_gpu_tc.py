@@ -127,3 +127,25 @@ def test_forecast_bf16_sdd_short(ops):
     assert rel_err(res['goal_map'].cpu().numpy(), g['goal_map']) < 3e-2
     # ADE is a soft-argmax expectation: robust to bf16; FDE depends on sampled goal pixels (top-k of p/q)
     np.testing.assert_allclose(res['ade'].cpu().numpy(), g['ade'], rtol=0, atol=0.25)
+
+
+@pytest.mark.parametrize('cin,cout,H,W,N', [(32, 30, 64, 96, 3), (32, 12, 416, 416, 2), (8, 6, 52, 40, 2)])
+def test_tc_predictor_logits_and_fused_softargmax(ops, cin, cout, H, W, N):
+    """1x1 predictor on the tensor cores: float32 logits, and the fused predictor + soft-argmax epilogue."""
+    torch.manual_seed(3)
+    x = bf16_exact(torch.relu(torch.randn(N, cin, H, W)))
+    w = bf16_exact(torch.randn(cout, cin, 1, 1) * 0.5)
+    b = torch.randn(cout)
+    ref = F.conv2d(x, w, b)
+    a = ops.tc_pack(x.cuda())
+    packed = ops.tc_pack_weights(w.cuda(), [cin])
+    bias = torch.zeros((cout + 15) // 16 * 16)
+    bias[:cout] = b
+    logits = ops.tc_conv1x1_f32(a, packed, bias.cuda(), cout).cpu()
+    assert rel_err(logits.numpy(), ref.numpy()) < 1e-4          # fp32 accumulate of bf16-exact operands, fp32 out
+    sa = ops.tc_conv1x1_softargmax(a, packed, bias.cuda(), cout).cpu().numpy()
+    np.testing.assert_allclose(sa, O.softargmax2d(ref).numpy(), rtol=0, atol=5e-3)
+    # peaky logits (what TTST sees after training): scale the predictor
+    packed50 = ops.tc_pack_weights((w * 8).cuda(), [cin])
+    sa50 = ops.tc_conv1x1_softargmax(a, packed50, (bias * 8).cuda(), cout).cpu().numpy()
+    np.testing.assert_allclose(sa50, O.softargmax2d(F.conv2d(x, w * 8, b * 8)).numpy(), rtol=0, atol=2e-2)

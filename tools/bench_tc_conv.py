@@ -1,0 +1,41 @@
+"""Micro-benchmark of the tensor-core conv kernel on the dominant Y-Net layer shapes (CUDA events)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from motion_style_transfer_b200 import ops  # noqa: E402
+
+SHAPES = [  # (source channels, C_out, H, W)
+    ((16, 32, 2), 32, 416, 416), ((64,), 32, 416, 416), ((16, 32, 16), 32, 416, 416), ((32,), 32, 416, 416), ((32,), 16, 416, 416), ((32, 32, 2), 32, 208, 208),
+    ((64,), 32, 208, 208), ((32, 64, 2), 64, 104, 104), ((64,), 64, 104, 104), ((130,), 130, 13, 13),
+]
+N = int(os.environ.get('N', 64))
+torch.manual_seed(0)
+print(f'env: CTAS_PER_SM={os.environ.get("YNET_TC_CTAS_PER_SM")} STAGES={os.environ.get("YNET_TC_STAGES")} '
+      f'J={os.environ.get("YNET_TC_J")} N={N}')
+_w = torch.randn(4096, 4096, device='cuda')
+for _ in range(20):
+    _w @ _w          # clock warm-up
+torch.cuda.synchronize()
+for cins, cout, H, W in SHAPES:
+    srcs = [ops.tc_pack(torch.randn(N, c, H, W, device='cuda')) for c in cins]
+    w = torch.randn(cout, sum(cins), 3, 3, device='cuda') * 0.1
+    packed = ops.tc_pack_weights(w, list(cins))
+    bias = torch.zeros((cout + 15) // 16 * 16, device='cuda')
+    for _ in range(10):
+        ops.tc_conv3x3(srcs, packed, bias, cout, True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        out = ops.tc_conv3x3(srcs, packed, bias, cout, True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    fl = 2.0 * 9 * sum(cins) * cout * H * W * N
+    cin_pad = sum((c + 15) // 16 * 16 for c in cins)
+    by = 2.0 * (cin_pad + (cout + 15) // 16 * 16) * H * W * N
+    print(f'{str(cins):>14} -> {cout:3d} @{H:3d}  {ms:8.3f} ms  {fl / ms / 1e9:7.1f} TF/s  {by / ms / 1e6:7.1f} GB/s')
