@@ -164,6 +164,8 @@ def main():
     ap.add_argument('--cpu-agents', type=int, default=4, help='agents of the bounded cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-layers', default=None, help='write a per-layer timing table to this path')
+    ap.add_argument('--no-graph', dest='graph', action='store_false',
+                    help='issue every kernel from Python instead of replaying the captured CUDA graph')
     ap.add_argument('--backend', default='bf16', choices=['bf16', 'fp32'],
                     help='bf16 = tcgen05 tensor-core engine (default), fp32 = CUDA-core reference-grade engine')
     args = ap.parse_args()
@@ -198,10 +200,23 @@ def main():
     traj_dev = [t.to(dev) for t in traj_host]
     scene_dev = scene_host.to(dev)
     rng = DeviceRng(seed=1234 + rank)
+    launches_per_step = None
+    if args.graph:
+        # the ~450 launches of one batch are captured once and replayed (utils/evaluate.py::GraphedForecaster)
+        from motion_style_transfer_b200.utils.evaluate import GraphedForecaster
+        gf = GraphedForecaster(model, tmpl, tuple(scene_dev.shape), tuple(traj_dev[0].shape), cfg['wps'], cfg['n_goal'],
+                               cfg['n_traj'], cfg['obs'], cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'],
+                               cfg['cwsp'], seed=1234 + rank)
+        l0 = ops.launch_count
+        gf.capture(scene_dev, traj_dev[0])
+        launches_per_step = (ops.launch_count - l0) // 3          # 2 eager warm-ups + the captured pass
 
-    def step(scene, traj):
-        return forecast_batch(model, scene, traj, tmpl, cfg['wps'], cfg['n_goal'], cfg['n_traj'], cfg['obs'],
-                              cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'], cfg['cwsp'], rng=rng)
+        def step(scene, traj):
+            return gf(scene, traj)
+    else:
+        def step(scene, traj):
+            return forecast_batch(model, scene, traj, tmpl, cfg['wps'], cfg['n_goal'], cfg['n_traj'], cfg['obs'],
+                                  cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'], cfg['cwsp'], rng=rng)
 
     def barrier():
         if world > 1:
@@ -222,15 +237,30 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = ops.launch_count
     t_wall0 = time.time()
+    from motion_style_transfer_b200.utils import kmeans as km_mod
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks, km_iters, host_ms = [], [], []
+    mem0 = torch.cuda.memory_stats(dev)
     e0.record()
     for it in range(args.warmup, n_iter):
+        th = time.perf_counter()
         res = step(scene_dev, traj_dev[it])
+        host_ms.append(1000 * (time.perf_counter() - th))
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append(ev)
+        km_iters.append(km_mod.last_iters)
     e1.record()
     barrier()
     t_wall1 = time.time()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = ops.launch_count - launches0
+    step_list = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+    km_diag = [int(k.max().item()) for k in km_iters if k is not None]
+    mem1 = torch.cuda.memory_stats(dev)
+    mem_diag = {k: mem1.get(k, 0) - mem0.get(k, 0) for k in ('num_alloc_retries', 'num_device_alloc', 'num_device_free')}
+    mem_diag['reserved_gb'] = mem1.get('reserved_bytes.all.peak', 0) / 2 ** 30
+    mem_diag['allocated_peak_gb'] = mem1.get('allocated_bytes.all.peak', 0) / 2 ** 30
+    launches = (ops.launch_count - launches0) if launches_per_step is None else launches_per_step * args.steps
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     ms_step = ms_total / args.steps
     traj_per_step = world * B * cfg['n_goal'] * cfg['n_traj']
@@ -239,12 +269,17 @@ def main():
     # ---- end to end through the public call with HOST buffers (H2D of inputs + D2H of metrics inside) -----
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_marks, e2e_km = [], []
     e2.record()
     for it in range(args.warmup, n_iter):
         sc = scene_host.to(dev, non_blocking=True)
         tr = traj_host[it].to(dev, non_blocking=True)
         r = step(sc, tr)
         ade_h, fde_h = r['ade'].cpu(), r['fde'].cpu()
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        e2e_marks.append(ev)
+        e2e_km.append(int(km_mod.last_iters.max().item()) if km_mod.last_iters is not None else None)
     e3.record()
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3)) / args.steps
@@ -256,8 +291,9 @@ def main():
     roofline, layer_table = None, None
     if rank == 0:
         peaks = load_peaks()
-        ops.profile_begin()
-        step(scene_dev, traj_dev[-1])
+        ops.profile_begin()       # eager pass (not the graph): per-launch CUDA events
+        forecast_batch(model, scene_dev, traj_dev[-1], tmpl, cfg['wps'], cfg['n_goal'], cfg['n_traj'], cfg['obs'],
+                       cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'], cfg['cwsp'], rng=rng)
         prof = ops.profile_end()
         layer_table = prof
         if prof:
@@ -310,13 +346,16 @@ def main():
             'metric': 'agent-trajectories/sec', 'value': value, 'unit': 'agent-trajectories/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': model.engine.backend_dtype(), 'data': 'synthetic',
-            'config': {'workload': workload_name(args, cfg), 'agents_per_gpu_per_step': B,
+            'config': {'workload': workload_name(args, cfg), 'agents_per_gpu_per_step': B, 'cuda_graph': bool(args.graph),
                        'global_agents_per_step': world * B, 'parallelism': f'dp{world} (agents sharded, no collective)',
                        'l2': 'inputs + activations per step >> 126 MB L2 (fresh synthetic tracks every step)',
                        'gflop_per_agent_reference_executed': GF_PER_AGENT[args.workload]},
             'e2e': {'value': e2e_value, 'unit': 'agent-trajectories/s', 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+            'diag': {'step_ms': step_list, 'host_issue_ms': host_ms, 'mem': mem_diag, 'kmeans_max_iters': km_diag,
+                     'e2e_step_ms': [a.elapsed_time(b) for a, b in zip([e2] + e2e_marks[:-1], e2e_marks)],
+                     'e2e_kmeans_max_iters': e2e_km},
             'effective_tflops_reference_normalised': value / (cfg['n_goal'] * cfg['n_traj']) *
                                                       GF_PER_AGENT[args.workload] / 1e3,
         }

@@ -121,11 +121,16 @@ int ynet_multinomial_topk(const float* prob, const float* expo, int32_t rows, in
                           const float* rowmax, const float* gsum, int32_t n, int64_t* idx, float* xy,
                           int32_t W, void* stream);
 /* Counter-based device generators for the production path (the parity path supplies randoms). */
-int ynet_rng_uniform_f64(uint64_t seed, uint64_t offset, int64_t n, double* out, void* stream);
-int ynet_rng_exponential_f32(uint64_t seed, uint64_t offset, int64_t n, float* out, void* stream);
+/* `epoch` (device uint64, may be NULL) is mixed into the seed on the device so that a captured CUDA graph draws
+ * fresh numbers on every replay; ynet_counter_add advances it. */
+int ynet_counter_add(uint64_t* counter, uint64_t inc, void* stream);
+int ynet_rng_uniform_f64(uint64_t seed, const uint64_t* epoch, uint64_t offset, int64_t n, double* out, void* stream);
+int ynet_rng_exponential_f32(uint64_t seed, const uint64_t* epoch, uint64_t offset, int64_t n, float* out,
+                             void* stream);
 /* K distinct indices in [0, N) per row: device analogue of np.random.choice(N, K, replace=False)
  * (utils/kmeans.py:17).  out (rows, K) int32. */
-int ynet_rng_choice(uint64_t seed, uint64_t offset, int32_t rows, int32_t N, int32_t K, int32_t* out, void* stream);
+int ynet_rng_choice(uint64_t seed, const uint64_t* epoch, uint64_t offset, int32_t rows, int32_t N, int32_t K,
+                    int32_t* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a14 kmeans (utils/kmeans.py:22-108, euclidean), batched over agents (the reference loops in
@@ -147,9 +152,10 @@ int ynet_kmeans_batched(const float* X, int32_t B, int32_t N, int32_t K, const i
  *     last_obs (B, 2); length_ratio = 1/(waypoint_num+2); sigma_factor (G) float per goal
  *     (sigma_factor - traj_idx); out (G, B, 2).
  * ------------------------------------------------------------------------------------------- */
+int64_t ynet_cws_waypoint_workspace_bytes(int32_t B, int32_t G);
 int ynet_cws_waypoint(const float* sig, int32_t B, int32_t H, int32_t W, const float* wp_in, int32_t G,
                       const float* last_obs, float length_ratio, const float* sigma_factor, float ratio,
-                      int32_t rot, float* out, void* stream);
+                      int32_t rot, float* out, void* workspace, int64_t workspace_bytes, void* stream);
 /* Materialises the normalised waypoint map (for the n_traj > 1 re-sampling, evaluate.py:213-216):
  *     out (B, H, W) for ONE goal g. */
 int ynet_cws_waypoint_map(const float* sig, int32_t B, int32_t H, int32_t W, const float* wp_in_g,

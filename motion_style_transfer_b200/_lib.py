@@ -51,11 +51,13 @@ _PROTOS = {
     'ynet_sampling_prepare': (c_int, [_P, _I, _L, _F, _P, _P, _P, _L, _P]),
     'ynet_multinomial_replacement': (c_int, [_P, _I, _L, _F, _P, _P, _P, _I, _P, _P, _P, _I, _P]),
     'ynet_multinomial_topk': (c_int, [_P, _P, _I, _L, _F, _P, _P, _I, _P, _P, _I, _P]),
-    'ynet_rng_uniform_f64': (c_int, [c_uint64, c_uint64, _L, _P, _P]),
-    'ynet_rng_exponential_f32': (c_int, [c_uint64, c_uint64, _L, _P, _P]),
-    'ynet_rng_choice': (c_int, [c_uint64, c_uint64, _I, _I, _I, _P, _P]),
+    'ynet_counter_add': (c_int, [_P, c_uint64, _P]),
+    'ynet_rng_uniform_f64': (c_int, [c_uint64, _P, c_uint64, _L, _P, _P]),
+    'ynet_rng_exponential_f32': (c_int, [c_uint64, _P, c_uint64, _L, _P, _P]),
+    'ynet_rng_choice': (c_int, [c_uint64, _P, c_uint64, _I, _I, _I, _P, _P]),
     'ynet_kmeans_batched': (c_int, [_P, _I, _I, _I, _P, _P, _I, _F, _I, _P, _P, _P, _P, _P]),
-    'ynet_cws_waypoint': (c_int, [_P, _I, _I, _I, _P, _I, _P, _F, _P, _F, _I, _P, _P]),
+    'ynet_cws_waypoint_workspace_bytes': (_L, [_I, _I]),
+    'ynet_cws_waypoint': (c_int, [_P, _I, _I, _I, _P, _I, _P, _F, _P, _F, _I, _P, _P, _L, _P]),
     'ynet_cws_waypoint_map': (c_int, [_P, _I, _I, _I, _P, _P, _F, _F, _F, _I, _P, _P]),
     'ynet_ade_fde': (c_int, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P]),
     'ynet_conv3x3_f32': (c_int, [POINTER(ConvSrc), _I, _I, _I, _I, _P, _P, _I, _I, _P, _P]),

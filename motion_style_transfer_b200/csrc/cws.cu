@@ -172,19 +172,24 @@ using namespace ynet;
 
 extern "C" {
 
+int64_t ynet_cws_waypoint_workspace_bytes(int32_t B, int32_t G) {
+  return (int64_t)B * kCwsSplits * G * 3 * (int64_t)sizeof(float);
+}
+
 int ynet_cws_waypoint(const float* sig, int32_t B, int32_t H, int32_t W, const float* wp_in, int32_t G,
                       const float* last_obs, float length_ratio, const float* sigma_factor, float ratio, int32_t rot,
-                      float* out, void* stream) {
+                      float* out, void* workspace, int64_t workspace_bytes, void* stream) {
   YNET_CHECK_ARG(sig && wp_in && last_obs && sigma_factor && out, "null pointer");
   YNET_CHECK_ARG(B > 0 && B <= 65535 && H > 1 && W > 1 && G > 0 && G <= 32, "bad shape (G <= 32 per call)");
-  float* partial = nullptr;
-  const size_t bytes = (size_t)B * kCwsSplits * G * 3 * sizeof(float);
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&partial), bytes, as_stream(stream));
-  if (e != cudaSuccess) return cuda_fail(e, "ynet_cws_waypoint(cudaMallocAsync)");
+  if (workspace == nullptr || workspace_bytes < ynet_cws_waypoint_workspace_bytes(B, G)) {
+    set_error("ynet_cws_waypoint: workspace too small");
+    return YNET_E_WORKSPACE;
+  }
+  float* partial = reinterpret_cast<float*>(workspace);
   cws_partial_kernel<<<dim3(kCwsSplits, B), 32 * G, 0, as_stream(stream)>>>(
       sig, H, W, wp_in, B, G, last_obs, length_ratio, sigma_factor, ratio, rot, kCwsSplits, partial);
+  YNET_LAUNCH_CHECK();
   cws_finalize_kernel<<<ceil_div(B * G, 256), 256, 0, as_stream(stream)>>>(partial, B, G, kCwsSplits, out);
-  cudaFreeAsync(partial, as_stream(stream));
   YNET_LAUNCH_CHECK();
   return YNET_OK;
 }

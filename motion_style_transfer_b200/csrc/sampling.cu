@@ -237,8 +237,16 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 
-__global__ void __launch_bounds__(256) rng_uniform_f64_kernel(uint64_t seed, uint64_t offset, long long n,
+// graph-safe streams: the effective seed mixes in a DEVICE-resident epoch counter, so that replaying a captured
+// CUDA graph (same kernel arguments) still draws fresh numbers every step
+__device__ __forceinline__ uint64_t mix_epoch(uint64_t seed, const uint64_t* epoch) {
+  return epoch ? seed + (*epoch) * 0x9E3779B97F4A7C15ull : seed;
+}
+__global__ void counter_add_kernel(uint64_t* ctr, uint64_t inc) { *ctr += inc; }
+
+__global__ void __launch_bounds__(256) rng_uniform_f64_kernel(uint64_t seed, const uint64_t* epoch, uint64_t offset, long long n,
                                                               double* __restrict__ out) {
+  seed = mix_epoch(seed, epoch);
   const long long pairs = (n + 1) / 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs;
        i += (long long)gridDim.x * blockDim.x) {
@@ -251,8 +259,9 @@ __global__ void __launch_bounds__(256) rng_uniform_f64_kernel(uint64_t seed, uin
   }
 }
 
-__global__ void __launch_bounds__(256) rng_exponential_f32_kernel(uint64_t seed, uint64_t offset, long long n,
+__global__ void __launch_bounds__(256) rng_exponential_f32_kernel(uint64_t seed, const uint64_t* epoch, uint64_t offset, long long n,
                                                                   float* __restrict__ out) {
+  seed = mix_epoch(seed, epoch);
   const long long quads = (n + 3) / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < quads;
        i += (long long)gridDim.x * blockDim.x) {
@@ -271,8 +280,9 @@ __global__ void __launch_bounds__(256) rng_exponential_f32_kernel(uint64_t seed,
 }
 
 // K distinct indices in [0, N) per row (the device analogue of np.random.choice(N, K, replace=False))
-__global__ void __launch_bounds__(128) rng_choice_kernel(uint64_t seed, uint64_t offset, int rows, int N, int K,
+__global__ void __launch_bounds__(128) rng_choice_kernel(uint64_t seed, const uint64_t* epoch, uint64_t offset, int rows, int N, int K,
                                                          int* __restrict__ out) {
+  seed = mix_epoch(seed, epoch);
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   int* o = out + (size_t)row * K;
@@ -351,28 +361,36 @@ int ynet_multinomial_topk(const float* prob, const float* expo, int32_t rows, in
   return YNET_OK;
 }
 
-int ynet_rng_uniform_f64(uint64_t seed, uint64_t offset, int64_t n, double* out, void* stream) {
+int ynet_counter_add(uint64_t* counter, uint64_t inc, void* stream) {
+  YNET_CHECK_ARG(counter, "null pointer");
+  counter_add_kernel<<<1, 1, 0, as_stream(stream)>>>(counter, inc);
+  YNET_LAUNCH_CHECK();
+  return YNET_OK;
+}
+
+int ynet_rng_uniform_f64(uint64_t seed, const uint64_t* epoch, uint64_t offset, int64_t n, double* out, void* stream) {
   YNET_CHECK_ARG(out && n >= 0, "bad argument");
   if (n == 0) return YNET_OK;
   const int blocks = (int)tmin<long long>(ceil_div<long long>((n + 1) / 2, 256), 8LL * sm_count());
-  rng_uniform_f64_kernel<<<blocks, 256, 0, as_stream(stream)>>>(seed, offset, n, out);
+  rng_uniform_f64_kernel<<<blocks, 256, 0, as_stream(stream)>>>(seed, epoch, offset, n, out);
   YNET_LAUNCH_CHECK();
   return YNET_OK;
 }
 
-int ynet_rng_choice(uint64_t seed, uint64_t offset, int32_t rows, int32_t N, int32_t K, int32_t* out, void* stream) {
+int ynet_rng_choice(uint64_t seed, const uint64_t* epoch, uint64_t offset, int32_t rows, int32_t N, int32_t K, int32_t* out,
+                    void* stream) {
   YNET_CHECK_ARG(out && rows >= 0 && N > 0 && K > 0 && K <= N, "bad argument");
   if (rows == 0) return YNET_OK;
-  rng_choice_kernel<<<ceil_div(rows, 128), 128, 0, as_stream(stream)>>>(seed, offset, rows, N, K, out);
+  rng_choice_kernel<<<ceil_div(rows, 128), 128, 0, as_stream(stream)>>>(seed, epoch, offset, rows, N, K, out);
   YNET_LAUNCH_CHECK();
   return YNET_OK;
 }
 
-int ynet_rng_exponential_f32(uint64_t seed, uint64_t offset, int64_t n, float* out, void* stream) {
+int ynet_rng_exponential_f32(uint64_t seed, const uint64_t* epoch, uint64_t offset, int64_t n, float* out, void* stream) {
   YNET_CHECK_ARG(out && n >= 0, "bad argument");
   if (n == 0) return YNET_OK;
   const int blocks = (int)tmin<long long>(ceil_div<long long>((n + 3) / 4, 256), 8LL * sm_count());
-  rng_exponential_f32_kernel<<<blocks, 256, 0, as_stream(stream)>>>(seed, offset, n, out);
+  rng_exponential_f32_kernel<<<blocks, 256, 0, as_stream(stream)>>>(seed, epoch, offset, n, out);
   YNET_LAUNCH_CHECK();
   return YNET_OK;
 }

@@ -245,23 +245,29 @@ def multinomial_topk(prob_map, expo, n, rel_threshold=None):
     return idx, xy
 
 
-def rng_uniform_f64(seed, offset, n, device):
+def rng_uniform_f64(seed, offset, n, device, epoch=None):
     out = torch.empty(n, dtype=torch.float64, device=device)
-    check(_L().ynet_rng_uniform_f64(seed, offset, n, _ptr(out), _stream()), 'rng_uniform_f64')
+    check(_L().ynet_rng_uniform_f64(seed, _ptr(epoch), offset, n, _ptr(out), _stream()), 'rng_uniform_f64')
     _count()
     return out
 
 
-def rng_exponential_f32(seed, offset, n, device):
+def rng_exponential_f32(seed, offset, n, device, epoch=None):
     out = torch.empty(n, dtype=torch.float32, device=device)
-    check(_L().ynet_rng_exponential_f32(seed, offset, n, _ptr(out), _stream()), 'rng_exponential_f32')
+    check(_L().ynet_rng_exponential_f32(seed, _ptr(epoch), offset, n, _ptr(out), _stream()), 'rng_exponential_f32')
     _count()
     return out
 
 
-def rng_choice(seed, offset, rows, N, K, device):
+def counter_add(counter, inc=1):
+    """counter: 1-element int64 CUDA tensor (device-resident epoch of a graph-safe DeviceRng)."""
+    check(_L().ynet_counter_add(_ptr(counter), int(inc), _stream()), 'counter_add')
+    _count()
+
+
+def rng_choice(seed, offset, rows, N, K, device, epoch=None):
     out = torch.empty(rows, K, dtype=torch.int32, device=device)
-    check(_L().ynet_rng_choice(seed, offset, rows, N, K, _ptr(out), _stream()), 'rng_choice')
+    check(_L().ynet_rng_choice(seed, _ptr(epoch), offset, rows, N, K, _ptr(out), _stream()), 'rng_choice')
     _count()
     return out
 
@@ -301,11 +307,12 @@ def cws_waypoint(sig, wp_in, last_obs, length_ratio, sigma_factor, ratio, rot):
     last_obs = _req(last_obs, name='last_obs')
     sigma_factor = _req(sigma_factor, name='sigma_factor')
     out = torch.empty(G, B, 2, dtype=torch.float32, device=sig.device)
+    ws = _workspace(_L().ynet_cws_waypoint_workspace_bytes(B, min(G, 32)), sig.device, 'cws')
     for g0 in range(0, G, 32):
         g1 = min(G, g0 + 32)
         check(_L().ynet_cws_waypoint(_ptr(sig), B, H, W, _ptr(wp_in[g0:g1]), g1 - g0, _ptr(last_obs),
                                      float(length_ratio), _ptr(sigma_factor[g0:g1]), float(ratio), int(bool(rot)),
-                                     _ptr(out[g0:g1]), _stream()), 'cws_waypoint')
+                                     _ptr(out[g0:g1]), _ptr(ws), ws.numel(), _stream()), 'cws_waypoint')
         _count(2)
     return out
 

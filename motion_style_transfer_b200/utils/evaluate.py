@@ -38,9 +38,12 @@ def _goal_samples_ttst(model, pred_goal_map, sig_goal, waypoints, n_goal, rel_th
     xy = sampling(sig_goal, num_samples=TTST_SAMPLES, replacement=True, rel_threshold=rel_thresh, rng=rng)
     X = xy[:, 0]                                                     # (B, S, 2)
     soft = ops.softargmax2d(pred_goal_map, channel=waypoints[-1])   # (B, 1, 2) first sample = softargmax
+    reseed_idx = None
     if kmeans_init is None and hasattr(rng, 'kmeans_init'):         # device generator: no host round trip
         kmeans_init = rng.kmeans_init(B, X.shape[1], n_goal - 1, X.device)
-    _, centres = kmeans_batched(X, n_goal - 1, init_idx=kmeans_init, tol=0.001, iter_limit=1000)
+        reseed_idx = rng.reseeds(B, X.shape[1], 64, X.device)
+    _, centres = kmeans_batched(X, n_goal - 1, init_idx=kmeans_init, tol=0.001, iter_limit=1000,
+                                reseed_idx=reseed_idx)
     return torch.cat([soft.unsqueeze(0), centres.permute(1, 0, 2).unsqueeze(2)], dim=0)
 
 
@@ -50,18 +53,16 @@ def _cws(model, sig_maps, goal_samples, last_observed, n_goal, n_traj, n_wp, CWS
     goal_samples = goal_samples.repeat(n_traj, 1, 1, 1)
     G, B = goal_samples.shape[0], goal_samples.shape[1]
     dev = goal_samples.device
-    traj_idx = torch.arange(G, device=dev) // n_goal
-    sf = (sigma_factor - traj_idx).float()
-    first = [g for g in range(G) if g // n_goal == 0]
-    rest = [g for g in range(G) if g // n_goal > 0]
+    rest = range(n_goal, G)                      # goals with traj_idx > 0 (only when n_traj > 1)
     out = torch.empty(G, B, n_wp, 2, dtype=torch.float32, device=dev)
     out[:, :, n_wp - 1] = goal_samples[:, :, 0]
-    # trajectories 0 of every goal: expectation of sigmoid * prior, all goals in one pass per level
-    cur = goal_samples[first, :, 0].contiguous()
+    # trajectories 0 of every goal (the first n_goal entries): expectation of sigmoid * prior, all goals in
+    # one pass per level.  Plain slices only: the block must stay CUDA-graph capturable.
+    sf0 = torch.full((n_goal,), float(sigma_factor), dtype=torch.float32, device=dev)
+    cur = goal_samples[:n_goal, :, 0].contiguous()
     for wnum in reversed(range(n_wp - 1)):
-        cur = ops.cws_waypoint(sig_maps[wnum][:, 0], cur, last_observed, 1.0 / (wnum + 2), sf[first].contiguous(),
-                               ratio, rot)
-        out[first, :, wnum] = cur
+        cur = ops.cws_waypoint(sig_maps[wnum][:, 0], cur, last_observed, 1.0 / (wnum + 2), sf0, ratio, rot)
+        out[:n_goal, :, wnum] = cur
     # further trajectories per goal re-sample from the thresholded map (evaluate.py:213-216); RNG is
     # consumed goal-major / level-minor exactly like the reference loop
     for g in rest:
@@ -205,3 +206,56 @@ def evaluate(model, val_loader, val_images, device, dataset_name, homo_mat, inpu
         trajs_dict['metaId'] = meta_id_ready
         trajs_dict['sceneId'] = scene_id_ready
     return val_ade_arr.mean(), val_fde_arr.mean(), df_out, trajs_dict
+
+
+class GraphedForecaster:
+    """``forecast_batch`` captured once as a CUDA graph and replayed per batch.
+
+    One batch of the evaluate() body is ~450 kernel launches; issued from Python that is ~45 ms of host
+    time per batch, more than the GPU needs.  The graph is captured for a fixed batch shape (B agents,
+    one scene size); inputs are copied into static device buffers, random numbers come from a graph-safe
+    ``DeviceRng`` whose per-step stream is selected by a device-resident epoch counter.
+    Outputs (``ade``, ``fde``, ``trajs``, ``waypoint_samples``) are static tensors overwritten by each replay.
+    """
+
+    def __init__(self, model, input_template, scene_shape, traj_shape, waypoints, n_goal, n_traj, obs_len,
+                 resize_factor=0.25, temperature=1.0, use_TTST=False, use_CWS=False, rel_thresh=0.002,
+                 CWS_params=None, seed=0, warmup=2):
+        from .image_utils import DeviceRng
+        dev = input_template.device
+        self.scene = torch.zeros(scene_shape, dtype=torch.float32, device=dev)
+        self.traj = torch.zeros(traj_shape, dtype=torch.float32, device=dev)
+        self.rng = DeviceRng(seed, graph_safe=True)
+        self._args = (model, self.scene, self.traj, input_template, waypoints, n_goal, n_traj, obs_len, resize_factor,
+                      temperature, use_TTST, use_CWS, rel_thresh, CWS_params)
+        self._warmup = warmup
+        self.graph = None
+        self.out = None
+
+    def _run(self):
+        self.rng.next_step(self.scene.device)
+        return forecast_batch(*self._args, rng=self.rng)
+
+    def capture(self, scene, trajectory):
+        """Warm up eagerly on real inputs (autotune, weight packing, workspaces), then capture."""
+        self.scene.copy_(scene)
+        self.traj.copy_(trajectory)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(self._warmup):
+                self._run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._run()
+        return self
+
+    def __call__(self, scene, trajectory):
+        if self.graph is None:
+            self.capture(scene, trajectory)
+        self.scene.copy_(scene, non_blocking=True)
+        self.traj.copy_(trajectory, non_blocking=True)
+        self.graph.replay()
+        return self.out

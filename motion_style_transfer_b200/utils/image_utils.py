@@ -62,24 +62,48 @@ def get_patch(template, traj, H, W):
 
 
 class DeviceRng:
-    """Counter-based (Philox) device generator for the production path."""
+    """Counter-based (Philox) device generator for the production path.
 
-    def __init__(self, seed=0):
+    With ``graph_safe=True`` the per-step stream is selected by a DEVICE-resident epoch counter (mixed into
+    the seed inside the kernels), so a captured CUDA graph draws fresh numbers on every replay: call
+    ``next_step()`` once per step (inside the captured region).  Within a step, offsets restart from 0.
+    """
+
+    def __init__(self, seed=0, graph_safe=False):
         self.seed = int(seed)
         self.offset = 0
+        self.graph_safe = graph_safe
+        self.epoch = None
+
+    def _epoch(self, device):
+        if not self.graph_safe:
+            return None
+        if self.epoch is None:
+            self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
+        return self.epoch
+
+    def next_step(self, device):
+        if self.graph_safe:
+            ops.counter_add(self._epoch(device), 1)
+            self.offset = 0
 
     def uniforms(self, rows, n, device):
-        out = ops.rng_uniform_f64(self.seed, self.offset, rows * n, device).view(rows, n)
+        out = ops.rng_uniform_f64(self.seed, self.offset, rows * n, device, self._epoch(device)).view(rows, n)
         self.offset += (rows * n + 1) // 2
         return out
 
     def exponentials(self, rows, S, device):
-        out = ops.rng_exponential_f32(self.seed, self.offset, rows * S, device).view(rows, S)
+        out = ops.rng_exponential_f32(self.seed, self.offset, rows * S, device, self._epoch(device)).view(rows, S)
         self.offset += (rows * S + 3) // 4
         return out
 
     def kmeans_init(self, rows, N, K, device):
-        out = ops.rng_choice(self.seed, self.offset, rows, N, K, device)
+        out = ops.rng_choice(self.seed, self.offset, rows, N, K, device, self._epoch(device))
+        self.offset += 1
+        return out
+
+    def reseeds(self, rows, N, R, device):
+        out = ops.rng_choice(self.seed ^ 0x5EED, self.offset, rows, N, R, device, self._epoch(device))
         self.offset += 1
         return out
 

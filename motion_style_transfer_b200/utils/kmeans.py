@@ -5,6 +5,9 @@ import torch
 from .. import ops
 
 
+last_iters = None
+
+
 def initialize(X, num_clusters):
     """kmeans.py:9-19: initial centres = X[np.random.choice(N, K, replace=False)]."""
     indices = np.random.choice(len(X), num_clusters, replace=False)
@@ -35,6 +38,8 @@ def kmeans_batched(X, num_clusters, init_idx=None, tol=1e-4, iter_limit=0, resee
     if reseed_idx is None:
         reseed_idx = _reseed_stream(B, 64, N, X.device)
     centres, assign, iters, status = ops.kmeans_batched(X.float(), init_idx, reseed_idx, tol, iter_limit, want_assign)
+    global last_iters
+    last_iters = iters          # device tensor (B,): Lloyd iterations per agent, for diagnostics
     return assign, centres
 
 
