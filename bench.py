@@ -159,7 +159,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='ind_long_ttst_cws', choices=sorted(WORKLOADS))
-    ap.add_argument('--agents', type=int, default=64, help='agents per GPU per step')
+    ap.add_argument('--agents', type=int, default=128, help='agents per GPU per step')
     ap.add_argument('--ref-agents', type=int, default=2, help='agents per step of the CPU reference arm')
     ap.add_argument('--cpu-agents', type=int, default=4, help='agents of the bounded cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -291,6 +291,10 @@ def main():
     roofline, layer_table = None, None
     if rank == 0:
         peaks = load_peaks()
+        _eager = lambda: forecast_batch(model, scene_dev, traj_dev[-1], tmpl, cfg['wps'], cfg['n_goal'], cfg['n_traj'],
+                                        cfg['obs'], cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'],
+                                        cfg['cwsp'], rng=rng)
+        _eager()                  # re-warm the eager allocator pool (graph capture emptied the cache)
         ops.profile_begin()       # eager pass (not the graph): per-launch CUDA events
         forecast_batch(model, scene_dev, traj_dev[-1], tmpl, cfg['wps'], cfg['n_goal'], cfg['n_traj'], cfg['obs'],
                        cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'], cfg['cwsp'], rng=rng)

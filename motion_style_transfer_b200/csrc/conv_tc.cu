@@ -498,29 +498,63 @@ c8_maxpool_kernel(const uint4* __restrict__ x, long long planes, int H, int W, u
   }
 }
 
-// bilinear x2 (align_corners=False) on C8 planes: (H, W) input size
+// bilinear x2 (align_corners=False) on C8 planes: (H, W) input size.
+// out[2i] = 0.25 in[i-1] + 0.75 in[i], out[2i+1] = 0.75 in[i] + 0.25 in[i+1] (indices clamped).  One thread owns the
+// 2x2 output block between input cells (ci-1, ci) x (cj-1, cj): 4 loads feed 4 outputs (the naive form needs 16).
 __global__ void __launch_bounds__(256)
 c8_upsample_kernel(const uint4* __restrict__ x, long long planes, int H, int W, uint4* __restrict__ out) {
-  const int OH = 2 * H, OW = 2 * W;
-  const long long total = planes * OH * OW;
+  const int OW = 2 * W;
+  const int CH = H + 1, CW = W + 1;
+  const long long total = planes * CH * CW;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const long long pl = t / ((long long)OH * OW);
-    const int r = (int)(t - pl * OH * OW);
-    const int y = r / OW, xx = r - y * OW;
-    const float fy = fmaxf(0.f, ((float)y + 0.5f) * 0.5f - 0.5f);
-    const float fx = fmaxf(0.f, ((float)xx + 0.5f) * 0.5f - 0.5f);
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const long long pl = t / ((long long)CH * CW);
+    const int r = (int)(t - pl * CH * CW);
+    const int ci = r / CW, cj = r - ci * CW;
+    const int i0 = max(ci - 1, 0), i1 = min(ci, H - 1);
+    const int j0 = max(cj - 1, 0), j1 = min(cj, W - 1);
     const uint4* q = x + pl * H * W;
-    float a[8], b[8], c[8], d[8], o[8];
-    unpack8(__ldg(q + (size_t)y0 * W + x0), a);
-    unpack8(__ldg(q + (size_t)y0 * W + x1), b);
-    unpack8(__ldg(q + (size_t)y1 * W + x0), c);
-    unpack8(__ldg(q + (size_t)y1 * W + x1), d);
+    float a[8], b[8], c[8], d[8];
+    unpack8(__ldg(q + (size_t)i0 * W + j0), a);
+    unpack8(__ldg(q + (size_t)i0 * W + j1), b);
+    unpack8(__ldg(q + (size_t)i1 * W + j0), c);
+    unpack8(__ldg(q + (size_t)i1 * W + j1), d);
+    float top_l[8], top_r[8], bot_l[8], bot_r[8];   // horizontally interpolated rows: left = col 2cj-1, right = col 2cj
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = (1.f - ly) * ((1.f - lx) * a[k] + lx * b[k]) + ly * ((1.f - lx) * c[k] + lx * d[k]);
-    out[t] = pack8(o);
+    for (int k = 0; k < 8; ++k) {
+      top_l[k] = 0.75f * a[k] + 0.25f * b[k];
+      top_r[k] = 0.25f * a[k] + 0.75f * b[k];
+      bot_l[k] = 0.75f * c[k] + 0.25f * d[k];
+      bot_r[k] = 0.25f * c[k] + 0.75f * d[k];
+    }
+    uint4* o = out + pl * 4 * H * W;
+    const bool has_l = cj >= 1, has_r = cj <= W - 1;
+    float v[8];
+    if (ci >= 1) {                // output row 2ci-1 = 0.75 r0 + 0.25 r1
+      const size_t row = (size_t)(2 * ci - 1) * OW;
+      if (has_l) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = 0.75f * top_l[k] + 0.25f * bot_l[k];
+        o[row + 2 * cj - 1] = pack8(v);
+      }
+      if (has_r) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = 0.75f * top_r[k] + 0.25f * bot_r[k];
+        o[row + 2 * cj] = pack8(v);
+      }
+    }
+    if (ci <= H - 1) {            // output row 2ci = 0.25 r0 + 0.75 r1
+      const size_t row = (size_t)(2 * ci) * OW;
+      if (has_l) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = 0.25f * top_l[k] + 0.75f * bot_l[k];
+        o[row + 2 * cj - 1] = pack8(v);
+      }
+      if (has_r) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = 0.25f * top_r[k] + 0.75f * bot_r[k];
+        o[row + 2 * cj] = pack8(v);
+      }
+    }
   }
 }
 
@@ -707,7 +741,7 @@ int ynet_tc_upsample2x(const void* x_c8, int32_t N, int32_t C_pad, int32_t H, in
   if (N == 0) return YNET_OK;
   YNET_CHECK_ARG(x_c8 && out_c8, "null pointer");
   const long long planes = (long long)N * (C_pad / 8);
-  c8_upsample_kernel<<<grid_1d(planes * 4LL * H * W), 256, 0, as_stream(stream)>>>(
+  c8_upsample_kernel<<<grid_1d(planes * (long long)(H + 1) * (W + 1)), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const uint4*>(x_c8), planes, H, W, reinterpret_cast<uint4*>(out_c8));
   YNET_LAUNCH_CHECK();
   return YNET_OK;

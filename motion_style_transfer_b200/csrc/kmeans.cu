@@ -16,7 +16,7 @@
 
 namespace ynet {
 
-constexpr int kKmThreads = 256;
+constexpr int kKmThreads = 512;
 constexpr int kKmMaxK = 64;
 
 struct KmShared {
