@@ -13,11 +13,10 @@ from collections import OrderedDict, deque
 from copy import deepcopy
 
 import torch
-import torch.distributed as dist
 from torch.utils.data import DataLoader
 from tqdm import tqdm
 
-from .. import ops
+from .. import ops, parallel
 from ..autograd_engine import BCEWithLogitsLoss
 from ..utils.dataloader import SceneDataset, scene_collate
 from ..utils.evaluate import evaluate
@@ -125,14 +124,11 @@ class FusedAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         for group in self.param_groups:
-            ps = [p for p in group['params'] if p.requires_grad and p.grad is not None]
+            flat, ps = parallel.flatten_grads(group['params'])
             if not ps:
                 continue
-            flat = torch.cat([p.grad.reshape(-1) for p in ps]) if (world > 1 or len(ps) > 1) else ps[0].grad.reshape(-1)
-            if world > 1:
-                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            grad_scale = parallel.allreduce_flat(flat)          # ONE collective per step; mean taken in the kernel
             off = 0
             for p in ps:
                 n = p.numel()
@@ -143,7 +139,7 @@ class FusedAdam(torch.optim.Optimizer):
                     st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st['step'] += 1
                 ops.adam_step(p.data, flat[off:off + n], st['exp_avg'], st['exp_avg_sq'], st['step'], group['lr'],
-                              group['betas'][0], group['betas'][1], group['eps'], 1.0 / world)
+                              group['betas'][0], group['betas'][1], group['eps'], grad_scale)
                 off += n
                 # the kernel wrote through a raw pointer: bump the version so cached folded weights refresh
                 if hasattr(torch.autograd.graph, 'increment_version'):

@@ -10,7 +10,7 @@ import numpy as np
 import pandas as pd
 import torch
 
-from .. import ops
+from .. import ops, parallel
 from ..engine import ChannelCat
 from .image_utils import HostRng, sampling
 from .kmeans import kmeans_batched
@@ -168,26 +168,46 @@ def evaluate(model, val_loader, val_images, device, dataset_name, homo_mat, inpu
             meta_ids = df_batch[0].metaId.unique()
             n_data = trajectory.shape[0]
             trajectory = trajectory.to(device=device, dtype=torch.float32)
-            for b in range(0, n_data, batch_size):
-                res = forecast_batch(model, scene_image, trajectory[b:b + batch_size].contiguous(), input_template,
+            # one process per GPU: this rank forecasts a contiguous range of the scene's agents (parallel.py);
+            # single-process runs own [0, n_data)
+            lo, hi = parallel.shard_bounds(n_data)
+            rows = {'ade': [], 'fde': [], 'prediction': [], 'goal_map': [], 'goal_sigmoid_map': [],
+                    'waypoint_sample': []}
+            for b in range(lo, hi, batch_size):
+                e = min(b + batch_size, hi)
+                res = forecast_batch(model, scene_image, trajectory[b:e].contiguous(), input_template,
                                      waypoints, n_goal, n_traj, obs_len, resize_factor, temperature, use_TTST,
                                      use_CWS, rel_thresh, CWS_params, want_maps=return_samples)
-                ade_list.append(res['ade'])
-                fde_list.append(res['fde'])
+                rows['ade'].append(res['ade'])
+                rows['fde'].append(res['fde'])
                 if return_preds:
-                    if b == 0:
-                        trajs_dict['groundtruth'].append(trajectory.cpu().numpy() / resize_factor)
-                    trajs, gt_future = res['trajs'], trajectory[b:b + batch_size, obs_len:]
+                    trajs, gt_future = res['trajs'], trajectory[b:e, obs_len:]
                     ade_batch = ((((gt_future - trajs) / resize_factor) ** 2).sum(dim=3) ** 0.5).mean(dim=2)
                     best = ade_batch.argmin(dim=0)
-                    trajs_dict['prediction'].append(
-                        (trajs[best, torch.arange(trajs.shape[1], device=device)] / resize_factor).cpu().numpy())
+                    rows['prediction'].append(trajs[best, torch.arange(trajs.shape[1], device=device)] / resize_factor)
                     if return_samples:
-                        trajs_dict['goal_map'].append(res['goal_map'].cpu().numpy())
-                        trajs_dict['goal_sigmoid_map'].append(
-                            ops.sigmoid_select(res['goal_map'], list(range(res['goal_map'].shape[1])),
-                                               temperature).cpu().numpy())
-                        trajs_dict['waypoint_sample'].append(res['waypoint_samples'].permute(1, 2, 0, 3).cpu().numpy())
+                        rows['goal_map'].append(res['goal_map'])
+                        rows['goal_sigmoid_map'].append(
+                            ops.sigmoid_select(res['goal_map'], list(range(res['goal_map'].shape[1])), temperature))
+                        rows['waypoint_sample'].append(res['waypoint_samples'].permute(1, 2, 0, 3))
+
+            def scene_rows(key, like):
+                """This scene's rows of ``key`` from every rank, in agent order."""
+                local = torch.cat(rows[key]) if rows[key] else like.new_zeros((0,) + tuple(like.shape[1:]))
+                return parallel.gather_rows(local.contiguous(), n_data)
+
+            empty = torch.zeros(0, dtype=torch.float32, device=device)
+            ade_list.append(scene_rows('ade', empty))
+            fde_list.append(scene_rows('fde', empty))
+            if return_preds:
+                trajs_dict['groundtruth'].append(trajectory.cpu().numpy() / resize_factor)
+                pred_like = trajectory[:0, obs_len:]
+                trajs_dict['prediction'].append(scene_rows('prediction', pred_like).cpu().numpy())
+                if return_samples:
+                    if parallel.world()[1] > 1 and not rows['goal_map']:
+                        raise RuntimeError('return_samples under data parallelism needs >= 1 agent per rank and scene')
+                    for key in ('goal_map', 'goal_sigmoid_map', 'waypoint_sample'):
+                        trajs_dict[key].append(scene_rows(key, rows[key][0]).cpu().numpy())
             meta_id_list.append(meta_ids)
             scene_id_list.append([scene_id] * n_data)
 

@@ -7,7 +7,7 @@ trainer passes (``FusedAdam`` = Adam kernel + optional NCCL all-reduce of the Lo
 """
 import torch
 
-from .. import ops
+from .. import ops, parallel
 from ..engine import ChannelCat
 
 
@@ -20,6 +20,8 @@ def train_epoch(model, train_loader, train_images, optimizer, criterion, loss_sc
     if device.type != 'cuda':
         raise RuntimeError('motion_style_transfer_b200.train_epoch runs on CUDA only (no CPU fallback)')
     train_loss = torch.zeros((), device=device)
+    world_size = parallel.world()[1]
+    trainable = [p for p in model.parameters() if p.requires_grad]
     train_ADE, train_FDE = [], []
     model.train()
     input_template = input_template.to(device=device, dtype=torch.float32)
@@ -35,8 +37,18 @@ def train_epoch(model, train_loader, train_images, optimizer, criterion, loss_sc
         for i in range(0, len(trajectory), batch_size):
             semantic_img = model.adapt_semantic(scene_image)
             _, _, H, W = scene_image.shape
-            traj = trajectory[i:i + batch_size]
+            batch_traj = trajectory[i:i + batch_size]
+            # one process per GPU: this rank takes a contiguous share of the batch's agents; its mean loss is
+            # weighted so that the rank-average of the gradients is the gradient of the full-batch mean
+            lo, hi = parallel.shard_bounds(batch_traj.shape[0])
+            traj = batch_traj[lo:hi]
             B = traj.shape[0]
+            shard_weight = B * world_size / batch_traj.shape[0]
+            if B == 0:      # more ranks than agents: contribute a zero gradient, stay in the collective
+                for p in trainable:
+                    p.grad = torch.zeros_like(p)
+                optimizer.step()
+                continue
             observed_map = ops.rasterize_patches(input_template, traj[:, :obs_len].reshape(-1, 2), H, W)
             observed_map = observed_map.view(B, obs_len, H, W)
             gt_future = traj[:, obs_len:].contiguous()
@@ -56,6 +68,8 @@ def train_epoch(model, train_loader, train_images, optimizer, criterion, loss_sc
             traj_loss = criterion(pred_traj_map, gt_future_map) * loss_scale
 
             loss = goal_loss + traj_loss
+            if world_size > 1:
+                loss = loss * shard_weight
             optimizer.zero_grad()
             loss.backward()
             optimizer.step()
@@ -68,6 +82,10 @@ def train_epoch(model, train_loader, train_images, optimizer, criterion, loss_sc
                 train_FDE.append(((((gt_future[:, -1:] - pred_goal[:, -1:]) / resize_factor) ** 2).sum(dim=2) ** 0.5)
                                  .mean(dim=1))
 
-    train_ADE = torch.cat(train_ADE).mean()
-    train_FDE = torch.cat(train_FDE).mean()
-    return train_ADE.item(), train_FDE.item(), train_loss.item()
+    train_ADE = torch.cat(train_ADE) if train_ADE else torch.zeros(0, device=device)
+    train_FDE = torch.cat(train_FDE) if train_FDE else torch.zeros(0, device=device)
+    if world_size == 1:
+        return train_ADE.mean().item(), train_FDE.mean().item(), train_loss.item()
+    ade, fde, _ = parallel.reduce_metric_sums(train_ADE.sum().item(), train_FDE.sum().item(), train_ADE.numel(), device)
+    loss_sum, _, _ = parallel.reduce_metric_sums(train_loss.item(), 0.0, world_size, device)   # mean over ranks
+    return ade, fde, loss_sum
