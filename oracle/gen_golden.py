@@ -218,7 +218,51 @@ def gen_evaluate(ns):
              **rnd, **{'sd/' + k: v for k, v in sd.items()})
 
 
-def main():
+def gen_train(ns):
+    """Two optimiser steps of the reference's train_epoch (train_epoch.py:8-136) with MoSA r=1 on stages 0-4:
+    freeze policy of trainer.py:117,137-139, Adam(lr) + BCEWithLogitsLoss as trainer.py:197,206."""
+    if ns.train_epoch is None:
+        print('train_epoch not importable:', ns.trainer_error)
+        return
+    for tag, network, kw in (('ynet', 'original', {}),
+                             ('ynetmod', 'fusion', dict(n_fusion=2, position=('scene', 'motion', 'fusion')))):
+        c = dict(H=64, W=96, obs=5, pred=6, wps=[2, 5], B=4, batch_size=2, resize=0.25, lr=1e-3, loss_scale=1000,
+                 kernlen=31, nsig=4)
+        m = build_ref_model(ns, c['obs'], c['pred'], len(c['wps']), network=network, **kw)
+        for p_ in m.parameters():
+            p_.requires_grad = False
+        for n, p_ in m.encoder.named_parameters():
+            if 'lora' in n:
+                p_.requires_grad = True
+        sd0 = {k: v.detach().clone().numpy() for k, v in m.state_dict().items()}
+        scene = O.synthetic_scene(c['H'], c['W'], seed=0)
+        tracks = O.synthetic_tracks(c['B'], c['obs'] + c['pred'], c['H'], c['W'], seed=3)
+        df = make_df(tracks / c['resize'])
+        ds = ns.dataloader.SceneDataset(df, resize=c['resize'], total_len=c['obs'] + c['pred'])
+        dl = DataLoader(ds, batch_size=1, collate_fn=ns.dataloader.scene_collate)
+        size = int(4200 * c['resize'])
+        tmpl = torch.Tensor(ns.image_utils.create_dist_mat(size))
+        gt_tmpl = torch.Tensor(ns.image_utils.create_gaussian_heatmap_template(size=size, kernlen=c['kernlen'],
+                                                                               nsig=c['nsig'], normalize=False))
+        opt = torch.optim.Adam(m.parameters(), lr=c['lr'])
+        crit = torch.nn.BCEWithLogitsLoss()
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            ade, fde, loss = ns.train_epoch.train_epoch(
+                m, dl, {'s0': scene}, opt, crit, c['loss_scale'], 'cpu', 'sdd', None, gt_tmpl, tmpl, c['wps'], 0,
+                c['obs'], c['pred'], c['batch_size'], 100, c['resize'], network)
+            traj = next(iter(dl))[0]
+        trained = {n: p_.detach().numpy() for n, p_ in m.named_parameters() if p_.requires_grad}
+        grads = {n: p_.grad.detach().numpy() for n, p_ in m.named_parameters() if p_.requires_grad}
+        save(f'train_{tag}', scene=scene.numpy(), trajectory=traj.numpy(), template_size=size,
+             train_ade=np.float32(ade), train_fde=np.float32(fde), train_loss=np.float32(loss),
+             cfg=np.array(repr(c)),
+             **{'sd/' + k: v for k, v in sd0.items()},
+             **{'trained/' + k: v for k, v in trained.items()},
+             **{'lastgrad/' + k: v for k, v in grads.items()})
+
+
+def main(only=None):
     torch.set_num_threads(1)     # reference's global-sum quirk depends on thread count (SURVEY 8)
     ns = ref_harness.load()
     gen_templates(ns)
@@ -229,6 +273,7 @@ def main():
     gen_cws(ns)
     gen_network(ns)
     gen_evaluate(ns)
+    gen_train(ns)
 
 
 if __name__ == '__main__':

@@ -547,6 +547,61 @@ def adam_step(p, g, m, v, step, lr, b1=0.9, b2=0.999, eps=1e-8):
     return p, m, v
 
 
+def train_epoch(sd, scene_image, trajectory, dist_template, gauss_template, waypoints, obs_len, pred_len,
+                batch_size, lr, loss_scale=1000.0, resize_factor=0.25, network='original', trainable=None):
+    """One epoch of utils/train_epoch.py:44-126 over ONE scene, from a state dict.
+
+    ``sd`` maps names to float32 tensors; ``trainable`` lists the names that train (default: every key containing
+    'lora' under 'encoder.', the MoSA freeze policy of models/trainer.py:117,137-139).  Gradients come from torch
+    autograd over the restated forward (the reference does the same, train_epoch.py:109-115); Adam is the
+    restated single-tensor update above.  Returns (train_ADE, train_FDE, train_loss, sd_after, last_grads).
+    """
+    sd = {k: torch.as_tensor(v).clone() for k, v in sd.items()}
+    if trainable is None:
+        trainable = [k for k in sd if k.startswith('encoder.') and 'lora' in k]
+    state = {k: (torch.zeros_like(sd[k]), torch.zeros_like(sd[k])) for k in trainable}
+    scene_image = torch.as_tensor(scene_image, dtype=torch.float32)
+    if scene_image.dim() == 3:
+        scene_image = scene_image[None]
+    trajectory = torch.as_tensor(trajectory, dtype=torch.float32)
+    _, _, H, W = scene_image.shape
+    total_loss, ades, fdes, step, grads = 0.0, [], [], 0, {}
+    for i in range(0, trajectory.shape[0], batch_size):
+        traj = trajectory[i:i + batch_size]
+        B = traj.shape[0]
+        leaf = {k: (v.clone().requires_grad_(True) if k in state else v) for k, v in sd.items()}
+        observed_map = torch.from_numpy(get_patch_stack(dist_template, traj[:, :obs_len].reshape(-1, 2).numpy(), H, W))
+        observed_map = observed_map.reshape(B, obs_len, H, W)
+        gt_future = traj[:, obs_len:]
+        gt_future_map = torch.from_numpy(get_patch_stack(gauss_template, gt_future.reshape(-1, 2).numpy(), H, W))
+        gt_future_map = gt_future_map.reshape(B, pred_len, H, W)
+        gt_wp = gt_future[:, waypoints]
+        gt_wp_map = torch.from_numpy(get_patch_stack(dist_template, gt_wp.reshape(-1, 2).numpy(), H, W))
+        gt_wp_map = gt_wp_map.reshape(B, len(waypoints), H, W)
+        feats = pred_features(leaf, scene_image.expand(B, -1, -1, -1), observed_map, network)
+        goal_map = pred_goal(leaf, feats)
+        goal_loss = bce_with_logits_mean(goal_map, gt_future_map) * loss_scale
+        pyr = avgpool_pyramid(gt_wp_map, len(feats))
+        traj_map = pred_traj(leaf, [torch.cat([f, p], dim=1) for f, p in zip(feats, pyr)])
+        traj_loss = bce_with_logits_mean(traj_map, gt_future_map) * loss_scale
+        loss = goal_loss + traj_loss
+        names = list(state)
+        gs = torch.autograd.grad(loss, [leaf[k] for k in names])
+        step += 1
+        for k, g in zip(names, gs):
+            m, v = state[k]
+            sd[k], m, v = adam_step(sd[k], g, m, v, step, lr)
+            state[k] = (m, v)
+            grads[k] = g
+        with torch.no_grad():
+            total_loss += float(loss)
+            pt = softargmax2d(traj_map.detach())
+            pg = softargmax2d(goal_map.detach()[:, -1:])
+            ades.append(((((gt_future - pt) / resize_factor) ** 2).sum(dim=2) ** 0.5).mean(dim=1))
+            fdes.append(((((gt_future[:, -1:] - pg) / resize_factor) ** 2).sum(dim=2) ** 0.5).mean(dim=1))
+    return float(torch.cat(ades).mean()), float(torch.cat(fdes).mean()), total_loss, sd, grads
+
+
 # --------------------------------------------------------------------------------------
 # synthetic workloads  (SURVEY.md section 8d)
 # --------------------------------------------------------------------------------------

@@ -177,3 +177,28 @@ def test_lora_init_is_noop():
     assert torch.equal(conv(x), base)
     assert conv.lora_A.shape == (6, 15) and conv.lora_B.shape == (21, 6)
     assert not conv.weight.requires_grad and conv.lora_A.requires_grad
+
+
+@pytest.mark.parametrize('tag,network', [('ynet', 'original'), ('ynetmod', 'fusion')])
+def test_train_epoch_against_reference_fixture(tag, network):
+    """Oracle restatement of train_epoch.py:44-126 (two Adam steps) vs the live reference's fixture."""
+    import ast
+    g = load_golden(f'train_{tag}')
+    c = ast.literal_eval(str(g['cfg']))
+    sd = golden_state_dict(g)
+    size = int(g['template_size'])
+    dist_t = O.create_dist_mat(size).astype(np.float32)
+    gauss_t = O.create_gaussian_heatmap_template(size, kernlen=c['kernlen'], nsig=c['nsig'],
+                                                 normalize=False).astype(np.float32)
+    torch.set_num_threads(1)
+    ade, fde, loss, sd_after, grads = O.train_epoch(sd, g['scene'], g['trajectory'], dist_t, gauss_t, c['wps'], c['obs'],
+                                                    c['pred'], c['batch_size'], c['lr'], c['loss_scale'], c['resize'],
+                                                    network)
+    assert abs(ade - float(g['train_ade'])) < 1e-3 and abs(fde - float(g['train_fde'])) < 1e-3
+    assert abs(loss - float(g['train_loss'])) < 1e-3 * abs(float(g['train_loss']))
+    keys = [k[8:] for k in g.files if k.startswith('trained/')]
+    assert keys and sorted(keys) == sorted(grads)
+    for k in keys:
+        np.testing.assert_allclose(sd_after[k].numpy(), g['trained/' + k], rtol=0, atol=2e-6)
+        ref = g['lastgrad/' + k]
+        np.testing.assert_allclose(grads[k].numpy(), ref, rtol=0, atol=1e-4 * max(np.abs(ref).max(), 1e-6))

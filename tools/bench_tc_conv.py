@@ -12,6 +12,8 @@ SHAPES = [  # (source channels, C_out, H, W)
     ((64,), 32, 208, 208), ((32, 64, 2), 64, 104, 104), ((64,), 64, 104, 104), ((130,), 130, 13, 13),
 ]
 N = int(os.environ.get('N', 64))
+if os.environ.get('SHAPES'):          # e.g. SHAPES=2,3 for an ncu capture of single layers
+    SHAPES = [SHAPES[int(i)] for i in os.environ['SHAPES'].split(',')]
 torch.manual_seed(0)
 print(f'env: CTAS_PER_SM={os.environ.get("YNET_TC_CTAS_PER_SM")} STAGES={os.environ.get("YNET_TC_STAGES")} '
       f'J={os.environ.get("YNET_TC_J")} N={N}')
