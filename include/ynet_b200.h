@@ -206,11 +206,24 @@ int ynet_lora_fold(const float* weight, const float* lora_A, const float* lora_B
 typedef struct ynet_tc_src {
   const void* ptr;      /* bf16 C8 planes                                                     */
   int32_t channels_pad; /* multiple of 16                                                     */
-  int32_t batch_mod;    /* > 0: image n reads source image n % batch_mod                      */
+  int32_t batch_mod;    /* > 0: image n reads source image n % batch_mod (goal-major stacking);
+                           < 0: image n reads source image n / (-batch_mod) (agent-major stacking:
+                           the n_goal decoder passes of one agent are consecutive images, so the
+                           agent's encoder features are re-read from L2, evaluate.py:259)        */
   int64_t batch_stride; /* elements (bf16); 0 = broadcast                                     */
 } ynet_tc_src;
 
 int ynet_tc_supported(void);
+
+/* a3 + a9 fused for the bf16 engine: get_patch of n_img x n_ch coordinates (image_utils.py:40-63) and the
+ * AvgPool2d(2^i) pyramid of the result (evaluate.py:255-257), written straight as bf16 C8 planes.
+ * coords: (n_img * n_ch, 2) float32 (x, y), n_ch <= 8.  outs_host[l], l < n_levels: (n_img, C_pad/8, H>>l, W>>l, 8)
+ * bf16; channel c < n_ch of chunk 0 holds the map, the other channels of chunk 0 are written as zero.
+ * write_pad = 0: chunks >= 1 are NOT written (the caller keeps them zero across calls); 1: zero-filled. */
+int ynet_tc_rasterize_pyramid_c8(const float* tmpl, int32_t tmpl_h, int32_t tmpl_w, const float* coords,
+                                 int32_t n_img, int32_t n_ch, int32_t H, int32_t W, int32_t n_levels,
+                                 void* const* outs_host, int32_t C_pad, int32_t write_pad, int32_t* oob_flag,
+                                 void* stream);
 int ynet_tc_pack_f32_to_c8(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, int64_t batch_stride,
                            void* out_c8, int32_t C_pad, void* stream);
 int ynet_tc_unpack_c8_to_f32(const void* x_c8, int32_t N, int32_t C, int32_t C_pad, int32_t H, int32_t W,
@@ -221,6 +234,24 @@ int ynet_tc_upsample2x(const void* x_c8, int32_t N, int32_t C_pad, int32_t H, in
 /* 1x1 predictor (ynet.py:450-451,469) reading C8 bf16, writing float32 NCHW logits (fp32 FMA). */
 int ynet_tc_predictor_f32(const void* x_c8, int32_t N, int32_t C_pad, int32_t C_in, int32_t H, int32_t W,
                           const float* weight, const float* bias, int32_t C_out, float* out, void* stream);
+/* F.interpolate(scale 2, bilinear, align_corners=False) + upsample_conv (ynet.py:463-464) as ONE low-resolution
+ * 3x3 conv with 4 x C_out phase channels and a depth-to-space store: the upsampled tensor is never materialised.
+ *   ynet_tc_upconv_phase_weights: weight (C_out, C_in, 3, 3), bias -> w_eff (4*cp, C_in, 3, 3), bias_eff (4*cp),
+ *     cp = C_out padded to 16; pack w_eff with ynet_tc_pack_weights(C_out = 4*cp, ksize = 3).
+ *   ynet_tc_upconv3x3: srcs are the LOW-resolution (h, w) C8 sources (src_channels_host = their real channel
+ *     counts); out_c8: (N, cp/8, 2h, 2w, 8).  `border_weight` (ynet_tc_upconv_border_weights of the original
+ *     float32 weight; ynet_tc_upconv_border_weight_bytes bytes) and the original `bias` are used to recompute the
+ *     one-pixel border ring exactly (index clamping and zero padding do not commute with the stencil).
+ *     C_out <= 64; relu must be 0. */
+int64_t ynet_tc_upconv_border_weight_bytes(int32_t C_out, int32_t n_src, const int32_t* src_channels_host);
+int ynet_tc_upconv_border_weights(const float* weight, int32_t C_out, int32_t n_src, const int32_t* src_channels_host,
+                                  float* out, void* stream);
+int ynet_tc_upconv_phase_weights(const float* weight, const float* bias, int32_t C_out, int32_t C_in, float* w_eff,
+                                 float* bias_eff, void* stream);
+int ynet_tc_upconv3x3(const ynet_tc_src* srcs_host, const int32_t* src_channels_host, int32_t n_src, int32_t N,
+                      int32_t h, int32_t w, const void* packed_phase_weight, const float* bias_eff,
+                      const float* border_weight, const float* bias, int32_t C_out, int32_t relu, void* out_c8,
+                      int32_t tune, void* stream);
 /* ksize = 3 (3x3 conv) or 1 (the 1x1 predictor). */
 int64_t ynet_tc_packed_weight_bytes(int32_t C_out, int32_t n_src, const int32_t* src_channels_pad_host,
                                     int32_t ksize);

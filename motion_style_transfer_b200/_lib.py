@@ -68,6 +68,7 @@ _PROTOS = {
     'ynet_upsample_bilinear2x_f32': (c_int, [_P, _L, _I, _I, _P, _P]),
     'ynet_lora_fold': (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     'ynet_tc_supported': (c_int, []),
+    'ynet_tc_rasterize_pyramid_c8': (c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _I, POINTER(c_void_p), _I, _I, _P, _P]),
     'ynet_tc_pack_f32_to_c8': (c_int, [_P, _I, _I, _I, _I, _L, _P, _I, _P]),
     'ynet_tc_unpack_c8_to_f32': (c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
     'ynet_tc_maxpool2x2': (c_int, [_P, _I, _I, _I, _I, _P, _P]),
@@ -78,6 +79,10 @@ _PROTOS = {
     'ynet_tc_conv1x1_f32': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
     'ynet_tc_conv1x1_softargmax_workspace_bytes': (_L, [_I, _I]),
     'ynet_tc_conv1x1_softargmax': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _P, _P, _L, _I, _P]),
+    'ynet_tc_upconv_phase_weights': (c_int, [_P, _P, _I, _I, _P, _P, _P]),
+    'ynet_tc_upconv_border_weight_bytes': (_L, [_I, _I, POINTER(c_int32)]),
+    'ynet_tc_upconv_border_weights': (c_int, [_P, _I, _I, POINTER(c_int32), _P, _P]),
+    'ynet_tc_upconv3x3': (c_int, [POINTER(TcSrc), POINTER(c_int32), _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _I, _P]),
     'ynet_tc_conv3x3': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _I, _P]),
     'ynet_bce_workspace_bytes': (_L, [_L]),
     'ynet_bce_logits_fwd_bwd': (c_int, [_P, _P, _L, _F, _P, _P, _P, _L, _P]),

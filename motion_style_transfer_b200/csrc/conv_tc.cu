@@ -33,7 +33,7 @@ constexpr unsigned TC_SPIN_LIMIT = 4u * 1000u * 1000u;             // bounded wa
 struct TcSrcDev {
   int kblocks;      // channels_pad / 16
   int bcast;        // source has batch 1
-  int batch_mod;    // > 0: image n reads n % batch_mod
+  int batch_mod;    // > 0: image n reads n % batch_mod; < 0: image n reads n / -batch_mod
   int pad_;
 };
 
@@ -57,7 +57,7 @@ struct TcParams {
   int* err;
 };
 
-constexpr int EPI_C8 = 0, EPI_NCHW_F32 = 1, EPI_SOFTARGMAX = 2;
+constexpr int EPI_C8 = 0, EPI_NCHW_F32 = 1, EPI_SOFTARGMAX = 2, EPI_UP2 = 3;
 constexpr int TC_LOGIT_PITCH = 33;
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------
@@ -217,7 +217,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         int kb = 0;
         for (int s = 0; s < p.n_src; ++s) {
           const CUtensorMap* map = (s == 0) ? &map0 : (s == 1) ? &map1 : (s == 2) ? &map2 : &map3;
-          const int ns = p.src[s].bcast ? 0 : (p.src[s].batch_mod > 0 ? n % p.src[s].batch_mod : n);
+          const int bm = p.src[s].batch_mod;
+          const int ns = p.src[s].bcast ? 0 : (bm > 0 ? n % bm : (bm < 0 ? n / (-bm) : n));
           for (int b = 0; b < p.src[s].kblocks; ++b, ++kb) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err);
             unsigned char* st = s_stage + (size_t)stage * p.stage_bytes;
@@ -359,6 +360,26 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
                 o.z = pack_bf16(f[8 * h + 4], f[8 * h + 5]);
                 o.w = pack_bf16(f[8 * h + 6], f[8 * h + 7]);
                 __nv_bfloat16* dst = p.out + ((((size_t)n * n_chunks + chunk) * p.H + y) * p.W + x) * 8;
+                *reinterpret_cast<uint4*>(dst) = o;
+              }
+            }
+          } else if (EPI == EPI_UP2) {
+            // phase-decomposed bilinear-x2 + conv: channel group c0 belongs to output phase (a, b) and lands on
+            // the high-resolution pixel (2y + a, 2x + b) (depth-to-space in the store)
+            if (inb) {
+              const int cp = p.n_pad >> 2;                 // padded C_out of one phase (multiple of 16)
+              const int phase = c0 / cp, o0 = c0 - phase * cp;
+              const int ya = 2 * y + (phase >> 1), xb2 = 2 * x + (phase & 1);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int chunk = (o0 >> 3) + h;
+                uint4 o;
+                o.x = pack_bf16(f[8 * h + 0], f[8 * h + 1]);
+                o.y = pack_bf16(f[8 * h + 2], f[8 * h + 3]);
+                o.z = pack_bf16(f[8 * h + 4], f[8 * h + 5]);
+                o.w = pack_bf16(f[8 * h + 6], f[8 * h + 7]);
+                __nv_bfloat16* dst =
+                    p.out + ((((size_t)n * (cp >> 3) + chunk) * (2 * p.H) + ya) * (size_t)(2 * p.W) + xb2) * 8;
                 *reinterpret_cast<uint4*>(dst) = o;
               }
             }
@@ -666,6 +687,207 @@ tc_partial_finalize_kernel(const float4* __restrict__ part, int rows, int slots,
   }
 }
 
+// ---- bilinear x2 + 3x3 conv as ONE low-resolution conv with 4 x C_out phase channels ------------------------
+// F.interpolate(scale 2, bilinear, align_corners=False) followed by conv3x3(pad 1) (ynet.py:463-464) is linear in
+// the low-resolution input x: the output pixel (2i + a, 2j + b) is a 3x3 stencil over x[i-1..i+1][j-1..j+1] whose
+// weights are  W_eff^{ab}[o,c,p,q] = sum_{dy,dx} w[o,c,dy,dx] alpha_a[dy][p] alpha_b[dx][q]  with
+//   alpha_0 = {{.75,.25,0},{.25,.75,0},{0,.75,.25}}   (rows: conv tap -1,0,+1; cols: low-res offset -1,0,+1)
+//   alpha_1 = {{.25,.75,0},{0,.75,.25},{0,.25,.75}}.
+// The upsampled tensor (4x the pixels) is never materialised and the MMA N dimension becomes 4 x C_out.
+// Exact in the interior; the one-pixel low-resolution border ring (index clamping of the interpolation and the
+// zero padding of the conv do not commute with the stencil) is recomputed by upconv_border_kernel.
+__constant__ float kAlpha[2][3][3] = {{{.75f, .25f, 0.f}, {.25f, .75f, 0.f}, {0.f, .75f, .25f}},
+                                      {{.25f, .75f, 0.f}, {0.f, .75f, .25f}, {0.f, .25f, .75f}}};
+
+// w (C_out, C_in, 3, 3) -> w_eff (4 * cp, C_in, 3, 3), rows (a, b, o) with o padded to cp; bias -> bias_eff (4 * cp)
+__global__ void __launch_bounds__(256)
+upconv_phase_weights_kernel(const float* __restrict__ w, const float* __restrict__ bias, int C_out, int C_in, int cp,
+                            float* __restrict__ w_eff, float* __restrict__ bias_eff) {
+  const int total = 4 * cp * C_in * 9;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int q = t % 3, pp = (t / 3) % 3;
+    const int c = (t / 9) % C_in;
+    const int row = t / (9 * C_in);
+    const int o = row % cp, phase = row / cp;
+    const int a = phase >> 1, b = phase & 1;
+    float v = 0.f;
+    if (o < C_out) {
+      const float* wk = w + ((size_t)o * C_in + c) * 9;
+      for (int dy = 0; dy < 3; ++dy)
+        for (int dx = 0; dx < 3; ++dx) v += wk[dy * 3 + dx] * kAlpha[a][dy][pp] * kAlpha[b][dx][q];
+    }
+    w_eff[t] = v;
+  }
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 4 * cp; t += gridDim.x * blockDim.x)
+    bias_eff[t] = (t % cp < C_out && bias != nullptr) ? bias[t % cp] : 0.f;
+}
+
+// Exact recomputation of the high-resolution outputs that belong to low-resolution border pixels (CUDA cores; the
+// ring is ~2 % of the pixels at 416^2).  One CTA column (blockIdx.y) = one group of OG output channels whose float32
+// weights [padded input channel][tap][OG] stay resident in shared memory; threads walk (image, ring pixel, phase).
+constexpr int UPB_THREADS = 256;
+struct UpBorderSrc {
+  const uint4* ptr[YNET_MAX_SOURCES];
+  long long batch_stride[YNET_MAX_SOURCES];   // in uint4 (pixels x chunks); 0 = broadcast
+  int real_chunks[YNET_MAX_SOURCES];          // ceil(real channels / 8)
+  int batch_mod[YNET_MAX_SOURCES];
+  int n_src;
+};
+struct UpBorderPack {
+  int real[YNET_MAX_SOURCES];
+  int n_src;
+};
+
+// weight (C_out, C_in, 3, 3) -> [group][padded channel][tap][OG] float32, channels padded per source to 8
+__global__ void __launch_bounds__(256)
+upconv_border_weights_kernel(const float* __restrict__ w, int C_out, int C_in, UpBorderPack ps, int cpad_total, int og,
+                             int groups, float* __restrict__ out) {
+  const int total = groups * cpad_total * 9 * og;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int o_in = t % og;
+    const int tap = (t / og) % 9;
+    const int cpad = (t / (og * 9)) % cpad_total;
+    const int g = t / (og * 9 * cpad_total);
+    int c = cpad, ci = -1, base = 0;
+    for (int s = 0; s < ps.n_src; ++s) {
+      const int padded = (ps.real[s] + 7) / 8 * 8;
+      if (c < padded) {
+        if (c < ps.real[s]) ci = base + c;
+        break;
+      }
+      c -= padded;
+      base += ps.real[s];
+    }
+    const int o = g * og + o_in;
+    out[t] = (ci >= 0 && o < C_out) ? w[((size_t)o * C_in + ci) * 9 + tap] : 0.f;
+  }
+}
+
+template <int OG>   // output channels per thread: 16 or 32
+__global__ void __launch_bounds__(UPB_THREADS, 2)
+upconv_border_kernel(UpBorderSrc src, int N, int h, int w, const float* __restrict__ bw /* [g][cpad][9][OG] */,
+                     const float* __restrict__ bias, int C_out, int cpad_total, __nv_bfloat16* __restrict__ out, int cp) {
+  extern __shared__ __align__(16) float s_wt[];   // [cpad_total][9][OG]
+  const int grp = blockIdx.y;
+  {
+    const float4* g4 = reinterpret_cast<const float4*>(bw + (size_t)grp * cpad_total * 9 * OG);
+    float4* s4 = reinterpret_cast<float4*>(s_wt);
+    for (int e = threadIdx.x; e < cpad_total * 9 * OG / 4; e += UPB_THREADS) s4[e] = __ldg(g4 + e);
+  }
+  __syncthreads();
+  const int ring = (h >= 2 && w >= 2) ? 2 * w + 2 * (h - 2) : h * w;
+  const long long total = (long long)N * ring * 4;
+  const int H2 = 2 * h, W2 = 2 * w;
+  for (long long t = (long long)blockIdx.x * UPB_THREADS + threadIdx.x; t < total; t += (long long)gridDim.x * UPB_THREADS) {
+    const int phase = (int)(t & 3);
+    const long long r0 = t >> 2;
+    const int n = (int)(r0 / ring);
+    int r = (int)(r0 - (long long)n * ring);
+    int i, j;
+    if (h < 2 || w < 2) {
+      i = r / w;
+      j = r - i * w;
+    } else if (r < w) {
+      i = 0;
+      j = r;
+    } else if (r < 2 * w) {
+      i = h - 1;
+      j = r - w;
+    } else {
+      r -= 2 * w;
+      i = 1 + (r >> 1);
+      j = (r & 1) ? w - 1 : 0;
+    }
+    const int v = 2 * i + (phase >> 1), u = 2 * j + (phase & 1);   // high-resolution output pixel
+    // The 3x3 hi-res window around (v, u) draws on the low-res rows i-1..i+1 / columns j-1..j+1 (clamped into the
+    // image = the interpolation's index clamping).  ay[d][r]: weight of low-res row slot r (0..2) in hi-res row
+    // v + d - 1; all-zero when that hi-res row lies in the conv's zero padding.  Same for columns.
+    float ay[3][3], ax[3][3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int vv = v + d - 1, uu = u + d - 1;
+      const bool vin = vv >= 0 && vv < H2, uin = uu >= 0 && uu < W2;
+      // hi-res index 2k: .25 x[k-1] + .75 x[k]; 2k+1: .75 x[k] + .25 x[k+1]  (slots relative to i-1 / j-1)
+      const int ky = (vv >> 1) - (i - 1), kx = (uu >> 1) - (j - 1);
+      const int ya = (vv & 1) ? ky : ky - 1, yb = (vv & 1) ? ky + 1 : ky;
+      const int xa = (uu & 1) ? kx : kx - 1, xb = (uu & 1) ? kx + 1 : kx;
+      const float fa = (vv & 1) ? .75f : .25f, fb = 1.f - fa;
+      const float ga = (uu & 1) ? .75f : .25f, gb = 1.f - ga;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        // slot r holds low-res row clamp(i - 1 + r): an (unclamped) tap row i - 1 + r lands on its own slot
+        ay[d][r] = vin ? ((ya == r ? fa : 0.f) + (yb == r ? fb : 0.f)) : 0.f;
+        ax[d][r] = uin ? ((xa == r ? ga : 0.f) + (xb == r ? gb : 0.f)) : 0.f;
+      }
+    }
+    int rows[3], cols[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      rows[r] = min(max(i - 1 + r, 0), h - 1);
+      cols[r] = min(max(j - 1 + r, 0), w - 1);
+    }
+    float acc[OG];
+#pragma unroll
+    for (int o = 0; o < OG; ++o) {
+      const int oo = grp * OG + o;
+      acc[o] = (bias != nullptr && oo < C_out) ? bias[oo] : 0.f;
+    }
+    int cpad = 0;
+    for (int s = 0; s < src.n_src; ++s) {
+      const int bm = src.batch_mod[s];
+      const int ns = (src.batch_stride[s] == 0) ? 0 : (bm > 0 ? n % bm : (bm < 0 ? n / (-bm) : n));
+      const uint4* xs = src.ptr[s] + (size_t)ns * src.batch_stride[s];
+      for (int ch = 0; ch < src.real_chunks[s]; ++ch, cpad += 8) {
+        const uint4* xc = xs + (size_t)ch * h * w;
+        const float* wq = s_wt + (size_t)cpad * 9 * OG;
+        uint4 X[3][3];   // packed 3x3 low-res neighbourhood (row slot, column slot)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) X[r][c] = __ldg(xc + (size_t)rows[r] * w + cols[c]);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          // vertical interpolation: R[c] = hi-res row (v + dy - 1) at low-res column slot c
+          float R[3][8];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float x0[8], x1[8], x2[8];
+            unpack8(X[0][c], x0);
+            unpack8(X[1][c], x1);
+            unpack8(X[2][c], x2);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) R[c][k] = ay[dy][0] * x0[k] + ay[dy][1] * x1[k] + ay[dy][2] * x2[k];
+          }
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            float uvals[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) uvals[k] = ax[dx][0] * R[0][k] + ax[dx][1] * R[1][k] + ax[dx][2] * R[2][k];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4* wv = reinterpret_cast<const float4*>(wq + (size_t)(k * 9 + dy * 3 + dx) * OG);
+#pragma unroll
+              for (int o4 = 0; o4 < OG / 4; ++o4) {
+                const float4 ww = wv[o4];
+                acc[4 * o4 + 0] = fmaf(uvals[k], ww.x, acc[4 * o4 + 0]);
+                acc[4 * o4 + 1] = fmaf(uvals[k], ww.y, acc[4 * o4 + 1]);
+                acc[4 * o4 + 2] = fmaf(uvals[k], ww.z, acc[4 * o4 + 2]);
+                acc[4 * o4 + 3] = fmaf(uvals[k], ww.w, acc[4 * o4 + 3]);
+              }
+            }
+          }
+        }
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out) + (((size_t)n * (cp >> 3) + grp * (OG / 8)) * H2 + v) * (size_t)W2 + u;
+#pragma unroll
+    for (int o = 0; o < OG; ++o)
+      if (grp * OG + o >= C_out) acc[o] = 0.f;
+#pragma unroll
+    for (int q = 0; q < OG / 8; ++q) dst[(size_t)q * H2 * W2] = pack8(acc + 8 * q);
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -875,7 +1097,8 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
       return YNET_E_INVALID;
     }
     const bool bcast = srcs[i].batch_stride == 0;
-    const int nsrc = bcast ? 1 : (srcs[i].batch_mod > 0 ? srcs[i].batch_mod : N);
+    const int bmod = srcs[i].batch_mod;
+    const int nsrc = bcast ? 1 : (bmod > 0 ? bmod : (bmod < 0 ? ceil_div(N, -bmod) : N));
     // A pixel row of one 8-channel chunk is W*8 contiguous bf16: that is the innermost TMA dimension, so one
     // box row is ONE (8J+2)*16-byte request instead of 8J+2 sixteen-byte ones.
     const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)(cp / 8), (cuuint64_t)nsrc};
@@ -942,6 +1165,7 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
   static bool configured = false;
   if (!configured) {
     cudaError_t e = tc_configure<9, EPI_C8>();
+    if (e == cudaSuccess) e = tc_configure<9, EPI_UP2>();
     if (e == cudaSuccess) e = tc_configure<1, EPI_NCHW_F32>();
     if (e == cudaSuccess) e = tc_configure<1, EPI_SOFTARGMAX>();
     if (e != cudaSuccess) return cuda_fail(e, "tc_launch(cudaFuncSetAttribute)");
@@ -958,6 +1182,8 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
   cudaStream_t st = as_stream(stream);
   if (taps == 9 && epi == EPI_C8)
     tc_dispatch<9, EPI_C8>(p.j, (unsigned)grid, smem_bytes, st, maps, p);
+  else if (taps == 9 && epi == EPI_UP2)
+    tc_dispatch<9, EPI_UP2>(p.j, (unsigned)grid, smem_bytes, st, maps, p);
   else if (taps == 1 && epi == EPI_NCHW_F32)
     tc_dispatch<1, EPI_NCHW_F32>(p.j, (unsigned)grid, smem_bytes, st, maps, p);
   else if (taps == 1 && epi == EPI_SOFTARGMAX)
@@ -983,6 +1209,112 @@ int ynet_tc_conv3x3(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int32_t H
   TcOut o{out_c8, nullptr, nullptr};
   return tc_launch("ynet_tc_conv3x3", srcs, n_src, N, H, W, packed_weight, bias, C_out, relu, C_out_pad, tune, 9, EPI_C8, o,
                    nullptr, stream);
+}
+
+int ynet_tc_upconv_phase_weights(const float* weight, const float* bias, int32_t C_out, int32_t C_in, float* w_eff,
+                                 float* bias_eff, void* stream) {
+  YNET_CHECK_ARG(weight && w_eff && bias_eff, "null pointer");
+  YNET_CHECK_ARG(C_out > 0 && C_in > 0, "bad shape");
+  const int cp = ceil_div(C_out, 16) * 16;
+  upconv_phase_weights_kernel<<<grid_1d((long long)4 * cp * C_in * 9), 256, 0, as_stream(stream)>>>(
+      weight, bias, C_out, C_in, cp, w_eff, bias_eff);
+  YNET_LAUNCH_CHECK();
+  return YNET_OK;
+}
+
+static inline int upb_og(int cp) { return cp >= 32 ? 32 : 16; }
+
+int64_t ynet_tc_upconv_border_weight_bytes(int32_t C_out, int32_t n_src, const int32_t* src_channels_host) {
+  if (C_out <= 0 || n_src <= 0 || n_src > YNET_MAX_SOURCES || !src_channels_host) return 0;
+  const int cp = ceil_div(C_out, 16) * 16;
+  long long cpad = 0;
+  for (int i = 0; i < n_src; ++i) cpad += ceil_div(src_channels_host[i], 8) * 8;
+  return cpad * 9 * cp * (long long)sizeof(float);
+}
+
+int ynet_tc_upconv_border_weights(const float* weight, int32_t C_out, int32_t n_src, const int32_t* src_channels_host,
+                                  float* out, void* stream) {
+  YNET_CHECK_ARG(weight && out && src_channels_host, "null pointer");
+  YNET_CHECK_ARG(C_out > 0 && n_src >= 1 && n_src <= YNET_MAX_SOURCES, "bad shape");
+  UpBorderPack ps;
+  memset(&ps, 0, sizeof(ps));
+  ps.n_src = n_src;
+  int cin = 0, cpad = 0;
+  for (int i = 0; i < n_src; ++i) {
+    YNET_CHECK_ARG(src_channels_host[i] > 0, "bad source channels");
+    ps.real[i] = src_channels_host[i];
+    cin += src_channels_host[i];
+    cpad += ceil_div(src_channels_host[i], 8) * 8;
+  }
+  const int cp = ceil_div(C_out, 16) * 16;
+  const int og = upb_og(cp);
+  upconv_border_weights_kernel<<<grid_1d((long long)cpad * 9 * cp), 256, 0, as_stream(stream)>>>(
+      weight, C_out, cin, ps, cpad, og, cp / og, out);
+  YNET_LAUNCH_CHECK();
+  return YNET_OK;
+}
+
+int ynet_tc_upconv3x3(const ynet_tc_src* srcs, const int32_t* src_channels_host, int32_t n_src, int32_t N, int32_t h,
+                      int32_t w, const void* packed_phase_weight, const float* bias_eff, const float* border_weight,
+                      const float* bias, int32_t C_out, int32_t relu, void* out_c8, int32_t tune, void* stream) {
+  YNET_CHECK_ARG(out_c8 != nullptr || N == 0, "null output");
+  YNET_CHECK_ALIGN(out_c8, 16);
+  YNET_CHECK_ARG(srcs && src_channels_host && border_weight, "null pointer");
+  YNET_CHECK_ALIGN(border_weight, 16);
+  YNET_CHECK_ARG(C_out > 0 && C_out <= 64, "C_out must be <= 64 (4 * C_out_pad <= 256 accumulator columns)");
+  if (relu != 0) {
+    set_error("ynet_tc_upconv3x3: ReLU is not supported (ynet.py:464 applies none after upsample_conv)");
+    return YNET_E_UNSUPPORTED;
+  }
+  const int cp = ceil_div(C_out, 16) * 16;
+  TcOut o{out_c8, nullptr, nullptr};
+  int rc = tc_launch("ynet_tc_upconv3x3", srcs, n_src, N, h, w, packed_phase_weight, bias_eff, 4 * cp, 0, 4 * cp, tune, 9,
+                     EPI_UP2, o, nullptr, stream);
+  if (rc != YNET_OK || N == 0) return rc;
+  if (const char* e = getenv("YNET_UPCONV_SKIP_BORDER"))   // profiling aid: time the tensor-core part alone
+    if (e[0] == '1') return YNET_OK;
+  UpBorderSrc bs;
+  memset(&bs, 0, sizeof(bs));
+  bs.n_src = n_src;
+  int cpad = 0;
+  for (int i = 0; i < n_src; ++i) {
+    YNET_CHECK_ARG(src_channels_host[i] > 0 && src_channels_host[i] <= srcs[i].channels_pad, "bad source channels");
+    bs.ptr[i] = reinterpret_cast<const uint4*>(srcs[i].ptr);
+    bs.batch_stride[i] = srcs[i].batch_stride / 8;
+    bs.real_chunks[i] = ceil_div(src_channels_host[i], 8);
+    bs.batch_mod[i] = srcs[i].batch_mod;
+    cpad += bs.real_chunks[i] * 8;
+  }
+  const int og = upb_og(cp);
+  const size_t smem = (size_t)cpad * 9 * og * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("ynet_tc_upconv3x3: border weights (%d channels x 9 x %d) exceed shared memory", cpad, og);
+    return YNET_E_UNSUPPORTED;
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(upconv_border_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(upconv_border_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "ynet_tc_upconv3x3(cudaFuncSetAttribute)");
+    configured = true;
+  }
+  const int ring = (h >= 2 && w >= 2) ? 2 * w + 2 * (h - 2) : h * w;
+  const long long total = (long long)N * ring * 4;
+  const int groups = cp / og;
+  const int per_sm = smem > 100 * 1024 ? 1 : (smem > 64 * 1024 ? 2 : 3);
+  const unsigned gx = (unsigned)tmax<long long>(
+      1, tmin<long long>(ceil_div<long long>(total, UPB_THREADS), (long long)ceil_div(per_sm * sm_count(), groups)));
+  dim3 grid(gx, groups);
+  __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(out_c8);
+  if (og == 16)
+    upconv_border_kernel<16><<<grid, UPB_THREADS, smem, as_stream(stream)>>>(bs, N, h, w, border_weight, bias, C_out, cpad,
+                                                                             outp, cp);
+  else
+    upconv_border_kernel<32><<<grid, UPB_THREADS, smem, as_stream(stream)>>>(bs, N, h, w, border_weight, bias, C_out, cpad,
+                                                                             outp, cp);
+  YNET_LAUNCH_CHECK();
+  return YNET_OK;
 }
 
 int ynet_tc_conv1x1_f32(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int32_t H, int32_t W, const void* packed_weight,

@@ -1,5 +1,7 @@
 // a1/a3/a9: template creation, trajectory-heatmap rasterisation, waypoint pyramid.
 // HBM-bound kernels: coalesced 128-bit stores, template reads served from L2 (4.4-7.7 MB << 126 MB).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace ynet {
@@ -136,6 +138,120 @@ avgpool_pyramid_kernel(const float* __restrict__ in, int H, int W, int n_levels,
   }
 }
 
+// ---- a3 + a9 fused for the tensor-core engine: waypoint maps -> bf16 C8 pyramid ------------------------------
+// One CTA = one 32x32 full-resolution block of one image: gathers the n_ch (<= 8) template windows into shared
+// memory, then writes every pyramid level as C8 planes (16 B = 8 bf16 channels per pixel; channels >= n_ch zero).
+// Replaces rasterize_gather + avgpool_pyramid + n_levels pack_c8 launches (and their float32 round trips).
+struct PyramidC8Outs {
+  uint4* p[6];
+};
+
+__device__ __forceinline__ uint4 pack8_bf16(const float* f) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(f[4], f[5]), d = __floats2bfloat162_rn(f[6], f[7]);
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&a);
+  o.y = *reinterpret_cast<uint32_t*>(&b);
+  o.z = *reinterpret_cast<uint32_t*>(&c);
+  o.w = *reinterpret_cast<uint32_t*>(&d);
+  return o;
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(256)
+wp_pyramid_c8_kernel(const float* __restrict__ tmpl, int th, int tw, const float* __restrict__ coords, int H, int W,
+                     int n_levels, int chunks, int write_pad, PyramidC8Outs outs, int* __restrict__ oob) {
+  __shared__ float s0[NCH][32][33];
+  __shared__ float s1[NCH][16][17];
+  __shared__ float s2[NCH][8][9];
+  __shared__ float s3[NCH][4][5];
+  __shared__ float s4[NCH][2][3];
+  const int n = blockIdx.z;
+  const int ty0 = blockIdx.y * 32, tx0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int x = __float2int_rn(coords[2 * (n * NCH + c) + 0]);  // round half to even == np.round
+    const int y = __float2int_rn(coords[2 * (n * NCH + c) + 1]);
+    const int yl = th / 2 - y, xl = tw / 2 - x;
+    const bool bad = (yl < 0) | (xl < 0) | (yl + H > th) | (xl + W > tw);
+    if (bad && oob != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) atomicExch(oob, 1);
+    const int sx = min(max(xl + tx0 + tx, 0), tw - 1);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int sy = min(max(yl + ty0 + ty + 8 * r, 0), th - 1);
+      s0[c][ty + 8 * r][tx] = __ldg(tmpl + (size_t)sy * tw + sx);
+    }
+  }
+  __syncthreads();
+  {  // level 0: 32 x 32, 4 pixels per thread
+    uint4* o = outs.p[0] + (size_t)n * chunks * H * W;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float f[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) f[c] = (c < NCH) ? s0[c < NCH ? c : 0][ty + 8 * r][tx] : 0.f;
+      const size_t pix = (size_t)(ty0 + ty + 8 * r) * W + tx0 + tx;
+      o[pix] = pack8_bf16(f);
+      if (write_pad)
+        for (int k = 1; k < chunks; ++k) o[(size_t)k * H * W + pix] = zero;
+    }
+  }
+  const int t = threadIdx.x;
+  auto reduce = [&](auto& src, auto& dst, int side, int lvl) {   // side = output block edge at this level
+    if (t < side * side) {
+      const int y = t / side, x = t - y * side;
+      float f[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c < NCH) {
+          const int cc = c < NCH ? c : 0;
+          const float v = 0.25f * ((src[cc][2 * y][2 * x] + src[cc][2 * y][2 * x + 1]) +
+                                   (src[cc][2 * y + 1][2 * x] + src[cc][2 * y + 1][2 * x + 1]));
+          dst[cc][y][x] = v;
+          f[c] = v;
+        } else {
+          f[c] = 0.f;
+        }
+      }
+      const int h = H >> lvl, w = W >> lvl;
+      const size_t pix = (size_t)((ty0 >> lvl) + y) * w + (tx0 >> lvl) + x;
+      uint4* o = outs.p[lvl] + (size_t)n * chunks * h * w;
+      o[pix] = pack8_bf16(f);
+      if (write_pad)
+        for (int k = 1; k < chunks; ++k) o[(size_t)k * h * w + pix] = zero;
+    }
+  };
+  if (n_levels <= 1) return;
+  reduce(s0, s1, 16, 1);
+  if (n_levels <= 2) return;
+  __syncthreads();
+  reduce(s1, s2, 8, 2);
+  if (n_levels <= 3) return;
+  __syncthreads();
+  reduce(s2, s3, 4, 3);
+  if (n_levels <= 4) return;
+  __syncthreads();
+  reduce(s3, s4, 2, 4);
+  if (n_levels <= 5) return;
+  __syncthreads();
+  if (t == 0) {
+    float f[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      f[c] = (c < NCH) ? 0.25f * ((s4[c < NCH ? c : 0][0][0] + s4[c < NCH ? c : 0][0][1]) +
+                                  (s4[c < NCH ? c : 0][1][0] + s4[c < NCH ? c : 0][1][1]))
+                       : 0.f;
+    const int h = H >> 5, w = W >> 5;
+    const size_t pix = (size_t)(ty0 >> 5) * w + (tx0 >> 5);
+    uint4* o = outs.p[5] + (size_t)n * chunks * h * w;
+    o[pix] = pack8_bf16(f);
+    if (write_pad)
+      for (int k = 1; k < chunks; ++k) o[(size_t)k * h * w + pix] = zero;
+  }
+}
+
 }  // namespace ynet
 
 using namespace ynet;
@@ -206,6 +322,46 @@ int ynet_avgpool_pyramid(const float* in, int32_t n, int32_t H, int32_t W, int32
       o.p[i] = (i < n_levels - 1) ? outs_host[i] + (size_t)n0 * (H >> (i + 1)) * (W >> (i + 1)) : nullptr;
     dim3 grid(W / 32, H / 32, nn);
     avgpool_pyramid_kernel<<<grid, 256, 0, as_stream(stream)>>>(in + (size_t)n0 * H * W, H, W, n_levels, o);
+    YNET_LAUNCH_CHECK();
+  }
+  return YNET_OK;
+}
+
+int ynet_tc_rasterize_pyramid_c8(const float* tmpl, int32_t th, int32_t tw, const float* coords, int32_t n_img,
+                                 int32_t n_ch, int32_t H, int32_t W, int32_t n_levels, void* const* outs_host,
+                                 int32_t C_pad, int32_t write_pad, int32_t* oob_flag, void* stream) {
+  YNET_CHECK_ARG(n_img >= 0 && n_ch >= 1 && n_ch <= 8 && H > 0 && W > 0 && th >= H && tw >= W, "bad shape (n_ch <= 8)");
+  YNET_CHECK_ARG(n_levels >= 1 && n_levels <= 6 && C_pad >= 8 && C_pad % 8 == 0, "n_levels in [1, 6], C_pad % 8 == 0");
+  if (H % 32 != 0 || W % 32 != 0) {
+    set_error("ynet_tc_rasterize_pyramid_c8: H and W must be multiples of 32 (trainer.py:60,581)");
+    return YNET_E_UNSUPPORTED;
+  }
+  if (n_img == 0) return YNET_OK;
+  YNET_CHECK_ARG(tmpl && coords && outs_host, "null pointer");
+  const int chunks = C_pad / 8;
+  for (int n0 = 0; n0 < n_img; n0 += 65535) {
+    const int nn = min(65535, n_img - n0);
+    PyramidC8Outs o;
+    for (int i = 0; i < 6; ++i) {
+      o.p[i] = nullptr;
+      if (i < n_levels) {
+        YNET_CHECK_ARG(outs_host[i] != nullptr, "null output level");
+        YNET_CHECK_ALIGN(outs_host[i], 16);
+        o.p[i] = reinterpret_cast<uint4*>(outs_host[i]) + (size_t)n0 * chunks * (H >> i) * (W >> i);
+      }
+    }
+    dim3 grid(W / 32, H / 32, nn);
+    const float* c = coords + 2 * (size_t)n0 * n_ch;
+    cudaStream_t st = as_stream(stream);
+#define YNET_WP_CASE(K)                                                                                              \
+  case K:                                                                                                            \
+    wp_pyramid_c8_kernel<K><<<grid, 256, 0, st>>>(tmpl, th, tw, c, H, W, n_levels, chunks, write_pad, o, oob_flag); \
+    break;
+    switch (n_ch) {
+      YNET_WP_CASE(1) YNET_WP_CASE(2) YNET_WP_CASE(3) YNET_WP_CASE(4) YNET_WP_CASE(5) YNET_WP_CASE(6) YNET_WP_CASE(7)
+      YNET_WP_CASE(8)
+    }
+#undef YNET_WP_CASE
     YNET_LAUNCH_CHECK();
   }
   return YNET_OK;

@@ -149,6 +149,28 @@ class YNetEngine:
                                                     p.bias.detach()))
         return ops.predictor_softargmax_f32(x, p.weight.detach().reshape(p.weight.shape[0], -1), p.bias.detach())
 
+    def decode_trajectories(self, feats, waypoint_samples, template, H, W, max_passes=256):
+        """The per-goal loop of evaluate.py:248-266 as stacked passes: rasterise every sampled waypoint set,
+        build its AvgPool pyramid, run the trajectory decoder on cat(features, pyramid) and soft-argmax.
+
+        waypoint_samples (G, B, n_wp, 2) -> trajectories (G, B, pred_len, 2).  Goal-major stacking: image
+        g * B + b of a launch reads the features of agent b (``n % B``).
+        """
+        G, B, n_wp, _ = waypoint_samples.shape
+        pred_len = self.model.traj_decoder.predictor.weight.shape[0]
+        trajs = torch.empty(G, B, pred_len, 2, dtype=torch.float32, device=waypoint_samples.device)
+        gc = max(1, min(G, max_passes // max(B, 1)))
+        for g0 in range(0, G, gc):
+            g1 = min(G, g0 + gc)
+            wp = waypoint_samples[g0:g1].reshape(-1, 2)                      # ((g1-g0)*B*n_wp, 2)
+            wmap = ops.rasterize_patches(template, wp, H, W).view((g1 - g0) * B, n_wp, H, W)
+            pyr = ops.avgpool_pyramid(wmap, len(feats))
+            traj_input = [ChannelCat(tuple(f) + (p,)) if isinstance(f, tuple) else ChannelCat((f, p))
+                          for f, p in zip(feats, pyr)]
+            trajs[g0:g1] = self.decoder_softargmax(self.model.traj_decoder, 'traj_decoder',
+                                                   traj_input).view(g1 - g0, B, -1, 2)
+        return trajs
+
 
 class YNetEngineTC(YNetEngine):
     """Throughput back end: tcgen05 implicit-GEMM convs on bf16 C8 planes (conv_tc.cu).
@@ -157,6 +179,8 @@ class YNetEngineTC(YNetEngine):
     semantic map, waypoint pyramids) are converted on entry with ``tc_pack``; the 1x1 predictor reads
     bf16 and writes float32 logits so that sigmoid / sampling / soft-argmax stay in fp32.
     """
+
+    upconv_max_cout = 16
 
     def __init__(self, model):
         super().__init__(model, backend='bf16')
@@ -187,6 +211,31 @@ class YNetEngineTC(YNetEngine):
             bias[:C_out] = module.bias.detach()
         self._wcache[key] = (ver, packed, bias)
         return packed, bias
+
+    def _tc_up_params(self, module, key, src_channels):
+        """Phase-decomposed weights of an upsample_conv (bilinear x2 folded into the stencil), cached by version."""
+        ver = (module.weight._version, module.weight.data_ptr(), tuple(src_channels))
+        hit = self._wcache.get(key + '#up')
+        if hit is not None and hit[0] == ver:
+            return hit[1:]
+        w = module.weight.detach().contiguous()
+        b = None if module.bias is None else module.bias.detach().contiguous()
+        w_eff, b_eff = ops.tc_upconv_phase_weights(w, b)
+        packed = ops.tc_pack_weights(w_eff, list(src_channels))
+        bw = ops.tc_upconv_border_weights(w, list(src_channels))
+        self._wcache[key + '#up'] = (ver, packed, b_eff, bw, b)
+        return packed, b_eff, bw, b
+
+    def _tupconv(self, module, key, sources):
+        """bilinear x2 + upsample_conv (ynet.py:463-464) in one launch on the low-resolution sources."""
+        # Measured on B200 (tools/bench_tc_conv.py, 240 images): the phase-decomposed form wins where the border ring
+        # is cheap (C_in * C_out small, i.e. the full-resolution upsample_conv.4: 0.88 ms vs 2.0 ms); at the deeper
+        # levels the CUDA-core ring recomputation costs more than the saved c8_upsample launch.
+        if module.weight.shape[0] > self.upconv_max_cout:
+            up = [ops.tc_upsample(s) for s in sources]
+            return self._tconv(module, key, up, False)
+        packed, b_eff, bw, b = self._tc_up_params(module, key, [s.C for s in sources])
+        return ops.tc_upconv3x3(sources, packed, b_eff, bw, b, module.weight.shape[0])
 
     def _tconv(self, module, key, sources, relu):
         packed, bias = self._tc_params(module, key, [s.C for s in sources])
@@ -222,7 +271,7 @@ class YNetEngineTC(YNetEngine):
         x = self._tconv(decoder.center[0], f'{key}.center.0', feats[0], True)
         x = self._tconv(decoder.center[2], f'{key}.center.2', [x], True)
         for i, skip in enumerate(feats[1:]):
-            up = self._tconv(decoder.upsample_conv[i], f'{key}.upsample_conv.{i}', [ops.tc_upsample(x)], False)
+            up = self._tupconv(decoder.upsample_conv[i], f'{key}.upsample_conv.{i}', [x])
             x = self._tconv(decoder.decoder[i][0], f'{key}.decoder.{i}.0', [up] + skip, True)
             x = self._tconv(decoder.decoder[i][2], f'{key}.decoder.{i}.2', [x], True)
         return x
@@ -231,6 +280,28 @@ class YNetEngineTC(YNetEngine):
         x = self.decoder_trunk(decoder, key, features)
         packed, bias = self._tc_params(decoder.predictor, f'{key}.predictor', [x.C])
         return ops.tc_conv1x1_f32(x, packed, bias, decoder.predictor.weight.shape[0])
+
+    def decode_trajectories(self, feats, waypoint_samples, template, H, W, max_passes=256):
+        """Agent-major stacking: the G passes of one agent are consecutive images of a launch, so the agent's
+        encoder features (``n // G``) are re-read from L2 instead of HBM; chunks walk the agents.  The waypoint
+        maps and their pyramid are rasterised straight into bf16 C8 planes (one launch per chunk)."""
+        G, B, n_wp, _ = waypoint_samples.shape
+        if n_wp > 8:
+            return super().decode_trajectories(feats, waypoint_samples, template, H, W, max_passes)
+        pred_len = self.model.traj_decoder.predictor.weight.shape[0]
+        trajs = torch.empty(G, B, pred_len, 2, dtype=torch.float32, device=waypoint_samples.device)
+        feats = [self._c8_parts(f) for f in feats]
+        bc = max(1, min(B, max_passes // max(G, 1)))
+        for b0 in range(0, B, bc):
+            b1 = min(B, b0 + bc)
+            nb = b1 - b0
+            wp = waypoint_samples[:, b0:b1].permute(1, 0, 2, 3).reshape(-1, 2).contiguous()   # (nb, G, n_wp) order
+            pyr = ops.tc_rasterize_pyramid(template, wp, nb * G, n_wp, H, W, len(feats))
+            traj_input = [ChannelCat(tuple(c.batch_slice(b0, b1).repeat_interleave(G) for c in f) + (p,))
+                          for f, p in zip(feats, pyr)]
+            out = self.decoder_softargmax(self.model.traj_decoder, 'traj_decoder', traj_input)   # (nb*G, pred, 2)
+            trajs[:, b0:b1] = out.view(nb, G, pred_len, 2).permute(1, 0, 2, 3)
+        return trajs
 
     def decoder_softargmax(self, decoder, key, features):
         """predictor + SoftArgmax2D fused into the tensor-core kernel's epilogue (logits never reach HBM)."""

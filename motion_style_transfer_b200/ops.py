@@ -546,16 +546,28 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999
 
 # ------------------------------------------------------------------------------------------------ a4-a8 tensor-core engine
 class C8:
-    """bf16 activation in C8 planes: data (N, C_pad/8, H, W, 8) bfloat16, logical channel count C."""
+    """bf16 activation in C8 planes: data (N, C_pad/8, H, W, 8) bfloat16, logical channel count C.
 
-    __slots__ = ('data', 'C')
+    ``rep`` > 1 makes a lazy ``repeat_interleave(rep, dim=0)``: as a conv source, image n reads data[n // rep]
+    (agent-major stacking of the n_goal decoder passes; nothing is copied).
+    """
 
-    def __init__(self, data, C):
-        self.data, self.C = data, C
+    __slots__ = ('data', 'C', 'rep')
+
+    def __init__(self, data, C, rep=1):
+        self.data, self.C, self.rep = data, C, rep
 
     @property
     def N(self):
-        return self.data.shape[0]
+        return self.data.shape[0] * self.rep
+
+    def repeat_interleave(self, rep):
+        return C8(self.data, self.C, self.rep * rep)
+
+    def batch_slice(self, b0, b1):
+        if self.rep != 1:
+            raise ValueError('batch_slice of a repeated C8')
+        return C8(self.data[b0:b1], self.C)
 
     @property
     def C_pad(self):
@@ -594,6 +606,44 @@ def tc_pack(x):
                                           _stream()), 'tc_pack_f32_to_c8')
     _count()
     return C8(out, C)
+
+
+_zero_planes = {}
+
+
+def tc_rasterize_pyramid(template, coords, n_img, n_ch, H, W, n_levels, slot=0):
+    """get_patch + AvgPool pyramid of ``n_img x n_ch`` waypoint coordinates written straight as bf16 C8 planes
+    (image_utils.py:40-63 + evaluate.py:255-257).  Returns n_levels C8 (n_img, 16-padded, H>>l, W>>l).
+
+    The outputs live in persistent buffers keyed by (shape, slot): their padding chunk is zeroed once and never
+    written again, so a call only writes 16 B per pixel.  Successive calls with the same key reuse the buffers
+    (stream-ordered); pass distinct ``slot``s for results that must coexist.
+    """
+    template = _req(template, name='template')
+    coords = _req(coords, name='coords').reshape(-1, 2)
+    if coords.shape[0] != n_img * n_ch:
+        raise ValueError(f'tc_rasterize_pyramid: expected {n_img * n_ch} coordinates, got {coords.shape[0]}')
+    key = (n_img, n_ch, H, W, n_levels, slot, template.device)
+    bufs = _zero_planes.get(key)
+    write_pad = 0
+    if bufs is None:
+        if torch.cuda.is_current_stream_capturing():
+            # graph-pool memory: cannot rely on a one-off memset, let the kernel write the padding every replay
+            bufs = [torch.empty(n_img, 2, H >> l, W >> l, 8, dtype=torch.bfloat16, device=template.device)
+                    for l in range(n_levels)]
+            write_pad = 1
+        else:
+            bufs = [torch.zeros(n_img, 2, H >> l, W >> l, 8, dtype=torch.bfloat16, device=template.device)
+                    for l in range(n_levels)]
+            _zero_planes[key] = bufs
+    outs = (ctypes.c_void_p * n_levels)(*[b.data_ptr() for b in bufs])
+    S = sum((H >> l) * (W >> l) for l in range(n_levels))
+    with _timed('wp_pyramid_c8_kernel', 0, (16.0 * S + 4.0 * n_ch * H * W) * n_img):
+        check(_L().ynet_tc_rasterize_pyramid_c8(_ptr(template), template.shape[0], template.shape[1], _ptr(coords), n_img,
+                                                n_ch, H, W, n_levels, outs, 16, write_pad, None, _stream()),
+              'tc_rasterize_pyramid_c8')
+    _count()
+    return [C8(b, n_ch) for b in bufs]
 
 
 def tc_unpack(a):
@@ -635,13 +685,26 @@ def tc_pack_weights(weight_oihw, src_channels):
     return packed
 
 
+def _tc_batch_mod(s, N):
+    """ynet_tc_src.batch_mod of source ``s`` inside a conv over N images (see include/ynet_b200.h)."""
+    if s.rep > 1:
+        if s.N != N:
+            raise ValueError(f'repeated source covers {s.N} images, the conv has N={N}')
+        return -s.rep
+    if 1 < s.N < N:
+        if N % s.N != 0:
+            raise ValueError(f'source batch {s.N} does not divide N={N}')
+        return s.N
+    return 0
+
+
 def _tc_src_array(sources, N):
     arr = (_lib.TcSrc * len(sources))()
     for i, s in enumerate(sources):
         arr[i].ptr = s.data.data_ptr()
         arr[i].channels_pad = s.C_pad
         arr[i].batch_stride = 0 if (s.N == 1 and N > 1) else s.data.stride(0)
-        arr[i].batch_mod = s.N if (1 < s.N < N) else 0
+        arr[i].batch_mod = _tc_batch_mod(s, N)
     return arr
 
 
@@ -681,9 +744,7 @@ def tc_conv3x3(sources, packed_weight, bias_pad, C_out, relu):
         arr[i].ptr = s.data.data_ptr()
         arr[i].channels_pad = s.C_pad
         arr[i].batch_stride = 0 if (s.N == 1 and N > 1) else s.data.stride(0)
-        arr[i].batch_mod = s.N if (1 < s.N < N) else 0
-        if 1 < s.N < N and N % s.N != 0:
-            raise ValueError(f'tc_conv3x3: source batch {s.N} does not divide N={N}')
+        arr[i].batch_mod = _tc_batch_mod(s, N)
     cp = _pad16(C_out)
     out = torch.empty(N, cp // 8, H, W, 8, dtype=torch.bfloat16, device=sources[0].data.device)
     cin_pad = sum(s.C_pad for s in sources)
@@ -699,13 +760,72 @@ def tc_conv3x3(sources, packed_weight, bias_pad, C_out, relu):
     return C8(out, C_out)
 
 
+def tc_upconv_phase_weights(weight_oihw, bias):
+    """(C_out, C_in, 3, 3) weight of an upsample_conv -> (w_eff (4*cp, C_in, 3, 3), bias_eff (4*cp,)) of the
+    equivalent low-resolution phase conv (see ynet_tc_upconv_phase_weights)."""
+    weight_oihw = _req(weight_oihw, name='weight')
+    C_out, C_in = weight_oihw.shape[:2]
+    cp = _pad16(C_out)
+    w_eff = torch.empty(4 * cp, C_in, 3, 3, dtype=torch.float32, device=weight_oihw.device)
+    b_eff = torch.empty(4 * cp, dtype=torch.float32, device=weight_oihw.device)
+    check(_L().ynet_tc_upconv_phase_weights(_ptr(weight_oihw), _ptr(bias), C_out, C_in, _ptr(w_eff), _ptr(b_eff),
+                                            _stream()), 'tc_upconv_phase_weights')
+    _count()
+    return w_eff, b_eff
+
+
+def tc_upconv_border_weights(weight_oihw, src_channels):
+    """float32 OIHW weight -> the shared-memory image of the border-ring kernel (see ynet_tc_upconv_border_weights)."""
+    weight_oihw = _req(weight_oihw, name='weight')
+    n = len(src_channels)
+    real = (ctypes.c_int32 * n)(*src_channels)
+    nbytes = _L().ynet_tc_upconv_border_weight_bytes(weight_oihw.shape[0], n, real)
+    out = torch.empty(nbytes // 4, dtype=torch.float32, device=weight_oihw.device)
+    check(_L().ynet_tc_upconv_border_weights(_ptr(weight_oihw), weight_oihw.shape[0], n, real, _ptr(out), _stream()),
+          'tc_upconv_border_weights')
+    _count()
+    return out
+
+
+def tc_upconv3x3(sources, packed_phase_weight, bias_eff, border_weight, bias, C_out):
+    """bilinear x2 + conv3x3 (ynet.py:463-464) of low-resolution C8 sources -> C8 (N, C_out, 2h, 2w), without
+    materialising the upsampled tensor."""
+    N = max(s.N for s in sources)
+    h, w = sources[0].H, sources[0].W
+    arr = (_lib.TcSrc * len(sources))()
+    for i, s in enumerate(sources):
+        if s.H != h or s.W != w:
+            raise ValueError('tc_upconv3x3: sources must share the spatial size')
+        arr[i].ptr = s.data.data_ptr()
+        arr[i].channels_pad = s.C_pad
+        arr[i].batch_stride = 0 if (s.N == 1 and N > 1) else s.data.stride(0)
+        arr[i].batch_mod = _tc_batch_mod(s, N)
+    real = (ctypes.c_int32 * len(sources))(*[s.C for s in sources])
+    cp = _pad16(C_out)
+    out = torch.empty(N, cp // 8, 2 * h, 2 * w, 8, dtype=torch.bfloat16, device=sources[0].data.device)
+    cin_pad = sum(s.C_pad for s in sources)
+    args = (arr, real, len(sources), N, h, w, _ptr(packed_phase_weight), _ptr(bias_eff), _ptr(border_weight), _ptr(bias),
+            C_out, 0, _ptr(out))
+    key = ('up', tuple(s.C_pad for s in sources), cp, h, w, min(N, 64))
+    tune = _tc_tune.get(key)
+    if tune is None:
+        tune = (_tc_autotune(key, args, fn='ynet_tc_upconv3x3', n_pad=4 * cp)
+                if (tc_autotune_enabled and not torch.cuda.is_current_stream_capturing()) else 0)
+    with _timed('tc_upconv3x3_kernel', 2.0 * 9 * sum(s.C for s in sources) * C_out * 4 * h * w * N,
+                (2.0 * cin_pad + 8.0 * cp) * h * w * N, tag=f'{cin_pad}->{cp}@up{2 * h}x{2 * w} N={N}'):
+        check(_L().ynet_tc_upconv3x3(*args, tune, _stream()), 'tc_upconv3x3')
+    _count(2)
+    return C8(out, C_out)
+
+
 tc_autotune_enabled = os.environ.get('YNET_TC_AUTOTUNE', '1') != '0'
 _tc_tune = {}
 
 
-def _tc_autotune(key, args):
+def _tc_autotune(key, args, fn='ynet_tc_conv3x3', n_pad=None):
     """Pick (accumulators per tile, CTAs per SM, stages) for one layer shape by timing the candidates once."""
-    cp = key[1]
+    cp = key[1] if n_pad is None else n_pad
+    launch = getattr(_L(), fn)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cands = [j | (ctas << 4) | (stages << 8) for j in (1, 2, 3) if j <= max(1, 512 // (2 * cp))
              for ctas in (2, 1) for stages in (6, 3)]
@@ -713,7 +833,7 @@ def _tc_autotune(key, args):
     def run(tune, reps):
         e0.record()
         for _ in range(reps):
-            check(_L().ynet_tc_conv3x3(*args, tune, _stream()), 'tc_conv3x3(autotune)')
+            check(launch(*args, tune, _stream()), fn + '(autotune)')
         e1.record()
         e1.synchronize()
         return e0.elapsed_time(e1) / reps

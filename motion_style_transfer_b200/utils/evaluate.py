@@ -117,17 +117,8 @@ def forecast_batch(model, scene_image, trajectory, input_template, waypoints, n_
         waypoint_samples = waypoint_samples.contiguous()
         G = waypoint_samples.shape[0]
 
-        # trajectory decoder: goals stacked along the batch axis; features are read modulo B
-        trajs = torch.empty(G, B, gt_future.shape[1], 2, dtype=torch.float32, device=trajectory.device)
-        gc = max(1, min(G, MAX_STACKED_PASSES // max(B, 1)))
-        for g0 in range(0, G, gc):
-            g1 = min(G, g0 + gc)
-            wp = waypoint_samples[g0:g1].reshape(-1, 2)                      # ((g1-g0)*B*n_wp, 2)
-            wmap = ops.rasterize_patches(input_template, wp, H, W).view((g1 - g0) * B, n_wp, H, W)
-            pyr = ops.avgpool_pyramid(wmap, len(feats))
-            traj_input = [ChannelCat(tuple(f) + (p,)) if isinstance(f, tuple) else ChannelCat((f, p))
-                          for f, p in zip(feats, pyr)]
-            trajs[g0:g1] = model.pred_traj_softargmax(traj_input).view(g1 - g0, B, -1, 2)
+        # trajectory decoder: the G = n_goal * n_traj passes are stacked along the batch axis by the engine
+        trajs = model.engine.decode_trajectories(feats, waypoint_samples, input_template, H, W, MAX_STACKED_PASSES)
         ade, fde = ops.ade_fde(gt_future, trajs, waypoint_samples, resize_factor)
     out = dict(ade=ade, fde=fde, trajs=trajs, waypoint_samples=waypoint_samples)
     if want_maps:

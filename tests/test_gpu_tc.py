@@ -149,3 +149,74 @@ def test_tc_predictor_logits_and_fused_softargmax(ops, cin, cout, H, W, N):
     packed50 = ops.tc_pack_weights((w * 8).cuda(), [cin])
     sa50 = ops.tc_conv1x1_softargmax(a, packed50, (bias * 8).cuda(), cout).cpu().numpy()
     np.testing.assert_allclose(sa50, O.softargmax2d(F.conv2d(x, w * 8, b * 8)).numpy(), rtol=0, atol=2e-2)
+
+
+def test_tc_conv_repeat_interleaved_source(ops):
+    """Agent-major stacking: a source with ``rep`` is read as image n // rep (no copy)."""
+    torch.manual_seed(4)
+    nb, G, H, W = 3, 4, 32, 24
+    feat = bf16_exact(torch.randn(nb, 32, H, W))
+    wp = bf16_exact(torch.randn(nb * G, 2, H, W))
+    w = bf16_exact(torch.randn(32, 34, 3, 3) * 0.1)
+    bias = torch.randn(32)
+    ref = F.relu(F.conv2d(torch.cat([feat.repeat_interleave(G, dim=0), wp], 1), w, bias, padding=1))
+    f8 = ops.tc_pack(feat.cuda())
+    srcs = [f8.batch_slice(0, nb).repeat_interleave(G), ops.tc_pack(wp.cuda())]
+    assert srcs[0].N == nb * G
+    packed = ops.tc_pack_weights(w.cuda(), [32, 2])
+    out = ops.tc_conv3x3(srcs, packed, bias.cuda(), 32, True)
+    assert rel_err(ops.tc_unpack(out).cpu().numpy(), ref.numpy()) < 5e-3
+    # a slice of the agents (chunked decoding): rows 1..2 only
+    out2 = ops.tc_conv3x3([f8.batch_slice(1, 3).repeat_interleave(G), ops.tc_pack(wp[G:].contiguous().cuda())], packed,
+                          bias.cuda(), 32, True)
+    assert torch.equal(ops.tc_unpack(out2), ops.tc_unpack(out)[G:])
+
+
+@pytest.mark.parametrize('n_img,n_ch,H,W', [(5, 2, 64, 96), (3, 1, 32, 32), (2, 8, 96, 64)])
+def test_tc_rasterize_pyramid_vs_oracle(ops, n_img, n_ch, H, W):
+    """get_patch + AvgPool2d(2^i) pyramid written straight as bf16 C8: equal to the oracle's float32 maps rounded
+    to bf16 (level 0 exactly; pooled levels within one bf16 ulp = 2^-8 relative, the 2x2 cascade sums in a
+    different order than AvgPool2d(2^i))."""
+    size = 300
+    tmpl = O.create_dist_mat(size).astype(np.float32)
+    g = torch.Generator().manual_seed(5)
+    coords = torch.rand(n_img * n_ch, 2, generator=g) * torch.tensor([W - 1.0, H - 1.0])
+    ref0 = torch.from_numpy(O.get_patch_stack(tmpl, coords.numpy(), H, W)).view(n_img, n_ch, H, W)
+    ref = O.avgpool_pyramid(ref0, 6)
+    for slot in (0, 0):          # second call reuses the persistent buffers (padding chunk stays zero)
+        pyr = ops.tc_rasterize_pyramid(torch.from_numpy(tmpl).cuda(), coords.cuda(), n_img, n_ch, H, W, 6, slot=slot)
+        for l, (a, r) in enumerate(zip(pyr, ref)):
+            assert a.C == n_ch and a.C_pad == 16 and a.data.shape == (n_img, 2, H >> l, W >> l, 8)
+            got = ops.tc_unpack(a).cpu()
+            if l == 0:
+                assert torch.equal(got, bf16_exact(r))
+            else:
+                assert rel_err(got.numpy(), r.numpy()) < 2.0 ** -7
+            assert float(a.data[:, 1].abs().max()) == 0.0
+            assert n_ch == 8 or float(a.data[:, 0, :, :, n_ch:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('cins,cout,h,w,N', [((32,), 16, 16, 24, 2), ((16,), 8, 13, 13, 3), ((64,), 32, 52, 52, 2),
+                                            ((130,), 64, 13, 13, 2), ((32,), 16, 208, 208, 1), ((8, 8), 4, 2, 2, 2),
+                                            ((16,), 8, 1, 1, 2)])
+def test_tc_upconv_vs_torch(ops, cins, cout, h, w, N):
+    """bilinear x2 + conv3x3 as one low-resolution phase conv (+ exact border ring) vs F.interpolate + F.conv2d."""
+    torch.manual_seed(6)
+    xs = [bf16_exact(torch.relu(torch.randn(N, c, h, w))) for c in cins]
+    wgt = torch.randn(cout, sum(cins), 3, 3) * 0.1
+    b = torch.randn(cout)
+    up = F.interpolate(torch.cat(xs, 1), scale_factor=2, mode='bilinear', align_corners=False)
+    ref = F.conv2d(up, wgt, b, padding=1)
+    srcs = [ops.tc_pack(x.cuda()) for x in xs]
+    w_eff, b_eff = ops.tc_upconv_phase_weights(wgt.cuda(), b.cuda())
+    packed = ops.tc_pack_weights(w_eff, list(cins))
+    bw = ops.tc_upconv_border_weights(wgt.cuda().contiguous(), list(cins))
+    out = ops.tc_upconv3x3(srcs, packed, b_eff, bw, b.cuda(), cout)
+    got = ops.tc_unpack(out).cpu()
+    assert got.shape == ref.shape
+    # bf16 rounding of the folded weights and of the output: 2^-8 relative each
+    assert rel_err(got.numpy(), ref.numpy()) < 8e-3
+    # the border ring is recomputed from the float32 weights: only the output rounding remains
+    ring = torch.ones_like(ref, dtype=torch.bool)
+    ring[:, :, 2:-2, 2:-2] = False
+    assert rel_err(got[ring].numpy(), ref[ring].numpy()) < 5e-3

@@ -41,3 +41,26 @@ for cins, cout, H, W in SHAPES:
     cin_pad = sum((c + 15) // 16 * 16 for c in cins)
     by = 2.0 * (cin_pad + (cout + 15) // 16 * 16) * H * W * N
     print(f'{str(cins):>14} -> {cout:3d} @{H:3d}  {ms:8.3f} ms  {fl / ms / 1e9:7.1f} TF/s  {by / ms / 1e6:7.1f} GB/s')
+
+UP_SHAPES = [((32,), 16, 208, 208), ((64,), 32, 104, 104), ((64,), 32, 52, 52), ((64,), 32, 26, 26), ((128,), 64, 13, 13)]
+if os.environ.get('UP', '1') != '0':
+    for cins, cout, h, w in UP_SHAPES:
+        srcs = [ops.tc_pack(torch.randn(N, c, h, w, device='cuda')) for c in cins]
+        wgt = (torch.randn(cout, sum(cins), 3, 3, device='cuda') * 0.1).contiguous()
+        b = torch.zeros(cout, device='cuda')
+        w_eff, b_eff = ops.tc_upconv_phase_weights(wgt, b)
+        packed = ops.tc_pack_weights(w_eff, list(cins))
+        bw = ops.tc_upconv_border_weights(wgt, list(cins))
+        for _ in range(10):
+            ops.tc_upconv3x3(srcs, packed, b_eff, bw, b, cout)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.tc_upconv3x3(srcs, packed, b_eff, bw, b, cout)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        fl = 2.0 * 9 * sum(cins) * cout * 4 * h * w * N
+        print(f'up {str(cins):>10} -> {cout:3d} @{h:3d}->{2 * h:3d}  {ms:8.3f} ms  {fl / ms / 1e9:7.1f} TF/s  tune={ops._tc_tune}')
+        ops._tc_tune.clear()
