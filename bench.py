@@ -163,6 +163,7 @@ def main():
     ap.add_argument('--ref-agents', type=int, default=2, help='agents per step of the CPU reference arm')
     ap.add_argument('--cpu-agents', type=int, default=4, help='agents of the bounded cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-roofline', action='store_true', help='skip the per-launch eager timing pass')
     ap.add_argument('--profile-layers', default=None, help='write a per-layer timing table to this path')
     ap.add_argument('--no-graph', dest='graph', action='store_false',
                     help='issue every kernel from Python instead of replaying the captured CUDA graph')
@@ -291,7 +292,7 @@ def main():
 
     # ---- roofline of the dominant kernel: per-launch CUDA-event timing of one extra step -----------------
     roofline, layer_table = None, None
-    if rank == 0:
+    if rank == 0 and not args.no_roofline:
         peaks = load_peaks()
         _eager = lambda: forecast_batch(model, scene_dev, traj_dev[-1], tmpl, cfg['wps'], cfg['n_goal'], cfg['n_traj'],
                                         cfg['obs'], cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'],
