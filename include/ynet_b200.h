@@ -263,15 +263,18 @@ int ynet_tc_conv3x3(const ynet_tc_src* srcs_host, int32_t n_src, int32_t N, int3
                     const void* packed_weight, const float* bias, int32_t C_out, int32_t relu, void* out_c8,
                     int32_t C_out_pad, int32_t tune, void* stream);
 
-/* The 1x1 predictor (ynet.py:450-451,469) on the tensor cores, same kernel with one tap:
+/* The 1x1 predictor (ynet.py:450-451,469) on the tensor cores:
  *   ynet_tc_conv1x1_f32        -> float32 NCHW logits (goal decoder: sigmoid / sampling need the map);
- *   ynet_tc_conv1x1_softargmax -> predictor + SoftArgmax2D (ynet.py:582-583) fused in the epilogue: the
- *       logits go TMEM -> registers -> shared memory -> per-channel online soft-max partials, never to HBM.
- *       out (N, C_out, 2) = (x, y); C_out <= 32. */
+ *   ynet_tc_conv1x1_softargmax -> predictor + SoftArgmax2D (ynet.py:582-583, softargmax.py:55-81) in one
+ *       kernel (pred_tc.cu): the MMA runs with the weights as the M operand and the pixels as the N
+ *       operand, so the accumulator is transposed (TMEM lane = channel, column = pixel) and every epilogue
+ *       thread reduces pixels of ONE channel straight from tcgen05.ld -- the logits never reach shared
+ *       memory or HBM.  One source (C8, <= 128 channels); out (N, C_out, 2) = (x, y); C_out <= 32.
+ *       workspace: ynet_tc_conv1x1_softargmax_workspace_bytes(N, C_out, H, W). */
 int ynet_tc_conv1x1_f32(const ynet_tc_src* srcs_host, int32_t n_src, int32_t N, int32_t H, int32_t W,
                         const void* packed_weight, const float* bias, int32_t C_out, float* out, int32_t tune,
                         void* stream);
-int64_t ynet_tc_conv1x1_softargmax_workspace_bytes(int32_t N, int32_t C_out);
+int64_t ynet_tc_conv1x1_softargmax_workspace_bytes(int32_t N, int32_t C_out, int32_t H, int32_t W);
 int ynet_tc_conv1x1_softargmax(const ynet_tc_src* srcs_host, int32_t n_src, int32_t N, int32_t H, int32_t W,
                                const void* packed_weight, const float* bias, int32_t C_out, float* out,
                                void* workspace, int64_t workspace_bytes, int32_t tune, void* stream);

@@ -77,7 +77,7 @@ _PROTOS = {
     'ynet_tc_packed_weight_bytes': (_L, [_I, _I, POINTER(c_int32), _I]),
     'ynet_tc_pack_weights': (c_int, [_P, _I, _I, POINTER(c_int32), POINTER(c_int32), _I, _P, _P]),
     'ynet_tc_conv1x1_f32': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
-    'ynet_tc_conv1x1_softargmax_workspace_bytes': (_L, [_I, _I]),
+    'ynet_tc_conv1x1_softargmax_workspace_bytes': (_L, [_I, _I, _I, _I]),
     'ynet_tc_conv1x1_softargmax': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _P, _P, _L, _I, _P]),
     'ynet_tc_upconv_phase_weights': (c_int, [_P, _P, _I, _I, _P, _P, _P]),
     'ynet_tc_upconv_border_weight_bytes': (_L, [_I, _I, POINTER(c_int32)]),

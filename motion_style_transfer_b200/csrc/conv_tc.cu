@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace ynet {
 
@@ -28,7 +29,6 @@ constexpr int TC_KB = 16;                            // channels per pipeline st
 constexpr int TC_MAX_J = 3;                          // 4-D TMA box: (8J+2)*8 elements <= 256
 constexpr int TC_THREADS = 192;
 constexpr int TC_MAX_STAGES = 32;
-constexpr unsigned TC_SPIN_LIMIT = 4u * 1000u * 1000u;             // bounded waits: trap instead of hanging
 
 struct TcSrcDev {
   int kblocks;      // channels_pad / 16
@@ -57,94 +57,7 @@ struct TcParams {
   int* err;
 };
 
-constexpr int EPI_C8 = 0, EPI_NCHW_F32 = 1, EPI_SOFTARGMAX = 2, EPI_UP2 = 3;
-constexpr int TC_LOGIT_PITCH = 33;
-
-// ---- PTX wrappers --------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err) {
-  uint32_t done = 0;
-  unsigned spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > TC_SPIN_LIMIT) {  // a protocol bug must not hang the GPU
-      if (err) atomicExch(err, 1);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = sm_100)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
+constexpr int EPI_C8 = 0, EPI_NCHW_F32 = 1, EPI_UP2 = 3;
 
 // ---- the conv kernel -------------------------------------------------------------------------------------
 template <int J, int TAPS, int EPI>
@@ -292,33 +205,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     const int m = q * 32 + lane;         // accumulator row = pixel of the tile
     const int py = m >> 3, px = m & 7;
     const int n_chunks = p.n_pad >> 3;
-    // EPI_SOFTARGMAX: thread t reduces channel (t & 31) over pixel group (t >> 5) of every accumulator
-    const int et = threadIdx.x - 64;
-    const int ec = et & 31, eg = et >> 5;
-    float* s_logit = s_bias + 256;       // [128][TC_LOGIT_PITCH]
-    float st_m = -3.402823466e+38f, st_s = 0.f, st_sx = 0.f, st_sy = 0.f;
-    int cur_n = -1;
-    auto flush = [&](int n_img) {
-      // combine the 4 pixel groups of each channel and publish one partial per (image, channel, CTA)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      float4* s_comb = reinterpret_cast<float4*>(s_logit);
-      s_comb[eg * 32 + ec] = make_float4(st_m, st_s, st_sx, st_sy);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (eg == 0 && ec < p.c_out) {
-        float M = -3.402823466e+38f;
-        for (int g = 0; g < 4; ++g) M = fmaxf(M, s_comb[g * 32 + ec].x);
-        float S = 0.f, SX = 0.f, SY = 0.f;
-        for (int g = 0; g < 4; ++g) {
-          const float4 v = s_comb[g * 32 + ec];
-          const float f = (v.x == -3.402823466e+38f) ? 0.f : __expf(v.x - M);
-          S += v.y * f;
-          SX += v.z * f;
-          SY += v.w * f;
-        }
-        p.partial[((size_t)n_img * p.c_out + ec) * gridDim.x + blockIdx.x] = make_float4(M, S, SX, SY);
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    };
     long long it = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int n = (int)(tile / tiles_per_img);
@@ -327,12 +213,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       const int y = y0 + py, xb = x0 + px;
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      if (EPI == EPI_SOFTARGMAX && n != cur_n) {
-        if (cur_n >= 0) flush(cur_n);
-        st_m = -3.402823466e+38f;
-        st_s = st_sx = st_sy = 0.f;
-        cur_n = n;
-      }
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * J * p.n_pad);
@@ -389,47 +269,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
               for (int k = 0; k < 16; ++k)
                 if (c0 + k < p.c_out) p.out_f32[(((size_t)n * p.c_out + c0 + k) * p.H + y) * p.W + x] = f[k];
             }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) s_logit[m * TC_LOGIT_PITCH + c0 + k] = f[k];
           }
-        }
-        if (EPI == EPI_SOFTARGMAX) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (ec < p.c_out) {
-            float vals[32];
-            float mx = -3.402823466e+38f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int pp = eg * 32 + i;
-              const bool ok = (y0 + (pp >> 3) < p.H) && (x0 + 8 * jj + (pp & 7) < p.W);
-              vals[i] = ok ? s_logit[pp * TC_LOGIT_PITCH + ec] : -3.402823466e+38f;
-              mx = fmaxf(mx, vals[i]);
-            }
-            if (mx > st_m) {
-              const float sc = (st_m == -3.402823466e+38f) ? 0.f : __expf(st_m - mx);
-              st_s *= sc;
-              st_sx *= sc;
-              st_sy *= sc;
-              st_m = mx;
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int pp = eg * 32 + i;
-              const float e = (vals[i] == -3.402823466e+38f) ? 0.f : __expf(vals[i] - st_m);
-              st_s += e;
-              st_sx = fmaf(e, (float)(x0 + 8 * jj + (pp & 7)), st_sx);
-              st_sy = fmaf(e, (float)(y0 + (pp >> 3)), st_sy);
-            }
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
     }
-    if (EPI == EPI_SOFTARGMAX && cur_n >= 0) flush(cur_n);
   }
 
   tc_fence_before();
@@ -646,47 +492,6 @@ c8_predictor_kernel(const uint4* __restrict__ x, int chunks, int C_in, long long
   }
 }
 
-__global__ void __launch_bounds__(256) tc_partial_init_kernel(float4* __restrict__ part, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    part[i] = make_float4(-3.402823466e+38f, 0.f, 0.f, 0.f);
-}
-
-// one warp per (image, channel): combine the per-CTA partials, apply 1/(sum + 1e-6)  (softargmax.py:68)
-__global__ void __launch_bounds__(256)
-tc_partial_finalize_kernel(const float4* __restrict__ part, int rows, int slots, float* __restrict__ out) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
-  float m = -3.402823466e+38f, sm = 0.f, sx = 0.f, sy = 0.f;
-  for (int i = lane; i < slots; i += 32) {
-    const float4 v = part[(size_t)row * slots + i];
-    const float M = fmaxf(m, v.x);
-    const float fa = (m == -3.402823466e+38f) ? 0.f : __expf(m - M);
-    const float fb = (v.x == -3.402823466e+38f) ? 0.f : __expf(v.x - M);
-    sm = sm * fa + v.y * fb;
-    sx = sx * fa + v.z * fb;
-    sy = sy * fa + v.w * fb;
-    m = M;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, sm, o);
-    const float x2 = __shfl_xor_sync(0xffffffffu, sx, o), y2 = __shfl_xor_sync(0xffffffffu, sy, o);
-    const float M = fmaxf(m, m2);
-    const float fa = (m == -3.402823466e+38f) ? 0.f : __expf(m - M);
-    const float fb = (m2 == -3.402823466e+38f) ? 0.f : __expf(m2 - M);
-    sm = sm * fa + s2 * fb;
-    sx = sx * fa + x2 * fb;
-    sy = sy * fa + y2 * fb;
-    m = M;
-  }
-  if (lane == 0) {
-    const float inv = 1.0f / (sm + 1e-6f);
-    out[2 * row + 0] = sx * inv;
-    out[2 * row + 1] = sy * inv;
-  }
-}
-
 // ---- bilinear x2 + 3x3 conv as ONE low-resolution conv with 4 x C_out phase channels ------------------------
 // F.interpolate(scale 2, bilinear, align_corners=False) followed by conv3x3(pad 1) (ynet.py:463-464) is linear in
 // the low-resolution input x: the output pixel (2i + a, 2j + b) is a 3x3 stencil over x[i-1..i+1][j-1..j+1] whose
@@ -889,11 +694,7 @@ upconv_border_kernel(UpBorderSrc src, int N, int h, int w, const float* __restri
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
+EncodeTiledFn tc_get_encode() {
   static EncodeTiledFn fn = nullptr;
   if (fn == nullptr) {
     void* ptr = nullptr;
@@ -919,7 +720,7 @@ int ynet_tc_supported(void) {
   int dev = 0, ma = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   cudaDeviceGetAttribute(&ma, cudaDevAttrComputeCapabilityMajor, dev);
-  return (ma == 10 && get_encode() != nullptr) ? 1 : 0;
+  return (ma == 10 && tc_get_encode() != nullptr) ? 1 : 0;
 }
 
 int ynet_tc_pack_f32_to_c8(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, int64_t batch_stride,
@@ -1067,7 +868,7 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
     return YNET_E_ALIGN;
   }
   if (N == 0) return YNET_OK;
-  EncodeTiledFn encode = get_encode();
+  EncodeTiledFn encode = tc_get_encode();
   if (encode == nullptr) {
     set_error("%s: cuTensorMapEncodeTiled is not available from the driver", who);
     return YNET_E_UNSUPPORTED;
@@ -1144,7 +945,7 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
   const int wblk = taps * 2 * C_out_pad * 16;
   const long long wall = (long long)kb_total * wblk;
   const int budget = 200 * 1024;
-  const int tail = (2 * TC_MAX_STAGES + 5) * 8 + 16 + 256 * 4 + (epi == EPI_SOFTARGMAX ? 128 * TC_LOGIT_PITCH * 4 : 0);
+  const int tail = (2 * TC_MAX_STAGES + 5) * 8 + 16 + 256 * 4;
   const char* force_stream = getenv("YNET_TC_FORCE_STREAMED");
   p.resident = (wall + 4 * p.a_bytes + tail <= budget) && !(force_stream && force_stream[0] == '1');
   p.wres_bytes = p.resident ? (int)ceil_div<long long>(wall, 1024) * 1024 : 0;
@@ -1167,7 +968,6 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
     cudaError_t e = tc_configure<9, EPI_C8>();
     if (e == cudaSuccess) e = tc_configure<9, EPI_UP2>();
     if (e == cudaSuccess) e = tc_configure<1, EPI_NCHW_F32>();
-    if (e == cudaSuccess) e = tc_configure<1, EPI_SOFTARGMAX>();
     if (e != cudaSuccess) return cuda_fail(e, "tc_launch(cudaFuncSetAttribute)");
     configured = true;
   }
@@ -1186,8 +986,6 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
     tc_dispatch<9, EPI_UP2>(p.j, (unsigned)grid, smem_bytes, st, maps, p);
   else if (taps == 1 && epi == EPI_NCHW_F32)
     tc_dispatch<1, EPI_NCHW_F32>(p.j, (unsigned)grid, smem_bytes, st, maps, p);
-  else if (taps == 1 && epi == EPI_SOFTARGMAX)
-    tc_dispatch<1, EPI_SOFTARGMAX>(p.j, (unsigned)grid, smem_bytes, st, maps, p);
   else {
     set_error("%s: unsupported (taps, epilogue) combination", who);
     return YNET_E_UNSUPPORTED;
@@ -1323,38 +1121,6 @@ int ynet_tc_conv1x1_f32(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int32
   TcOut o{nullptr, out, nullptr};
   return tc_launch("ynet_tc_conv1x1_f32", srcs, n_src, N, H, W, packed_weight, bias, C_out, 0, ceil_div(C_out, 16) * 16, tune,
                    1, EPI_NCHW_F32, o, nullptr, stream);
-}
-
-int64_t ynet_tc_conv1x1_softargmax_workspace_bytes(int32_t N, int32_t C_out) {
-  return (int64_t)N * C_out * 2 * sm_count() * (int64_t)sizeof(float4);
-}
-
-int ynet_tc_conv1x1_softargmax(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int32_t H, int32_t W,
-                               const void* packed_weight, const float* bias, int32_t C_out, float* out, void* workspace,
-                               int64_t workspace_bytes, int32_t tune, void* stream) {
-  YNET_CHECK_ARG(out != nullptr || N == 0, "null output");
-  YNET_CHECK_ARG(C_out > 0 && C_out <= 32, "C_out must be <= 32 for the fused soft-argmax epilogue");
-  if (N == 0) return YNET_OK;
-  if (workspace == nullptr || workspace_bytes < ynet_tc_conv1x1_softargmax_workspace_bytes(N, C_out)) {
-    set_error("ynet_tc_conv1x1_softargmax: workspace too small");
-    return YNET_E_WORKSPACE;
-  }
-  YNET_CHECK_ALIGN(workspace, 16);
-  float4* part = reinterpret_cast<float4*>(workspace);
-  const int slots = 2 * sm_count();
-  const long long n_part = (long long)N * C_out * slots;
-  tc_partial_init_kernel<<<grid_1d(n_part), 256, 0, as_stream(stream)>>>(part, n_part);
-  YNET_LAUNCH_CHECK();
-  // the kernel indexes partials with gridDim.x slots per (image, channel): pin the slot count
-  int grid = slots;
-  TcOut o{nullptr, nullptr, part};
-  // run with exactly `grid` (<= slots) CTAs; the finalize pass reads `grid` slots per row
-  int rc = tc_launch("ynet_tc_conv1x1_softargmax", srcs, n_src, N, H, W, packed_weight, bias, C_out, 0,
-                     ceil_div(C_out, 16) * 16, tune, 1, EPI_SOFTARGMAX, o, &grid, stream);
-  if (rc != YNET_OK) return rc;
-  tc_partial_finalize_kernel<<<ceil_div(N * C_out, 8), 256, 0, as_stream(stream)>>>(part, N * C_out, grid, out);
-  YNET_LAUNCH_CHECK();
-  return YNET_OK;
 }
 
 }  // extern "C"

@@ -723,10 +723,10 @@ def tc_conv1x1_f32(a, packed_weight, bias_pad, C_out):
 def tc_conv1x1_softargmax(a, packed_weight, bias_pad, C_out):
     """1x1 predictor + SoftArgmax2D fused on the tensor-core kernel: C8 activation -> (N, C_out, 2)."""
     out = torch.empty(a.N, C_out, 2, dtype=torch.float32, device=a.data.device)
-    nb = _L().ynet_tc_conv1x1_softargmax_workspace_bytes(a.N, C_out)
+    nb = _L().ynet_tc_conv1x1_softargmax_workspace_bytes(a.N, C_out, a.H, a.W)
     ws = _workspace(nb, a.data.device, 'tc_softargmax')
     arr = _tc_src_array([a], a.N)
-    with _timed('tc_conv_kernel<1x1,softargmax>', 2.0 * a.C * C_out * a.H * a.W * a.N, 2.0 * a.C_pad * a.H * a.W * a.N):
+    with _timed('tc_pred_softargmax_kernel', 2.0 * a.C * C_out * a.H * a.W * a.N, 2.0 * a.C_pad * a.H * a.W * a.N):
         check(_L().ynet_tc_conv1x1_softargmax(arr, 1, a.N, a.H, a.W, _ptr(packed_weight), _ptr(bias_pad), C_out,
                                               _ptr(out), _ptr(ws), ws.numel(), 0, _stream()), 'tc_conv1x1_softargmax')
     _count(3)

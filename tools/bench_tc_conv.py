@@ -64,3 +64,22 @@ if os.environ.get('UP', '1') != '0':
         fl = 2.0 * 9 * sum(cins) * cout * 4 * h * w * N
         print(f'up {str(cins):>10} -> {cout:3d} @{h:3d}->{2 * h:3d}  {ms:8.3f} ms  {fl / ms / 1e9:7.1f} TF/s  tune={ops._tc_tune}')
         ops._tc_tune.clear()
+
+if os.environ.get('PRED', '1') != '0':
+    for cin, cout, H, W in [(32, 30, 416, 416), (32, 12, 416, 416)]:
+        a = ops.tc_pack(torch.relu(torch.randn(N, cin, H, W, device='cuda')))
+        wgt = torch.randn(cout, cin, 1, 1, device='cuda') * 0.5
+        packed = ops.tc_pack_weights(wgt, [cin])
+        bias = torch.zeros((cout + 15) // 16 * 16, device='cuda')
+        for _ in range(5):
+            ops.tc_conv1x1_softargmax(a, packed, bias, cout)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.tc_conv1x1_softargmax(a, packed, bias, cout)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        by = 2.0 * a.C_pad * H * W * N
+        print(f'pred+softargmax {cin} -> {cout} @{H}  {ms:8.3f} ms  {by / ms / 1e6:7.1f} GB/s')
