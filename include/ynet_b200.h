@@ -211,6 +211,9 @@ typedef struct ynet_tc_src {
                            the n_goal decoder passes of one agent are consecutive images, so the
                            agent's encoder features are re-read from L2, evaluate.py:259)        */
   int64_t batch_stride; /* elements (bf16); 0 = broadcast                                     */
+  int32_t center_only;  /* 1: the source carries hoisted partial sums -- only the centre tap is applied
+                           and its K blocks hold ONE tap in the packed weights (pack it with ksize 1) */
+  int32_t reserved;
 } ynet_tc_src;
 
 int ynet_tc_supported(void);
@@ -262,6 +265,18 @@ int ynet_tc_pack_weights(const float* weight, int32_t C_out, int32_t n_src, cons
 int ynet_tc_conv3x3(const ynet_tc_src* srcs_host, int32_t n_src, int32_t N, int32_t H, int32_t W,
                     const void* packed_weight, const float* bias, int32_t C_out, int32_t relu, void* out_c8,
                     int32_t C_out_pad, int32_t tune, void* stream);
+
+/* Goal-loop hoisting: the encoder-feature channels of every trajectory-decoder input
+ * (evaluate.py:259, ynet.py:466) are identical for the n_goal passes of an agent, so their share of
+ * decoder.i.0 / center.0 is computed ONCE per agent by ynet_tc_conv3x3_hilo -- the raw fp32 partial sums
+ * (no bias, no ReLU) leave as bf16 -- with_lo = 1: a (hi, lo) pair, out_c8: (N, 2*C_out_pad/8, H, W, 8), channels
+ * [hi | lo], ~2^-17 relative; with_lo = 0: hi only, (N, C_out_pad/8, H, W, 8) -- and re-enter the per-goal conv
+ * as a `center_only` source with identity weights.
+ * Packed weights of a conv with mixed sources = the per-source ynet_tc_pack_weights images (ksize 3 for
+ * 3x3 sources, ksize 1 for centre-only ones) concatenated in source order. */
+int ynet_tc_conv3x3_hilo(const ynet_tc_src* srcs_host, int32_t n_src, int32_t N, int32_t H, int32_t W,
+                         const void* packed_weight, int32_t C_out, void* out_c8, int32_t C_out_pad, int32_t with_lo,
+                         int32_t tune, void* stream);
 
 /* The 1x1 predictor (ynet.py:450-451,469) on the tensor cores:
  *   ynet_tc_conv1x1_f32        -> float32 NCHW logits (goal decoder: sigmoid / sampling need the map);

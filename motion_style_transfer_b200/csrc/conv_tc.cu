@@ -34,8 +34,9 @@ struct TcSrcDev {
   int kblocks;      // channels_pad / 16
   int bcast;        // source has batch 1
   int batch_mod;    // > 0: image n reads n % batch_mod; < 0: image n reads n / -batch_mod
-  int pad_;
+  int center;       // 1: only the centre tap is applied to this source (hoisted partial sums, one-tap weights)
 };
+constexpr int TC_MAX_KB = 32;
 
 struct TcParams {
   TcSrcDev src[YNET_MAX_SOURCES];
@@ -43,6 +44,10 @@ struct TcParams {
   int tiles_x, tiles_y;
   long long total_tiles;
   int kb_total;           // sum of kblocks
+  int with_lo;            // EPI_HILO: also write the low halves
+  uint32_t center_mask;   // bit kb: K block kb belongs to a centre-tap-only source
+  int w_total;            // bytes of the packed weights
+  int wofs[TC_MAX_KB];    // byte offset of K block kb in the packed weights (9-tap and 1-tap blocks are mixed)
   int resident;           // weights resident in smem
   int stages, stage_bytes, wres_bytes, tmem_cols;
   int j;                  // accumulators (8-pixel column blocks) per tile: consecutive MMAs hit different ones
@@ -57,7 +62,7 @@ struct TcParams {
   int* err;
 };
 
-constexpr int EPI_C8 = 0, EPI_NCHW_F32 = 1, EPI_UP2 = 3;
+constexpr int EPI_C8 = 0, EPI_NCHW_F32 = 1, EPI_UP2 = 3, EPI_HILO = 4;
 
 // ---- the conv kernel -------------------------------------------------------------------------------------
 template <int J, int TAPS, int EPI>
@@ -80,7 +85,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
   uint64_t* w_bar = tempty_bar + 2;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(w_bar + 1);
   float* s_bias = reinterpret_cast<float*>(w_bar + 2);
-  for (int i = threadIdx.x; i < p.n_pad; i += TC_THREADS) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.n_pad; i += TC_THREADS) s_bias[i] = (p.bias != nullptr) ? p.bias[i] : 0.f;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -114,7 +119,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     // ===================== TMA producer =====================
     if (lane == 0) {
       if (p.resident) {
-        const uint32_t total = (uint32_t)p.kb_total * wblk_bytes;
+        const uint32_t total = (uint32_t)p.w_total;
         mbar_expect_tx(smem_u32(w_bar), total);
         for (uint32_t off = 0; off < total; off += 32768) {
           const uint32_t n = min(32768u, total - off);
@@ -136,9 +141,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err);
             unsigned char* st = s_stage + (size_t)stage * p.stage_bytes;
             const uint32_t fb = smem_u32(&full_bar[stage]);
-            mbar_expect_tx(fb, p.a_bytes + (p.resident ? 0 : wblk_bytes));
+            const uint32_t wb = ((p.center_mask >> kb) & 1u) ? (uint32_t)(wblk_bytes / TAPS) : (uint32_t)wblk_bytes;
+            mbar_expect_tx(fb, p.a_bytes + (p.resident ? 0u : wb));
             tma_load_4d(smem_u32(st), map, fb, 8 * (x0 - HALO), y0 - HALO, 2 * b, ns);
-            if (!p.resident) bulk_load(smem_u32(st + p.a_bytes), p.wpacked + (size_t)kb * wblk_bytes, wblk_bytes, fb);
+            if (!p.resident) bulk_load(smem_u32(st + p.a_bytes), p.wpacked + p.wofs[kb], wb, fb);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -175,20 +181,30 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           tc_fence_after();
           unsigned char* st = s_stage + (size_t)stage * p.stage_bytes;
           const uint32_t a_lo0 = ((smem_u32(st) >> 4) & 0x3FFF) | A_LBO_FIELD;
-          const uint32_t b_base = p.resident ? smem_u32(s_w + (size_t)kb * wblk_bytes) : smem_u32(st + p.a_bytes);
+          const uint32_t b_base = p.resident ? smem_u32(s_w + p.wofs[kb]) : smem_u32(st + p.a_bytes);
           uint32_t b_lo = ((b_base >> 4) & 0x3FFF) | b_lbo_field;
           const uint32_t acc_first = (kb > 0) ? 1u : 0u;
-#pragma unroll
-          for (int tap = 0; tap < TAPS; ++tap) {
+          if (TAPS == 9 && ((p.center_mask >> kb) & 1u)) {
+            // hoisted partial sums: identity weights on the centre tap only
             const uint64_t bdesc = ((uint64_t)b_hi << 32) | b_lo;
 #pragma unroll
             for (int jj = 0; jj < J; ++jj) {
-              // consecutive MMAs target different accumulators (column blocks of the tile)
-              const uint64_t adesc =
-                  ((uint64_t)A_HI << 32) | (a_lo0 + (uint32_t)((TAPS == 9 ? (tap / 3) * BW + (tap % 3) : 0) + 8 * jj));
-              tc_mma_bf16(d_tmem + (uint32_t)(jj * p.n_pad), adesc, bdesc, idesc, tap == 0 ? acc_first : 1u);
+              const uint64_t adesc = ((uint64_t)A_HI << 32) | (a_lo0 + (uint32_t)(BW + 1 + 8 * jj));
+              tc_mma_bf16(d_tmem + (uint32_t)(jj * p.n_pad), adesc, bdesc, idesc, acc_first);
             }
-            b_lo += b_tap_step;
+          } else {
+#pragma unroll
+            for (int tap = 0; tap < TAPS; ++tap) {
+              const uint64_t bdesc = ((uint64_t)b_hi << 32) | b_lo;
+#pragma unroll
+              for (int jj = 0; jj < J; ++jj) {
+                // consecutive MMAs target different accumulators (column blocks of the tile)
+                const uint64_t adesc =
+                    ((uint64_t)A_HI << 32) | (a_lo0 + (uint32_t)((TAPS == 9 ? (tap / 3) * BW + (tap % 3) : 0) + 8 * jj));
+                tc_mma_bf16(d_tmem + (uint32_t)(jj * p.n_pad), adesc, bdesc, idesc, tap == 0 ? acc_first : 1u);
+              }
+              b_lo += b_tap_step;
+            }
           }
           tc_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when these MMAs retire
           if (++stage == p.stages) {
@@ -261,6 +277,33 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
                 __nv_bfloat16* dst =
                     p.out + ((((size_t)n * (cp >> 3) + chunk) * (2 * p.H) + ya) * (size_t)(2 * p.W) + xb2) * 8;
                 *reinterpret_cast<uint4*>(dst) = o;
+              }
+            }
+          } else if (EPI == EPI_HILO) {
+            // raw partial sums as a bf16 pair: hi = bf16(f), lo = bf16(f - hi); channels [hi: n_pad | lo: n_pad]
+            if (inb) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int chunk = (c0 >> 3) + h;
+                float hi[8], lo[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  hi[k] = __bfloat162float(__float2bfloat16_rn(f[8 * h + k]));
+                  lo[k] = f[8 * h + k] - hi[k];
+                }
+                uint4 o, ol;
+                o.x = pack_bf16(hi[0], hi[1]);
+                o.y = pack_bf16(hi[2], hi[3]);
+                o.z = pack_bf16(hi[4], hi[5]);
+                o.w = pack_bf16(hi[6], hi[7]);
+                ol.x = pack_bf16(lo[0], lo[1]);
+                ol.y = pack_bf16(lo[2], lo[3]);
+                ol.z = pack_bf16(lo[4], lo[5]);
+                ol.w = pack_bf16(lo[6], lo[7]);
+                const int planes = p.with_lo ? 2 * n_chunks : n_chunks;
+                __nv_bfloat16* dst = p.out + ((((size_t)n * planes + chunk) * p.H + y) * p.W + x) * 8;
+                *reinterpret_cast<uint4*>(dst) = o;
+                if (p.with_lo) *reinterpret_cast<uint4*>(dst + (size_t)n_chunks * p.H * p.W * 8) = ol;
               }
             }
           } else if (EPI == EPI_NCHW_F32) {
@@ -854,7 +897,7 @@ static void tc_dispatch(int j, unsigned grid, size_t smem, cudaStream_t st, cons
 static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N, int H, int W, const void* packed_weight,
                      const float* bias, int C_out, int relu, int C_out_pad, int tune, int taps, int epi, TcOut out,
                      int* grid_out, void* stream) {
-  if (!(srcs && packed_weight && bias)) {
+  if (!(srcs && packed_weight && (bias || epi == EPI_HILO))) {
     set_error("%s: null pointer", who);
     return YNET_E_INVALID;
   }
@@ -890,7 +933,7 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
   p.a_sbo = p.bw * 16;
   CUtensorMap maps[YNET_MAX_SOURCES];
   memset(maps, 0, sizeof(maps));
-  int kb_total = 0;
+  int kb_total = 0, w_total = 0;
   for (int i = 0; i < n_src; ++i) {
     const int cp = srcs[i].channels_pad;
     if (!(srcs[i].ptr && cp > 0 && cp % 16 == 0) || reinterpret_cast<uintptr_t>(srcs[i].ptr) % 16 != 0) {
@@ -921,8 +964,19 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
     p.src[i].kblocks = cp / 16;
     p.src[i].bcast = bcast ? 1 : 0;
     p.src[i].batch_mod = srcs[i].batch_mod;
+    p.src[i].center = (taps == 9 && srcs[i].center_only) ? 1 : 0;
+    if (kb_total + cp / 16 > TC_MAX_KB) {
+      set_error("%s: more than %d input K blocks", who, TC_MAX_KB);
+      return YNET_E_UNSUPPORTED;
+    }
+    for (int b = 0; b < cp / 16; ++b) {
+      p.wofs[kb_total + b] = w_total;
+      w_total += (p.src[i].center ? 1 : taps) * 2 * C_out_pad * 16;
+      if (p.src[i].center) p.center_mask |= 1u << (kb_total + b);
+    }
     kb_total += cp / 16;
   }
+  p.w_total = w_total;
   for (int i = n_src; i < YNET_MAX_SOURCES; ++i) maps[i] = maps[0];
   p.n_src = n_src;
   p.N = N;
@@ -930,7 +984,8 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
   p.W = W;
   p.n_pad = C_out_pad;
   p.c_out = C_out;
-  p.relu = relu;
+  p.relu = (epi == EPI_HILO) ? 0 : relu;
+  p.with_lo = (epi == EPI_HILO && relu == 2) ? 1 : 0;
   p.tiles_x = ceil_div(W, 8 * p.j);
   p.tiles_y = ceil_div(H, TC_TH);
   p.total_tiles = (long long)N * p.tiles_x * p.tiles_y;
@@ -943,7 +998,7 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
   p.err = nullptr;
 
   const int wblk = taps * 2 * C_out_pad * 16;
-  const long long wall = (long long)kb_total * wblk;
+  const long long wall = w_total;
   const int budget = 200 * 1024;
   const int tail = (2 * TC_MAX_STAGES + 5) * 8 + 16 + 256 * 4;
   const char* force_stream = getenv("YNET_TC_FORCE_STREAMED");
@@ -967,6 +1022,7 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
   if (!configured) {
     cudaError_t e = tc_configure<9, EPI_C8>();
     if (e == cudaSuccess) e = tc_configure<9, EPI_UP2>();
+    if (e == cudaSuccess) e = tc_configure<9, EPI_HILO>();
     if (e == cudaSuccess) e = tc_configure<1, EPI_NCHW_F32>();
     if (e != cudaSuccess) return cuda_fail(e, "tc_launch(cudaFuncSetAttribute)");
     configured = true;
@@ -984,6 +1040,8 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
     tc_dispatch<9, EPI_C8>(p.j, (unsigned)grid, smem_bytes, st, maps, p);
   else if (taps == 9 && epi == EPI_UP2)
     tc_dispatch<9, EPI_UP2>(p.j, (unsigned)grid, smem_bytes, st, maps, p);
+  else if (taps == 9 && epi == EPI_HILO)
+    tc_dispatch<9, EPI_HILO>(p.j, (unsigned)grid, smem_bytes, st, maps, p);
   else if (taps == 1 && epi == EPI_NCHW_F32)
     tc_dispatch<1, EPI_NCHW_F32>(p.j, (unsigned)grid, smem_bytes, st, maps, p);
   else {
@@ -1007,6 +1065,15 @@ int ynet_tc_conv3x3(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int32_t H
   TcOut o{out_c8, nullptr, nullptr};
   return tc_launch("ynet_tc_conv3x3", srcs, n_src, N, H, W, packed_weight, bias, C_out, relu, C_out_pad, tune, 9, EPI_C8, o,
                    nullptr, stream);
+}
+
+int ynet_tc_conv3x3_hilo(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int32_t H, int32_t W, const void* packed_weight,
+                         int32_t C_out, void* out_c8, int32_t C_out_pad, int32_t with_lo, int32_t tune, void* stream) {
+  YNET_CHECK_ARG(out_c8 != nullptr || N == 0, "null output");
+  YNET_CHECK_ALIGN(out_c8, 16);
+  TcOut o{out_c8, nullptr, nullptr};
+  return tc_launch("ynet_tc_conv3x3_hilo", srcs, n_src, N, H, W, packed_weight, nullptr, C_out, with_lo ? 2 : 0, C_out_pad,
+                   tune, 9, EPI_HILO, o, nullptr, stream);
 }
 
 int ynet_tc_upconv_phase_weights(const float* weight, const float* bias, int32_t C_out, int32_t C_in, float* w_eff,

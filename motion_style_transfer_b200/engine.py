@@ -9,6 +9,8 @@ Two back ends behind the same walk:
   * ``fp32``  -- CUDA-core fp32 kernels (conv_f32.cu): the <=1e-3 parity mode;
   * ``bf16``  -- tcgen05/TMEM implicit-GEMM kernels (conv_tc.cu): the throughput mode.
 """
+import os
+
 import torch
 
 from . import ops
@@ -281,14 +283,81 @@ class YNetEngineTC(YNetEngine):
         packed, bias = self._tc_params(decoder.predictor, f'{key}.predictor', [x.C])
         return ops.tc_conv1x1_f32(x, packed, bias, decoder.predictor.weight.shape[0])
 
+    # Goal-loop hoisting.  Every trajectory-decoder input is cat(upsampled x, encoder feature, waypoint
+    # pyramid) (ynet.py:466, evaluate.py:259); the encoder feature is the same for the n_goal passes of an agent, so its
+    # share of center.0 / decoder.i.0 is computed once per agent (raw fp32 sums kept as a bf16 hi + lo pair) and
+    # re-enters each per-goal conv as a one-tap identity source.
+    hoist = True
+    hoist_lo = os.environ.get('YNET_HOIST_LO', '0') == '1'     # keep the low halves of the partial sums too
+
+    def _hoist_params(self, module, key, layout):
+        """Packed weights (+ padded bias) of a conv whose sources are ``layout``: ('conv', (c0, c1)) | ('partial', C_out)."""
+        ver = (module.weight._version, module.weight.data_ptr(), tuple(layout))
+        hit = self._wcache.get(key + '#hoist')
+        if hit is not None and hit[0] == ver:
+            return hit[1], hit[2]
+        w = module.weight.detach()
+        packed = ops.tc_pack_hoisted_weights(w, layout)
+        C_out = w.shape[0]
+        bias = torch.zeros(ops._pad16(C_out), dtype=torch.float32, device=w.device)
+        if module.bias is not None:
+            bias[:C_out] = module.bias.detach()
+        self._wcache[key + '#hoist'] = (ver, packed, bias)
+        return packed, bias
+
+    def _partial(self, module, key, parts, c0):
+        """hi/lo partial sums of conv ``module`` over its input channels [c0, c0 + sum(part channels))."""
+        chans = [t.C for t in parts]
+        ver = (module.weight._version, module.weight.data_ptr(), c0, tuple(chans))
+        hit = self._wcache.get(key + '#partial')
+        if hit is None or hit[0] != ver:
+            w = module.weight.detach()[:, c0:c0 + sum(chans)].contiguous()
+            hit = (ver, ops.tc_pack_weights(w, chans))
+            self._wcache[key + '#partial'] = hit
+        return ops.tc_conv3x3_hilo(parts, hit[1], module.weight.shape[0], self.hoist_lo)
+
+    def _traj_partials(self, decoder, key, feats_rev):
+        """One partial per decoder level for a chunk of agents: [center.0, decoder.0.0, ..., decoder.4.0]."""
+        out = [self._partial(decoder.center[0], f'{key}.center.0', feats_rev[0], 0)]
+        for i, skip in enumerate(feats_rev[1:]):
+            c_up = decoder.upsample_conv[i].weight.shape[0]
+            out.append(self._partial(decoder.decoder[i][0], f'{key}.decoder.{i}.0', skip, c_up))
+        return out
+
+    def _tconv_hoisted(self, module, key, up, partial, pyr_level, c_feat):
+        """conv(cat(up, feature, waypoints)) with the feature share taken from ``partial``."""
+        layout, srcs, c = [], [], 0
+        if up is not None:
+            layout.append(('conv', (0, up.C)))
+            srcs.append(up)
+            c = up.C
+        layout.append(('partial', partial.C))
+        srcs.append(partial)
+        layout.append(('conv', (c + c_feat, c + c_feat + pyr_level.C)))
+        srcs.append(pyr_level)
+        packed, bias = self._hoist_params(module, key, layout)
+        return ops.tc_conv3x3(srcs, packed, bias, module.weight.shape[0], True)
+
+    def _decoder_trunk_hoisted(self, decoder, key, partials, pyr_rev, c_feats):
+        x = self._tconv_hoisted(decoder.center[0], f'{key}.center.0', None, partials[0], pyr_rev[0], c_feats[0])
+        x = self._tconv(decoder.center[2], f'{key}.center.2', [x], True)
+        for i in range(len(partials) - 1):
+            up = self._tupconv(decoder.upsample_conv[i], f'{key}.upsample_conv.{i}', [x])
+            x = self._tconv_hoisted(decoder.decoder[i][0], f'{key}.decoder.{i}.0', up, partials[i + 1], pyr_rev[i + 1],
+                                    c_feats[i + 1])
+            x = self._tconv(decoder.decoder[i][2], f'{key}.decoder.{i}.2', [x], True)
+        return x
+
     def decode_trajectories(self, feats, waypoint_samples, template, H, W, max_passes=256):
         """Agent-major stacking: the G passes of one agent are consecutive images of a launch, so the agent's
-        encoder features (``n // G``) are re-read from L2 instead of HBM; chunks walk the agents.  The waypoint
-        maps and their pyramid are rasterised straight into bf16 C8 planes (one launch per chunk)."""
+        encoder features / hoisted partial sums (``n // G``) are re-read from L2 instead of HBM; chunks walk the
+        agents.  The waypoint maps and their pyramid are rasterised straight into bf16 C8 planes (one launch per
+        chunk)."""
         G, B, n_wp, _ = waypoint_samples.shape
-        if n_wp > 8:
+        dec = self.model.traj_decoder
+        pred_len = dec.predictor.weight.shape[0]
+        if n_wp > 8 or pred_len > 32:
             return super().decode_trajectories(feats, waypoint_samples, template, H, W, max_passes)
-        pred_len = self.model.traj_decoder.predictor.weight.shape[0]
         trajs = torch.empty(G, B, pred_len, 2, dtype=torch.float32, device=waypoint_samples.device)
         feats = [self._c8_parts(f) for f in feats]
         bc = max(1, min(B, max_passes // max(G, 1)))
@@ -297,9 +366,17 @@ class YNetEngineTC(YNetEngine):
             nb = b1 - b0
             wp = waypoint_samples[:, b0:b1].permute(1, 0, 2, 3).reshape(-1, 2).contiguous()   # (nb, G, n_wp) order
             pyr = ops.tc_rasterize_pyramid(template, wp, nb * G, n_wp, H, W, len(feats))
-            traj_input = [ChannelCat(tuple(c.batch_slice(b0, b1).repeat_interleave(G) for c in f) + (p,))
-                          for f, p in zip(feats, pyr)]
-            out = self.decoder_softargmax(self.model.traj_decoder, 'traj_decoder', traj_input)   # (nb*G, pred, 2)
+            if self.hoist:
+                feats_rev = [[c.batch_slice(b0, b1) for c in f] for f in feats][::-1]
+                partials = [q.repeat_interleave(G) for q in self._traj_partials(dec, 'traj_decoder', feats_rev)]
+                x = self._decoder_trunk_hoisted(dec, 'traj_decoder', partials, pyr[::-1],
+                                                [sum(c.C for c in f) for f in feats_rev])
+                packed, bias = self._tc_params(dec.predictor, 'traj_decoder.predictor', [x.C])
+                out = ops.tc_conv1x1_softargmax(x, packed, bias, pred_len)
+            else:
+                traj_input = [ChannelCat(tuple(c.batch_slice(b0, b1).repeat_interleave(G) for c in f) + (p,))
+                              for f, p in zip(feats, pyr)]
+                out = self.decoder_softargmax(dec, 'traj_decoder', traj_input)   # (nb*G, pred, 2)
             trajs[:, b0:b1] = out.view(nb, G, pred_len, 2).permute(1, 0, 2, 3)
         return trajs
 

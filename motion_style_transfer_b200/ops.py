@@ -552,22 +552,23 @@ class C8:
     (agent-major stacking of the n_goal decoder passes; nothing is copied).
     """
 
-    __slots__ = ('data', 'C', 'rep')
+    __slots__ = ('data', 'C', 'rep', 'center')
 
-    def __init__(self, data, C, rep=1):
-        self.data, self.C, self.rep = data, C, rep
+    def __init__(self, data, C, rep=1, center=False):
+        # center: hoisted partial sums (hi | lo); a conv applies identity weights on its centre tap only
+        self.data, self.C, self.rep, self.center = data, C, rep, center
 
     @property
     def N(self):
         return self.data.shape[0] * self.rep
 
     def repeat_interleave(self, rep):
-        return C8(self.data, self.C, self.rep * rep)
+        return C8(self.data, self.C, self.rep * rep, self.center)
 
     def batch_slice(self, b0, b1):
         if self.rep != 1:
             raise ValueError('batch_slice of a repeated C8')
-        return C8(self.data[b0:b1], self.C)
+        return C8(self.data[b0:b1], self.C, 1, self.center)
 
     @property
     def C_pad(self):
@@ -745,19 +746,71 @@ def tc_conv3x3(sources, packed_weight, bias_pad, C_out, relu):
         arr[i].channels_pad = s.C_pad
         arr[i].batch_stride = 0 if (s.N == 1 and N > 1) else s.data.stride(0)
         arr[i].batch_mod = _tc_batch_mod(s, N)
+        arr[i].center_only = 1 if s.center else 0
     cp = _pad16(C_out)
     out = torch.empty(N, cp // 8, H, W, 8, dtype=torch.bfloat16, device=sources[0].data.device)
     cin_pad = sum(s.C_pad for s in sources)
     args = (arr, len(sources), N, H, W, _ptr(packed_weight), _ptr(bias_pad), C_out, 1 if relu else 0, _ptr(out), cp)
-    key = (tuple(s.C_pad for s in sources), cp, H, W, min(N, 64))
+    key = (tuple(-s.C_pad if s.center else s.C_pad for s in sources), cp, H, W, min(N, 64))
     tune = _tc_tune.get(key)
     if tune is None:
         tune = _tc_autotune(key, args) if (tc_autotune_enabled and not torch.cuda.is_current_stream_capturing()) else 0
-    with _timed('tc_conv3x3_kernel', 2.0 * 9 * sum(s.C for s in sources) * C_out * H * W * N,
-                2.0 * (cin_pad + cp) * H * W * N, tag=f'{cin_pad}->{cp}@{H}x{W} N={N}'):
+    hoisted = '+P' if any(s.center for s in sources) else ''
+    with _timed('tc_conv3x3_kernel', 2.0 * 9 * sum(s.C for s in sources if not s.center) * C_out * H * W * N,
+                2.0 * (cin_pad + cp) * H * W * N, tag=f'{cin_pad}{hoisted}->{cp}@{H}x{W} N={N}'):
         check(_L().ynet_tc_conv3x3(*args, tune, _stream()), 'tc_conv3x3')
     _count()
     return C8(out, C_out)
+
+
+def tc_conv3x3_hilo(sources, packed_weight, C_out, with_lo=True):
+    """Raw 3x3 partial sums (no bias / ReLU) of C8 sources as a bf16 (hi | lo) pair: C8 with 2 * pad16(C_out)
+    channels, flagged ``center`` so that a later tc_conv3x3 adds it through identity weights (goal-loop hoisting)."""
+    N = max(s.N for s in sources)
+    H, W = sources[0].H, sources[0].W
+    arr = (_lib.TcSrc * len(sources))()
+    for i, s in enumerate(sources):
+        if s.H != H or s.W != W:
+            raise ValueError('tc_conv3x3_hilo: sources must share the spatial size')
+        arr[i].ptr = s.data.data_ptr()
+        arr[i].channels_pad = s.C_pad
+        arr[i].batch_stride = 0 if (s.N == 1 and N > 1) else s.data.stride(0)
+        arr[i].batch_mod = _tc_batch_mod(s, N)
+    cp = _pad16(C_out)
+    k = 2 if with_lo else 1
+    out = torch.empty(N, k * cp // 8, H, W, 8, dtype=torch.bfloat16, device=sources[0].data.device)
+    cin_pad = sum(s.C_pad for s in sources)
+    with _timed('tc_conv3x3_hilo_kernel', 2.0 * 9 * sum(s.C for s in sources) * C_out * H * W * N,
+                2.0 * (cin_pad + k * cp) * H * W * N, tag=f'{cin_pad}->{cp}x{k}@{H}x{W} N={N}'):
+        check(_L().ynet_tc_conv3x3_hilo(arr, len(sources), N, H, W, _ptr(packed_weight), C_out, _ptr(out), cp, k - 1, 0,
+                                        _stream()), 'tc_conv3x3_hilo')
+    _count()
+    return C8(out, k * cp, 1, True)
+
+
+def tc_pack_hoisted_weights(weight_oihw, parts):
+    """Packed weights of a conv whose sources mix 3x3 inputs and hoisted partial sums.
+
+    parts: list in source order of ('conv', (c0, c1)) -- input channels [c0, c1) of ``weight_oihw`` applied as 3x3 --
+    or ('partial', channels) -- a ``center`` source with ``channels`` = pad16(C_out) (hi) or twice that (hi | lo):
+    identity on the centre tap."""
+    C_out = weight_oihw.shape[0]
+    cp = _pad16(C_out)
+    bufs = []
+    for kind, arg in parts:
+        if kind == 'conv':
+            c0, c1 = arg
+            bufs.append(tc_pack_weights(weight_oihw[:, c0:c1].contiguous(), [c1 - c0]))
+        else:
+            eye = torch.zeros(C_out, arg, 1, 1, dtype=torch.float32, device=weight_oihw.device)
+            idx = torch.arange(C_out, device=weight_oihw.device)
+            eye[idx, idx, 0, 0] = 1.0
+            if arg == 2 * cp:
+                eye[idx, cp + idx, 0, 0] = 1.0
+            elif arg != cp:
+                raise ValueError(f'partial source has {arg} channels, expected {cp} or {2 * cp}')
+            bufs.append(tc_pack_weights(eye, [arg]))
+    return torch.cat(bufs)
 
 
 def tc_upconv_phase_weights(weight_oihw, bias):

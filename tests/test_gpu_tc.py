@@ -220,3 +220,36 @@ def test_tc_upconv_vs_torch(ops, cins, cout, h, w, N):
     ring = torch.ones_like(ref, dtype=torch.bool)
     ring[:, :, 2:-2, 2:-2] = False
     assert rel_err(got[ring].numpy(), ref[ring].numpy()) < 5e-3
+
+
+def test_tc_hoisted_partial_sums_match_direct_conv(ops):
+    """Goal-loop hoisting: conv(cat(up, feature, wp)) == conv(cat(up, wp)) + hi/lo partial(feature) via identity taps."""
+    torch.manual_seed(11)
+    nb, G, H, W = 2, 3, 32, 40
+    up = bf16_exact(torch.randn(nb * G, 16, H, W))
+    feat = bf16_exact(torch.randn(nb, 32, H, W))
+    wp = bf16_exact(torch.rand(nb * G, 2, H, W) * 2)
+    w = bf16_exact(torch.randn(32, 50, 3, 3) * 0.1)
+    bias = torch.randn(32)
+    ref = F.relu(F.conv2d(torch.cat([up, feat.repeat_interleave(G, dim=0), wp], 1), w, bias, padding=1))
+    f8 = ops.tc_pack(feat.cuda())
+    part = ops.tc_conv3x3_hilo([f8], ops.tc_pack_weights(w[:, 16:48].contiguous().cuda(), [32]), 32)
+    assert part.center and part.C_pad == 64
+    # the (hi | lo) pair reproduces the fp32 partial sums to ~2^-16 relative
+    pf = ops.tc_unpack(part).cpu()
+    raw = F.conv2d(feat, w[:, 16:48], None, padding=1)
+    assert rel_err((pf[:, :32] + pf[:, 32:]).numpy(), raw.numpy()) < 3e-5
+    packed = ops.tc_pack_hoisted_weights(w.cuda(), [('conv', (0, 16)), ('partial', 64), ('conv', (48, 50))])
+    bp = torch.zeros(32)
+    bp[:32] = bias
+    out = ops.tc_conv3x3([ops.tc_pack(up.cuda()), part.repeat_interleave(G), ops.tc_pack(wp.cuda())], packed, bp.cuda(),
+                         32, True)
+    got = ops.tc_unpack(out).cpu()
+    assert rel_err(got.numpy(), ref.numpy()) < 6e-3          # bf16 output rounding only
+    # hi-only partial sums: one more bf16 rounding of the feature share
+    part1 = ops.tc_conv3x3_hilo([f8], ops.tc_pack_weights(w[:, 16:48].contiguous().cuda(), [32]), 32, with_lo=False)
+    assert part1.C_pad == 32
+    packed1 = ops.tc_pack_hoisted_weights(w.cuda(), [('conv', (0, 16)), ('partial', 32), ('conv', (48, 50))])
+    out1 = ops.tc_conv3x3([ops.tc_pack(up.cuda()), part1.repeat_interleave(G), ops.tc_pack(wp.cuda())], packed1, bp.cuda(),
+                          32, True)
+    assert rel_err(ops.tc_unpack(out1).cpu().numpy(), ref.numpy()) < 1.2e-2
