@@ -213,7 +213,8 @@ typedef struct ynet_tc_src {
   int64_t batch_stride; /* elements (bf16); 0 = broadcast                                     */
   int32_t center_only;  /* 1: the source carries hoisted partial sums -- only the centre tap is applied
                            and its K blocks hold ONE tap in the packed weights (pack it with ksize 1) */
-  int32_t reserved;
+  int32_t chunks_stored; /* 0 = channels_pad / 8; else the number of 8-channel planes the tensor really holds
+                           (< channels_pad / 8): the missing planes read as zero (TMA out-of-bounds fill) */
 } ynet_tc_src;
 
 int ynet_tc_supported(void);
@@ -227,6 +228,13 @@ int ynet_tc_rasterize_pyramid_c8(const float* tmpl, int32_t tmpl_h, int32_t tmpl
                                  int32_t n_img, int32_t n_ch, int32_t H, int32_t W, int32_t n_levels,
                                  void* const* outs_host, int32_t C_pad, int32_t write_pad, int32_t* oob_flag,
                                  void* stream);
+/* The same maps in im2col form for level 0 (full resolution) or 1 (2x2 average pool): channel c*9 + kh*3 + kw of
+ * pixel (y, x) = map_c[y+kh-1][x+kw-1], 0 outside the image.  A conv reads it as a `center_only` source with the
+ * 1x1 weights W[:, wp channels].reshape(C_out, 9 n_ch): one MMA per 16 im2col channels instead of nine per
+ * (mostly empty) 16-channel K block.  out_c8: (n_img, C_pad/8, H>>level, W>>level, 8), C_pad >= 9 n_ch; n_ch <= 3. */
+int ynet_tc_rasterize_im2col_c8(const float* tmpl, int32_t tmpl_h, int32_t tmpl_w, const float* coords, int32_t n_img,
+                                int32_t n_ch, int32_t H, int32_t W, int32_t level, void* out_c8, int32_t C_pad,
+                                void* stream);
 int ynet_tc_pack_f32_to_c8(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, int64_t batch_stride,
                            void* out_c8, int32_t C_pad, void* stream);
 int ynet_tc_unpack_c8_to_f32(const void* x_c8, int32_t N, int32_t C, int32_t C_pad, int32_t H, int32_t W,

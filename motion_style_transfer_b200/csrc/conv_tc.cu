@@ -945,8 +945,15 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
     const int nsrc = bcast ? 1 : (bmod > 0 ? bmod : (bmod < 0 ? ceil_div(N, -bmod) : N));
     // A pixel row of one 8-channel chunk is W*8 contiguous bf16: that is the innermost TMA dimension, so one
     // box row is ONE (8J+2)*16-byte request instead of 8J+2 sixteen-byte ones.
-    const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)(cp / 8), (cuuint64_t)nsrc};
-    const cuuint64_t bs = bcast ? (cuuint64_t)(cp / 8) * H * W * 16 : (cuuint64_t)srcs[i].batch_stride * 2;
+    // chunks_stored < cp / 8: the tensor holds fewer 8-channel planes than the K padding (e.g. 2 waypoint channels =
+    // ONE plane inside a 16-channel K block); TMA zero-fills the missing planes without touching HBM
+    const int stored = (srcs[i].chunks_stored > 0) ? srcs[i].chunks_stored : cp / 8;
+    if (stored > cp / 8) {
+      set_error("%s: source %d stores more planes than channels_pad / 8", who, i);
+      return YNET_E_INVALID;
+    }
+    const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)stored, (cuuint64_t)nsrc};
+    const cuuint64_t bs = bcast ? (cuuint64_t)stored * H * W * 16 : (cuuint64_t)srcs[i].batch_stride * 2;
     if (bs % 16 != 0) {
       set_error("%s: batch stride must be a multiple of 8 elements", who);
       return YNET_E_ALIGN;

@@ -252,6 +252,69 @@ wp_pyramid_c8_kernel(const float* __restrict__ tmpl, int th, int tw, const float
   }
 }
 
+
+// ---- a3 + a9 in im2col form for the tensor-core engine -------------------------------------------------------
+// The n_wp (1-2) waypoint channels of a trajectory-decoder input occupy a whole 16-channel K block of the conv: nine
+// MMAs per tile for two real channels.  Written as im2col instead -- channel c * 9 + kh * 3 + kw of pixel (y, x) =
+// map_c[y + kh - 1][x + kw - 1], 0 outside the image (the conv's zero padding) -- the same contribution is ONE 1x1
+// (centre-tap) K block per 16 im2col channels.  Level L in {0, 1}: the map is the 2^L average pool of the rasterised
+// distance map, pooled with the same arithmetic as wp_pyramid_c8_kernel.
+template <int NCH, int L>
+__global__ void __launch_bounds__(256)
+wp_im2col_c8_kernel(const float* __restrict__ tmpl, int th, int tw, const float* __restrict__ coords, int H, int W,
+                    int chunks, uint4* __restrict__ out) {
+  constexpr int S = 1 << L;             // pooling factor
+  constexpr int OB = 32 >> L;           // output block edge
+  constexpr int R = 32 + 2 * S;         // level-0 region edge (block + one pooled pixel of halo)
+  constexpr int RP = OB + 2;            // pooled region edge
+  __shared__ float s0[NCH][R][R + 1];
+  __shared__ float sp[NCH][RP][RP + 1];
+  const int n = blockIdx.z;
+  const int by0 = blockIdx.y * 32, bx0 = blockIdx.x * 32;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int x = __float2int_rn(coords[2 * (n * NCH + c) + 0]);  // round half to even == np.round
+    const int y = __float2int_rn(coords[2 * (n * NCH + c) + 1]);
+    const int yl = th / 2 - y, xl = tw / 2 - x;
+    for (int idx = threadIdx.x; idx < R * R; idx += 256) {
+      const int ry = idx / R, rx = idx - ry * R;
+      const int gy = by0 - S + ry, gx = bx0 - S + rx;
+      float v = 0.f;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        const int sy = min(max(yl + gy, 0), th - 1), sx = min(max(xl + gx, 0), tw - 1);
+        v = __ldg(tmpl + (size_t)sy * tw + sx);
+      }
+      s0[c][ry][rx] = v;
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NCH * RP * RP; idx += 256) {
+    const int c = idx / (RP * RP), r = idx - c * RP * RP;
+    const int py = r / RP, px = r - py * RP;
+    float v;
+    if (L == 0)
+      v = s0[c][py][px];
+    else
+      v = 0.25f * ((s0[c][2 * py][2 * px] + s0[c][2 * py][2 * px + 1]) + (s0[c][2 * py + 1][2 * px] + s0[c][2 * py + 1][2 * px + 1]));
+    sp[c][py][px] = v;
+  }
+  __syncthreads();
+  const int h = H >> L, w = W >> L;
+  uint4* o = out + (size_t)n * chunks * h * w;
+  for (int idx = threadIdx.x; idx < chunks * OB * OB; idx += 256) {
+    const int k = idx / (OB * OB), r = idx - k * OB * OB;
+    const int oy = r / OB, ox = r - oy * OB;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = 8 * k + j;
+      const int c = ch / 9, tap = ch - 9 * c;
+      f[j] = (c < NCH) ? sp[c < NCH ? c : 0][oy + tap / 3][ox + tap % 3] : 0.f;
+    }
+    o[(size_t)k * h * w + (size_t)((by0 >> L) + oy) * w + (bx0 >> L) + ox] = pack8_bf16(f);
+  }
+}
+
 }  // namespace ynet
 
 using namespace ynet;
@@ -362,6 +425,33 @@ int ynet_tc_rasterize_pyramid_c8(const float* tmpl, int32_t th, int32_t tw, cons
       YNET_WP_CASE(8)
     }
 #undef YNET_WP_CASE
+    YNET_LAUNCH_CHECK();
+  }
+  return YNET_OK;
+}
+
+int ynet_tc_rasterize_im2col_c8(const float* tmpl, int32_t th, int32_t tw, const float* coords, int32_t n_img, int32_t n_ch,
+                                int32_t H, int32_t W, int32_t level, void* out_c8, int32_t C_pad, void* stream) {
+  YNET_CHECK_ARG(n_img >= 0 && n_ch >= 1 && n_ch <= 3 && H > 0 && W > 0 && th >= H && tw >= W, "bad shape (n_ch <= 3)");
+  YNET_CHECK_ARG((level == 0 || level == 1) && C_pad >= 9 * n_ch && C_pad % 16 == 0, "level in {0, 1}, C_pad >= 9 n_ch, % 16");
+  if (H % 32 != 0 || W % 32 != 0) {
+    set_error("ynet_tc_rasterize_im2col_c8: H and W must be multiples of 32 (trainer.py:60,581)");
+    return YNET_E_UNSUPPORTED;
+  }
+  if (n_img == 0) return YNET_OK;
+  YNET_CHECK_ARG(tmpl && coords && out_c8, "null pointer");
+  YNET_CHECK_ALIGN(out_c8, 16);
+  const int chunks = C_pad / 8;
+  cudaStream_t st = as_stream(stream);
+  for (int n0 = 0; n0 < n_img; n0 += 65535) {
+    const int nn = min(65535, n_img - n0);
+    dim3 grid(W / 32, H / 32, nn);
+    const float* c = coords + 2 * (size_t)n0 * n_ch;
+    uint4* o = reinterpret_cast<uint4*>(out_c8) + (size_t)n0 * chunks * (H >> level) * (W >> level);
+#define YNET_I2C_CASE(K, LV)                                                                   \
+  if (n_ch == K && level == LV) wp_im2col_c8_kernel<K, LV><<<grid, 256, 0, st>>>(tmpl, th, tw, c, H, W, chunks, o);
+    YNET_I2C_CASE(1, 0) YNET_I2C_CASE(2, 0) YNET_I2C_CASE(3, 0) YNET_I2C_CASE(1, 1) YNET_I2C_CASE(2, 1) YNET_I2C_CASE(3, 1)
+#undef YNET_I2C_CASE
     YNET_LAUNCH_CHECK();
   }
   return YNET_OK;

@@ -575,6 +575,11 @@ class C8:
         return self.data.shape[1] * 8
 
     @property
+    def K_pad(self):
+        """Channels a conv sees (multiple of 16); planes beyond the stored ones read as zero (TMA fill)."""
+        return (self.C_pad + 15) // 16 * 16
+
+    @property
     def H(self):
         return self.data.shape[2]
 
@@ -585,6 +590,22 @@ class C8:
 
 def _pad16(c):
     return (c + 15) // 16 * 16
+
+
+def tc_rasterize_im2col(template, coords, n_img, n_ch, H, W, level):
+    """Waypoint maps of pyramid level 0 or 1 in im2col form (see ynet_tc_rasterize_im2col_c8): a ``center`` C8 with
+    9 * n_ch channels whose conv weights are W[:, wp channels].reshape(C_out, 9 * n_ch, 1, 1)."""
+    template = _req(template, name='template')
+    coords = _req(coords, name='coords').reshape(-1, 2)
+    if coords.shape[0] != n_img * n_ch:
+        raise ValueError(f'tc_rasterize_im2col: expected {n_img * n_ch} coordinates, got {coords.shape[0]}')
+    cp = _pad16(9 * n_ch)
+    out = torch.empty(n_img, cp // 8, H >> level, W >> level, 8, dtype=torch.bfloat16, device=template.device)
+    with _timed('wp_im2col_c8_kernel', 0, (2.0 * cp * ((H >> level) * (W >> level)) + 4.0 * n_ch * H * W) * n_img):
+        check(_L().ynet_tc_rasterize_im2col_c8(_ptr(template), template.shape[0], template.shape[1], _ptr(coords), n_img,
+                                               n_ch, H, W, level, _ptr(out), cp, _stream()), 'tc_rasterize_im2col_c8')
+    _count()
+    return C8(out, 9 * n_ch, 1, True)
 
 
 def tc_supported():
@@ -609,39 +630,25 @@ def tc_pack(x):
     return C8(out, C)
 
 
-_zero_planes = {}
-
-
 def tc_rasterize_pyramid(template, coords, n_img, n_ch, H, W, n_levels, slot=0):
     """get_patch + AvgPool pyramid of ``n_img x n_ch`` waypoint coordinates written straight as bf16 C8 planes
-    (image_utils.py:40-63 + evaluate.py:255-257).  Returns n_levels C8 (n_img, 16-padded, H>>l, W>>l).
-
-    The outputs live in persistent buffers keyed by (shape, slot): their padding chunk is zeroed once and never
-    written again, so a call only writes 16 B per pixel.  Successive calls with the same key reuse the buffers
-    (stream-ordered); pass distinct ``slot``s for results that must coexist.
+    (image_utils.py:40-63 + evaluate.py:255-257).  Returns n_levels C8 (n_img, ONE 8-channel plane, H>>l, W>>l):
+    16 B per pixel; a conv pads the K block to 16 channels through the TMA zero fill (``C8.K_pad``).
+    ``slot`` is accepted for compatibility and ignored (every call returns fresh tensors).
     """
     template = _req(template, name='template')
     coords = _req(coords, name='coords').reshape(-1, 2)
     if coords.shape[0] != n_img * n_ch:
         raise ValueError(f'tc_rasterize_pyramid: expected {n_img * n_ch} coordinates, got {coords.shape[0]}')
-    key = (n_img, n_ch, H, W, n_levels, slot, template.device)
-    bufs = _zero_planes.get(key)
+    # n_ch <= 8 channels fit ONE 8-channel plane; the conv's TMA zero-fills the other plane of the 16-channel K block
+    bufs = [torch.empty(n_img, 1, H >> l, W >> l, 8, dtype=torch.bfloat16, device=template.device)
+            for l in range(n_levels)]
     write_pad = 0
-    if bufs is None:
-        if torch.cuda.is_current_stream_capturing():
-            # graph-pool memory: cannot rely on a one-off memset, let the kernel write the padding every replay
-            bufs = [torch.empty(n_img, 2, H >> l, W >> l, 8, dtype=torch.bfloat16, device=template.device)
-                    for l in range(n_levels)]
-            write_pad = 1
-        else:
-            bufs = [torch.zeros(n_img, 2, H >> l, W >> l, 8, dtype=torch.bfloat16, device=template.device)
-                    for l in range(n_levels)]
-            _zero_planes[key] = bufs
     outs = (ctypes.c_void_p * n_levels)(*[b.data_ptr() for b in bufs])
     S = sum((H >> l) * (W >> l) for l in range(n_levels))
-    with _timed('wp_pyramid_c8_kernel', 0, (16.0 * S + 4.0 * n_ch * H * W) * n_img):
+    with _timed('wp_pyramid_c8_kernel', 0, 16.0 * S * n_img):
         check(_L().ynet_tc_rasterize_pyramid_c8(_ptr(template), template.shape[0], template.shape[1], _ptr(coords), n_img,
-                                                n_ch, H, W, n_levels, outs, 16, write_pad, None, _stream()),
+                                                n_ch, H, W, n_levels, outs, 8, write_pad, None, _stream()),
               'tc_rasterize_pyramid_c8')
     _count()
     return [C8(b, n_ch) for b in bufs]
@@ -743,7 +750,8 @@ def tc_conv3x3(sources, packed_weight, bias_pad, C_out, relu):
         if s.H != H or s.W != W:
             raise ValueError('tc_conv3x3: sources must share the spatial size')
         arr[i].ptr = s.data.data_ptr()
-        arr[i].channels_pad = s.C_pad
+        arr[i].channels_pad = s.K_pad
+        arr[i].chunks_stored = s.C_pad // 8
         arr[i].batch_stride = 0 if (s.N == 1 and N > 1) else s.data.stride(0)
         arr[i].batch_mod = _tc_batch_mod(s, N)
         arr[i].center_only = 1 if s.center else 0
@@ -751,7 +759,7 @@ def tc_conv3x3(sources, packed_weight, bias_pad, C_out, relu):
     out = torch.empty(N, cp // 8, H, W, 8, dtype=torch.bfloat16, device=sources[0].data.device)
     cin_pad = sum(s.C_pad for s in sources)
     args = (arr, len(sources), N, H, W, _ptr(packed_weight), _ptr(bias_pad), C_out, 1 if relu else 0, _ptr(out), cp)
-    key = (tuple(-s.C_pad if s.center else s.C_pad for s in sources), cp, H, W, min(N, 64))
+    key = (tuple(-s.K_pad if s.center else s.K_pad for s in sources), cp, H, W, min(N, 64))
     tune = _tc_tune.get(key)
     if tune is None:
         tune = _tc_autotune(key, args) if (tc_autotune_enabled and not torch.cuda.is_current_stream_capturing()) else 0
@@ -773,7 +781,8 @@ def tc_conv3x3_hilo(sources, packed_weight, C_out, with_lo=True):
         if s.H != H or s.W != W:
             raise ValueError('tc_conv3x3_hilo: sources must share the spatial size')
         arr[i].ptr = s.data.data_ptr()
-        arr[i].channels_pad = s.C_pad
+        arr[i].channels_pad = s.K_pad
+        arr[i].chunks_stored = s.C_pad // 8
         arr[i].batch_stride = 0 if (s.N == 1 and N > 1) else s.data.stride(0)
         arr[i].batch_mod = _tc_batch_mod(s, N)
     cp = _pad16(C_out)
@@ -791,7 +800,8 @@ def tc_conv3x3_hilo(sources, packed_weight, C_out, with_lo=True):
 def tc_pack_hoisted_weights(weight_oihw, parts):
     """Packed weights of a conv whose sources mix 3x3 inputs and hoisted partial sums.
 
-    parts: list in source order of ('conv', (c0, c1)) -- input channels [c0, c1) of ``weight_oihw`` applied as 3x3 --
+    parts: list in source order of ('conv', (c0, c1)) -- input channels [c0, c1) of ``weight_oihw`` applied as 3x3 --,
+    ('i2c', (c0, c1)) -- the same channels read from an im2col ``center`` source (tc_rasterize_im2col) --
     or ('partial', channels) -- a ``center`` source with ``channels`` = pad16(C_out) (hi) or twice that (hi | lo):
     identity on the centre tap."""
     C_out = weight_oihw.shape[0]
@@ -801,6 +811,10 @@ def tc_pack_hoisted_weights(weight_oihw, parts):
         if kind == 'conv':
             c0, c1 = arg
             bufs.append(tc_pack_weights(weight_oihw[:, c0:c1].contiguous(), [c1 - c0]))
+        elif kind == 'i2c':       # im2col source: channel c * 9 + kh * 3 + kw <-> weight[:, c0 + c, kh, kw]
+            c0, c1 = arg
+            w1 = weight_oihw[:, c0:c1].reshape(C_out, (c1 - c0) * 9, 1, 1).contiguous()
+            bufs.append(tc_pack_weights(w1, [(c1 - c0) * 9]))
         else:
             eye = torch.zeros(C_out, arg, 1, 1, dtype=torch.float32, device=weight_oihw.device)
             idx = torch.arange(C_out, device=weight_oihw.device)

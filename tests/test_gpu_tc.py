@@ -183,10 +183,11 @@ def test_tc_rasterize_pyramid_vs_oracle(ops, n_img, n_ch, H, W):
     coords = torch.rand(n_img * n_ch, 2, generator=g) * torch.tensor([W - 1.0, H - 1.0])
     ref0 = torch.from_numpy(O.get_patch_stack(tmpl, coords.numpy(), H, W)).view(n_img, n_ch, H, W)
     ref = O.avgpool_pyramid(ref0, 6)
-    for slot in (0, 0):          # second call reuses the persistent buffers (padding chunk stays zero)
+    for slot in (0, 0):          # repeated calls return fresh, identical planes
         pyr = ops.tc_rasterize_pyramid(torch.from_numpy(tmpl).cuda(), coords.cuda(), n_img, n_ch, H, W, 6, slot=slot)
         for l, (a, r) in enumerate(zip(pyr, ref)):
-            assert a.C == n_ch and a.C_pad == 16 and a.data.shape == (n_img, 2, H >> l, W >> l, 8)
+            # ONE 8-channel plane per level; a conv sees K_pad = 16 channels (TMA zero-fills the missing plane)
+            assert a.C == n_ch and a.C_pad == 8 and a.K_pad == 16 and a.data.shape == (n_img, 1, H >> l, W >> l, 8)
             got = ops.tc_unpack(a).cpu()
             if l == 0:
                 assert torch.equal(got, bf16_exact(r))
@@ -253,3 +254,28 @@ def test_tc_hoisted_partial_sums_match_direct_conv(ops):
     out1 = ops.tc_conv3x3([ops.tc_pack(up.cuda()), part1.repeat_interleave(G), ops.tc_pack(wp.cuda())], packed1, bp.cuda(),
                           32, True)
     assert rel_err(ops.tc_unpack(out1).cpu().numpy(), ref.numpy()) < 1.2e-2
+
+
+@pytest.mark.parametrize('level', [0, 1])
+def test_tc_im2col_waypoint_source_matches_3x3(ops, level):
+    """Waypoint maps written as im2col + a 1x1 centre-tap K block == the 3x3 conv over the plain maps."""
+    torch.manual_seed(12)
+    n_img, n_wp, H, W = 3, 2, 64, 96
+    tmpl = ops.create_dist_template(300, 'cuda')
+    coords = torch.tensor([[10.2, 5.5], [80.0, 60.0], [0.0, 0.0], [95.0, 63.0], [40.5, 31.5], [47.0, 2.0]], device='cuda')
+    pyr = ops.tc_rasterize_pyramid(tmpl, coords, n_img, n_wp, H, W, 2, slot=77)
+    plain = pyr[level]
+    i2c = ops.tc_rasterize_im2col(tmpl, coords, n_img, n_wp, H, W, level)
+    assert i2c.center and i2c.C == 18 and i2c.H == H >> level
+    # im2col channel (c, kh, kw) is the plain map shifted by (kh - 1, kw - 1) with zero fill
+    pm = ops.tc_unpack(plain).cpu()
+    im = ops.tc_unpack(i2c).cpu()
+    ref = F.unfold(pm, 3, padding=1).view(n_img, n_wp * 9, H >> level, W >> level)
+    assert torch.equal(im, ref)
+    w = bf16_exact(torch.randn(32, 18, 3, 3) * 0.1)
+    bias = torch.randn(32)
+    up = ops.tc_pack(bf16_exact(torch.randn(n_img, 16, H >> level, W >> level)).cuda())
+    direct = ops.tc_conv3x3([up, plain], ops.tc_pack_weights(w.cuda(), [16, 2]), bias.cuda(), 32, True)
+    packed = ops.tc_pack_hoisted_weights(w.cuda(), [('conv', (0, 16)), ('i2c', (16, 18))])
+    fused = ops.tc_conv3x3([up, i2c], packed, bias.cuda(), 32, True)
+    assert rel_err(ops.tc_unpack(fused).cpu().numpy(), ops.tc_unpack(direct).cpu().numpy()) < 4e-3
