@@ -297,6 +297,15 @@ int ynet_tc_conv3x3_hilo(const ynet_tc_src* srcs_host, int32_t n_src, int32_t N,
 int ynet_tc_conv1x1_f32(const ynet_tc_src* srcs_host, int32_t n_src, int32_t N, int32_t H, int32_t W,
                         const void* packed_weight, const float* bias, int32_t C_out, float* out, int32_t tune,
                         void* stream);
+/* decoder.4.2 + predictor + SoftArgmax2D in ONE kernel (ynet.py:448-451,468-469 + 582-583): the 3x3 conv's bf16
+ * output tile stays in shared memory, is multiplied there with the (replicated) predictor weights and reduced by
+ * the soft-argmax warps; neither the activation (64 B/pixel out + in) nor the logits reach HBM.  C_out <= 64,
+ * C_pred <= 32; packed_pred_weight = ynet_tc_pack_weights(predictor weight, ksize 1, one source of C_out channels);
+ * workspace: ynet_tc_conv1x1_softargmax_workspace_bytes(N, C_pred, H, W).  out (N, C_pred, 2) = (x, y). */
+int ynet_tc_conv3x3_pred_softargmax(const ynet_tc_src* srcs_host, int32_t n_src, int32_t N, int32_t H, int32_t W,
+                                    const void* packed_weight, const float* bias, int32_t C_out, int32_t relu,
+                                    const void* packed_pred_weight, const float* pred_bias, int32_t C_pred,
+                                    float* out, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t ynet_tc_conv1x1_softargmax_workspace_bytes(int32_t N, int32_t C_out, int32_t H, int32_t W);
 int ynet_tc_conv1x1_softargmax(const ynet_tc_src* srcs_host, int32_t n_src, int32_t N, int32_t H, int32_t W,
                                const void* packed_weight, const float* bias, int32_t C_out, float* out,

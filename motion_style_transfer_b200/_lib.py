@@ -86,6 +86,7 @@ _PROTOS = {
     'ynet_tc_upconv_border_weights': (c_int, [_P, _I, _I, POINTER(c_int32), _P, _P]),
     'ynet_tc_upconv3x3': (c_int, [POINTER(TcSrc), POINTER(c_int32), _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _I, _P]),
     'ynet_tc_conv3x3': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _I, _P]),
+    'ynet_tc_conv3x3_pred_softargmax': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P, _L, _P]),
     'ynet_tc_conv3x3_hilo': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P]),
     'ynet_bce_workspace_bytes': (_L, [_L]),
     'ynet_bce_logits_fwd_bwd': (c_int, [_P, _P, _L, _F, _P, _P, _P, _L, _P]),

@@ -62,7 +62,7 @@ struct TcParams {
   int* err;
 };
 
-constexpr int EPI_C8 = 0, EPI_NCHW_F32 = 1, EPI_UP2 = 3, EPI_HILO = 4;
+constexpr int EPI_C8 = 0, EPI_NCHW_F32 = 1, EPI_UP2 = 3, EPI_HILO = 4, EPI_PRED = 5;
 
 // ---- the conv kernel -------------------------------------------------------------------------------------
 template <int J, int TAPS, int EPI>
@@ -216,7 +216,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
       }
     }
   } else {
-    // ===================== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====================
+    // ===================== epilogue: 4 warps; warp w owns TMEM lanes 32*(w%4) .. +31 =====================
     const int q = warp & 3;
     const int m = q * 32 + lane;         // accumulator row = pixel of the tile
     const int py = m >> 3, px = m & 7;
@@ -327,6 +327,295 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
                  : "memory");
+  }
+}
+
+// ---- 3x3 conv + ReLU -> 1x1 predictor -> SoftArgmax2D in ONE kernel (decoder.4.2 + predictor + softargmax) ----------
+// The conv's bf16 output tile never leaves the SM: the conv epilogue writes it to shared memory in the K-major C8
+// layout, the MMA warp multiplies it (as the N = 256-pixel operand) with the replicated predictor weights (M = 128:
+// see pred_tc.cu) and 16 soft-argmax warps reduce the transposed logits (TMEM lane = channel) straight from
+// tcgen05.ld.  Saves the 64 B/pixel write + 64 B/pixel read of the activation and one launch; the soft-argmax warps
+// (MUFU / issue bound) run concurrently with the conv's MMAs (shared-memory-operand bound).
+// TMEM: conv accumulators 2 x (2 x 32) columns at [0, 128), predictor accumulator 256 columns at [256, 512).
+struct PredFuse {
+  const unsigned char* pw;   // predictor weights [kb][1][2][pn_pad][8] bf16
+  const float* pbias;        // pn_pad floats
+  float4* partial;
+  int c_pred, pn_pad, slots;
+  long long tiles_per_cta;
+};
+constexpr int FP_CONV_EPI_WARPS = 8;   // two per TMEM lane quadrant: one per column block (4 warps alone bound the tile)
+constexpr int FP_J = 2;
+// warp 0: TMA; warps 1..2: MMA issuers (one per column block: a single issuing thread needs ~45 cycles of descriptor
+// set-up per MMA and would bound the tile); 8 conv-epilogue warps; 16 soft-argmax warps
+constexpr int FP_THREADS = 32 * (1 + FP_J + FP_CONV_EPI_WARPS + PR_EPI_WARPS);   // 864
+
+__global__ void __launch_bounds__(FP_THREADS, 1)
+tc_conv_pred_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                    const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3, const TcParams p,
+                    const PredFuse f) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int J = FP_J, BW = 8 * J + 2, BH = TC_TH + 2;
+  const int y_chunks = p.n_pad >> 3;                 // 8-channel planes of the conv output
+  const int y_bytes = y_chunks * 256 * 16;           // one Y buffer: [chunk][16 rows][16 px][8 ch]
+  const int kbp = p.n_pad >> 4;                      // predictor K blocks
+
+  unsigned char* s_w = smem;
+  unsigned char* s_stage = smem + p.wres_bytes;
+  unsigned char* s_y = s_stage + (size_t)p.stages * p.stage_bytes;
+  unsigned char* s_pw = s_y + 2 * y_bytes;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pw + (size_t)kbp * PR_WBLK_BYTES);
+  uint64_t* full_bar = s_bar;
+  uint64_t* empty_bar = s_bar + TC_MAX_STAGES;
+  uint64_t* tfull_bar = s_bar + 2 * TC_MAX_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* w_bar = tempty_bar + 2;
+  uint64_t* y_bar = w_bar + 1;          // [2] conv output tile written (4 epilogue warps)
+  uint64_t* yfree_bar = y_bar + 2;      // [2] predictor MMAs that read the buffer have retired
+  uint64_t* pfull_bar = yfree_bar + 2;  // predictor accumulator complete
+  uint64_t* pempty_bar = pfull_bar + 1; // predictor accumulator drained (16 soft-argmax warps)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(pempty_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(pempty_bar + 2);
+  for (int i = threadIdx.x; i < p.n_pad; i += FP_THREADS) s_bias[i] = p.bias[i];
+  pred_stage_weights(s_pw, f.pw, kbp, f.pn_pad, threadIdx.x, FP_THREADS);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), J);     // one tcgen05.commit per MMA-issuing warp
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tfull_bar[a]), J);
+      mbar_init(smem_u32(&tempty_bar[a]), FP_CONV_EPI_WARPS);
+      mbar_init(smem_u32(&y_bar[a]), FP_CONV_EPI_WARPS);
+      mbar_init(smem_u32(&yfree_bar[a]), 1);
+    }
+    mbar_init(smem_u32(w_bar), 1);
+    mbar_init(smem_u32(pfull_bar), 1);
+    mbar_init(smem_u32(pempty_bar), PR_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t pacc = tmem_base + 256u;
+
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const long long t0 = (long long)blockIdx.x * f.tiles_per_cta;
+  const long long t1 = tmin<long long>(p.total_tiles, t0 + f.tiles_per_cta);
+  // tile coordinates advance incrementally in every role
+  int n = (int)(t0 / tiles_per_img);
+  const int r0t = (int)(t0 - (long long)n * tiles_per_img);
+  int ty = r0t / p.tiles_x, tx = r0t - ty * p.tiles_x;
+  auto next_tile = [&]() {
+    if (++tx == p.tiles_x) {
+      tx = 0;
+      if (++ty == p.tiles_y) {
+        ty = 0;
+        ++n;
+      }
+    }
+  };
+  const int wblk_bytes = 9 * 2 * p.n_pad * 16;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t total = (uint32_t)p.w_total;
+      mbar_expect_tx(smem_u32(w_bar), total);
+      for (uint32_t off = 0; off < total; off += 32768) {
+        const uint32_t nb = min(32768u, total - off);
+        bulk_load(smem_u32(s_w + off), p.wpacked + off, nb, smem_u32(w_bar));
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = t0; tile < t1; ++tile) {
+        const int y0 = ty * TC_TH, x0 = tx * 8 * J;
+        int kb = 0;
+        for (int s = 0; s < p.n_src; ++s) {
+          const CUtensorMap* map = (s == 0) ? &map0 : (s == 1) ? &map1 : (s == 2) ? &map2 : &map3;
+          const int bm = p.src[s].batch_mod;
+          const int ns = p.src[s].bcast ? 0 : (bm > 0 ? n % bm : (bm < 0 ? n / (-bm) : n));
+          for (int b = 0; b < p.src[s].kblocks; ++b, ++kb) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, nullptr);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_expect_tx(fb, p.a_bytes);
+            tma_load_4d(smem_u32(s_stage + (size_t)stage * p.stage_bytes), map, fb, 8 * (x0 - 1), y0 - 1, 2 * b, ns);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+        next_tile();
+      }
+    }
+  } else if (warp <= J) {
+    // ===================== MMA issuers: warp 1 + jj issues the conv MMAs of column block jj; warp 1 also issues the
+    // predictor MMAs of tile i - 1 after the conv MMAs of tile i =====================
+    const int jj = warp - 1;
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc_p = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+      auto issue_pred = [&](uint32_t j) {
+        const uint32_t b = j & 1u;
+        mbar_wait(smem_u32(&y_bar[b]), (j >> 1) & 1u, nullptr);          // conv output tile j is in shared memory
+        mbar_wait(smem_u32(pempty_bar), (j & 1u) ^ 1u, nullptr);         // soft-argmax of tile j - 1 has drained pacc
+        tc_fence_after();
+        for (int kb = 0; kb < kbp; ++kb) {
+          const uint64_t adesc = make_desc(smem_u32(s_pw + (size_t)kb * PR_WBLK_BYTES), 128 * 16, 128);
+          const uint64_t bdesc = make_desc(smem_u32(s_y + (size_t)b * y_bytes + (size_t)kb * 2 * 4096), 4096, 128);
+          tc_mma_bf16(pacc, adesc, bdesc, idesc_p, kb > 0 ? 1u : 0u);
+        }
+        tc_commit(smem_u32(pfull_bar));
+        tc_commit(smem_u32(&yfree_bar[b]));
+      };
+      mbar_wait(smem_u32(w_bar), 0, nullptr);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      constexpr uint32_t A_HI = (uint32_t)((BW * 16) >> 4) | (1u << 14);
+      constexpr uint32_t A_LBO_FIELD = (uint32_t)((BH * BW * 16) >> 4) << 16;
+      const uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);
+      const uint32_t b_lbo_field = (uint32_t)((p.n_pad * 16) >> 4) << 16;
+      const uint32_t b_tap_step = (uint32_t)(2 * p.n_pad);
+      for (long long tile = t0; tile < t1; ++tile, ++it) {
+        const uint32_t acc = it & 1u;
+        mbar_wait(smem_u32(&tempty_bar[acc]), ((it >> 1) & 1u) ^ 1u, nullptr);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)(J * p.n_pad);
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase, nullptr);
+          tc_fence_after();
+          const uint32_t a_lo0 = ((smem_u32(s_stage + (size_t)stage * p.stage_bytes) >> 4) & 0x3FFF) | A_LBO_FIELD;
+          uint32_t b_lo = ((smem_u32(s_w + p.wofs[kb]) >> 4) & 0x3FFF) | b_lbo_field;
+          const uint32_t acc_first = (kb > 0) ? 1u : 0u;
+          if ((p.center_mask >> kb) & 1u) {
+            const uint64_t bdesc = ((uint64_t)b_hi << 32) | b_lo;
+            {
+              const uint64_t adesc = ((uint64_t)A_HI << 32) | (a_lo0 + (uint32_t)(BW + 1 + 8 * jj));
+              tc_mma_bf16(d_tmem + (uint32_t)(jj * p.n_pad), adesc, bdesc, idesc, acc_first);
+            }
+          } else {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint64_t bdesc = ((uint64_t)b_hi << 32) | b_lo;
+              {
+                const uint64_t adesc = ((uint64_t)A_HI << 32) | (a_lo0 + (uint32_t)((tap / 3) * BW + (tap % 3) + 8 * jj));
+                tc_mma_bf16(d_tmem + (uint32_t)(jj * p.n_pad), adesc, bdesc, idesc, tap == 0 ? acc_first : 1u);
+              }
+              b_lo += b_tap_step;
+            }
+          }
+          tc_commit(smem_u32(&empty_bar[stage]));
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(smem_u32(&tfull_bar[acc]));
+        if (jj == 0 && it >= 1) issue_pred(it - 1);
+      }
+      if (jj == 0 && it >= 1) issue_pred(it - 1);
+    }
+  } else if (warp < 1 + J + FP_CONV_EPI_WARPS) {
+    // ===================== conv epilogue: accumulator -> bias -> ReLU -> bf16 -> shared memory (K-major C8) =============
+    const int q = warp & 3;
+    const int jj = (warp - (1 + J)) >> 2;          // column block of this warp
+    const int m = q * 32 + lane;
+    const int py = m >> 3, px = m & 7;
+    uint32_t it = 0;
+    for (long long tile = t0; tile < t1; ++tile, ++it) {
+      const uint32_t acc = it & 1u;
+      mbar_wait(smem_u32(&tfull_bar[acc]), (it >> 1) & 1u, nullptr);
+      mbar_wait(smem_u32(&yfree_bar[acc]), ((it >> 1) & 1u) ^ 1u, nullptr);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)(J * p.n_pad);
+      unsigned char* yb = s_y + (size_t)acc * y_bytes + py * 256 + px * 16;
+      {
+        for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_row + (uint32_t)(jj * p.n_pad + c0), v);
+          float fv[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            fv[k] = __uint_as_float(v[k]) + s_bias[c0 + k];
+            if (p.relu) fv[k] = fmaxf(fv[k], 0.f);
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint4 o;
+            o.x = pack_bf16(fv[8 * h + 0], fv[8 * h + 1]);
+            o.y = pack_bf16(fv[8 * h + 2], fv[8 * h + 3]);
+            o.z = pack_bf16(fv[8 * h + 4], fv[8 * h + 5]);
+            o.w = pack_bf16(fv[8 * h + 6], fv[8 * h + 7]);
+            *reinterpret_cast<uint4*>(yb + ((c0 >> 3) + h) * 4096 + jj * 128) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&tempty_bar[acc]));
+        mbar_arrive(smem_u32(&y_bar[acc]));
+      }
+    }
+  } else {
+    // ===================== soft-argmax: 16 warps, one tile row each; TMEM lane = channel =====================
+    const int e = warp - (1 + J + FP_CONV_EPI_WARPS);
+    const int q = warp & 3;
+    const int row = q * 4 + (e >> 2);
+    const bool active = lane < f.c_pred;
+    const float bias = active ? f.pbias[lane] : 0.f;
+    SoftState st{PR_NEG, 0.f, 0.f, 0.f};
+    int cur_n = -1;
+    auto flush = [&](int n_img) {
+      if (active) {
+        const long long first_cta = ((long long)n_img * tiles_per_img) / f.tiles_per_cta;
+        const int slot = (int)(blockIdx.x - first_cta) * PR_EPI_WARPS + e;
+        f.partial[((size_t)n_img * f.c_pred + lane) * f.slots + slot] = make_float4(st.m, st.s, st.sx, st.sy);
+      }
+    };
+    uint32_t it = 0;
+    for (long long tile = t0; tile < t1; ++tile, ++it) {
+      const int y = ty * TC_TH + row, x0 = tx * 8 * J;
+      if (n != cur_n) {
+        if (cur_n >= 0) flush(cur_n);
+        st = SoftState{PR_NEG, 0.f, 0.f, 0.f};
+        cur_n = n;
+      }
+      mbar_wait(smem_u32(pfull_bar), it & 1u, nullptr);
+      tc_fence_after();
+      uint32_t v[16];
+      tmem_ld16(pacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(row * 16), v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(pempty_bar));      // the values are in registers: release the accumulator
+      if (y < p.H) {
+        if (x0 + 8 * J <= p.W)
+          softargmax_row16(st, v, bias, x0, y);
+        else
+          softargmax_row16_masked(st, v, bias, x0, y, p.W);
+      }
+      next_tile();
+    }
+    if (cur_n >= 0) flush(cur_n);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -871,6 +1160,7 @@ struct TcOut {
   void* c8;
   float* f32;
   float4* partial;
+  PredFuse* fuse;      // EPI_PRED: predictor weights / partial buffer (tiles_per_cta and slots are filled in by tc_launch)
 };
 
 template <int TAPS, int EPI>
@@ -925,6 +1215,7 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
   if (const char* e = getenv("YNET_TC_J")) j = tmin(j_cap, atoi(e));
   if (tune & 0xF) j = tmin(j_cap, tune & 0xF);
   j = tmax(1, j);
+  if (epi == EPI_PRED) j = FP_J;
   p.j = j;
   p.bw = 8 * j + 2 * halo;
   const int bh = TC_TH + 2 * halo;
@@ -1034,6 +1325,36 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
     if (e != cudaSuccess) return cuda_fail(e, "tc_launch(cudaFuncSetAttribute)");
     configured = true;
   }
+  if (epi == EPI_PRED) {
+    if (!p.resident || C_out_pad > 64 || out.fuse == nullptr) {
+      set_error("%s: the fused conv + predictor kernel needs resident weights and C_out_pad <= 64", who);
+      return YNET_E_UNSUPPORTED;
+    }
+    const PredPlan pl = pred_plan(N, H, W);
+    PredFuse f = *out.fuse;
+    f.tiles_per_cta = pl.tiles_per_cta;
+    f.slots = pl.slots;
+    const int y_bytes = (C_out_pad / 8) * 4096;
+    const int kbp = C_out_pad / 16;
+    const int tail_f = (2 * TC_MAX_STAGES + 12) * 8 + 16 + 256 * 4;
+    p.stages = tmin(10, (200 * 1024 - p.wres_bytes - 2 * y_bytes - kbp * PR_WBLK_BYTES - tail_f) / p.stage_bytes);
+    if (p.stages < 2) {
+      set_error("%s: layer does not fit shared memory", who);
+      return YNET_E_UNSUPPORTED;
+    }
+    const size_t smem_f = (size_t)p.wres_bytes + (size_t)p.stages * p.stage_bytes + 2 * (size_t)y_bytes +
+                          (size_t)kbp * PR_WBLK_BYTES + tail_f + 1024;
+    static bool configured_f = false;
+    if (!configured_f) {
+      cudaError_t e = cudaFuncSetAttribute(tc_conv_pred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "tc_launch(cudaFuncSetAttribute)");
+      configured_f = true;
+    }
+    tc_conv_pred_kernel<<<pl.grid, FP_THREADS, smem_f, as_stream(stream)>>>(maps[0], maps[1], maps[2], maps[3], p, f);
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return cuda_fail(le, who);
+    return YNET_OK;
+  }
   int ctas_per_sm = (smem_bytes <= 110 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
   if (const char* e = getenv("YNET_TC_CTAS_PER_SM")) ctas_per_sm = tmax(1, tmin(2, atoi(e)));
   if ((tune >> 4) & 0xF) ctas_per_sm = tmin(ctas_per_sm, tmax(1, (tune >> 4) & 0xF));
@@ -1069,16 +1390,50 @@ int ynet_tc_conv3x3(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int32_t H
                     void* stream) {
   YNET_CHECK_ARG(out_c8 != nullptr || N == 0, "null output");
   YNET_CHECK_ALIGN(out_c8, 16);
-  TcOut o{out_c8, nullptr, nullptr};
+  TcOut o{out_c8, nullptr, nullptr, nullptr};
   return tc_launch("ynet_tc_conv3x3", srcs, n_src, N, H, W, packed_weight, bias, C_out, relu, C_out_pad, tune, 9, EPI_C8, o,
                    nullptr, stream);
+}
+
+int ynet_tc_conv3x3_pred_softargmax(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int32_t H, int32_t W,
+                                    const void* packed_weight, const float* bias, int32_t C_out, int32_t relu,
+                                    const void* packed_pred_weight, const float* pred_bias, int32_t C_pred, float* out,
+                                    void* workspace, int64_t workspace_bytes, void* stream) {
+  YNET_CHECK_ARG(out != nullptr || N == 0, "null output");
+  YNET_CHECK_ARG(packed_pred_weight && pred_bias, "null pointer");
+  YNET_CHECK_ARG(C_pred > 0 && C_pred <= 32 && C_out > 0 && C_out <= 64, "C_pred <= 32, C_out <= 64");
+  if (N == 0) return YNET_OK;
+  YNET_CHECK_ALIGN(packed_pred_weight, 16);
+  if (workspace == nullptr || workspace_bytes < ynet_tc_conv1x1_softargmax_workspace_bytes(N, C_pred, H, W)) {
+    set_error("ynet_tc_conv3x3_pred_softargmax: workspace too small");
+    return YNET_E_WORKSPACE;
+  }
+  YNET_CHECK_ALIGN(workspace, 16);
+  const PredPlan pl = pred_plan(N, H, W);
+  PredFuse f;
+  memset(&f, 0, sizeof(f));
+  f.pw = reinterpret_cast<const unsigned char*>(packed_pred_weight);
+  f.pbias = pred_bias;
+  f.partial = reinterpret_cast<float4*>(workspace);
+  f.c_pred = C_pred;
+  f.pn_pad = ceil_div(C_pred, 16) * 16;
+  cudaStream_t st = as_stream(stream);
+  cudaError_t le = pred_partial_init(f.partial, (long long)N * C_pred * pl.slots, st);
+  if (le != cudaSuccess) return cuda_fail(le, "ynet_tc_conv3x3_pred_softargmax");
+  TcOut o{nullptr, nullptr, nullptr, &f};
+  int rc = tc_launch("ynet_tc_conv3x3_pred_softargmax", srcs, n_src, N, H, W, packed_weight, bias, C_out, relu,
+                     ceil_div(C_out, 16) * 16, 0, 9, EPI_PRED, o, nullptr, stream);
+  if (rc != YNET_OK) return rc;
+  le = pred_partial_finalize(f.partial, N * C_pred, pl.slots, out, st);
+  if (le != cudaSuccess) return cuda_fail(le, "ynet_tc_conv3x3_pred_softargmax");
+  return YNET_OK;
 }
 
 int ynet_tc_conv3x3_hilo(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int32_t H, int32_t W, const void* packed_weight,
                          int32_t C_out, void* out_c8, int32_t C_out_pad, int32_t with_lo, int32_t tune, void* stream) {
   YNET_CHECK_ARG(out_c8 != nullptr || N == 0, "null output");
   YNET_CHECK_ALIGN(out_c8, 16);
-  TcOut o{out_c8, nullptr, nullptr};
+  TcOut o{out_c8, nullptr, nullptr, nullptr};
   return tc_launch("ynet_tc_conv3x3_hilo", srcs, n_src, N, H, W, packed_weight, nullptr, C_out, with_lo ? 2 : 0, C_out_pad,
                    tune, 9, EPI_HILO, o, nullptr, stream);
 }
@@ -1139,7 +1494,7 @@ int ynet_tc_upconv3x3(const ynet_tc_src* srcs, const int32_t* src_channels_host,
     return YNET_E_UNSUPPORTED;
   }
   const int cp = ceil_div(C_out, 16) * 16;
-  TcOut o{out_c8, nullptr, nullptr};
+  TcOut o{out_c8, nullptr, nullptr, nullptr};
   int rc = tc_launch("ynet_tc_upconv3x3", srcs, n_src, N, h, w, packed_phase_weight, bias_eff, 4 * cp, 0, 4 * cp, tune, 9,
                      EPI_UP2, o, nullptr, stream);
   if (rc != YNET_OK || N == 0) return rc;
@@ -1192,7 +1547,7 @@ int ynet_tc_upconv3x3(const ynet_tc_src* srcs, const int32_t* src_channels_host,
 int ynet_tc_conv1x1_f32(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int32_t H, int32_t W, const void* packed_weight,
                         const float* bias, int32_t C_out, float* out, int32_t tune, void* stream) {
   YNET_CHECK_ARG(out != nullptr || N == 0, "null output");
-  TcOut o{nullptr, out, nullptr};
+  TcOut o{nullptr, out, nullptr, nullptr};
   return tc_launch("ynet_tc_conv1x1_f32", srcs, n_src, N, H, W, packed_weight, bias, C_out, 0, ceil_div(C_out, 16) * 16, tune,
                    1, EPI_NCHW_F32, o, nullptr, stream);
 }

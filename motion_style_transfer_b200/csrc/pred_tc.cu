@@ -20,22 +20,9 @@
 
 namespace ynet {
 
-constexpr int PR_TH = 16;            // tile rows
-constexpr int PR_J = 2;              // 8-pixel column blocks per tile: tile = 16 x 16 pixels = ONE N = 256 accumulator
-constexpr int PR_TW = 8 * PR_J;
-constexpr int PR_EPI_WARPS = 16;           // one tile row (16 pixels) per warp
 constexpr int PR_THREADS = 64 + 32 * PR_EPI_WARPS;
 constexpr int PR_STAGES = 14;
 constexpr int PR_STAGE_BYTES = 2 * PR_TH * PR_TW * 16;   // one 16-channel K block of a tile: [chunk][row][px][8 ch]
-constexpr int PR_WBLK_BYTES = 2 * 128 * 16;              // weights of one K block: [chunk][128 rows][8 ch]
-constexpr int PR_MAX_KB = 8;
-constexpr float PR_NEG = -3.402823466e+38f;
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 struct PredParams {
   int N, H, W, c_out, n_pad, kblocks;
@@ -61,18 +48,7 @@ tc_pred_softargmax_kernel(const __grid_constant__ CUtensorMap map, const PredPar
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  // weights -> shared memory, rows replicated into the four lane quadrants (row r carries channel r % 32)
-  {
-    const uint4* g = reinterpret_cast<const uint4*>(p.wpacked);
-    uint4* s = reinterpret_cast<uint4*>(s_w);
-    const int total = p.kblocks * 2 * 128;
-    for (int e = threadIdx.x; e < total; e += PR_THREADS) {
-      const int r = e & 127, kc = e >> 7;          // kc = kb * 2 + chunk
-      const int ch = r & 31;
-      s[e] = (ch < p.n_pad) ? __ldg(g + (size_t)kc * p.n_pad + ch) : make_uint4(0, 0, 0, 0);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-  }
+  pred_stage_weights(s_w, p.wpacked, p.kblocks, p.n_pad, threadIdx.x, PR_THREADS);
   if (threadIdx.x == 0) {
     for (int s = 0; s < PR_STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
@@ -129,7 +105,7 @@ tc_pred_softargmax_kernel(const __grid_constant__ CUtensorMap map, const PredPar
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {   // whole warp, uniform control flow; the MMA / commit instructions elect one lane
       // D = F32, A = B = BF16, both K-major, N = 256 pixels (the whole 16 x 16 tile), M = 128 (4 x 32 replicated channels)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
       int stage = 0;
@@ -147,14 +123,14 @@ tc_pred_softargmax_kernel(const __grid_constant__ CUtensorMap map, const PredPar
           // a tile row is 16 px = two contiguous 128-byte core matrices: all 32 eight-pixel groups of the tile are
           // 128 B apart, so ONE N = 256 instruction covers the tile; accumulator column = row * 16 + x
           const uint64_t bdesc = make_desc(st, PR_TH * PR_TW * 16, 128);
-          tc_mma_bf16(tmem_base + (uint32_t)(acc * 256), adesc, bdesc, idesc, kb > 0 ? 1u : 0u);
-          tc_commit(smem_u32(&empty_bar[stage]));
+          tc_mma_bf16_elect(tmem_base + (uint32_t)(acc * 256), adesc, bdesc, idesc, kb > 0 ? 1u : 0u);
+          tc_commit_elect(smem_u32(&empty_bar[stage]));
           if (++stage == PR_STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(smem_u32(&tfull_bar[acc]));
+        tc_commit_elect(smem_u32(&tfull_bar[acc]));
       }
     }
   } else {
@@ -164,28 +140,26 @@ tc_pred_softargmax_kernel(const __grid_constant__ CUtensorMap map, const PredPar
     const int row = q * 4 + (e >> 2);              // tile row reduced by this warp (4 warps per lane quadrant)
     const bool active = lane < p.c_out;
     const float bias = active ? p.bias[lane] : 0.f;
-    float st_m = PR_NEG, st_s = 0.f, st_sx = 0.f, st_sy = 0.f;
+    SoftState st{PR_NEG, 0.f, 0.f, 0.f};
     int cur_n = -1;
     auto flush = [&](int n_img) {
       if (active) {
         const long long first_cta = ((long long)n_img * tiles_per_img) / p.tiles_per_cta;
         const int slot = (int)(blockIdx.x - first_cta) * PR_EPI_WARPS + e;
-        p.partial[((size_t)n_img * p.c_out + lane) * p.slots + slot] = make_float4(st_m, st_s, st_sx, st_sy);
+        p.partial[((size_t)n_img * p.c_out + lane) * p.slots + slot] = make_float4(st.m, st.s, st.sx, st.sy);
       }
     };
     // tile coordinates advance incrementally (no per-tile 64-bit divisions in the hot loop)
     int n = (int)(t0 / tiles_per_img);
     int r0t = (int)(t0 - (long long)n * tiles_per_img);
     int ty = r0t / p.tiles_x, tx = r0t - ty * p.tiles_x;
-    constexpr float LOG2E = 1.4426950408889634f;
     uint32_t it = 0;
     for (long long tile = t0; tile < t1; ++tile, ++it) {
       const int y0 = ty * PR_TH, x0 = tx * PR_TW;
       const int acc = (int)(it & 1u);
       if (n != cur_n) {
         if (cur_n >= 0) flush(cur_n);
-        st_m = PR_NEG;
-        st_s = st_sx = st_sy = 0.f;
+        st = SoftState{PR_NEG, 0.f, 0.f, 0.f};
         cur_n = n;
       }
       mbar_wait(smem_u32(&tfull_bar[acc]), (it >> 1) & 1u, nullptr);
@@ -193,63 +167,11 @@ tc_pred_softargmax_kernel(const __grid_constant__ CUtensorMap map, const PredPar
       const int y = y0 + row;
       uint32_t v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + row * 16), v);
-      if (x0 + PR_TW <= p.W) {
-        // fast path (every tile when W is a multiple of 16): ~5 instructions per pixel
-        if (y < p.H) {
-          float mx = __uint_as_float(v[0]);
-#pragma unroll
-          for (int i = 1; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-          mx += bias;
-          if (mx > st_m) {     // rare after the first tiles of an image
-            const float sc = (st_m == PR_NEG) ? 0.f : __expf(st_m - mx);
-            st_s *= sc;
-            st_sx *= sc;
-            st_sy *= sc;
-            st_m = mx;
-          }
-          const float k = (bias - st_m) * LOG2E;       // e = 2^(a log2e + (bias - m) log2e) = exp(a + bias - m)
-          float ex[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) ex[i] = ex2_approx(fmaf(__uint_as_float(v[i]), LOG2E, k));
-          // four independent chains: se = sum e_i, sxl = sum i e_i
-          float s0 = ex[0] + ex[1], s1 = ex[4] + ex[5], s2 = ex[8] + ex[9], s3 = ex[12] + ex[13];
-          float x0s = ex[1], x1s = ex[4] * 4.f, x2s = ex[8] * 8.f, x3s = ex[12] * 12.f;
-          s0 += ex[2];  s1 += ex[6];  s2 += ex[10];  s3 += ex[14];
-          x0s = fmaf(ex[2], 2.f, x0s);   x1s = fmaf(ex[5], 5.f, x1s);   x2s = fmaf(ex[9], 9.f, x2s);   x3s = fmaf(ex[13], 13.f, x3s);
-          s0 += ex[3];  s1 += ex[7];  s2 += ex[11];  s3 += ex[15];
-          x0s = fmaf(ex[3], 3.f, x0s);   x1s = fmaf(ex[6], 6.f, x1s);   x2s = fmaf(ex[10], 10.f, x2s); x3s = fmaf(ex[14], 14.f, x3s);
-          x1s = fmaf(ex[7], 7.f, x1s);   x2s = fmaf(ex[11], 11.f, x2s); x3s = fmaf(ex[15], 15.f, x3s);
-          const float se = (s0 + s1) + (s2 + s3);
-          const float sxl = (x0s + x1s) + (x2s + x3s);
-          st_s += se;
-          st_sx += fmaf((float)x0, se, sxl);
-          st_sy = fmaf((float)y, se, st_sy);
-        }
-      } else if (y < p.H) {
-        float mx = PR_NEG;
-        unsigned okm = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const bool ok = x0 + i < p.W;
-          okm |= ok ? (1u << i) : 0u;
-          if (ok) mx = fmaxf(mx, __uint_as_float(v[i]) + bias);
-        }
-        if (okm != 0) {
-          if (mx > st_m) {
-            const float sc = (st_m == PR_NEG) ? 0.f : __expf(st_m - mx);
-            st_s *= sc;
-            st_sx *= sc;
-            st_sy *= sc;
-            st_m = mx;
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float ev = ((okm >> i) & 1u) ? __expf(__uint_as_float(v[i]) + bias - st_m) : 0.f;
-            st_s += ev;
-            st_sx = fmaf(ev, (float)(x0 + i), st_sx);
-            st_sy = fmaf(ev, (float)y, st_sy);
-          }
-        }
+      if (y < p.H) {
+        if (x0 + PR_TW <= p.W)
+          softargmax_row16(st, v, bias, x0, y);
+        else
+          softargmax_row16_masked(st, v, bias, x0, y, p.W);
       }
       tc_fence_before();
       __syncwarp();
@@ -314,12 +236,7 @@ pred_partial_finalize_kernel(const float4* __restrict__ part, int rows, int slot
   }
 }
 
-struct PredPlan {
-  int tiles_x, tiles_y, grid, slots;
-  long long total_tiles, tiles_per_cta;
-};
-
-static PredPlan pred_plan(int N, int H, int W) {
+PredPlan pred_plan(int N, int H, int W) {
   PredPlan pl;
   pl.tiles_x = ceil_div(W, PR_TW);
   pl.tiles_y = ceil_div(H, PR_TH);
@@ -331,6 +248,16 @@ static PredPlan pred_plan(int N, int H, int W) {
   // CTAs own contiguous tile ranges: an image is touched by at most ceil(per_img / tiles_per_cta) + 1 of them
   pl.slots = (int)(ceil_div<long long>(per_img, pl.tiles_per_cta) + 1) * PR_EPI_WARPS;
   return pl;
+}
+
+cudaError_t pred_partial_init(float4* part, long long n_part, cudaStream_t st) {
+  const unsigned ig = (unsigned)tmax<long long>(1, tmin<long long>(ceil_div<long long>(n_part, 256), 8LL * sm_count()));
+  pred_partial_init_kernel<<<ig, 256, 0, st>>>(part, n_part);
+  return cudaGetLastError();
+}
+cudaError_t pred_partial_finalize(const float4* part, int rows, int slots, float* out, cudaStream_t st) {
+  pred_partial_finalize_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(part, rows, slots, out);
+  return cudaGetLastError();
 }
 
 }  // namespace ynet
@@ -414,13 +341,12 @@ int ynet_tc_conv1x1_softargmax(const ynet_tc_src* srcs, int32_t n_src, int32_t N
   }
   cudaStream_t st = as_stream(stream);
   const long long n_part = (long long)N * C_out * pl.slots;
-  const unsigned ig = (unsigned)tmax<long long>(1, tmin<long long>(ceil_div<long long>(n_part, 256), 8LL * sm_count()));
-  pred_partial_init_kernel<<<ig, 256, 0, st>>>(p.partial, n_part);
-  YNET_LAUNCH_CHECK();
+  cudaError_t le = pred_partial_init(p.partial, n_part, st);
+  if (le != cudaSuccess) return cuda_fail(le, "ynet_tc_conv1x1_softargmax");
   tc_pred_softargmax_kernel<<<pl.grid, PR_THREADS, smem_bytes, st>>>(map, p);
   YNET_LAUNCH_CHECK();
-  pred_partial_finalize_kernel<<<ceil_div(N * C_out, 8), 256, 0, st>>>(p.partial, N * C_out, pl.slots, out);
-  YNET_LAUNCH_CHECK();
+  le = pred_partial_finalize(p.partial, N * C_out, pl.slots, out, st);
+  if (le != cudaSuccess) return cuda_fail(le, "ynet_tc_conv1x1_softargmax");
   return YNET_OK;
 }
 

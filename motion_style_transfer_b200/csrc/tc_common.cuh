@@ -40,6 +40,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
   }
 }
+// Whole-warp wait with uniform control flow afterwards: one lane spins, the warp reconverges on __syncwarp().  Used by
+// the MMA-issuing warp so that ptxas keeps the descriptor arithmetic on the uniform datapath.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity, nullptr);
+  __syncwarp();
+}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
   asm volatile(
@@ -73,6 +79,26 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uin
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Variants for a warp that runs the issue loop with all 32 lanes (uniform control flow) and elects one lane per
+// instruction.  Measured on B200: good for a loop with a few large MMAs per tile (pred_tc.cu: 0.90 -> 0.63 ms), bad
+// for the conv kernels' 36+ small MMAs per tile (2.6 -> 11.6 ms): those issue from `if (lane == 0)`.
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = sm_100)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -101,5 +127,109 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn tc_get_encode();   // cuTensorMapEncodeTiled through the runtime's driver entry point (conv_tc.cu)
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ---- predictor + soft-argmax building blocks shared by pred_tc.cu and the fused conv + predictor kernel ----------
+constexpr int PR_TH = 16;            // tile rows
+constexpr int PR_J = 2;              // 8-pixel column blocks per tile: tile = 16 x 16 pixels = ONE N = 256 accumulator
+constexpr int PR_TW = 8 * PR_J;
+constexpr int PR_EPI_WARPS = 16;           // one tile row (16 pixels) per warp
+constexpr int PR_WBLK_BYTES = 2 * 128 * 16;              // weights of one K block: [chunk][128 rows][8 ch]
+constexpr int PR_MAX_KB = 8;
+constexpr float PR_NEG = -3.402823466e+38f;
+
+struct PredPlan {
+  int tiles_x, tiles_y, grid, slots;
+  long long total_tiles, tiles_per_cta;
+};
+PredPlan pred_plan(int N, int H, int W);
+cudaError_t pred_partial_init(float4* part, long long n_part, cudaStream_t st);
+cudaError_t pred_partial_finalize(const float4* part, int rows, int slots, float* out, cudaStream_t st);
+
+// Online soft-argmax state of ONE channel (softargmax.py:67-81): running max, sum e, sum e x, sum e y.
+struct SoftState {
+  float m, s, sx, sy;
+};
+
+// One tile row of 16 logits (raw accumulators a[i], logit = a[i] + bias) at pixels (x0 + i, y): the lean interior path
+// (~5 instructions per pixel: FFMA, MUFU.EX2 and three accumulations on four independent chains).
+__device__ __forceinline__ void softargmax_row16(SoftState& st, const uint32_t (&v)[16], float bias, int x0, int y) {
+  constexpr float LOG2E = 1.4426950408889634f;
+  float mx = __uint_as_float(v[0]);
+#pragma unroll
+  for (int i = 1; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+  mx += bias;
+  if (mx > st.m) {     // rare after the first tiles of an image
+    const float sc = (st.m == PR_NEG) ? 0.f : __expf(st.m - mx);
+    st.s *= sc;
+    st.sx *= sc;
+    st.sy *= sc;
+    st.m = mx;
+  }
+  const float k = (bias - st.m) * LOG2E;       // e = 2^(a log2e + (bias - m) log2e) = exp(a + bias - m)
+  float ex[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) ex[i] = ex2_approx(fmaf(__uint_as_float(v[i]), LOG2E, k));
+  float s0 = ex[0] + ex[1], s1 = ex[4] + ex[5], s2 = ex[8] + ex[9], s3 = ex[12] + ex[13];
+  float x0s = ex[1], x1s = ex[4] * 4.f, x2s = ex[8] * 8.f, x3s = ex[12] * 12.f;
+  s0 += ex[2];  s1 += ex[6];  s2 += ex[10];  s3 += ex[14];
+  x0s = fmaf(ex[2], 2.f, x0s);   x1s = fmaf(ex[5], 5.f, x1s);   x2s = fmaf(ex[9], 9.f, x2s);   x3s = fmaf(ex[13], 13.f, x3s);
+  s0 += ex[3];  s1 += ex[7];  s2 += ex[11];  s3 += ex[15];
+  x0s = fmaf(ex[3], 3.f, x0s);   x1s = fmaf(ex[6], 6.f, x1s);   x2s = fmaf(ex[10], 10.f, x2s); x3s = fmaf(ex[14], 14.f, x3s);
+  x1s = fmaf(ex[7], 7.f, x1s);   x2s = fmaf(ex[11], 11.f, x2s); x3s = fmaf(ex[15], 15.f, x3s);
+  const float se = (s0 + s1) + (s2 + s3);
+  const float sxl = (x0s + x1s) + (x2s + x3s);
+  st.s += se;
+  st.sx += fmaf((float)x0, se, sxl);
+  st.sy = fmaf((float)y, se, st.sy);
+}
+
+// The same for a row that crosses the right image border (pixels x0 + i >= W are masked).
+__device__ __forceinline__ void softargmax_row16_masked(SoftState& st, const uint32_t (&v)[16], float bias, int x0, int y,
+                                                        int W) {
+  float mx = PR_NEG;
+  unsigned okm = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool ok = x0 + i < W;
+    okm |= ok ? (1u << i) : 0u;
+    if (ok) mx = fmaxf(mx, __uint_as_float(v[i]) + bias);
+  }
+  if (okm == 0) return;
+  if (mx > st.m) {
+    const float sc = (st.m == PR_NEG) ? 0.f : __expf(st.m - mx);
+    st.s *= sc;
+    st.sx *= sc;
+    st.sy *= sc;
+    st.m = mx;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float ev = ((okm >> i) & 1u) ? __expf(__uint_as_float(v[i]) + bias - st.m) : 0.f;
+    st.s += ev;
+    st.sx = fmaf(ev, (float)(x0 + i), st.sx);
+    st.sy = fmaf(ev, (float)y, st.sy);
+  }
+}
+
+// Predictor weights [kb][2][n_pad][8] bf16 -> shared memory [kb][2][128][8] with the (<= 32) rows replicated into the
+// four 32-lane quadrants of the M = 128 operand (row r carries channel r % 32).
+__device__ __forceinline__ void pred_stage_weights(unsigned char* s_w, const unsigned char* wpacked, int kblocks, int n_pad,
+                                                   int tid, int nthreads) {
+  const uint4* g = reinterpret_cast<const uint4*>(wpacked);
+  uint4* s = reinterpret_cast<uint4*>(s_w);
+  const int total = kblocks * 2 * 128;
+  for (int e = tid; e < total; e += nthreads) {
+    const int r = e & 127, kc = e >> 7;          // kc = kb * 2 + chunk
+    const int ch = r & 31;
+    s[e] = (ch < n_pad) ? __ldg(g + (size_t)kc * n_pad + ch) : make_uint4(0, 0, 0, 0);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+}
 
 }  // namespace ynet

@@ -345,14 +345,33 @@ class YNetEngineTC(YNetEngine):
         packed, bias = self._hoist_params(module, key, layout)
         return ops.tc_conv3x3(srcs, packed, bias, module.weight.shape[0], True)
 
-    def _decoder_trunk_hoisted(self, decoder, key, partials, pyr_rev, c_feats):
+    # decoder.4.2 + predictor + soft-argmax in one kernel (tc_conv_pred_kernel).  Correct and tested, but measured SLOWER
+    # on B200 than the two separate launches (2.0 ms vs 1.10 + 0.69 ms per 240 images): with one 864-thread CTA per SM the
+    # tile loop is paced by the accumulator hand-offs instead of by the tensor pipe (25 % active).  Off by default.
+    fuse_predictor = os.environ.get('YNET_FUSE_PREDICTOR', '0') == '1'
+
+    def _conv_pred_softargmax(self, conv, key, x, predictor, pkey):
+        """conv (+ReLU) -> predictor -> SoftArgmax2D without writing the conv output (ynet.py:468-469 + 582-583)."""
+        packed, bias = self._tc_params(conv, key, [x.C])
+        ppacked, pbias = self._tc_params(predictor, pkey, [conv.weight.shape[0]])
+        return ops.tc_conv3x3_pred_softargmax([x], packed, bias, conv.weight.shape[0], True, ppacked, pbias,
+                                              predictor.weight.shape[0])
+
+    def _decoder_trunk_hoisted(self, decoder, key, partials, pyr_rev, c_feats, softargmax=False):
         x = self._tconv_hoisted(decoder.center[0], f'{key}.center.0', None, partials[0], pyr_rev[0], c_feats[0])
         x = self._tconv(decoder.center[2], f'{key}.center.2', [x], True)
         for i in range(len(partials) - 1):
             up = self._tupconv(decoder.upsample_conv[i], f'{key}.upsample_conv.{i}', [x])
             x = self._tconv_hoisted(decoder.decoder[i][0], f'{key}.decoder.{i}.0', up, partials[i + 1], pyr_rev[i + 1],
                                     c_feats[i + 1])
+            last = i == len(partials) - 2
+            if last and softargmax and self.fuse_predictor and decoder.decoder[i][2].weight.shape[0] <= 64:
+                return self._conv_pred_softargmax(decoder.decoder[i][2], f'{key}.decoder.{i}.2', x, decoder.predictor,
+                                                  f'{key}.predictor')
             x = self._tconv(decoder.decoder[i][2], f'{key}.decoder.{i}.2', [x], True)
+        if softargmax:
+            packed, bias = self._tc_params(decoder.predictor, f'{key}.predictor', [x.C])
+            return ops.tc_conv1x1_softargmax(x, packed, bias, decoder.predictor.weight.shape[0])
         return x
 
     def decode_trajectories(self, feats, waypoint_samples, template, H, W, max_passes=256):
@@ -379,10 +398,8 @@ class YNetEngineTC(YNetEngine):
             if self.hoist:
                 feats_rev = [[c.batch_slice(b0, b1) for c in f] for f in feats][::-1]
                 partials = [q.repeat_interleave(G) for q in self._traj_partials(dec, 'traj_decoder', feats_rev)]
-                x = self._decoder_trunk_hoisted(dec, 'traj_decoder', partials, pyr[::-1],
-                                                [sum(c.C for c in f) for f in feats_rev])
-                packed, bias = self._tc_params(dec.predictor, 'traj_decoder.predictor', [x.C])
-                out = ops.tc_conv1x1_softargmax(x, packed, bias, pred_len)
+                out = self._decoder_trunk_hoisted(dec, 'traj_decoder', partials, pyr[::-1],
+                                                  [sum(c.C for c in f) for f in feats_rev], softargmax=True)
             else:
                 traj_input = [ChannelCat(tuple(c.batch_slice(b0, b1).repeat_interleave(G) for c in f) + (p,))
                               for f, p in zip(feats, pyr)]

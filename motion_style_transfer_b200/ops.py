@@ -771,6 +771,34 @@ def tc_conv3x3(sources, packed_weight, bias_pad, C_out, relu):
     return C8(out, C_out)
 
 
+def tc_conv3x3_pred_softargmax(sources, packed_weight, bias_pad, C_out, relu, packed_pred, pred_bias_pad, C_pred):
+    """conv3x3(+bias, +ReLU) -> 1x1 predictor -> SoftArgmax2D in one kernel: C8 sources -> (N, C_pred, 2)."""
+    N = max(s.N for s in sources)
+    H, W = sources[0].H, sources[0].W
+    arr = (_lib.TcSrc * len(sources))()
+    for i, s in enumerate(sources):
+        if s.H != H or s.W != W:
+            raise ValueError('tc_conv3x3_pred_softargmax: sources must share the spatial size')
+        arr[i].ptr = s.data.data_ptr()
+        arr[i].channels_pad = s.K_pad
+        arr[i].chunks_stored = s.C_pad // 8
+        arr[i].batch_stride = 0 if (s.N == 1 and N > 1) else s.data.stride(0)
+        arr[i].batch_mod = _tc_batch_mod(s, N)
+        arr[i].center_only = 1 if s.center else 0
+    out = torch.empty(N, C_pred, 2, dtype=torch.float32, device=sources[0].data.device)
+    nb = _L().ynet_tc_conv1x1_softargmax_workspace_bytes(N, C_pred, H, W)
+    ws = _workspace(nb, out.device, 'tc_softargmax')
+    cin_pad = sum(s.K_pad for s in sources)
+    flops = 2.0 * (9 * sum(s.C for s in sources if not s.center) * C_out + C_out * C_pred) * H * W * N
+    with _timed('tc_conv_pred_kernel', flops, 2.0 * cin_pad * H * W * N, tag=f'{cin_pad}->{_pad16(C_out)}->{C_pred}@{H}x{W} N={N}'):
+        check(_L().ynet_tc_conv3x3_pred_softargmax(arr, len(sources), N, H, W, _ptr(packed_weight), _ptr(bias_pad), C_out,
+                                                   1 if relu else 0, _ptr(packed_pred), _ptr(pred_bias_pad), C_pred,
+                                                   _ptr(out), _ptr(ws), ws.numel(), _stream()),
+              'tc_conv3x3_pred_softargmax')
+    _count(3)
+    return out
+
+
 def tc_conv3x3_hilo(sources, packed_weight, C_out, with_lo=True):
     """Raw 3x3 partial sums (no bias / ReLU) of C8 sources as a bf16 (hi | lo) pair: C8 with 2 * pad16(C_out)
     channels, flagged ``center`` so that a later tc_conv3x3 adds it through identity weights (goal-loop hoisting)."""

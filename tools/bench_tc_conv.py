@@ -83,3 +83,23 @@ if os.environ.get('PRED', '1') != '0':
         ms = e0.elapsed_time(e1) / 10
         by = 2.0 * a.C_pad * H * W * N
         print(f'pred+softargmax {cin} -> {cout} @{H}  {ms:8.3f} ms  {by / ms / 1e6:7.1f} GB/s')
+
+if os.environ.get('FUSED', '1') != '0':
+    cin = cmid = 32
+    cout, H, W = 30, 416, 416
+    a = ops.tc_pack(torch.relu(torch.randn(N, cin, H, W, device='cuda')))
+    w = torch.randn(cmid, cin, 3, 3, device='cuda') * 0.1
+    packed = ops.tc_pack_weights(w, [cin])
+    bias = torch.zeros(32, device='cuda')
+    ppacked = ops.tc_pack_weights(torch.randn(cout, cmid, 1, 1, device='cuda') * 0.5, [cmid])
+    pbias = torch.zeros(32, device='cuda')
+    for _ in range(5):
+        ops.tc_conv3x3_pred_softargmax([a], packed, bias, cmid, True, ppacked, pbias, cout)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ops.tc_conv3x3_pred_softargmax([a], packed, bias, cmid, True, ppacked, pbias, cout)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f'fused conv {cin}->{cmid} + pred {cout} + softargmax @{H}  {e0.elapsed_time(e1) / 10:8.3f} ms')
