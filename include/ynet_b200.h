@@ -215,6 +215,9 @@ typedef struct ynet_tc_src {
                            and its K blocks hold ONE tap in the packed weights (pack it with ksize 1) */
   int32_t chunks_stored; /* 0 = channels_pad / 8; else the number of 8-channel planes the tensor really holds
                            (< channels_pad / 8): the missing planes read as zero (TMA out-of-bounds fill) */
+  int32_t padded;       /* 1: planes are (H + 2) x (W + 2) with a one-pixel REPLICATED ring around the H x W image
+                           (ynet_tc_pad_replicate, or a conv's padded output): input of ynet_tc_upconv3x3 only */
+  int32_t reserved;
 } ynet_tc_src;
 
 int ynet_tc_supported(void);
@@ -253,7 +256,12 @@ int ynet_tc_predictor_f32(const void* x_c8, int32_t N, int32_t C_pad, int32_t C_
  *     counts); out_c8: (N, cp/8, 2h, 2w, 8).  `border_weight` (ynet_tc_upconv_border_weights of the original
  *     float32 weight; ynet_tc_upconv_border_weight_bytes bytes) and the original `bias` are used to recompute the
  *     one-pixel border ring exactly (index clamping and zero padding do not commute with the stencil).
- *     C_out <= 64; relu must be 0. */
+ *     When the sources are `padded` (replicated one-pixel ring) the stencil is exact up to the conv's zero padding
+ *     and only the outermost high-resolution ring is corrected (3-5 taps per pixel instead of 9 on a 2-pixel ring).
+ *     C_out <= 64; relu must be 0.
+ *   ynet_tc_pad_replicate: (N, C_pad/8, H, W, 8) -> (N, C_pad/8, H+2, W+2, 8); ynet_tc_conv3x3 writes the same layout
+ *     directly when bit 1 of `relu` is set (relu: bit 0 = ReLU, bit 1 = padded output). */
+int ynet_tc_pad_replicate(const void* x_c8, int32_t N, int32_t C_pad, int32_t H, int32_t W, void* out_c8, void* stream);
 int64_t ynet_tc_upconv_border_weight_bytes(int32_t C_out, int32_t n_src, const int32_t* src_channels_host);
 int ynet_tc_upconv_border_weights(const float* weight, int32_t C_out, int32_t n_src, const int32_t* src_channels_host,
                                   float* out, void* stream);

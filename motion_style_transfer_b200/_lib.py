@@ -23,7 +23,8 @@ class ConvSrc(Structure):
 
 class TcSrc(Structure):
     _fields_ = [('ptr', c_void_p), ('channels_pad', c_int32), ('batch_mod', c_int32), ('batch_stride', c_int64),
-                ('center_only', c_int32), ('chunks_stored', c_int32)]
+                ('center_only', c_int32), ('chunks_stored', c_int32),
+                ('padded', c_int32), ('reserved', c_int32)]
 
 
 class YnetError(RuntimeError):
@@ -87,6 +88,7 @@ _PROTOS = {
     'ynet_tc_upconv3x3': (c_int, [POINTER(TcSrc), POINTER(c_int32), _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _I, _P]),
     'ynet_tc_conv3x3': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _I, _P]),
     'ynet_tc_conv3x3_pred_softargmax': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P, _L, _P]),
+    'ynet_tc_pad_replicate': (c_int, [_P, _I, _I, _I, _I, _P, _P]),
     'ynet_tc_conv3x3_hilo': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P]),
     'ynet_bce_workspace_bytes': (_L, [_L]),
     'ynet_bce_logits_fwd_bwd': (c_int, [_P, _P, _L, _F, _P, _P, _P, _L, _P]),

@@ -35,6 +35,8 @@ struct TcSrcDev {
   int bcast;        // source has batch 1
   int batch_mod;    // > 0: image n reads n % batch_mod; < 0: image n reads n / -batch_mod
   int center;       // 1: only the centre tap is applied to this source (hoisted partial sums, one-tap weights)
+  int off;          // 1: the tensor carries a one-pixel replicate-padded ring (dims H + 2, W + 2): shift the TMA box
+  int pad_[3];
 };
 constexpr int TC_MAX_KB = 32;
 
@@ -45,6 +47,7 @@ struct TcParams {
   long long total_tiles;
   int kb_total;           // sum of kblocks
   int with_lo;            // EPI_HILO: also write the low halves
+  int pad_out;            // EPI_C8: write (H + 2, W + 2) planes with a replicated one-pixel ring (input of an upconv)
   uint32_t center_mask;   // bit kb: K block kb belongs to a centre-tap-only source
   int w_total;            // bytes of the packed weights
   int wofs[TC_MAX_KB];    // byte offset of K block kb in the packed weights (9-tap and 1-tap blocks are mixed)
@@ -143,7 +146,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             const uint32_t fb = smem_u32(&full_bar[stage]);
             const uint32_t wb = ((p.center_mask >> kb) & 1u) ? (uint32_t)(wblk_bytes / TAPS) : (uint32_t)wblk_bytes;
             mbar_expect_tx(fb, p.a_bytes + (p.resident ? 0u : wb));
-            tma_load_4d(smem_u32(st), map, fb, 8 * (x0 - HALO), y0 - HALO, 2 * b, ns);
+            tma_load_4d(smem_u32(st), map, fb, 8 * (x0 - HALO + p.src[s].off), y0 - HALO + p.src[s].off, 2 * b, ns);
             if (!p.resident) bulk_load(smem_u32(st + p.a_bytes), p.wpacked + p.wofs[kb], wb, fb);
             if (++stage == p.stages) {
               stage = 0;
@@ -247,6 +250,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           }
           if (EPI == EPI_C8) {
             if (inb) {
+              const int po = p.pad_out;
+              const int Hp = p.H + 2 * po, Wp = p.W + 2 * po;
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const int chunk = (c0 >> 3) + h;
@@ -255,8 +260,25 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
                 o.y = pack_bf16(f[8 * h + 2], f[8 * h + 3]);
                 o.z = pack_bf16(f[8 * h + 4], f[8 * h + 5]);
                 o.w = pack_bf16(f[8 * h + 6], f[8 * h + 7]);
-                __nv_bfloat16* dst = p.out + ((((size_t)n * n_chunks + chunk) * p.H + y) * p.W + x) * 8;
-                *reinterpret_cast<uint4*>(dst) = o;
+                uint4* dst = reinterpret_cast<uint4*>(p.out) + (((size_t)n * n_chunks + chunk) * Hp + (y + po)) * Wp + (x + po);
+                *dst = o;
+                if (po) {
+                  // replicate the border pixels into the ring (the bilinear index clamping of the consumer)
+                  const int dyv = (y == 0) ? -1 : ((y == p.H - 1) ? 1 : 0);
+                  const int dxv = (x == 0) ? -1 : ((x == p.W - 1) ? 1 : 0);
+                  if (dyv != 0) dst[dyv * Wp] = o;
+                  if (dxv != 0) dst[dxv] = o;
+                  if (dyv != 0 && dxv != 0) dst[dyv * Wp + dxv] = o;
+                  if (p.H == 1 && y == 0) {      // a one-row image is both borders
+                    dst[Wp] = o;
+                    if (dxv != 0) dst[Wp + dxv] = o;
+                  }
+                  if (p.W == 1 && x == 0) {
+                    dst[1] = o;
+                    if (dyv != 0) dst[dyv * Wp + 1] = o;
+                    if (p.H == 1) dst[Wp + 1] = o;
+                  }
+                }
               }
             }
           } else if (EPI == EPI_UP2) {
@@ -757,6 +779,19 @@ c8_upsample_kernel(const uint4* __restrict__ x, long long planes, int H, int W, 
   }
 }
 
+// one-pixel replicate padding of C8 planes: (planes, H, W) -> (planes, H + 2, W + 2)
+__global__ void __launch_bounds__(256)
+c8_pad_replicate_kernel(const uint4* __restrict__ x, long long planes, int H, int W, uint4* __restrict__ out) {
+  const int Hp = H + 2, Wp = W + 2;
+  const long long total = planes * Hp * Wp;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long pl = t / ((long long)Hp * Wp);
+    const int r = (int)(t - pl * Hp * Wp);
+    const int y = min(max(r / Wp - 1, 0), H - 1), xx = min(max(r % Wp - 1, 0), W - 1);
+    out[t] = __ldg(x + (pl * H + y) * W + xx);
+  }
+}
+
 // weights OIHW f32 -> [kb][tap][2][n_pad][8] bf16 over the concatenated, per-source padded input channels
 struct PackSrc {
   int real[YNET_MAX_SOURCES], pad[YNET_MAX_SOURCES];
@@ -1025,6 +1060,99 @@ upconv_border_kernel(UpBorderSrc src, int N, int h, int w, const float* __restri
   }
 }
 
+// ---- exact border of the phase-decomposed upconv on a REPLICATE-PADDED low-resolution input ----------------------
+// With the one-pixel replicated ring the low-resolution stencil reproduces the bilinear index clamping everywhere; what
+// remains is the conv's ZERO padding: the stencil behaves as if the upsampled image continued (clamped) outside
+// [0, 2h) x [0, 2w).  Only the outermost high-resolution ring is affected, by exactly the taps that fall outside:
+//   out[v, u] -= sum_{(dy, dx) outside} w[o, c, dy, dx] * U~[v + dy - 1, u + dx - 1][c],
+// U~[v', u'] = the bilinear value computed from the padded tensor without any clamping (valid for -1 <= v' <= 2h).
+// Three taps per edge pixel, five per corner, instead of the nine-tap recomputation of a two-pixel ring.
+template <int OG>
+__global__ void __launch_bounds__(UPB_THREADS, 2)
+upconv_ringfix_kernel(UpBorderSrc src, int N, int h, int w, const float* __restrict__ bw /* [g][cpad][9][OG] */,
+                      int cpad_total, __nv_bfloat16* __restrict__ out, int cp) {
+  extern __shared__ __align__(16) float s_wt[];   // [cpad_total][9][OG]
+  const int grp = blockIdx.y;
+  {
+    const float4* g4 = reinterpret_cast<const float4*>(bw + (size_t)grp * cpad_total * 9 * OG);
+    float4* s4 = reinterpret_cast<float4*>(s_wt);
+    for (int e = threadIdx.x; e < cpad_total * 9 * OG / 4; e += UPB_THREADS) s4[e] = __ldg(g4 + e);
+  }
+  __syncthreads();
+  const int H2 = 2 * h, W2 = 2 * w;
+  const int ring = (H2 >= 2 && W2 >= 2) ? 2 * W2 + 2 * (H2 - 2) : H2 * W2;
+  const int wp = w + 2;                          // padded low-resolution pitch
+  const long long total = (long long)N * ring;
+  for (long long t = (long long)blockIdx.x * UPB_THREADS + threadIdx.x; t < total; t += (long long)gridDim.x * UPB_THREADS) {
+    const int n = (int)(t / ring);
+    int r = (int)(t - (long long)n * ring);
+    int v, u;
+    if (r < W2) {
+      v = 0;
+      u = r;
+    } else if (r < 2 * W2) {
+      v = H2 - 1;
+      u = r - W2;
+    } else {
+      r -= 2 * W2;
+      v = 1 + (r >> 1);
+      u = (r & 1) ? W2 - 1 : 0;
+    }
+    float acc[OG];
+#pragma unroll
+    for (int o = 0; o < OG; ++o) acc[o] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int vv = v + tap / 3 - 1, uu = u + tap % 3 - 1;
+      if (vv >= 0 && vv < H2 && uu >= 0 && uu < W2) continue;      // inside taps are already exact
+      // U~[vv, uu] from the padded tensor: vv = 2k + a (floor division, k may be -1 or h)
+      const int kv = (vv + 2) / 2 - 1, av = (vv + 2) & 1;
+      const int ku = (uu + 2) / 2 - 1, au = (uu + 2) & 1;
+      const int r0 = kv + av;                     // padded rows r0, r0 + 1
+      const int c0 = ku + au;
+      const float fy0 = av ? 0.75f : 0.25f, fy1 = 1.f - fy0;
+      const float fx0 = au ? 0.75f : 0.25f, fx1 = 1.f - fx0;
+      int cpad = 0;
+      for (int s = 0; s < src.n_src; ++s) {
+        const int bm = src.batch_mod[s];
+        const int ns = (src.batch_stride[s] == 0) ? 0 : (bm > 0 ? n % bm : (bm < 0 ? n / (-bm) : n));
+        const uint4* xs = src.ptr[s] + (size_t)ns * src.batch_stride[s];
+        for (int ch = 0; ch < src.real_chunks[s]; ++ch, cpad += 8) {
+          const uint4* xc = xs + (size_t)ch * (h + 2) * wp + (size_t)r0 * wp + c0;
+          float a[8], b[8], c[8], d[8], uv[8];
+          unpack8(__ldg(xc), a);
+          unpack8(__ldg(xc + 1), b);
+          unpack8(__ldg(xc + wp), c);
+          unpack8(__ldg(xc + wp + 1), d);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) uv[k] = fy0 * (fx0 * a[k] + fx1 * b[k]) + fy1 * (fx0 * c[k] + fx1 * d[k]);
+          const float* wq = s_wt + ((size_t)cpad * 9 + tap) * OG;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float4* wv = reinterpret_cast<const float4*>(wq + (size_t)k * 9 * OG);
+#pragma unroll
+            for (int o4 = 0; o4 < OG / 4; ++o4) {
+              const float4 ww = wv[o4];
+              acc[4 * o4 + 0] = fmaf(uv[k], ww.x, acc[4 * o4 + 0]);
+              acc[4 * o4 + 1] = fmaf(uv[k], ww.y, acc[4 * o4 + 1]);
+              acc[4 * o4 + 2] = fmaf(uv[k], ww.z, acc[4 * o4 + 2]);
+              acc[4 * o4 + 3] = fmaf(uv[k], ww.w, acc[4 * o4 + 3]);
+            }
+          }
+        }
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out) + (((size_t)n * (cp >> 3) + grp * (OG / 8)) * H2 + v) * (size_t)W2 + u;
+#pragma unroll
+    for (int q = 0; q < OG / 8; ++q) {
+      float cur[8];
+      unpack8(dst[(size_t)q * H2 * W2], cur);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cur[k] -= acc[8 * q + k];
+      dst[(size_t)q * H2 * W2] = pack8(cur);
+    }
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 EncodeTiledFn tc_get_encode() {
   static EncodeTiledFn fn = nullptr;
@@ -1086,6 +1214,17 @@ int ynet_tc_maxpool2x2(const void* x_c8, int32_t N, int32_t C_pad, int32_t H, in
   YNET_CHECK_ARG(x_c8 && out_c8, "null pointer");
   const long long planes = (long long)N * (C_pad / 8);
   c8_maxpool_kernel<<<grid_1d(planes * (H / 2) * (W / 2)), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(x_c8), planes, H, W, reinterpret_cast<uint4*>(out_c8));
+  YNET_LAUNCH_CHECK();
+  return YNET_OK;
+}
+
+int ynet_tc_pad_replicate(const void* x_c8, int32_t N, int32_t C_pad, int32_t H, int32_t W, void* out_c8, void* stream) {
+  YNET_CHECK_ARG(N >= 0 && C_pad % 8 == 0 && H >= 1 && W >= 1, "bad shape");
+  if (N == 0) return YNET_OK;
+  YNET_CHECK_ARG(x_c8 && out_c8, "null pointer");
+  const long long planes = (long long)N * (C_pad / 8);
+  c8_pad_replicate_kernel<<<grid_1d(planes * (long long)(H + 2) * (W + 2)), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const uint4*>(x_c8), planes, H, W, reinterpret_cast<uint4*>(out_c8));
   YNET_LAUNCH_CHECK();
   return YNET_OK;
@@ -1243,13 +1382,15 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
       set_error("%s: source %d stores more planes than channels_pad / 8", who, i);
       return YNET_E_INVALID;
     }
-    const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)stored, (cuuint64_t)nsrc};
-    const cuuint64_t bs = bcast ? (cuuint64_t)stored * H * W * 16 : (cuuint64_t)srcs[i].batch_stride * 2;
+    const int po = srcs[i].padded ? 1 : 0;       // tensor dims (H + 2, W + 2): replicate-padded ring
+    const cuuint64_t Hs = (cuuint64_t)H + 2 * po, Ws = (cuuint64_t)W + 2 * po;
+    const cuuint64_t dims[4] = {Ws * 8, Hs, (cuuint64_t)stored, (cuuint64_t)nsrc};
+    const cuuint64_t bs = bcast ? (cuuint64_t)stored * Hs * Ws * 16 : (cuuint64_t)srcs[i].batch_stride * 2;
     if (bs % 16 != 0) {
       set_error("%s: batch stride must be a multiple of 8 elements", who);
       return YNET_E_ALIGN;
     }
-    const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, bs};
+    const cuuint64_t strides[3] = {Ws * 16, Hs * Ws * 16, bs};
     const cuuint32_t box[4] = {(cuuint32_t)p.bw * 8, (cuuint32_t)bh, 2, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(srcs[i].ptr), dims, strides, box,
@@ -1263,6 +1404,7 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
     p.src[i].bcast = bcast ? 1 : 0;
     p.src[i].batch_mod = srcs[i].batch_mod;
     p.src[i].center = (taps == 9 && srcs[i].center_only) ? 1 : 0;
+    p.src[i].off = po;
     if (kb_total + cp / 16 > TC_MAX_KB) {
       set_error("%s: more than %d input K blocks", who, TC_MAX_KB);
       return YNET_E_UNSUPPORTED;
@@ -1282,7 +1424,8 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
   p.W = W;
   p.n_pad = C_out_pad;
   p.c_out = C_out;
-  p.relu = (epi == EPI_HILO) ? 0 : relu;
+  p.relu = (epi == EPI_HILO) ? 0 : (relu & 1);
+  p.pad_out = (epi == EPI_C8 && (relu & 2)) ? 1 : 0;
   p.with_lo = (epi == EPI_HILO && relu == 2) ? 1 : 0;
   p.tiles_x = ceil_div(W, 8 * p.j);
   p.tiles_y = ceil_div(H, TC_TH);
@@ -1523,8 +1666,32 @@ int ynet_tc_upconv3x3(const ynet_tc_src* srcs, const int32_t* src_channels_host,
     cudaError_t e = cudaFuncSetAttribute(upconv_border_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(upconv_border_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(upconv_ringfix_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(upconv_ringfix_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "ynet_tc_upconv3x3(cudaFuncSetAttribute)");
     configured = true;
+  }
+  int n_padded = 0;
+  for (int i = 0; i < n_src; ++i) n_padded += srcs[i].padded ? 1 : 0;
+  YNET_CHECK_ARG(n_padded == 0 || n_padded == n_src, "either all or none of the sources carry the replicate-padded ring");
+  if (n_padded == n_src) {
+    // replicate-padded inputs: the tensor-core result is exact except for the zero padding of the outermost ring
+    const int ring_hi = 2 * (2 * w) + 2 * (2 * h - 2);
+    const long long total_hi = (long long)N * ring_hi;
+    const int groups_hi = cp / og;
+    const int per_sm_hi = smem > 100 * 1024 ? 1 : (smem > 64 * 1024 ? 2 : 3);
+    const unsigned gxh = (unsigned)tmax<long long>(
+        1, tmin<long long>(ceil_div<long long>(total_hi, UPB_THREADS), (long long)ceil_div(per_sm_hi * sm_count(), groups_hi)));
+    dim3 gridh(gxh, groups_hi);
+    __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(out_c8);
+    if (og == 16)
+      upconv_ringfix_kernel<16><<<gridh, UPB_THREADS, smem, as_stream(stream)>>>(bs, N, h, w, border_weight, cpad, outh, cp);
+    else
+      upconv_ringfix_kernel<32><<<gridh, UPB_THREADS, smem, as_stream(stream)>>>(bs, N, h, w, border_weight, cpad, outh, cp);
+    YNET_LAUNCH_CHECK();
+    return YNET_OK;
   }
   const int ring = (h >= 2 && w >= 2) ? 2 * w + 2 * (h - 2) : h * w;
   const long long total = (long long)N * ring * 4;

@@ -182,7 +182,7 @@ class YNetEngineTC(YNetEngine):
     bf16 and writes float32 logits so that sigmoid / sampling / soft-argmax stay in fp32.
     """
 
-    upconv_max_cout = 16
+    upconv_max_cout = int(os.environ.get('YNET_UPCONV_MAX_COUT', '64'))
 
     def __init__(self, model):
         super().__init__(model, backend='bf16')
@@ -230,18 +230,25 @@ class YNetEngineTC(YNetEngine):
 
     def _tupconv(self, module, key, sources):
         """bilinear x2 + upsample_conv (ynet.py:463-464) in one launch on the low-resolution sources."""
-        # Measured on B200 (tools/bench_tc_conv.py, 240 images): the phase-decomposed form wins where the border ring
-        # is cheap (C_in * C_out small, i.e. the full-resolution upsample_conv.4: 0.88 ms vs 2.0 ms); at the deeper
-        # levels the CUDA-core ring recomputation costs more than the saved c8_upsample launch.
+        # Phase-decomposed at every level: the producing conv writes a replicate-padded tensor (the bilinear index
+        # clamping made explicit), so the low-resolution stencil is exact up to the conv's zero padding and only the
+        # outermost high-resolution ring needs a 3-5-tap CUDA-core correction.  (With zero-filled borders the ring was a
+        # 9-tap recomputation of two pixels, which cost more than the saved c8_upsample launch below 416^2.)
         if module.weight.shape[0] > self.upconv_max_cout:
-            up = [ops.tc_upsample(s) for s in sources]
+            up = [ops.tc_upsample(s) for s in sources]      # (accepts replicate-padded inputs: uses the interior)
             return self._tconv(module, key, up, False)
         packed, b_eff, bw, b = self._tc_up_params(module, key, [s.C for s in sources])
         return ops.tc_upconv3x3(sources, packed, b_eff, bw, b, module.weight.shape[0])
 
-    def _tconv(self, module, key, sources, relu):
+    def _tconv(self, module, key, sources, relu, pad_out=False):
         packed, bias = self._tc_params(module, key, [s.C for s in sources])
-        return ops.tc_conv3x3(sources, packed, bias, module.weight.shape[0], relu)
+        return ops.tc_conv3x3(sources, packed, bias, module.weight.shape[0], relu, pad_out)
+
+    def _feeds_upconv(self, decoder, i):
+        """Does the output of center.2 (i = -1) / decoder.i.2 feed an upsample_conv that runs phase-decomposed?  Then
+        the conv writes the replicate-padded layout directly (no separate padding pass)."""
+        nxt = i + 1
+        return nxt < len(decoder.upsample_conv) and decoder.upsample_conv[nxt].weight.shape[0] <= self.upconv_max_cout
 
     def _run_stages_tc(self, stages, key, cur):
         feats = []
@@ -271,11 +278,11 @@ class YNetEngineTC(YNetEngine):
     def decoder_trunk(self, decoder, key, features):
         feats = [self._c8_parts(f) for f in features][::-1]
         x = self._tconv(decoder.center[0], f'{key}.center.0', feats[0], True)
-        x = self._tconv(decoder.center[2], f'{key}.center.2', [x], True)
+        x = self._tconv(decoder.center[2], f'{key}.center.2', [x], True, self._feeds_upconv(decoder, -1))
         for i, skip in enumerate(feats[1:]):
             up = self._tupconv(decoder.upsample_conv[i], f'{key}.upsample_conv.{i}', [x])
             x = self._tconv(decoder.decoder[i][0], f'{key}.decoder.{i}.0', [up] + skip, True)
-            x = self._tconv(decoder.decoder[i][2], f'{key}.decoder.{i}.2', [x], True)
+            x = self._tconv(decoder.decoder[i][2], f'{key}.decoder.{i}.2', [x], True, self._feeds_upconv(decoder, i))
         return x
 
     def decoder_logits(self, decoder, key, features):
@@ -359,7 +366,7 @@ class YNetEngineTC(YNetEngine):
 
     def _decoder_trunk_hoisted(self, decoder, key, partials, pyr_rev, c_feats, softargmax=False):
         x = self._tconv_hoisted(decoder.center[0], f'{key}.center.0', None, partials[0], pyr_rev[0], c_feats[0])
-        x = self._tconv(decoder.center[2], f'{key}.center.2', [x], True)
+        x = self._tconv(decoder.center[2], f'{key}.center.2', [x], True, self._feeds_upconv(decoder, -1))
         for i in range(len(partials) - 1):
             up = self._tupconv(decoder.upsample_conv[i], f'{key}.upsample_conv.{i}', [x])
             x = self._tconv_hoisted(decoder.decoder[i][0], f'{key}.decoder.{i}.0', up, partials[i + 1], pyr_rev[i + 1],
@@ -368,7 +375,7 @@ class YNetEngineTC(YNetEngine):
             if last and softargmax and self.fuse_predictor and decoder.decoder[i][2].weight.shape[0] <= 64:
                 return self._conv_pred_softargmax(decoder.decoder[i][2], f'{key}.decoder.{i}.2', x, decoder.predictor,
                                                   f'{key}.predictor')
-            x = self._tconv(decoder.decoder[i][2], f'{key}.decoder.{i}.2', [x], True)
+            x = self._tconv(decoder.decoder[i][2], f'{key}.decoder.{i}.2', [x], True, self._feeds_upconv(decoder, i))
         if softargmax:
             packed, bias = self._tc_params(decoder.predictor, f'{key}.predictor', [x.C])
             return ops.tc_conv1x1_softargmax(x, packed, bias, decoder.predictor.weight.shape[0])

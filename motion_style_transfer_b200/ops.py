@@ -552,23 +552,30 @@ class C8:
     (agent-major stacking of the n_goal decoder passes; nothing is copied).
     """
 
-    __slots__ = ('data', 'C', 'rep', 'center')
+    __slots__ = ('data', 'C', 'rep', 'center', 'pad')
 
-    def __init__(self, data, C, rep=1, center=False):
+    def __init__(self, data, C, rep=1, center=False, pad=0):
         # center: hoisted partial sums (hi | lo); a conv applies identity weights on its centre tap only
-        self.data, self.C, self.rep, self.center = data, C, rep, center
+        # pad = 1: planes are (H + 2, W + 2) with a one-pixel replicated ring (input of tc_upconv3x3 only)
+        self.data, self.C, self.rep, self.center, self.pad = data, C, rep, center, pad
 
     @property
     def N(self):
         return self.data.shape[0] * self.rep
 
     def repeat_interleave(self, rep):
-        return C8(self.data, self.C, self.rep * rep, self.center)
+        return C8(self.data, self.C, self.rep * rep, self.center, self.pad)
 
     def batch_slice(self, b0, b1):
         if self.rep != 1:
             raise ValueError('batch_slice of a repeated C8')
-        return C8(self.data[b0:b1], self.C, 1, self.center)
+        return C8(self.data[b0:b1], self.C, 1, self.center, self.pad)
+
+    def unpadded(self):
+        """The H x W interior of a replicate-padded C8 as a plain (contiguous) C8."""
+        if not self.pad:
+            return self
+        return C8(self.data[:, :, 1:-1, 1:-1].contiguous(), self.C, self.rep, self.center, 0)
 
     @property
     def C_pad(self):
@@ -581,11 +588,11 @@ class C8:
 
     @property
     def H(self):
-        return self.data.shape[2]
+        return self.data.shape[2] - 2 * self.pad
 
     @property
     def W(self):
-        return self.data.shape[3]
+        return self.data.shape[3] - 2 * self.pad
 
 
 def _pad16(c):
@@ -654,7 +661,22 @@ def tc_rasterize_pyramid(template, coords, n_img, n_ch, H, W, n_levels, slot=0):
     return [C8(b, n_ch) for b in bufs]
 
 
+def tc_pad_replicate(a):
+    """One-pixel replicate padding of a C8 (the bilinear index clamping of tc_upconv3x3 made explicit)."""
+    if a.pad:
+        return a
+    if a.rep != 1:
+        raise ValueError('tc_pad_replicate of a repeated C8')
+    out = torch.empty(a.data.shape[0], a.C_pad // 8, a.H + 2, a.W + 2, 8, dtype=torch.bfloat16, device=a.data.device)
+    with _timed('c8_pad_replicate_kernel', 0, 4.0 * a.C_pad * a.data.shape[0] * a.H * a.W):
+        check(_L().ynet_tc_pad_replicate(_ptr(a.data), a.data.shape[0], a.C_pad, a.H, a.W, _ptr(out), _stream()),
+              'tc_pad_replicate')
+    _count()
+    return C8(out, a.C, 1, a.center, 1)
+
+
 def tc_unpack(a):
+    a = a.unpadded()
     out = torch.empty(a.N, a.C, a.H, a.W, dtype=torch.float32, device=a.data.device)
     check(_L().ynet_tc_unpack_c8_to_f32(_ptr(a.data), a.N, a.C, a.C_pad, a.H, a.W, _ptr(out), _stream()),
           'tc_unpack_c8_to_f32')
@@ -663,6 +685,7 @@ def tc_unpack(a):
 
 
 def tc_maxpool(a):
+    a = a.unpadded()
     out = torch.empty(a.N, a.C_pad // 8, a.H // 2, a.W // 2, 8, dtype=torch.bfloat16, device=a.data.device)
     with _timed('c8_maxpool_kernel', 0, 2.5 * a.C_pad * a.N * a.H * a.W):
         check(_L().ynet_tc_maxpool2x2(_ptr(a.data), a.N, a.C_pad, a.H, a.W, _ptr(out), _stream()), 'tc_maxpool2x2')
@@ -671,6 +694,7 @@ def tc_maxpool(a):
 
 
 def tc_upsample(a):
+    a = a.unpadded()
     out = torch.empty(a.N, a.C_pad // 8, a.H * 2, a.W * 2, 8, dtype=torch.bfloat16, device=a.data.device)
     with _timed('c8_upsample_kernel', 0, 10.0 * a.C_pad * a.N * a.H * a.W):
         check(_L().ynet_tc_upsample2x(_ptr(a.data), a.N, a.C_pad, a.H, a.W, _ptr(out), _stream()), 'tc_upsample2x')
@@ -741,8 +765,11 @@ def tc_conv1x1_softargmax(a, packed_weight, bias_pad, C_out):
     return out
 
 
-def tc_conv3x3(sources, packed_weight, bias_pad, C_out, relu):
-    """sources: list of C8 (batch N, 1 = broadcast, or a divisor of N = modulo).  Returns C8 (N, C_out)."""
+def tc_conv3x3(sources, packed_weight, bias_pad, C_out, relu, pad_out=False):
+    """sources: list of C8 (batch N, 1 = broadcast, or a divisor of N = modulo).  Returns C8 (N, C_out);
+    pad_out: write the replicate-padded (H + 2, W + 2) layout that tc_upconv3x3 consumes."""
+    if any(s.pad for s in sources):
+        raise ValueError('tc_conv3x3: replicate-padded C8 tensors are inputs of tc_upconv3x3 only')
     N = max(s.N for s in sources)
     H, W = sources[0].H, sources[0].W
     arr = (_lib.TcSrc * len(sources))()
@@ -756,10 +783,12 @@ def tc_conv3x3(sources, packed_weight, bias_pad, C_out, relu):
         arr[i].batch_mod = _tc_batch_mod(s, N)
         arr[i].center_only = 1 if s.center else 0
     cp = _pad16(C_out)
-    out = torch.empty(N, cp // 8, H, W, 8, dtype=torch.bfloat16, device=sources[0].data.device)
+    po = 1 if pad_out else 0
+    out = torch.empty(N, cp // 8, H + 2 * po, W + 2 * po, 8, dtype=torch.bfloat16, device=sources[0].data.device)
     cin_pad = sum(s.C_pad for s in sources)
-    args = (arr, len(sources), N, H, W, _ptr(packed_weight), _ptr(bias_pad), C_out, 1 if relu else 0, _ptr(out), cp)
-    key = (tuple(-s.K_pad if s.center else s.K_pad for s in sources), cp, H, W, min(N, 64))
+    args = (arr, len(sources), N, H, W, _ptr(packed_weight), _ptr(bias_pad), C_out, (1 if relu else 0) | (2 * po),
+            _ptr(out), cp)
+    key = (tuple(-s.K_pad if s.center else s.K_pad for s in sources), cp, H, W, min(N, 64), po)
     tune = _tc_tune.get(key)
     if tune is None:
         tune = _tc_autotune(key, args) if (tc_autotune_enabled and not torch.cuda.is_current_stream_capturing()) else 0
@@ -768,7 +797,7 @@ def tc_conv3x3(sources, packed_weight, bias_pad, C_out, relu):
                 2.0 * (cin_pad + cp) * H * W * N, tag=f'{cin_pad}{hoisted}->{cp}@{H}x{W} N={N}'):
         check(_L().ynet_tc_conv3x3(*args, tune, _stream()), 'tc_conv3x3')
     _count()
-    return C8(out, C_out)
+    return C8(out, C_out, 1, False, po)
 
 
 def tc_conv3x3_pred_softargmax(sources, packed_weight, bias_pad, C_out, relu, packed_pred, pred_bias_pad, C_pred):
@@ -882,9 +911,13 @@ def tc_upconv_border_weights(weight_oihw, src_channels):
     return out
 
 
-def tc_upconv3x3(sources, packed_phase_weight, bias_eff, border_weight, bias, C_out):
+def tc_upconv3x3(sources, packed_phase_weight, bias_eff, border_weight, bias, C_out, exact_ring=True):
     """bilinear x2 + conv3x3 (ynet.py:463-464) of low-resolution C8 sources -> C8 (N, C_out, 2h, 2w), without
     materialising the upsampled tensor."""
+    if exact_ring and all(s.rep == 1 for s in sources):
+        sources = [tc_pad_replicate(s) for s in sources]     # no-op for producers that already wrote the padded layout
+    else:
+        sources = [s.unpadded() for s in sources]
     N = max(s.N for s in sources)
     h, w = sources[0].H, sources[0].W
     arr = (_lib.TcSrc * len(sources))()
@@ -895,13 +928,14 @@ def tc_upconv3x3(sources, packed_phase_weight, bias_eff, border_weight, bias, C_
         arr[i].channels_pad = s.C_pad
         arr[i].batch_stride = 0 if (s.N == 1 and N > 1) else s.data.stride(0)
         arr[i].batch_mod = _tc_batch_mod(s, N)
+        arr[i].padded = s.pad
     real = (ctypes.c_int32 * len(sources))(*[s.C for s in sources])
     cp = _pad16(C_out)
     out = torch.empty(N, cp // 8, 2 * h, 2 * w, 8, dtype=torch.bfloat16, device=sources[0].data.device)
     cin_pad = sum(s.C_pad for s in sources)
     args = (arr, real, len(sources), N, h, w, _ptr(packed_phase_weight), _ptr(bias_eff), _ptr(border_weight), _ptr(bias),
             C_out, 0, _ptr(out))
-    key = ('up', tuple(s.C_pad for s in sources), cp, h, w, min(N, 64))
+    key = ('up', tuple(s.C_pad for s in sources), cp, h, w, min(N, 64), sources[0].pad)
     tune = _tc_tune.get(key)
     if tune is None:
         tune = (_tc_autotune(key, args, fn='ynet_tc_upconv3x3', n_pad=4 * cp)

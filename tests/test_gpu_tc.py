@@ -303,3 +303,38 @@ def test_tc_fused_conv_predictor_softargmax(ops, cin, cmid, cout, H, W, N):
     mid = bf16_exact(F.relu(F.conv2d(x, w, b, padding=1)))
     ref = O.softargmax2d(F.conv2d(mid, wp_, bp)).numpy()
     np.testing.assert_allclose(fused, ref, rtol=0, atol=3e-2)
+
+
+def test_tc_conv_padded_output_and_exact_upconv_ring(ops):
+    """A conv can write the replicate-padded layout directly; the phase-decomposed upconv on it equals
+    F.interpolate(bilinear x2) + conv3x3 including the border ring."""
+    torch.manual_seed(14)
+    N, cin, cmid, cout, h, w = 3, 16, 64, 32, 13, 26
+    x = bf16_exact(torch.randn(N, cin, h, w))
+    w1 = bf16_exact(torch.randn(cmid, cin, 3, 3) * 0.2)
+    b1 = torch.randn(cmid) * 0.1
+    a = ops.tc_pack(x.cuda())
+    packed = ops.tc_pack_weights(w1.cuda(), [cin])
+    bias = torch.zeros(cmid)
+    bias[:cmid] = b1
+    plain = ops.tc_conv3x3([a], packed, bias.cuda(), cmid, True)
+    padded = ops.tc_conv3x3([a], packed, bias.cuda(), cmid, True, pad_out=True)
+    assert padded.pad == 1 and padded.H == h and padded.data.shape[2] == h + 2
+    assert torch.equal(padded.data, ops.tc_pad_replicate(plain).data)
+    pl = plain.data.permute(0, 1, 4, 2, 3).float().reshape(N, -1, h, w)                 # (N, C_pad, h, w)
+    ref_pad = F.pad(pl, (1, 1, 1, 1), mode='replicate').reshape(N, -1, 8, h + 2, w + 2).permute(0, 1, 3, 4, 2)
+    assert torch.equal(padded.data, ref_pad.to(torch.bfloat16))
+    w2 = bf16_exact(torch.randn(cout, cmid, 3, 3) * 0.1).contiguous()
+    b2 = torch.randn(cout)
+    w_eff, b_eff = ops.tc_upconv_phase_weights(w2.cuda(), b2.cuda())
+    pk = ops.tc_pack_weights(w_eff, [cmid])
+    bw = ops.tc_upconv_border_weights(w2.cuda(), [cmid])
+    got = ops.tc_unpack(ops.tc_upconv3x3([padded], pk, b_eff, bw, b2.cuda(), cout)).cpu()
+    mid = ops.tc_unpack(plain).cpu()
+    ref = F.conv2d(F.interpolate(mid, scale_factor=2, mode='bilinear', align_corners=False), w2, b2, padding=1)
+    err = (got - ref).abs()
+    scale = ref.abs().max()
+    assert err.max() / scale < 1.2e-2
+    ring = torch.ones_like(err, dtype=torch.bool)
+    ring[:, :, 1:-1, 1:-1] = False
+    assert err[ring].max() / scale < 1.2e-2 and err[ring].mean() < 2 * err[~ring].mean() + 1e-3
