@@ -1498,9 +1498,12 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
     if (le != cudaSuccess) return cuda_fail(le, who);
     return YNET_OK;
   }
-  int ctas_per_sm = (smem_bytes <= 110 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
-  if (const char* e = getenv("YNET_TC_CTAS_PER_SM")) ctas_per_sm = tmax(1, tmin(2, atoi(e)));
-  if ((tune >> 4) & 0xF) ctas_per_sm = tmin(ctas_per_sm, tmax(1, (tune >> 4) & 0xF));
+  // co-resident CTAs per SM: every CTA brings its own MMA-issuing thread (a single thread needs ~45 cycles of
+  // descriptor set-up per small-N MMA), bounded by shared memory, the 512 TMEM columns and 2048 threads
+  const int fit = (int)tmin<size_t>(4, tmin<size_t>((size_t)(225 * 1024) / (smem_bytes + 1024), (size_t)(512 / p.tmem_cols)));
+  int ctas_per_sm = tmax(1, tmin(fit, 2));
+  if (const char* e = getenv("YNET_TC_CTAS_PER_SM")) ctas_per_sm = tmax(1, tmin(fit, atoi(e)));
+  if ((tune >> 4) & 0xF) ctas_per_sm = tmax(1, tmin(fit, (tune >> 4) & 0xF));
   long long grid = tmin<long long>(p.total_tiles, (long long)sm_count() * ctas_per_sm);
   if (grid_out != nullptr) {
     if (*grid_out > 0) grid = tmin<long long>(grid, *grid_out);   // caller sized its partial buffer for this many CTAs

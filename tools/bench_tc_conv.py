@@ -40,7 +40,8 @@ for cins, cout, H, W in SHAPES:
     fl = 2.0 * 9 * sum(cins) * cout * H * W * N
     cin_pad = sum((c + 15) // 16 * 16 for c in cins)
     by = 2.0 * (cin_pad + (cout + 15) // 16 * 16) * H * W * N
-    print(f'{str(cins):>14} -> {cout:3d} @{H:3d}  {ms:8.3f} ms  {fl / ms / 1e9:7.1f} TF/s  {by / ms / 1e6:7.1f} GB/s')
+    print(f'{str(cins):>14} -> {cout:3d} @{H:3d}  {ms:8.3f} ms  {fl / ms / 1e9:7.1f} TF/s  {by / ms / 1e6:7.1f} GB/s  tune={[hex(v) for v in ops._tc_tune.values()]}')
+    ops._tc_tune.clear()
 
 UP_SHAPES = [((32,), 16, 208, 208), ((64,), 32, 104, 104), ((64,), 32, 52, 52), ((64,), 32, 26, 26), ((128,), 64, 13, 13)]
 if os.environ.get('UP', '1') != '0':
