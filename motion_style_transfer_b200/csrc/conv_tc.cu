@@ -1067,6 +1067,8 @@ upconv_border_kernel(UpBorderSrc src, int N, int h, int w, const float* __restri
 //   out[v, u] -= sum_{(dy, dx) outside} w[o, c, dy, dx] * U~[v + dy - 1, u + dx - 1][c],
 // U~[v', u'] = the bilinear value computed from the padded tensor without any clamping (valid for -1 <= v' <= 2h).
 // Three taps per edge pixel, five per corner, instead of the nine-tap recomputation of a two-pixel ring.
+// One thread = TWO consecutive ring pixels x OG output channels: every weight vector read from shared memory feeds both
+// pixels, and the multiply-adds are packed fp32x2 (FFMA2) -- the kernel is instruction bound on the CUDA cores.
 template <int OG>
 __global__ void __launch_bounds__(UPB_THREADS, 2)
 upconv_ringfix_kernel(UpBorderSrc src, int N, int h, int w, const float* __restrict__ bw /* [g][cpad][9][OG] */,
@@ -1080,75 +1082,106 @@ upconv_ringfix_kernel(UpBorderSrc src, int N, int h, int w, const float* __restr
   }
   __syncthreads();
   const int H2 = 2 * h, W2 = 2 * w;
-  const int ring = (H2 >= 2 && W2 >= 2) ? 2 * W2 + 2 * (H2 - 2) : H2 * W2;
+  const int ring = 2 * W2 + 2 * (H2 - 2);        // even
   const int wp = w + 2;                          // padded low-resolution pitch
-  const long long total = (long long)N * ring;
+  const long long total = (long long)N * (ring / 2);
   for (long long t = (long long)blockIdx.x * UPB_THREADS + threadIdx.x; t < total; t += (long long)gridDim.x * UPB_THREADS) {
-    const int n = (int)(t / ring);
-    int r = (int)(t - (long long)n * ring);
-    int v, u;
-    if (r < W2) {
-      v = 0;
-      u = r;
-    } else if (r < 2 * W2) {
-      v = H2 - 1;
-      u = r - W2;
-    } else {
-      r -= 2 * W2;
-      v = 1 + (r >> 1);
-      u = (r & 1) ? W2 - 1 : 0;
-    }
-    float acc[OG];
+    const int n = (int)(t / (ring / 2));
+    const int r2 = 2 * (int)(t - (long long)n * (ring / 2));
+    int pv[2], pu[2];
 #pragma unroll
-    for (int o = 0; o < OG; ++o) acc[o] = 0.f;
+    for (int i = 0; i < 2; ++i) {
+      int r = r2 + i;
+      if (r < W2) {
+        pv[i] = 0;
+        pu[i] = r;
+      } else if (r < 2 * W2) {
+        pv[i] = H2 - 1;
+        pu[i] = r - W2;
+      } else {
+        r -= 2 * W2;
+        pv[i] = 1 + (r >> 1);
+        pu[i] = (r & 1) ? W2 - 1 : 0;
+      }
+    }
+    float2 acc[2][OG / 2];
+#pragma unroll
+    for (int o = 0; o < OG / 2; ++o) acc[0][o] = acc[1][o] = make_float2(0.f, 0.f);
     for (int tap = 0; tap < 9; ++tap) {
-      const int vv = v + tap / 3 - 1, uu = u + tap % 3 - 1;
-      if (vv >= 0 && vv < H2 && uu >= 0 && uu < W2) continue;      // inside taps are already exact
-      // U~[vv, uu] from the padded tensor: vv = 2k + a (floor division, k may be -1 or h)
-      const int kv = (vv + 2) / 2 - 1, av = (vv + 2) & 1;
-      const int ku = (uu + 2) / 2 - 1, au = (uu + 2) & 1;
-      const int r0 = kv + av;                     // padded rows r0, r0 + 1
-      const int c0 = ku + au;
-      const float fy0 = av ? 0.75f : 0.25f, fy1 = 1.f - fy0;
-      const float fx0 = au ? 0.75f : 0.25f, fx1 = 1.f - fx0;
+      bool need[2];
+      int r0[2], c0[2];
+      float fy0[2], fx0[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int vv = pv[i] + tap / 3 - 1, uu = pu[i] + tap % 3 - 1;
+        need[i] = !(vv >= 0 && vv < H2 && uu >= 0 && uu < W2);       // inside taps are already exact
+        // U~[vv, uu] from the padded tensor: vv = 2k + a (floor division, k may be -1 or h)
+        const int kv = (vv + 2) / 2 - 1, av = (vv + 2) & 1;
+        const int ku = (uu + 2) / 2 - 1, au = (uu + 2) & 1;
+        r0[i] = kv + av;                          // padded rows r0, r0 + 1
+        c0[i] = ku + au;
+        fy0[i] = av ? 0.75f : 0.25f;
+        fx0[i] = au ? 0.75f : 0.25f;
+      }
+      if (!need[0] && !need[1]) continue;
       int cpad = 0;
       for (int s = 0; s < src.n_src; ++s) {
         const int bm = src.batch_mod[s];
         const int ns = (src.batch_stride[s] == 0) ? 0 : (bm > 0 ? n % bm : (bm < 0 ? n / (-bm) : n));
         const uint4* xs = src.ptr[s] + (size_t)ns * src.batch_stride[s];
         for (int ch = 0; ch < src.real_chunks[s]; ++ch, cpad += 8) {
-          const uint4* xc = xs + (size_t)ch * (h + 2) * wp + (size_t)r0 * wp + c0;
-          float a[8], b[8], c[8], d[8], uv[8];
-          unpack8(__ldg(xc), a);
-          unpack8(__ldg(xc + 1), b);
-          unpack8(__ldg(xc + wp), c);
-          unpack8(__ldg(xc + wp + 1), d);
+          float uv[2][8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) uv[k] = fy0 * (fx0 * a[k] + fx1 * b[k]) + fy1 * (fx0 * c[k] + fx1 * d[k]);
+          for (int i = 0; i < 2; ++i) {
+            if (need[i]) {
+              const uint4* xc = xs + (size_t)ch * (h + 2) * wp + (size_t)r0[i] * wp + c0[i];
+              float a[8], b[8], c[8], d[8];
+              unpack8(__ldg(xc), a);
+              unpack8(__ldg(xc + 1), b);
+              unpack8(__ldg(xc + wp), c);
+              unpack8(__ldg(xc + wp + 1), d);
+              const float fy1 = 1.f - fy0[i], fx1 = 1.f - fx0[i];
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                uv[i][k] = fy0[i] * (fx0[i] * a[k] + fx1 * b[k]) + fy1 * (fx0[i] * c[k] + fx1 * d[k]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) uv[i][k] = 0.f;
+            }
+          }
           const float* wq = s_wt + ((size_t)cpad * 9 + tap) * OG;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const float4* wv = reinterpret_cast<const float4*>(wq + (size_t)k * 9 * OG);
+            const float2 u0 = make_float2(uv[0][k], uv[0][k]), u1 = make_float2(uv[1][k], uv[1][k]);
 #pragma unroll
             for (int o4 = 0; o4 < OG / 4; ++o4) {
               const float4 ww = wv[o4];
-              acc[4 * o4 + 0] = fmaf(uv[k], ww.x, acc[4 * o4 + 0]);
-              acc[4 * o4 + 1] = fmaf(uv[k], ww.y, acc[4 * o4 + 1]);
-              acc[4 * o4 + 2] = fmaf(uv[k], ww.z, acc[4 * o4 + 2]);
-              acc[4 * o4 + 3] = fmaf(uv[k], ww.w, acc[4 * o4 + 3]);
+              const float2 wa = make_float2(ww.x, ww.y), wb = make_float2(ww.z, ww.w);
+              acc[0][2 * o4 + 0] = __ffma2_rn(u0, wa, acc[0][2 * o4 + 0]);
+              acc[0][2 * o4 + 1] = __ffma2_rn(u0, wb, acc[0][2 * o4 + 1]);
+              acc[1][2 * o4 + 0] = __ffma2_rn(u1, wa, acc[1][2 * o4 + 0]);
+              acc[1][2 * o4 + 1] = __ffma2_rn(u1, wb, acc[1][2 * o4 + 1]);
             }
           }
         }
       }
     }
-    uint4* dst = reinterpret_cast<uint4*>(out) + (((size_t)n * (cp >> 3) + grp * (OG / 8)) * H2 + v) * (size_t)W2 + u;
 #pragma unroll
-    for (int q = 0; q < OG / 8; ++q) {
-      float cur[8];
-      unpack8(dst[(size_t)q * H2 * W2], cur);
+    for (int i = 0; i < 2; ++i) {
+      uint4* dst =
+          reinterpret_cast<uint4*>(out) + (((size_t)n * (cp >> 3) + grp * (OG / 8)) * H2 + pv[i]) * (size_t)W2 + pu[i];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) cur[k] -= acc[8 * q + k];
-      dst[(size_t)q * H2 * W2] = pack8(cur);
+      for (int q = 0; q < OG / 8; ++q) {
+        float cur[8];
+        unpack8(dst[(size_t)q * H2 * W2], cur);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          cur[2 * k] -= acc[i][4 * q + k].x;
+          cur[2 * k + 1] -= acc[i][4 * q + k].y;
+        }
+        dst[(size_t)q * H2 * W2] = pack8(cur);
+      }
     }
   }
 }
@@ -1682,7 +1715,7 @@ int ynet_tc_upconv3x3(const ynet_tc_src* srcs, const int32_t* src_channels_host,
   if (n_padded == n_src) {
     // replicate-padded inputs: the tensor-core result is exact except for the zero padding of the outermost ring
     const int ring_hi = 2 * (2 * w) + 2 * (2 * h - 2);
-    const long long total_hi = (long long)N * ring_hi;
+    const long long total_hi = (long long)N * (ring_hi / 2);        // two ring pixels per thread
     const int groups_hi = cp / og;
     const int per_sm_hi = smem > 100 * 1024 ? 1 : (smem > 64 * 1024 ? 2 : 3);
     const unsigned gxh = (unsigned)tmax<long long>(
