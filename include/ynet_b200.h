@@ -257,7 +257,10 @@ int ynet_tc_predictor_f32(const void* x_c8, int32_t N, int32_t C_pad, int32_t C_
  *     float32 weight; ynet_tc_upconv_border_weight_bytes bytes) and the original `bias` are used to recompute the
  *     one-pixel border ring exactly (index clamping and zero padding do not commute with the stencil).
  *     When the sources are `padded` (replicated one-pixel ring) the stencil is exact up to the conv's zero padding
- *     and only the outermost high-resolution ring is corrected (3-5 taps per pixel instead of 9 on a 2-pixel ring).
+ *     and only the outermost high-resolution ring is corrected (3-5 taps per pixel instead of 9 on a 2-pixel ring):
+ *     per image, the outside line of each edge is interpolated once into shared memory and the outside taps are
+ *     applied with warp-level bf16 mma (fragments appended to `border_weight`); YNET_RINGFIX_MMA=0 selects the
+ *     float32 CUDA-core variant.
  *     C_out <= 64; relu must be 0.
  *   ynet_tc_pad_replicate: (N, C_pad/8, H, W, 8) -> (N, C_pad/8, H+2, W+2, 8); ynet_tc_conv3x3 writes the same layout
  *     directly when bit 1 of `relu` is set (relu: bit 0 = ReLU, bit 1 = padded output). */

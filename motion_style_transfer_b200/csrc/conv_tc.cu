@@ -1186,6 +1186,175 @@ upconv_ringfix_kernel(UpBorderSrc src, int N, int h, int w, const float* __restr
   }
 }
 
+// ---- the same ring correction on the tensor cores (warp-level mma.sync) ------------------------------------------
+// The CUDA-core kernel above is instruction bound: 3 taps x C_in x C_out multiply-adds per ring pixel is 2.4 GMAC per
+// launch at 208^2 -> 416^2, and every U~ value is interpolated three times (once per neighbouring pixel).  Here one CTA
+// owns one image and walks its four edges.  Per edge: (1) the outside line U~ (one hi-res row / column just beyond the
+// image, with a one-pixel apron) is interpolated ONCE into shared memory as bf16 [position][channel]; (2) the edge's
+// three outside taps are staged as mma B fragments; (3) each warp takes 16 consecutive ring pixels: A = the line at
+// positions q + t (t = tap along the edge) read with ldmatrix, K = 3 taps x C_in, N = C_out; (4) the fp32 result is
+// subtracted from the tensor-core output in place.  Corner pixels: the row edges take their three row taps (including
+// the diagonal one), the column edges skip line positions -1 and L (apron zeroed), and __syncthreads() between the
+// edges orders the two read-modify-writes.
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int RFM_THREADS = 256;
+struct RfmGeom {
+  int cpad;        // padded input channels of all sources (multiple of 8)
+  int cpad16;      // ... rounded up to the K step
+  int pitch;       // bytes per line position (cpad16 * 2 + 16: conflict-free ldmatrix rows)
+  int line_rows;   // positions held per line: 16 * tiles + 2
+  int line_bytes;  // line_rows * pitch rounded up to 16
+};
+
+// mma B fragments of the three outside taps of every edge, appended to the float32 border weights:
+// [edge][kstep][n tile][lane][4] bf16, element (k = t * cpad16 + c, o) = w[o][c][tap(edge, t)]
+__global__ void __launch_bounds__(256)
+upconv_ringfix_frag_kernel(const float* __restrict__ w, int C_out, int C_in, UpBorderPack ps, int cpad_total, int cpad16,
+                           int cp, __nv_bfloat16* __restrict__ frag) {
+  const int per_edge = 3 * cpad16 * cp;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 4 * per_edge; idx += gridDim.x * blockDim.x) {
+    const int edge = idx / per_edge, rem = idx - edge * per_edge;
+    const int o = rem % cp, k = rem / cp;
+    const int t = k / cpad16, cpd = k - t * cpad16;
+    const int tap = (edge == 0) ? t : (edge == 1) ? 6 + t : (edge == 2) ? 3 * t : 3 * t + 2;
+    int c = cpd, ci = -1, base = 0;
+    if (cpd < cpad_total) {
+      for (int sidx = 0; sidx < ps.n_src; ++sidx) {
+        const int padded = (ps.real[sidx] + 7) / 8 * 8;
+        if (c < padded) {
+          if (c < ps.real[sidx]) ci = base + c;
+          break;
+        }
+        c -= padded;
+        base += ps.real[sidx];
+      }
+    }
+    const float v = (ci >= 0 && o < C_out) ? w[((size_t)o * C_in + ci) * 9 + tap] : 0.f;
+    const int ks = k >> 4, kk = k & 15, nt_total = cp >> 3;
+    const int fl = (o & 7) * 4 + ((kk & 7) >> 1);
+    frag[((size_t)((edge * (3 * cpad16 >> 4) + ks) * nt_total + (o >> 3)) * 32 + fl) * 4 + (kk >> 3) * 2 + (kk & 1)] =
+        __float2bfloat16_rn(v);
+  }
+}
+
+template <int NT>   // output-channel tiles of 8 (cp / 8)
+__global__ void __launch_bounds__(RFM_THREADS)
+upconv_ringfix_mma_kernel(UpBorderSrc src, int N, int h, int w, const uint2* __restrict__ frag, RfmGeom gm,
+                          __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char rf_smem[];   // two lines: one edge pair at a time
+  const int n = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H2 = 2 * h, W2 = 2 * w, wp = w + 2;
+  const int ksteps_per_tap = gm.cpad16 >> 4, ksteps = 3 * ksteps_per_tap;
+  const int chunks16 = gm.cpad16 >> 3;
+
+  for (int pair = 0; pair < 2; ++pair) {      // rows (top, bottom), then columns (left, right)
+    const bool row_edge = pair == 0;
+    const int L = row_edge ? W2 : H2;
+    const int tiles = (L + 15) >> 4;
+    // (1) the two outside lines: position p <-> hi-res coordinate p - 1 along the edge
+    const int items = gm.line_rows * chunks16;
+#pragma unroll 4
+    for (int item = threadIdx.x; item < 2 * items; item += RFM_THREADS) {
+      const int side = item >= items ? 1 : 0;
+      const int it = item - side * items;
+      const int pos = it / chunks16, chunk = it - pos * chunks16;
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      const bool live = pos < L + 2 && chunk * 8 < gm.cpad && (row_edge || (pos != 0 && pos != L + 1));
+      if (live) {
+        const int q = pos - 1;
+        const int vv = row_edge ? (side ? H2 : -1) : q;
+        const int uu = row_edge ? q : (side ? W2 : -1);
+        // U~[vv, uu] from the padded tensor (same arithmetic as upconv_ringfix_kernel)
+        const int kv = (vv + 2) / 2 - 1, av = (vv + 2) & 1;
+        const int ku = (uu + 2) / 2 - 1, au = (uu + 2) & 1;
+        const int r0 = kv + av, c0 = ku + au;
+        const float fy0 = av ? 0.75f : 0.25f, fx0 = au ? 0.75f : 0.25f;
+        const float fy1 = 1.f - fy0, fx1 = 1.f - fx0;
+        int ch = chunk, s = 0;
+        while (ch >= src.real_chunks[s]) ch -= src.real_chunks[s++];
+        const int bm = src.batch_mod[s];
+        const int ns = (src.batch_stride[s] == 0) ? 0 : (bm > 0 ? n % bm : (bm < 0 ? n / (-bm) : n));
+        const uint4* xc = src.ptr[s] + (size_t)ns * src.batch_stride[s] + (size_t)ch * (h + 2) * wp + (size_t)r0 * wp + c0;
+        float a[8], b[8], c[8], d[8], u[8];
+        unpack8(__ldg(xc), a);
+        unpack8(__ldg(xc + 1), b);
+        unpack8(__ldg(xc + wp), c);
+        unpack8(__ldg(xc + wp + 1), d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) u[k] = fy0 * (fx0 * a[k] + fx1 * b[k]) + fy1 * (fx0 * c[k] + fx1 * d[k]);
+        val = pack8(u);
+      }
+      *reinterpret_cast<uint4*>(rf_smem + (size_t)side * gm.line_bytes + (size_t)pos * gm.pitch + chunk * 16) = val;
+    }
+    __syncthreads();
+    // (3) 16 ring pixels per warp step
+    const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lcol = (lane >> 4) * 8;
+    for (int tile2 = warp; tile2 < 2 * tiles; tile2 += RFM_THREADS / 32) {
+      const int side = tile2 >= tiles ? 1 : 0;
+      const int q0 = (tile2 - side * tiles) << 4;
+      const int edge = 2 * pair + side;       // 0 top, 1 bottom, 2 left, 3 right
+      const unsigned char* line = rf_smem + (size_t)side * gm.line_bytes;
+      const uint2* bf = frag + (size_t)edge * ksteps * NT * 32 + lane;
+      // the ring pixels this thread corrects (rows g, g + 8; channels 2 tq, 2 tq + 1 of every 8-channel tile): fetch
+      // them before the K loop so that the HBM latency hides behind the MMAs
+      const int g = lane >> 2, tq = lane & 3;
+      __nv_bfloat162* dst[2];
+      __nv_bfloat162 cur[2][NT];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int q = q0 + g + half * 8;
+        const int v = row_edge ? (side ? H2 - 1 : 0) : q;
+        const int u = row_edge ? q : (side ? W2 - 1 : 0);
+        dst[half] = (q < L) ? reinterpret_cast<__nv_bfloat162*>(out + (((size_t)n * NT * H2 + v) * (size_t)W2 + u) * 8 + 2 * tq)
+                            : nullptr;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+          if (dst[half] != nullptr) cur[half][nt] = dst[half][(size_t)nt * H2 * W2 * 4];
+      }
+      float acc[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll 2
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int t = ks / ksteps_per_tap, c0 = (ks - t * ksteps_per_tap) << 4;
+        uint32_t a[4];
+        ldmatrix_x4(smem_u32(line + (size_t)(q0 + lrow + t) * gm.pitch + (c0 + lcol) * 2), a);
+        uint2 b[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) b[nt] = __ldg(bf + (size_t)(ks * NT + nt) * 32);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_bf16_16816(acc[nt], a, b[nt].x, b[nt].y);
+      }
+      // (4) out -= correction
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (dst[half] != nullptr) {
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            float2 f = __bfloat1622float2(cur[half][nt]);
+            f.x -= acc[nt][half * 2 + 0];
+            f.y -= acc[nt][half * 2 + 1];
+            dst[half][(size_t)nt * H2 * W2 * 4] = __floats2bfloat162_rn(f.x, f.y);
+          }
+        }
+      }
+    }
+    __syncthreads();   // the column pair reuses the lines and rewrites the corner pixels
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 EncodeTiledFn tc_get_encode() {
   static EncodeTiledFn fn = nullptr;
@@ -1635,7 +1804,9 @@ int64_t ynet_tc_upconv_border_weight_bytes(int32_t C_out, int32_t n_src, const i
   const int cp = ceil_div(C_out, 16) * 16;
   long long cpad = 0;
   for (int i = 0; i < n_src; ++i) cpad += ceil_div(src_channels_host[i], 8) * 8;
-  return cpad * 9 * cp * (long long)sizeof(float);
+  // float32 [g][cpad][9][og] image of the CUDA-core border kernels, then the bf16 mma fragments of the ring fix
+  const long long cpad16 = (cpad + 15) / 16 * 16;
+  return cpad * 9 * cp * (long long)sizeof(float) + 4 * 3 * cpad16 * cp * 2;
 }
 
 int ynet_tc_upconv_border_weights(const float* weight, int32_t C_out, int32_t n_src, const int32_t* src_channels_host,
@@ -1656,6 +1827,10 @@ int ynet_tc_upconv_border_weights(const float* weight, int32_t C_out, int32_t n_
   const int og = upb_og(cp);
   upconv_border_weights_kernel<<<grid_1d((long long)cpad * 9 * cp), 256, 0, as_stream(stream)>>>(
       weight, C_out, cin, ps, cpad, og, cp / og, out);
+  YNET_LAUNCH_CHECK();
+  const int cpad16 = ceil_div(cpad, 16) * 16;
+  upconv_ringfix_frag_kernel<<<grid_1d((long long)12 * cpad16 * cp), 256, 0, as_stream(stream)>>>(
+      weight, C_out, cin, ps, cpad, cpad16, cp, reinterpret_cast<__nv_bfloat16*>(out + (size_t)cpad * 9 * cp));
   YNET_LAUNCH_CHECK();
   return YNET_OK;
 }
@@ -1714,6 +1889,40 @@ int ynet_tc_upconv3x3(const ynet_tc_src* srcs, const int32_t* src_channels_host,
   YNET_CHECK_ARG(n_padded == 0 || n_padded == n_src, "either all or none of the sources carry the replicate-padded ring");
   if (n_padded == n_src) {
     // replicate-padded inputs: the tensor-core result is exact except for the zero padding of the outermost ring
+    {
+      const char* env = getenv("YNET_RINGFIX_MMA");     // "0": the CUDA-core kernel (kept as the cross-check)
+      const bool use_mma = !(env != nullptr && env[0] == '0');
+      RfmGeom gm;
+      gm.cpad = cpad;
+      gm.cpad16 = ceil_div(cpad, 16) * 16;
+      gm.pitch = gm.cpad16 * 2 + 16;
+      gm.line_rows = 16 * ceil_div(2 * tmax(h, w), 16) + 2;
+      gm.line_bytes = ceil_div(gm.line_rows * gm.pitch, 16) * 16;
+      const size_t rf_smem = (size_t)2 * gm.line_bytes;
+      const int nt = cp / 8;
+      if (use_mma && rf_smem <= 200 * 1024 && (nt == 2 || nt == 4 || nt == 8)) {
+        static bool rf_configured = false;
+        if (!rf_configured) {
+          cudaError_t e = cudaFuncSetAttribute(upconv_ringfix_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(upconv_ringfix_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(upconv_ringfix_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          if (e != cudaSuccess) return cuda_fail(e, "ynet_tc_upconv3x3(cudaFuncSetAttribute, ring fix)");
+          rf_configured = true;
+        }
+        __nv_bfloat16* outm = reinterpret_cast<__nv_bfloat16*>(out_c8);
+        const uint2* frag = reinterpret_cast<const uint2*>(border_weight + (size_t)cpad * 9 * cp);
+        if (nt == 2)
+          upconv_ringfix_mma_kernel<2><<<N, RFM_THREADS, rf_smem, as_stream(stream)>>>(bs, N, h, w, frag, gm, outm);
+        else if (nt == 4)
+          upconv_ringfix_mma_kernel<4><<<N, RFM_THREADS, rf_smem, as_stream(stream)>>>(bs, N, h, w, frag, gm, outm);
+        else
+          upconv_ringfix_mma_kernel<8><<<N, RFM_THREADS, rf_smem, as_stream(stream)>>>(bs, N, h, w, frag, gm, outm);
+        YNET_LAUNCH_CHECK();
+        return YNET_OK;
+      }
+    }
     const int ring_hi = 2 * (2 * w) + 2 * (2 * h - 2);
     const long long total_hi = (long long)N * (ring_hi / 2);        // two ring pixels per thread
     const int groups_hi = cp / og;

@@ -76,74 +76,76 @@ __device__ __forceinline__ float normalised(float v, bool use_thr, float thr, fl
   return __fdiv_rn(kept, gsum);                           // prob / prob.sum()
 }
 
-// ---- sequential float32 CDF: one warp per row -----------------------------------------------------
-constexpr int kCdfChunk = 1024;       // elements staged per step
-constexpr int kCdfWarpsPerCta = 4;
+// ---- sequential float32 CDF: one CTA per row, warp-specialised -------------------------------------
+// torch.multinomial's CPU CDF is a sequential fp32 running sum, so each row is ONE dependent FADD chain
+// (173 056 adds at 4 cycles each is the floor).  Everything else is taken off that chain: lane 0 of warp 0
+// only walks a staged chunk in shared memory; warps 1-3 meanwhile write the previous chunk's prefix sums
+// to HBM and load + threshold + normalise the next chunk into the buffer that just became free.
+constexpr int kCdfChunk = 2048;       // elements per staged chunk (two buffers)
+constexpr int kCdfThreads = 128;
+constexpr int kCdfHelpers = kCdfThreads - 32;
 
-__global__ void __launch_bounds__(kCdfWarpsPerCta * 32)
+__global__ void __launch_bounds__(kCdfThreads)
 cdf_sequential_kernel(const float* __restrict__ p, int rows, long long S, bool use_thr, float rel,
                       const float* __restrict__ rowmax, const float* __restrict__ gsum_ptr, float* __restrict__ cdf) {
-  __shared__ __align__(16) float buf_all[kCdfWarpsPerCta][kCdfChunk];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * kCdfWarpsPerCta + warp;
-  if (row >= rows) return;
-  float* buf = buf_all[warp];
+  __shared__ __align__(16) float buf[2][kCdfChunk];
+  const int row = blockIdx.x;
   const float* src = p + (size_t)row * S;
   float* dst = cdf + (size_t)row * S;
   const float thr = use_thr ? __fmul_rn(rowmax[row], rel) : 0.f;
   const float gsum = use_thr ? *gsum_ptr : 1.f;
-
-  constexpr int PER = kCdfChunk / 32;  // 32 elements per lane per chunk
-  float r[PER];
   const long long n_chunks = ceil_div<long long>(S, kCdfChunk);
-  // prefetch chunk 0
-#pragma unroll
-  for (int k = 0; k < PER; ++k) {
-    const long long e = (long long)k * 32 + lane;
-    r[k] = (e < S) ? __ldg(src + e) : 0.f;
-  }
-  float carry = 0.f;
-  for (long long c = 0; c < n_chunks; ++c) {
+  const int helper = (int)threadIdx.x - 32;          // >= 0: staging / write-out thread
+
+  auto stage = [&](long long c) {                    // chunk c -> buf[c & 1] (zero tail: x + 0 is exact)
+    float* b = buf[c & 1];
     const long long base = c * kCdfChunk;
+    constexpr int PER = (kCdfChunk + kCdfHelpers - 1) / kCdfHelpers;
+    float r[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {                  // all loads in flight before the first division
+      const int i = helper + k * kCdfHelpers;
+      r[k] = (i < kCdfChunk && base + i < S) ? __ldg(src + base + i) : 0.f;
+    }
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
-      const long long e = base + (long long)k * 32 + lane;
-      buf[k * 32 + lane] = (e < S) ? normalised(r[k], use_thr, thr, gsum) : 0.f;
+      const int i = helper + k * kCdfHelpers;
+      if (i < kCdfChunk) b[i] = (base + i < S) ? normalised(r[k], use_thr, thr, gsum) : 0.f;
     }
-    // prefetch the next chunk while lane 0 walks this one
-    if (c + 1 < n_chunks) {
-#pragma unroll
-      for (int k = 0; k < PER; ++k) {
-        const long long e = base + kCdfChunk + (long long)k * 32 + lane;
-        r[k] = (e < S) ? __ldg(src + e) : 0.f;
-      }
-    }
-    __syncwarp();
-    if (lane == 0) {
-      float4* b4 = reinterpret_cast<float4*>(buf);
+  };
+  if (helper >= 0) stage(0);
+  __syncthreads();
+  float carry = 0.f;
+  for (long long c = 0; c < n_chunks; ++c) {
+    if (threadIdx.x == 0) {
+      float4* b4 = reinterpret_cast<float4*>(buf[c & 1]);
       float acc = carry;
-#pragma unroll 8
+#pragma unroll 16
       for (int i = 0; i < kCdfChunk / 4; ++i) {
         float4 v = b4[i];
-        acc = __fadd_rn(acc, v.x);
-        v.x = acc;
-        acc = __fadd_rn(acc, v.y);
-        v.y = acc;
-        acc = __fadd_rn(acc, v.z);
-        v.z = acc;
-        acc = __fadd_rn(acc, v.w);
-        v.w = acc;
+        v.x = acc = __fadd_rn(acc, v.x);
+        v.y = acc = __fadd_rn(acc, v.y);
+        v.z = acc = __fadd_rn(acc, v.z);
+        v.w = acc = __fadd_rn(acc, v.w);
         b4[i] = v;
       }
       carry = acc;
+    } else if (helper >= 0) {
+      if (c > 0) {                                   // prefix sums of chunk c - 1 -> HBM
+        const float* b = buf[(c - 1) & 1];
+        const long long base = (c - 1) * kCdfChunk;
+        for (int i = helper; i < kCdfChunk; i += kCdfHelpers)
+          if (base + i < S) dst[base + i] = b[i];
+      }
+      if (c + 1 < n_chunks) stage(c + 1);            // same buffer as chunk c - 1, now free
     }
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      const long long e = base + (long long)k * 32 + lane;
-      if (e < S) dst[e] = buf[k * 32 + lane];
-    }
-    __syncwarp();
+    __syncthreads();
+  }
+  if (helper >= 0) {
+    const float* b = buf[(n_chunks - 1) & 1];
+    const long long base = (n_chunks - 1) * kCdfChunk;
+    for (int i = helper; i < kCdfChunk; i += kCdfHelpers)
+      if (base + i < S) dst[base + i] = b[i];
   }
 }
 
@@ -339,7 +341,7 @@ int ynet_multinomial_replacement(const float* prob, int32_t rows, int64_t S, flo
   YNET_CHECK_ARG(rows > 0 && rows <= 65535 && S > 0 && n > 0 && W > 0, "bad shape");
   const bool use_thr = rel_threshold >= 0.f;
   YNET_CHECK_ARG(!use_thr || (rowmax && gsum), "threshold requested without rowmax/gsum (ynet_sampling_prepare)");
-  cdf_sequential_kernel<<<ceil_div(rows, kCdfWarpsPerCta), kCdfWarpsPerCta * 32, 0, as_stream(stream)>>>(
+  cdf_sequential_kernel<<<rows, kCdfThreads, 0, as_stream(stream)>>>(
       prob, rows, S, use_thr, rel_threshold, rowmax, gsum, cdf_ws);
   YNET_LAUNCH_CHECK();
   cdf_search_kernel<<<dim3(ceil_div(n, 256), rows), 256, 0, as_stream(stream)>>>(
