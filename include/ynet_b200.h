@@ -217,8 +217,13 @@ typedef struct ynet_tc_src {
                            (< channels_pad / 8): the missing planes read as zero (TMA out-of-bounds fill) */
   int32_t padded;       /* 1: planes are (H + 2) x (W + 2) with a one-pixel REPLICATED ring around the H x W image
                            (ynet_tc_pad_replicate, or a conv's padded output): input of ynet_tc_upconv3x3 only */
-  int32_t reserved;
+  int32_t tap_mask;     /* 0: all taps (or the centre tap when center_only).  YNET_TC_TAPS_QUAD: the planes hold the
+                           2x2 neighbourhood of every pixel (channel (dy*2+dx)*n + c = map_c[y+dy][x+dx], zero outside
+                           the image; ynet_tc_rasterize_pyramid_c8 with quad_levels) so that the four taps anchored at
+                           (-1,-1) (-1,0) (0,-1) (0,0) cover the 3x3 window: 4 MMAs per K block instead of 9.  The K
+                           blocks hold FOUR taps in the packed weights (pack a (C_out, C, 2, 2) weight, ksize 2)      */
 } ynet_tc_src;
+#define YNET_TC_TAPS_QUAD 0x1B
 
 int ynet_tc_supported(void);
 
@@ -226,11 +231,14 @@ int ynet_tc_supported(void);
  * AvgPool2d(2^i) pyramid of the result (evaluate.py:255-257), written straight as bf16 C8 planes.
  * coords: (n_img * n_ch, 2) float32 (x, y), n_ch <= 8.  outs_host[l], l < n_levels: (n_img, C_pad/8, H>>l, W>>l, 8)
  * bf16; channel c < n_ch of chunk 0 holds the map, the other channels of chunk 0 are written as zero.
- * write_pad = 0: chunks >= 1 are NOT written (the caller keeps them zero across calls); 1: zero-filled. */
+ * write_pad = 0: chunks >= 1 are NOT written (the caller keeps them zero across calls); 1: zero-filled.
+ * quad_levels in [0, 2] (n_ch <= 2, C_pad == 8): levels l < quad_levels are written as 2x2-neighbourhood planes --
+ * channel (dy*2 + dx) * n_ch + c of pixel (y, x) = map_c[y + dy][x + dx], zero outside the image -- for conv sources
+ * with tap_mask = YNET_TC_TAPS_QUAD (4 MMAs per K block instead of 9 at the same 16 B per pixel). */
 int ynet_tc_rasterize_pyramid_c8(const float* tmpl, int32_t tmpl_h, int32_t tmpl_w, const float* coords,
                                  int32_t n_img, int32_t n_ch, int32_t H, int32_t W, int32_t n_levels,
-                                 void* const* outs_host, int32_t C_pad, int32_t write_pad, int32_t* oob_flag,
-                                 void* stream);
+                                 void* const* outs_host, int32_t C_pad, int32_t write_pad, int32_t quad_levels,
+                                 int32_t* oob_flag, void* stream);
 /* The same maps in im2col form for level 0 (full resolution) or 1 (2x2 average pool): channel c*9 + kh*3 + kw of
  * pixel (y, x) = map_c[y+kh-1][x+kw-1], 0 outside the image.  A conv reads it as a `center_only` source with the
  * 1x1 weights W[:, wp channels].reshape(C_out, 9 n_ch): one MMA per 16 im2col channels instead of nine per
@@ -274,7 +282,7 @@ int ynet_tc_upconv3x3(const ynet_tc_src* srcs_host, const int32_t* src_channels_
                       int32_t h, int32_t w, const void* packed_phase_weight, const float* bias_eff,
                       const float* border_weight, const float* bias, int32_t C_out, int32_t relu, void* out_c8,
                       int32_t tune, void* stream);
-/* ksize = 3 (3x3 conv) or 1 (the 1x1 predictor). */
+/* ksize = 3 (3x3 conv), 1 (the 1x1 predictor, centre-only sources) or 2 (2x2-neighbourhood sources, YNET_TC_TAPS_QUAD). */
 int64_t ynet_tc_packed_weight_bytes(int32_t C_out, int32_t n_src, const int32_t* src_channels_pad_host,
                                     int32_t ksize);
 int ynet_tc_pack_weights(const float* weight, int32_t C_out, int32_t n_src, const int32_t* src_channels_host,

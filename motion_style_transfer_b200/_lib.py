@@ -24,7 +24,7 @@ class ConvSrc(Structure):
 class TcSrc(Structure):
     _fields_ = [('ptr', c_void_p), ('channels_pad', c_int32), ('batch_mod', c_int32), ('batch_stride', c_int64),
                 ('center_only', c_int32), ('chunks_stored', c_int32),
-                ('padded', c_int32), ('reserved', c_int32)]
+                ('padded', c_int32), ('tap_mask', c_int32)]
 
 
 class YnetError(RuntimeError):
@@ -71,7 +71,7 @@ _PROTOS = {
     'ynet_lora_fold': (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     'ynet_tc_supported': (c_int, []),
     'ynet_tc_rasterize_im2col_c8': (c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
-    'ynet_tc_rasterize_pyramid_c8': (c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _I, POINTER(c_void_p), _I, _I, _P, _P]),
+    'ynet_tc_rasterize_pyramid_c8': (c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _I, POINTER(c_void_p), _I, _I, _I, _P, _P]),
     'ynet_tc_pack_f32_to_c8': (c_int, [_P, _I, _I, _I, _I, _L, _P, _I, _P]),
     'ynet_tc_unpack_c8_to_f32': (c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
     'ynet_tc_maxpool2x2': (c_int, [_P, _I, _I, _I, _I, _P, _P]),

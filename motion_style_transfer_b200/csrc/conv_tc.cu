@@ -49,6 +49,7 @@ struct TcParams {
   int with_lo;            // EPI_HILO: also write the low halves
   int pad_out;            // EPI_C8: write (H + 2, W + 2) planes with a replicated one-pixel ring (input of an upconv)
   uint32_t center_mask;   // bit kb: K block kb belongs to a centre-tap-only source
+  uint32_t quad_mask;     // bit kb: K block kb belongs to a 2x2-neighbourhood source: taps (0,0) (0,1) (1,0) (1,1) only
   int w_total;            // bytes of the packed weights
   int wofs[TC_MAX_KB];    // byte offset of K block kb in the packed weights (9-tap and 1-tap blocks are mixed)
   int resident;           // weights resident in smem
@@ -144,7 +145,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err);
             unsigned char* st = s_stage + (size_t)stage * p.stage_bytes;
             const uint32_t fb = smem_u32(&full_bar[stage]);
-            const uint32_t wb = ((p.center_mask >> kb) & 1u) ? (uint32_t)(wblk_bytes / TAPS) : (uint32_t)wblk_bytes;
+            const uint32_t wb = ((p.center_mask >> kb) & 1u) ? (uint32_t)(wblk_bytes / TAPS)
+                                : ((p.quad_mask >> kb) & 1u) ? (uint32_t)(4 * (wblk_bytes / TAPS))
+                                                             : (uint32_t)wblk_bytes;
             mbar_expect_tx(fb, p.a_bytes + (p.resident ? 0u : wb));
             tma_load_4d(smem_u32(st), map, fb, 8 * (x0 - HALO + p.src[s].off), y0 - HALO + p.src[s].off, 2 * b, ns);
             if (!p.resident) bulk_load(smem_u32(st + p.a_bytes), p.wpacked + p.wofs[kb], wb, fb);
@@ -194,6 +197,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             for (int jj = 0; jj < J; ++jj) {
               const uint64_t adesc = ((uint64_t)A_HI << 32) | (a_lo0 + (uint32_t)(BW + 1 + 8 * jj));
               tc_mma_bf16(d_tmem + (uint32_t)(jj * p.n_pad), adesc, bdesc, idesc, acc_first);
+            }
+          } else if (TAPS == 9 && ((p.quad_mask >> kb) & 1u)) {
+            // 2x2-neighbourhood planes (waypoint maps): the four taps anchored at (-1,-1) (-1,0) (0,-1) (0,0) cover
+            // the 3x3 window; the packed weights hold exactly these four taps
+#pragma unroll
+            for (int t4 = 0; t4 < 4; ++t4) {
+              const uint64_t bdesc = ((uint64_t)b_hi << 32) | b_lo;
+#pragma unroll
+              for (int jj = 0; jj < J; ++jj) {
+                const uint64_t adesc = ((uint64_t)A_HI << 32) | (a_lo0 + (uint32_t)((t4 >> 1) * BW + (t4 & 1) + 8 * jj));
+                tc_mma_bf16(d_tmem + (uint32_t)(jj * p.n_pad), adesc, bdesc, idesc, t4 == 0 ? acc_first : 1u);
+              }
+              b_lo += b_tap_step;
             }
           } else {
 #pragma unroll
@@ -1459,7 +1475,7 @@ int ynet_tc_predictor_f32(const void* x_c8, int32_t N, int32_t C_pad, int32_t C_
 }
 
 int64_t ynet_tc_packed_weight_bytes(int32_t C_out, int32_t n_src, const int32_t* src_channels_pad_host, int32_t ksize) {
-  if (C_out <= 0 || n_src <= 0 || n_src > YNET_MAX_SOURCES || !src_channels_pad_host || (ksize != 1 && ksize != 3))
+  if (C_out <= 0 || n_src <= 0 || n_src > YNET_MAX_SOURCES || !src_channels_pad_host || (ksize != 1 && ksize != 2 && ksize != 3))
     return 0;
   const int n_pad = ceil_div(C_out, 16) * 16;
   long long kb = 0;
@@ -1470,7 +1486,7 @@ int64_t ynet_tc_packed_weight_bytes(int32_t C_out, int32_t n_src, const int32_t*
 int ynet_tc_pack_weights(const float* weight, int32_t C_out, int32_t n_src, const int32_t* src_channels_host,
                          const int32_t* src_channels_pad_host, int32_t ksize, void* packed, void* stream) {
   YNET_CHECK_ARG(weight && packed && src_channels_host && src_channels_pad_host, "null pointer");
-  YNET_CHECK_ARG(C_out > 0 && n_src >= 1 && n_src <= YNET_MAX_SOURCES && (ksize == 1 || ksize == 3), "bad shape");
+  YNET_CHECK_ARG(C_out > 0 && n_src >= 1 && n_src <= YNET_MAX_SOURCES && (ksize >= 1 && ksize <= 3), "bad shape");
   PackSrc ps;
   memset(&ps, 0, sizeof(ps));
   ps.n_src = n_src;
@@ -1606,6 +1622,15 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
     p.src[i].bcast = bcast ? 1 : 0;
     p.src[i].batch_mod = srcs[i].batch_mod;
     p.src[i].center = (taps == 9 && srcs[i].center_only) ? 1 : 0;
+    const bool quad = taps == 9 && !srcs[i].center_only && srcs[i].tap_mask == YNET_TC_TAPS_QUAD;
+    if (srcs[i].tap_mask != 0 && !quad) {
+      set_error("%s: source %d: tap_mask must be 0 or YNET_TC_TAPS_QUAD (3x3 convs, not centre-only)", who, i);
+      return YNET_E_INVALID;
+    }
+    if (quad && (epi == EPI_PRED || po)) {
+      set_error("%s: source %d: 2x2-neighbourhood sources are not supported by this variant", who, i);
+      return YNET_E_UNSUPPORTED;
+    }
     p.src[i].off = po;
     if (kb_total + cp / 16 > TC_MAX_KB) {
       set_error("%s: more than %d input K blocks", who, TC_MAX_KB);
@@ -1613,8 +1638,9 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
     }
     for (int b = 0; b < cp / 16; ++b) {
       p.wofs[kb_total + b] = w_total;
-      w_total += (p.src[i].center ? 1 : taps) * 2 * C_out_pad * 16;
+      w_total += (p.src[i].center ? 1 : (quad ? 4 : taps)) * 2 * C_out_pad * 16;
       if (p.src[i].center) p.center_mask |= 1u << (kb_total + b);
+      if (quad) p.quad_mask |= 1u << (kb_total + b);
     }
     kb_total += cp / 16;
   }

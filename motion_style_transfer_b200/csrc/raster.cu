@@ -253,6 +253,131 @@ wp_pyramid_c8_kernel(const float* __restrict__ tmpl, int th, int tw, const float
 }
 
 
+// ---- the same pyramid with 2x2-NEIGHBOURHOOD planes at the finest levels ---------------------------------------
+// The n_wp <= 2 waypoint channels leave six of the eight channels of the plane empty, and the conv spends nine MMAs per
+// tile on that K block.  Levels l < quad_levels store, at pixel (y, x), channel (dy*2 + dx) * NCH + c = map_c[y+dy][x+dx]
+// (dy, dx in {0, 1}; zero outside the image = the conv's zero padding): the 3x3 window is then covered by the FOUR taps
+// anchored at (-1,-1) (-1,0) (0,-1) (0,0) (ynet_tc_src.tap_mask = YNET_TC_TAPS_QUAD) at the same 16 B per pixel.
+// Pooled levels use the same arithmetic as wp_pyramid_c8_kernel; levels >= quad_levels keep the plain layout.
+template <int NCH>
+__global__ void __launch_bounds__(256)
+wp_pyramid_quad_c8_kernel(const float* __restrict__ tmpl, int th, int tw, const float* __restrict__ coords, int H, int W,
+                          int n_levels, int quad_levels, PyramidC8Outs outs, int* __restrict__ oob) {
+  static_assert(NCH * 4 <= 8, "2x2 neighbourhood of NCH channels must fit one 8-channel plane");
+  __shared__ float s0[NCH][34][35];
+  __shared__ float s1[NCH][17][18];
+  __shared__ float s2[NCH][8][9];
+  __shared__ float s3[NCH][4][5];
+  __shared__ float s4[NCH][2][3];
+  const int n = blockIdx.z;
+  const int ty0 = blockIdx.y * 32, tx0 = blockIdx.x * 32;
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int x = __float2int_rn(coords[2 * (n * NCH + c) + 0]);  // round half to even == np.round
+    const int y = __float2int_rn(coords[2 * (n * NCH + c) + 1]);
+    const int yl = th / 2 - y, xl = tw / 2 - x;
+    const bool bad = (yl < 0) | (xl < 0) | (yl + H > th) | (xl + W > tw);
+    if (bad && oob != nullptr && t == 0 && blockIdx.x == 0 && blockIdx.y == 0) atomicExch(oob, 1);
+    // 34 x 34 region (block + two pixels of apron): a warp per row, lanes 0-1 also fetch the two apron columns
+    const int lane = t & 31;
+    for (int ry = t >> 5; ry < 34; ry += 8) {
+      const int gy = ty0 + ry;
+      const int sy = min(max(yl + gy, 0), th - 1);
+      const float* row = tmpl + (size_t)sy * tw;
+      s0[c][ry][lane] = (gy < H) ? __ldg(row + min(max(xl + tx0 + lane, 0), tw - 1)) : 0.f;
+      if (lane < 2) {
+        const int gx = tx0 + 32 + lane;
+        s0[c][ry][32 + lane] = (gy < H && gx < W) ? __ldg(row + min(max(xl + gx, 0), tw - 1)) : 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  {  // level 0: 32 x 32, 4 pixels per thread
+    const int tx = t & 31, ty = t >> 5;
+    uint4* o = outs.p[0] + (size_t)n * H * W;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int y = ty + 8 * r;
+      float f[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = 0.f;
+      if (quad_levels > 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) f[q * NCH + c] = s0[c][y + (q >> 1)][tx + (q & 1)];
+      } else {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) f[c] = s0[c][y][tx];
+      }
+      o[(size_t)(ty0 + y) * W + tx0 + tx] = pack8_bf16(f);
+    }
+  }
+  if (n_levels <= 1) return;
+  for (int idx = t; idx < NCH * 17 * 17; idx += 256) {   // level 1 incl. one pooled pixel of apron
+    const int c = idx / 289, r = idx - c * 289;
+    const int py = r / 17, px = r - py * 17;
+    s1[c][py][px] = 0.25f * ((s0[c][2 * py][2 * px] + s0[c][2 * py][2 * px + 1]) +
+                             (s0[c][2 * py + 1][2 * px] + s0[c][2 * py + 1][2 * px + 1]));
+  }
+  __syncthreads();
+  {
+    const int y = t >> 4, x = t & 15;
+    const int h = H >> 1, w = W >> 1;
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = 0.f;
+    if (quad_levels > 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) f[q * NCH + c] = s1[c][y + (q >> 1)][x + (q & 1)];
+    } else {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) f[c] = s1[c][y][x];
+    }
+    outs.p[1][(size_t)n * h * w + (size_t)((ty0 >> 1) + y) * w + (tx0 >> 1) + x] = pack8_bf16(f);
+  }
+  auto reduce = [&](auto& src, auto& dst, int side, int lvl) {   // side = output block edge at this level
+    if (t < side * side) {
+      const int y = t / side, x = t - y * side;
+      float f[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const float v = 0.25f * ((src[c][2 * y][2 * x] + src[c][2 * y][2 * x + 1]) +
+                                 (src[c][2 * y + 1][2 * x] + src[c][2 * y + 1][2 * x + 1]));
+        dst[c][y][x] = v;
+        f[c] = v;
+      }
+      const int h = H >> lvl, w = W >> lvl;
+      outs.p[lvl][(size_t)n * h * w + (size_t)((ty0 >> lvl) + y) * w + (tx0 >> lvl) + x] = pack8_bf16(f);
+    }
+  };
+  if (n_levels <= 2) return;
+  reduce(s1, s2, 8, 2);
+  if (n_levels <= 3) return;
+  __syncthreads();
+  reduce(s2, s3, 4, 3);
+  if (n_levels <= 4) return;
+  __syncthreads();
+  reduce(s3, s4, 2, 4);
+  if (n_levels <= 5) return;
+  __syncthreads();
+  if (t == 0) {
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) f[c] = 0.25f * ((s4[c][0][0] + s4[c][0][1]) + (s4[c][1][0] + s4[c][1][1]));
+    const int h = H >> 5, w = W >> 5;
+    outs.p[5][(size_t)n * h * w + (size_t)(ty0 >> 5) * w + (tx0 >> 5)] = pack8_bf16(f);
+  }
+}
+
+
 // ---- a3 + a9 in im2col form for the tensor-core engine -------------------------------------------------------
 // The n_wp (1-2) waypoint channels of a trajectory-decoder input occupy a whole 16-channel K block of the conv: nine
 // MMAs per tile for two real channels.  Written as im2col instead -- channel c * 9 + kh * 3 + kw of pixel (y, x) =
@@ -392,8 +517,10 @@ int ynet_avgpool_pyramid(const float* in, int32_t n, int32_t H, int32_t W, int32
 
 int ynet_tc_rasterize_pyramid_c8(const float* tmpl, int32_t th, int32_t tw, const float* coords, int32_t n_img,
                                  int32_t n_ch, int32_t H, int32_t W, int32_t n_levels, void* const* outs_host,
-                                 int32_t C_pad, int32_t write_pad, int32_t* oob_flag, void* stream) {
+                                 int32_t C_pad, int32_t write_pad, int32_t quad_levels, int32_t* oob_flag, void* stream) {
   YNET_CHECK_ARG(n_img >= 0 && n_ch >= 1 && n_ch <= 8 && H > 0 && W > 0 && th >= H && tw >= W, "bad shape (n_ch <= 8)");
+  YNET_CHECK_ARG(quad_levels >= 0 && quad_levels <= 2 && (quad_levels == 0 || (n_ch <= 2 && C_pad == 8)),
+                 "quad_levels in [0, 2]; 2x2-neighbourhood planes need n_ch <= 2 and C_pad == 8");
   YNET_CHECK_ARG(n_levels >= 1 && n_levels <= 6 && C_pad >= 8 && C_pad % 8 == 0, "n_levels in [1, 6], C_pad % 8 == 0");
   if (H % 32 != 0 || W % 32 != 0) {
     set_error("ynet_tc_rasterize_pyramid_c8: H and W must be multiples of 32 (trainer.py:60,581)");
@@ -416,6 +543,14 @@ int ynet_tc_rasterize_pyramid_c8(const float* tmpl, int32_t th, int32_t tw, cons
     dim3 grid(W / 32, H / 32, nn);
     const float* c = coords + 2 * (size_t)n0 * n_ch;
     cudaStream_t st = as_stream(stream);
+    if (quad_levels > 0) {
+      if (n_ch == 1)
+        wp_pyramid_quad_c8_kernel<1><<<grid, 256, 0, st>>>(tmpl, th, tw, c, H, W, n_levels, quad_levels, o, oob_flag);
+      else
+        wp_pyramid_quad_c8_kernel<2><<<grid, 256, 0, st>>>(tmpl, th, tw, c, H, W, n_levels, quad_levels, o, oob_flag);
+      YNET_LAUNCH_CHECK();
+      continue;
+    }
 #define YNET_WP_CASE(K)                                                                                              \
   case K:                                                                                                            \
     wp_pyramid_c8_kernel<K><<<grid, 256, 0, st>>>(tmpl, th, tw, c, H, W, n_levels, chunks, write_pad, o, oob_flag); \

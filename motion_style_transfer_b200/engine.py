@@ -299,6 +299,9 @@ class YNetEngineTC(YNetEngine):
     # Measured on B200: 13 instead of 20 MMAs per tile at 416^2, but the 32-channel im2col planes double the waypoint
     # bytes and the layer turns HBM-bound (1.25 vs 1.28 ms per 240 images, plus a 0.5 ms rasteriser) -> off by default.
     im2col_levels = int(os.environ.get('YNET_IM2COL_LEVELS', '0'))
+    # Waypoint maps of the two finest levels as 2x2-neighbourhood planes: 4 instead of 9 MMAs per tile on the waypoint
+    # K block at the same 16 B per pixel (the 416^2 / 208^2 input convs are bound by the MMA operand fetch).
+    quad_levels = int(os.environ.get('YNET_QUAD_LEVELS', '2'))
     hoist_lo = os.environ.get('YNET_HOIST_LO', '0') == '1'     # keep the low halves of the partial sums too
 
     def _hoist_params(self, module, key, layout):
@@ -344,7 +347,9 @@ class YNetEngineTC(YNetEngine):
             c = up.C
         layout.append(('partial', partial.C))
         srcs.append(partial)
-        if pyr_level.center:      # im2col waypoint maps (9 channels per waypoint)
+        if pyr_level.taps:        # 2x2-neighbourhood planes: four taps per K block
+            layout.append(('quad', (c + c_feat, pyr_level.C // 4)))
+        elif pyr_level.center:    # im2col waypoint maps (9 channels per waypoint)
             layout.append(('i2c', (c + c_feat, c + c_feat + pyr_level.C // 9)))
         else:
             layout.append(('conv', (c + c_feat, c + c_feat + pyr_level.C)))
@@ -398,7 +403,8 @@ class YNetEngineTC(YNetEngine):
             b1 = min(B, b0 + bc)
             nb = b1 - b0
             wp = waypoint_samples[:, b0:b1].permute(1, 0, 2, 3).reshape(-1, 2).contiguous()   # (nb, G, n_wp) order
-            pyr = ops.tc_rasterize_pyramid(template, wp, nb * G, n_wp, H, W, len(feats))
+            quad = min(self.quad_levels, len(feats)) if (self.hoist and n_wp <= 2) else 0
+            pyr = ops.tc_rasterize_pyramid(template, wp, nb * G, n_wp, H, W, len(feats), quad_levels=quad)
             if self.hoist and n_wp <= 3:
                 for lvl in range(min(self.im2col_levels, len(pyr))):
                     pyr[lvl] = ops.tc_rasterize_im2col(template, wp, nb * G, n_wp, H, W, lvl)

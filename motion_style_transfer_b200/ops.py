@@ -552,24 +552,25 @@ class C8:
     (agent-major stacking of the n_goal decoder passes; nothing is copied).
     """
 
-    __slots__ = ('data', 'C', 'rep', 'center', 'pad')
+    __slots__ = ('data', 'C', 'rep', 'center', 'pad', 'taps')
 
-    def __init__(self, data, C, rep=1, center=False, pad=0):
+    def __init__(self, data, C, rep=1, center=False, pad=0, taps=0):
         # center: hoisted partial sums (hi | lo); a conv applies identity weights on its centre tap only
         # pad = 1: planes are (H + 2, W + 2) with a one-pixel replicated ring (input of tc_upconv3x3 only)
-        self.data, self.C, self.rep, self.center, self.pad = data, C, rep, center, pad
+        # taps = TAPS_QUAD: 2x2-neighbourhood planes (tc_rasterize_pyramid quad levels); C counts the stored channels
+        self.data, self.C, self.rep, self.center, self.pad, self.taps = data, C, rep, center, pad, taps
 
     @property
     def N(self):
         return self.data.shape[0] * self.rep
 
     def repeat_interleave(self, rep):
-        return C8(self.data, self.C, self.rep * rep, self.center, self.pad)
+        return C8(self.data, self.C, self.rep * rep, self.center, self.pad, self.taps)
 
     def batch_slice(self, b0, b1):
         if self.rep != 1:
             raise ValueError('batch_slice of a repeated C8')
-        return C8(self.data[b0:b1], self.C, 1, self.center, self.pad)
+        return C8(self.data[b0:b1], self.C, 1, self.center, self.pad, self.taps)
 
     def unpadded(self):
         """The H x W interior of a replicate-padded C8 as a plain (contiguous) C8."""
@@ -637,11 +638,33 @@ def tc_pack(x):
     return C8(out, C)
 
 
-def tc_rasterize_pyramid(template, coords, n_img, n_ch, H, W, n_levels, slot=0):
+TAPS_QUAD = 0x1B      # ynet_b200.h YNET_TC_TAPS_QUAD: taps (0,0) (0,1) (1,0) (1,1) of the 3x3 window
+
+
+def tc_quad_weights(weight_oihw, c0, n_ch):
+    """(C_out, C_in, 3, 3) weight -> the (C_out, 4 * n_ch, 2, 2) weight of a 2x2-neighbourhood source holding input
+    channels [c0, c0 + n_ch): stored channel (dy*2 + dx) * n_ch + c under the tap anchored at (ty - 1, tx - 1) carries
+    w[:, c0 + c, ty + dy, tx + dx]; every 3x3 tap is assigned to exactly one (anchor, offset) pair -- the anchors at -1
+    use only offset 0, so a zero-filled out-of-image anchor loses nothing that lies inside the image."""
+    C_out = weight_oihw.shape[0]
+    q = torch.zeros(C_out, 4 * n_ch, 2, 2, dtype=torch.float32, device=weight_oihw.device)
+    for ty in range(2):
+        for tx in range(2):
+            for dy in range(2):
+                for dx in range(2):
+                    if (ty == 0 and dy == 1) or (tx == 0 and dx == 1):
+                        continue
+                    q[:, (dy * 2 + dx) * n_ch:(dy * 2 + dx + 1) * n_ch, ty, tx] = weight_oihw[:, c0:c0 + n_ch, ty + dy, tx + dx]
+    return q
+
+
+def tc_rasterize_pyramid(template, coords, n_img, n_ch, H, W, n_levels, slot=0, quad_levels=0):
     """get_patch + AvgPool pyramid of ``n_img x n_ch`` waypoint coordinates written straight as bf16 C8 planes
     (image_utils.py:40-63 + evaluate.py:255-257).  Returns n_levels C8 (n_img, ONE 8-channel plane, H>>l, W>>l):
     16 B per pixel; a conv pads the K block to 16 channels through the TMA zero fill (``C8.K_pad``).
     ``slot`` is accepted for compatibility and ignored (every call returns fresh tensors).
+    ``quad_levels`` (n_ch <= 2): the finest levels are written as 2x2-neighbourhood planes (C8.taps = TAPS_QUAD,
+    4 * n_ch stored channels): a conv spends four MMAs per K block on them instead of nine.
     """
     template = _req(template, name='template')
     coords = _req(coords, name='coords').reshape(-1, 2)
@@ -655,10 +678,10 @@ def tc_rasterize_pyramid(template, coords, n_img, n_ch, H, W, n_levels, slot=0):
     S = sum((H >> l) * (W >> l) for l in range(n_levels))
     with _timed('wp_pyramid_c8_kernel', 0, 16.0 * S * n_img):
         check(_L().ynet_tc_rasterize_pyramid_c8(_ptr(template), template.shape[0], template.shape[1], _ptr(coords), n_img,
-                                                n_ch, H, W, n_levels, outs, 8, write_pad, None, _stream()),
+                                                n_ch, H, W, n_levels, outs, 8, write_pad, quad_levels, None, _stream()),
               'tc_rasterize_pyramid_c8')
     _count()
-    return [C8(b, n_ch) for b in bufs]
+    return [C8(b, 4 * n_ch, taps=TAPS_QUAD) if l < quad_levels else C8(b, n_ch) for l, b in enumerate(bufs)]
 
 
 def tc_pad_replicate(a):
@@ -782,18 +805,21 @@ def tc_conv3x3(sources, packed_weight, bias_pad, C_out, relu, pad_out=False):
         arr[i].batch_stride = 0 if (s.N == 1 and N > 1) else s.data.stride(0)
         arr[i].batch_mod = _tc_batch_mod(s, N)
         arr[i].center_only = 1 if s.center else 0
+        arr[i].tap_mask = s.taps
     cp = _pad16(C_out)
     po = 1 if pad_out else 0
     out = torch.empty(N, cp // 8, H + 2 * po, W + 2 * po, 8, dtype=torch.bfloat16, device=sources[0].data.device)
     cin_pad = sum(s.C_pad for s in sources)
     args = (arr, len(sources), N, H, W, _ptr(packed_weight), _ptr(bias_pad), C_out, (1 if relu else 0) | (2 * po),
             _ptr(out), cp)
-    key = (tuple(-s.K_pad if s.center else s.K_pad for s in sources), cp, H, W, min(N, 64), po)
+    key = (tuple(-s.K_pad if s.center else (s.K_pad, s.taps) if s.taps else s.K_pad for s in sources), cp, H, W,
+           min(N, 64), po)
     tune = _tc_tune.get(key)
     if tune is None:
         tune = _tc_autotune(key, args) if (tc_autotune_enabled and not torch.cuda.is_current_stream_capturing()) else 0
-    hoisted = '+P' if any(s.center for s in sources) else ''
-    with _timed('tc_conv3x3_kernel', 2.0 * 9 * sum(s.C for s in sources if not s.center) * C_out * H * W * N,
+    hoisted = ('+P' if any(s.center for s in sources) else '') + ('+Q' if any(s.taps for s in sources) else '')
+    real_c = sum((s.C // 4 if s.taps else s.C) for s in sources if not s.center)     # quad planes store 4 copies
+    with _timed('tc_conv3x3_kernel', 2.0 * 9 * real_c * C_out * H * W * N,
                 2.0 * (cin_pad + cp) * H * W * N, tag=f'{cin_pad}{hoisted}->{cp}@{H}x{W} N={N}'):
         check(_L().ynet_tc_conv3x3(*args, tune, _stream()), 'tc_conv3x3')
     _count()
@@ -858,7 +884,8 @@ def tc_pack_hoisted_weights(weight_oihw, parts):
     """Packed weights of a conv whose sources mix 3x3 inputs and hoisted partial sums.
 
     parts: list in source order of ('conv', (c0, c1)) -- input channels [c0, c1) of ``weight_oihw`` applied as 3x3 --,
-    ('i2c', (c0, c1)) -- the same channels read from an im2col ``center`` source (tc_rasterize_im2col) --
+    ('i2c', (c0, c1)) -- the same channels read from an im2col ``center`` source (tc_rasterize_im2col) --,
+    ('quad', (c0, n)) -- channels [c0, c0 + n) read from 2x2-neighbourhood planes (tc_rasterize_pyramid quad levels) --
     or ('partial', channels) -- a ``center`` source with ``channels`` = pad16(C_out) (hi) or twice that (hi | lo):
     identity on the centre tap."""
     C_out = weight_oihw.shape[0]
@@ -868,6 +895,9 @@ def tc_pack_hoisted_weights(weight_oihw, parts):
         if kind == 'conv':
             c0, c1 = arg
             bufs.append(tc_pack_weights(weight_oihw[:, c0:c1].contiguous(), [c1 - c0]))
+        elif kind == 'quad':      # 2x2-neighbourhood source: (first input channel, channels)
+            c0, n_ch = arg
+            bufs.append(tc_pack_weights(tc_quad_weights(weight_oihw, c0, n_ch), [4 * n_ch]))
         elif kind == 'i2c':       # im2col source: channel c * 9 + kh * 3 + kw <-> weight[:, c0 + c, kh, kw]
             c0, c1 = arg
             w1 = weight_oihw[:, c0:c1].reshape(C_out, (c1 - c0) * 9, 1, 1).contiguous()

@@ -256,6 +256,45 @@ def test_tc_upconv_padded_ring_mma_and_cuda_core(ops, cins, cout, h, w, N, monke
     assert rel_err(got['1'].numpy(), got['0'].numpy()) < 1e-2    # a bf16 ulp or two of the largest values
 
 
+@pytest.mark.parametrize('n_wp,H,W', [(2, 64, 96), (1, 32, 32), (2, 416, 416)])
+def test_tc_quad_waypoint_planes(ops, n_wp, H, W):
+    """2x2-neighbourhood waypoint planes (quad levels): the planes hold map[y+dy][x+dx] (zero outside the image), and a
+    conv over them with the four anchored taps equals the nine-tap conv over the plain planes."""
+    torch.manual_seed(21)
+    n_img, levels = 3, 4
+    tmpl = ops.create_dist_template(max(H, W) * 3, 'cuda')
+    coords = torch.stack([torch.rand(n_img * n_wp) * (W - 1), torch.rand(n_img * n_wp) * (H - 1)], 1).cuda()
+    plain = ops.tc_rasterize_pyramid(tmpl, coords, n_img, n_wp, H, W, levels)
+    quad = ops.tc_rasterize_pyramid(tmpl, coords, n_img, n_wp, H, W, levels, quad_levels=2)
+    for l in range(levels):
+        p, q = plain[l].data[:, 0].float(), quad[l].data[:, 0].float()          # (n_img, h, w, 8)
+        if l >= 2:
+            assert quad[l].taps == 0 and torch.equal(p, q)
+            continue
+        assert quad[l].taps == ops.TAPS_QUAD and quad[l].C == 4 * n_wp
+        padded = F.pad(p[..., :n_wp], (0, 0, 0, 1, 0, 1))                        # zero row / column beyond the image
+        h, w = p.shape[1], p.shape[2]
+        for dy in range(2):
+            for dx in range(2):
+                k = (dy * 2 + dx) * n_wp
+                assert torch.equal(q[..., k:k + n_wp], padded[:, dy:dy + h, dx:dx + w])
+        assert float(q[..., 4 * n_wp:].abs().max()) == 0.0 if 4 * n_wp < 8 else True
+    # conv(cat(x, wp)) through both layouts
+    cx, cout = 16, 32
+    x = bf16_exact(torch.randn(n_img, cx, H, W))
+    wgt = bf16_exact(torch.randn(cout, cx + n_wp, 3, 3) * 0.1).cuda()
+    bias = torch.randn(cout).cuda()
+    a = ops.tc_pack(x.cuda())
+    ref = ops.tc_conv3x3([a, plain[0]], ops.tc_pack_weights(wgt, [cx, n_wp]), bias, cout, True)
+    pk = ops.tc_pack_hoisted_weights(wgt, [('conv', (0, cx)), ('quad', (cx, n_wp))])
+    got = ops.tc_conv3x3([a, quad[0]], pk, bias, cout, True)
+    r, g = ops.tc_unpack(ref).cpu(), ops.tc_unpack(got).cpu()
+    wp_plain = plain[0].data[:, 0, :, :, :n_wp].float().permute(0, 3, 1, 2).cpu()
+    tref = F.relu(F.conv2d(torch.cat([x, wp_plain], 1), wgt.cpu(), bias.cpu(), padding=1))
+    assert rel_err(g.numpy(), tref.numpy()) < 6e-3
+    assert rel_err(g.numpy(), r.numpy()) < 4e-3          # same bf16 products, different accumulation order
+
+
 def test_tc_hoisted_partial_sums_match_direct_conv(ops):
     """Goal-loop hoisting: conv(cat(up, feature, wp)) == conv(cat(up, wp)) + hi/lo partial(feature) via identity taps."""
     torch.manual_seed(11)
