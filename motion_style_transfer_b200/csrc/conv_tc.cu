@@ -259,10 +259,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           uint32_t v[16];
           tmem_ld16(t_row + (uint32_t)(jj * p.n_pad + c0), v);
           float f[16];
+          {
+            // s_bias is 16-byte aligned (barrier block of 70 x 8 bytes after 128-byte-aligned stages): four LDS.128
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            f[k] = __uint_as_float(v[k]) + s_bias[c0 + k];
-            if (p.relu) f[k] = fmaxf(f[k], 0.f);
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const float4 b = b4[k4];
+              f[4 * k4 + 0] = __uint_as_float(v[4 * k4 + 0]) + b.x;
+              f[4 * k4 + 1] = __uint_as_float(v[4 * k4 + 1]) + b.y;
+              f[4 * k4 + 2] = __uint_as_float(v[4 * k4 + 2]) + b.z;
+              f[4 * k4 + 3] = __uint_as_float(v[4 * k4 + 3]) + b.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
           }
           if (EPI == EPI_C8) {
             if (inb) {

@@ -6,6 +6,7 @@ GPU (the reference round-trips them through numpy at evaluate.py:112,251), the p
 loop (147-155) and the per-(goal, agent) CWS loop (172-224) are single batched kernels, and the
 n_goal trajectory-decoder passes (249-266) are stacked along the batch axis.
 """
+import os
 import numpy as np
 import pandas as pd
 import torch
@@ -16,7 +17,8 @@ from .image_utils import HostRng, sampling
 from .kmeans import kmeans_batched
 
 TTST_SAMPLES = 10000          # evaluate.py:138
-MAX_STACKED_PASSES = 256      # agent x goal decoder passes per launch (bounds activation memory)
+# agent x goal decoder passes per launch (bounds activation memory: ~40 MB per pass at 416^2)
+MAX_STACKED_PASSES = int(os.environ.get('YNET_MAX_STACKED_PASSES', '640'))
 
 
 def torch_multivariate_gaussian_heatmap(coordinates, H, W, dist, sigma_factor, ratio, device, rot=False):
