@@ -298,10 +298,19 @@ def main():
                                         cfg['obs'], cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'],
                                         cfg['cwsp'], rng=rng)
         _eager()                  # re-warm the eager allocator pool (graph capture emptied the cache)
-        ops.profile_begin()       # eager pass (not the graph): per-launch CUDA events
-        forecast_batch(model, scene_dev, traj_dev[-1], tmpl, cfg['wps'], cfg['n_goal'], cfg['n_traj'], cfg['obs'],
-                       cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'], cfg['cwsp'], rng=rng)
-        prof = ops.profile_end()
+        # eager passes (not the graph): per-launch CUDA events.  An event pair also spans any host stall between the two
+        # records (allocator growth, lazy module load) while the stream is idle, so the pass runs three times and every
+        # launch keeps its minimum.
+        prof = None
+        for _ in range(3):
+            ops.profile_begin()
+            _eager()
+            cur = ops.profile_end()
+            if prof is None or len(cur) != len(prof):
+                prof = cur
+            else:
+                for a, b in zip(prof, cur):
+                    a['ms'] = min(a['ms'], b['ms'])
         layer_table = prof
         if prof:
             by_kernel = {}

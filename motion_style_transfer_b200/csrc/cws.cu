@@ -60,15 +60,25 @@ __global__ void cws_partial_kernel(const float* __restrict__ sig, int H, int W, 
   const float* src = sig + (size_t)b * S;
   const CwsPrior p = make_prior(wp_in[((size_t)g * B + b) * 2 + 0], wp_in[((size_t)g * B + b) * 2 + 1],
                                 last_obs[2 * b + 0], last_obs[2 * b + 1], length_ratio, sigma_factor[g], ratio, rot);
-  const int per = ceil_div(S, splits);
-  const int i0 = split * per, i1 = min(S, i0 + per);
+  // whole rows per split: the row terms of the quadratic form are hoisted and no pixel index is divided
+  const int rows_per = ceil_div(H, splits);
+  const int r0 = split * rows_per, r1 = min(H, r0 + rows_per);
   float s = 0.f, sx = 0.f, sy = 0.f;
-  for (int t = i0 + lane; t < i1; t += 32) {
-    const int i = t / W, j = t - i * W;
-    const float w = src[t] * prior_value(p, i, j, H, W);
-    s += w;
-    sx = fmaf(w, (float)j, sx);
-    sy = fmaf(w, (float)i, sy);
+  for (int i = r0; i < r1; ++i) {
+    const float v = linspace0n(i, H) - p.my;
+    const float qv = p.t11 * v * v, tv = 2.0f * p.t01 * v;
+    const float* row = src + (size_t)i * W;
+    float rs = 0.f;
+    for (int j = lane; j < W; j += 32) {
+      const float u = linspace0n(j, W) - p.mx;
+      // same operation order as prior_value: t00*u*u + 2*t01*u*v + t11*v*v
+      const float q = p.t00 * u * u + tv * u + qv;
+      const float w = row[j] * __expf(-0.5f * q);
+      rs += w;
+      sx = fmaf(w, (float)j, sx);
+    }
+    s += rs;
+    sy = fmaf(rs, (float)i, sy);
   }
   s = warp_sum(s);
   sx = warp_sum(sx);
@@ -140,15 +150,16 @@ cws_map_kernel(const float* __restrict__ sig, int H, int W, const float* __restr
     dst[t] = (src[t] * (prior_value(p, t / W, t % W, H, W) * inv_k)) / tot;
 }
 
-// a17: one thread per agent (K*T <= a few hundred terms)
+// a17: one warp per agent, lane = sampled future k (each lane keeps the reference's sequential sum over t; the min over
+// k is order independent)
 __global__ void ade_fde_kernel(const float* __restrict__ gt, const float* __restrict__ trajs,
                                const float* __restrict__ wps, int K, int B, int T, int n_wp, float resize,
                                float* __restrict__ ade, float* __restrict__ fde) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= B) return;
   float best_a = 3.4e38f, best_f = 3.4e38f;
   const float gx = gt[((size_t)b * T + T - 1) * 2 + 0], gy = gt[((size_t)b * T + T - 1) * 2 + 1];
-  for (int k = 0; k < K; ++k) {
+  for (int k = lane; k < K; k += 32) {
     float acc = 0.f;
     for (int t = 0; t < T; ++t) {
       const float ex = (gt[((size_t)b * T + t) * 2 + 0] - trajs[(((size_t)k * B + b) * T + t) * 2 + 0]) / resize;
@@ -160,8 +171,15 @@ __global__ void ade_fde_kernel(const float* __restrict__ gt, const float* __rest
     const float fy = (gy - wps[(((size_t)k * B + b) * n_wp + n_wp - 1) * 2 + 1]) / resize;
     best_f = fminf(best_f, sqrtf(fx * fx + fy * fy));
   }
-  ade[b] = best_a;
-  fde[b] = best_f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    best_a = fminf(best_a, __shfl_xor_sync(0xffffffffu, best_a, o));
+    best_f = fminf(best_f, __shfl_xor_sync(0xffffffffu, best_f, o));
+  }
+  if (lane == 0) {
+    ade[b] = best_a;
+    fde[b] = best_f;
+  }
 }
 
 constexpr int kCwsSplits = 8;
@@ -210,8 +228,8 @@ int ynet_ade_fde(const float* gt, const float* trajs, const float* wps, int32_t 
   YNET_CHECK_ARG(gt && trajs && wps && ade && fde, "null pointer");
   YNET_CHECK_ARG(K > 0 && B >= 0 && T > 0 && n_wp > 0 && resize_factor > 0.f, "bad shape");
   if (B == 0) return YNET_OK;
-  ade_fde_kernel<<<ceil_div(B, 128), 128, 0, as_stream(stream)>>>(gt, trajs, wps, K, B, T, n_wp, resize_factor, ade,
-                                                                  fde);
+  ade_fde_kernel<<<ceil_div(B, 4), 128, 0, as_stream(stream)>>>(gt, trajs, wps, K, B, T, n_wp, resize_factor, ade,
+                                                                fde);
   YNET_LAUNCH_CHECK();
   return YNET_OK;
 }

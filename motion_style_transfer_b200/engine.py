@@ -290,6 +290,24 @@ class YNetEngineTC(YNetEngine):
         packed, bias = self._tc_params(decoder.predictor, f'{key}.predictor', [x.C])
         return ops.tc_conv1x1_f32(x, packed, bias, decoder.predictor.weight.shape[0])
 
+    def decoder_logits_subset(self, decoder, key, features, channels):
+        """decoder_logits restricted to the predictor rows ``channels``: evaluate() only ever reads the waypoint
+        channels of the goal map (evaluate.py:128-131,142), so the other pred_len - n_wp float32 planes are not written.
+        The kept channels are bit-identical to the full map (same K order per output channel)."""
+        x = self.decoder_trunk(decoder, key, features)
+        p = decoder.predictor
+        channels = tuple(int(c) % p.weight.shape[0] for c in channels)
+        ver = (p.weight._version, p.weight.data_ptr(), p.bias._version, channels, x.C)
+        hit = self._wcache.get(f'{key}.predictor#subset')
+        if hit is None or hit[0] != ver:
+            idx = torch.tensor(channels, device=p.weight.device)
+            w = p.weight.detach().index_select(0, idx).contiguous()
+            bias = torch.zeros(ops._pad16(len(channels)), dtype=torch.float32, device=w.device)
+            bias[:len(channels)] = p.bias.detach().index_select(0, idx)
+            hit = (ver, ops.tc_pack_weights(w, [x.C]), bias)
+            self._wcache[f'{key}.predictor#subset'] = hit
+        return ops.tc_conv1x1_f32(x, hit[1], hit[2], len(channels))
+
     # Goal-loop hoisting (SURVEY 7.6).  Every trajectory-decoder input is cat(upsampled x, encoder feature, waypoint
     # pyramid) (ynet.py:466, evaluate.py:259); the encoder feature is the same for the n_goal passes of an agent, so its
     # share of center.0 / decoder.i.0 is computed once per agent (raw fp32 sums kept as a bf16 hi + lo pair) and

@@ -95,7 +95,13 @@ def forecast_batch(model, scene_image, trajectory, input_template, waypoints, n_
         observed_map = ops.rasterize_patches(input_template, observed, H, W).view(B, obs_len, H, W)
         gt_future = trajectory[:, obs_len:].contiguous()
         feats = model.pred_features(scene_image, observed_map)
-        pred_goal_map = model.pred_goal(feats)
+        subset = getattr(model.engine, 'decoder_logits_subset', None)
+        if subset is not None and not want_maps:
+            # only the waypoint channels of the goal map are ever read (evaluate.py:128-131,142): skip the others
+            pred_goal_map = subset(model.goal_decoder, 'goal_decoder', feats, waypoints)       # (B, n_wp, H, W)
+            waypoints = list(range(n_wp))
+        else:
+            pred_goal_map = model.pred_goal(feats)
         sig = [ops.sigmoid_select(pred_goal_map, [w], temperature) for w in waypoints]   # n_wp x (B, 1, H, W)
 
         if use_TTST:
