@@ -48,6 +48,19 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, src='fallback')
 
 
+def load_traffic(kernel, agents):
+    """Average DRAM bytes per launch of `kernel` from the committed ncu pass of this command
+    (profiles/ncu_traffic_r01.json, tools/ncu_traffic.py); None when the capture was made at another batch size."""
+    p = os.path.join(ROOT, 'profiles', 'ncu_traffic_r01.json')
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    k = d.get('kernels', {}).get(kernel)
+    if d.get('agents_per_step') != agents or not k or not k.get('launches'):
+        return None
+    return k['dram_bytes'] / k['launches']
+
+
 def build_model_state(cfg, seed=0):
     """Random-init Y-Net + MoSA r=1 on encoder stages 0-4 (reference default init, LoRA B ~ N(0, 0.02),
     predictors x50 so that the heat maps are peaky: SURVEY 8d)."""
@@ -325,13 +338,15 @@ def main():
             if top['flops'] > 0:
                 ach = top['flops'] / (top['ms'] / 1000) / 1e12
                 roofline = dict(bound='tensor', kernel=top_name, achieved=ach, peak=peaks['bf16_tflops'],
-                                unit='TFLOP/s', frac=ach / peaks['bf16_tflops'], traffic=None,
+                                unit='TFLOP/s', frac=ach / peaks['bf16_tflops'], traffic=load_traffic(top_name, B),
+                                algorithmic_bytes_per_launch=top['bytes'] / top['n'],
+                                hbm_gbs=top['bytes'] / (top['ms'] / 1000) / 1e9, hbm_peak_gbs=peaks['hbm_gbs'],
                                 launches=top['n'], avg_launch_ms=top['ms'] / top['n'],
                                 share_of_step=top['ms'] / step_ms, peak_source=peaks['src'] + ' (burst bf16 cuBLAS)')
             else:
                 ach = top['bytes'] / (top['ms'] / 1000) / 1e9
                 roofline = dict(bound='hbm', kernel=top_name, achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s',
-                                frac=ach / peaks['hbm_gbs'], traffic=None, launches=top['n'],
+                                frac=ach / peaks['hbm_gbs'], traffic=load_traffic(top_name, B), launches=top['n'],
                                 avg_launch_ms=top['ms'] / top['n'], share_of_step=top['ms'] / step_ms,
                                 peak_source=peaks['src'])
         if args.profile_layers:

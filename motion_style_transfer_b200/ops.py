@@ -819,8 +819,10 @@ def tc_conv3x3(sources, packed_weight, bias_pad, C_out, relu, pad_out=False):
         tune = _tc_autotune(key, args) if (tc_autotune_enabled and not torch.cuda.is_current_stream_capturing()) else 0
     hoisted = ('+P' if any(s.center for s in sources) else '') + ('+Q' if any(s.taps for s in sources) else '')
     real_c = sum((s.C // 4 if s.taps else s.C) for s in sources if not s.center)     # quad planes store 4 copies
+    # algorithmic bytes: every DISTINCT source image read once (a repeated / broadcast source is shared by its images)
+    in_bytes = sum(2.0 * s.C_pad * min(s.data.shape[0], N) for s in sources) * H * W
     with _timed('tc_conv3x3_kernel', 2.0 * 9 * real_c * C_out * H * W * N,
-                2.0 * (cin_pad + cp) * H * W * N, tag=f'{cin_pad}{hoisted}->{cp}@{H}x{W} N={N}'):
+                in_bytes + 2.0 * cp * H * W * N, tag=f'{cin_pad}{hoisted}->{cp}@{H}x{W} N={N}'):
         check(_L().ynet_tc_conv3x3(*args, tune, _stream()), 'tc_conv3x3')
     _count()
     return C8(out, C_out, 1, False, po)
