@@ -64,6 +64,7 @@ struct TcParams {
   float4* partial;                // EPI 2: soft-argmax partials (m, s, sx, sy) [(n * c_out + c) * gridDim.x + cta]
   int c_out;                      // real output channels
   int* err;
+  int dbg;                        // profiling aid (YNET_TC_DBG): 1 = epilogue skips the global stores, 2 = skips everything
 };
 
 constexpr int EPI_C8 = 0, EPI_NCHW_F32 = 1, EPI_UP2 = 3, EPI_HILO = 4, EPI_PRED = 5;
@@ -254,7 +255,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 #pragma unroll
       for (int jj = 0; jj < J; ++jj) {
         const int x = xb + 8 * jj;
-        const bool inb = (y < p.H) && (x < p.W);
+        const bool inb = (y < p.H) && (x < p.W) && p.dbg == 0;
+        if (p.dbg == 2) continue;
         for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(t_row + (uint32_t)(jj * p.n_pad + c0), v);
@@ -1676,6 +1678,7 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
   p.out_f32 = out.f32;
   p.partial = out.partial;
   p.err = nullptr;
+  if (const char* e = getenv("YNET_TC_DBG")) p.dbg = atoi(e);
 
   const int wblk = taps * 2 * C_out_pad * 16;
   const long long wall = w_total;
