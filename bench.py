@@ -304,7 +304,7 @@ def main():
     d2h = 2 * B * 4
 
     # ---- roofline of the dominant kernel: per-launch CUDA-event timing of one extra step -----------------
-    roofline, layer_table = None, None
+    roofline, layer_table, kernel_table = None, None, []
     if rank == 0 and not args.no_roofline:
         peaks = load_peaks()
         _eager = lambda: forecast_batch(model, scene_dev, traj_dev[-1], tmpl, cfg['wps'], cfg['n_goal'], cfg['n_traj'],
@@ -349,6 +349,16 @@ def main():
                                 frac=ach / peaks['hbm_gbs'], traffic=load_traffic(top_name, B), launches=top['n'],
                                 avg_launch_ms=top['ms'] / top['n'], share_of_step=top['ms'] / step_ms,
                                 peak_source=peaks['src'])
+        if prof:
+            # every kernel class of the step against its own roofline: convs vs the tensor peak, the
+            # rasterise / soft-argmax / sampling / CWS kernels vs the measured HBM copy bandwidth (algorithmic bytes)
+            for name, k in sorted(by_kernel.items(), key=lambda kv: -kv[1]['ms'])[:10]:
+                row = dict(kernel=name, launches=k['n'], ms=k['ms'], share_of_step=k['ms'] / step_ms)
+                if k['flops'] > 0:
+                    row.update(tflops=k['flops'] / k['ms'] / 1e9, tensor_frac=k['flops'] / k['ms'] / 1e9 / peaks['bf16_tflops'])
+                if k['bytes'] > 0:
+                    row.update(hbm_gbs=k['bytes'] / k['ms'] / 1e6, hbm_frac=k['bytes'] / k['ms'] / 1e6 / peaks['hbm_gbs'])
+                kernel_table.append(row)
         if args.profile_layers:
             with open(args.profile_layers, 'w') as f:
                 json.dump(dict(step_ms=sum(p['ms'] for p in prof), launches=prof), f, indent=1)
@@ -384,6 +394,7 @@ def main():
             'e2e': {'value': e2e_value, 'unit': 'agent-trajectories/s', 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+            'kernels': kernel_table,
             'diag': {'step_ms': step_list, 'host_issue_ms': host_ms, 'mem': mem_diag, 'kmeans_max_iters': km_diag,
                      'e2e_step_ms': [a.elapsed_time(b) for a, b in zip([e2] + e2e_marks[:-1], e2e_marks)],
                      'e2e_kmeans_max_iters': e2e_km},

@@ -280,15 +280,25 @@ wp_pyramid_quad_c8_kernel(const float* __restrict__ tmpl, int th, int tw, const 
     const bool bad = (yl < 0) | (xl < 0) | (yl + H > th) | (xl + W > tw);
     if (bad && oob != nullptr && t == 0 && blockIdx.x == 0 && blockIdx.y == 0) atomicExch(oob, 1);
     // 34 x 34 region (block + two pixels of apron): a warp per row, lanes 0-1 also fetch the two apron columns
-    const int lane = t & 31;
-    for (int ry = t >> 5; ry < 34; ry += 8) {
-      const int gy = ty0 + ry;
+    // all ten loads of a thread are issued before the first shared-memory store (one L2 round trip per block)
+    const int lane = t & 31, wrp = t >> 5;
+    float v[5], va[5];
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      const int ry = wrp + 8 * it, gy = ty0 + ry;
       const int sy = min(max(yl + gy, 0), th - 1);
       const float* row = tmpl + (size_t)sy * tw;
-      s0[c][ry][lane] = (gy < H) ? __ldg(row + min(max(xl + tx0 + lane, 0), tw - 1)) : 0.f;
-      if (lane < 2) {
-        const int gx = tx0 + 32 + lane;
-        s0[c][ry][32 + lane] = (gy < H && gx < W) ? __ldg(row + min(max(xl + gx, 0), tw - 1)) : 0.f;
+      const bool rok = ry < 34 && gy < H;
+      const int gx = tx0 + 32 + lane;
+      v[it] = rok ? __ldg(row + min(max(xl + tx0 + lane, 0), tw - 1)) : 0.f;
+      va[it] = (rok && lane < 2 && gx < W) ? __ldg(row + min(max(xl + gx, 0), tw - 1)) : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      const int ry = wrp + 8 * it;
+      if (ry < 34) {
+        s0[c][ry][lane] = v[it];
+        if (lane < 2) s0[c][ry][32 + lane] = va[it];
       }
     }
   }
@@ -315,11 +325,20 @@ wp_pyramid_quad_c8_kernel(const float* __restrict__ tmpl, int th, int tw, const 
     }
   }
   if (n_levels <= 1) return;
-  for (int idx = t; idx < NCH * 17 * 17; idx += 256) {   // level 1 incl. one pooled pixel of apron
-    const int c = idx / 289, r = idx - c * 289;
-    const int py = r / 17, px = r - py * 17;
-    s1[c][py][px] = 0.25f * ((s0[c][2 * py][2 * px] + s0[c][2 * py][2 * px + 1]) +
-                             (s0[c][2 * py + 1][2 * px] + s0[c][2 * py + 1][2 * px + 1]));
+  // level 1 incl. one pooled pixel of apron: 17 x 17 per channel; threads 0..255 take the 16 x 16 core, the next
+  // 33 * NCH (< 256) the apron row and column
+  {
+    const int py = t >> 4, px = t & 15;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+      s1[c][py][px] = 0.25f * ((s0[c][2 * py][2 * px] + s0[c][2 * py][2 * px + 1]) +
+                               (s0[c][2 * py + 1][2 * px] + s0[c][2 * py + 1][2 * px + 1]));
+    if (t < 33 * NCH) {
+      const int c = t / 33, r = t - c * 33;
+      const int ay = r < 17 ? 16 : r - 17, ax = r < 17 ? r : 16;      // row 16 (17 entries), then column 16 (16 entries)
+      s1[c][ay][ax] = 0.25f * ((s0[c][2 * ay][2 * ax] + s0[c][2 * ay][2 * ax + 1]) +
+                               (s0[c][2 * ay + 1][2 * ax] + s0[c][2 * ay + 1][2 * ax + 1]));
+    }
   }
   __syncthreads();
   {
