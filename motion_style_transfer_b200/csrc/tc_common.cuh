@@ -9,6 +9,7 @@
 namespace ynet {
 
 constexpr unsigned TC_SPIN_LIMIT = 4u * 1000u * 1000u;             // bounded waits: trap instead of hanging
+constexpr uint32_t TC_WAIT_HINT_NS = 2000u;                       // mbarrier.try_wait suspend-time hint: the waiting warp sleeps in hardware instead of re-issuing the poll
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -28,10 +29,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(TC_WAIT_HINT_NS)
         : "memory");
     if (done) break;
     if (++spins > TC_SPIN_LIMIT) {  // a protocol bug must not hang the GPU
