@@ -257,6 +257,42 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
         const int x = xb + 8 * jj;
         const bool inb = (y < p.H) && (x < p.W) && p.dbg == 0;
         if (p.dbg == 2) continue;
+        if (EPI == EPI_UP2) {
+          // phase-decomposed bilinear-x2 + conv: the four phase groups of a low-resolution pixel (y, x) land on the
+          // high-resolution pixels (2y + a, 2x + b).  The two b phases of one row are ADJACENT pixels of the C8 plane:
+          // both are fetched and written as one 32-byte store (full sectors instead of two half-filled ones).
+          const int cp = p.n_pad >> 2;                 // padded C_out of one phase (multiple of 16)
+          for (int a = 0; a < 2; ++a) {
+            for (int o0 = 0; o0 < cp; o0 += 16) {
+              uint32_t v0[16], v1[16];
+              tmem_ld16_nowait(t_row + (uint32_t)(jj * p.n_pad + (2 * a) * cp + o0), v0);
+              tmem_ld16_nowait(t_row + (uint32_t)(jj * p.n_pad + (2 * a + 1) * cp + o0), v1);
+              tmem_ld_wait();
+              if (inb) {
+                const float4* b0 = reinterpret_cast<const float4*>(s_bias + (2 * a) * cp + o0);
+                const float4* b1 = reinterpret_cast<const float4*>(s_bias + (2 * a + 1) * cp + o0);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const float4 ba = b0[2 * h], bb = b0[2 * h + 1], bc = b1[2 * h], bd = b1[2 * h + 1];
+                  uint32_t o[8];
+                  o[0] = pack_bf16(__uint_as_float(v0[8 * h + 0]) + ba.x, __uint_as_float(v0[8 * h + 1]) + ba.y);
+                  o[1] = pack_bf16(__uint_as_float(v0[8 * h + 2]) + ba.z, __uint_as_float(v0[8 * h + 3]) + ba.w);
+                  o[2] = pack_bf16(__uint_as_float(v0[8 * h + 4]) + bb.x, __uint_as_float(v0[8 * h + 5]) + bb.y);
+                  o[3] = pack_bf16(__uint_as_float(v0[8 * h + 6]) + bb.z, __uint_as_float(v0[8 * h + 7]) + bb.w);
+                  o[4] = pack_bf16(__uint_as_float(v1[8 * h + 0]) + bc.x, __uint_as_float(v1[8 * h + 1]) + bc.y);
+                  o[5] = pack_bf16(__uint_as_float(v1[8 * h + 2]) + bc.z, __uint_as_float(v1[8 * h + 3]) + bc.w);
+                  o[6] = pack_bf16(__uint_as_float(v1[8 * h + 4]) + bd.x, __uint_as_float(v1[8 * h + 5]) + bd.y);
+                  o[7] = pack_bf16(__uint_as_float(v1[8 * h + 6]) + bd.z, __uint_as_float(v1[8 * h + 7]) + bd.w);
+                  const int chunk = (o0 >> 3) + h;
+                  __nv_bfloat16* dst =
+                      p.out + ((((size_t)n * (cp >> 3) + chunk) * (2 * p.H) + (2 * y + a)) * (size_t)(2 * p.W) + 2 * x) * 8;
+                  st_global_v8(dst, o);
+                }
+              }
+            }
+          }
+          continue;
+        }
         for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(t_row + (uint32_t)(jj * p.n_pad + c0), v);
