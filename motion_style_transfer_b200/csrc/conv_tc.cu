@@ -267,7 +267,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
               uint32_t v0[16], v1[16];
               tmem_ld16_nowait(t_row + (uint32_t)(jj * p.n_pad + (2 * a) * cp + o0), v0);
               tmem_ld16_nowait(t_row + (uint32_t)(jj * p.n_pad + (2 * a + 1) * cp + o0), v1);
-              tmem_ld_wait();
+              tmem_ld_wait(v0);
+              tmem_ld_wait(v1);
               if (inb) {
                 const float4* b0 = reinterpret_cast<const float4*>(s_bias + (2 * a) * cp + o0);
                 const float4* b1 = reinterpret_cast<const float4*>(s_bias + (2 * a + 1) * cp + o0);
@@ -293,9 +294,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           }
           continue;
         }
+        uint32_t v[16], vn[16];
+        tmem_ld16(t_row + (uint32_t)(jj * p.n_pad), v);
         for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(t_row + (uint32_t)(jj * p.n_pad + c0), v);
+          // the next 16 columns are in flight while these are converted and stored
+          const bool more = c0 + 16 < p.n_pad;
+          if (more) tmem_ld16_nowait(t_row + (uint32_t)(jj * p.n_pad + c0 + 16), vn);
           float f[16];
           {
             // s_bias is 16-byte aligned (barrier block of 70 x 8 bytes after 128-byte-aligned stages): four LDS.128
@@ -399,6 +403,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
               for (int k = 0; k < 16; ++k)
                 if (c0 + k < p.c_out) p.out_f32[(((size_t)n * p.c_out + c0 + k) * p.H + y) * p.W + x] = f[k];
             }
+          }
+          if (more) {
+            tmem_ld_wait(vn);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = vn[k];
           }
         }
       }
