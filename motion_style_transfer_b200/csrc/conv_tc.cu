@@ -1337,6 +1337,32 @@ upconv_ringfix_mma_kernel(UpBorderSrc src, int N, int h, int w, const uint2* __r
     const bool row_edge = pair == 0;
     const int L = row_edge ? W2 : H2;
     const int tiles = (L + 15) >> 4;
+    // ring pixel (rows g / g + 8 of tile `tile2`) this thread corrects; nullptr beyond the edge
+    const int g = lane >> 2, tq = lane & 3;
+    auto ring_ptr = [&](int tile2, int half) -> __nv_bfloat162* {
+      const int side = tile2 >= tiles ? 1 : 0;
+      const int q = ((tile2 - side * tiles) << 4) + g + half * 8;
+      if (q >= L) return nullptr;
+      const int v = row_edge ? (side ? H2 - 1 : 0) : q;
+      const int u = row_edge ? q : (side ? W2 - 1 : 0);
+      return reinterpret_cast<__nv_bfloat162*>(out + (((size_t)n * NT * H2 + v) * (size_t)W2 + u) * 8 + 2 * tq);
+    };
+    constexpr int RB = NT >= 8 ? 2 : 4;          // tiles whose ring pixels are in flight per warp
+    __nv_bfloat162 cur[RB][2][NT];
+    auto prefetch = [&](int first) {
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int tile2 = first + i * (RFM_THREADS / 32);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const __nv_bfloat162* src = (tile2 < 2 * tiles) ? ring_ptr(tile2, half) : nullptr;
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt)
+            if (src != nullptr) cur[i][half][nt] = src[(size_t)nt * H2 * W2 * 4];
+        }
+      }
+    };
+    prefetch(warp);
     // (1) the two outside lines: position p <-> hi-res coordinate p - 1 along the edge
     const int items = gm.line_rows * chunks16;
 #pragma unroll 4
@@ -1373,54 +1399,47 @@ upconv_ringfix_mma_kernel(UpBorderSrc src, int N, int h, int w, const uint2* __r
       *reinterpret_cast<uint4*>(rf_smem + (size_t)side * gm.line_bytes + (size_t)pos * gm.pitch + chunk * 16) = val;
     }
     __syncthreads();
-    // (3) 16 ring pixels per warp step
+    // (3) 16 ring pixels per warp step.  The ring pixels a thread corrects (rows g, g + 8 of its tiles; channels 2 tq,
+    // 2 tq + 1 of every 8-channel tile) do not depend on the line: the first RB tiles of every warp were fetched before
+    // the interpolation stage above, so their HBM latency is hidden behind it.
     const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lcol = (lane >> 4) * 8;
-    for (int tile2 = warp; tile2 < 2 * tiles; tile2 += RFM_THREADS / 32) {
-      const int side = tile2 >= tiles ? 1 : 0;
-      const int q0 = (tile2 - side * tiles) << 4;
-      const int edge = 2 * pair + side;       // 0 top, 1 bottom, 2 left, 3 right
-      const unsigned char* line = rf_smem + (size_t)side * gm.line_bytes;
-      const uint2* bf = frag + (size_t)edge * ksteps * NT * 32 + lane;
-      // the ring pixels this thread corrects (rows g, g + 8; channels 2 tq, 2 tq + 1 of every 8-channel tile): fetch
-      // them before the K loop so that the HBM latency hides behind the MMAs
-      const int g = lane >> 2, tq = lane & 3;
-      __nv_bfloat162* dst[2];
-      __nv_bfloat162 cur[2][NT];
+    for (int first = warp; first < 2 * tiles; first += RB * (RFM_THREADS / 32)) {
+      if (first != warp) prefetch(first);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int q = q0 + g + half * 8;
-        const int v = row_edge ? (side ? H2 - 1 : 0) : q;
-        const int u = row_edge ? q : (side ? W2 - 1 : 0);
-        dst[half] = (q < L) ? reinterpret_cast<__nv_bfloat162*>(out + (((size_t)n * NT * H2 + v) * (size_t)W2 + u) * 8 + 2 * tq)
-                            : nullptr;
+      for (int i = 0; i < RB; ++i) {
+        const int tile2 = first + i * (RFM_THREADS / 32);
+        if (tile2 >= 2 * tiles) break;
+        const int side = tile2 >= tiles ? 1 : 0;
+        const int q0 = (tile2 - side * tiles) << 4;
+        const int edge = 2 * pair + side;       // 0 top, 1 bottom, 2 left, 3 right
+        const unsigned char* line = rf_smem + (size_t)side * gm.line_bytes;
+        const uint2* bf = frag + (size_t)edge * ksteps * NT * 32 + lane;
+        float acc[NT][4];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-          if (dst[half] != nullptr) cur[half][nt] = dst[half][(size_t)nt * H2 * W2 * 4];
-      }
-      float acc[NT][4];
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 #pragma unroll 2
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const int t = ks / ksteps_per_tap, c0 = (ks - t * ksteps_per_tap) << 4;
-        uint32_t a[4];
-        ldmatrix_x4(smem_u32(line + (size_t)(q0 + lrow + t) * gm.pitch + (c0 + lcol) * 2), a);
-        uint2 b[NT];
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int t = ks / ksteps_per_tap, c0 = (ks - t * ksteps_per_tap) << 4;
+          uint32_t a[4];
+          ldmatrix_x4(smem_u32(line + (size_t)(q0 + lrow + t) * gm.pitch + (c0 + lcol) * 2), a);
+          uint2 b[NT];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) b[nt] = __ldg(bf + (size_t)(ks * NT + nt) * 32);
+          for (int nt = 0; nt < NT; ++nt) b[nt] = __ldg(bf + (size_t)(ks * NT + nt) * 32);
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma_bf16_16816(acc[nt], a, b[nt].x, b[nt].y);
-      }
-      // (4) out -= correction
+          for (int nt = 0; nt < NT; ++nt) mma_bf16_16816(acc[nt], a, b[nt].x, b[nt].y);
+        }
+        // (4) out -= correction
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        if (dst[half] != nullptr) {
+        for (int half = 0; half < 2; ++half) {
+          __nv_bfloat162* dst = ring_ptr(tile2, half);
+          if (dst != nullptr) {
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt) {
-            float2 f = __bfloat1622float2(cur[half][nt]);
-            f.x -= acc[nt][half * 2 + 0];
-            f.y -= acc[nt][half * 2 + 1];
-            dst[half][(size_t)nt * H2 * W2 * 4] = __floats2bfloat162_rn(f.x, f.y);
+            for (int nt = 0; nt < NT; ++nt) {
+              float2 f = __bfloat1622float2(cur[i][half][nt]);
+              f.x -= acc[nt][half * 2 + 0];
+              f.y -= acc[nt][half * 2 + 1];
+              dst[(size_t)nt * H2 * W2 * 4] = __floats2bfloat162_rn(f.x, f.y);
+            }
           }
         }
       }
