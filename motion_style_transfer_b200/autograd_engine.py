@@ -9,7 +9,7 @@ projection (dA = s B^T dM, dB = s dM A^T) are CUDA kernels.
 import torch
 
 from . import ops
-from .engine import ChannelCat, _parts
+from .engine import ChannelCat, _parts, _parallel_as_3x3
 from .ops import SRC_DIRECT, SRC_POOL2, SRC_UP2
 
 
@@ -136,7 +136,15 @@ class BCEWithLogitsLoss(torch.nn.Module):
 def _conv(module, sources, relu, H, W):
     tensors = [t for t, _ in sources]
     modes = tuple(m for _, m in sources)
-    return Conv3x3Fn.apply(module.weight, module.bias, getattr(module, 'lora_A', None), getattr(module, 'lora_B', None),
+    weight = module.weight
+    if hasattr(module, 'serial_layer'):
+        raise NotImplementedError('serial adapters (AdapterLayer) normalise with batch statistics in training mode: '
+                                  'fine-tuning them is outside the B200 hot path')
+    if hasattr(module, 'parallel_layer'):
+        # AdapterLayer, parallel (ynet.py:121-130): conv(x, W) + sum_k conv_k(x, W_k) = conv(x, W + sum_k pad(W_k)); the
+        # weight-space sum is differentiable, so dW_k falls out of the conv's wgrad kernel through autograd
+        weight = weight + _parallel_as_3x3(module.parallel_layer, differentiable=True)
+    return Conv3x3Fn.apply(weight, module.bias, getattr(module, 'lora_A', None), getattr(module, 'lora_B', None),
                            relu, modes, H, W, *tensors)
 
 
@@ -171,6 +179,9 @@ def pred_features(model, scene_map, motion_map):
         mf = _run_stages(enc.motion_stages, motion)
         feats = [ChannelCat((a, b)) for a, b in zip(sf, mf)]
         return feats + _run_stages(enc.fusion_stages, list(feats[-1]))
+    if getattr(enc, 'adapters', None) is not None:
+        raise NotImplementedError('fine-tuning the block-level serial / parallel adapters of YNetEncoderB is outside the '
+                                  'B200 hot path (inference is supported)')
     return _run_stages(enc.stages, scene + motion)
 
 

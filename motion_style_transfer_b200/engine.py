@@ -48,6 +48,87 @@ def _parts(x):
     return out
 
 
+# ---- serial / parallel adapter baselines (ynet.py:15-131, 237-283): weight-space arithmetic ---------------------------
+# Tiny tensors (<= C_out x C_in x 9 floats), computed once per weight version and cached by the engines.
+
+def _module_version(module):
+    """Changes whenever a parameter or buffer of ``module`` is written (BatchNorm running statistics included)."""
+    return tuple((t._version, t.data_ptr()) for t in list(module.parameters()) + list(module.buffers()))
+
+
+def _bn_affine(bn):
+    """Eval-mode BatchNorm2d as y = a * x + b per channel."""
+    if bn.training:
+        raise NotImplementedError('serial adapters normalise with batch statistics in training mode: fine-tuning them is '
+                                  'outside the B200 hot path (inference folds the running statistics)')
+    a = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+    return a, bn.bias.detach() - a * bn.running_mean
+
+
+def _parallel_as_3x3(parallel_layer, differentiable=False):
+    """Sum of the adapter's k x k convs (k in {1, 3}, stride 1, no bias) as ONE (C_out, C_in, 3, 3) weight."""
+    layers = list(parallel_layer) if isinstance(parallel_layer, torch.nn.ModuleList) else [parallel_layer]
+    total = None
+    for conv in layers:
+        k = conv.weight.shape[-1]
+        if k not in (1, 3) or conv.stride != (1, 1) or conv.bias is not None:
+            raise NotImplementedError(f'parallel adapter {k}x{k} / stride {conv.stride} / bias does not fold into a 3x3 conv')
+        w = conv.weight if differentiable else conv.weight.detach()
+        if k == 1:
+            w = torch.nn.functional.pad(w, (1, 1, 1, 1))
+        total = w if total is None else total + w
+    return total
+
+
+def _serial_map(serial_layer):
+    """x + conv1x1(BN(x)) = M x + c  (eval mode): M = I + S diag(a), c = S b."""
+    a, b = _bn_affine(serial_layer[0])
+    conv = serial_layer[1]
+    S = conv.weight.detach()[:, :, 0, 0]
+    M = torch.eye(S.shape[0], device=S.device, dtype=S.dtype) + S * a[None, :]
+    c = S @ b
+    if conv.bias is not None:
+        c = c + conv.bias.detach()
+    return M, c
+
+
+def fold_adapter_layer(module, w, b):
+    """Effective (weight, bias) of an AdapterLayer (ynet.py:117-131) in inference: the conv it decorates with the
+    adapter folded in.  parallel: W + sum_k pad(W_k); serial: M (W x + b) + c."""
+    if hasattr(module, 'parallel_layer'):
+        w = w + _parallel_as_3x3(module.parallel_layer)
+    if hasattr(module, 'serial_layer'):
+        M, c = _serial_map(module.serial_layer)
+        w = torch.einsum('oc,cikl->oikl', M, w)
+        b = c if b is None else M @ b + c
+    return w.contiguous(), (None if b is None else b.contiguous())
+
+
+def _identity_3x3(C, device, dtype=torch.float32):
+    w = torch.zeros(C, C, 3, 3, dtype=dtype, device=device)
+    idx = torch.arange(C, device=device)
+    w[idx, idx, 1, 1] = 1.0
+    return w
+
+
+def block_adapter_weights(adapter, C_out):
+    """One extra conv launch per adapted stage of YNetEncoderB (ynet.py:258-283), as (weight, bias, needs_input):
+    serial  : out = M y + c                      -> conv3x3([y]) with M on the centre tap;
+    parallel: out = y + sum_k conv_k(stage input) -> conv3x3([y, stage input]) with [identity | W_p]."""
+    dev = next(adapter.parameters()).device
+    if hasattr(adapter, 'serial_layer'):
+        M, c = _serial_map(adapter.serial_layer)
+        w = torch.zeros(C_out, C_out, 3, 3, dtype=M.dtype, device=dev)
+        w[:, :, 1, 1] = M
+        return w, c.contiguous(), False
+    wp = _parallel_as_3x3(adapter.parallel_layer)
+    return torch.cat([_identity_3x3(C_out, dev, wp.dtype), wp], dim=1).contiguous(), None, True
+
+
+def _is_adapter_layer(module):
+    return hasattr(module, 'adapter_name') and (hasattr(module, 'parallel_layer') or hasattr(module, 'serial_layer'))
+
+
 class YNetEngine:
     def __init__(self, model, backend='fp32'):
         self.model = model
@@ -65,13 +146,16 @@ class YNetEngine:
         Bm = getattr(module, 'lora_B', None)
         ver = (module.weight._version, module.weight.data_ptr(),
                None if A is None else (A._version, A.data_ptr()),
-               None if Bm is None else (Bm._version, Bm.data_ptr()))
+               None if Bm is None else (Bm._version, Bm.data_ptr()),
+               _module_version(module) if _is_adapter_layer(module) else None)
         hit = self._wcache.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1], hit[2]
         w = module.weight.detach()
-        packed = ops.lora_fold(w, None if A is None else A.detach(), None if Bm is None else Bm.detach(), packed=True)
         bias = None if module.bias is None else module.bias.detach()
+        if _is_adapter_layer(module):
+            w, bias = fold_adapter_layer(module, w, bias)
+        packed = ops.lora_fold(w, None if A is None else A.detach(), None if Bm is None else Bm.detach(), packed=True)
         self._wcache[key] = (ver, packed, bias)
         return packed, bias
 
@@ -81,11 +165,23 @@ class YNetEngine:
         return ops.conv3x3_f32(sources, packed, bias, relu, N, H, W)
 
     # ---------------------------------------------------------------- encoder
-    def _run_stages(self, stages, key, x_parts, first_mode):
+    def _block_adapter(self, adapter, key, y, stage_inputs, H, W):
+        """AdapterBlock of YNetEncoderB on a stage output ``y`` (fp32 engine): one extra conv launch."""
+        ver = _module_version(adapter)
+        hit = self._wcache.get(key)
+        if hit is None or hit[0] != ver:
+            w, bias, needs_input = block_adapter_weights(adapter, y.shape[1])
+            hit = (ver, ops.lora_fold(w, None, None, packed=True), bias, needs_input)
+            self._wcache[key] = hit
+        srcs = [(y, SRC_DIRECT)] + (list(stage_inputs) if hit[3] else [])
+        return ops.conv3x3_f32(srcs, hit[1], hit[2], False, max(t.shape[0] for t, _ in srcs), H, W)
+
+    def _run_stages(self, stages, key, x_parts, first_mode, adapters=None, position=()):
         """Walk an nn.ModuleList of Sequential stages ([conv,relu] | [pool,conv,relu,conv,relu] | [pool])."""
         feats = []
         cur = x_parts
         mode = first_mode
+        position = list(position)
         for si, stage in enumerate(stages):
             mods = list(stage)
             convs = [(j, m) for j, m in enumerate(mods) if isinstance(m, torch.nn.Conv2d)]
@@ -101,10 +197,14 @@ class YNetEngine:
                 cur = [y]
                 continue
             m_in = SRC_POOL2 if has_pool else mode
+            stage_inputs = [(t, m_in) for t in cur]
             for ci, (j, conv) in enumerate(convs):
                 srcs = [(t, m_in if ci == 0 else SRC_DIRECT) for t in cur]
                 y = self._conv(conv, f'{key}.{si}.{j}', srcs, True, H, W)
                 cur = [y]
+            if adapters is not None and si in position:
+                ai = position.index(si)
+                cur = [self._block_adapter(adapters[ai], f'{key}.adapters.{ai}', cur[0], stage_inputs, H, W)]
             feats.append(cur[0])
         return feats, cur
 
@@ -118,7 +218,8 @@ class YNetEngine:
             feats = [ChannelCat((a, b)) for a, b in zip(sf, mf)]
             ff, _ = self._run_stages(enc.fusion_stages, 'encoder.fusion_stages', list(feats[-1]), SRC_DIRECT)
             return feats + ff
-        feats, _ = self._run_stages(enc.stages, 'encoder.stages', scene + motion, SRC_DIRECT)
+        feats, _ = self._run_stages(enc.stages, 'encoder.stages', scene + motion, SRC_DIRECT,
+                                    getattr(enc, 'adapters', None), getattr(enc, 'position', ()))
         return feats
 
     # ---------------------------------------------------------------- decoders
@@ -200,17 +301,20 @@ class YNetEngineTC(YNetEngine):
         Bm = getattr(module, 'lora_B', None)
         ver = (module.weight._version, module.weight.data_ptr(),
                None if A is None else (A._version, A.data_ptr()),
-               None if Bm is None else (Bm._version, Bm.data_ptr()), tuple(src_channels))
+               None if Bm is None else (Bm._version, Bm.data_ptr()), tuple(src_channels),
+               _module_version(module) if _is_adapter_layer(module) else None)
         hit = self._wcache.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1], hit[2]
-        w_eff = ops.lora_fold(module.weight.detach(), None if A is None else A.detach(),
-                              None if Bm is None else Bm.detach(), packed=False)
+        w, b = module.weight.detach(), (None if module.bias is None else module.bias.detach())
+        if _is_adapter_layer(module):
+            w, b = fold_adapter_layer(module, w, b)
+        w_eff = ops.lora_fold(w, None if A is None else A.detach(), None if Bm is None else Bm.detach(), packed=False)
         packed = ops.tc_pack_weights(w_eff, list(src_channels))
         C_out = module.weight.shape[0]
         bias = torch.zeros(ops._pad16(C_out), dtype=torch.float32, device=module.weight.device)
-        if module.bias is not None:
-            bias[:C_out] = module.bias.detach()
+        if b is not None:
+            bias[:C_out] = b
         self._wcache[key] = (ver, packed, bias)
         return packed, bias
 
@@ -250,8 +354,23 @@ class YNetEngineTC(YNetEngine):
         nxt = i + 1
         return nxt < len(decoder.upsample_conv) and decoder.upsample_conv[nxt].weight.shape[0] <= self.upconv_max_cout
 
-    def _run_stages_tc(self, stages, key, cur):
+    def _block_adapter_tc(self, adapter, key, y, stage_inputs):
+        """AdapterBlock of YNetEncoderB on a stage output ``y`` (bf16 engine): one extra conv launch."""
+        ver = (_module_version(adapter), tuple(s.C for s in stage_inputs))
+        hit = self._wcache.get(key)
+        if hit is None or hit[0] != ver:
+            w, b, needs_input = block_adapter_weights(adapter, y.C)
+            chans = [y.C] + ([s.C for s in stage_inputs] if needs_input else [])
+            bias = torch.zeros(ops._pad16(y.C), dtype=torch.float32, device=w.device)
+            if b is not None:
+                bias[:y.C] = b
+            hit = (ver, ops.tc_pack_weights(w, chans), bias, needs_input)
+            self._wcache[key] = hit
+        return ops.tc_conv3x3([y] + (list(stage_inputs) if hit[3] else []), hit[1], hit[2], y.C, False)
+
+    def _run_stages_tc(self, stages, key, cur, adapters=None, position=()):
         feats = []
+        position = list(position)
         for si, stage in enumerate(stages):
             mods = list(stage)
             convs = [(j, m) for j, m in enumerate(mods) if isinstance(m, torch.nn.Conv2d)]
@@ -260,8 +379,12 @@ class YNetEngineTC(YNetEngine):
             if not convs:
                 feats.append(cur[0] if len(cur) == 1 else ChannelCat(cur))
                 continue
+            stage_inputs = cur
             for j, conv in convs:
                 cur = [self._tconv(conv, f'{key}.{si}.{j}', cur, True)]
+            if adapters is not None and si in position:
+                ai = position.index(si)
+                cur = [self._block_adapter_tc(adapters[ai], f'{key}.adapters.{ai}', cur[0], stage_inputs)]
             feats.append(cur[0])
         return feats
 
@@ -273,7 +396,8 @@ class YNetEngineTC(YNetEngine):
             mf = self._run_stages_tc(enc.motion_stages, 'encoder.motion_stages', motion)
             feats = [ChannelCat((a, b)) for a, b in zip(sf, mf)]
             return feats + self._run_stages_tc(enc.fusion_stages, 'encoder.fusion_stages', list(feats[-1]))
-        return self._run_stages_tc(enc.stages, 'encoder.stages', scene + motion)
+        return self._run_stages_tc(enc.stages, 'encoder.stages', scene + motion, getattr(enc, 'adapters', None),
+                                   getattr(enc, 'position', ()))
 
     def decoder_trunk(self, decoder, key, features):
         feats = [self._c8_parts(f) for f in features][::-1]

@@ -7,8 +7,15 @@ are parameter containers: all arithmetic is done by ``YNetEngine`` through libyn
 
 Supported on the hot path: ``network in {'original', 'fusion'}`` with plain convs or MoSA/LoRA
 convs (``train_net`` containing ``mosa``; ``position`` = stage ids or scene/motion/fusion).
-The serial/parallel adapter baselines, the ``embed`` network and the ``semantic`` adapter
-(ynet.py:15-131,154-167,513-519) are out of this round's scope and raise.
+
+SURVEY 8f rank 3 (the paper's comparison baselines, ynet.py:15-131,237-283): the serial / parallel
+adapters, layer level (``AdapterLayer``, ``train_net`` containing ``Layer``, e.g. ``parallelLayer_3x3`` of
+scripts/sdd/ped_to_biker/tune_pa.sh:22) and block level (``AdapterBlock`` inside ``YNetEncoderB``), are
+parameter containers with the reference's names; the engines fold them into the conv they decorate
+(inference: exact; BatchNorm in eval mode is an affine map) or run them as one extra conv launch.
+Fine-tuning is supported for the parallel layer adapters (linear in weight space); serial adapters
+train with batch statistics and raise in training mode.
+The ``embed`` network and the ``semantic`` adapter (ynet.py:154-167,513-519) raise.
 """
 import torch
 import torch.nn as nn
@@ -30,8 +37,71 @@ def get_conv2d(train_net, l, position, kernel_size, in_channels, out_channels=No
         return lora.Conv2d(in_channels, out_channels, kernel_size=kernel_size, r=rank, stride=stride,
                            padding=padding)
     if 'Layer' in train_net and str(l) in pos:
-        raise NotImplementedError('AdapterLayer baselines (ynet.py:69-131) are outside the B200 hot path')
+        return AdapterLayer(in_channels, out_channels, kernel_size, adapter_name=train_net, stride=stride,
+                            padding=padding)
     return nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding)
+
+
+def _plain_conv(in_channels, out_channels=None, kernel_size=1, stride=1, is_bias=False):
+    """ynet.py:8-12: the adapters' own convs (same padding, no bias by default)."""
+    out_channels = in_channels if out_channels is None else out_channels
+    return nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=kernel_size // 2,
+                     bias=is_bias)
+
+
+def _adapter_sizes(adapter_name):
+    """'parallelLayer_1x1_3x3' -> ['1x1', '3x3'] (ynet.py:21-22)."""
+    return adapter_name.split('_')[1:]
+
+
+def _build_adapter(owner, adapter_name, in_channels, out_channels, serial_channels, stride, is_bias):
+    """Submodules of an adapter with the reference's names and creation order (ynet.py:24-50, 88-115): the default
+    initialisation consumes the global RNG exactly like the reference before the weights are zeroed."""
+    sizes = _adapter_sizes(adapter_name)
+    if 'serial' in adapter_name:
+        owner.serial_layer = nn.Sequential(nn.BatchNorm2d(serial_channels), _plain_conv(serial_channels, is_bias=is_bias))
+        nn.init.zeros_(owner.serial_layer[1].weight)
+        if is_bias:
+            nn.init.zeros_(owner.serial_layer[1].bias)
+    elif 'parallel' in adapter_name and len(sizes) < 2:
+        k = int(sizes[0].split('x')[0]) if sizes else 1
+        owner.parallel_layer = _plain_conv(in_channels, out_channels, k, stride, is_bias)
+        for p in owner.parallel_layer.parameters():
+            nn.init.zeros_(p)
+    elif 'parallel' in adapter_name:
+        owner.parallel_layer = nn.ModuleList(
+            [_plain_conv(in_channels, out_channels, int(s.split('x')[0]), stride, is_bias) for s in sizes])
+        for p in owner.parallel_layer.parameters():
+            nn.init.zeros_(p)
+    else:
+        raise ValueError(f'Invalid adapter={adapter_name}')
+
+
+class AdapterBlock(nn.Module):
+    """Block-level adapter of YNetEncoderB (ynet.py:15-66): serial = x + conv1x1(BN(x)) on a stage output,
+    parallel = sum of k x k convs of the stage INPUT added to the stage output.  Parameter container."""
+
+    def __init__(self, adapter_name, in_channels, out_channels=None, stride=1, is_bias=False):
+        super().__init__()
+        self.is_bias = is_bias
+        self.adapter_name = adapter_name
+        self.adapter_size = _adapter_sizes(adapter_name)
+        self.is_multiple = len(self.adapter_size) >= 2
+        _build_adapter(self, adapter_name, in_channels, out_channels, in_channels, stride, is_bias)
+
+
+class AdapterLayer(nn.Conv2d):
+    """Layer-level adapter (ynet.py:69-131): a conv whose output gets + conv1x1(BN(out)) (serial) or + sum of k x k
+    convs of the same input (parallel).  Parameter container; the engines fold it into ONE 3x3 conv."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, adapter_name, adapter_dropout=0., stride=1,
+                 is_bias=False, **kwargs):
+        nn.Conv2d.__init__(self, in_channels, out_channels, kernel_size, **kwargs)
+        self.is_bias = is_bias
+        self.adapter_name = adapter_name
+        self.adapter_size = _adapter_sizes(adapter_name)
+        self.is_multiple = len(self.adapter_size) >= 2
+        _build_adapter(self, adapter_name, in_channels, out_channels, out_channels, stride, is_bias)
 
 
 def _mosa_rank(train_net):
@@ -75,11 +145,10 @@ class YNetEncoderL(YNetEncoder):
 
 
 class YNetEncoderB(YNetEncoder):
-    """ynet.py:237-283 without the serial/parallel adapter blocks (not on the hot path)."""
+    """ynet.py:237-283: the plain encoder plus, for ``train_net`` containing serial / parallel, one AdapterBlock per
+    adapted stage (``adapters[j]`` belongs to stage ``position[j]``)."""
 
     def __init__(self, in_channels, channels=(64, 128, 256, 512, 512), train_net=None, position=[]):
-        if 'serial' in train_net or 'parallel' in train_net:
-            raise NotImplementedError('serial/parallel adapter baselines are outside the B200 hot path')
         pos = []
         for i in position:
             try:
@@ -87,6 +156,12 @@ class YNetEncoderB(YNetEncoder):
             except (TypeError, ValueError):
                 pos.append(i)
         super().__init__(in_channels, channels, train_net, pos)
+        par_channels_in = [in_channels] + list(channels[:-1])
+        if 'serial' in train_net:
+            self.adapters = nn.ModuleList([AdapterBlock(train_net, channels[i]) for i in self.position])
+        elif 'parallel' in train_net:
+            self.adapters = nn.ModuleList(
+                [AdapterBlock(train_net, par_channels_in[i], channels[i]) for i in self.position])
 
 
 class YNetEncoderFusion(nn.Module):

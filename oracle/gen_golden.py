@@ -173,6 +173,64 @@ def gen_network(ns):
              **{'sd/' + k: v for k, v in sd.items()})
 
 
+ADAPTER_VARIANTS = (   # tag, train_net, position  (the comparison baselines, ynet.py:15-131, 237-283)
+    ('parallelLayer_3x3', 'parallelLayer_3x3', (0, 1, 2, 3, 4)),      # scripts/sdd/ped_to_biker/tune_pa.sh:22
+    ('parallelLayer_1x1_3x3', 'parallelLayer_1x1_3x3', (1, 3)),
+    ('serialLayer', 'serialLayer', (0, 2, 4)),
+    ('serial_block', 'serial', (0, 1, 2, 3, 4)),
+    ('parallel_block_1x1', 'parallel_1x1', (0, 2)),
+    ('parallel_block_1x1_3x3', 'parallel_1x1_3x3', (1, 4)),
+)
+
+
+def gen_adapters(ns):
+    """Encoder features (+ goal logits) of the reference with the serial / parallel adapter baselines, eval mode, and
+    the reference's autograd gradients of the parallel layer adapters (the only adapter baseline that fine-tunes here)."""
+    for tag, train_net, position in ADAPTER_VARIANTS:
+        m = build_ref_model(ns, 5, 6, 2, train_net=train_net, position=position, seed=4)
+        g = torch.Generator().manual_seed(11)
+        with torch.no_grad():          # adapters are zero-initialised (ynet.py:43-50): make them non-trivial
+            for n, p in m.encoder.named_parameters():
+                if 'serial_layer.1' in n or 'parallel_layer' in n:
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+                elif 'serial_layer.0' in n:
+                    p.copy_(1.0 + 0.3 * torch.randn(p.shape, generator=g) if n.endswith('weight')
+                            else 0.2 * torch.randn(p.shape, generator=g))
+            for n, b in m.encoder.named_buffers():
+                if n.endswith('running_mean'):
+                    b.copy_(0.3 * torch.randn(b.shape, generator=g))
+                elif n.endswith('running_var'):
+                    b.copy_(0.5 + torch.rand(b.shape, generator=g))
+        m.eval()
+        torch.manual_seed(12)
+        scene = torch.softmax(torch.randn(1, 6, 32, 32), 1).expand(2, -1, -1, -1)
+        motion = torch.rand(2, 5, 32, 32) * 2
+        extra = {}
+        if 'parallelLayer' in train_net:
+            for p in m.parameters():
+                p.requires_grad = False
+            train = {n: p for n, p in m.encoder.named_parameters() if 'parallel' in n}     # trainer.py:133-135
+            for p in train.values():
+                p.requires_grad = True
+            feats = m.pred_features(scene, motion)
+            goal = m.pred_goal(feats)
+            (goal.square().mean() * 100.0).backward()
+            extra = {'grad/encoder.' + n: p.grad.numpy() for n, p in train.items()}
+            feats = [f.detach() for f in feats]
+            goal = goal.detach()
+        else:
+            with torch.no_grad():
+                feats = m.pred_features(scene, motion)
+                goal = m.pred_goal(feats)
+        # only the encoder is stored: the decoders are the default initialisation under seed 4, which the drop-in
+        # reproduces bit for bit (same modules, same creation order)
+        sd = {k: v.detach().numpy() for k, v in m.state_dict().items() if k.startswith('encoder.')}
+        save(f'adapter_{tag}', scene=scene[:1].numpy(), motion=motion.numpy(), goal=goal.numpy(), seed=np.array(4),
+             train_net=np.array(train_net), position=np.array(position),
+             **{f'feat{i}': f.numpy() for i, f in enumerate(feats)}, **extra,
+             **{'sd/' + k: v for k, v in sd.items()})
+
+
 def gen_evaluate(ns):
     cfgs = [
         dict(name='eval_sdd_short', H=64, W=96, obs=8, pred=12, wps=[11], B=3, resize=0.25, n_goal=20,
@@ -272,6 +330,7 @@ def main(only=None):
     gen_kmeans(ns)
     gen_cws(ns)
     gen_network(ns)
+    gen_adapters(ns)
     gen_evaluate(ns)
     gen_train(ns)
 

@@ -341,34 +341,73 @@ def effective_weight(sd, prefix):
     return w
 
 
+def _serial_adapter(sd, prefix, x):
+    """Adapter serial branch in eval mode (ynet.py:26-28, 63-65, 119-121): conv1x1(BatchNorm(x)) + x."""
+    p = prefix + '.serial_layer'
+    y = F.batch_norm(x, sd[p + '.0.running_mean'], sd[p + '.0.running_var'], sd[p + '.0.weight'], sd[p + '.0.bias'],
+                     training=False, eps=1e-5)
+    return F.conv2d(y, sd[p + '.1.weight'], sd.get(p + '.1.bias')) + x
+
+
+def _parallel_adapter(sd, prefix, x):
+    """Adapter parallel branch (ynet.py:30-41, 55-62, 122-129): sum of the k x k convs of x (same padding, no bias)."""
+    p = prefix + '.parallel_layer'
+    if p + '.weight' in sd:
+        ws = [sd[p + '.weight']]
+    else:
+        ws, i = [], 0
+        while f'{p}.{i}.weight' in sd:
+            ws.append(sd[f'{p}.{i}.weight'])
+            i += 1
+    y = 0
+    for w in ws:
+        y = y + F.conv2d(x, w, None, padding=w.shape[-1] // 2)
+    return y
+
+
 def _conv(sd, prefix, x, relu=True, pad=1):
     y = F.conv2d(x, effective_weight(sd, prefix), sd[prefix + '.bias'], padding=pad)
+    if prefix + '.serial_layer.1.weight' in sd:                       # AdapterLayer.forward, ynet.py:117-131
+        y = _serial_adapter(sd, prefix, y)
+    elif prefix + '.parallel_layer.weight' in sd or prefix + '.parallel_layer.0.weight' in sd:
+        y = y + _parallel_adapter(sd, prefix, x)
     return F.relu(y) if relu else y
 
 
-def _run_stage_list(sd, prefix, n_stage_total, x, first_has_pool):
-    """A ModuleList of Sequential stages as built in ynet.py:192-215 / 309-367."""
+def _run_stage_list(sd, prefix, n_stage_total, x, first_has_pool, adapter_position=None):
+    """A ModuleList of Sequential stages as built in ynet.py:192-215 / 309-367.  ``adapter_position``: stage ids that
+    carry a block-level AdapterBlock ``encoder.adapters.{j}`` (YNetEncoderB.forward, ynet.py:258-283)."""
     feats = []
     i = 0
+    pos = [int(p) for p in adapter_position] if adapter_position is not None else []
     while True:
         base = f'{prefix}.{i}'
         has0 = f'{base}.0.weight' in sd
         has1 = f'{base}.1.weight' in sd
         if has0:                      # [conv, relu]
+            xin = x
             x = _conv(sd, f'{base}.0', x)
         elif has1:                    # [pool, conv, relu, conv, relu]
             x = F.max_pool2d(x, 2, 2)
+            xin = x
             x = _conv(sd, f'{base}.1', x)
             x = _conv(sd, f'{base}.3', x)
         else:
             break
+        if i in pos:
+            a = f'encoder.adapters.{pos.index(i)}'
+            if a + '.serial_layer.1.weight' in sd:        # x = adapter(stage(x)), ynet.py:262-266
+                x = _serial_adapter(sd, a, x)
+            else:                                         # x = stage(x) + adapter(stage input), ynet.py:267-279
+                x = x + _parallel_adapter(sd, a, xin)
         feats.append(x)
         i += 1
     return feats, x, i
 
 
-def pred_features(sd, scene_map, motion_map, network='original'):
-    """models/ynet.py:570-575, 229-234 (Y-Net) and 369-395 (Y-Net-Mod)."""
+def pred_features(sd, scene_map, motion_map, network='original', adapter_position=None):
+    """models/ynet.py:570-575, 229-234 (Y-Net), 258-283 (Y-Net with block-level adapters at ``adapter_position``) and
+    369-395 (Y-Net-Mod)."""
     scene_map = torch.as_tensor(scene_map, dtype=torch.float32)
     motion_map = torch.as_tensor(motion_map, dtype=torch.float32)
     if network == 'fusion':
@@ -380,7 +419,8 @@ def pred_features(sd, scene_map, motion_map, network='original'):
         feats.append(F.max_pool2d(x, 2, 2))     # trailing pool-only stage
         return feats
     x = torch.cat([scene_map, motion_map], dim=1)
-    feats, x, _ = _run_stage_list(sd, 'encoder.stages', 0, x, False)
+    has_blocks = any(k.startswith('encoder.adapters.') for k in sd)
+    feats, x, _ = _run_stage_list(sd, 'encoder.stages', 0, x, False, adapter_position if has_blocks else None)
     feats.append(F.max_pool2d(x, 2, 2))
     return feats
 

@@ -41,3 +41,22 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+ADAPTER_TAGS = ['parallelLayer_3x3', 'parallelLayer_1x1_3x3', 'serialLayer', 'serial_block', 'parallel_block_1x1',
+                'parallel_block_1x1_3x3']
+
+
+def build_adapter_model(g, device='cpu'):
+    """Drop-in YNet of an ``adapter_<tag>`` fixture (oracle/gen_golden.py::gen_adapters): decoders = the default
+    initialisation under the fixture's seed (bit-identical to the reference's, same modules in the same order), encoder =
+    the fixture's tensors."""
+    from motion_style_transfer_b200.models.ynet import YNet
+    torch.manual_seed(int(g['seed']))
+    m = YNet(obs_len=5, pred_len=6, segmentation_model_fp=None, encoder_channels=list(SMALL_ENC),
+             decoder_channels=list(SMALL_DEC), n_waypoints=2, train_net=str(g['train_net']),
+             position=[int(p) for p in g['position']], network='original')
+    sd = golden_state_dict(g)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(not k.startswith('encoder.') for k in missing)
+    return m.to(device).eval()

@@ -223,3 +223,58 @@ def test_evaluate_dropin_signature_against_fixture(ops):
     np.testing.assert_allclose(df.fde.values, g['fde'], rtol=0, atol=0.05)
     assert td['goal_map'].shape == g['goal_map'].shape and td['waypoint_sample'].shape == g['waypoint_sample'].shape
     assert abs(ade - g['ade'].mean()) < 0.05 and abs(fde - g['fde'].mean()) < 0.05
+
+
+# ---- serial / parallel adapter baselines (ynet.py:15-131, 237-283) -----------------------------------
+from helpers import ADAPTER_TAGS, build_adapter_model     # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('backend,tol', [('fp32', REL), ('bf16', 2.5e-2)])
+@pytest.mark.parametrize('tag', ADAPTER_TAGS)
+def test_adapter_baselines_against_reference_fixture(ops, tag, backend, tol):
+    """Layer-level adapters folded into their conv, block-level adapters as one extra conv launch: encoder features and
+    goal logits of the live reference (eval mode)."""
+    g = load_golden(f'adapter_{tag}')
+    m = build_adapter_model(g, 'cuda').set_backend(backend)
+    scene = torch.from_numpy(g['scene']).cuda()
+    motion = torch.from_numpy(g['motion']).cuda()
+    with torch.no_grad():
+        feats = m.pred_features(scene, motion)
+        for i, f in enumerate(feats):
+            f = ops.tc_unpack(f) if isinstance(f, ops.C8) else f
+            assert rel_err(f.cpu().numpy(), g[f'feat{i}']) < tol, f'feature {i}'
+        goal = m.pred_goal(feats)
+        assert rel_err(goal.cpu().numpy(), g['goal']) < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag', ['parallelLayer_3x3', 'parallelLayer_1x1_3x3'])
+def test_parallel_layer_adapter_gradients_against_reference(ops, tag):
+    """Fine-tuning the parallel layer adapters (scripts/sdd/ped_to_biker/tune_pa.sh): gradients of the trainable tensors
+    (trainer.py:133-135) from the device autograd engine vs the reference's autograd."""
+    from motion_style_transfer_b200.models.trainer import apply_freeze_policy
+    g = load_golden(f'adapter_{tag}')
+    m = build_adapter_model(g, 'cuda')
+    apply_freeze_policy(m, str(g['train_net']), [int(p) for p in g['position']], 'original')
+    names = [n for n, p in m.named_parameters() if p.requires_grad]
+    assert names and all('parallel' in n for n in names)
+    m.train()
+    feats = m.pred_features(torch.from_numpy(g['scene']).cuda(), torch.from_numpy(g['motion']).cuda())
+    goal = m.pred_goal(feats)
+    assert rel_err(goal.detach().cpu().numpy(), g['goal']) < REL
+    (goal.square().mean() * 100.0).backward()
+    for n, p in m.named_parameters():
+        if p.requires_grad:
+            assert rel_err(p.grad.cpu().numpy(), g['grad/' + n]) < 2e-3, n
+
+
+@pytest.mark.gpu
+def test_serial_adapters_raise_in_training_mode(ops):
+    g = load_golden('adapter_serialLayer')
+    m = build_adapter_model(g, 'cuda')
+    for p in m.encoder.parameters():
+        p.requires_grad = True
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m.pred_features(torch.from_numpy(g['scene']).cuda(), torch.from_numpy(g['motion']).cuda())

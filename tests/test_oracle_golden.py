@@ -101,6 +101,77 @@ def test_network_forward(tag, network):
     np.testing.assert_allclose(traj.numpy(), g['traj'], rtol=1e-5, atol=1e-6)
 
 
+# ---- serial / parallel adapter baselines (ynet.py:15-131, 237-283) -----------------------------------
+from helpers import ADAPTER_TAGS, build_adapter_model     # noqa: E402
+
+
+@pytest.mark.parametrize('tag', ADAPTER_TAGS)
+def test_adapter_baselines_oracle_against_reference_fixture(tag):
+    """The oracle's eval-mode restatement of AdapterLayer / AdapterBlock vs the live reference's features and goal logits."""
+    g = load_golden(f'adapter_{tag}')
+    torch.set_num_threads(1)
+    m = build_adapter_model(g)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    scene = torch.from_numpy(g['scene']).expand(2, -1, -1, -1)
+    feats = O.pred_features(sd, scene, g['motion'], 'original', adapter_position=g['position'])
+    for i, f in enumerate(feats):
+        np.testing.assert_allclose(f.numpy(), g[f'feat{i}'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(O.pred_goal(sd, feats).numpy(), g['goal'], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize('tag', ADAPTER_TAGS)
+def test_adapter_folding_is_the_adapter_forward(tag):
+    """Host logic of the engines (weight-space folding, engine.fold_adapter_layer / block_adapter_weights): one 3x3 conv
+    with the folded weights equals the adapter's own forward as restated by the oracle."""
+    import torch.nn.functional as F
+    from motion_style_transfer_b200 import engine as E
+    g = load_golden(f'adapter_{tag}')
+    m = build_adapter_model(g).double()
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    torch.manual_seed(0)
+    if 'Layer' in str(g['train_net']):
+        stage = int(g['position'][-1])
+        conv = m.encoder.stages[stage][1 if stage else 0]
+        prefix = f'encoder.stages.{stage}.{1 if stage else 0}'
+        x = torch.randn(2, conv.weight.shape[1], 12, 10, dtype=torch.float64)
+        w, b = E.fold_adapter_layer(conv, conv.weight.detach(), conv.bias.detach())
+        np.testing.assert_allclose(F.conv2d(x, w, b, padding=1).numpy(), O._conv(sd, prefix, x, relu=False).numpy(),
+                                   rtol=1e-10, atol=1e-12)
+    else:
+        ai = len(g['position']) - 1
+        adapter = m.encoder.adapters[ai]
+        cout = m.encoder.stages[int(g['position'][ai])][-2].weight.shape[0]
+        w, b, needs_input = E.block_adapter_weights(adapter, cout)
+        y = torch.randn(2, cout, 12, 10, dtype=torch.float64)
+        if needs_input:
+            xin = torch.randn(2, w.shape[1] - cout, 12, 10, dtype=torch.float64)
+            ref = y + O._parallel_adapter(sd, f'encoder.adapters.{ai}', xin)
+            got = F.conv2d(torch.cat([y, xin], 1), w.double(), None, padding=1)
+        else:
+            ref = O._serial_adapter(sd, f'encoder.adapters.{ai}', y)
+            got = F.conv2d(y, w.double(), b.double(), padding=1)
+        np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason='needs the reference tree (build container only)')
+@pytest.mark.parametrize('train_net,position', [('parallelLayer_3x3', [0, 1, 2, 3, 4]), ('parallelLayer_1x1_3x3', [1, 3]),
+                                                ('serialLayer', [0, 2, 4]), ('serial', [0, 1, 2, 3, 4]),
+                                                ('parallel_1x1', [0, 2]), ('parallel', [0, 1])])
+def test_live_reference_adapter_state_dict_is_identical(train_net, position):
+    """Same keys in the same order and the same default initialisation under one seed: checkpoints interchange."""
+    from motion_style_transfer_b200.models.ynet import YNet
+    ns = ref_harness.load()
+    kw = dict(obs_len=5, pred_len=6, segmentation_model_fp=None, encoder_channels=[8, 8, 16, 16, 16],
+              decoder_channels=[16, 16, 16, 8, 8], n_waypoints=2, train_net=train_net, position=list(position),
+              network='original')
+    torch.manual_seed(3)
+    a = ns.ynet.YNet(**kw).state_dict()
+    torch.manual_seed(3)
+    b = YNet(**kw).state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(torch.equal(a[k], b[k]) for k in a)
+
+
 class _ReplayRng:
     """Feeds the randoms recorded in the fixture instead of drawing from global RNGs."""
 
