@@ -15,7 +15,9 @@ parameter containers with the reference's names; the engines fold them into the 
 (inference: exact; BatchNorm in eval mode is an affine map) or run them as one extra conv launch.
 Fine-tuning is supported for the parallel layer adapters (linear in weight space); serial adapters
 train with batch statistics and raise in training mode.
-The ``embed`` network and the ``semantic`` adapter (ynet.py:154-167,513-519) raise.
+The ``embed`` network (three conv + ReLU layers on the semantic map and on the observed maps before the encoder,
+ynet.py:154-167,529-531) runs through the float32 conv kernel, forward and backward.  The ``semantic`` adapter
+(ynet.py:513-519) cannot be constructed in the reference itself (TypeError) and raises the same error here.
 """
 import torch
 import torch.nn as nn
@@ -120,6 +122,34 @@ def _double_conv_stage(train_net, l, position, cin, cout, rank):
         _pool(),
         get_conv2d(train_net, l, position, 3, cin, cout, rank), nn.ReLU(inplace=False),
         get_conv2d(train_net, l, position, 3, cout, cout, rank), nn.ReLU(inplace=False))
+
+
+def _conv3x3_f32(x, weight, bias, relu):
+    """One 3x3 conv (+ReLU) of a float32 NCHW map through the CUDA-core kernel; differentiable when grads are on."""
+    x = x.float().contiguous()
+    N, _, H, W = x.shape
+    if torch.is_grad_enabled() and (weight.requires_grad or x.requires_grad or (bias is not None and bias.requires_grad)):
+        from .. import autograd_engine
+        return autograd_engine.Conv3x3Fn.apply(weight, bias, None, None, relu, (ops.SRC_DIRECT,), H, W, x)
+    packed = ops.lora_fold(weight.detach().contiguous(), None, None, packed=True)
+    return ops.conv3x3_f32([(x, ops.SRC_DIRECT)], packed, None if bias is None else bias.detach(), relu, N, H, W)
+
+
+class Embedding(nn.Module):
+    """ynet.py:154-167: three (conv3x3 + ReLU) layers, channels -> channels (``network='embed'``)."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.conv = nn.Sequential(
+            nn.Conv2d(channels, channels, kernel_size=3, stride=1, padding=1), nn.ReLU(inplace=False),
+            nn.Conv2d(channels, channels, kernel_size=3, stride=1, padding=1), nn.ReLU(inplace=False),
+            nn.Conv2d(channels, channels, kernel_size=3, stride=1, padding=1), nn.ReLU(inplace=False))
+
+    def forward(self, x):
+        for m in self.conv:
+            if isinstance(m, nn.Conv2d):
+                x = _conv3x3_f32(x, m.weight, m.bias, True)
+        return x
 
 
 class YNetEncoder(nn.Module):
@@ -241,18 +271,22 @@ class YNet(nn.Module):
         self.feature_channels = n_semantic_classes + obs_len
         self.network = network
         if 'semantic' in train_net:
-            raise NotImplementedError('semantic adapter (ynet.py:513-519) is outside the B200 hot path')
+            # ynet.py:513-519 passes position=None into get_conv2d, which iterates over it (ynet.py:140): the reference
+            # cannot construct this model (verified against the live reference), so there is no behaviour to reproduce
+            raise TypeError("train_net containing 'semantic': the reference's semantic adapter cannot be constructed "
+                            "(ynet.py:516 -> ynet.py:140: 'NoneType' object is not iterable)")
         if network == 'fusion':
             assert n_fusion is not None
             self.encoder = YNetEncoderFusion(n_semantic_classes, obs_len, encoder_channels, train_net=train_net,
                                              position=position, n_fusion=n_fusion)
-        elif network == 'original':
+        elif network == 'original' or network == 'embed':
+            if network == 'embed':            # ynet.py:529-531
+                self.scene_embedding = Embedding(n_semantic_classes)
+                self.motion_embedding = Embedding(obs_len)
             if 'mosa' in train_net or 'Layer' in train_net:
                 self.encoder = YNetEncoderL(self.feature_channels, encoder_channels, train_net, position)
             else:
                 self.encoder = YNetEncoderB(self.feature_channels, encoder_channels, train_net, position)
-        elif network == 'embed':
-            raise NotImplementedError("network='embed' (ynet.py:154-167) is outside the B200 hot path")
         else:
             raise ValueError('No network parameter is provided')
         self.goal_decoder = YNetDecoder(encoder_channels, decoder_channels, output_len=pred_len)
@@ -286,7 +320,7 @@ class YNet(nn.Module):
         return self.semantic_segmentation(image)
 
     def adapt_semantic(self, semantic_img):
-        return semantic_img
+        return semantic_img       # ynet.py:554-559: identity unless a semantic adapter exists (it cannot, see __init__)
 
     def pred_features(self, scene_map, motion_map):
         if self._training_graph():

@@ -13,7 +13,7 @@ import torch
 
 from .. import ops, parallel
 from ..engine import ChannelCat
-from .image_utils import HostRng, sampling
+from .image_utils import HostRng, sampling, swap_pavement_terrain
 from .kmeans import kmeans_batched
 
 TTST_SAMPLES = 10000          # evaluate.py:138
@@ -79,7 +79,7 @@ def _cws(model, sig_maps, goal_samples, last_observed, n_goal, n_traj, n_wp, CWS
 
 def forecast_batch(model, scene_image, trajectory, input_template, waypoints, n_goal, n_traj, obs_len,
                    resize_factor=0.25, temperature=1.0, use_TTST=False, use_CWS=False, rel_thresh=0.002,
-                   CWS_params=None, rng=None, kmeans_init=None, want_maps=False):
+                   CWS_params=None, rng=None, kmeans_init=None, want_maps=False, embed_motion=False):
     """One iteration of the reference's batch loop (evaluate.py:109-291), everything on the device.
 
     scene_image (1, n_cls, H, W) semantic map; trajectory (B, obs+pred, 2) float32 device tensor in
@@ -94,6 +94,8 @@ def forecast_batch(model, scene_image, trajectory, input_template, waypoints, n_
         observed = trajectory[:, :obs_len].reshape(-1, 2)
         observed_map = ops.rasterize_patches(input_template, observed, H, W).view(B, obs_len, H, W)
         gt_future = trajectory[:, obs_len:].contiguous()
+        if embed_motion:                           # evaluate.py:120-121 (network='embed')
+            observed_map = model.motion_embedding(observed_map)
         feats = model.pred_features(scene_image, observed_map)
         subset = getattr(model.engine, 'decoder_logits_subset', None)
         if subset is not None and not want_maps:
@@ -142,10 +144,6 @@ def evaluate(model, val_loader, val_images, device, dataset_name, homo_mat, inpu
     """Reference signature (evaluate.py:37-42) -> (ade, fde, DataFrame[metaId, sceneId, ade, fde], dict|None)."""
     if str(dataset_name).lower() == 'eth':
         raise NotImplementedError('ETH/UCY homography path (image2world) is outside the B200 hot path')
-    if network == 'embed':
-        raise NotImplementedError("network='embed' is outside the B200 hot path")
-    if swap_semantic:
-        raise NotImplementedError('swap_semantic is outside the B200 hot path')
     model.eval()
     device = torch.device(device)
     if device.type != 'cuda':
@@ -164,6 +162,10 @@ def evaluate(model, val_loader, val_images, device, dataset_name, homo_mat, inpu
             scene_image = val_images[scene_id].to(device).unsqueeze(0)
             scene_image = model.segmentation(scene_image)
             scene_image = model.adapt_semantic(scene_image).float().contiguous()
+            if swap_semantic:                      # evaluate.py:95-96, image_utils.py:165-171
+                scene_image = swap_pavement_terrain(scene_image)
+            if network == 'embed':                 # evaluate.py:99-100
+                scene_image = model.scene_embedding(scene_image)
             meta_ids = df_batch[0].metaId.unique()
             n_data = trajectory.shape[0]
             trajectory = trajectory.to(device=device, dtype=torch.float32)
@@ -176,7 +178,8 @@ def evaluate(model, val_loader, val_images, device, dataset_name, homo_mat, inpu
                 e = min(b + batch_size, hi)
                 res = forecast_batch(model, scene_image, trajectory[b:e].contiguous(), input_template,
                                      waypoints, n_goal, n_traj, obs_len, resize_factor, temperature, use_TTST,
-                                     use_CWS, rel_thresh, CWS_params, want_maps=return_samples)
+                                     use_CWS, rel_thresh, CWS_params, want_maps=return_samples,
+                                     embed_motion=(network == 'embed'))
                 rows['ade'].append(res['ade'])
                 rows['fde'].append(res['fde'])
                 if return_preds:

@@ -61,6 +61,16 @@ def get_patch(template, traj, H, W):
     return list(get_patch_stack(template, traj, H, W).unbind(0))
 
 
+def swap_pavement_terrain(semantic_img):
+    """image_utils.py:165-173: exchange semantic classes 1 and 2 of a (B, C, H, W) map (``--swap_semantic``).  Returns a
+    new tensor (the reference swaps in place on the tensor it has just produced)."""
+    if semantic_img.dim() != 4:
+        raise ValueError(f'semanctic image has shape {semantic_img.shape} but should have 4 dimensions')
+    order = list(range(semantic_img.shape[1]))
+    order[1], order[2] = order[2], order[1]
+    return semantic_img[:, order].contiguous()
+
+
 class DeviceRng:
     """Counter-based (Philox) device generator for the production path.
 

@@ -9,13 +9,12 @@ import torch
 
 from .. import ops, parallel
 from ..engine import ChannelCat
+from .image_utils import swap_pavement_terrain
 
 
 def train_epoch(model, train_loader, train_images, optimizer, criterion, loss_scale, device, dataset_name, homo_mat,
                 gt_template, input_template, waypoints, epoch, obs_len, pred_len, batch_size, e_unfreeze,
                 resize_factor, network=None, swap_semantic=False):
-    if network == 'embed' or swap_semantic:
-        raise NotImplementedError("network='embed' / swap_semantic are outside the B200 hot path")
     device = torch.device(device)
     if device.type != 'cuda':
         raise RuntimeError('motion_style_transfer_b200.train_epoch runs on CUDA only (no CPU fallback)')
@@ -36,6 +35,8 @@ def train_epoch(model, train_loader, train_images, optimizer, criterion, loss_sc
         trajectory = trajectory.to(device=device, dtype=torch.float32)
         for i in range(0, len(trajectory), batch_size):
             semantic_img = model.adapt_semantic(scene_image)
+            if swap_semantic:                      # train_epoch.py:57-58
+                semantic_img = swap_pavement_terrain(semantic_img)
             _, _, H, W = scene_image.shape
             batch_traj = trajectory[i:i + batch_size]
             # one process per GPU: this rank takes a contiguous share of the batch's agents; its mean loss is
@@ -57,6 +58,9 @@ def train_epoch(model, train_loader, train_images, optimizer, criterion, loss_sc
             gt_waypoint_map = ops.rasterize_patches(input_template, gt_waypoints.reshape(-1, 2), H, W)
             gt_waypoint_map = gt_waypoint_map.view(B, gt_waypoints.shape[1], H, W)
 
+            if network == 'embed':                 # train_epoch.py:81-83
+                semantic_img = model.scene_embedding(semantic_img)
+                observed_map = model.motion_embedding(observed_map)
             features = model.pred_features(semantic_img, observed_map)            # scene broadcast over B
             pred_goal_map = model.pred_goal(features)
             goal_loss = criterion(pred_goal_map, gt_future_map) * loss_scale

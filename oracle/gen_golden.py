@@ -231,6 +231,25 @@ def gen_adapters(ns):
              **{'sd/' + k: v for k, v in sd.items()})
 
 
+def gen_embed_semantic(ns):
+    """network='embed' (ynet.py:154-167, 529-531; evaluate.py:99-100,120-121) of the reference: embedded maps, goal logits
+    and the autograd gradients of the embedding layers.  (The semantic adapter, ynet.py:513-519, cannot be constructed:
+    get_conv2d iterates over position=None.)"""
+    torch.manual_seed(12)
+    scene = torch.softmax(torch.randn(1, 6, 32, 32), 1)
+    motion = torch.rand(2, 5, 32, 32) * 2
+    m = build_ref_model(ns, 5, 6, 2, train_net='all', position=(), network='embed', seed=5)
+    sc = m.scene_embedding(scene)
+    mo = m.motion_embedding(motion)
+    feats = m.pred_features(sc.expand(2, -1, -1, -1), mo)
+    goal = m.pred_goal(feats)
+    (goal.square().mean() * 100.0).backward()
+    grads = {'grad/' + n: p.grad.numpy() for n, p in m.named_parameters() if 'embedding' in n}
+    sd = {k: v.detach().numpy() for k, v in m.state_dict().items() if k.startswith(('encoder.', 'scene_', 'motion_'))}
+    save('embed', scene=scene.numpy(), motion=motion.numpy(), scene_emb=sc.detach().numpy(), motion_emb=mo.detach().numpy(),
+         goal=goal.detach().numpy(), seed=np.array(5), **grads, **{'sd/' + k: v for k, v in sd.items()})
+
+
 def gen_evaluate(ns):
     cfgs = [
         dict(name='eval_sdd_short', H=64, W=96, obs=8, pred=12, wps=[11], B=3, resize=0.25, n_goal=20,
@@ -331,6 +350,7 @@ def main(only=None):
     gen_cws(ns)
     gen_network(ns)
     gen_adapters(ns)
+    gen_embed_semantic(ns)
     gen_evaluate(ns)
     gen_train(ns)
 

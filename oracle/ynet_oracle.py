@@ -662,3 +662,23 @@ def synthetic_tracks(B, total_len, H=416, W=416, seed=0, jitter=0.0):
     if jitter:
         tr = tr + torch.randn(B, total_len, 2, generator=g) * jitter
     return tr.float()
+
+
+# --------------------------------------------------------------------------------------
+# network='embed' (models/ynet.py:154-167; evaluate.py:99-100,120-121) and --swap_semantic
+# --------------------------------------------------------------------------------------
+
+
+def embedding_forward(sd, prefix, x):
+    """Embedding.forward (ynet.py:166-167): three (conv3x3 + ReLU) layers ``<prefix>.conv.{0,2,4}``."""
+    x = torch.as_tensor(x, dtype=torch.float32)
+    for i in (0, 2, 4):
+        x = F.relu(F.conv2d(x, sd[f'{prefix}.conv.{i}.weight'], sd[f'{prefix}.conv.{i}.bias'], padding=1))
+    return x
+
+
+def swap_pavement_terrain(semantic_img):
+    """image_utils.py:165-171: exchange channels 1 and 2."""
+    out = torch.as_tensor(semantic_img).clone()
+    out[:, 1], out[:, 2] = torch.as_tensor(semantic_img)[:, 2], torch.as_tensor(semantic_img)[:, 1]
+    return out

@@ -278,3 +278,31 @@ def test_serial_adapters_raise_in_training_mode(ops):
     m.train()
     with pytest.raises(NotImplementedError):
         m.pred_features(torch.from_numpy(g['scene']).cuda(), torch.from_numpy(g['motion']).cuda())
+
+
+@pytest.mark.gpu
+def test_embed_network_against_reference_fixture(ops):
+    """network='embed': the embedding layers (forward and backward through the float32 conv kernels) and the goal logits
+    behind them vs the live reference."""
+    from motion_style_transfer_b200.models.ynet import YNet
+    g = load_golden('embed')
+    torch.manual_seed(int(g['seed']))
+    m = YNet(obs_len=5, pred_len=6, segmentation_model_fp=None, encoder_channels=[8, 8, 16, 16, 16],
+             decoder_channels=[16, 16, 16, 8, 8], n_waypoints=2, train_net='all', position=[], network='embed')
+    missing, unexpected = m.load_state_dict(golden_state_dict(g), strict=False)
+    assert not unexpected and all(k.startswith(('goal_decoder.', 'traj_decoder.')) for k in missing)
+    m = m.cuda()
+    scene, motion = torch.from_numpy(g['scene']).cuda(), torch.from_numpy(g['motion']).cuda()
+    with torch.no_grad():
+        assert rel_err(m.scene_embedding(scene).cpu().numpy(), g['scene_emb']) < REL
+        assert rel_err(m.motion_embedding(motion).cpu().numpy(), g['motion_emb']) < REL
+    for p in m.parameters():
+        p.requires_grad = True
+    m.train()
+    sc, mo = m.scene_embedding(scene), m.motion_embedding(motion)
+    goal = m.pred_goal(m.pred_features(sc, mo))
+    assert rel_err(goal.detach().cpu().numpy(), g['goal']) < REL
+    (goal.square().mean() * 100.0).backward()
+    for n, p in m.named_parameters():
+        if 'embedding' in n:
+            assert rel_err(p.grad.cpu().numpy(), g['grad/' + n]) < 2e-3, n

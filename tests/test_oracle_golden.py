@@ -172,6 +172,38 @@ def test_live_reference_adapter_state_dict_is_identical(train_net, position):
     assert all(torch.equal(a[k], b[k]) for k in a)
 
 
+def test_embed_network_oracle_against_reference_fixture():
+    g = load_golden('embed')
+    sd = golden_state_dict(g)
+    torch.set_num_threads(1)
+    np.testing.assert_allclose(O.embedding_forward(sd, 'scene_embedding', g['scene']).numpy(), g['scene_emb'],
+                               rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(O.embedding_forward(sd, 'motion_embedding', g['motion']).numpy(), g['motion_emb'],
+                               rtol=1e-5, atol=1e-6)
+
+
+def test_semantic_adapter_mirrors_the_reference_failure():
+    """ynet.py:516 passes position=None into get_conv2d (ynet.py:140): the reference raises TypeError; so does the drop-in."""
+    from motion_style_transfer_b200.models.ynet import YNet
+    kw = dict(obs_len=5, pred_len=6, segmentation_model_fp=None, encoder_channels=[8, 8, 16, 16, 16],
+              decoder_channels=[16, 16, 16, 8, 8], n_waypoints=2, train_net='semantic_3x3', position=[], network='original')
+    with pytest.raises(TypeError):
+        YNet(**kw)
+    if ref_harness.available():
+        with pytest.raises(TypeError):
+            ref_harness.load().ynet.YNet(**kw)
+
+
+def test_swap_pavement_terrain_host_logic():
+    from motion_style_transfer_b200.utils.image_utils import swap_pavement_terrain
+    x = torch.arange(2 * 6 * 3 * 4, dtype=torch.float32).reshape(2, 6, 3, 4)
+    assert torch.equal(swap_pavement_terrain(x), O.swap_pavement_terrain(x))
+    if ref_harness.available():
+        assert torch.equal(swap_pavement_terrain(x), ref_harness.load().image_utils.swap_pavement_terrain(x.clone()))
+    with pytest.raises(ValueError):
+        swap_pavement_terrain(x[0])
+
+
 class _ReplayRng:
     """Feeds the randoms recorded in the fixture instead of drawing from global RNGs."""
 
