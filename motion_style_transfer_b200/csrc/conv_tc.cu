@@ -24,7 +24,6 @@
 namespace ynet {
 
 constexpr int TC_TH = 16;                            // output tile height; width = 8 * J pixels (J accumulators)
-constexpr int TC_BH = TC_TH + 2;                     // halo box height; width = 8 * J + 2
 constexpr int TC_KB = 16;                            // channels per pipeline stage (one UMMA K step)
 constexpr int TC_MAX_J = 3;                          // 4-D TMA box: (8J+2)*8 elements <= 256
 constexpr int TC_THREADS = 192;
@@ -350,26 +349,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
                 }
               }
             }
-          } else if (EPI == EPI_UP2) {
-            // phase-decomposed bilinear-x2 + conv: channel group c0 belongs to output phase (a, b) and lands on
-            // the high-resolution pixel (2y + a, 2x + b) (depth-to-space in the store)
-            if (inb) {
-              const int cp = p.n_pad >> 2;                 // padded C_out of one phase (multiple of 16)
-              const int phase = c0 / cp, o0 = c0 - phase * cp;
-              const int ya = 2 * y + (phase >> 1), xb2 = 2 * x + (phase & 1);
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int chunk = (o0 >> 3) + h;
-                uint4 o;
-                o.x = pack_bf16(f[8 * h + 0], f[8 * h + 1]);
-                o.y = pack_bf16(f[8 * h + 2], f[8 * h + 3]);
-                o.z = pack_bf16(f[8 * h + 4], f[8 * h + 5]);
-                o.w = pack_bf16(f[8 * h + 6], f[8 * h + 7]);
-                __nv_bfloat16* dst =
-                    p.out + ((((size_t)n * (cp >> 3) + chunk) * (2 * p.H) + ya) * (size_t)(2 * p.W) + xb2) * 8;
-                *reinterpret_cast<uint4*>(dst) = o;
-              }
-            }
           } else if (EPI == EPI_HILO) {
             // raw partial sums as a bf16 pair: hi = bf16(f), lo = bf16(f - hi); channels [hi: n_pad | lo: n_pad]
             if (inb) {
@@ -520,7 +499,6 @@ tc_conv_pred_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
       }
     }
   };
-  const int wblk_bytes = 9 * 2 * p.n_pad * 16;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
