@@ -122,38 +122,129 @@ class ClockSampler:
                     samples=len(sm))
 
 
+def _reference_evaluate(model_state, cfg, B, device, seeds, ns):
+    """One call of the UNMODIFIED reference's utils/evaluate.py::evaluate (evaluate.py:37-315) on one synthetic scene of B
+    agents through its own SceneDataset / DataLoader; returns (seconds, ade, fde).  `ns` = oracle.ref_harness.load()."""
+    import pandas as pd
+    import warnings
+    from torch.utils.data import DataLoader
+    from motion_style_transfer_b200 import synthetic as S
+    m = ns.ynet.YNet(obs_len=cfg['obs'], pred_len=cfg['pred'], segmentation_model_fp=None, encoder_channels=ENC,
+                     decoder_channels=DEC, n_waypoints=len(cfg['wps']), train_net='mosa_1', position=[0, 1, 2, 3, 4],
+                     network='original')
+    m.load_state_dict(model_state, strict=True)
+    m = m.to(device).eval()
+    total = cfg['obs'] + cfg['pred']
+    tracks = S.synthetic_tracks(B, total, H, W, seed=seeds[0]) / cfg['resize']
+    rows = [dict(frame=t, trackId=b, x=float(tracks[b, t, 0]), y=float(tracks[b, t, 1]), sceneId='s0', metaId=b)
+            for b in range(B) for t in range(total)]
+    ds = ns.dataloader.SceneDataset(pd.DataFrame(rows), resize=cfg['resize'], total_len=total)
+    dl = DataLoader(ds, batch_size=1, collate_fn=ns.dataloader.scene_collate)
+    tmpl = torch.Tensor(ns.image_utils.create_dist_mat(int(4200 * cfg['resize'])))
+    images = {'s0': S.synthetic_scene(H, W, seed=0)}
+    torch.manual_seed(seeds[1])
+    np.random.seed(seeds[2])
+    if torch.device(device).type == 'cuda':
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ade, fde, _, _ = ns.evaluate.evaluate(m, dl, images, device, 'sdd', None, tmpl, cfg['wps'], 'test', cfg['n_goal'],
+                                              cfg['n_traj'], cfg['obs'], B, cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'],
+                                              cfg['thr'], cfg['cwsp'], network='original')
+    if torch.device(device).type == 'cuda':
+        torch.cuda.synchronize()
+    return time.perf_counter() - t0, float(ade), float(fde)
+
+
+def _torch_network_only(model_state, cfg, B, device, ns):
+    """The reference's own network calls of one evaluate() batch -- pred_features, pred_goal, n_goal x (pred_traj +
+    softargmax) (evaluate.py:123-126, 248-266) -- on `device`, inputs resident, under fp32 (TF32 convs) and bf16 autocast:
+    the cuDNN number the hand-written engine has to beat on the same silicon."""
+    m = ns.ynet.YNet(obs_len=cfg['obs'], pred_len=cfg['pred'], segmentation_model_fp=None, encoder_channels=ENC,
+                     decoder_channels=DEC, n_waypoints=len(cfg['wps']), train_net='mosa_1', position=[0, 1, 2, 3, 4],
+                     network='original')
+    m.load_state_dict(model_state, strict=True)
+    m = m.to(device).eval()
+    g = torch.Generator(device='cpu').manual_seed(0)
+    sem = torch.softmax(torch.randn(1, 6, H, W, generator=g), 1).to(device).expand(B, -1, -1, -1)
+    obs = torch.rand(B, cfg['obs'], H, W, generator=g).to(device)
+    wp = torch.rand(B, len(cfg['wps']), H, W, generator=g).to(device)
+    pools = [torch.nn.AvgPool2d(2 ** i, 2 ** i) for i in range(1, 6)]
+    out = {}
+
+    def body():
+        feats = m.pred_features(sem, obs)
+        m.pred_goal(feats)
+        for _ in range(cfg['n_goal'] * cfg['n_traj']):
+            pyr = [wp] + [p(wp) for p in pools]
+            m.softargmax(m.pred_traj([torch.cat([f, w], dim=1) for f, w in zip(feats, pyr)]))
+
+    for name, ctx in (('tf32', torch.autocast('cuda', enabled=False)), ('bf16_autocast', torch.autocast('cuda', dtype=torch.bfloat16))):
+        with torch.no_grad(), ctx:
+            body()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                body()
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 2
+        out[name] = dict(ms_per_batch=ms, agent_trajectories_per_s=B * cfg['n_goal'] * cfg['n_traj'] / (ms / 1000))
+    out['what'] = f'{B} agents, inputs resident, CUDA events; no sampling / k-means / CWS / rasterisation'
+    return out
+
+
 def run_reference(args, cfg, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path = the oracle port
-    (oracle/ynet_oracle.py, pinned bit-for-bit against the live reference), on all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path on all host threads.  When the unmodified
+    reference is importable (oracle/_ref staged by oracle/build_ref.py, or /root/reference) this is its
+    utils/evaluate.py::evaluate itself (kind "reference"); otherwise the oracle port (kind "port")."""
     if rank != 0:
         return
-    from oracle import ynet_oracle as O
+    from oracle import ref_harness
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     m = build_model_state(cfg)
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
-    scene = O.synthetic_scene(H, W, seed=0)[None]
-    tmpl = O.create_dist_mat(int(4200 * cfg['resize'])).astype(np.float32)
     B = args.ref_agents
+    kind = 'reference' if ref_harness.available() else 'port'
     times = []
-    for it in range(args.warmup + args.steps):
-        traj = O.synthetic_tracks(B, cfg['obs'] + cfg['pred'], H, W, seed=100 + it)
-        torch.manual_seed(1000 + it)
-        np.random.seed(2000 + it)
-        t0 = time.perf_counter()
-        O.evaluate_batch(sd, scene, traj, tmpl, cfg['wps'], cfg['n_goal'], cfg['n_traj'], cfg['obs'], cfg['resize'],
-                         cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'], cfg['cwsp'])
-        if it >= args.warmup:
-            times.append(time.perf_counter() - t0)
+    if kind == 'reference':
+        ns = ref_harness.load()
+        for it in range(args.warmup + args.steps):
+            dt, _, _ = _reference_evaluate(sd, cfg, B, 'cpu', (100 + it, 1000 + it, 2000 + it), ns)
+            if it >= args.warmup:
+                times.append(dt)
+    else:
+        from oracle import ynet_oracle as O
+        scene = O.synthetic_scene(H, W, seed=0)[None]
+        tmpl = O.create_dist_mat(int(4200 * cfg['resize'])).astype(np.float32)
+        for it in range(args.warmup + args.steps):
+            traj = O.synthetic_tracks(B, cfg['obs'] + cfg['pred'], H, W, seed=100 + it)
+            torch.manual_seed(1000 + it)
+            np.random.seed(2000 + it)
+            t0 = time.perf_counter()
+            O.evaluate_batch(sd, scene, traj, tmpl, cfg['wps'], cfg['n_goal'], cfg['n_traj'], cfg['obs'], cfg['resize'],
+                             cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'], cfg['cwsp'])
+            if it >= args.warmup:
+                times.append(time.perf_counter() - t0)
     ms = 1000 * sum(times) / len(times)
     val = B * cfg['n_goal'] * cfg['n_traj'] / (ms / 1000)
-    sample = f'{B} agents x {cfg["n_goal"] * cfg["n_traj"]} trajectories per step, {args.steps} steps, 416x416'
+    what = ('unmodified reference utils/evaluate.py::evaluate on device cpu' if kind == 'reference'
+            else 'oracle port (reference not staged)')
+    sample = (f'{what}: {B} agents x {cfg["n_goal"] * cfg["n_traj"]} trajectories per step (one scene, one batch), '
+              f'{args.steps} steps, 416x416, torch CPU fp32 with {threads} threads; the GPU arm runs the same workload with '
+              f'{args.agents} agents per step -- a CPU step of that size would take ~{ms / 1000 * args.agents / B / 60:.0f} min')
     print(json.dumps({
         'impl': 'reference', 'metric': 'agent-trajectories/sec', 'value': val, 'unit': 'agent-trajectories/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(args, cfg), 'agents_per_step': B},
-        'cpu_baseline': {'value': val, 'unit': 'agent-trajectories/s', 'cores': threads, 'kind': 'port',
+        'config': {'workload': workload_name(args, cfg), 'agents_per_step': B,
+                   'agents_per_step_note': 'bounded sample of the GPU arm\'s workload (same scene size, model, TTST/CWS '
+                                           'settings); throughput per agent-trajectory does not depend on the batch size '
+                                           'on the CPU (per-agent Python loops)'},
+        'cpu_baseline': {'value': val, 'unit': 'agent-trajectories/s', 'cores': threads, 'kind': kind,
                          'sample': sample},
         'e2e': {'value': val, 'unit': 'agent-trajectories/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
@@ -176,6 +267,8 @@ def main():
     ap.add_argument('--ref-agents', type=int, default=2, help='agents per step of the CPU reference arm')
     ap.add_argument('--cpu-agents', type=int, default=4, help='agents of the bounded cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--torch-cuda-agents', type=int, default=32,
+                    help='agents of the secondary bar: the unmodified reference on device cuda (0 = skip)')
     ap.add_argument('--no-roofline', action='store_true', help='skip the per-launch eager timing pass')
     ap.add_argument('--profile-layers', default=None, help='write a per-layer timing table to this path')
     ap.add_argument('--no-graph', dest='graph', action='store_false',
@@ -204,7 +297,7 @@ def main():
     _lib.load()
 
     model = build_model_state(cfg).to(dev).eval().set_backend(args.backend)
-    from oracle import ynet_oracle as O          # synthetic-input generators only (test infrastructure)
+    from motion_style_transfer_b200 import synthetic as O      # synthetic-input generators (the product never imports oracle)
     scene_host = O.synthetic_scene(H, W, seed=0)[None].contiguous().pin_memory()
     tmpl = ops.create_dist_template(int(4200 * cfg['resize']), dev)
     B = args.agents
@@ -363,24 +456,48 @@ def main():
             with open(args.profile_layers, 'w') as f:
                 json.dump(dict(step_ms=sum(p['ms'] for p in prof), launches=prof), f, indent=1)
 
-    # ---- bounded CPU baseline (oracle port) on this host, rank 0 at N=1 only ------------------------------
-    cpu_baseline = None
+    # ---- bounded CPU baseline on this host, rank 0 at N=1 only: the unmodified reference's evaluate() when staged
+    # (oracle/_ref, kind "reference"), else the oracle port.  The only place the b200 arm touches oracle/ (as the checker
+    # being TIMED next to the product, never as part of it) --------------------------------------------------------------
+    cpu_baseline, torch_cuda = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ref_harness
         threads = os.cpu_count() or 1
         torch.set_num_threads(threads)
         sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
         Bc = args.cpu_agents
-        traj = O.synthetic_tracks(Bc, total_len, H, W, seed=77)
-        tm = O.create_dist_mat(int(4200 * cfg['resize'])).astype(np.float32)
-        torch.manual_seed(1)
-        np.random.seed(2)
-        t0 = time.perf_counter()
-        O.evaluate_batch(sd, scene_host, traj, tm, cfg['wps'], cfg['n_goal'], cfg['n_traj'], cfg['obs'],
-                         cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'], cfg['cwsp'])
-        dt = time.perf_counter() - t0
+        if ref_harness.available():
+            ns = ref_harness.load()
+            dt, _, _ = _reference_evaluate(sd, cfg, Bc, 'cpu', (77, 1, 2), ns)
+            kind, what = 'reference', 'unmodified reference utils/evaluate.py::evaluate, device cpu'
+        else:
+            from oracle import ynet_oracle as ORC
+            traj = ORC.synthetic_tracks(Bc, total_len, H, W, seed=77)
+            tm = ORC.create_dist_mat(int(4200 * cfg['resize'])).astype(np.float32)
+            torch.manual_seed(1)
+            np.random.seed(2)
+            t0 = time.perf_counter()
+            ORC.evaluate_batch(sd, scene_host, traj, tm, cfg['wps'], cfg['n_goal'], cfg['n_traj'], cfg['obs'],
+                               cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'], cfg['cwsp'])
+            dt = time.perf_counter() - t0
+            kind, what = 'port', 'oracle port'
         cpu_baseline = dict(value=Bc * cfg['n_goal'] * cfg['n_traj'] / dt, unit='agent-trajectories/s', cores=threads,
-                            kind='port', sample=f'{Bc} agents x {cfg["n_goal"]} trajectories, one batch, '
-                                                f'{dt:.1f} s, torch CPU fp32 with {threads} threads')
+                            kind=kind, sample=f'{what}: {Bc} agents x {cfg["n_goal"]} trajectories, one batch, '
+                                              f'{dt:.1f} s, torch CPU fp32 with {threads} threads')
+        # ---- the secondary bar: the SAME unmodified reference on device='cuda', i.e. stock
+        # PyTorch / cuDNN on this very B200 (TF32 convs = torch's default; host-side per-agent k-means as the reference
+        # has it), and its network alone (encoder + goal decoder + 20 trajectory-decoder passes) under bf16 autocast
+        if ref_harness.available() and args.torch_cuda_agents > 0:
+            try:
+                Bt = args.torch_cuda_agents
+                _reference_evaluate(sd, cfg, min(Bt, 4), dev, (78, 3, 4), ns)              # warm-up (cuDNN autotune)
+                dt, _, _ = _reference_evaluate(sd, cfg, Bt, dev, (79, 5, 6), ns)
+                torch_cuda = dict(value=Bt * cfg['n_goal'] * cfg['n_traj'] / dt, unit='agent-trajectories/s',
+                                  what='unmodified reference evaluate() on device cuda (PyTorch eager + cuDNN, TF32 convs, '
+                                       f'host k-means as in kmeans.py:146-148), {Bt} agents in one batch, {dt:.2f} s')
+                torch_cuda['network_only'] = _torch_network_only(sd, cfg, Bt, dev, ns)
+            except Exception as e:      # the secondary bar must never break the bench line
+                torch_cuda = dict(error=repr(e)[:300])
 
     if rank == 0:
         out = {
@@ -394,6 +511,7 @@ def main():
             'e2e': {'value': e2e_value, 'unit': 'agent-trajectories/s', 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+            'torch_cuda_baseline': torch_cuda,
             'kernels': kernel_table,
             'diag': {'step_ms': step_list, 'host_issue_ms': host_ms, 'mem': mem_diag, 'kmeans_max_iters': km_diag,
                      'e2e_step_ms': [a.elapsed_time(b) for a, b in zip([e2] + e2e_marks[:-1], e2e_marks)],

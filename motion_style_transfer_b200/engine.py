@@ -56,6 +56,13 @@ def _module_version(module):
     return tuple((t._version, t.data_ptr()) for t in list(module.parameters()) + list(module.buffers()))
 
 
+def _bias_version(module):
+    """Cache-key part for a conv's bias: bias-only fine-tuning (train_net 'bias*', trainer.py:150-175) updates it in
+    place while the weight never changes."""
+    b = getattr(module, 'bias', None)
+    return None if b is None else (b._version, b.data_ptr())
+
+
 def _bn_affine(bn):
     """Eval-mode BatchNorm2d as y = a * x + b per channel."""
     if bn.training:
@@ -301,7 +308,7 @@ class YNetEngineTC(YNetEngine):
         Bm = getattr(module, 'lora_B', None)
         ver = (module.weight._version, module.weight.data_ptr(),
                None if A is None else (A._version, A.data_ptr()),
-               None if Bm is None else (Bm._version, Bm.data_ptr()), tuple(src_channels),
+               None if Bm is None else (Bm._version, Bm.data_ptr()), tuple(src_channels), _bias_version(module),
                _module_version(module) if _is_adapter_layer(module) else None)
         hit = self._wcache.get(key)
         if hit is not None and hit[0] == ver:
@@ -320,7 +327,7 @@ class YNetEngineTC(YNetEngine):
 
     def _tc_up_params(self, module, key, src_channels):
         """Phase-decomposed weights of an upsample_conv (bilinear x2 folded into the stencil), cached by version."""
-        ver = (module.weight._version, module.weight.data_ptr(), tuple(src_channels))
+        ver = (module.weight._version, module.weight.data_ptr(), tuple(src_channels), _bias_version(module))
         hit = self._wcache.get(key + '#up')
         if hit is not None and hit[0] == ver:
             return hit[1:]
@@ -421,7 +428,7 @@ class YNetEngineTC(YNetEngine):
         x = self.decoder_trunk(decoder, key, features)
         p = decoder.predictor
         channels = tuple(int(c) % p.weight.shape[0] for c in channels)
-        ver = (p.weight._version, p.weight.data_ptr(), p.bias._version, channels, x.C)
+        ver = (p.weight._version, p.weight.data_ptr(), _bias_version(p), channels, x.C)
         hit = self._wcache.get(f'{key}.predictor#subset')
         if hit is None or hit[0] != ver:
             idx = torch.tensor(channels, device=p.weight.device)
@@ -448,7 +455,7 @@ class YNetEngineTC(YNetEngine):
 
     def _hoist_params(self, module, key, layout):
         """Packed weights (+ padded bias) of a conv whose sources are ``layout``: ('conv', (c0, c1)) | ('partial', C_out)."""
-        ver = (module.weight._version, module.weight.data_ptr(), tuple(layout))
+        ver = (module.weight._version, module.weight.data_ptr(), tuple(layout), _bias_version(module))
         hit = self._wcache.get(key + '#hoist')
         if hit is not None and hit[0] == ver:
             return hit[1], hit[2]

@@ -7,6 +7,7 @@ Data preparation (pandas / cv2 / segmentation preprocessing, trainer.py:518-584)
 path: ``prepare_data`` delegates to the reference's own ``utils.data_utils`` when it is importable,
 and ``train_prepared`` / ``test_prepared`` accept ready-made (images dict, DataLoader) pairs.
 """
+import os
 import pathlib
 import re
 from collections import OrderedDict, deque
@@ -124,14 +125,26 @@ class FusedAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
+        dp = parallel.world()[1] > 1
         for group in self.param_groups:
-            flat, ps = parallel.flatten_grads(group['params'])
+            # Under data parallelism the flat buffer has ONE layout on every rank (all trainable tensors, zeros where a
+            # rank has no gradient) followed by one "has a gradient" flag per tensor: after the SUM a tensor is stepped
+            # iff some rank produced a gradient for it -- torch.optim.Adam's skip-if-None rule, decided globally.
+            flat, ps = parallel.flatten_grads(group['params'], fixed_layout=dp)
             if not ps:
                 continue
+            n_grad = sum(p.numel() for p in ps)
+            if dp:
+                flags = torch.tensor([0.0 if p.grad is None else 1.0 for p in ps], dtype=flat.dtype, device=flat.device)
+                flat = torch.cat([flat, flags])
             grad_scale = parallel.allreduce_flat(flat)          # ONE collective per step; mean taken in the kernel
+            live = (flat[n_grad:] > 0).tolist() if dp else [True] * len(ps)
             off = 0
-            for p in ps:
+            for p, has_grad in zip(ps, live):
                 n = p.numel()
+                if not has_grad:
+                    off += n
+                    continue
                 st = self.state[p]
                 if not st:
                     st['step'] = 0
@@ -188,6 +201,14 @@ class YNetTrainer:
                smooth_val=False, **kwargs):
         model = self.model.to(self.device)
         apply_freeze_policy(model, train_net, position, network, ynet_bias)
+        if 'segmentation' in str(train_net):
+            # trainer.py:176-184 marks segmentation-backbone tensors trainable, and train_epoch.py:34-47 then runs the
+            # backbone with gradients once epoch >= e_unfreeze.  The backbone is outside the B200 path (it runs under
+            # no_grad here), so such a run would silently train nothing.
+            raise NotImplementedError("train_net='segmentation_*' fine-tunes the segmentation backbone, which is outside "
+                                      'the B200 hot path')
+        # one process per GPU: every rank starts from rank 0's trainable tensors (LoRA A is random per process)
+        parallel.broadcast_params([p for p in model.parameters() if p.requires_grad])
         optimizer = FusedAdam(model.parameters(), lr=lr)
         if fine_tune:
             print('LR Schedular because finetuning')
@@ -239,10 +260,11 @@ class YNetTrainer:
                 best_state_dict = curr_model_dict
                 if not fine_tune:
                     print(f'Best Epoch {e}: \nVal ADE: {val_ADE} \nVal FDE: {val_FDE}')
-                    pathlib.Path(ckpt_path).mkdir(parents=True, exist_ok=True)
-                    torch.save(model.state_dict(), f'{ckpt_path}/{experiment_name}_weights.pt')
+                    if parallel.world()[0] == 0:        # replicas are identical: one writer
+                        pathlib.Path(ckpt_path).mkdir(parents=True, exist_ok=True)
+                        torch.save(model.state_dict(), f'{ckpt_path}/{experiment_name}_weights.pt')
+                    parallel.barrier()
             if (e + 1) % save_every_n == 0:
-                pathlib.Path(ckpt_path).mkdir(parents=True, exist_ok=True)
                 self.save_params(f'{ckpt_path}/{experiment_name}__epoch_{e}.pt', train_net)
             if fine_tune and (best_val_ADE < min(self.val_ADE[-n_early_stop:])):
                 print(f'Early stop at epoch {e}')
@@ -250,7 +272,6 @@ class YNetTrainer:
         print(f'Best epoch at {best_epoch}')
         if best_epoch != 0 and best_state_dict is not None:
             model.load_state_dict(best_state_dict, strict=True)
-        pathlib.Path(ckpt_path).mkdir(parents=True, exist_ok=True)
         self.save_params(f'{ckpt_path}/{experiment_name}.pt', train_net)
         return self.val_ADE, self.val_FDE
 
@@ -322,7 +343,8 @@ class YNetTrainer:
                                            use_raw_data=use_raw_data)
             print('Augmented data and images')
         dataset = SceneDataset(df, resize=resize_factor, total_len=obs_len + pred_len)
-        dataloader = DataLoader(dataset, batch_size=1, collate_fn=scene_collate, shuffle=(mode == 'train'))
+        dataloader = DataLoader(dataset, batch_size=1, collate_fn=scene_collate, shuffle=(mode == 'train'),
+                                generator=parallel.shared_generator() if mode == 'train' else None)
         resize(images_dict, factor=resize_factor, seg_mask=False)
         pad(images_dict, division_factor=self.division_factor)
         preprocess_image_for_segmentation(images_dict, seg_mask=False)
@@ -341,7 +363,14 @@ class YNetTrainer:
             for name, param in self.model.named_parameters():
                 if param.requires_grad:
                     state_dict[name] = param
-        torch.save(state_dict, path)
+        # one process per GPU: the replicas hold identical tensors, rank 0 alone writes (concurrent torch.save calls on
+        # one path corrupt the file); everyone waits so that a following load sees the complete file
+        if parallel.world()[0] == 0:
+            parent = os.path.dirname(str(path))
+            if parent:
+                pathlib.Path(parent).mkdir(parents=True, exist_ok=True)
+            torch.save(state_dict, path)
+        parallel.barrier()
 
     def load_separated_params(self, pretrained_path, tuned_path):
         self.model.load_state_dict(torch.load(pretrained_path, map_location=self.device), strict=False)

@@ -37,13 +37,20 @@ def _req(t, dtype=torch.float32, name='tensor'):
 
 
 _ws_cache = {}
+_ws_retired = []      # outgrown buffers stay alive: a captured CUDA graph may have their addresses baked in
 
 
 def _workspace(nbytes, device, tag):
-    """Caller-owned scratch, grown on demand and reused per (device, tag)."""
+    """Caller-owned scratch, grown on demand and reused per (device, tag).
+
+    A buffer that a larger request outgrows is retired, never freed: ``GraphedForecaster`` captures these pointers into
+    a CUDA graph, and a later eager call with a bigger batch must not hand the memory the graph still replays into back
+    to the allocator.  (Scratch sizes are a few MB; the retired list grows only when a size record is broken.)"""
     key = (device, tag)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _ws_retired.append(buf)
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf

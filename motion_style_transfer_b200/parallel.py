@@ -60,7 +60,8 @@ def gather_rows(local, n_total):
 
 
 def reduce_metric_sums(sum_ade, sum_fde, count, device=None):
-    """One SUM all-reduce of (sum ADE, sum FDE, n agents) -> global means."""
+    """One SUM all-reduce of (sum ADE, sum FDE, n) -> global means.  ``count`` is THIS rank's share of n
+    (agents of its shard; 1 per rank for a mean over ranks): the counts are summed like the values."""
     t = torch.tensor([float(sum_ade), float(sum_fde), float(count)], dtype=torch.float64, device=device)
     if world()[1] > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -68,8 +69,18 @@ def reduce_metric_sums(sum_ade, sum_fde, count, device=None):
     return t[0].item() / n, t[1].item() / n, int(t[2].item())
 
 
-def flatten_grads(params):
-    """The trainable tensors' gradients as ONE contiguous buffer (+ the params that contributed, in order)."""
+def flatten_grads(params, fixed_layout=False):
+    """The trainable tensors' gradients as ONE contiguous buffer (+ the params that contributed, in order).
+
+    ``fixed_layout`` (used whenever the buffer feeds a collective): every trainable tensor takes part, a missing
+    gradient counts as zero -- all ranks then build the same layout even if one of them saw no agents or a tensor
+    received no gradient on it, so the all-reduce sizes always match."""
+    if fixed_layout:
+        ps = [p for p in params if p.requires_grad]
+        if not ps:
+            return None, ps
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in ps])
+        return flat, ps
     ps = [p for p in params if p.requires_grad and p.grad is not None]
     if not ps:
         return None, ps
@@ -91,3 +102,27 @@ def broadcast_params(params, src=0):
         return
     for p in params:
         dist.broadcast(p.data, src=src)
+
+
+def barrier():
+    if world()[1] > 1:
+        dist.barrier()
+
+
+def shared_generator(seed=None):
+    """A torch.Generator whose state is identical on every rank (rank 0 draws the seed, everyone adopts it).
+
+    ``train_epoch`` shards the AGENTS of each batch across ranks, which presumes that all ranks walk the scenes in the
+    same order: the shuffling train DataLoader must therefore draw from a shared stream, not from each process's own
+    default generator."""
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+    if world()[1] > 1:
+        t = torch.tensor([seed], dtype=torch.int64)
+        if dist.get_backend() == 'nccl':
+            t = t.cuda()
+        dist.broadcast(t, src=0)
+        seed = int(t.item())
+    g = torch.Generator()
+    g.manual_seed(seed)
+    return g

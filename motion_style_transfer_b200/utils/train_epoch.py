@@ -21,6 +21,11 @@ def train_epoch(model, train_loader, train_images, optimizer, criterion, loss_sc
     train_loss = torch.zeros((), device=device)
     world_size = parallel.world()[1]
     trainable = [p for p in model.parameters() if p.requires_grad]
+    if any(p.requires_grad for p in model.semantic_segmentation.parameters()):
+        # train_epoch.py:34-47 re-runs the segmentation backbone WITH gradients once epoch >= e_unfreeze; here it runs
+        # once per scene under no_grad (the backbone is outside the B200 path), which would train nothing, silently.
+        raise NotImplementedError('fine-tuning the segmentation backbone (train_net=segmentation_*, e_unfreeze) is '
+                                  'outside the B200 hot path')
     train_ADE, train_FDE = [], []
     model.train()
     input_template = input_template.to(device=device, dtype=torch.float32)
@@ -91,5 +96,5 @@ def train_epoch(model, train_loader, train_images, optimizer, criterion, loss_sc
     if world_size == 1:
         return train_ADE.mean().item(), train_FDE.mean().item(), train_loss.item()
     ade, fde, _ = parallel.reduce_metric_sums(train_ADE.sum().item(), train_FDE.sum().item(), train_ADE.numel(), device)
-    loss_sum, _, _ = parallel.reduce_metric_sums(train_loss.item(), 0.0, world_size, device)   # mean over ranks
+    loss_sum, _, _ = parallel.reduce_metric_sums(train_loss.item(), 0.0, 1, device)   # mean over ranks (count 1 each)
     return ade, fde, loss_sum

@@ -1,10 +1,10 @@
-"""Import the UNMODIFIED reference from /root/reference (test infrastructure only).
+"""Import the UNMODIFIED reference (test / bench infrastructure only).
 
-Only usable in the build container: /root/reference does not exist on the GPU
-box, so nothing that runs there (``-m gpu`` tests, ``smoke()``, ``bench.py``) may
-call into this module.  It is used by ``oracle/gen_golden.py`` to produce the
-committed fixtures under ``tests/golden/`` and by the ``not gpu`` tests that pin
-the restatement in ``oracle/ynet_oracle.py`` against the live reference.
+Two locations: /root/reference in the build container, or the byte-identical staged copy
+``oracle/_ref/reference`` that ``oracle/build_ref.py`` makes (git-ignored, travels to the GPU box,
+where /root/reference does not exist).  Used by ``oracle/gen_golden.py`` to produce the committed
+fixtures under ``tests/golden/``, by the tests that pin ``oracle/ynet_oracle.py`` against the live
+reference, and by ``bench.py --impl reference`` (the reference's own evaluate() on the host cores).
 
 Recipe follows SURVEY.md Appendix A:
   * ``loralib`` -> ``oracle/loralib_restatement.py`` (package not installed);
@@ -16,7 +16,17 @@ import os
 import sys
 import types
 
-REF_PATH = os.environ.get('REF_PATH', '/root/reference')
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref', 'reference')
+
+
+def _find_ref():
+    for p in (os.environ.get('REF_PATH'), '/root/reference', _STAGED):
+        if p and os.path.isdir(os.path.join(p, 'models')):
+            return p
+    return os.environ.get('REF_PATH', '/root/reference')
+
+
+REF_PATH = _find_ref()
 
 _loaded = {}
 

@@ -305,3 +305,13 @@ def test_train_epoch_against_reference_fixture(tag, network):
         np.testing.assert_allclose(sd_after[k].numpy(), g['trained/' + k], rtol=0, atol=2e-6)
         ref = g['lastgrad/' + k]
         np.testing.assert_allclose(grads[k].numpy(), ref, rtol=0, atol=1e-4 * max(np.abs(ref).max(), 1e-6))
+
+
+def test_product_synthetic_generators_match_the_oracles():
+    """bench.py / tools feed the product from motion_style_transfer_b200.synthetic (the product never imports oracle);
+    the oracle's own generators must produce the same tensors so that both arms see identical inputs."""
+    from motion_style_transfer_b200 import synthetic as S
+    assert torch.equal(S.synthetic_scene(32, 64, seed=3), O.synthetic_scene(32, 64, seed=3))
+    for jitter in (0.0, 0.5):
+        assert torch.equal(S.synthetic_tracks(5, 35, 64, 96, seed=7, jitter=jitter),
+                           O.synthetic_tracks(5, 35, 64, 96, seed=7, jitter=jitter))

@@ -112,3 +112,31 @@ def _grad_case(rank, world):
 def test_flat_gradient_allreduce_matches_full_batch_gloo():
     res = _run(_grad_case)
     assert res[0] and res[1]
+
+
+def _layout_case(rank, world):
+    """Fixed-layout flat gradients: a tensor without a gradient on one rank still lines up, the loss mean
+    over ranks is sum / world (count 1 per rank), and the shared generator gives every rank the same scene order."""
+    a = torch.nn.Parameter(torch.ones(3))
+    b = torch.nn.Parameter(torch.ones(2))
+    if rank == 0:
+        a.grad = torch.full((3,), 2.0)          # rank 0: only `a` has a gradient
+    else:
+        a.grad = torch.full((3,), 4.0)
+        b.grad = torch.full((2,), 6.0)
+    flat, ps = parallel.flatten_grads([a, b], fixed_layout=True)
+    ok = len(ps) == 2 and flat.numel() == 5
+    scale = parallel.allreduce_flat(flat)
+    ok = ok and torch.allclose(flat * scale, torch.tensor([3.0, 3.0, 3.0, 3.0, 3.0]))
+    mean_loss, _, n = parallel.reduce_metric_sums(10.0 * (rank + 1), 0.0, 1)
+    ok = ok and abs(mean_loss - 15.0) < 1e-12 and n == world
+    torch.manual_seed(100 + rank)               # different default streams per process
+    perm = torch.randperm(16, generator=parallel.shared_generator()).tolist()
+    parallel.barrier()
+    return bool(ok), perm
+
+
+def test_fixed_layout_loss_mean_and_shared_generator_gloo():
+    res = _run(_layout_case)
+    assert res[0][0] and res[1][0]
+    assert res[0][1] == res[1][1]

@@ -23,7 +23,8 @@ import bench  # noqa: E402
 from motion_style_transfer_b200 import ops  # noqa: E402
 from motion_style_transfer_b200.utils.dataloader import SceneDataset, scene_collate  # noqa: E402
 from motion_style_transfer_b200.utils.evaluate import evaluate  # noqa: E402
-from oracle import ynet_oracle as O  # noqa: E402  (synthetic input generators only)
+from motion_style_transfer_b200.utils.image_utils import create_dist_mat  # noqa: E402
+from motion_style_transfer_b200 import synthetic as O  # noqa: E402  (synthetic input generators)
 
 
 def main():
@@ -45,7 +46,7 @@ def main():
                                  metaId=s * args.agents + b))
         images[f's{s}'] = O.synthetic_scene(bench.H, bench.W, seed=s)
     df = pd.DataFrame(rows)
-    tmpl = torch.from_numpy(O.create_dist_mat(int(4200 * cfg['resize'])).astype(np.float32))
+    tmpl = torch.Tensor(create_dist_mat(size=int(4200 * cfg['resize'])))
 
     def run(frame):
         loader = DataLoader(SceneDataset(frame, resize=cfg['resize'], total_len=total), batch_size=1,

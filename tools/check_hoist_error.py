@@ -10,7 +10,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from motion_style_transfer_b200 import ops  # noqa: E402
-from oracle import ynet_oracle as O  # noqa: E402  (synthetic inputs only)
+from motion_style_transfer_b200 import synthetic as O  # noqa: E402  (synthetic input generators)
 
 cfg = bench.WORKLOADS['ind_long_ttst_cws']
 H = W = 416
