@@ -140,7 +140,7 @@ def _reference_evaluate(model_state, cfg, B, device, seeds, ns):
             for b in range(B) for t in range(total)]
     ds = ns.dataloader.SceneDataset(pd.DataFrame(rows), resize=cfg['resize'], total_len=total)
     dl = DataLoader(ds, batch_size=1, collate_fn=ns.dataloader.scene_collate)
-    tmpl = torch.Tensor(ns.image_utils.create_dist_mat(int(4200 * cfg['resize'])))
+    tmpl = torch.Tensor(ns.image_utils.create_dist_mat(int(4200 * cfg['resize']))).to(device)      # trainer.py:326
     images = {'s0': S.synthetic_scene(H, W, seed=0)}
     torch.manual_seed(seeds[1])
     np.random.seed(seeds[2])

@@ -330,6 +330,32 @@ int ynet_tc_conv1x1_softargmax(const ynet_tc_src* srcs_host, int32_t n_src, int3
                                const void* packed_weight, const float* bias, int32_t C_out, float* out,
                                void* workspace, int64_t workspace_bytes, int32_t tune, void* stream);
 
+/* Row-marching, kh-stacked 3x3 conv for the C_out <= 32 layers of the decoders' full-resolution levels
+ * (ynet.py:466-468: decoder.4.2, decoder.3.2) -- rowconv_tc.cu.  The three kernel rows are stacked along the MMA's N
+ * dimension (N = 96) and the accumulators of consecutive output rows form a ring of TMEM slots, so one input row of a
+ * 128-pixel strip costs 3 MMAs per 16-channel K block instead of 9 (the N = 32 MMAs of ynet_tc_conv3x3 are bound by
+ * the shared-memory operand fetch).  One plain C8 source with channels_pad <= 64; H >= 2.
+ *   ynet_tc_rowconv_pack_weights: OIHW float32 (C_out <= 32, C_in, 3, 3), LoRA already folded -> bf16
+ *       [K block][kw][2][96 = kh * 32 + co][8]; size = ynet_tc_rowconv_packed_weight_bytes(C_in_pad).
+ *   ynet_tc_rowconv3x3: conv + bias + ReLU (relu & 1) -> C8 (N, C_out_pad / 8, H, W, 8); relu & 2: the
+ *       replicate-padded (H + 2, W + 2) layout that ynet_tc_upconv3x3 consumes.  bias32: 32 floats, zero beyond C_out.
+ *   ynet_tc_rowconv3x3_pred_softargmax: conv + bias + ReLU -> 1x1 predictor -> SoftArgmax2D (ynet.py:468-469 + 582-583,
+ *       softargmax.py:55-81) in ONE kernel: the conv output row stays in shared memory as the N operand of the predictor
+ *       MMA, whose transposed accumulator (TMEM lane = channel) is reduced by the soft-argmax warps; neither the
+ *       activation nor the logits reach HBM.  packed_pred_weight = ynet_tc_pack_weights(predictor weight, ksize 1, one
+ *       source of C_out channels); C_pred <= 32; out (N, C_pred, 2) = (x, y);
+ *       workspace: ynet_tc_rowconv_softargmax_workspace_bytes(N, C_pred, W). */
+int64_t ynet_tc_rowconv_packed_weight_bytes(int32_t C_in_pad);
+int ynet_tc_rowconv_pack_weights(const float* weight, int32_t C_out, int32_t C_in, int32_t C_in_pad, void* packed,
+                                 void* stream);
+int ynet_tc_rowconv3x3(const ynet_tc_src* src_host, int32_t N, int32_t H, int32_t W, const void* packed_weight,
+                       const float* bias32, int32_t C_out, int32_t relu, void* out_c8, int32_t C_out_pad, void* stream);
+int64_t ynet_tc_rowconv_softargmax_workspace_bytes(int32_t N, int32_t C_pred, int32_t W);
+int ynet_tc_rowconv3x3_pred_softargmax(const ynet_tc_src* src_host, int32_t N, int32_t H, int32_t W,
+                                       const void* packed_weight, const float* bias32, int32_t C_out, int32_t relu,
+                                       const void* packed_pred_weight, const float* pred_bias, int32_t C_pred,
+                                       float* out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a18 fine-tuning step pieces (utils/train_epoch.py:86-115, models/trainer.py:197-206).
  * ------------------------------------------------------------------------------------------- */

@@ -121,7 +121,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // single-thread region ptxas keeps on the uniform datapath (tc_common.cuh)
       if (p.resident) {
         const uint32_t total = (uint32_t)p.w_total;
         mbar_expect_tx(smem_u32(w_bar), total);
@@ -161,7 +161,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // single-thread region ptxas keeps on the uniform datapath (tc_common.cuh)
       // instruction descriptor: D = F32, A = B = BF16, K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
       if (p.resident) mbar_wait(smem_u32(w_bar), 0, p.err);
@@ -502,7 +502,7 @@ tc_conv_pred_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // single-thread region ptxas keeps on the uniform datapath (tc_common.cuh)
       const uint32_t total = (uint32_t)p.w_total;
       mbar_expect_tx(smem_u32(w_bar), total);
       for (uint32_t off = 0; off < total; off += 32768) {
@@ -536,7 +536,7 @@ tc_conv_pred_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
     // ===================== MMA issuers: warp 1 + jj issues the conv MMAs of column block jj; warp 1 also issues the
     // predictor MMAs of tile i - 1 after the conv MMAs of tile i =====================
     const int jj = warp - 1;
-    if (lane == 0) {
+    if (elect_one()) {   // single-thread region ptxas keeps on the uniform datapath (tc_common.cuh)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t idesc_p = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
       auto issue_pred = [&](uint32_t j) {

@@ -76,7 +76,7 @@ tc_pred_softargmax_kernel(const __grid_constant__ CUtensorMap map, const PredPar
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int n = (int)(t0 / tiles_per_img);

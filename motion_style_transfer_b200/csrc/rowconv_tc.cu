@@ -1,0 +1,588 @@
+// a7/a8 tail: ROW-MARCHING, kh-STACKED 3x3 convolution for the C_out <= 32 layers of the decoders' full-resolution
+// levels (ynet.py:466-468: decoder.4.2, decoder.3.2), optionally fused with the 1x1 predictor and SoftArgmax2D
+// (ynet.py:469 + 582-583, softargmax.py:55-81) so that neither the conv output nor the logits ever reach HBM.
+//
+// Why another conv kernel.  conv_tc.cu computes a 16 x 8-pixel tile with nine M = 128 x N = C_out MMAs per 16-channel K
+// block.  With C_out = 32 every MMA is 16 cycles of math behind 5 KB of shared-memory operand fetch (4 KB of pixels,
+// 1 KB of weights): the operand fetch caps the tensor pipe at 40 % (profiles/ncu_full_r01d_tail416.md).  Useful flops
+// per fetched pixel byte = N, so N has to grow.  Here the three kernel ROWS are stacked along N:
+//
+//   D[x, (kh, co)] += sum_ci  in[Y, x + kw - 1, ci] * W[co, ci, kh, kw]          (one MMA per (K block, kw), N = 96)
+//
+// for ONE input row Y of a 128-pixel strip.  Column group kh of that product belongs to OUTPUT row Y + 1 - kh, and the
+// accumulators of consecutive output rows are laid out as a ring of 32-column TMEM slots in DESCENDING row order, so
+// the three groups of one N = 96 MMA land on the slots of rows Y + 1, Y, Y - 1 directly: the tensor core does the
+// row-shifted accumulation, the epilogue of an output row is a plain 32-column read once input row Y + 1 has been
+// multiplied.  Per K block and row: 3 MMAs of 48 math cycles behind 7 KB of operands (56 cycles) instead of 9 MMAs of
+// 16 cycles behind 5 KB (40 cycles each): 168 instead of 360 cycles, all columns useful.
+// Slots are zeroed by the epilogue after it has drained them (tcgen05.st), so every MMA accumulates; where the slot
+// triple wraps around the ring (2 rows in 8) or touches the image's first / last row the MMA is split / narrowed.
+//
+// Work item = (image, 126-pixel column strip); a CTA marches down all H rows of its strip.  An input row arrives by ONE
+// TMA: the C8 planes are described to the TMA unit as 8-byte elements (2 per pixel), so a box line may be 256 elements
+// = 128 pixels long and start at ANY pixel; box {128 px, 1 row, all chunks} at x = xs0 - 1 lands as [chunk][128 px][8 ch]
+// -- the K-major operand layout with the kw taps as 16-byte start offsets, zero-filled outside the image (= the conv's
+// padding).  (A first version viewed the row as 16-pixel segments, 40 box lines of 256 B per row: the TMA unit's
+// per-line rate, ~25 cycles, then bounded the kernel at 1 000 cycles per row.)  Lanes 126 / 127 of the M = 128 MMA read
+// past the window and are discarded.
+//
+// Fused tail (FUSE = true): the conv epilogue writes the bf16 row to shared memory as the N = 128-pixel operand of
+// the predictor MMA (weights = M operand, replicated into the four lane quadrants as in pred_tc.cu), whose transposed
+// accumulator (TMEM lane = channel, column = pixel) is reduced by eight soft-argmax warps straight from tcgen05.ld.
+// Both epilogues run as two warp sets that alternate rows, so the per-row latency chain (barrier wake-up, tcgen05.ld,
+// tcgen05.st) of one row overlaps the next row's.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace ynet {
+
+constexpr int RC_M = 128;                       // MMA M = pixels of a window row
+constexpr int RC_VW = 126;                      // valid output pixels per strip row (window = [xs0 - 1, xs0 + 127))
+constexpr int RC_CHUNK_BYTES = RC_M * 16;       // one 8-channel chunk of a window row
+constexpr int RC_CO = 32;                       // output channels = columns per TMEM slot
+constexpr int RC_NS = 8;                        // TMEM slot ring (256 columns)
+constexpr int RC_STAGES = 6;                    // input-row ring
+constexpr int RC_NY = 4;                        // conv-output row ring (fused tail)
+constexpr int RC_MAX_KB = 4;                    // <= 64 input channels
+constexpr int RC_WBLK = 2 * 96 * 16;            // weights of one (K block, kw): [2 chunks][96 = (kh, co)][8 ch] bf16
+constexpr int RC_YROW = 4 * RC_M * 16;          // one conv-output row: [4 chunks][128 px][8 ch] bf16
+constexpr int RC_EPI_WARPS = 8;                 // two sets of four (one warp per TMEM lane quadrant), alternating rows
+constexpr int RC_SOFT_WARPS = 8;                // likewise
+constexpr int RC_THREADS_PLAIN = 32 * (2 + RC_EPI_WARPS);        // TMA, MMA, epilogue warps
+constexpr int RC_THREADS_FUSED = 32 * (2 + RC_EPI_WARPS + 1 + RC_SOFT_WARPS);   // + predictor MMA warp + soft-argmax warps
+constexpr uint32_t RC_PACC = 256;               // first TMEM column of the two predictor accumulators (2 x 128)
+
+struct RcParams {
+  int N, H, W, kb, chunks, strips;
+  long long items;
+  int relu, out_chunks, pad_out;
+  int bcast, batch_mod;
+  int row_bytes;
+  const unsigned char* w96;    // [kb][kw][2][96][8] bf16
+  const float* bias;           // 32 floats (zero beyond C_out)
+  __nv_bfloat16* out;          // plain: C8 planes (N, out_chunks, H + 2 pad, W + 2 pad, 8)
+  const unsigned char* pw;     // fused: predictor weights [kbp][2][pn_pad][8] bf16 (ynet_tc_pack_weights, ksize 1)
+  const float* pbias;
+  float4* partial;             // (m, s, sx, sy) [(n * c_pred + c) * slots + strip * RC_SOFT_WARPS + warp]
+  int c_pred, pn_pad, slots;
+  int kbp;                     // predictor K blocks = ceil(C_out / 16) (1 or 2)
+};
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+      "[%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 32 lanes x 32 columns <- the bias (the drained accumulator slot is handed back holding the bias: every MMA
+// accumulates, and the epilogue needs no add)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]),
+      "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// bf16x2 = (lo, hi) with optional ReLU folded into the conversion
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack_bf16_act(uint32_t lo, uint32_t hi) {
+  uint32_t d;
+  if (RELU)
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  else
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return d;
+}
+
+__device__ __forceinline__ int rc_slot(int row) { return RC_NS - 1 - (row & (RC_NS - 1)); }
+
+template <bool FUSE>
+__global__ void __launch_bounds__(FUSE ? RC_THREADS_FUSED : RC_THREADS_PLAIN, FUSE ? 1 : 2)
+tc_rowconv_kernel(const __grid_constant__ CUtensorMap map, const RcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NTHREADS = FUSE ? RC_THREADS_FUSED : RC_THREADS_PLAIN;
+  constexpr int W_L4 = 2 + RC_EPI_WARPS;            // predictor MMA warp
+  constexpr int W_SOFT = W_L4 + 1;                  // first soft-argmax warp
+
+  unsigned char* s_w = smem;                                                    // kb * 3 * RC_WBLK
+  unsigned char* s_in = s_w + (size_t)p.kb * 3 * RC_WBLK;                       // RC_STAGES * row_bytes (+ 1 KB slack)
+  unsigned char* s_y = s_in + (size_t)RC_STAGES * p.row_bytes + 1024;           // fused: RC_NY * RC_YROW
+  unsigned char* s_pw = s_y + (FUSE ? RC_NY * RC_YROW : 0);                     // fused: 2 * PR_WBLK_BYTES
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_pw + (FUSE ? 2 * PR_WBLK_BYTES : 0));
+  uint64_t* in_full = bars;
+  uint64_t* in_empty = in_full + RC_STAGES;
+  uint64_t* acc_full = in_empty + RC_STAGES;
+  uint64_t* acc_empty = acc_full + RC_NS;
+  uint64_t* y_full = acc_empty + RC_NS;
+  uint64_t* y_empty = y_full + RC_NY;
+  uint64_t* p_full = y_empty + RC_NY;
+  uint64_t* p_empty = p_full + 2;
+  uint64_t* w_bar = p_empty + 2;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  if (FUSE) pred_stage_weights(s_pw, p.pw, p.kbp, p.pn_pad, threadIdx.x, NTHREADS);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RC_STAGES; ++s) {
+      mbar_init(smem_u32(&in_full[s]), 1);
+      mbar_init(smem_u32(&in_empty[s]), 1);
+    }
+    for (int s = 0; s < RC_NS; ++s) {
+      mbar_init(smem_u32(&acc_full[s]), 1);
+      mbar_init(smem_u32(&acc_empty[s]), 4);
+    }
+    for (int s = 0; s < RC_NY; ++s) {
+      mbar_init(smem_u32(&y_full[s]), 4);
+      mbar_init(smem_u32(&y_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&p_full[s]), 1);
+      mbar_init(smem_u32(&p_empty[s]), 4);
+    }
+    mbar_init(smem_u32(w_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  constexpr uint32_t TMEM_COLS = FUSE ? 512u : 256u;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  // the slot ring starts out holding the bias: the first four epilogue warps initialise their lane quadrants
+  uint32_t bz[32];
+  if (warp >= 2 && warp < 2 + RC_EPI_WARPS) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bz[i] = __float_as_uint(p.bias[i]);
+    if (warp < 6) {
+      const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll
+      for (int s = 0; s < RC_NS; ++s) tmem_st32(t_row + (uint32_t)(s * RC_CO), bz);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    // ===================== TMA producer: one input row per transaction =====================
+    if (elect_one()) {
+      const uint32_t wtotal = (uint32_t)(p.kb * 3 * RC_WBLK);
+      mbar_expect_tx(smem_u32(w_bar), wtotal);
+      for (uint32_t off = 0; off < wtotal; off += 18432) {
+        const uint32_t nb = min(18432u, wtotal - off);
+        bulk_load(smem_u32(s_w + off), p.w96 + off, nb, smem_u32(w_bar));
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int n = (int)(item / p.strips), s = (int)(item - (long long)n * p.strips);
+        const int ns = p.bcast ? 0 : (p.batch_mod > 0 ? n % p.batch_mod : (p.batch_mod < 0 ? n / (-p.batch_mod) : n));
+        const int c0 = 2 * (s * RC_VW - 1);                 // 8-byte elements: two per pixel
+        for (int Y = 0; Y < p.H; ++Y) {
+          mbar_wait(smem_u32(&in_empty[stage]), phase ^ 1, nullptr);
+          const uint32_t fb = smem_u32(&in_full[stage]);
+          mbar_expect_tx(fb, (uint32_t)p.row_bytes);
+          tma_load_4d(smem_u32(s_in + (size_t)stage * p.row_bytes), &map, fb, c0, Y, 0, ns);
+          if (++stage == RC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== conv MMA issuer =====================
+    if (elect_one()) {
+      mbar_wait(smem_u32(w_bar), 0, nullptr);
+      // descriptors: K-major, no swizzle; LBO = chunk stride, SBO = stride of 8-row groups (128 B: rows are contiguous)
+      constexpr uint32_t A_HI = (uint32_t)(128 >> 4) | (1u << 14);
+      constexpr uint32_t A_LBO = (uint32_t)(RC_CHUNK_BYTES >> 4) << 16;
+      constexpr uint32_t B_HI = (uint32_t)(128 >> 4) | (1u << 14);
+      constexpr uint32_t B_LBO = (uint32_t)((96 * 16) >> 4) << 16;
+      const uint32_t w_lo0 = ((smem_u32(s_w) >> 4) & 0x3FFF) | B_LBO;
+      const uint32_t a_base = ((smem_u32(s_in) >> 4) & 0x3FFF) | A_LBO;
+      const uint32_t a_step = (uint32_t)(p.row_bytes >> 4);
+      constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+      const int kbn = p.kb, H = p.H;
+      int stage = 0;
+      uint32_t phase = 0;
+      int g = 0;                             // running output-row index of this CTA (slot ring position)
+      // one run of MMAs: kernel rows kh0 .. kh0 + len - 1 of input row g -> the slots of output rows g + 1 - kh0 ...
+      auto issue = [&](uint32_t a_lo0, int kh0, int len) {
+        const uint32_t idesc = IDESC0 | ((uint32_t)(len * (RC_CO >> 3)) << 17);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(rc_slot(g + 1 - kh0) * RC_CO);
+        uint32_t b_lo = w_lo0 + (uint32_t)(kh0 * RC_CO);                       // 32 weight rows x 16 B per kernel row
+        uint32_t a_lo = a_lo0;
+        for (int kb = 0; kb < kbn; ++kb) {
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const uint64_t adesc = ((uint64_t)A_HI << 32) | (a_lo + (uint32_t)kw);
+            const uint64_t bdesc = ((uint64_t)B_HI << 32) | (b_lo + (uint32_t)(kw * (RC_WBLK >> 4)));
+            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
+          }
+          a_lo += 2 * (RC_CHUNK_BYTES >> 4);
+          b_lo += 3 * (RC_WBLK >> 4);
+        }
+      };
+      for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+        for (int Y = 0; Y < H; ++Y, ++g) {
+          // the slots this row writes FIRST must have been drained: row g + 1 (and row g at the top of a strip)
+          if (Y == 0) mbar_wait(smem_u32(&acc_empty[rc_slot(g)]), (uint32_t)(((g / RC_NS) & 1) ^ 1), nullptr);
+          if (Y + 1 < H)
+            mbar_wait(smem_u32(&acc_empty[rc_slot(g + 1)]), (uint32_t)((((g + 1) / RC_NS) & 1) ^ 1), nullptr);
+          mbar_wait(smem_u32(&in_full[stage]), phase, nullptr);
+          tc_fence_after();
+          // kernel rows kh_lo..kh_hi contribute (output row g + 1 - kh must exist).  The slots of rows g + 1, g, g - 1 are
+          // consecutive except where the ring wraps: after kh = 0 when g % 8 == 7, after kh = 1 when g % 8 == 0.
+          const int kh_lo = (Y + 1 < H) ? 0 : 1, kh_hi = (Y >= 1) ? 2 : 1;
+          const int pos = g & (RC_NS - 1);
+          const int brk = (pos == RC_NS - 1) ? 1 : (pos == 0 ? 2 : 3);          // first kernel row of a second run
+          const uint32_t a_lo0 = a_base + (uint32_t)stage * a_step;
+          const int a_end = min(brk, kh_hi + 1);
+          if (a_end > kh_lo) issue(a_lo0, kh_lo, a_end - kh_lo);
+          const int b0 = max(brk, kh_lo);
+          if (b0 <= kh_hi) issue(a_lo0, b0, kh_hi - b0 + 1);
+          tc_commit(smem_u32(&in_empty[stage]));
+          if (Y >= 1) tc_commit(smem_u32(&acc_full[rc_slot(g - 1)]));
+          if (Y == H - 1) tc_commit(smem_u32(&acc_full[rc_slot(g)]));
+          if (++stage == RC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp < 2 + RC_EPI_WARPS) {
+    // ===================== conv epilogue: 2 sets x 4 warps; warp w owns TMEM lanes 32 (w % 4) .. +31 = pixels; set k
+    // takes the rows with g % 2 == k =====================
+    const int q = warp & 3, set = (warp - 2) >> 2;
+    const int m = q * 32 + lane;                    // pixel of the window row (window starts at xs0 - 1: lane = x - xs0)
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    int g = 0;
+    for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int n = (int)(item / p.strips), s = (int)(item - (long long)n * p.strips);
+      const int x = s * RC_VW + m;
+      const bool live = m < RC_VW && x < p.W;
+      for (int Y = 0; Y < p.H; ++Y, ++g) {
+        if ((g & 1) != set) continue;
+        const int sl = rc_slot(g);
+        mbar_wait(smem_u32(&acc_full[sl]), (uint32_t)((g / RC_NS) & 1), nullptr);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(t_row + (uint32_t)(sl * RC_CO), v);
+        tmem_st32(t_row + (uint32_t)(sl * RC_CO), bz);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&acc_empty[sl]));
+        uint4 o[4];
+        if (p.relu) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            o[c].x = pack_bf16_act<true>(v[8 * c + 0], v[8 * c + 1]);
+            o[c].y = pack_bf16_act<true>(v[8 * c + 2], v[8 * c + 3]);
+            o[c].z = pack_bf16_act<true>(v[8 * c + 4], v[8 * c + 5]);
+            o[c].w = pack_bf16_act<true>(v[8 * c + 6], v[8 * c + 7]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            o[c].x = pack_bf16_act<false>(v[8 * c + 0], v[8 * c + 1]);
+            o[c].y = pack_bf16_act<false>(v[8 * c + 2], v[8 * c + 3]);
+            o[c].z = pack_bf16_act<false>(v[8 * c + 4], v[8 * c + 5]);
+            o[c].w = pack_bf16_act<false>(v[8 * c + 6], v[8 * c + 7]);
+          }
+        }
+        if (FUSE) {
+          const int b = g & (RC_NY - 1);
+          if (lane == 0) mbar_wait(smem_u32(&y_empty[b]), (uint32_t)(((g / RC_NY) & 1) ^ 1), nullptr);
+          __syncwarp();
+          unsigned char* yb = s_y + (size_t)b * RC_YROW + m * 16;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(yb + c * (RC_M * 16)) = o[c];
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&y_full[b]));
+        } else if (live) {
+          const int po = p.pad_out;
+          const int Hp = p.H + 2 * po, Wp = p.W + 2 * po;
+          for (int c = 0; c < p.out_chunks; ++c) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out) + (((size_t)n * p.out_chunks + c) * Hp + (Y + po)) * Wp + (x + po);
+            *dst = o[c];
+            if (po) {      // replicate the border pixels into the ring (input of the phase-decomposed upconv)
+              const int dyv = (Y == 0) ? -1 : ((Y == p.H - 1) ? 1 : 0);
+              const int dxv = (x == 0) ? -1 : ((x == p.W - 1) ? 1 : 0);
+              if (dyv != 0) dst[dyv * Wp] = o[c];
+              if (dxv != 0) dst[dxv] = o[c];
+              if (dyv != 0 && dxv != 0) dst[dyv * Wp + dxv] = o[c];
+            }
+          }
+        }
+      }
+    }
+  } else if (FUSE && warp == W_L4) {
+    // ===================== predictor MMA issuer: D[channel, pixel] = Wp (M = 128, replicated) x row (N = 128) ==========
+    if (elect_one()) {
+      constexpr uint32_t IDESC_P = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      int g = 0;
+      for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+        for (int Y = 0; Y < p.H; ++Y, ++g) {
+          const int b = g & (RC_NY - 1), a = g & 1;
+          mbar_wait(smem_u32(&p_empty[a]), (uint32_t)(((g >> 1) & 1) ^ 1), nullptr);
+          mbar_wait(smem_u32(&y_full[b]), (uint32_t)((g / RC_NY) & 1), nullptr);
+          tc_fence_after();
+          for (int kbp = 0; kbp < p.kbp; ++kbp) {
+            const uint64_t adesc = make_desc(smem_u32(s_pw + (size_t)kbp * PR_WBLK_BYTES), 128 * 16, 128);
+            const uint64_t bdesc = make_desc(smem_u32(s_y + (size_t)b * RC_YROW + (size_t)kbp * 2 * (RC_M * 16)), RC_M * 16, 128);
+            tc_mma_bf16(tmem_base + RC_PACC + (uint32_t)(a * 128), adesc, bdesc, IDESC_P, kbp > 0 ? 1u : 0u);
+          }
+          tc_commit(smem_u32(&p_full[a]));
+          tc_commit(smem_u32(&y_empty[b]));
+        }
+      }
+    }
+  } else if (FUSE) {
+    // ===================== soft-argmax: 2 sets x 4 warps; TMEM lane = channel, column = pixel of the window row; set k
+    // takes the rows with g % 2 == k (= predictor accumulator k), each warp the 32 pixels of its lane quadrant ==========
+    const int e = warp - W_SOFT;
+    const int q = warp & 3, set = e >> 2;
+    const int col0 = 32 * q;
+    const bool active = lane < p.c_pred;
+    const float bias = active ? p.pbias[lane] : 0.f;
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + RC_PACC + (uint32_t)(set * 128 + col0);
+    int g = 0;
+    for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int n = (int)(item / p.strips), s = (int)(item - (long long)n * p.strips);
+      const int x0 = s * RC_VW + col0;
+      const int lim = min(p.W, s * RC_VW + RC_VW);          // first pixel beyond this strip's valid columns
+      SoftState st{PR_NEG, 0.f, 0.f, 0.f};
+      for (int Y = 0; Y < p.H; ++Y, ++g) {
+        if ((g & 1) != set) continue;
+        mbar_wait(smem_u32(&p_full[set]), (uint32_t)((g >> 1) & 1), nullptr);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(t_addr, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&p_empty[set]));      // the values are in registers: release the accumulator
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t(&vh)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&v[16 * h]);
+          const int xh = x0 + 16 * h;
+          if (xh + 16 <= lim)
+            softargmax_row16(st, vh, bias, xh, Y);
+          else if (xh < lim)
+            softargmax_row16_masked(st, vh, bias, xh, Y, lim);
+        }
+      }
+      if (active) p.partial[((size_t)n * p.c_pred + lane) * p.slots + s * RC_SOFT_WARPS + e] = make_float4(st.m, st.s, st.sx, st.sy);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// weights OIHW f32 (C_out <= 32, C_in <= 64, 3, 3) -> [kb][kw][2 chunks][96 = kh * 32 + co][8 ch] bf16
+__global__ void __launch_bounds__(256)
+rc_pack_weights_kernel(const float* __restrict__ w, int C_out, int C_in, int kb, __nv_bfloat16* __restrict__ out) {
+  const int total = kb * 3 * 2 * 96 * 8;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int k8 = t & 7;
+    int r = t >> 3;
+    const int nrow = r % 96;
+    r /= 96;
+    const int c = r & 1;
+    r >>= 1;
+    const int kw = r % 3, b = r / 3;
+    const int kh = nrow / RC_CO, co = nrow - kh * RC_CO;
+    const int ci = b * 16 + c * 8 + k8;
+    const float v = (co < C_out && ci < C_in) ? w[(((size_t)co * C_in + ci) * 3 + kh) * 3 + kw] : 0.f;
+    out[t] = __float2bfloat16_rn(v);
+  }
+}
+
+static int rc_launch(const char* who, bool fuse, const ynet_tc_src* src, int N, int H, int W, RcParams& p, void* stream) {
+  if (!(src && src->ptr) || reinterpret_cast<uintptr_t>(src->ptr) % 16 != 0) {
+    set_error("%s: source must be a 16-byte aligned C8 tensor", who);
+    return YNET_E_INVALID;
+  }
+  const int cp = src->channels_pad;
+  if (!(cp > 0 && cp % 16 == 0 && cp / 16 <= RC_MAX_KB) || src->padded || src->center_only || src->tap_mask) {
+    set_error("%s: channels_pad must be 16..64 (plain C8 source)", who);
+    return YNET_E_INVALID;
+  }
+  if (!(N >= 0 && H >= 2 && W >= 1)) {
+    set_error("%s: needs H >= 2 (got %d x %d)", who, H, W);
+    return YNET_E_UNSUPPORTED;
+  }
+  if (N == 0) return YNET_OK;
+  EncodeTiledFn encode = tc_get_encode();
+  if (encode == nullptr) {
+    set_error("%s: cuTensorMapEncodeTiled is not available from the driver", who);
+    return YNET_E_UNSUPPORTED;
+  }
+  const bool bcast = src->batch_stride == 0;
+  const int bmod = src->batch_mod;
+  const int nsrc = bcast ? 1 : (bmod > 0 ? bmod : (bmod < 0 ? ceil_div(N, -bmod) : N));
+  const int stored = (src->chunks_stored > 0) ? src->chunks_stored : cp / 8;
+  // The planes as 8-byte elements, two per pixel: a box line may then span 128 pixels (256 elements) from any pixel.
+  const cuuint64_t dims[4] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)stored, (cuuint64_t)nsrc};
+  const cuuint64_t bs = bcast ? (cuuint64_t)stored * H * W * 16 : (cuuint64_t)src->batch_stride * 2;
+  if (bs % 16 != 0) {
+    set_error("%s: batch stride must be a multiple of 8 elements", who);
+    return YNET_E_ALIGN;
+  }
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, bs};
+  const cuuint32_t box[4] = {(cuuint32_t)RC_M * 2, 1, (cuuint32_t)(cp / 8), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(src->ptr), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("%s: cuTensorMapEncodeTiled failed (%d) (W=%d H=%d C=%d)", who, (int)r, W, H, cp);
+    return YNET_E_CUDA;
+  }
+  p.N = N;
+  p.H = H;
+  p.W = W;
+  p.kb = cp / 16;
+  p.chunks = cp / 8;
+  p.strips = ceil_div(W, RC_VW);
+  p.items = (long long)N * p.strips;
+  p.bcast = bcast ? 1 : 0;
+  p.batch_mod = bmod;
+  p.row_bytes = p.chunks * RC_CHUNK_BYTES;
+  const size_t smem = (size_t)p.kb * 3 * RC_WBLK + (size_t)RC_STAGES * p.row_bytes + 1024 +
+                      (fuse ? (size_t)RC_NY * RC_YROW + 2 * PR_WBLK_BYTES : 0) + 64 * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_rowconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc_rowconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, who);
+    configured = true;
+  }
+  if (smem > 200 * 1024) {
+    set_error("%s: layer does not fit shared memory", who);
+    return YNET_E_UNSUPPORTED;
+  }
+  // plain: 256 TMEM columns and < 100 KB per CTA -> two co-resident CTAs per SM; fused: one (512 columns)
+  const int per_sm = fuse ? 1 : ((smem + 1024 <= 110 * 1024) ? 2 : 1);
+  const long long grid = tmin<long long>(p.items, (long long)sm_count() * per_sm);
+  cudaStream_t st = as_stream(stream);
+  if (fuse)
+    tc_rowconv_kernel<true><<<(unsigned)grid, RC_THREADS_FUSED, smem, st>>>(map, p);
+  else
+    tc_rowconv_kernel<false><<<(unsigned)grid, RC_THREADS_PLAIN, smem, st>>>(map, p);
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) return cuda_fail(le, who);
+  return YNET_OK;
+}
+
+}  // namespace ynet
+
+using namespace ynet;
+
+extern "C" {
+
+int64_t ynet_tc_rowconv_packed_weight_bytes(int32_t C_in_pad) {
+  if (C_in_pad <= 0 || C_in_pad % 16 != 0 || C_in_pad / 16 > RC_MAX_KB) return 0;
+  return (int64_t)(C_in_pad / 16) * 3 * RC_WBLK;
+}
+
+int ynet_tc_rowconv_pack_weights(const float* weight, int32_t C_out, int32_t C_in, int32_t C_in_pad, void* packed,
+                                 void* stream) {
+  YNET_CHECK_ARG(weight && packed, "null pointer");
+  YNET_CHECK_ARG(C_out > 0 && C_out <= RC_CO && C_in > 0 && C_in <= C_in_pad && C_in_pad % 16 == 0 &&
+                     C_in_pad / 16 <= RC_MAX_KB,
+                 "C_out <= 32, C_in <= C_in_pad <= 64");
+  YNET_CHECK_ALIGN(packed, 16);
+  const int kb = C_in_pad / 16;
+  rc_pack_weights_kernel<<<ceil_div(kb * 3 * 2 * 96 * 8, 256), 256, 0, as_stream(stream)>>>(
+      weight, C_out, C_in, kb, reinterpret_cast<__nv_bfloat16*>(packed));
+  YNET_LAUNCH_CHECK();
+  return YNET_OK;
+}
+
+int ynet_tc_rowconv3x3(const ynet_tc_src* src, int32_t N, int32_t H, int32_t W, const void* packed_weight,
+                       const float* bias32, int32_t C_out, int32_t relu, void* out_c8, int32_t C_out_pad, void* stream) {
+  YNET_CHECK_ARG(packed_weight && bias32 && (out_c8 || N == 0), "null pointer");
+  YNET_CHECK_ARG(C_out > 0 && C_out <= RC_CO && C_out_pad % 16 == 0 && C_out_pad >= C_out && C_out_pad <= RC_CO, "C_out <= 32");
+  YNET_CHECK_ALIGN(packed_weight, 16);
+  YNET_CHECK_ALIGN(out_c8, 16);
+  RcParams p;
+  memset(&p, 0, sizeof(p));
+  p.w96 = reinterpret_cast<const unsigned char*>(packed_weight);
+  p.bias = bias32;
+  p.relu = relu & 1;
+  p.pad_out = (relu & 2) ? 1 : 0;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out_c8);
+  p.out_chunks = C_out_pad / 8;
+  return rc_launch("ynet_tc_rowconv3x3", false, src, N, H, W, p, stream);
+}
+
+int64_t ynet_tc_rowconv_softargmax_workspace_bytes(int32_t N, int32_t C_pred, int32_t W) {
+  if (N <= 0 || C_pred <= 0 || W <= 0) return 0;
+  return (int64_t)N * C_pred * ceil_div(W, RC_VW) * RC_SOFT_WARPS * (int64_t)sizeof(float4);
+}
+
+int ynet_tc_rowconv3x3_pred_softargmax(const ynet_tc_src* src, int32_t N, int32_t H, int32_t W, const void* packed_weight,
+                                       const float* bias32, int32_t C_out, int32_t relu, const void* packed_pred_weight,
+                                       const float* pred_bias, int32_t C_pred, float* out, void* workspace,
+                                       int64_t workspace_bytes, void* stream) {
+  YNET_CHECK_ARG(packed_weight && bias32 && packed_pred_weight && pred_bias && (out || N == 0), "null pointer");
+  YNET_CHECK_ARG(C_pred > 0 && C_pred <= 32 && C_out > 0 && C_out <= RC_CO, "C_pred <= 32, C_out <= 32");
+  YNET_CHECK_ALIGN(packed_weight, 16);
+  YNET_CHECK_ALIGN(packed_pred_weight, 16);
+  if (N == 0) return YNET_OK;
+  if (workspace == nullptr || workspace_bytes < ynet_tc_rowconv_softargmax_workspace_bytes(N, C_pred, W)) {
+    set_error("ynet_tc_rowconv3x3_pred_softargmax: workspace too small");
+    return YNET_E_WORKSPACE;
+  }
+  YNET_CHECK_ALIGN(workspace, 16);
+  RcParams p;
+  memset(&p, 0, sizeof(p));
+  p.w96 = reinterpret_cast<const unsigned char*>(packed_weight);
+  p.bias = bias32;
+  p.relu = relu & 1;
+  p.pw = reinterpret_cast<const unsigned char*>(packed_pred_weight);
+  p.pbias = pred_bias;
+  p.partial = reinterpret_cast<float4*>(workspace);
+  p.c_pred = C_pred;
+  p.pn_pad = ceil_div(C_pred, 16) * 16;
+  p.kbp = ceil_div(C_out, 16);
+  p.slots = ceil_div(W, RC_VW) * RC_SOFT_WARPS;
+  int rc = rc_launch("ynet_tc_rowconv3x3_pred_softargmax", true, src, N, H, W, p, stream);
+  if (rc != YNET_OK) return rc;
+  cudaError_t le = pred_partial_finalize(p.partial, N * C_pred, p.slots, out, as_stream(stream));
+  if (le != cudaSuccess) return cuda_fail(le, "ynet_tc_rowconv3x3_pred_softargmax");
+  return YNET_OK;
+}
+
+}  // extern "C"

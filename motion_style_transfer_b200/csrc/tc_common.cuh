@@ -47,6 +47,20 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
   if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity, nullptr);
   __syncwarp();
 }
+// One elected lane of a converged warp.  Guard single-thread roles (TMA producer, MMA issuer) with THIS, not with
+// `lane == 0`: ptxas recognises the elect.sync-guarded region as single-threaded and keeps descriptors, barrier addresses
+// and the tcgen05 / TMA instructions on the uniform datapath (2-3 instructions per MMA); behind `lane == 0` every
+// tcgen05.mma is wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (8-12 instructions), and a single issuing thread
+// then takes ~100 cycles per MMA (measured: the issue thread, not the tensor pipe, bounded rowconv_tc.cu at first).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
   asm volatile(

@@ -351,9 +351,49 @@ class YNetEngineTC(YNetEngine):
         packed, b_eff, bw, b = self._tc_up_params(module, key, [s.C for s in sources])
         return ops.tc_upconv3x3(sources, packed, b_eff, bw, b, module.weight.shape[0])
 
+    # Row-marching kh-stacked kernel (rowconv_tc.cu) for single-source convs with C_out <= 32: N = 96 MMAs
+    # instead of the operand-fetch-bound N = 32 ones; with the predictor + soft-argmax fused behind decoder.4.2.
+    rowconv = os.environ.get('YNET_ROWCONV', '1') == '1'
+
+    def _rowconv_params(self, module, key, k_pad):
+        """(kh-stacked packed weight, 32-float bias) of a 3x3 conv with C_out <= 32; LoRA / adapters folded first."""
+        A = getattr(module, 'lora_A', None)
+        Bm = getattr(module, 'lora_B', None)
+        ver = (module.weight._version, module.weight.data_ptr(),
+               None if A is None else (A._version, A.data_ptr()),
+               None if Bm is None else (Bm._version, Bm.data_ptr()), k_pad, _bias_version(module),
+               _module_version(module) if _is_adapter_layer(module) else None)
+        hit = self._wcache.get(key + '#row')
+        if hit is not None and hit[0] == ver:
+            return hit[1], hit[2]
+        w, b = module.weight.detach(), (None if module.bias is None else module.bias.detach())
+        if _is_adapter_layer(module):
+            w, b = fold_adapter_layer(module, w, b)
+        w_eff = ops.lora_fold(w, None if A is None else A.detach(), None if Bm is None else Bm.detach(), packed=False)
+        packed = ops.tc_rowconv_pack_weights(w_eff, k_pad)
+        bias = torch.zeros(32, dtype=torch.float32, device=module.weight.device)
+        if b is not None:
+            bias[:module.weight.shape[0]] = b
+        self._wcache[key + '#row'] = (ver, packed, bias)
+        return packed, bias
+
+    def _use_rowconv(self, module, sources):
+        return (self.rowconv and len(sources) == 1 and module.weight.shape[-1] == 3
+                and ops.tc_rowconv_supported(sources[0], module.weight.shape[0]))
+
     def _tconv(self, module, key, sources, relu, pad_out=False):
+        if self._use_rowconv(module, sources):
+            packed, bias = self._rowconv_params(module, key, sources[0].K_pad)
+            return ops.tc_rowconv3x3(sources[0], packed, bias, module.weight.shape[0], relu, pad_out)
         packed, bias = self._tc_params(module, key, [s.C for s in sources])
         return ops.tc_conv3x3(sources, packed, bias, module.weight.shape[0], relu, pad_out)
+
+    def _conv_pred_softargmax_row(self, conv, key, x, predictor, pkey):
+        """conv (+ReLU) -> predictor -> SoftArgmax2D in the row-marching kernel (ynet.py:468-469 + 582-583)."""
+        packed, bias = self._rowconv_params(conv, key, x.K_pad)
+        ppacked, pbias = self._tc_params(predictor, pkey, [conv.weight.shape[0]])
+        return ops.tc_rowconv3x3_pred_softargmax(x, packed, bias, conv.weight.shape[0], True, ppacked, pbias,
+                                                 predictor.weight.shape[0])
 
     def _feeds_upconv(self, decoder, i):
         """Does the output of center.2 (i = -1) / decoder.i.2 feed an upsample_conv that runs phase-decomposed?  Then
@@ -526,6 +566,10 @@ class YNetEngineTC(YNetEngine):
             x = self._tconv_hoisted(decoder.decoder[i][0], f'{key}.decoder.{i}.0', up, partials[i + 1], pyr_rev[i + 1],
                                     c_feats[i + 1])
             last = i == len(partials) - 2
+            if (last and softargmax and self._use_rowconv(decoder.decoder[i][2], [x])
+                    and decoder.predictor.weight.shape[0] <= 32):
+                return self._conv_pred_softargmax_row(decoder.decoder[i][2], f'{key}.decoder.{i}.2', x, decoder.predictor,
+                                                      f'{key}.predictor')
             if last and softargmax and self.fuse_predictor and decoder.decoder[i][2].weight.shape[0] <= 64:
                 return self._conv_pred_softargmax(decoder.decoder[i][2], f'{key}.decoder.{i}.2', x, decoder.predictor,
                                                   f'{key}.predictor')

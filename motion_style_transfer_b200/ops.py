@@ -986,6 +986,64 @@ def tc_upconv3x3(sources, packed_phase_weight, bias_eff, border_weight, bias, C_
     return C8(out, C_out)
 
 
+# ---- row-marching kh-stacked conv (rowconv_tc.cu): the C_out <= 32 layers of the full-resolution decoder levels ----------
+def tc_rowconv_supported(a, C_out):
+    """Can ``tc_rowconv3x3*`` take the plain C8 activation ``a`` (see ynet_tc_rowconv3x3)?"""
+    return (isinstance(a, C8) and not a.pad and not a.center and not a.taps and a.K_pad <= 64 and C_out <= 32
+            and a.H >= 2)
+
+
+def tc_rowconv_pack_weights(weight_oihw, C_in_pad):
+    """Effective OIHW float32 3x3 weight (C_out <= 32) -> bf16 [K block][kw][2][96 = kh * 32 + co][8]."""
+    weight_oihw = _req(weight_oihw, name='weight')
+    C_out, C_in = weight_oihw.shape[:2]
+    packed = torch.empty(_L().ynet_tc_rowconv_packed_weight_bytes(C_in_pad), dtype=torch.uint8, device=weight_oihw.device)
+    check(_L().ynet_tc_rowconv_pack_weights(_ptr(weight_oihw), C_out, C_in, C_in_pad, _ptr(packed), _stream()),
+          'tc_rowconv_pack_weights')
+    _count()
+    return packed
+
+
+def _rowconv_src(a):
+    arr = (_lib.TcSrc * 1)()
+    arr[0].ptr = a.data.data_ptr()
+    arr[0].channels_pad = a.K_pad
+    arr[0].chunks_stored = a.C_pad // 8
+    arr[0].batch_stride = a.data.stride(0)
+    arr[0].batch_mod = -a.rep if a.rep > 1 else 0
+    return arr
+
+
+def tc_rowconv3x3(a, packed_weight, bias32, C_out, relu, pad_out=False):
+    """conv3x3 + bias (+ ReLU) of ONE plain C8 source with C_out <= 32 -> C8 (see ynet_tc_rowconv3x3)."""
+    cp = _pad16(C_out)
+    po = 1 if pad_out else 0
+    out = torch.empty(a.N, cp // 8, a.H + 2 * po, a.W + 2 * po, 8, dtype=torch.bfloat16, device=a.data.device)
+    with _timed('tc_rowconv_kernel', 2.0 * 9 * a.C * C_out * a.H * a.W * a.N,
+                2.0 * a.C_pad * min(a.data.shape[0], a.N) * a.H * a.W + 2.0 * cp * a.H * a.W * a.N,
+                tag=f'{a.K_pad}->{cp}@{a.H}x{a.W} N={a.N}'):
+        check(_L().ynet_tc_rowconv3x3(_rowconv_src(a), a.N, a.H, a.W, _ptr(packed_weight), _ptr(bias32), C_out,
+                                      (1 if relu else 0) | (2 * po), _ptr(out), cp, _stream()), 'tc_rowconv3x3')
+    _count()
+    return C8(out, C_out, 1, False, po)
+
+
+def tc_rowconv3x3_pred_softargmax(a, packed_weight, bias32, C_out, relu, packed_pred, pred_bias_pad, C_pred):
+    """conv3x3 (+bias, +ReLU) -> 1x1 predictor -> SoftArgmax2D in one kernel: C8 (N, <= 64 ch) -> (N, C_pred, 2)."""
+    out = torch.empty(a.N, C_pred, 2, dtype=torch.float32, device=a.data.device)
+    nb = _L().ynet_tc_rowconv_softargmax_workspace_bytes(a.N, C_pred, a.W)
+    ws = _workspace(nb, out.device, 'tc_rowconv_softargmax')
+    flops = 2.0 * (9 * a.C * C_out + C_out * C_pred) * a.H * a.W * a.N
+    with _timed('tc_rowconv_kernel<pred,softargmax>', flops, 2.0 * a.C_pad * min(a.data.shape[0], a.N) * a.H * a.W,
+                tag=f'{a.K_pad}->{_pad16(C_out)}->{C_pred}@{a.H}x{a.W} N={a.N}'):
+        check(_L().ynet_tc_rowconv3x3_pred_softargmax(_rowconv_src(a), a.N, a.H, a.W, _ptr(packed_weight), _ptr(bias32),
+                                                      C_out, 1 if relu else 0, _ptr(packed_pred), _ptr(pred_bias_pad), C_pred,
+                                                      _ptr(out), _ptr(ws), ws.numel(), _stream()),
+              'tc_rowconv3x3_pred_softargmax')
+    _count(2)
+    return out
+
+
 tc_autotune_enabled = os.environ.get('YNET_TC_AUTOTUNE', '1') != '0'
 _tc_tune = {}
 

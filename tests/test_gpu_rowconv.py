@@ -1,0 +1,129 @@
+"""GPU tests of the row-marching, kh-stacked conv kernel (csrc/rowconv_tc.cu) through the C ABI: the plain conv against
+F.conv2d and against the tile kernel (ynet_tc_conv3x3), and the fused conv + predictor + SoftArgmax2D tail
+(ynet.py:468-469 + 582-583, softargmax.py:55-81) against a float32 torch restatement and the unfused launches.
+
+STATED TOLERANCE: bf16 operands, fp32 accumulation: conv output <= 5e-3 of max|ref| (bf16 output rounding); soft-argmax
+coordinates <= 2e-2 px against float32 logits computed from the bf16-rounded activation.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_err
+from oracle import ynet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops(cuda_device):
+    from motion_style_transfer_b200 import ops as _ops
+    if not _ops.tc_supported():
+        pytest.fail('tensor-core engine unavailable on this device (needs sm_100 + cuTensorMapEncodeTiled)')
+    return _ops
+
+
+def bf16_exact(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _bias32(b):
+    out = torch.zeros(32)
+    out[:b.numel()] = b
+    return out.cuda()
+
+
+@pytest.mark.parametrize('cin,cout,H,W,N,relu', [
+    (32, 32, 16, 16, 1, False),       # one strip, 16 of 126 lanes live
+    (32, 32, 13, 13, 2, True),        # any width
+    (32, 32, 30, 127, 2, True),       # 126 + 1 pixels
+    (32, 32, 64, 64, 2, True),
+    (16, 32, 48, 32, 3, True),        # one K block
+    (64, 32, 40, 160, 2, True),       # four K blocks, two strips (126 + 34 pixels)
+    (32, 16, 33, 48, 2, False),       # odd height, C_out 16
+    (24, 30, 21, 272, 2, True),       # padded channels on both sides, three strips
+    (32, 32, 2, 16, 5, True),         # minimal height: both rows are border rows
+    (32, 32, 416, 416, 1, True),      # decoder.4.2
+])
+def test_rowconv3x3_vs_torch(ops, cin, cout, H, W, N, relu):
+    torch.manual_seed(1)
+    x = bf16_exact(torch.randn(N, cin, H, W))
+    w = bf16_exact(torch.randn(cout, cin, 3, 3) * 0.1)
+    b = torch.randn(cout)
+    ref = F.conv2d(x, w, b, padding=1)
+    ref = F.relu(ref) if relu else ref
+    a = ops.tc_pack(x.cuda())
+    assert ops.tc_rowconv_supported(a, cout)
+    packed = ops.tc_rowconv_pack_weights(w.cuda(), a.K_pad)
+    out = ops.tc_rowconv3x3(a, packed, _bias32(b), cout, relu)
+    torch.cuda.synchronize()
+    got = ops.tc_unpack(out).cpu()
+    assert got.shape == ref.shape
+    assert rel_err(got.numpy(), ref.numpy()) < 5e-3
+    # same operands, same fp32 accumulation up to the summation order: the tile kernel agrees to a bf16 ulp
+    packed_t = ops.tc_pack_weights(w.cuda(), [cin])
+    bias_t = torch.zeros((cout + 15) // 16 * 16)
+    bias_t[:cout] = b
+    tile = ops.tc_unpack(ops.tc_conv3x3([a], packed_t, bias_t.cuda(), cout, relu)).cpu()
+    assert rel_err(got.numpy(), tile.numpy()) < 2.0 ** -7
+    # a second launch reuses a clean accumulator ring (the epilogue hands every slot back zeroed)
+    out2 = ops.tc_rowconv3x3(a, packed, _bias32(b), cout, relu)
+    assert torch.equal(out2.data, out.data)
+
+
+def test_rowconv3x3_padded_output_and_repeated_source(ops):
+    """pad_out: the replicate-padded layout the phase-decomposed upconv consumes; rep: agent-major stacked source."""
+    torch.manual_seed(2)
+    nb, G, H, W = 2, 3, 24, 48
+    x = bf16_exact(torch.randn(nb, 32, H, W))
+    w = bf16_exact(torch.randn(32, 32, 3, 3) * 0.1)
+    b = torch.randn(32)
+    ref = F.relu(F.conv2d(x, w, b, padding=1))
+    a = ops.tc_pack(x.cuda())
+    packed = ops.tc_rowconv_pack_weights(w.cuda(), a.K_pad)
+    out = ops.tc_rowconv3x3(a, packed, _bias32(b), 32, True, pad_out=True)
+    assert out.pad == 1 and out.data.shape == (nb, 4, H + 2, W + 2, 8)
+    inner = ops.tc_unpack(out).cpu()
+    assert rel_err(inner.numpy(), ref.numpy()) < 5e-3
+    full = ops.tc_unpack(ops.C8(out.data, 32)).cpu()              # the (H + 2, W + 2) planes as they are
+    assert torch.equal(full, F.pad(inner, (1, 1, 1, 1), mode='replicate'))
+    rep = ops.tc_rowconv3x3(a.repeat_interleave(G), packed, _bias32(b), 32, True)
+    assert rep.N == nb * G
+    assert torch.equal(ops.tc_unpack(rep).cpu(), ops.tc_unpack(out).cpu().repeat_interleave(G, dim=0))
+
+
+@pytest.mark.parametrize('cin,cpred,H,W,N', [(32, 30, 64, 96, 3), (32, 12, 416, 416, 2), (16, 6, 34, 144, 2),
+                                             (32, 30, 208, 208, 5)])
+def test_rowconv_pred_softargmax(ops, cin, cpred, H, W, N):
+    torch.manual_seed(3)
+    x = bf16_exact(torch.relu(torch.randn(N, cin, H, W)))
+    w = bf16_exact(torch.randn(32, cin, 3, 3) * 0.1)
+    b = torch.randn(32) * 0.1
+    wp = bf16_exact(torch.randn(cpred, 32, 1, 1) * 0.5)
+    bp = torch.randn(cpred)
+    y = bf16_exact(F.relu(F.conv2d(x, w, b, padding=1)))          # the activation as the kernel rounds it
+    ref = O.softargmax2d(F.conv2d(y, wp, bp)).numpy()
+    a = ops.tc_pack(x.cuda())
+    packed = ops.tc_rowconv_pack_weights(w.cuda(), a.K_pad)
+    ppacked = ops.tc_pack_weights(wp.cuda(), [32])
+    pb = torch.zeros((cpred + 15) // 16 * 16)
+    pb[:cpred] = bp
+    got = ops.tc_rowconv3x3_pred_softargmax(a, packed, _bias32(b), 32, True, ppacked, pb.cuda(), cpred)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    assert got.shape == (N, cpred, 2)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=2e-2)
+    # the unfused launches (tile conv -> predictor + soft-argmax kernel)
+    packed_t = ops.tc_pack_weights(w.cuda(), [cin])
+    yt = ops.tc_conv3x3([a], packed_t, _bias32(b), 32, True)
+    unf = ops.tc_conv1x1_softargmax(yt, ppacked, pb.cuda(), cpred).cpu().numpy()
+    np.testing.assert_allclose(got, unf, rtol=0, atol=2e-2)
+    # peaky logits (what the trained / x50 model produces)
+    ppacked8 = ops.tc_pack_weights((wp * 8).cuda(), [32])
+    got8 = ops.tc_rowconv3x3_pred_softargmax(a, packed, _bias32(b), 32, True, ppacked8, (pb * 8).cuda(), cpred).cpu().numpy()
+    # (a bf16 rounding boundary of one activation -- fp32 sums in another order than torch's -- moves a logit by
+    # 8 x 0.4 %; with two competing peaks that shifts the expectation by ~0.1 px.  The unfused kernels see the same.)
+    np.testing.assert_allclose(got8, O.softargmax2d(F.conv2d(y, wp * 8, bp * 8)).numpy(), rtol=0, atol=0.25)
+    unf8 = ops.tc_conv1x1_softargmax(yt, ppacked8, (pb * 8).cuda(), cpred).cpu().numpy()
+    np.testing.assert_allclose(got8, unf8, rtol=0, atol=0.25)

@@ -1,0 +1,56 @@
+"""Micro-benchmark of the row-marching conv kernel (rowconv_tc.cu) next to the tile kernel on the same layer (CUDA events).
+
+    N=640 python tools/bench_rowconv.py            # env: N images, MODE=plain|fused|both|tile, HW=416
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from motion_style_transfer_b200 import ops  # noqa: E402
+
+N = int(os.environ.get('N', 320))
+HW = int(os.environ.get('HW', 416))
+MODE = os.environ.get('MODE', 'both')
+REPS = int(os.environ.get('REPS', 5))
+torch.manual_seed(0)
+_w = torch.randn(4096, 4096, device='cuda')
+for _ in range(20):
+    _w @ _w          # clock warm-up
+torch.cuda.synchronize()
+x = ops.tc_pack(torch.relu(torch.randn(N, 32, HW, HW, device='cuda')))
+w = torch.randn(32, 32, 3, 3, device='cuda') * 0.1
+bias = torch.randn(32, device='cuda') * 0.1
+wp = torch.randn(30, 32, 1, 1, device='cuda') * 0.5
+pb = torch.zeros(32, device='cuda')
+packed_row = ops.tc_rowconv_pack_weights(w, 32)
+packed_tile = ops.tc_pack_weights(w, [32])
+ppacked = ops.tc_pack_weights(wp, [32])
+
+
+def timeit(name, fn, flops, nbytes):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(REPS):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / REPS
+    print(f'{name:>28} N={N} @{HW}: {ms:8.3f} ms  {flops / ms / 1e9:7.1f} TF/s  {nbytes / ms / 1e6:7.0f} GB/s')
+
+
+S = HW * HW * N
+f_conv = 2.0 * 9 * 32 * 32 * S
+if MODE in ('both', 'tile'):
+    timeit('tile conv', lambda: ops.tc_conv3x3([x], packed_tile, bias, 32, True), f_conv, 128.0 * S)
+    y = ops.tc_conv3x3([x], packed_tile, bias, 32, True)
+    timeit('tile pred+softargmax', lambda: ops.tc_conv1x1_softargmax(y, ppacked, pb, 30), 2.0 * 32 * 30 * S, 64.0 * S)
+if MODE in ('both', 'plain'):
+    timeit('row conv', lambda: ops.tc_rowconv3x3(x, packed_row, bias, 32, True), f_conv, 128.0 * S)
+if MODE in ('both', 'fused'):
+    timeit('row conv+pred+softargmax', lambda: ops.tc_rowconv3x3_pred_softargmax(x, packed_row, bias, 32, True, ppacked, pb, 30),
+           f_conv + 2.0 * 32 * 30 * S, 64.0 * S)
