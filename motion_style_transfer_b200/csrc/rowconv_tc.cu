@@ -45,7 +45,7 @@ constexpr int RC_VW = 126;                      // valid output pixels per strip
 constexpr int RC_CHUNK_BYTES = RC_M * 16;       // one 8-channel chunk of a window row
 constexpr int RC_CO = 32;                       // output channels = columns per TMEM slot
 constexpr int RC_NS = 8;                        // TMEM slot ring (256 columns)
-constexpr int RC_STAGES = 6;                    // input-row ring
+constexpr int RC_STAGES = 8;                    // input-row ring (= RC_NS: ring positions of a row are compile-time)
 constexpr int RC_NY = 4;                        // conv-output row ring (fused tail)
 constexpr int RC_MAX_KB = 4;                    // <= 64 input channels
 constexpr int RC_WBLK = 2 * 96 * 16;            // weights of one (K block, kw): [2 chunks][96 = (kh, co)][8 ch] bf16
@@ -109,6 +109,140 @@ __device__ __forceinline__ uint32_t pack_bf16_act(uint32_t lo, uint32_t hi) {
 }
 
 __device__ __forceinline__ int rc_slot(int row) { return RC_NS - 1 - (row & (RC_NS - 1)); }
+
+// ---- single-thread issue paths with compile-time ring positions -----------------------------------------------------------
+// The issuing thread is a scalar instruction stream (~8 cycles per dependent instruction): at ~150 instructions per row it,
+// not the tensor pipe, bounded the kernel (profiles/ncu_r02_rowconv_fused_v3.md).  Rows repeat with period 8 (slot ring =
+// stage ring = 8), so an interior row's barrier addresses, TMEM columns and descriptor offsets are immediates.
+constexpr uint32_t RC_A_HI = (uint32_t)(128 >> 4) | (1u << 14);                  // SBO = 128 B | descriptor version
+constexpr uint32_t RC_B_HI = (uint32_t)(128 >> 4) | (1u << 14);
+constexpr uint32_t RC_IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+
+// kernel rows KH0 .. KH0 + LEN - 1 of one input row -> LEN consecutive slots starting at SLOT
+template <int KH0, int LEN, int SLOT, int KB>
+__device__ __forceinline__ void rc_run(uint32_t tmem_base, uint32_t a_lo, uint32_t w_lo0, int kbn) {
+  constexpr uint32_t idesc = RC_IDESC0 | ((uint32_t)(LEN * (RC_CO >> 3)) << 17);
+  const uint32_t d_tmem = tmem_base + (uint32_t)(SLOT * RC_CO);
+  const uint32_t b_lo0 = w_lo0 + (uint32_t)(KH0 * RC_CO);
+  if (KB > 0) {
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+        tc_mma_bf16(d_tmem, ((uint64_t)RC_A_HI << 32) | (a_lo + (uint32_t)(kb * 2 * (RC_CHUNK_BYTES >> 4) + kw)),
+                    ((uint64_t)RC_B_HI << 32) | (b_lo0 + (uint32_t)((kb * 3 + kw) * (RC_WBLK >> 4))), idesc, 1u);
+  } else {
+    uint32_t a = a_lo, b = b_lo0;
+    for (int kb = 0; kb < kbn; ++kb) {
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+        tc_mma_bf16(d_tmem, ((uint64_t)RC_A_HI << 32) | (a + (uint32_t)kw),
+                    ((uint64_t)RC_B_HI << 32) | (b + (uint32_t)(kw * (RC_WBLK >> 4))), idesc, 1u);
+      a += 2 * (RC_CHUNK_BYTES >> 4);
+      b += 3 * (RC_WBLK >> 4);
+    }
+  }
+}
+
+// an INTERIOR input row (1 <= Y <= H - 2) whose running index g has g % 8 == POS.  bars = shared address of in_full[0];
+// ph = (g >> 3) & 1.  Barrier block layout: in_full[8] in_empty[8] acc_full[8] acc_empty[8] ...
+template <int POS, int KB>
+__device__ __forceinline__ void rc_fast_row(uint32_t tmem_base, uint32_t a_lo, uint32_t w_lo0, int kbn, uint32_t bars,
+                                            uint32_t ph) {
+  constexpr int S_UP = RC_NS - 1 - ((POS + 1) & (RC_NS - 1));      // slot of output row g + 1 (first written here)
+  constexpr int S_MID = RC_NS - 1 - POS;
+  constexpr int S_DN = RC_NS - 1 - ((POS + RC_NS - 1) & (RC_NS - 1));   // slot of output row g - 1 (completed here)
+  mbar_wait(bars + 8u * (3 * RC_NS + S_UP), (POS == RC_NS - 1) ? ph : (ph ^ 1u), nullptr);   // acc_empty[S_UP], use (g + 1) / 8
+  mbar_wait(bars + 8u * POS, ph, nullptr);                                                   // in_full[POS]
+  tc_fence_after();
+  if (POS == RC_NS - 1) {          // the ring wraps between rows g + 1 and g
+    rc_run<0, 1, S_UP, KB>(tmem_base, a_lo, w_lo0, kbn);
+    rc_run<1, 2, S_MID, KB>(tmem_base, a_lo, w_lo0, kbn);
+  } else if (POS == 0) {           // ... between rows g and g - 1
+    rc_run<0, 2, S_UP, KB>(tmem_base, a_lo, w_lo0, kbn);
+    rc_run<2, 1, S_DN, KB>(tmem_base, a_lo, w_lo0, kbn);
+  } else {
+    rc_run<0, 3, S_UP, KB>(tmem_base, a_lo, w_lo0, kbn);
+  }
+  tc_commit(bars + 8u * (RC_NS + POS));              // in_empty[POS]
+  tc_commit(bars + 8u * (2 * RC_NS + S_DN));         // acc_full[S_DN]: output row g - 1 is complete
+}
+
+template <int KB>
+__device__ __forceinline__ void rc_conv_issuer(const RcParams& p, uint32_t tmem_base, uint32_t a_base, uint32_t w_lo0,
+                                               uint32_t bars) {
+  constexpr uint32_t B_LBO_DUMMY = 0;
+  (void)B_LBO_DUMMY;
+  const uint32_t a_step = (uint32_t)(p.row_bytes >> 4);
+  const int kbn = p.kb, H = p.H;
+  const uint32_t in_full = bars, in_empty = bars + 8u * RC_NS, acc_full = bars + 16u * RC_NS, acc_empty = bars + 24u * RC_NS;
+  int g = 0;                                 // running row index of this CTA: slot ring and stage ring position
+  for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+    for (int Y = 0; Y < H; ++Y, ++g) {
+      const int pos = g & (RC_NS - 1);
+      const uint32_t ph = (uint32_t)((g >> 3) & 1);
+      const uint32_t a_lo = a_base + (uint32_t)pos * a_step;
+      if (Y >= 1 && Y + 1 < H) {
+        if (pos == 0 && Y + RC_NS < H) {       // eight interior rows in a row: straight-line code
+          uint32_t a = a_lo;
+          rc_fast_row<0, KB>(tmem_base, a, w_lo0, kbn, bars, ph);  a += a_step;
+          rc_fast_row<1, KB>(tmem_base, a, w_lo0, kbn, bars, ph);  a += a_step;
+          rc_fast_row<2, KB>(tmem_base, a, w_lo0, kbn, bars, ph);  a += a_step;
+          rc_fast_row<3, KB>(tmem_base, a, w_lo0, kbn, bars, ph);  a += a_step;
+          rc_fast_row<4, KB>(tmem_base, a, w_lo0, kbn, bars, ph);  a += a_step;
+          rc_fast_row<5, KB>(tmem_base, a, w_lo0, kbn, bars, ph);  a += a_step;
+          rc_fast_row<6, KB>(tmem_base, a, w_lo0, kbn, bars, ph);  a += a_step;
+          rc_fast_row<7, KB>(tmem_base, a, w_lo0, kbn, bars, ph);
+          Y += RC_NS - 1;
+          g += RC_NS - 1;
+          continue;
+        }
+        switch (pos) {
+          case 0: rc_fast_row<0, KB>(tmem_base, a_lo, w_lo0, kbn, bars, ph); break;
+          case 1: rc_fast_row<1, KB>(tmem_base, a_lo, w_lo0, kbn, bars, ph); break;
+          case 2: rc_fast_row<2, KB>(tmem_base, a_lo, w_lo0, kbn, bars, ph); break;
+          case 3: rc_fast_row<3, KB>(tmem_base, a_lo, w_lo0, kbn, bars, ph); break;
+          case 4: rc_fast_row<4, KB>(tmem_base, a_lo, w_lo0, kbn, bars, ph); break;
+          case 5: rc_fast_row<5, KB>(tmem_base, a_lo, w_lo0, kbn, bars, ph); break;
+          case 6: rc_fast_row<6, KB>(tmem_base, a_lo, w_lo0, kbn, bars, ph); break;
+          default: rc_fast_row<7, KB>(tmem_base, a_lo, w_lo0, kbn, bars, ph); break;
+        }
+        continue;
+      }
+      // ---- first / last row of a strip: generic path (2 rows in H) ----
+      // the slots this row writes FIRST must have been drained: row g + 1 (and row g at the top of a strip)
+      if (Y == 0) mbar_wait(acc_empty + 8u * rc_slot(g), ph ^ 1u, nullptr);
+      if (Y + 1 < H) mbar_wait(acc_empty + 8u * rc_slot(g + 1), (uint32_t)((((g + 1) >> 3) & 1) ^ 1), nullptr);
+      mbar_wait(in_full + 8u * pos, ph, nullptr);
+      tc_fence_after();
+      // kernel rows kh_lo..kh_hi contribute (output row g + 1 - kh must exist).  The slots of rows g + 1, g, g - 1 are
+      // consecutive except where the ring wraps: after kh = 0 when g % 8 == 7, after kh = 1 when g % 8 == 0.
+      const int kh_lo = (Y + 1 < H) ? 0 : 1, kh_hi = (Y >= 1) ? 2 : 1;
+      const int brk = (pos == RC_NS - 1) ? 1 : (pos == 0 ? 2 : 3);          // first kernel row of a second run
+      auto issue = [&](int kh0, int len) {
+        const uint32_t idesc = RC_IDESC0 | ((uint32_t)(len * (RC_CO >> 3)) << 17);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(rc_slot(g + 1 - kh0) * RC_CO);
+        uint32_t b_lo = w_lo0 + (uint32_t)(kh0 * RC_CO);
+        uint32_t a = a_lo;
+        for (int kb = 0; kb < kbn; ++kb) {
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+            tc_mma_bf16(d_tmem, ((uint64_t)RC_A_HI << 32) | (a + (uint32_t)kw),
+                        ((uint64_t)RC_B_HI << 32) | (b_lo + (uint32_t)(kw * (RC_WBLK >> 4))), idesc, 1u);
+          a += 2 * (RC_CHUNK_BYTES >> 4);
+          b_lo += 3 * (RC_WBLK >> 4);
+        }
+      };
+      const int a_end = min(brk, kh_hi + 1);
+      if (a_end > kh_lo) issue(kh_lo, a_end - kh_lo);
+      const int b0 = max(brk, kh_lo);
+      if (b0 <= kh_hi) issue(b0, kh_hi - b0 + 1);
+      tc_commit(in_empty + 8u * pos);
+      if (Y >= 1) tc_commit(acc_full + 8u * rc_slot(g - 1));
+      if (Y == H - 1) tc_commit(acc_full + 8u * rc_slot(g));
+    }
+  }
+}
 
 template <bool FUSE>
 __global__ void __launch_bounds__(FUSE ? RC_THREADS_FUSED : RC_THREADS_PLAIN, FUSE ? 1 : 2)
@@ -215,62 +349,14 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map, const RcParams p) {
     if (elect_one()) {
       mbar_wait(smem_u32(w_bar), 0, nullptr);
       // descriptors: K-major, no swizzle; LBO = chunk stride, SBO = stride of 8-row groups (128 B: rows are contiguous)
-      constexpr uint32_t A_HI = (uint32_t)(128 >> 4) | (1u << 14);
       constexpr uint32_t A_LBO = (uint32_t)(RC_CHUNK_BYTES >> 4) << 16;
-      constexpr uint32_t B_HI = (uint32_t)(128 >> 4) | (1u << 14);
       constexpr uint32_t B_LBO = (uint32_t)((96 * 16) >> 4) << 16;
       const uint32_t w_lo0 = ((smem_u32(s_w) >> 4) & 0x3FFF) | B_LBO;
       const uint32_t a_base = ((smem_u32(s_in) >> 4) & 0x3FFF) | A_LBO;
-      const uint32_t a_step = (uint32_t)(p.row_bytes >> 4);
-      constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
-      const int kbn = p.kb, H = p.H;
-      int stage = 0;
-      uint32_t phase = 0;
-      int g = 0;                             // running output-row index of this CTA (slot ring position)
-      // one run of MMAs: kernel rows kh0 .. kh0 + len - 1 of input row g -> the slots of output rows g + 1 - kh0 ...
-      auto issue = [&](uint32_t a_lo0, int kh0, int len) {
-        const uint32_t idesc = IDESC0 | ((uint32_t)(len * (RC_CO >> 3)) << 17);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(rc_slot(g + 1 - kh0) * RC_CO);
-        uint32_t b_lo = w_lo0 + (uint32_t)(kh0 * RC_CO);                       // 32 weight rows x 16 B per kernel row
-        uint32_t a_lo = a_lo0;
-        for (int kb = 0; kb < kbn; ++kb) {
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const uint64_t adesc = ((uint64_t)A_HI << 32) | (a_lo + (uint32_t)kw);
-            const uint64_t bdesc = ((uint64_t)B_HI << 32) | (b_lo + (uint32_t)(kw * (RC_WBLK >> 4)));
-            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
-          }
-          a_lo += 2 * (RC_CHUNK_BYTES >> 4);
-          b_lo += 3 * (RC_WBLK >> 4);
-        }
-      };
-      for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
-        for (int Y = 0; Y < H; ++Y, ++g) {
-          // the slots this row writes FIRST must have been drained: row g + 1 (and row g at the top of a strip)
-          if (Y == 0) mbar_wait(smem_u32(&acc_empty[rc_slot(g)]), (uint32_t)(((g / RC_NS) & 1) ^ 1), nullptr);
-          if (Y + 1 < H)
-            mbar_wait(smem_u32(&acc_empty[rc_slot(g + 1)]), (uint32_t)((((g + 1) / RC_NS) & 1) ^ 1), nullptr);
-          mbar_wait(smem_u32(&in_full[stage]), phase, nullptr);
-          tc_fence_after();
-          // kernel rows kh_lo..kh_hi contribute (output row g + 1 - kh must exist).  The slots of rows g + 1, g, g - 1 are
-          // consecutive except where the ring wraps: after kh = 0 when g % 8 == 7, after kh = 1 when g % 8 == 0.
-          const int kh_lo = (Y + 1 < H) ? 0 : 1, kh_hi = (Y >= 1) ? 2 : 1;
-          const int pos = g & (RC_NS - 1);
-          const int brk = (pos == RC_NS - 1) ? 1 : (pos == 0 ? 2 : 3);          // first kernel row of a second run
-          const uint32_t a_lo0 = a_base + (uint32_t)stage * a_step;
-          const int a_end = min(brk, kh_hi + 1);
-          if (a_end > kh_lo) issue(a_lo0, kh_lo, a_end - kh_lo);
-          const int b0 = max(brk, kh_lo);
-          if (b0 <= kh_hi) issue(a_lo0, b0, kh_hi - b0 + 1);
-          tc_commit(smem_u32(&in_empty[stage]));
-          if (Y >= 1) tc_commit(smem_u32(&acc_full[rc_slot(g - 1)]));
-          if (Y == H - 1) tc_commit(smem_u32(&acc_full[rc_slot(g)]));
-          if (++stage == RC_STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-      }
+      if (p.kb == 2)
+        rc_conv_issuer<2>(p, tmem_base, a_base, w_lo0, smem_u32(in_full));
+      else
+        rc_conv_issuer<0>(p, tmem_base, a_base, w_lo0, smem_u32(in_full));
     }
   } else if (warp < 2 + RC_EPI_WARPS) {
     // ===================== conv epilogue: 2 sets x 4 warps; warp w owns TMEM lanes 32 (w % 4) .. +31 = pixels; set k
@@ -343,20 +429,28 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map, const RcParams p) {
     // ===================== predictor MMA issuer: D[channel, pixel] = Wp (M = 128, replicated) x row (N = 128) ==========
     if (elect_one()) {
       constexpr uint32_t IDESC_P = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      // descriptors as (hi, lo) halves; the row buffer b and the K block only move the start-address field
+      constexpr uint32_t P_HI = (uint32_t)(128 >> 4) | (1u << 14);
+      constexpr uint32_t P_LBO = (uint32_t)((RC_M * 16) >> 4) << 16;
+      const uint32_t pa_lo = ((smem_u32(s_pw) >> 4) & 0x3FFF) | P_LBO;
+      const uint32_t pb_lo = ((smem_u32(s_y) >> 4) & 0x3FFF) | P_LBO;
+      const uint32_t yf = smem_u32(y_full), ye = smem_u32(y_empty), pf = smem_u32(p_full), pe = smem_u32(p_empty);
+      const int kbpn = p.kbp;
       int g = 0;
       for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
         for (int Y = 0; Y < p.H; ++Y, ++g) {
-          const int b = g & (RC_NY - 1), a = g & 1;
-          mbar_wait(smem_u32(&p_empty[a]), (uint32_t)(((g >> 1) & 1) ^ 1), nullptr);
-          mbar_wait(smem_u32(&y_full[b]), (uint32_t)((g / RC_NY) & 1), nullptr);
+          const uint32_t b = (uint32_t)(g & (RC_NY - 1)), a = (uint32_t)(g & 1);
+          mbar_wait(pe + 8u * a, (uint32_t)(((g >> 1) & 1) ^ 1), nullptr);
+          mbar_wait(yf + 8u * b, (uint32_t)((g / RC_NY) & 1), nullptr);
           tc_fence_after();
-          for (int kbp = 0; kbp < p.kbp; ++kbp) {
-            const uint64_t adesc = make_desc(smem_u32(s_pw + (size_t)kbp * PR_WBLK_BYTES), 128 * 16, 128);
-            const uint64_t bdesc = make_desc(smem_u32(s_y + (size_t)b * RC_YROW + (size_t)kbp * 2 * (RC_M * 16)), RC_M * 16, 128);
-            tc_mma_bf16(tmem_base + RC_PACC + (uint32_t)(a * 128), adesc, bdesc, IDESC_P, kbp > 0 ? 1u : 0u);
-          }
-          tc_commit(smem_u32(&p_full[a]));
-          tc_commit(smem_u32(&y_empty[b]));
+          const uint32_t d = tmem_base + RC_PACC + a * 128u;
+          const uint32_t bl = pb_lo + b * (uint32_t)(RC_YROW >> 4);
+          tc_mma_bf16(d, ((uint64_t)P_HI << 32) | pa_lo, ((uint64_t)P_HI << 32) | bl, IDESC_P, 0u);
+          if (kbpn > 1)
+            tc_mma_bf16(d, ((uint64_t)P_HI << 32) | (pa_lo + (uint32_t)(PR_WBLK_BYTES >> 4)),
+                        ((uint64_t)P_HI << 32) | (bl + (uint32_t)((2 * RC_M * 16) >> 4)), IDESC_P, 1u);
+          tc_commit(pf + 8u * a);
+          tc_commit(ye + 8u * b);
         }
       }
     }

@@ -9,7 +9,7 @@
 namespace ynet {
 
 constexpr unsigned TC_SPIN_LIMIT = 4u * 1000u * 1000u;             // bounded waits: trap instead of hanging
-constexpr uint32_t TC_WAIT_HINT_NS = 2000u;                       // mbarrier.try_wait suspend-time hint: the waiting warp sleeps in hardware instead of re-issuing the poll
+constexpr long long TC_WAIT_CYCLES = 8LL * 1000 * 1000 * 1000;    // ~4 s of SM clock
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -23,19 +23,28 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// mbarrier.try_wait WITHOUT a suspend-time hint: the instruction (SASS SYNCS...TRYWAIT) suspends the warp in hardware until
+// the phase completes or a system time limit expires, so a waiting warp issues nothing.  Round 1 passed a 2 us hint: ptxas
+// then emits TRYWAIT + NANOSLEEP.SYNCS + PHASECHK + a spin counter, and NANOSLEEP.SYNCS returns on ANY barrier activity of
+// the CTA -- with ~35 barriers toggling per row the waiting warps of rowconv_tc.cu re-issued that 7-instruction loop 20-40
+// times per wait and took more than half of the SM's issue slots away from the single-thread TMA / MMA roles
+// (profiles/ncu_r02_rowconv_fused_v3.md).  The spin bound stays: a protocol bug must trap, not hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err) {
   uint32_t done = 0;
   unsigned spins = 0;
+  long long t0 = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(TC_WAIT_HINT_NS)
+        : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    if (++spins > TC_SPIN_LIMIT) {  // a protocol bug must not hang the GPU
+    // a protocol bug must not hang the GPU: give up after TC_SPIN_LIMIT failed waits or ~4 s, whichever comes first
+    if (spins == 0) t0 = clock64();
+    if (++spins > TC_SPIN_LIMIT || clock64() - t0 > TC_WAIT_CYCLES) {
       if (err) atomicExch(err, 1);
       __trap();
     }
@@ -227,32 +236,15 @@ __device__ __forceinline__ void softargmax_row16(SoftState& st, const uint32_t (
   st.sy = fmaf((float)y, se, st.sy);
 }
 
-// The same for a row that crosses the right image border (pixels x0 + i >= W are masked).
+// The same for a row that crosses the right border (pixels x0 + i >= W are masked): the masked accumulators are replaced
+// by a huge negative value (their exponential is exactly 0) and the lean path does the rest.
 __device__ __forceinline__ void softargmax_row16_masked(SoftState& st, const uint32_t (&v)[16], float bias, int x0, int y,
                                                         int W) {
-  float mx = PR_NEG;
-  unsigned okm = 0;
+  if (x0 >= W) return;
+  uint32_t vm[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const bool ok = x0 + i < W;
-    okm |= ok ? (1u << i) : 0u;
-    if (ok) mx = fmaxf(mx, __uint_as_float(v[i]) + bias);
-  }
-  if (okm == 0) return;
-  if (mx > st.m) {
-    const float sc = (st.m == PR_NEG) ? 0.f : __expf(st.m - mx);
-    st.s *= sc;
-    st.sx *= sc;
-    st.sy *= sc;
-    st.m = mx;
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float ev = ((okm >> i) & 1u) ? __expf(__uint_as_float(v[i]) + bias - st.m) : 0.f;
-    st.s += ev;
-    st.sx = fmaf(ev, (float)(x0 + i), st.sx);
-    st.sy = fmaf(ev, (float)y, st.sy);
-  }
+  for (int i = 0; i < 16; ++i) vm[i] = (x0 + i < W) ? v[i] : __float_as_uint(-1.0e30f);
+  softargmax_row16(st, vm, bias, x0, y);
 }
 
 // Predictor weights [kb][2][n_pad][8] bf16 -> shared memory [kb][2][128][8] with the (<= 32) rows replicated into the
