@@ -339,6 +339,10 @@ int ynet_tc_conv1x1_softargmax(const ynet_tc_src* srcs_host, int32_t n_src, int3
  *       [K block][kw][2][96 = kh * 32 + co][8]; size = ynet_tc_rowconv_packed_weight_bytes(C_in_pad).
  *   ynet_tc_rowconv3x3: conv + bias + ReLU (relu & 1) -> C8 (N, C_out_pad / 8, H, W, 8); relu & 2: the
  *       replicate-padded (H + 2, W + 2) layout that ynet_tc_upconv3x3 consumes.  bias32: 32 floats, zero beyond C_out.
+ *       Up to 3 plain C8 sources = torch.cat along channels (ynet.py:466, evaluate.py:259), <= 64 padded channels in
+ *       total, weights packed over the per-source padded concatenation; partial_host (optional): the agent's hoisted
+ *       encoder-feature share of this conv (ynet_tc_conv3x3_hilo output, 32 channels hi [+ 32 lo]), added in fp32 by the
+ *       epilogue before the activation instead of re-entering through identity-weight MMAs.
  *   ynet_tc_rowconv3x3_pred_softargmax: conv + bias + ReLU -> 1x1 predictor -> SoftArgmax2D (ynet.py:468-469 + 582-583,
  *       softargmax.py:55-81) in ONE kernel: the conv output row stays in shared memory as the N operand of the predictor
  *       MMA, whose transposed accumulator (TMEM lane = channel) is reduced by the soft-argmax warps; neither the
@@ -348,8 +352,9 @@ int ynet_tc_conv1x1_softargmax(const ynet_tc_src* srcs_host, int32_t n_src, int3
 int64_t ynet_tc_rowconv_packed_weight_bytes(int32_t C_in_pad);
 int ynet_tc_rowconv_pack_weights(const float* weight, int32_t C_out, int32_t C_in, int32_t C_in_pad, void* packed,
                                  void* stream);
-int ynet_tc_rowconv3x3(const ynet_tc_src* src_host, int32_t N, int32_t H, int32_t W, const void* packed_weight,
-                       const float* bias32, int32_t C_out, int32_t relu, void* out_c8, int32_t C_out_pad, void* stream);
+int ynet_tc_rowconv3x3(const ynet_tc_src* srcs_host, int32_t n_src, const ynet_tc_src* partial_host, int32_t N,
+                       int32_t H, int32_t W, const void* packed_weight, const float* bias32, int32_t C_out, int32_t relu,
+                       void* out_c8, int32_t C_out_pad, void* stream);
 int64_t ynet_tc_rowconv_softargmax_workspace_bytes(int32_t N, int32_t C_pred, int32_t W);
 int ynet_tc_rowconv3x3_pred_softargmax(const ynet_tc_src* src_host, int32_t N, int32_t H, int32_t W,
                                        const void* packed_weight, const float* bias32, int32_t C_out, int32_t relu,

@@ -51,7 +51,7 @@ constexpr int RC_MAX_KB = 4;                    // <= 64 input channels
 constexpr int RC_WBLK = 2 * 96 * 16;            // weights of one (K block, kw): [2 chunks][96 = (kh, co)][8 ch] bf16
 constexpr int RC_YROW = 4 * RC_M * 16;          // one conv-output row: [4 chunks][128 px][8 ch] bf16
 constexpr int RC_EPI_WARPS = 8;                 // two sets of four (one warp per TMEM lane quadrant), alternating rows
-constexpr int RC_SOFT_WARPS = 8;                // likewise
+constexpr int RC_SOFT_WARPS = 16;               // two sets x 4 lane quadrants x 2 sixteen-pixel halves
 constexpr int RC_THREADS_PLAIN = 32 * (2 + RC_EPI_WARPS);        // TMA, MMA, epilogue warps
 constexpr int RC_THREADS_FUSED = 32 * (2 + RC_EPI_WARPS + 1 + RC_SOFT_WARPS);   // + predictor MMA warp + soft-argmax warps
 constexpr uint32_t RC_PACC = 256;               // first TMEM column of the two predictor accumulators (2 x 128)
@@ -60,8 +60,16 @@ struct RcParams {
   int N, H, W, kb, chunks, strips;
   long long items;
   int relu, out_chunks, pad_out;
-  int bcast, batch_mod;
-  int row_bytes;
+  int row_bytes;               // bytes of one row buffer = chunks * 2 KB
+  int row_tx;                  // bytes the TMA transactions of one row deliver (= stored chunks * 2 KB)
+  int n_src;                   // conv sources (<= 3): their chunks are laid side by side in the row buffer (torch.cat)
+  int src_stored[3];           // 8-channel planes source s really holds (TMA box depth)
+  int src_coff[3];             // first chunk slot of source s in the row buffer
+  int src_bcast[3], src_mod[3];
+  int zero_fill;               // some chunk slots are never written by TMA (K padding): zero the ring once
+  const uint4* part;           // hoisted partial sums (goal-loop hoisting, ynet_tc_conv3x3_hilo): bf16 C8, 4 chunks hi
+  long long part_bs;           //   [+ 4 chunks lo], added by the epilogue before the activation; batch stride in uint4
+  int part_mod, part_chunks;
   const unsigned char* w96;    // [kb][kw][2][96][8] bf16
   const float* bias;           // 32 floats (zero beyond C_out)
   __nv_bfloat16* out;          // plain: C8 planes (N, out_chunks, H + 2 pad, W + 2 pad, 8)
@@ -146,15 +154,26 @@ __device__ __forceinline__ void rc_run(uint32_t tmem_base, uint32_t a_lo, uint32
 
 // an INTERIOR input row (1 <= Y <= H - 2) whose running index g has g % 8 == POS.  bars = shared address of in_full[0];
 // ph = (g >> 3) & 1.  Barrier block layout: in_full[8] in_empty[8] acc_full[8] acc_empty[8] ...
-template <int POS, int KB>
-__device__ __forceinline__ void rc_fast_row(uint32_t tmem_base, uint32_t a_lo, uint32_t w_lo0, int kbn, uint32_t bars,
-                                            uint32_t ph) {
+// pre: bit 0 = acc_empty of this row already seen complete, bit 1 = in_full (probed while the previous row was issued);
+// returns the same two bits for row g + 1 (probed before this row's MMAs are issued) when PROBE, else 0.
+template <int POS, int KB, bool PROBE>
+__device__ __forceinline__ uint32_t rc_fast_row(uint32_t tmem_base, uint32_t a_lo, uint32_t w_lo0, int kbn, uint32_t bars,
+                                                uint32_t ph, uint32_t pre) {
   constexpr int S_UP = RC_NS - 1 - ((POS + 1) & (RC_NS - 1));      // slot of output row g + 1 (first written here)
   constexpr int S_MID = RC_NS - 1 - POS;
   constexpr int S_DN = RC_NS - 1 - ((POS + RC_NS - 1) & (RC_NS - 1));   // slot of output row g - 1 (completed here)
-  mbar_wait(bars + 8u * (3 * RC_NS + S_UP), (POS == RC_NS - 1) ? ph : (ph ^ 1u), nullptr);   // acc_empty[S_UP], use (g + 1) / 8
-  mbar_wait(bars + 8u * POS, ph, nullptr);                                                   // in_full[POS]
+  if (!(pre & 1u))
+    mbar_wait(bars + 8u * (3 * RC_NS + S_UP), (POS == RC_NS - 1) ? ph : (ph ^ 1u), nullptr);   // acc_empty[S_UP], use (g + 1) / 8
+  if (!(pre & 2u)) mbar_wait(bars + 8u * POS, ph, nullptr);                                    // in_full[POS]
   tc_fence_after();
+  uint32_t nxt = 0;
+  if (PROBE) {
+    constexpr int NP = (POS + 1) & (RC_NS - 1);
+    constexpr int S_UPN = RC_NS - 1 - ((NP + 1) & (RC_NS - 1));
+    const uint32_t phn = (POS == RC_NS - 1) ? (ph ^ 1u) : ph;
+    nxt = mbar_test(bars + 8u * (3 * RC_NS + S_UPN), (NP == RC_NS - 1) ? phn : (phn ^ 1u)) |
+          (mbar_test(bars + 8u * NP, phn) << 1);
+  }
   if (POS == RC_NS - 1) {          // the ring wraps between rows g + 1 and g
     rc_run<0, 1, S_UP, KB>(tmem_base, a_lo, w_lo0, kbn);
     rc_run<1, 2, S_MID, KB>(tmem_base, a_lo, w_lo0, kbn);
@@ -166,13 +185,12 @@ __device__ __forceinline__ void rc_fast_row(uint32_t tmem_base, uint32_t a_lo, u
   }
   tc_commit(bars + 8u * (RC_NS + POS));              // in_empty[POS]
   tc_commit(bars + 8u * (2 * RC_NS + S_DN));         // acc_full[S_DN]: output row g - 1 is complete
+  return nxt;
 }
 
 template <int KB>
 __device__ __forceinline__ void rc_conv_issuer(const RcParams& p, uint32_t tmem_base, uint32_t a_base, uint32_t w_lo0,
                                                uint32_t bars) {
-  constexpr uint32_t B_LBO_DUMMY = 0;
-  (void)B_LBO_DUMMY;
   const uint32_t a_step = (uint32_t)(p.row_bytes >> 4);
   const int kbn = p.kb, H = p.H;
   const uint32_t in_full = bars, in_empty = bars + 8u * RC_NS, acc_full = bars + 16u * RC_NS, acc_empty = bars + 24u * RC_NS;
@@ -183,29 +201,29 @@ __device__ __forceinline__ void rc_conv_issuer(const RcParams& p, uint32_t tmem_
       const uint32_t ph = (uint32_t)((g >> 3) & 1);
       const uint32_t a_lo = a_base + (uint32_t)pos * a_step;
       if (Y >= 1 && Y + 1 < H) {
-        if (pos == 0 && Y + RC_NS < H) {       // eight interior rows in a row: straight-line code
-          uint32_t a = a_lo;
-          rc_fast_row<0, KB>(tmem_base, a, w_lo0, kbn, bars, ph);  a += a_step;
-          rc_fast_row<1, KB>(tmem_base, a, w_lo0, kbn, bars, ph);  a += a_step;
-          rc_fast_row<2, KB>(tmem_base, a, w_lo0, kbn, bars, ph);  a += a_step;
-          rc_fast_row<3, KB>(tmem_base, a, w_lo0, kbn, bars, ph);  a += a_step;
-          rc_fast_row<4, KB>(tmem_base, a, w_lo0, kbn, bars, ph);  a += a_step;
-          rc_fast_row<5, KB>(tmem_base, a, w_lo0, kbn, bars, ph);  a += a_step;
-          rc_fast_row<6, KB>(tmem_base, a, w_lo0, kbn, bars, ph);  a += a_step;
-          rc_fast_row<7, KB>(tmem_base, a, w_lo0, kbn, bars, ph);
+        if (pos == 0 && Y + RC_NS < H) {       // eight interior rows in a row: straight-line code, probes one row ahead
+          uint32_t a = a_lo, pre = 0;
+          pre = rc_fast_row<0, KB, true>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
+          pre = rc_fast_row<1, KB, true>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
+          pre = rc_fast_row<2, KB, true>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
+          pre = rc_fast_row<3, KB, true>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
+          pre = rc_fast_row<4, KB, true>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
+          pre = rc_fast_row<5, KB, true>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
+          pre = rc_fast_row<6, KB, true>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
+          rc_fast_row<7, KB, false>(tmem_base, a, w_lo0, kbn, bars, ph, pre);
           Y += RC_NS - 1;
           g += RC_NS - 1;
           continue;
         }
         switch (pos) {
-          case 0: rc_fast_row<0, KB>(tmem_base, a_lo, w_lo0, kbn, bars, ph); break;
-          case 1: rc_fast_row<1, KB>(tmem_base, a_lo, w_lo0, kbn, bars, ph); break;
-          case 2: rc_fast_row<2, KB>(tmem_base, a_lo, w_lo0, kbn, bars, ph); break;
-          case 3: rc_fast_row<3, KB>(tmem_base, a_lo, w_lo0, kbn, bars, ph); break;
-          case 4: rc_fast_row<4, KB>(tmem_base, a_lo, w_lo0, kbn, bars, ph); break;
-          case 5: rc_fast_row<5, KB>(tmem_base, a_lo, w_lo0, kbn, bars, ph); break;
-          case 6: rc_fast_row<6, KB>(tmem_base, a_lo, w_lo0, kbn, bars, ph); break;
-          default: rc_fast_row<7, KB>(tmem_base, a_lo, w_lo0, kbn, bars, ph); break;
+          case 0: rc_fast_row<0, KB, false>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
+          case 1: rc_fast_row<1, KB, false>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
+          case 2: rc_fast_row<2, KB, false>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
+          case 3: rc_fast_row<3, KB, false>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
+          case 4: rc_fast_row<4, KB, false>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
+          case 5: rc_fast_row<5, KB, false>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
+          case 6: rc_fast_row<6, KB, false>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
+          default: rc_fast_row<7, KB, false>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
         }
         continue;
       }
@@ -246,7 +264,8 @@ __device__ __forceinline__ void rc_conv_issuer(const RcParams& p, uint32_t tmem_
 
 template <bool FUSE>
 __global__ void __launch_bounds__(FUSE ? RC_THREADS_FUSED : RC_THREADS_PLAIN, FUSE ? 1 : 2)
-tc_rowconv_kernel(const __grid_constant__ CUtensorMap map, const RcParams p) {
+tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                  const __grid_constant__ CUtensorMap map2, const RcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -286,7 +305,7 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map, const RcParams p) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&p_full[s]), 1);
-      mbar_init(smem_u32(&p_empty[s]), 4);
+      mbar_init(smem_u32(&p_empty[s]), RC_SOFT_WARPS / 2);
     }
     mbar_init(smem_u32(w_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -313,6 +332,11 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map, const RcParams p) {
       for (int s = 0; s < RC_NS; ++s) tmem_st32(t_row + (uint32_t)(s * RC_CO), bz);
     }
   }
+  if (p.zero_fill) {     // K-padding chunk slots that no TMA transaction ever writes must read as zero
+    uint4* z = reinterpret_cast<uint4*>(s_in);
+    for (int i = threadIdx.x; i < RC_STAGES * (p.row_bytes >> 4); i += NTHREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -330,13 +354,21 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map, const RcParams p) {
       uint32_t phase = 0;
       for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
         const int n = (int)(item / p.strips), s = (int)(item - (long long)n * p.strips);
-        const int ns = p.bcast ? 0 : (p.batch_mod > 0 ? n % p.batch_mod : (p.batch_mod < 0 ? n / (-p.batch_mod) : n));
+        int ns[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int bm = p.src_mod[i];
+          ns[i] = p.src_bcast[i] ? 0 : (bm > 0 ? n % bm : (bm < 0 ? n / (-bm) : n));
+        }
         const int c0 = 2 * (s * RC_VW - 1);                 // 8-byte elements: two per pixel
         for (int Y = 0; Y < p.H; ++Y) {
           mbar_wait(smem_u32(&in_empty[stage]), phase ^ 1, nullptr);
           const uint32_t fb = smem_u32(&in_full[stage]);
-          mbar_expect_tx(fb, (uint32_t)p.row_bytes);
-          tma_load_4d(smem_u32(s_in + (size_t)stage * p.row_bytes), &map, fb, c0, Y, 0, ns);
+          const uint32_t dst = smem_u32(s_in + (size_t)stage * p.row_bytes);
+          mbar_expect_tx(fb, (uint32_t)p.row_tx);
+          tma_load_4d(dst + (uint32_t)(p.src_coff[0] * RC_CHUNK_BYTES), &map0, fb, c0, Y, 0, ns[0]);
+          if (p.n_src > 1) tma_load_4d(dst + (uint32_t)(p.src_coff[1] * RC_CHUNK_BYTES), &map1, fb, c0, Y, 0, ns[1]);
+          if (p.n_src > 2) tma_load_4d(dst + (uint32_t)(p.src_coff[2] * RC_CHUNK_BYTES), &map2, fb, c0, Y, 0, ns[2]);
           if (++stage == RC_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -364,13 +396,24 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map, const RcParams p) {
     const int q = warp & 3, set = (warp - 2) >> 2;
     const int m = q * 32 + lane;                    // pixel of the window row (window starts at xs0 - 1: lane = x - xs0)
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    int g = 0;
-    for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+    int g0 = 0;                                     // running index of the strip's first row
+    const int H = p.H;
+    for (long long item = blockIdx.x; item < p.items; item += gridDim.x, g0 += H) {
       const int n = (int)(item / p.strips), s = (int)(item - (long long)n * p.strips);
       const int x = s * RC_VW + m;
       const bool live = m < RC_VW && x < p.W;
-      for (int Y = 0; Y < p.H; ++Y, ++g) {
-        if ((g & 1) != set) continue;
+      const int npart = p.part_mod > 0 ? n % p.part_mod : (p.part_mod < 0 ? n / (-p.part_mod) : n);
+      const uint4* part_px = p.part + (size_t)npart * p.part_bs + x;
+      const bool has_part = p.part != nullptr && live;
+      const size_t part_cs = (size_t)p.H * p.W;
+      uint4 ph[4];                 // this pixel's partial sums of the row being processed (loaded one row ahead)
+      if (!FUSE && has_part) {
+        const uint4* pp = part_px + (size_t)((g0 ^ set) & 1) * p.W;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ph[c] = __ldg(pp + (size_t)c * part_cs);
+      }
+      for (int Y = (g0 ^ set) & 1; Y < H; Y += 2) {          // this set's rows: g % 2 == set
+        const int g = g0 + Y;
         const int sl = rc_slot(g);
         mbar_wait(smem_u32(&acc_full[sl]), (uint32_t)((g / RC_NS) & 1), nullptr);
         tc_fence_after();
@@ -380,6 +423,38 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map, const RcParams p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&acc_empty[sl]));
+        if (!FUSE && has_part) {     // + the agent's hoisted encoder-feature share of this conv (fp32 add)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t hw[4] = {ph[c].x, ph[c].y, ph[c].z, ph[c].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              v[8 * c + 2 * k] = __float_as_uint(__uint_as_float(v[8 * c + 2 * k]) + __uint_as_float(hw[k] << 16));
+              v[8 * c + 2 * k + 1] =
+                  __float_as_uint(__uint_as_float(v[8 * c + 2 * k + 1]) + __uint_as_float(hw[k] & 0xFFFF0000u));
+            }
+          }
+          if (p.part_chunks > 4) {   // the low halves of the partial sums (YNET_HOIST_LO=1)
+            const uint4* pl = part_px + (size_t)Y * p.W + 4 * part_cs;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ph[c] = __ldg(pl + (size_t)c * part_cs);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t hw[4] = {ph[c].x, ph[c].y, ph[c].z, ph[c].w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                v[8 * c + 2 * k] = __float_as_uint(__uint_as_float(v[8 * c + 2 * k]) + __uint_as_float(hw[k] << 16));
+                v[8 * c + 2 * k + 1] =
+                    __float_as_uint(__uint_as_float(v[8 * c + 2 * k + 1]) + __uint_as_float(hw[k] & 0xFFFF0000u));
+              }
+            }
+          }
+          if (Y + 2 < H) {           // the next row of this set: in flight during the stores and the next accumulator wait
+            const uint4* pn = part_px + (size_t)(Y + 2) * p.W;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ph[c] = __ldg(pn + (size_t)c * part_cs);
+          }
+        }
         uint4 o[4];
         if (p.relu) {
 #pragma unroll
@@ -411,7 +486,9 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map, const RcParams p) {
         } else if (live) {
           const int po = p.pad_out;
           const int Hp = p.H + 2 * po, Wp = p.W + 2 * po;
-          for (int c = 0; c < p.out_chunks; ++c) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c >= p.out_chunks) break;
             uint4* dst = reinterpret_cast<uint4*>(p.out) + (((size_t)n * p.out_chunks + c) * Hp + (Y + po)) * Wp + (x + po);
             *dst = o[c];
             if (po) {      // replicate the border pixels into the ring (input of the phase-decomposed upconv)
@@ -455,37 +532,44 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map, const RcParams p) {
       }
     }
   } else if (FUSE) {
-    // ===================== soft-argmax: 2 sets x 4 warps; TMEM lane = channel, column = pixel of the window row; set k
-    // takes the rows with g % 2 == k (= predictor accumulator k), each warp the 32 pixels of its lane quadrant ==========
+    // ===================== soft-argmax: 2 sets x 4 lane quadrants x 2 halves = 16 warps; TMEM lane = channel, column =
+    // pixel of the window row; set k takes the rows with g % 2 == k (= predictor accumulator k), each warp 16 pixels =====
     const int e = warp - W_SOFT;
-    const int q = warp & 3, set = e >> 2;
-    const int col0 = 32 * q;
+    const int q = warp & 3, set = (e >> 2) & 1, half = e >> 3;
+    const int col0 = 32 * q + 16 * half;
     const bool active = lane < p.c_pred;
     const float bias = active ? p.pbias[lane] : 0.f;
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + RC_PACC + (uint32_t)(set * 128 + col0);
-    int g = 0;
-    for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+    const uint32_t pf = smem_u32(&p_full[set]), pe = smem_u32(&p_empty[set]);
+    const int H = p.H, W = p.W;
+    int g0 = 0;
+    for (long long item = blockIdx.x; item < p.items; item += gridDim.x, g0 += H) {
       const int n = (int)(item / p.strips), s = (int)(item - (long long)n * p.strips);
       const int x0 = s * RC_VW + col0;
-      const int lim = min(p.W, s * RC_VW + RC_VW);          // first pixel beyond this strip's valid columns
+      const int lim = min(W, s * RC_VW + RC_VW);          // first pixel beyond this strip's valid columns
       SoftState st{PR_NEG, 0.f, 0.f, 0.f};
-      for (int Y = 0; Y < p.H; ++Y, ++g) {
-        if ((g & 1) != set) continue;
-        mbar_wait(smem_u32(&p_full[set]), (uint32_t)((g >> 1) & 1), nullptr);
-        tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32(t_addr, v);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&p_empty[set]));      // the values are in registers: release the accumulator
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t(&vh)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&v[16 * h]);
-          const int xh = x0 + 16 * h;
-          if (xh + 16 <= lim)
-            softargmax_row16(st, vh, bias, xh, Y);
-          else if (xh < lim)
-            softargmax_row16_masked(st, vh, bias, xh, Y, lim);
+      if (x0 < lim) {
+        const bool full = x0 + 16 <= lim;
+        for (int Y = (g0 ^ set) & 1; Y < H; Y += 2) {
+          const int g = g0 + Y;
+          mbar_wait(pf, (uint32_t)((g >> 1) & 1), nullptr);
+          tc_fence_after();
+          uint32_t v[16];
+          tmem_ld16(t_addr, v);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pe);      // the values are in registers: release the accumulator
+          if (full)
+            softargmax_row16(st, v, bias, x0, Y);
+          else
+            softargmax_row16_masked(st, v, bias, x0, Y, lim);
+        }
+      } else {
+        // nothing to reduce in these columns (right of the image / of the strip), but the accumulator hand-shake goes on
+        for (int Y = (g0 ^ set) & 1; Y < H; Y += 2) {
+          mbar_wait(pf, (uint32_t)(((g0 + Y) >> 1) & 1), nullptr);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pe);
         }
       }
       if (active) p.partial[((size_t)n * p.c_pred + lane) * p.slots + s * RC_SOFT_WARPS + e] = make_float4(st.m, st.s, st.sx, st.sy);
@@ -519,14 +603,10 @@ rc_pack_weights_kernel(const float* __restrict__ w, int C_out, int C_in, int kb,
   }
 }
 
-static int rc_launch(const char* who, bool fuse, const ynet_tc_src* src, int N, int H, int W, RcParams& p, void* stream) {
-  if (!(src && src->ptr) || reinterpret_cast<uintptr_t>(src->ptr) % 16 != 0) {
-    set_error("%s: source must be a 16-byte aligned C8 tensor", who);
-    return YNET_E_INVALID;
-  }
-  const int cp = src->channels_pad;
-  if (!(cp > 0 && cp % 16 == 0 && cp / 16 <= RC_MAX_KB) || src->padded || src->center_only || src->tap_mask) {
-    set_error("%s: channels_pad must be 16..64 (plain C8 source)", who);
+static int rc_launch(const char* who, bool fuse, const ynet_tc_src* srcs, int n_src, const ynet_tc_src* partial, int N,
+                     int H, int W, RcParams& p, void* stream) {
+  if (!(srcs && n_src >= 1 && n_src <= 3)) {
+    set_error("%s: 1..3 conv sources", who);
     return YNET_E_INVALID;
   }
   if (!(N >= 0 && H >= 2 && W >= 1)) {
@@ -539,38 +619,76 @@ static int rc_launch(const char* who, bool fuse, const ynet_tc_src* src, int N, 
     set_error("%s: cuTensorMapEncodeTiled is not available from the driver", who);
     return YNET_E_UNSUPPORTED;
   }
-  const bool bcast = src->batch_stride == 0;
-  const int bmod = src->batch_mod;
-  const int nsrc = bcast ? 1 : (bmod > 0 ? bmod : (bmod < 0 ? ceil_div(N, -bmod) : N));
-  const int stored = (src->chunks_stored > 0) ? src->chunks_stored : cp / 8;
-  // The planes as 8-byte elements, two per pixel: a box line may then span 128 pixels (256 elements) from any pixel.
-  const cuuint64_t dims[4] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)stored, (cuuint64_t)nsrc};
-  const cuuint64_t bs = bcast ? (cuuint64_t)stored * H * W * 16 : (cuuint64_t)src->batch_stride * 2;
-  if (bs % 16 != 0) {
-    set_error("%s: batch stride must be a multiple of 8 elements", who);
-    return YNET_E_ALIGN;
+  CUtensorMap maps[3];
+  memset(maps, 0, sizeof(maps));
+  int chunks = 0, stored_total = 0;
+  for (int i = 0; i < n_src; ++i) {
+    const ynet_tc_src& sc = srcs[i];
+    const int cp = sc.channels_pad;
+    if (!sc.ptr || reinterpret_cast<uintptr_t>(sc.ptr) % 16 != 0 || !(cp > 0 && cp % 16 == 0) || sc.padded ||
+        sc.center_only || sc.tap_mask) {
+      set_error("%s: source %d must be a plain 16-byte aligned C8 tensor with channels_pad a multiple of 16", who, i);
+      return YNET_E_INVALID;
+    }
+    const bool bcast = sc.batch_stride == 0;
+    const int bmod = sc.batch_mod;
+    const int nsrc = bcast ? 1 : (bmod > 0 ? bmod : (bmod < 0 ? ceil_div(N, -bmod) : N));
+    const int stored = (sc.chunks_stored > 0) ? sc.chunks_stored : cp / 8;
+    if (stored > cp / 8) {
+      set_error("%s: source %d stores more planes than channels_pad / 8", who, i);
+      return YNET_E_INVALID;
+    }
+    // The planes as 8-byte elements, two per pixel: a box line may then span 128 pixels (256 elements) from any pixel.
+    const cuuint64_t dims[4] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)stored, (cuuint64_t)nsrc};
+    const cuuint64_t bs = bcast ? (cuuint64_t)stored * H * W * 16 : (cuuint64_t)sc.batch_stride * 2;
+    if (bs % 16 != 0) {
+      set_error("%s: batch stride must be a multiple of 8 elements", who);
+      return YNET_E_ALIGN;
+    }
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, bs};
+    const cuuint32_t box[4] = {(cuuint32_t)RC_M * 2, 1, (cuuint32_t)stored, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(sc.ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("%s: cuTensorMapEncodeTiled failed (%d) for source %d (W=%d H=%d C=%d)", who, (int)r, i, W, H, cp);
+      return YNET_E_CUDA;
+    }
+    p.src_stored[i] = stored;
+    p.src_coff[i] = chunks;
+    p.src_bcast[i] = bcast ? 1 : 0;
+    p.src_mod[i] = bmod;
+    chunks += cp / 8;
+    stored_total += stored;
   }
-  const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, bs};
-  const cuuint32_t box[4] = {(cuuint32_t)RC_M * 2, 1, (cuuint32_t)(cp / 8), 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUtensorMap map;
-  memset(&map, 0, sizeof(map));
-  CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(src->ptr), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("%s: cuTensorMapEncodeTiled failed (%d) (W=%d H=%d C=%d)", who, (int)r, W, H, cp);
-    return YNET_E_CUDA;
+  for (int i = n_src; i < 3; ++i) maps[i] = maps[0];
+  if (chunks / 2 > RC_MAX_KB) {
+    set_error("%s: more than %d input channels", who, RC_MAX_KB * 16);
+    return YNET_E_UNSUPPORTED;
+  }
+  p.n_src = n_src;
+  p.zero_fill = (stored_total != chunks) ? 1 : 0;
+  p.row_tx = stored_total * RC_CHUNK_BYTES;
+  if (partial != nullptr) {
+    const int pc = partial->channels_pad / 8;
+    if (!partial->ptr || reinterpret_cast<uintptr_t>(partial->ptr) % 16 != 0 || !(pc == 4 || pc == 8) ||
+        partial->batch_stride <= 0 || fuse) {
+      set_error("%s: the partial-sum source must be a 32- or 64-channel (hi | lo) C8 tensor", who);
+      return YNET_E_INVALID;
+    }
+    p.part = reinterpret_cast<const uint4*>(partial->ptr);
+    p.part_bs = partial->batch_stride / 8;
+    p.part_mod = partial->batch_mod;
+    p.part_chunks = pc;
   }
   p.N = N;
   p.H = H;
   p.W = W;
-  p.kb = cp / 16;
-  p.chunks = cp / 8;
+  p.kb = chunks / 2;
+  p.chunks = chunks;
   p.strips = ceil_div(W, RC_VW);
   p.items = (long long)N * p.strips;
-  p.bcast = bcast ? 1 : 0;
-  p.batch_mod = bmod;
   p.row_bytes = p.chunks * RC_CHUNK_BYTES;
   const size_t smem = (size_t)p.kb * 3 * RC_WBLK + (size_t)RC_STAGES * p.row_bytes + 1024 +
                       (fuse ? (size_t)RC_NY * RC_YROW + 2 * PR_WBLK_BYTES : 0) + 64 * 8 + 16 + 1024;
@@ -586,14 +704,14 @@ static int rc_launch(const char* who, bool fuse, const ynet_tc_src* src, int N, 
     set_error("%s: layer does not fit shared memory", who);
     return YNET_E_UNSUPPORTED;
   }
-  // plain: 256 TMEM columns and < 100 KB per CTA -> two co-resident CTAs per SM; fused: one (512 columns)
+  // plain: 256 TMEM columns and < 110 KB per CTA -> two co-resident CTAs per SM; fused: one (512 columns)
   const int per_sm = fuse ? 1 : ((smem + 1024 <= 110 * 1024) ? 2 : 1);
   const long long grid = tmin<long long>(p.items, (long long)sm_count() * per_sm);
   cudaStream_t st = as_stream(stream);
   if (fuse)
-    tc_rowconv_kernel<true><<<(unsigned)grid, RC_THREADS_FUSED, smem, st>>>(map, p);
+    tc_rowconv_kernel<true><<<(unsigned)grid, RC_THREADS_FUSED, smem, st>>>(maps[0], maps[1], maps[2], p);
   else
-    tc_rowconv_kernel<false><<<(unsigned)grid, RC_THREADS_PLAIN, smem, st>>>(map, p);
+    tc_rowconv_kernel<false><<<(unsigned)grid, RC_THREADS_PLAIN, smem, st>>>(maps[0], maps[1], maps[2], p);
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) return cuda_fail(le, who);
   return YNET_OK;
@@ -624,8 +742,9 @@ int ynet_tc_rowconv_pack_weights(const float* weight, int32_t C_out, int32_t C_i
   return YNET_OK;
 }
 
-int ynet_tc_rowconv3x3(const ynet_tc_src* src, int32_t N, int32_t H, int32_t W, const void* packed_weight,
-                       const float* bias32, int32_t C_out, int32_t relu, void* out_c8, int32_t C_out_pad, void* stream) {
+int ynet_tc_rowconv3x3(const ynet_tc_src* srcs, int32_t n_src, const ynet_tc_src* partial, int32_t N, int32_t H, int32_t W,
+                       const void* packed_weight, const float* bias32, int32_t C_out, int32_t relu, void* out_c8,
+                       int32_t C_out_pad, void* stream) {
   YNET_CHECK_ARG(packed_weight && bias32 && (out_c8 || N == 0), "null pointer");
   YNET_CHECK_ARG(C_out > 0 && C_out <= RC_CO && C_out_pad % 16 == 0 && C_out_pad >= C_out && C_out_pad <= RC_CO, "C_out <= 32");
   YNET_CHECK_ALIGN(packed_weight, 16);
@@ -638,7 +757,7 @@ int ynet_tc_rowconv3x3(const ynet_tc_src* src, int32_t N, int32_t H, int32_t W, 
   p.pad_out = (relu & 2) ? 1 : 0;
   p.out = reinterpret_cast<__nv_bfloat16*>(out_c8);
   p.out_chunks = C_out_pad / 8;
-  return rc_launch("ynet_tc_rowconv3x3", false, src, N, H, W, p, stream);
+  return rc_launch("ynet_tc_rowconv3x3", false, srcs, n_src, partial, N, H, W, p, stream);
 }
 
 int64_t ynet_tc_rowconv_softargmax_workspace_bytes(int32_t N, int32_t C_pred, int32_t W) {
@@ -672,7 +791,7 @@ int ynet_tc_rowconv3x3_pred_softargmax(const ynet_tc_src* src, int32_t N, int32_
   p.pn_pad = ceil_div(C_pred, 16) * 16;
   p.kbp = ceil_div(C_out, 16);
   p.slots = ceil_div(W, RC_VW) * RC_SOFT_WARPS;
-  int rc = rc_launch("ynet_tc_rowconv3x3_pred_softargmax", true, src, N, H, W, p, stream);
+  int rc = rc_launch("ynet_tc_rowconv3x3_pred_softargmax", true, src, 1, nullptr, N, H, W, p, stream);
   if (rc != YNET_OK) return rc;
   cudaError_t le = pred_partial_finalize(p.partial, N * C_pred, p.slots, out, as_stream(stream));
   if (le != cudaSuccess) return cuda_fail(le, "ynet_tc_rowconv3x3_pred_softargmax");

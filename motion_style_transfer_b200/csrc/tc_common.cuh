@@ -50,6 +50,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
   }
 }
+// Non-blocking probe of a phase (1 = complete).  The MMA issuers probe the NEXT row's barriers before they issue the current
+// row's MMAs, so the ~100-cycle latency of the probe overlaps the issue work instead of stalling the scalar thread.
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
 // Whole-warp wait with uniform control flow afterwards: one lane spins, the warp reconverges on __syncwarp().  Used by
 // the MMA-issuing warp so that ptxas keeps the descriptor arithmetic on the uniform datapath.
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {

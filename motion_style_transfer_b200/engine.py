@@ -527,8 +527,29 @@ class YNetEngineTC(YNetEngine):
             out.append(self._partial(decoder.decoder[i][0], f'{key}.decoder.{i}.0', skip, c_up))
         return out
 
+    def _tconv_hoisted_row(self, module, key, up, partial, pyr_level, c_feat):
+        """The same through the row-marching kernel: conv sources [up, waypoint planes] side by side on the K axis, the
+        hoisted partial added in fp32 by the epilogue (no identity-weight MMAs)."""
+        srcs = [up, pyr_level]
+        ver = (module.weight._version, module.weight.data_ptr(), tuple(s.K_pad for s in srcs), c_feat,
+               _bias_version(module))
+        hit = self._wcache.get(key + '#rowhoist')
+        if hit is None or hit[0] != ver:
+            w = module.weight.detach()
+            parts = [(0, up.C, up.K_pad), (up.C + c_feat, up.C + c_feat + pyr_level.C, pyr_level.K_pad)]
+            bias = torch.zeros(32, dtype=torch.float32, device=w.device)
+            if module.bias is not None:
+                bias[:w.shape[0]] = module.bias.detach()
+            hit = (ver, ops.tc_rowconv_pack_weights_cat(w, parts), bias)
+            self._wcache[key + '#rowhoist'] = hit
+        return ops.tc_rowconv3x3(srcs, hit[1], hit[2], module.weight.shape[0], True, partial=partial)
+
     def _tconv_hoisted(self, module, key, up, partial, pyr_level, c_feat):
         """conv(cat(up, feature, waypoints)) with the feature share taken from ``partial``."""
+        if (self.rowconv and up is not None and not pyr_level.taps and not pyr_level.center
+                and ops.tc_rowconv_supported([up, pyr_level], module.weight.shape[0])
+                and partial.C_pad in (32, 64) and partial.H == up.H):
+            return self._tconv_hoisted_row(module, key, up, partial, pyr_level, c_feat)
         layout, srcs, c = [], [], 0
         if up is not None:
             layout.append(('conv', (0, up.C)))
@@ -597,6 +618,8 @@ class YNetEngineTC(YNetEngine):
             nb = b1 - b0
             wp = waypoint_samples[:, b0:b1].permute(1, 0, 2, 3).reshape(-1, 2).contiguous()   # (nb, G, n_wp) order
             quad = min(self.quad_levels, len(feats)) if (self.hoist and n_wp <= 2) else 0
+            if self.rowconv and quad and dec.decoder[len(feats) - 2][0].weight.shape[0] <= 32:
+                quad = 0      # the finest level's input conv runs in the row-marching kernel, which takes plain planes
             pyr = ops.tc_rasterize_pyramid(template, wp, nb * G, n_wp, H, W, len(feats), quad_levels=quad)
             if self.hoist and n_wp <= 3:
                 for lvl in range(min(self.im2col_levels, len(pyr))):

@@ -988,9 +988,15 @@ def tc_upconv3x3(sources, packed_phase_weight, bias_eff, border_weight, bias, C_
 
 # ---- row-marching kh-stacked conv (rowconv_tc.cu): the C_out <= 32 layers of the full-resolution decoder levels ----------
 def tc_rowconv_supported(a, C_out):
-    """Can ``tc_rowconv3x3*`` take the plain C8 activation ``a`` (see ynet_tc_rowconv3x3)?"""
-    return (isinstance(a, C8) and not a.pad and not a.center and not a.taps and a.K_pad <= 64 and C_out <= 32
-            and a.H >= 2)
+    """Can ``tc_rowconv3x3*`` take the plain C8 activation(s) ``a`` (one C8 or a list = channel concat)?"""
+    srcs = a if isinstance(a, (list, tuple)) else [a]
+    if not (1 <= len(srcs) <= 3) or C_out > 32:
+        return False
+    for s in srcs:
+        if not isinstance(s, C8) or s.pad or s.center or s.taps:
+            return False
+    return (sum(s.K_pad for s in srcs) <= 64 and srcs[0].H >= 2
+            and all(s.H == srcs[0].H and s.W == srcs[0].W for s in srcs))
 
 
 def tc_rowconv_pack_weights(weight_oihw, C_in_pad):
@@ -1004,26 +1010,51 @@ def tc_rowconv_pack_weights(weight_oihw, C_in_pad):
     return packed
 
 
-def _rowconv_src(a):
-    arr = (_lib.TcSrc * 1)()
-    arr[0].ptr = a.data.data_ptr()
-    arr[0].channels_pad = a.K_pad
-    arr[0].chunks_stored = a.C_pad // 8
-    arr[0].batch_stride = a.data.stride(0)
-    arr[0].batch_mod = -a.rep if a.rep > 1 else 0
+def tc_rowconv_pack_weights_cat(weight_oihw, parts):
+    """Packed weights of a multi-source row conv: ``parts`` = [(c0, c1, K_pad)] per source, in source order -- source i
+    carries input channels [c0, c1) of ``weight_oihw`` and occupies K_pad (multiple of 16) channels of the K axis."""
+    w = weight_oihw
+    cols = []
+    for c0, c1, kp in parts:
+        blk = torch.zeros(w.shape[0], kp, 3, 3, dtype=torch.float32, device=w.device)
+        blk[:, :c1 - c0] = w[:, c0:c1]
+        cols.append(blk)
+    wcat = torch.cat(cols, dim=1).contiguous()
+    return tc_rowconv_pack_weights(wcat, wcat.shape[1])
+
+
+def _rowconv_srcs(srcs, N):
+    arr = (_lib.TcSrc * len(srcs))()
+    for i, a in enumerate(srcs):
+        arr[i].ptr = a.data.data_ptr()
+        arr[i].channels_pad = a.K_pad
+        arr[i].chunks_stored = a.C_pad // 8
+        arr[i].batch_stride = 0 if (a.N == 1 and N > 1) else a.data.stride(0)
+        arr[i].batch_mod = _tc_batch_mod(a, N)
     return arr
 
 
-def tc_rowconv3x3(a, packed_weight, bias32, C_out, relu, pad_out=False):
-    """conv3x3 + bias (+ ReLU) of ONE plain C8 source with C_out <= 32 -> C8 (see ynet_tc_rowconv3x3)."""
+def tc_rowconv3x3(a, packed_weight, bias32, C_out, relu, pad_out=False, partial=None):
+    """conv3x3 + bias (+ ReLU) with C_out <= 32 of one plain C8 source or a list of <= 3 (= channel concat) -> C8
+    (see ynet_tc_rowconv3x3).  ``partial``: hoisted partial sums (tc_conv3x3_hilo output) added before the activation."""
+    srcs = list(a) if isinstance(a, (list, tuple)) else [a]
+    N = max(s.N for s in srcs + ([partial] if partial is not None else []))
+    H, W = srcs[0].H, srcs[0].W
     cp = _pad16(C_out)
     po = 1 if pad_out else 0
-    out = torch.empty(a.N, cp // 8, a.H + 2 * po, a.W + 2 * po, 8, dtype=torch.bfloat16, device=a.data.device)
-    with _timed('tc_rowconv_kernel', 2.0 * 9 * a.C * C_out * a.H * a.W * a.N,
-                2.0 * a.C_pad * min(a.data.shape[0], a.N) * a.H * a.W + 2.0 * cp * a.H * a.W * a.N,
-                tag=f'{a.K_pad}->{cp}@{a.H}x{a.W} N={a.N}'):
-        check(_L().ynet_tc_rowconv3x3(_rowconv_src(a), a.N, a.H, a.W, _ptr(packed_weight), _ptr(bias32), C_out,
-                                      (1 if relu else 0) | (2 * po), _ptr(out), cp, _stream()), 'tc_rowconv3x3')
+    out = torch.empty(N, cp // 8, H + 2 * po, W + 2 * po, 8, dtype=torch.bfloat16, device=srcs[0].data.device)
+    parr = None
+    in_bytes = sum(2.0 * s.C_pad * min(s.data.shape[0], N) for s in srcs) * H * W
+    if partial is not None:
+        parr = _rowconv_srcs([partial], N)
+        parr[0].channels_pad = partial.C_pad
+        in_bytes += 2.0 * partial.C_pad * min(partial.data.shape[0], N) * H * W
+    k_pad = sum(s.K_pad for s in srcs)
+    tag = f'{k_pad}{"+P" if partial is not None else ""}->{cp}@{H}x{W} N={N}'
+    with _timed('tc_rowconv_kernel', 2.0 * 9 * sum(s.C for s in srcs) * C_out * H * W * N,
+                in_bytes + 2.0 * cp * H * W * N, tag=tag):
+        check(_L().ynet_tc_rowconv3x3(_rowconv_srcs(srcs, N), len(srcs), parr, N, H, W, _ptr(packed_weight), _ptr(bias32),
+                                      C_out, (1 if relu else 0) | (2 * po), _ptr(out), cp, _stream()), 'tc_rowconv3x3')
     _count()
     return C8(out, C_out, 1, False, po)
 
@@ -1036,7 +1067,7 @@ def tc_rowconv3x3_pred_softargmax(a, packed_weight, bias32, C_out, relu, packed_
     flops = 2.0 * (9 * a.C * C_out + C_out * C_pred) * a.H * a.W * a.N
     with _timed('tc_rowconv_kernel<pred,softargmax>', flops, 2.0 * a.C_pad * min(a.data.shape[0], a.N) * a.H * a.W,
                 tag=f'{a.K_pad}->{_pad16(C_out)}->{C_pred}@{a.H}x{a.W} N={a.N}'):
-        check(_L().ynet_tc_rowconv3x3_pred_softargmax(_rowconv_src(a), a.N, a.H, a.W, _ptr(packed_weight), _ptr(bias32),
+        check(_L().ynet_tc_rowconv3x3_pred_softargmax(_rowconv_srcs([a], a.N), a.N, a.H, a.W, _ptr(packed_weight), _ptr(bias32),
                                                       C_out, 1 if relu else 0, _ptr(packed_pred), _ptr(pred_bias_pad), C_pred,
                                                       _ptr(out), _ptr(ws), ws.numel(), _stream()),
               'tc_rowconv3x3_pred_softargmax')

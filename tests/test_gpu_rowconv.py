@@ -127,3 +127,37 @@ def test_rowconv_pred_softargmax(ops, cin, cpred, H, W, N):
     np.testing.assert_allclose(got8, O.softargmax2d(F.conv2d(y, wp * 8, bp * 8)).numpy(), rtol=0, atol=0.25)
     unf8 = ops.tc_conv1x1_softargmax(yt, ppacked8, (pb * 8).cuda(), cpred).cpu().numpy()
     np.testing.assert_allclose(got8, unf8, rtol=0, atol=0.25)
+
+
+def test_rowconv_multi_source_with_hoisted_partial(ops):
+    """decoder.i.0 of the trajectory decoder as the row kernel runs it: cat(up, feature, waypoints) with the feature
+    share hoisted (tc_conv3x3_hilo, once per agent) and added by the epilogue; sources [up, waypoint plane] side by side
+    on the K axis; agent-major stacking (the partial is read as image n // G)."""
+    torch.manual_seed(4)
+    nb, G, H, W = 2, 3, 40, 150
+    c_up, c_feat, n_wp = 16, 32, 2
+    up = bf16_exact(torch.randn(nb * G, c_up, H, W))
+    feat = bf16_exact(torch.relu(torch.randn(nb, c_feat, H, W)))
+    wp = bf16_exact(torch.rand(nb * G, n_wp, H, W))
+    w = bf16_exact(torch.randn(32, c_up + c_feat + n_wp, 3, 3) * 0.1)
+    b = torch.randn(32) * 0.1
+    ref = F.relu(F.conv2d(torch.cat([up, feat.repeat_interleave(G, dim=0), wp], 1), w, b, padding=1))
+    a_up, a_wp = ops.tc_pack(up.cuda()), ops.tc_pack(wp.cuda())
+    f8 = ops.tc_pack(feat.cuda())
+    wf = w[:, c_up:c_up + c_feat].contiguous().cuda()
+    for with_lo, tol in ((True, 5e-3), (False, 8e-3)):
+        part = ops.tc_conv3x3_hilo([f8], ops.tc_pack_weights(wf, [c_feat]), 32, with_lo).repeat_interleave(G)
+        packed = ops.tc_rowconv_pack_weights_cat(w.cuda(), [(0, c_up, a_up.K_pad), (c_up + c_feat, c_up + c_feat + n_wp, a_wp.K_pad)])
+        out = ops.tc_rowconv3x3([a_up, a_wp], packed, _bias32(b), 32, True, partial=part)
+        torch.cuda.synchronize()
+        got = ops.tc_unpack(out).cpu()
+        assert got.shape == ref.shape
+        assert rel_err(got.numpy(), ref.numpy()) < tol
+    # three conv sources, no partial: plain concatenation
+    x3 = bf16_exact(torch.randn(nb * G, 8, H, W))
+    w3 = bf16_exact(torch.randn(24, c_up + 8 + n_wp, 3, 3) * 0.1)
+    ref3 = F.conv2d(torch.cat([up, x3, wp], 1), w3, None, padding=1)
+    a3 = ops.tc_pack(x3.cuda())
+    packed3 = ops.tc_rowconv_pack_weights_cat(w3.cuda(), [(0, 16, 16), (16, 24, a3.K_pad), (24, 26, a_wp.K_pad)])
+    out3 = ops.tc_rowconv3x3([a_up, a3, a_wp], packed3, torch.zeros(32).cuda(), 24, False)
+    assert rel_err(ops.tc_unpack(out3).cpu().numpy(), ref3.numpy()) < 5e-3

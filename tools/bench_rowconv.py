@@ -54,3 +54,18 @@ if MODE in ('both', 'plain'):
 if MODE in ('both', 'fused'):
     timeit('row conv+pred+softargmax', lambda: ops.tc_rowconv3x3_pred_softargmax(x, packed_row, bias, 32, True, ppacked, pb, 30),
            f_conv + 2.0 * 32 * 30 * S, 64.0 * S)
+
+if MODE in ('both', 'l2'):
+    # decoder.4.0 of the trajectory decoder: cat(up 16, feature 32 (hoisted), waypoints 2) -> 32, agent-major (G = 20)
+    G = 20
+    nb = N // G
+    up = ops.tc_pack(torch.randn(nb * G, 16, HW, HW, device='cuda'))
+    wpl = ops.tc_pack(torch.rand(nb * G, 2, HW, HW, device='cuda'))
+    wpl = ops.C8(wpl.data[:, :1].contiguous(), 2)          # one stored plane, as tc_rasterize_pyramid writes it
+    feat = ops.tc_pack(torch.relu(torch.randn(nb, 32, HW, HW, device='cuda')))
+    w2 = torch.randn(32, 50, 3, 3, device='cuda') * 0.1
+    part = ops.tc_conv3x3_hilo([feat], ops.tc_pack_weights(w2[:, 16:48].contiguous(), [32]), 32, False).repeat_interleave(G)
+    packed2 = ops.tc_rowconv_pack_weights_cat(w2, [(0, 16, 16), (48, 50, 16)])
+    S2 = HW * HW * nb * G
+    timeit('row conv [up|P|wp] -> 32', lambda: ops.tc_rowconv3x3([up, wpl], packed2, bias, 32, True, partial=part),
+           2.0 * 9 * 18 * 32 * S2, (32.0 + 16.0 + 64.0) * S2)
