@@ -34,10 +34,15 @@ WORKLOADS = {
     # BASELINE.json configs[0] shape: SDD short-term eval (config/sdd_shortterm_eval.yaml)
     'sdd_short': dict(obs=8, pred=12, wps=[11], resize=0.25, T=1.0, thr=0.01, ttst=False, cws=False, cwsp=None,
                       n_goal=20, n_traj=1),
+    # BASELINE.json configs[3] shape: Y-Net-Mod (network=fusion, n_fusion=2) on config/inD_shortterm_eval.yaml
+    # (scripts/inD/scene1_car_to_truck/ynetmod/*.sh:4-11), MoSA on the scene / motion / fusion branches
+    'ind_short_ynetmod': dict(obs=8, pred=12, wps=[11], resize=0.33, T=1.0, thr=0.002, ttst=False, cws=False, cwsp=None,
+                              n_goal=20, n_traj=1, network='fusion', n_fusion=2, position=['scene', 'motion', 'fusion']),
 }
 ENC, DEC = [32, 32, 64, 64, 64], [64, 64, 64, 32, 32]
 H = W = 416
-GF_PER_AGENT = {'ind_long_ttst_cws': 371.6, 'sdd_short': 364.7}    # reference-executed GFLOP
+GF_PER_AGENT = {'ind_long_ttst_cws': 371.6, 'sdd_short': 364.7,     # reference-executed GFLOP
+                'ind_short_ynetmod': 364.7 - 4.68 + 2.44}             # Y-Net-Mod encoder: 2.44 instead of 4.68 GF
 
 
 def load_peaks():
@@ -67,8 +72,9 @@ def build_model_state(cfg, seed=0):
     from motion_style_transfer_b200.models.ynet import YNet
     torch.manual_seed(seed)
     m = YNet(obs_len=cfg['obs'], pred_len=cfg['pred'], segmentation_model_fp=None, encoder_channels=ENC,
-             decoder_channels=DEC, n_waypoints=len(cfg['wps']), train_net='mosa_1', position=[0, 1, 2, 3, 4],
-             network='original')
+             decoder_channels=DEC, n_waypoints=len(cfg['wps']), train_net='mosa_1',
+             position=cfg.get('position', [0, 1, 2, 3, 4]), network=cfg.get('network', 'original'),
+             n_fusion=cfg.get('n_fusion'))
     g = torch.Generator().manual_seed(seed + 1)
     with torch.no_grad():
         for n, p in m.named_parameters():
@@ -130,8 +136,9 @@ def _reference_evaluate(model_state, cfg, B, device, seeds, ns):
     from torch.utils.data import DataLoader
     from motion_style_transfer_b200 import synthetic as S
     m = ns.ynet.YNet(obs_len=cfg['obs'], pred_len=cfg['pred'], segmentation_model_fp=None, encoder_channels=ENC,
-                     decoder_channels=DEC, n_waypoints=len(cfg['wps']), train_net='mosa_1', position=[0, 1, 2, 3, 4],
-                     network='original')
+                     decoder_channels=DEC, n_waypoints=len(cfg['wps']), train_net='mosa_1',
+                     position=cfg.get('position', [0, 1, 2, 3, 4]), network=cfg.get('network', 'original'),
+                     n_fusion=cfg.get('n_fusion'))
     m.load_state_dict(model_state, strict=True)
     m = m.to(device).eval()
     total = cfg['obs'] + cfg['pred']
@@ -151,7 +158,7 @@ def _reference_evaluate(model_state, cfg, B, device, seeds, ns):
         warnings.simplefilter('ignore')
         ade, fde, _, _ = ns.evaluate.evaluate(m, dl, images, device, 'sdd', None, tmpl, cfg['wps'], 'test', cfg['n_goal'],
                                               cfg['n_traj'], cfg['obs'], B, cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'],
-                                              cfg['thr'], cfg['cwsp'], network='original')
+                                              cfg['thr'], cfg['cwsp'], network=cfg.get('network', 'original'))
     if torch.device(device).type == 'cuda':
         torch.cuda.synchronize()
     return time.perf_counter() - t0, float(ade), float(fde)
@@ -162,8 +169,9 @@ def _torch_network_only(model_state, cfg, B, device, ns):
     softargmax) (evaluate.py:123-126, 248-266) -- on `device`, inputs resident, under fp32 (TF32 convs) and bf16 autocast:
     the cuDNN number the hand-written engine has to beat on the same silicon."""
     m = ns.ynet.YNet(obs_len=cfg['obs'], pred_len=cfg['pred'], segmentation_model_fp=None, encoder_channels=ENC,
-                     decoder_channels=DEC, n_waypoints=len(cfg['wps']), train_net='mosa_1', position=[0, 1, 2, 3, 4],
-                     network='original')
+                     decoder_channels=DEC, n_waypoints=len(cfg['wps']), train_net='mosa_1',
+                     position=cfg.get('position', [0, 1, 2, 3, 4]), network=cfg.get('network', 'original'),
+                     n_fusion=cfg.get('n_fusion'))
     m.load_state_dict(model_state, strict=True)
     m = m.to(device).eval()
     g = torch.Generator(device='cpu').manual_seed(0)
@@ -251,7 +259,9 @@ def run_reference(args, cfg, rank, world):
 
 
 def workload_name(args, cfg):
-    return (f'Y-Net+MoSA(mosa_1, encoder stages 0-4) {args.workload} eval, obs {cfg["obs"]}/pred {cfg["pred"]}, '
+    net = 'Y-Net-Mod+MoSA(mosa_1, scene/motion/fusion branches)' if cfg.get('network') == 'fusion' else \
+        'Y-Net+MoSA(mosa_1, encoder stages 0-4)'
+    return (f'{net} {args.workload} eval, obs {cfg["obs"]}/pred {cfg["pred"]}, '
             f'{cfg["n_goal"]} goals, TTST={cfg["ttst"]} (10k samples + k-means 19), CWS={cfg["cws"]}, '
             f'synthetic {H}x{W} semantic map, random-init weights')
 

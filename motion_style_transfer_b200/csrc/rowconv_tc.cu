@@ -52,8 +52,12 @@ constexpr int RC_WBLK = 2 * 96 * 16;            // weights of one (K block, kw):
 constexpr int RC_YROW = 4 * RC_M * 16;          // one conv-output row: [4 chunks][128 px][8 ch] bf16
 constexpr int RC_EPI_WARPS = 8;                 // two sets of four (one warp per TMEM lane quadrant), alternating rows
 constexpr int RC_SOFT_WARPS = 16;               // two sets x 4 lane quadrants x 2 sixteen-pixel halves
+// warp 0: TMA; warp 1: conv MMA issuer.  (rc_conv_issuer can split the rows between two issuing warps, ISS = 2: measured on
+// B200 it buys nothing once the barrier probes are hoisted -- 1.567 vs 1.570 ms per 320 images -- and the fp32 accumulation
+// order of a slot then depends on how the two threads' MMAs interleave, i.e. results change in the last bit from run to
+// run.  One issuer keeps the kernel deterministic.)
 constexpr int RC_THREADS_PLAIN = 32 * (2 + RC_EPI_WARPS);        // TMA, MMA, epilogue warps
-constexpr int RC_THREADS_FUSED = 32 * (2 + RC_EPI_WARPS + 1 + RC_SOFT_WARPS);   // + predictor MMA warp + soft-argmax warps
+constexpr int RC_THREADS_FUSED = 32 * (2 + RC_EPI_WARPS + 1 + RC_SOFT_WARPS);   // TMA, MMA, epilogue, predictor MMA, soft-argmax
 constexpr uint32_t RC_PACC = 256;               // first TMEM column of the two predictor accumulators (2 x 128)
 
 struct RcParams {
@@ -154,9 +158,12 @@ __device__ __forceinline__ void rc_run(uint32_t tmem_base, uint32_t a_lo, uint32
 
 // an INTERIOR input row (1 <= Y <= H - 2) whose running index g has g % 8 == POS.  bars = shared address of in_full[0];
 // ph = (g >> 3) & 1.  Barrier block layout: in_full[8] in_empty[8] acc_full[8] acc_empty[8] ...
-// pre: bit 0 = acc_empty of this row already seen complete, bit 1 = in_full (probed while the previous row was issued);
-// returns the same two bits for row g + 1 (probed before this row's MMAs are issued) when PROBE, else 0.
-template <int POS, int KB, bool PROBE>
+// Two issuing threads share the rows (issuer k: g % 2 == k), so an output row's accumulator is complete when BOTH the
+// issuer of its own input row (middle kernel row) and the issuer of the next input row (last contribution) have committed:
+// acc_full counts two arrivals.
+// pre: bit 0 = acc_empty of this row already seen complete, bit 1 = in_full (probed while this issuer's previous row was
+// issued); returns the same two bits for row g + 2 (probed before this row's MMAs are issued) when PROBE, else 0.
+template <int POS, int KB, bool PROBE, int ISS>
 __device__ __forceinline__ uint32_t rc_fast_row(uint32_t tmem_base, uint32_t a_lo, uint32_t w_lo0, int kbn, uint32_t bars,
                                                 uint32_t ph, uint32_t pre) {
   constexpr int S_UP = RC_NS - 1 - ((POS + 1) & (RC_NS - 1));      // slot of output row g + 1 (first written here)
@@ -168,9 +175,9 @@ __device__ __forceinline__ uint32_t rc_fast_row(uint32_t tmem_base, uint32_t a_l
   tc_fence_after();
   uint32_t nxt = 0;
   if (PROBE) {
-    constexpr int NP = (POS + 1) & (RC_NS - 1);
+    constexpr int NP = (POS + ISS) & (RC_NS - 1);
     constexpr int S_UPN = RC_NS - 1 - ((NP + 1) & (RC_NS - 1));
-    const uint32_t phn = (POS == RC_NS - 1) ? (ph ^ 1u) : ph;
+    const uint32_t phn = (POS >= RC_NS - ISS) ? (ph ^ 1u) : ph;
     nxt = mbar_test(bars + 8u * (3 * RC_NS + S_UPN), (NP == RC_NS - 1) ? phn : (phn ^ 1u)) |
           (mbar_test(bars + 8u * NP, phn) << 1);
   }
@@ -184,46 +191,60 @@ __device__ __forceinline__ uint32_t rc_fast_row(uint32_t tmem_base, uint32_t a_l
     rc_run<0, 3, S_UP, KB>(tmem_base, a_lo, w_lo0, kbn);
   }
   tc_commit(bars + 8u * (RC_NS + POS));              // in_empty[POS]
-  tc_commit(bars + 8u * (2 * RC_NS + S_DN));         // acc_full[S_DN]: output row g - 1 is complete
+  if (ISS == 2) tc_commit(bars + 8u * (2 * RC_NS + S_MID));   // acc_full[S_MID]: this issuer's share of output row g
+  tc_commit(bars + 8u * (2 * RC_NS + S_DN));         // acc_full[S_DN]: the last contribution to output row g - 1
   return nxt;
 }
 
-template <int KB>
+// ISS = 2: issuer `who` (0 / 1) takes the input rows with g % 2 == who; ISS = 1: one issuer (who = 0) takes all rows
+template <int KB, int ISS>
 __device__ __forceinline__ void rc_conv_issuer(const RcParams& p, uint32_t tmem_base, uint32_t a_base, uint32_t w_lo0,
-                                               uint32_t bars) {
+                                               uint32_t bars, int who) {
   const uint32_t a_step = (uint32_t)(p.row_bytes >> 4);
   const int kbn = p.kb, H = p.H;
   const uint32_t in_full = bars, in_empty = bars + 8u * RC_NS, acc_full = bars + 16u * RC_NS, acc_empty = bars + 24u * RC_NS;
-  int g = 0;                                 // running row index of this CTA: slot ring and stage ring position
-  for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
-    for (int Y = 0; Y < H; ++Y, ++g) {
+  int g0 = 0;                                // running index of the strip's first row: slot ring and stage ring position
+  for (long long item = blockIdx.x; item < p.items; item += gridDim.x, g0 += H) {
+    for (int Y = (ISS == 2) ? ((g0 ^ who) & 1) : 0; Y < H; Y += ISS) {
+      const int g = g0 + Y;
       const int pos = g & (RC_NS - 1);
       const uint32_t ph = (uint32_t)((g >> 3) & 1);
       const uint32_t a_lo = a_base + (uint32_t)pos * a_step;
       if (Y >= 1 && Y + 1 < H) {
-        if (pos == 0 && Y + RC_NS < H) {       // eight interior rows in a row: straight-line code, probes one row ahead
-          uint32_t a = a_lo, pre = 0;
-          pre = rc_fast_row<0, KB, true>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
-          pre = rc_fast_row<1, KB, true>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
-          pre = rc_fast_row<2, KB, true>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
-          pre = rc_fast_row<3, KB, true>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
-          pre = rc_fast_row<4, KB, true>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
-          pre = rc_fast_row<5, KB, true>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
-          pre = rc_fast_row<6, KB, true>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
-          rc_fast_row<7, KB, false>(tmem_base, a, w_lo0, kbn, bars, ph, pre);
-          Y += RC_NS - 1;
-          g += RC_NS - 1;
+        if (pos == who && Y + RC_NS < H) {     // this issuer's four rows of an aligned group of eight, all interior:
+          uint32_t a = a_lo, pre = 0;          // straight-line code, barriers probed one row ahead
+          if (ISS == 1) {
+            pre = rc_fast_row<0, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
+            pre = rc_fast_row<1, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
+            pre = rc_fast_row<2, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
+            pre = rc_fast_row<3, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
+            pre = rc_fast_row<4, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
+            pre = rc_fast_row<5, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
+            pre = rc_fast_row<6, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
+            rc_fast_row<7, KB, false, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);
+          } else if (who == 0) {
+            pre = rc_fast_row<0, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += 2 * a_step;
+            pre = rc_fast_row<2, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += 2 * a_step;
+            pre = rc_fast_row<4, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += 2 * a_step;
+            rc_fast_row<6, KB, false, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);
+          } else {
+            pre = rc_fast_row<1, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += 2 * a_step;
+            pre = rc_fast_row<3, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += 2 * a_step;
+            pre = rc_fast_row<5, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += 2 * a_step;
+            rc_fast_row<7, KB, false, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);
+          }
+          Y += RC_NS - ISS;
           continue;
         }
         switch (pos) {
-          case 0: rc_fast_row<0, KB, false>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
-          case 1: rc_fast_row<1, KB, false>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
-          case 2: rc_fast_row<2, KB, false>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
-          case 3: rc_fast_row<3, KB, false>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
-          case 4: rc_fast_row<4, KB, false>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
-          case 5: rc_fast_row<5, KB, false>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
-          case 6: rc_fast_row<6, KB, false>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
-          default: rc_fast_row<7, KB, false>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
+          case 0: rc_fast_row<0, KB, false, ISS>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
+          case 1: rc_fast_row<1, KB, false, ISS>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
+          case 2: rc_fast_row<2, KB, false, ISS>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
+          case 3: rc_fast_row<3, KB, false, ISS>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
+          case 4: rc_fast_row<4, KB, false, ISS>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
+          case 5: rc_fast_row<5, KB, false, ISS>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
+          case 6: rc_fast_row<6, KB, false, ISS>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
+          default: rc_fast_row<7, KB, false, ISS>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
         }
         continue;
       }
@@ -256,8 +277,9 @@ __device__ __forceinline__ void rc_conv_issuer(const RcParams& p, uint32_t tmem_
       const int b0 = max(brk, kh_lo);
       if (b0 <= kh_hi) issue(b0, kh_hi - b0 + 1);
       tc_commit(in_empty + 8u * pos);
-      if (Y >= 1) tc_commit(acc_full + 8u * rc_slot(g - 1));
-      if (Y == H - 1) tc_commit(acc_full + 8u * rc_slot(g));
+      if (ISS == 2) tc_commit(acc_full + 8u * rc_slot(g));         // this issuer's share of output row g
+      if (Y >= 1) tc_commit(acc_full + 8u * rc_slot(g - 1));       // last contribution to output row g - 1
+      if (Y == H - 1) tc_commit(acc_full + 8u * rc_slot(g));       // no input row below: the last arrival comes from here
     }
   }
 }
@@ -270,7 +292,8 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NTHREADS = FUSE ? RC_THREADS_FUSED : RC_THREADS_PLAIN;
-  constexpr int W_L4 = 2 + RC_EPI_WARPS;            // predictor MMA warp
+  constexpr int W_EPI = 2;                          // first epilogue warp
+  constexpr int W_L4 = W_EPI + RC_EPI_WARPS;        // predictor MMA warp
   constexpr int W_SOFT = W_L4 + 1;                  // first soft-argmax warp
 
   unsigned char* s_w = smem;                                                    // kb * 3 * RC_WBLK
@@ -323,10 +346,10 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
   const uint32_t tmem_base = *s_tmem;
   // the slot ring starts out holding the bias: the first four epilogue warps initialise their lane quadrants
   uint32_t bz[32];
-  if (warp >= 2 && warp < 2 + RC_EPI_WARPS) {
+  if (warp >= W_EPI && warp < W_EPI + RC_EPI_WARPS) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) bz[i] = __float_as_uint(p.bias[i]);
-    if (warp < 6) {
+    if (warp < W_EPI + 4) {
       const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll
       for (int s = 0; s < RC_NS; ++s) tmem_st32(t_row + (uint32_t)(s * RC_CO), bz);
@@ -376,8 +399,8 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== conv MMA issuer =====================
+  } else if (warp < W_EPI) {
+    // ===================== conv MMA issuers (warps 1, 2; the plain kernel issues from warp 1 alone) =====================
     if (elect_one()) {
       mbar_wait(smem_u32(w_bar), 0, nullptr);
       // descriptors: K-major, no swizzle; LBO = chunk stride, SBO = stride of 8-row groups (128 B: rows are contiguous)
@@ -386,14 +409,14 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
       const uint32_t w_lo0 = ((smem_u32(s_w) >> 4) & 0x3FFF) | B_LBO;
       const uint32_t a_base = ((smem_u32(s_in) >> 4) & 0x3FFF) | A_LBO;
       if (p.kb == 2)
-        rc_conv_issuer<2>(p, tmem_base, a_base, w_lo0, smem_u32(in_full));
+        rc_conv_issuer<2, 1>(p, tmem_base, a_base, w_lo0, smem_u32(in_full), warp - 1);
       else
-        rc_conv_issuer<0>(p, tmem_base, a_base, w_lo0, smem_u32(in_full));
+        rc_conv_issuer<0, 1>(p, tmem_base, a_base, w_lo0, smem_u32(in_full), warp - 1);
     }
-  } else if (warp < 2 + RC_EPI_WARPS) {
+  } else if (warp < W_EPI + RC_EPI_WARPS) {
     // ===================== conv epilogue: 2 sets x 4 warps; warp w owns TMEM lanes 32 (w % 4) .. +31 = pixels; set k
     // takes the rows with g % 2 == k =====================
-    const int q = warp & 3, set = (warp - 2) >> 2;
+    const int q = warp & 3, set = (warp - W_EPI) >> 2;
     const int m = q * 32 + lane;                    // pixel of the window row (window starts at xs0 - 1: lane = x - xs0)
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
     int g0 = 0;                                     // running index of the strip's first row

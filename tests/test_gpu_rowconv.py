@@ -114,6 +114,10 @@ def test_rowconv_pred_softargmax(ops, cin, cpred, H, W, N):
     got = got.cpu().numpy()
     assert got.shape == (N, cpred, 2)
     np.testing.assert_allclose(got, ref, rtol=0, atol=2e-2)
+    # two MMA-issuing warps accumulate into the same TMEM slots: the result must not depend on how their MMAs interleave
+    for _ in range(3):
+        again = ops.tc_rowconv3x3_pred_softargmax(a, packed, _bias32(b), 32, True, ppacked, pb.cuda(), cpred).cpu().numpy()
+        assert np.array_equal(again, got)
     # the unfused launches (tile conv -> predictor + soft-argmax kernel)
     packed_t = ops.tc_pack_weights(w.cuda(), [cin])
     yt = ops.tc_conv3x3([a], packed_t, _bias32(b), 32, True)
