@@ -55,8 +55,8 @@ def load_peaks():
 
 def load_traffic(kernel, agents):
     """Average DRAM bytes per launch of `kernel` from the committed ncu pass of this command
-    (profiles/ncu_traffic_r01.json, tools/ncu_traffic.py); None when the capture was made at another batch size."""
-    p = os.path.join(ROOT, 'profiles', 'ncu_traffic_r01.json')
+    (profiles/ncu_traffic_r02.json, tools/ncu_traffic.py); None when the capture was made at another batch size."""
+    p = os.path.join(ROOT, 'profiles', 'ncu_traffic_r02.json')
     if not os.path.exists(p):
         return None
     d = json.load(open(p))
@@ -258,6 +258,137 @@ def run_reference(args, cfg, rank, world):
     }))
 
 
+def _scene_loader(cfg, n_agents, seed=10):
+    """One synthetic scene of n_agents agents as the drop-in SceneDataset / DataLoader pair evaluate() and train_epoch()
+    take (dataloader.py:8-50)."""
+    import pandas as pd
+    from torch.utils.data import DataLoader
+    from motion_style_transfer_b200 import synthetic as S
+    from motion_style_transfer_b200.utils.dataloader import SceneDataset, scene_collate
+    total = cfg['obs'] + cfg['pred']
+    tr = S.synthetic_tracks(n_agents, total, H, W, seed=seed).numpy() / cfg['resize']
+    df = pd.DataFrame({'frame': np.tile(np.arange(total), n_agents), 'trackId': np.repeat(np.arange(n_agents), total),
+                       'x': tr[:, :, 0].reshape(-1), 'y': tr[:, :, 1].reshape(-1), 'sceneId': 's0',
+                       'metaId': np.repeat(np.arange(n_agents), total)})
+    ds = SceneDataset(df, resize=cfg['resize'], total_len=total)
+    return DataLoader(ds, batch_size=1, collate_fn=scene_collate), {'s0': S.synthetic_scene(H, W, seed=0)}
+
+
+def _dist_max(ms, world, dev):
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+def run_evaluate_mode(args, cfg, rank, world, dev):
+    """--mode evaluate: ONE scene of --agents agents through the reference-named drop-in utils/evaluate.py::evaluate()
+    (23-argument signature, DataLoader, host RNG semantics).  Under torchrun the agents of the scene are sharded over the
+    ranks (parallel.shard_bounds) and the per-agent rows are gathered at the end of the scene (parallel.gather_rows, NCCL)
+    INSIDE the timed region: strong scaling of one fixed job."""
+    import torch.distributed as dist
+    from motion_style_transfer_b200.utils.evaluate import evaluate
+    from motion_style_transfer_b200.utils.image_utils import create_dist_mat
+    model = build_model_state(cfg).to(dev).eval().set_backend(args.backend)
+    loader, images = _scene_loader(cfg, args.agents)
+    tmpl = torch.Tensor(create_dist_mat(size=int(4200 * cfg['resize'])))
+    bs = args.chunk_agents if args.chunk_agents > 0 else 128
+
+    def call():
+        return evaluate(model, loader, images, dev, 'sdd', None, tmpl, cfg['wps'], 'test', cfg['n_goal'], cfg['n_traj'],
+                        cfg['obs'], bs, cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'], cfg['cwsp'])
+
+    for _ in range(max(1, args.warmup)):
+        torch.manual_seed(1)
+        np.random.seed(2)
+        call()
+    times, res = [], None
+    for it in range(args.steps):
+        torch.manual_seed(100 + it)
+        np.random.seed(200 + it)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = call()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(_dist_max(e0.elapsed_time(e1), world, dev))
+    ms = sum(times) / len(times)
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'agent-trajectories/sec (sharded evaluate() drop-in, one scene, rows gathered)', 'mode': 'evaluate',
+            'value': args.agents * cfg['n_goal'] * cfg['n_traj'] / (ms / 1000), 'unit': 'agent-trajectories/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': model.engine.backend_dtype(), 'data': 'synthetic',
+            'config': {'workload': workload_name(args, cfg), 'agents_per_scene': args.agents, 'batch_size': bs,
+                       'agents_per_rank': -(-args.agents // world), 'collective': 'all_gather of (ade, fde) rows per scene'},
+            'ade': float(res[0]), 'fde': float(res[1]), 'step_ms': times}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_finetune_mode(args, cfg, rank, world, dev):
+    """--mode finetune: optimiser steps of the drop-in utils/train_epoch.py::train_epoch (BASELINE configs 2 / 4):
+    rasterise -> encoder -> goal + trajectory decoders -> 2 x BCEWithLogits x 1000 -> backward -> FusedAdam, batches of
+    --chunk-agents (default 10, scripts/*/tune_mosa*.sh) agents; under torchrun the agents of every batch are sharded over
+    the ranks and the flattened adapter gradient is summed with ONE NCCL all-reduce per step (parallel.allreduce_flat)."""
+    import torch.distributed as dist
+    from motion_style_transfer_b200 import parallel
+    from motion_style_transfer_b200.autograd_engine import BCEWithLogitsLoss
+    from motion_style_transfer_b200.models.trainer import FusedAdam, apply_freeze_policy
+    from motion_style_transfer_b200.utils.image_utils import create_dist_mat, create_gaussian_heatmap_template
+    from motion_style_transfer_b200.utils.train_epoch import train_epoch
+    model = build_model_state(cfg).to(dev)
+    net = cfg.get('network', 'original')
+    pos = cfg.get('position', [0, 1, 2, 3, 4])
+    apply_freeze_policy(model, 'mosa_1', pos, net)
+    trainable = [q for q in model.parameters() if q.requires_grad]
+    parallel.broadcast_params(trainable)
+    opt = FusedAdam(model.parameters(), lr=0.003)
+    crit = BCEWithLogitsLoss()
+    bs = args.chunk_agents if args.chunk_agents > 0 else 10
+    n_batches = max(1, args.agents // bs)
+    loader, images = _scene_loader(cfg, n_batches * bs, seed=20)
+    size = int(4200 * cfg['resize'])
+    tmpl = torch.Tensor(create_dist_mat(size=size)).to(dev)
+    gt_tmpl = torch.Tensor(create_gaussian_heatmap_template(size=size, kernlen=31, nsig=4, normalize=False)).to(dev)
+
+    def epoch(e):
+        return train_epoch(model, loader, images, opt, crit, 1000, dev, 'sdd', None, gt_tmpl, tmpl, cfg['wps'], e, cfg['obs'],
+                           cfg['pred'], bs, 10000, cfg['resize'], net if net != 'original' else None)
+
+    for e in range(max(1, args.warmup)):
+        epoch(e)
+    times, out = [], None
+    for it in range(args.steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = epoch(100 + it)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(_dist_max(e0.elapsed_time(e1), world, dev) / n_batches)
+    ms = sum(times) / len(times)
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'fine-tune optimiser steps/sec (train_epoch drop-in, MoSA r=1 adapters)', 'mode': 'finetune',
+            'value': 1000.0 / ms, 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': workload_name(args, cfg).replace(' eval,', ' fine-tune,'), 'agents_per_step': bs,
+                       'steps_per_epoch': n_batches, 'trainable_floats': int(sum(q.numel() for q in trainable)),
+                       'collective': 'one all-reduce of the flattened adapter gradient per step'},
+            'train_ade': out[0], 'train_fde': out[1], 'train_loss': out[2], 'step_ms': times}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def workload_name(args, cfg):
     net = 'Y-Net-Mod+MoSA(mosa_1, scene/motion/fusion branches)' if cfg.get('network') == 'fusion' else \
         'Y-Net+MoSA(mosa_1, encoder stages 0-4)'
@@ -274,6 +405,12 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='ind_long_ttst_cws', choices=sorted(WORKLOADS))
     ap.add_argument('--agents', type=int, default=128, help='agents per GPU per step')
+    ap.add_argument('--chunk-agents', type=int, default=0,
+                    help='agents per captured graph replay (0 = all of --agents in one replay); the throughput sweep runs '
+                         '--agents 1024 ... 65536 in chunks of 128')
+    ap.add_argument('--mode', default='forecast', choices=['forecast', 'evaluate', 'finetune'],
+                    help='forecast = the evaluate() batch body (driver default); evaluate = one scene of --agents agents '
+                         'through the sharded drop-in evaluate() (strong scaling); finetune = train_epoch optimiser steps')
     ap.add_argument('--ref-agents', type=int, default=2, help='agents per step of the CPU reference arm')
     ap.add_argument('--cpu-agents', type=int, default=4, help='agents of the bounded cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -305,6 +442,10 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
     _lib.load()
+    if args.mode == 'evaluate':
+        return run_evaluate_mode(args, cfg, rank, world, dev)
+    if args.mode == 'finetune':
+        return run_finetune_mode(args, cfg, rank, world, dev)
 
     model = build_model_state(cfg).to(dev).eval().set_backend(args.backend)
     from motion_style_transfer_b200 import synthetic as O      # synthetic-input generators (the product never imports oracle)
@@ -318,22 +459,39 @@ def main():
     scene_dev = scene_host.to(dev)
     rng = DeviceRng(seed=1234 + rank)
     launches_per_step = None
+    C = args.chunk_agents if args.chunk_agents > 0 else B
+    assert B % C == 0, '--agents must be a multiple of --chunk-agents'
+    n_chunks = B // C
+    ade_all = torch.empty(B, dtype=torch.float32, device=dev)
+    fde_all = torch.empty(B, dtype=torch.float32, device=dev)
+
+    def chunked(fn):
+        """One step = all B agents, C at a time through `fn` (whose outputs are overwritten by the next replay)."""
+        if n_chunks == 1:
+            return fn
+        def run(scene, traj):
+            for c in range(n_chunks):
+                r = fn(scene, traj[c * C:(c + 1) * C])
+                ade_all[c * C:(c + 1) * C].copy_(r['ade'])
+                fde_all[c * C:(c + 1) * C].copy_(r['fde'])
+            return dict(ade=ade_all, fde=fde_all)
+        return run
+
     if args.graph:
         # the ~450 launches of one batch are captured once and replayed (utils/evaluate.py::GraphedForecaster)
         from motion_style_transfer_b200.utils.evaluate import GraphedForecaster
-        gf = GraphedForecaster(model, tmpl, tuple(scene_dev.shape), tuple(traj_dev[0].shape), cfg['wps'], cfg['n_goal'],
+        gf = GraphedForecaster(model, tmpl, tuple(scene_dev.shape), (C,) + tuple(traj_dev[0].shape[1:]), cfg['wps'], cfg['n_goal'],
                                cfg['n_traj'], cfg['obs'], cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'],
                                cfg['cwsp'], seed=1234 + rank)
         l0 = ops.launch_count
-        gf.capture(scene_dev, traj_dev[0])
-        launches_per_step = (ops.launch_count - l0) // 3          # 2 eager warm-ups + the captured pass
+        gf.capture(scene_dev, traj_dev[0][:C])
+        launches_per_step = (ops.launch_count - l0) // 3 * n_chunks      # 2 eager warm-ups + the captured pass, per chunk
 
-        def step(scene, traj):
-            return gf(scene, traj)
+        step = chunked(lambda scene, traj: gf(scene, traj))
     else:
-        def step(scene, traj):
-            return forecast_batch(model, scene, traj, tmpl, cfg['wps'], cfg['n_goal'], cfg['n_traj'], cfg['obs'],
-                                  cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'], cfg['cwsp'], rng=rng)
+        step = chunked(lambda scene, traj: forecast_batch(
+            model, scene, traj, tmpl, cfg['wps'], cfg['n_goal'], cfg['n_traj'], cfg['obs'], cfg['resize'], cfg['T'],
+            cfg['ttst'], cfg['cws'], cfg['thr'], cfg['cwsp'], rng=rng))
 
     def barrier():
         if world > 1:
@@ -410,7 +568,7 @@ def main():
     roofline, layer_table, kernel_table = None, None, []
     if rank == 0 and not args.no_roofline:
         peaks = load_peaks()
-        _eager = lambda: forecast_batch(model, scene_dev, traj_dev[-1], tmpl, cfg['wps'], cfg['n_goal'], cfg['n_traj'],
+        _eager = lambda: forecast_batch(model, scene_dev, traj_dev[-1][:C], tmpl, cfg['wps'], cfg['n_goal'], cfg['n_traj'],
                                         cfg['obs'], cfg['resize'], cfg['T'], cfg['ttst'], cfg['cws'], cfg['thr'],
                                         cfg['cwsp'], rng=rng)
         _eager()                  # re-warm the eager allocator pool (graph capture emptied the cache)
@@ -438,20 +596,24 @@ def main():
                 k['n'] += 1
             top_name, top = max(by_kernel.items(), key=lambda kv: kv[1]['ms'])
             step_ms = sum(p['ms'] for p in prof)
-            if top['flops'] > 0:
-                ach = top['flops'] / (top['ms'] / 1000) / 1e12
-                roofline = dict(bound='tensor', kernel=top_name, achieved=ach, peak=peaks['bf16_tflops'],
-                                unit='TFLOP/s', frac=ach / peaks['bf16_tflops'], traffic=load_traffic(top_name, B),
-                                algorithmic_bytes_per_launch=top['bytes'] / top['n'],
-                                hbm_gbs=top['bytes'] / (top['ms'] / 1000) / 1e9, hbm_peak_gbs=peaks['hbm_gbs'],
-                                launches=top['n'], avg_launch_ms=top['ms'] / top['n'],
-                                share_of_step=top['ms'] / step_ms, peak_source=peaks['src'] + ' (burst bf16 cuBLAS)')
+            # which roof bounds the dominant kernel: its arithmetic intensity (executed flops / algorithmic bytes) against the
+            # ridge of the MEASURED peaks.  Below the ridge the kernel cannot exceed AI x HBM bandwidth: it is judged against
+            # the HBM copy bandwidth; above it against the bf16 tensor peak.  Both fractions are reported.
+            ridge = peaks['bf16_tflops'] * 1e12 / (peaks['hbm_gbs'] * 1e9)
+            ai = top['flops'] / top['bytes'] if top['bytes'] > 0 else float('inf')
+            tf = top['flops'] / (top['ms'] / 1000) / 1e12
+            gbs = top['bytes'] / (top['ms'] / 1000) / 1e9
+            common = dict(kernel=top_name, traffic=load_traffic(top_name, C), algorithmic_bytes_per_launch=top['bytes'] / top['n'],
+                          flops_per_launch=top['flops'] / top['n'], arithmetic_intensity=ai, ridge_flop_per_byte=ridge,
+                          tensor_tflops=tf, tensor_frac=tf / peaks['bf16_tflops'], hbm_gbs=gbs,
+                          hbm_frac=gbs / peaks['hbm_gbs'], launches=top['n'], avg_launch_ms=top['ms'] / top['n'],
+                          share_of_step=top['ms'] / step_ms)
+            if top['flops'] > 0 and ai >= ridge:
+                roofline = dict(bound='tensor', achieved=tf, peak=peaks['bf16_tflops'], unit='TFLOP/s',
+                                frac=tf / peaks['bf16_tflops'], peak_source=peaks['src'] + ' (burst bf16 cuBLAS)', **common)
             else:
-                ach = top['bytes'] / (top['ms'] / 1000) / 1e9
-                roofline = dict(bound='hbm', kernel=top_name, achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s',
-                                frac=ach / peaks['hbm_gbs'], traffic=load_traffic(top_name, B), launches=top['n'],
-                                avg_launch_ms=top['ms'] / top['n'], share_of_step=top['ms'] / step_ms,
-                                peak_source=peaks['src'])
+                roofline = dict(bound='hbm', achieved=gbs, peak=peaks['hbm_gbs'], unit='GB/s', frac=gbs / peaks['hbm_gbs'],
+                                peak_source=peaks['src'] + ' (copy bandwidth)', **common)
         if prof:
             # every kernel class of the step against its own roofline: convs vs the tensor peak, the
             # rasterise / soft-argmax / sampling / CWS kernels vs the measured HBM copy bandwidth (algorithmic bytes)
@@ -514,7 +676,8 @@ def main():
             'metric': 'agent-trajectories/sec', 'value': value, 'unit': 'agent-trajectories/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': model.engine.backend_dtype(), 'data': 'synthetic',
-            'config': {'workload': workload_name(args, cfg), 'agents_per_gpu_per_step': B, 'cuda_graph': bool(args.graph),
+            'config': {'workload': workload_name(args, cfg), 'agents_per_gpu_per_step': B, 'agents_per_graph_replay': C,
+                       'cuda_graph': bool(args.graph),
                        'global_agents_per_step': world * B, 'parallelism': f'dp{world} (agents sharded, no collective)',
                        'l2': 'inputs + activations per step >> 126 MB L2 (fresh synthetic tracks every step)',
                        'gflop_per_agent_reference_executed': GF_PER_AGENT[args.workload]},

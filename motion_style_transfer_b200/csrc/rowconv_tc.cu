@@ -33,6 +33,7 @@
 // tcgen05.st) of one row overlaps the next row's.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -45,7 +46,10 @@ constexpr int RC_VW = 126;                      // valid output pixels per strip
 constexpr int RC_CHUNK_BYTES = RC_M * 16;       // one 8-channel chunk of a window row
 constexpr int RC_CO = 32;                       // output channels = columns per TMEM slot
 constexpr int RC_NS = 8;                        // TMEM slot ring (256 columns)
-constexpr int RC_STAGES = 8;                    // input-row ring (= RC_NS: ring positions of a row are compile-time)
+constexpr int RC_STAGES_PLAIN = 8;              // input-row ring: two co-resident CTAs per SM keep 16 rows (128 KB) in flight
+constexpr int RC_STAGES_FUSED = 16;             // one CTA per SM: with 8 rows in flight the fused kernel was bound by the TMA
+                                                // round trip (~2 us under load / 7 free stages = 580 cycles per row, even with
+                                                // all math stripped: YNET_RC_DBG=7); 16 rows = 128 KB in flight per SM
 constexpr int RC_NY = 4;                        // conv-output row ring (fused tail)
 constexpr int RC_MAX_KB = 4;                    // <= 64 input channels
 constexpr int RC_WBLK = 2 * 96 * 16;            // weights of one (K block, kw): [2 chunks][96 = (kh, co)][8 ch] bf16
@@ -58,7 +62,8 @@ constexpr int RC_SOFT_WARPS = 16;               // two sets x 4 lane quadrants x
 // run.  One issuer keeps the kernel deterministic.)
 constexpr int RC_THREADS_PLAIN = 32 * (2 + RC_EPI_WARPS);        // TMA, MMA, epilogue warps
 constexpr int RC_THREADS_FUSED = 32 * (2 + RC_EPI_WARPS + 1 + RC_SOFT_WARPS);   // TMA, MMA, epilogue, predictor MMA, soft-argmax
-constexpr uint32_t RC_PACC = 256;               // first TMEM column of the two predictor accumulators (2 x 128)
+constexpr uint32_t RC_PACC = 256;               // first TMEM column of the two predictor accumulators (2 x 128).  (Four 64-pixel
+                                                // accumulators were tried to shorten the soft-argmax -> MMA hand-off: no gain.)
 
 struct RcParams {
   int N, H, W, kb, chunks, strips;
@@ -82,6 +87,8 @@ struct RcParams {
   float4* partial;             // (m, s, sx, sy) [(n * c_pred + c) * slots + strip * RC_SOFT_WARPS + warp]
   int c_pred, pn_pad, slots;
   int kbp;                     // predictor K blocks = ceil(C_out / 16) (1 or 2)
+  int dbg;                     // profiling aid (YNET_RC_DBG): 1 = soft-argmax warps skip the math, 2 = conv epilogue skips the
+                               // conversion + shared-memory stores, 4 = one conv MMA per row instead of 3 * kb (results are garbage)
 };
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -163,24 +170,30 @@ __device__ __forceinline__ void rc_run(uint32_t tmem_base, uint32_t a_lo, uint32
 // acc_full counts two arrivals.
 // pre: bit 0 = acc_empty of this row already seen complete, bit 1 = in_full (probed while this issuer's previous row was
 // issued); returns the same two bits for row g + 2 (probed before this row's MMAs are issued) when PROBE, else 0.
-template <int POS, int KB, bool PROBE, int ISS>
-__device__ __forceinline__ uint32_t rc_fast_row(uint32_t tmem_base, uint32_t a_lo, uint32_t w_lo0, int kbn, uint32_t bars,
-                                                uint32_t ph, uint32_t pre) {
+template <int POS, int KB, bool PROBE, int ISS, int NSTG>
+__device__ __forceinline__ uint32_t rc_fast_row(uint32_t tmem_base, uint32_t a_base, uint32_t a_step, uint32_t w_lo0, int kbn,
+                                                uint32_t bars, int g, uint32_t pre) {
   constexpr int S_UP = RC_NS - 1 - ((POS + 1) & (RC_NS - 1));      // slot of output row g + 1 (first written here)
   constexpr int S_MID = RC_NS - 1 - POS;
   constexpr int S_DN = RC_NS - 1 - ((POS + RC_NS - 1) & (RC_NS - 1));   // slot of output row g - 1 (completed here)
+  const uint32_t abars = bars + 16u * NSTG;                       // acc_full[0]; acc_empty[0] = abars + 8 * RC_NS
+  const uint32_t ph = (uint32_t)((g >> 3) & 1);                    // slot-ring turn of row g
+  const int stage = g & (NSTG - 1);
+  const uint32_t ph_in = (uint32_t)((g / NSTG) & 1);
   if (!(pre & 1u))
-    mbar_wait(bars + 8u * (3 * RC_NS + S_UP), (POS == RC_NS - 1) ? ph : (ph ^ 1u), nullptr);   // acc_empty[S_UP], use (g + 1) / 8
-  if (!(pre & 2u)) mbar_wait(bars + 8u * POS, ph, nullptr);                                    // in_full[POS]
+    mbar_wait(abars + 8u * (RC_NS + S_UP), (POS == RC_NS - 1) ? ph : (ph ^ 1u), nullptr);   // acc_empty[S_UP], use (g + 1) / 8
+  if (!(pre & 2u)) mbar_wait(bars + 8u * (uint32_t)stage, ph_in, nullptr);                   // in_full[stage]
   tc_fence_after();
   uint32_t nxt = 0;
   if (PROBE) {
     constexpr int NP = (POS + ISS) & (RC_NS - 1);
     constexpr int S_UPN = RC_NS - 1 - ((NP + 1) & (RC_NS - 1));
     const uint32_t phn = (POS >= RC_NS - ISS) ? (ph ^ 1u) : ph;
-    nxt = mbar_test(bars + 8u * (3 * RC_NS + S_UPN), (NP == RC_NS - 1) ? phn : (phn ^ 1u)) |
-          (mbar_test(bars + 8u * NP, phn) << 1);
+    const int gn = g + ISS;
+    nxt = mbar_test(abars + 8u * (RC_NS + S_UPN), (NP == RC_NS - 1) ? phn : (phn ^ 1u)) |
+          (mbar_test(bars + 8u * (uint32_t)(gn & (NSTG - 1)), (uint32_t)((gn / NSTG) & 1)) << 1);
   }
+  const uint32_t a_lo = a_base + (uint32_t)stage * a_step;
   if (POS == RC_NS - 1) {          // the ring wraps between rows g + 1 and g
     rc_run<0, 1, S_UP, KB>(tmem_base, a_lo, w_lo0, kbn);
     rc_run<1, 2, S_MID, KB>(tmem_base, a_lo, w_lo0, kbn);
@@ -190,61 +203,63 @@ __device__ __forceinline__ uint32_t rc_fast_row(uint32_t tmem_base, uint32_t a_l
   } else {
     rc_run<0, 3, S_UP, KB>(tmem_base, a_lo, w_lo0, kbn);
   }
-  tc_commit(bars + 8u * (RC_NS + POS));              // in_empty[POS]
-  if (ISS == 2) tc_commit(bars + 8u * (2 * RC_NS + S_MID));   // acc_full[S_MID]: this issuer's share of output row g
-  tc_commit(bars + 8u * (2 * RC_NS + S_DN));         // acc_full[S_DN]: the last contribution to output row g - 1
+  tc_commit(bars + 8u * (uint32_t)(NSTG + stage));   // in_empty[stage]
+  if (ISS == 2) tc_commit(abars + 8u * S_MID);       // acc_full[S_MID]: this issuer's share of output row g
+  tc_commit(abars + 8u * S_DN);                      // acc_full[S_DN]: the last contribution to output row g - 1
   return nxt;
 }
 
 // ISS = 2: issuer `who` (0 / 1) takes the input rows with g % 2 == who; ISS = 1: one issuer (who = 0) takes all rows
-template <int KB, int ISS>
+template <int KB, int ISS, int NSTG>
 __device__ __forceinline__ void rc_conv_issuer(const RcParams& p, uint32_t tmem_base, uint32_t a_base, uint32_t w_lo0,
                                                uint32_t bars, int who) {
   const uint32_t a_step = (uint32_t)(p.row_bytes >> 4);
-  const int kbn = p.kb, H = p.H;
-  const uint32_t in_full = bars, in_empty = bars + 8u * RC_NS, acc_full = bars + 16u * RC_NS, acc_empty = bars + 24u * RC_NS;
+  const int kbn = (p.dbg & 4) ? 1 : p.kb, H = p.H;
+  const uint32_t in_full = bars, in_empty = bars + 8u * NSTG, acc_full = bars + 16u * NSTG, acc_empty = acc_full + 8u * RC_NS;
   int g0 = 0;                                // running index of the strip's first row: slot ring and stage ring position
   for (long long item = blockIdx.x; item < p.items; item += gridDim.x, g0 += H) {
     for (int Y = (ISS == 2) ? ((g0 ^ who) & 1) : 0; Y < H; Y += ISS) {
       const int g = g0 + Y;
       const int pos = g & (RC_NS - 1);
       const uint32_t ph = (uint32_t)((g >> 3) & 1);
-      const uint32_t a_lo = a_base + (uint32_t)pos * a_step;
+      const int stage = g & (NSTG - 1);
+      const uint32_t ph_in = (uint32_t)((g / NSTG) & 1);
+      const uint32_t a_lo = a_base + (uint32_t)stage * a_step;
       if (Y >= 1 && Y + 1 < H) {
-        if (pos == who && Y + RC_NS < H) {     // this issuer's four rows of an aligned group of eight, all interior:
-          uint32_t a = a_lo, pre = 0;          // straight-line code, barriers probed one row ahead
+        if (pos == who && Y + RC_NS < H) {     // an aligned group of eight interior rows (this issuer's share of it):
+          uint32_t pre = 0;                    // straight-line code, barriers probed one row ahead
           if (ISS == 1) {
-            pre = rc_fast_row<0, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
-            pre = rc_fast_row<1, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
-            pre = rc_fast_row<2, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
-            pre = rc_fast_row<3, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
-            pre = rc_fast_row<4, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
-            pre = rc_fast_row<5, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
-            pre = rc_fast_row<6, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += a_step;
-            rc_fast_row<7, KB, false, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);
+            pre = rc_fast_row<0, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, pre);
+            pre = rc_fast_row<1, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 1, pre);
+            pre = rc_fast_row<2, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 2, pre);
+            pre = rc_fast_row<3, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 3, pre);
+            pre = rc_fast_row<4, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 4, pre);
+            pre = rc_fast_row<5, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 5, pre);
+            pre = rc_fast_row<6, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 6, pre);
+            rc_fast_row<7, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 7, pre);
           } else if (who == 0) {
-            pre = rc_fast_row<0, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += 2 * a_step;
-            pre = rc_fast_row<2, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += 2 * a_step;
-            pre = rc_fast_row<4, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += 2 * a_step;
-            rc_fast_row<6, KB, false, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);
+            pre = rc_fast_row<0, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, pre);
+            pre = rc_fast_row<2, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 2, pre);
+            pre = rc_fast_row<4, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 4, pre);
+            rc_fast_row<6, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 6, pre);
           } else {
-            pre = rc_fast_row<1, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += 2 * a_step;
-            pre = rc_fast_row<3, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += 2 * a_step;
-            pre = rc_fast_row<5, KB, true, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);  a += 2 * a_step;
-            rc_fast_row<7, KB, false, ISS>(tmem_base, a, w_lo0, kbn, bars, ph, pre);
+            pre = rc_fast_row<1, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, pre);
+            pre = rc_fast_row<3, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 2, pre);
+            pre = rc_fast_row<5, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 4, pre);
+            rc_fast_row<7, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 6, pre);
           }
           Y += RC_NS - ISS;
           continue;
         }
         switch (pos) {
-          case 0: rc_fast_row<0, KB, false, ISS>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
-          case 1: rc_fast_row<1, KB, false, ISS>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
-          case 2: rc_fast_row<2, KB, false, ISS>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
-          case 3: rc_fast_row<3, KB, false, ISS>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
-          case 4: rc_fast_row<4, KB, false, ISS>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
-          case 5: rc_fast_row<5, KB, false, ISS>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
-          case 6: rc_fast_row<6, KB, false, ISS>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
-          default: rc_fast_row<7, KB, false, ISS>(tmem_base, a_lo, w_lo0, kbn, bars, ph, 0u); break;
+          case 0: rc_fast_row<0, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+          case 1: rc_fast_row<1, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+          case 2: rc_fast_row<2, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+          case 3: rc_fast_row<3, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+          case 4: rc_fast_row<4, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+          case 5: rc_fast_row<5, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+          case 6: rc_fast_row<6, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+          default: rc_fast_row<7, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
         }
         continue;
       }
@@ -252,7 +267,7 @@ __device__ __forceinline__ void rc_conv_issuer(const RcParams& p, uint32_t tmem_
       // the slots this row writes FIRST must have been drained: row g + 1 (and row g at the top of a strip)
       if (Y == 0) mbar_wait(acc_empty + 8u * rc_slot(g), ph ^ 1u, nullptr);
       if (Y + 1 < H) mbar_wait(acc_empty + 8u * rc_slot(g + 1), (uint32_t)((((g + 1) >> 3) & 1) ^ 1), nullptr);
-      mbar_wait(in_full + 8u * pos, ph, nullptr);
+      mbar_wait(in_full + 8u * (uint32_t)stage, ph_in, nullptr);
       tc_fence_after();
       // kernel rows kh_lo..kh_hi contribute (output row g + 1 - kh must exist).  The slots of rows g + 1, g, g - 1 are
       // consecutive except where the ring wraps: after kh = 0 when g % 8 == 7, after kh = 1 when g % 8 == 0.
@@ -276,7 +291,7 @@ __device__ __forceinline__ void rc_conv_issuer(const RcParams& p, uint32_t tmem_
       if (a_end > kh_lo) issue(kh_lo, a_end - kh_lo);
       const int b0 = max(brk, kh_lo);
       if (b0 <= kh_hi) issue(b0, kh_hi - b0 + 1);
-      tc_commit(in_empty + 8u * pos);
+      tc_commit(in_empty + 8u * (uint32_t)stage);
       if (ISS == 2) tc_commit(acc_full + 8u * rc_slot(g));         // this issuer's share of output row g
       if (Y >= 1) tc_commit(acc_full + 8u * rc_slot(g - 1));       // last contribution to output row g - 1
       if (Y == H - 1) tc_commit(acc_full + 8u * rc_slot(g));       // no input row below: the last arrival comes from here
@@ -293,17 +308,18 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NTHREADS = FUSE ? RC_THREADS_FUSED : RC_THREADS_PLAIN;
   constexpr int W_EPI = 2;                          // first epilogue warp
+  constexpr int NSTG = FUSE ? RC_STAGES_FUSED : RC_STAGES_PLAIN;
   constexpr int W_L4 = W_EPI + RC_EPI_WARPS;        // predictor MMA warp
   constexpr int W_SOFT = W_L4 + 1;                  // first soft-argmax warp
 
   unsigned char* s_w = smem;                                                    // kb * 3 * RC_WBLK
   unsigned char* s_in = s_w + (size_t)p.kb * 3 * RC_WBLK;                       // RC_STAGES * row_bytes (+ 1 KB slack)
-  unsigned char* s_y = s_in + (size_t)RC_STAGES * p.row_bytes + 1024;           // fused: RC_NY * RC_YROW
+  unsigned char* s_y = s_in + (size_t)NSTG * p.row_bytes + 1024;           // fused: RC_NY * RC_YROW
   unsigned char* s_pw = s_y + (FUSE ? RC_NY * RC_YROW : 0);                     // fused: 2 * PR_WBLK_BYTES
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_pw + (FUSE ? 2 * PR_WBLK_BYTES : 0));
   uint64_t* in_full = bars;
-  uint64_t* in_empty = in_full + RC_STAGES;
-  uint64_t* acc_full = in_empty + RC_STAGES;
+  uint64_t* in_empty = in_full + NSTG;
+  uint64_t* acc_full = in_empty + NSTG;
   uint64_t* acc_empty = acc_full + RC_NS;
   uint64_t* y_full = acc_empty + RC_NS;
   uint64_t* y_empty = y_full + RC_NY;
@@ -314,7 +330,7 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
 
   if (FUSE) pred_stage_weights(s_pw, p.pw, p.kbp, p.pn_pad, threadIdx.x, NTHREADS);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < RC_STAGES; ++s) {
+    for (int s = 0; s < NSTG; ++s) {
       mbar_init(smem_u32(&in_full[s]), 1);
       mbar_init(smem_u32(&in_empty[s]), 1);
     }
@@ -357,7 +373,7 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
   }
   if (p.zero_fill) {     // K-padding chunk slots that no TMA transaction ever writes must read as zero
     uint4* z = reinterpret_cast<uint4*>(s_in);
-    for (int i = threadIdx.x; i < RC_STAGES * (p.row_bytes >> 4); i += NTHREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < NSTG * (p.row_bytes >> 4); i += NTHREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
@@ -392,7 +408,7 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
           tma_load_4d(dst + (uint32_t)(p.src_coff[0] * RC_CHUNK_BYTES), &map0, fb, c0, Y, 0, ns[0]);
           if (p.n_src > 1) tma_load_4d(dst + (uint32_t)(p.src_coff[1] * RC_CHUNK_BYTES), &map1, fb, c0, Y, 0, ns[1]);
           if (p.n_src > 2) tma_load_4d(dst + (uint32_t)(p.src_coff[2] * RC_CHUNK_BYTES), &map2, fb, c0, Y, 0, ns[2]);
-          if (++stage == RC_STAGES) {
+          if (++stage == NSTG) {
             stage = 0;
             phase ^= 1;
           }
@@ -408,10 +424,10 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
       constexpr uint32_t B_LBO = (uint32_t)((96 * 16) >> 4) << 16;
       const uint32_t w_lo0 = ((smem_u32(s_w) >> 4) & 0x3FFF) | B_LBO;
       const uint32_t a_base = ((smem_u32(s_in) >> 4) & 0x3FFF) | A_LBO;
-      if (p.kb == 2)
-        rc_conv_issuer<2, 1>(p, tmem_base, a_base, w_lo0, smem_u32(in_full), warp - 1);
+      if (p.kb == 2 && !(p.dbg & 4))
+        rc_conv_issuer<2, 1, NSTG>(p, tmem_base, a_base, w_lo0, smem_u32(in_full), warp - 1);
       else
-        rc_conv_issuer<0, 1>(p, tmem_base, a_base, w_lo0, smem_u32(in_full), warp - 1);
+        rc_conv_issuer<0, 1, NSTG>(p, tmem_base, a_base, w_lo0, smem_u32(in_full), warp - 1);
     }
   } else if (warp < W_EPI + RC_EPI_WARPS) {
     // ===================== conv epilogue: 2 sets x 4 warps; warp w owns TMEM lanes 32 (w % 4) .. +31 = pixels; set k
@@ -479,6 +495,13 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
           }
         }
         uint4 o[4];
+        if (FUSE && (p.dbg & 2)) {
+          const int b = g & (RC_NY - 1);
+          if (lane == 0) mbar_wait(smem_u32(&y_empty[b]), (uint32_t)(((g / RC_NY) & 1) ^ 1), nullptr);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&y_full[b]));
+          continue;
+        }
         if (p.relu) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -536,22 +559,30 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
       const uint32_t pb_lo = ((smem_u32(s_y) >> 4) & 0x3FFF) | P_LBO;
       const uint32_t yf = smem_u32(y_full), ye = smem_u32(y_empty), pf = smem_u32(p_full), pe = smem_u32(p_empty);
       const int kbpn = p.kbp;
-      int g = 0;
-      for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
-        for (int Y = 0; Y < p.H; ++Y, ++g) {
-          const uint32_t b = (uint32_t)(g & (RC_NY - 1)), a = (uint32_t)(g & 1);
-          mbar_wait(pe + 8u * a, (uint32_t)(((g >> 1) & 1) ^ 1), nullptr);
-          mbar_wait(yf + 8u * b, (uint32_t)((g / RC_NY) & 1), nullptr);
-          tc_fence_after();
-          const uint32_t d = tmem_base + RC_PACC + a * 128u;
-          const uint32_t bl = pb_lo + b * (uint32_t)(RC_YROW >> 4);
-          tc_mma_bf16(d, ((uint64_t)P_HI << 32) | pa_lo, ((uint64_t)P_HI << 32) | bl, IDESC_P, 0u);
-          if (kbpn > 1)
-            tc_mma_bf16(d, ((uint64_t)P_HI << 32) | (pa_lo + (uint32_t)(PR_WBLK_BYTES >> 4)),
-                        ((uint64_t)P_HI << 32) | (bl + (uint32_t)((2 * RC_M * 16) >> 4)), IDESC_P, 1u);
-          tc_commit(pf + 8u * a);
-          tc_commit(ye + 8u * b);
+      // One row: wait (unless the probe taken a row earlier already saw both barriers complete), probe the next row's
+      // barriers, issue, commit: the probes overlap the ~100-cycle barrier latency with the issue work.
+      uint32_t pre = 0;
+      long long total_rows = 0;
+      for (long long item = blockIdx.x; item < p.items; item += gridDim.x) total_rows += p.H;
+      for (long long gl = 0; gl < total_rows; ++gl) {
+        const int g = (int)gl;
+        const uint32_t b = (uint32_t)(g & (RC_NY - 1)), a = (uint32_t)(g & 1);
+        if (!(pre & 1u)) mbar_wait(pe + 8u * a, (uint32_t)(((g >> 1) & 1) ^ 1), nullptr);
+        if (!(pre & 2u)) mbar_wait(yf + 8u * b, (uint32_t)((g / RC_NY) & 1), nullptr);
+        tc_fence_after();
+        {
+          const int gn = g + 1;
+          pre = mbar_test(pe + 8u * (uint32_t)(gn & 1), (uint32_t)(((gn >> 1) & 1) ^ 1)) |
+                (mbar_test(yf + 8u * (uint32_t)(gn & (RC_NY - 1)), (uint32_t)((gn / RC_NY) & 1)) << 1);
         }
+        const uint32_t d = tmem_base + RC_PACC + a * 128u;
+        const uint32_t bl = pb_lo + b * (uint32_t)(RC_YROW >> 4);
+        tc_mma_bf16(d, ((uint64_t)P_HI << 32) | pa_lo, ((uint64_t)P_HI << 32) | bl, IDESC_P, 0u);
+        if (kbpn > 1)
+          tc_mma_bf16(d, ((uint64_t)P_HI << 32) | (pa_lo + (uint32_t)(PR_WBLK_BYTES >> 4)),
+                      ((uint64_t)P_HI << 32) | (bl + (uint32_t)((2 * RC_M * 16) >> 4)), IDESC_P, 1u);
+        tc_commit(pf + 8u * a);
+        tc_commit(ye + 8u * b);
       }
     }
   } else if (FUSE) {
@@ -582,6 +613,7 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(pe);      // the values are in registers: release the accumulator
+          if (p.dbg & 1) continue;
           if (full)
             softargmax_row16(st, v, bias, x0, Y);
           else
@@ -705,6 +737,7 @@ static int rc_launch(const char* who, bool fuse, const ynet_tc_src* srcs, int n_
     p.part_mod = partial->batch_mod;
     p.part_chunks = pc;
   }
+  if (const char* e = getenv("YNET_RC_DBG")) p.dbg = atoi(e);
   p.N = N;
   p.H = H;
   p.W = W;
@@ -713,8 +746,8 @@ static int rc_launch(const char* who, bool fuse, const ynet_tc_src* srcs, int n_
   p.strips = ceil_div(W, RC_VW);
   p.items = (long long)N * p.strips;
   p.row_bytes = p.chunks * RC_CHUNK_BYTES;
-  const size_t smem = (size_t)p.kb * 3 * RC_WBLK + (size_t)RC_STAGES * p.row_bytes + 1024 +
-                      (fuse ? (size_t)RC_NY * RC_YROW + 2 * PR_WBLK_BYTES : 0) + 64 * 8 + 16 + 1024;
+  const size_t smem = (size_t)p.kb * 3 * RC_WBLK + (size_t)(fuse ? RC_STAGES_FUSED : RC_STAGES_PLAIN) * p.row_bytes + 1024 +
+                      (fuse ? (size_t)RC_NY * RC_YROW + 2 * PR_WBLK_BYTES : 0) + 80 * 8 + 16 + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_rowconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -587,7 +587,7 @@ class YNetEngineTC(YNetEngine):
             x = self._tconv_hoisted(decoder.decoder[i][0], f'{key}.decoder.{i}.0', up, partials[i + 1], pyr_rev[i + 1],
                                     c_feats[i + 1])
             last = i == len(partials) - 2
-            if (last and softargmax and self._use_rowconv(decoder.decoder[i][2], [x])
+            if (last and softargmax and self._use_rowconv(decoder.decoder[i][2], [x]) and x.K_pad <= 32
                     and decoder.predictor.weight.shape[0] <= 32):
                 return self._conv_pred_softargmax_row(decoder.decoder[i][2], f'{key}.decoder.{i}.2', x, decoder.predictor,
                                                       f'{key}.predictor')
@@ -625,12 +625,14 @@ class YNetEngineTC(YNetEngine):
                 for lvl in range(min(self.im2col_levels, len(pyr))):
                     pyr[lvl] = ops.tc_rasterize_im2col(template, wp, nb * G, n_wp, H, W, lvl)
             if self.hoist:
-                feats_rev = [[c.batch_slice(b0, b1) for c in f] for f in feats][::-1]
+                # (a batch-1 feature is shared by all agents -- the scene branch of Y-Net-Mod, ynet.py:374-387 -- and stays whole)
+                feats_rev = [[c if c.data.shape[0] == 1 else c.batch_slice(b0, b1) for c in f] for f in feats][::-1]
                 partials = [q.repeat_interleave(G) for q in self._traj_partials(dec, 'traj_decoder', feats_rev)]
                 out = self._decoder_trunk_hoisted(dec, 'traj_decoder', partials, pyr[::-1],
                                                   [sum(c.C for c in f) for f in feats_rev], softargmax=True)
             else:
-                traj_input = [ChannelCat(tuple(c.batch_slice(b0, b1).repeat_interleave(G) for c in f) + (p,))
+                traj_input = [ChannelCat(tuple((c if c.data.shape[0] == 1 else c.batch_slice(b0, b1).repeat_interleave(G))
+                                               for c in f) + (p,))
                               for f, p in zip(feats, pyr)]
                 out = self.decoder_softargmax(dec, 'traj_decoder', traj_input)   # (nb*G, pred, 2)
             trajs[:, b0:b1] = out.view(nb, G, pred_len, 2).permute(1, 0, 2, 3)

@@ -3,7 +3,7 @@
 
     ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
         --profile-from-start off -c 600 --csv --log-file gpurun_out/traffic.csv python bench.py --steps 1 --warmup 3 ...
-    python tools/ncu_traffic.py gpurun_out/traffic.csv <agents per step> > profiles/ncu_traffic_r01.json
+    python tools/ncu_traffic.py gpurun_out/traffic.csv <agents per step> > profiles/ncu_traffic_r02.json
 
 bench.py reads the JSON for `roofline.traffic` (average DRAM bytes per launch of the dominant kernel).
 """
@@ -13,6 +13,8 @@ import re
 import sys
 
 LABELS = [   # ops.py timing label <- ncu kernel name
+    ('tc_rowconv_kernel<pred,softargmax>', r'tc_rowconv_kernel<\(bool\)1>|tc_rowconv_kernel<true>|tc_rowconv_kernel<1>'),
+    ('tc_rowconv_kernel', r'tc_rowconv_kernel<\(bool\)0>|tc_rowconv_kernel<false>|tc_rowconv_kernel<0>'),
     ('tc_conv3x3_kernel', r'tc_conv_kernel<\d, 9, 0>'),
     ('tc_conv3x3_hilo_kernel', r'tc_conv_kernel<\d, 9, 4>'),
     ('tc_upconv3x3_kernel', r'tc_conv_kernel<\d, 9, 3>|upconv_ringfix'),
