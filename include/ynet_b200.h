@@ -362,6 +362,23 @@ int ynet_tc_rowconv3x3_pred_softargmax(const ynet_tc_src* src_host, int32_t N, i
                                        float* out, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * scene-image preprocessing in front of the path (trainer.py:578-582), one launch per scene.
+ * ynet_scene_preprocess_u8: uint8 HWC (3 channels, as cv2.imread returns it) -> cv2.resize(fx = fy = f, INTER_AREA)
+ *     (utils/image_utils.py:85-92) -> zero pad at the bottom / right to (Hp, Wp) (95-107) -> smp normalisation
+ *     (x / 255 - mean) / std in float64 and HWC -> CHW float32 (66-82).  Bit-exact against OpenCV.  (dh, dw) =
+ *     cvRound(size * f); area tables = cv::computeResizeAreaTab for scale 1 / f as CSR arrays (device) -- or int_scale > 0
+ *     for an integer scale whose blocks fit (OpenCV's integer path).  out_chw (3, Hp, Wp) and / or out_u8_hwc (dh, dw, 3)
+ *     (the resized image alone: the reference-named resize()).
+ * ynet_scene_onehot_u8: segmentation masks: cv2.INTER_NEAREST -> zero pad -> one-hot float32 (classes, Hp, Wp).
+ * ------------------------------------------------------------------------------------------- */
+int ynet_scene_preprocess_u8(const uint8_t* img_hwc, int32_t H, int32_t W, int32_t dh, int32_t dw, int32_t Hp, int32_t Wp,
+                             const int32_t* xt_start, const int32_t* xt_src, const float* xt_w, const int32_t* yt_start,
+                             const int32_t* yt_src, const float* yt_w, int32_t int_scale, const double* mean3_host,
+                             const double* std3_host, float* out_chw, uint8_t* out_u8_hwc, void* stream);
+int ynet_scene_onehot_u8(const uint8_t* mask, int32_t H, int32_t W, int32_t dh, int32_t dw, int32_t Hp, int32_t Wp,
+                         double inv_factor, int32_t classes, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a18 fine-tuning step pieces (utils/train_epoch.py:86-115, models/trainer.py:197-206).
  * ------------------------------------------------------------------------------------------- */
 /* BCEWithLogitsLoss(mean) forward + d(loss*scale)/dlogits in one pass.  loss_out: 1 float (mean,

@@ -319,35 +319,37 @@ class YNetTrainer:
     # ------------------------------------------------------------------------------------------ data
     def prepare_data(self, df, image_path, dataset_name, mode, obs_len, pred_len, resize_factor, use_raw_data,
                      augment=False):
-        """trainer.py:518-584.  Image loading / cv2 resize+pad / segmentation preprocessing are host-side,
-        once per scene and outside the hot path: they are taken from the reference's own modules."""
-        try:
-            from utils.data_utils import augment_data, create_images_dict
-            from utils.image_utils import preprocess_image_for_segmentation, pad, resize
-        except Exception as e:  # pragma: no cover - needs the reference tree on sys.path
-            raise RuntimeError('prepare_data needs the reference\'s utils.data_utils / utils.image_utils (data '
-                               'pipeline is out of scope here); use train_prepared / test_prepared with ready '
-                               f'images + DataLoader instead ({e!r})')
+        """trainer.py:518-584.  Scene images are read with cv2 (host I/O, data_utils.py:248-263) and go through ONE fused
+        CUDA launch each -- resize (INTER_AREA) -> pad to a multiple of ``division_factor`` -> segmentation-backbone
+        normalisation, bit-exact against the reference's cv2 / numpy chain (utils/image_utils.py); the
+        returned dict holds device tensors.  Augmentation (data_utils.py:115-233) is outside the hot path."""
+        import cv2
+        from ..utils.image_utils import preprocess_scene_images
         dataset_name = dataset_name.lower()
         names = {'sdd': 'reference.jpg', 'ind-dataset-v1.0': 'reference.png', 'eth': 'oracle.png'}
         if dataset_name not in names:
             raise ValueError(f'{dataset_name} dataset is not supported')
         if dataset_name == 'eth':
             raise NotImplementedError('ETH/UCY homography path is outside the B200 hot path')
-        if not augment:
-            images_dict = create_images_dict(df.sceneId.unique(), image_path=image_path,
-                                             image_file=names[dataset_name], use_raw_data=use_raw_data)
-            print('No data and images augmentation')
-        else:
-            df, images_dict = augment_data(df, image_path=image_path, image_file=names[dataset_name], seg_mask=False,
-                                           use_raw_data=use_raw_data)
-            print('Augmented data and images')
+        if augment:
+            raise NotImplementedError('data / image augmentation (data_utils.py:115-233) is outside the B200 hot path; '
+                                      'augment the DataFrame and the images beforehand and use train_prepared()')
+        images_dict = {}
+        for scene in df.sceneId.unique():
+            if use_raw_data:
+                scene_name, scene_idx = scene.split('_')
+                im_path = os.path.join(image_path, scene_name, f'video{scene_idx}', names[dataset_name])
+            else:
+                im_path = os.path.join(image_path, scene, names[dataset_name])
+            im = cv2.imread(im_path)                 # channels: blue, green, red (data_utils.py:262)
+            if im is None:
+                raise FileNotFoundError(im_path)
+            images_dict[scene] = im
+        print('No data and images augmentation')
         dataset = SceneDataset(df, resize=resize_factor, total_len=obs_len + pred_len)
         dataloader = DataLoader(dataset, batch_size=1, collate_fn=scene_collate, shuffle=(mode == 'train'),
                                 generator=parallel.shared_generator() if mode == 'train' else None)
-        resize(images_dict, factor=resize_factor, seg_mask=False)
-        pad(images_dict, division_factor=self.division_factor)
-        preprocess_image_for_segmentation(images_dict, seg_mask=False)
+        preprocess_scene_images(images_dict, resize_factor, self.division_factor, seg_mask=False, device=self.device)
         return images_dict, dataloader, None
 
     # ------------------------------------------------------------------------------------------ checkpoints

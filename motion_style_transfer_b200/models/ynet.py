@@ -319,6 +319,20 @@ class YNet(nn.Module):
     def segmentation(self, image):
         return self.semantic_segmentation(image)
 
+    def segmentation_cached(self, scene_id, image):
+        """``segmentation(image)`` memoised per scene: evaluate() re-runs the frozen segmentation
+        backbone for every scene in every round / epoch (evaluate.py:86-90, trainer.py:336-345); the semantic map only
+        depends on the scene image and the backbone's weights, so it is kept until either changes."""
+        ver = (image.data_ptr(), image._version, tuple(image.shape),
+               tuple((q.data_ptr(), q._version) for q in self.semantic_segmentation.parameters()))
+        cache = self.__dict__.setdefault('_semantic_cache', {})
+        hit = cache.get(scene_id)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        out = self.semantic_segmentation(image)
+        cache[scene_id] = (ver, out)
+        return out
+
     def adapt_semantic(self, semantic_img):
         return semantic_img       # ynet.py:554-559: identity unless a semantic adapter exists (it cannot, see __init__)
 

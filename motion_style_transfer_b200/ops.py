@@ -148,6 +148,37 @@ def avgpool_pyramid(maps, n_levels):
     return [maps] + outs
 
 
+# ------------------------------------------------------------------------------------------------ 8f rank 2: scene images
+def scene_preprocess_u8(img_u8, dh, dw, Hp, Wp, xt, yt, int_scale, mean3=None, std3=None, want_chw=True, want_u8=False):
+    """uint8 HWC CUDA image -> (float32 (3, Hp, Wp) normalised | None, uint8 (dh, dw, 3) resized | None).
+    xt / yt: (start, src, weight) CUDA tensors of cv::computeResizeAreaTab (None with int_scale > 0)."""
+    img_u8 = _req(img_u8, torch.uint8, 'image')
+    H, W, C = img_u8.shape
+    if C != 3:
+        raise ValueError(f'scene_preprocess_u8: expected an (H, W, 3) image, got {tuple(img_u8.shape)}')
+    out = torch.empty(3, Hp, Wp, dtype=torch.float32, device=img_u8.device) if want_chw else None
+    out8 = torch.empty(dh, dw, 3, dtype=torch.uint8, device=img_u8.device) if want_u8 else None
+    m = (ctypes.c_double * 3)(*mean3) if mean3 is not None else None
+    sd = (ctypes.c_double * 3)(*std3) if std3 is not None else None
+    tabs = [None] * 6 if int_scale else [_ptr(t) for t in (xt + yt)]
+    with _timed('scene_preprocess_kernel', 0, 3.0 * H * W + 12.0 * Hp * Wp):
+        check(_L().ynet_scene_preprocess_u8(_ptr(img_u8), H, W, dh, dw, Hp, Wp, *tabs, int(int_scale), m, sd, _ptr(out),
+                                            _ptr(out8), _stream()), 'scene_preprocess_u8')
+    _count()
+    return out, out8
+
+
+def scene_onehot_u8(mask_u8, dh, dw, Hp, Wp, inv_factor, classes):
+    """uint8 (H, W) CUDA segmentation mask -> float32 (classes, Hp, Wp): INTER_NEAREST resize, zero pad, one-hot."""
+    mask_u8 = _req(mask_u8, torch.uint8, 'mask')
+    H, W = mask_u8.shape
+    out = torch.empty(classes, Hp, Wp, dtype=torch.float32, device=mask_u8.device)
+    check(_L().ynet_scene_onehot_u8(_ptr(mask_u8), H, W, dh, dw, Hp, Wp, float(inv_factor), classes, _ptr(out), _stream()),
+          'scene_onehot_u8')
+    _count()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ a10/a12/a13
 def softargmax2d(x, channel=None):
     """(B, C, H, W) -> (B, C, 2); with `channel` only that channel of every image -> (B, 1, 2)."""

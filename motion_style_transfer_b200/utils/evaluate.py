@@ -159,8 +159,10 @@ def evaluate(model, val_loader, val_images, device, dataset_name, homo_mat, inpu
 
     with torch.no_grad():
         for trajectory, df_batch, scene_id in val_loader:
-            scene_image = val_images[scene_id].to(device).unsqueeze(0)
-            scene_image = model.segmentation(scene_image)
+            scene_tensor = val_images[scene_id]
+            if scene_tensor.device != device:       # keep the scene resident: later rounds / epochs reuse the same tensor
+                scene_tensor = val_images[scene_id] = scene_tensor.to(device)
+            scene_image = model.segmentation_cached(scene_id, scene_tensor.unsqueeze(0))
             scene_image = model.adapt_semantic(scene_image).float().contiguous()
             if swap_semantic:                      # evaluate.py:95-96, image_utils.py:165-171
                 scene_image = swap_pavement_terrain(scene_image)

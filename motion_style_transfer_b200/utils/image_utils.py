@@ -2,8 +2,10 @@
 
 ``create_dist_mat`` / ``create_gaussian_heatmap_template`` / ``gkern`` are one-off host numpy code
 (identical formulas, image_utils.py:7-37); ``get_patch`` and ``sampling`` run on the device.
-Image preprocessing (resize/pad/smp preprocessing, image2world, swap_pavement_terrain) is outside
-the hot path.
+Scene-image preprocessing (image_utils.py:66-107: resize / pad / segmentation-backbone normalisation)
+runs as ONE fused CUDA launch per scene (``preprocess_scene_images``); ``resize`` / ``pad`` /
+``preprocess_image_for_segmentation`` keep the reference's names and in-place dict semantics on top of the same kernels.
+image2world (ETH/UCY homography) stays outside.
 """
 import numpy as np
 import torch
@@ -150,3 +152,121 @@ def sampling(probability_map, num_samples, rel_threshold=None, replacement=False
         q = rng.exponentials(B * C, H * W, dev)
         _, xy = ops.multinomial_topk(probability_map, q, num_samples, rel_threshold)
     return xy
+
+
+# ---- scene-image preprocessing (image_utils.py:66-107, trainer.py:578-582) -----------------------------
+# smp.encoders.get_preprocessing_fn('resnet101', 'imagenet') (segmentation_models_pytorch 0.1.0, requirements.txt:7; the
+# package is absent, the constants are its published ones): input_space RGB, input_range [0, 1]
+SMP_MEAN = (0.485, 0.456, 0.406)
+SMP_STD = (0.229, 0.224, 0.225)
+
+
+def area_table(ssize, dsize, scale):
+    """cv::computeResizeAreaTab for one axis as CSR arrays (start (dsize + 1,), src, float32 weight), in OpenCV's
+    accumulation order (host logic; the kernel walks it)."""
+    start, src, w = [0], [], []
+    for d in range(dsize):
+        f1 = d * scale
+        f2 = f1 + scale
+        cell = min(scale, ssize - f1)
+        s1, s2 = int(np.ceil(f1)), int(np.floor(f2))
+        s2 = min(s2, ssize - 1)
+        s1 = min(s1, s2)
+        if s1 - f1 > 1e-3:
+            src.append(s1 - 1)
+            w.append((s1 - f1) / cell)
+        for sx in range(s1, s2):
+            src.append(sx)
+            w.append(1.0 / cell)
+        if f2 - s2 > 1e-3:
+            src.append(s2)
+            w.append(min(min(f2 - s2, 1.0), cell) / cell)
+        start.append(len(src))
+    return (np.asarray(start, np.int32), np.asarray(src, np.int32), np.asarray(w, np.float64).astype(np.float32))
+
+
+def _resize_plan(H, W, factor):
+    """(dh, dw, scale, integer scale or 0) of cv2.resize(img, (0, 0), fx=factor, fy=factor, INTER_AREA)."""
+    dh, dw = int(np.rint(H * factor)), int(np.rint(W * factor))
+    scale = 1.0 / factor
+    isc = int(np.rint(scale))
+    fast = abs(scale - isc) < np.finfo(np.float64).eps and dh * isc <= H and dw * isc <= W
+    return dh, dw, scale, (isc if fast else 0)
+
+
+def _ceil_to(v, d):
+    return int(np.ceil(v / d) * d)
+
+
+_tab_cache = {}
+
+
+def _device_tabs(H, W, dh, dw, scale, device):
+    key = (H, W, dh, dw, scale, str(device))
+    hit = _tab_cache.get(key)
+    if hit is None:
+        xt = tuple(torch.from_numpy(a).to(device) for a in area_table(W, dw, scale))
+        yt = tuple(torch.from_numpy(a).to(device) for a in area_table(H, dh, scale))
+        hit = _tab_cache[key] = (xt, yt)
+    return hit
+
+
+def preprocess_scene_image(im, factor, division_factor=32, seg_mask=False, classes=6, device='cuda'):
+    """resize -> pad -> preprocess_image_for_segmentation of ONE scene image (trainer.py:578-582) in one launch:
+    uint8 (H, W, 3) numpy / tensor (or (H, W) mask with seg_mask) -> float32 (C, Hp, Wp) CUDA tensor."""
+    t = torch.as_tensor(np.ascontiguousarray(im) if isinstance(im, np.ndarray) else im)
+    if t.dtype != torch.uint8:
+        raise TypeError(f'scene images are uint8 (cv2.imread), got {t.dtype}')
+    t = t.to(device).contiguous()
+    H, W = t.shape[:2]
+    dh, dw, scale, isc = _resize_plan(H, W, factor)
+    Hp, Wp = _ceil_to(dh, division_factor), _ceil_to(dw, division_factor)
+    if seg_mask:
+        return ops.scene_onehot_u8(t, dh, dw, Hp, Wp, scale, classes)
+    xt, yt = (None, None) if isc else _device_tabs(H, W, dh, dw, scale, t.device)
+    return ops.scene_preprocess_u8(t, dh, dw, Hp, Wp, xt, yt, isc, SMP_MEAN, SMP_STD)[0]
+
+
+def preprocess_scene_images(images, factor, division_factor=32, seg_mask=False, classes=6, device='cuda'):
+    """The three preprocessing calls of trainer.py:578-582 over a dict of scene images, fused: {scene: uint8 image} ->
+    {scene: float32 (C, Hp, Wp) CUDA tensor} (in place, like the reference's helpers)."""
+    for key, im in images.items():
+        images[key] = preprocess_scene_image(im, factor, division_factor, seg_mask, classes, device)
+    return images
+
+
+def resize(images, factor, seg_mask=False):
+    """image_utils.py:85-92 (in place): cv2.resize(fx = fy = factor, INTER_AREA; INTER_NEAREST for masks) on the device;
+    the dict keeps numpy uint8 images like the reference's."""
+    for key, im in images.items():
+        t = torch.as_tensor(np.ascontiguousarray(im)).cuda()
+        H, W = t.shape[:2]
+        dh, dw, scale, isc = _resize_plan(H, W, factor)
+        if seg_mask:
+            ys = torch.clamp(torch.floor(torch.arange(dh, dtype=torch.float64, device=t.device) * scale).long(), max=H - 1)
+            xs = torch.clamp(torch.floor(torch.arange(dw, dtype=torch.float64, device=t.device) * scale).long(), max=W - 1)
+            images[key] = t[ys][:, xs].cpu().numpy()
+            continue
+        xt, yt = (None, None) if isc else _device_tabs(H, W, dh, dw, scale, t.device)
+        images[key] = ops.scene_preprocess_u8(t, dh, dw, dh, dw, xt, yt, isc, want_chw=False, want_u8=True)[1].cpu().numpy()
+
+
+def pad(images, division_factor=32):
+    """image_utils.py:95-107 (in place): zero border at the bottom / right up to a multiple of division_factor."""
+    for key, im in images.items():
+        H, W = im.shape[:2]
+        widths = ((0, _ceil_to(H, division_factor) - H), (0, _ceil_to(W, division_factor) - W)) + ((0, 0),) * (im.ndim - 2)
+        images[key] = np.pad(im, widths, mode='constant')
+
+
+def preprocess_image_for_segmentation(images, encoder='resnet101', encoder_weights='imagenet', seg_mask=False, classes=6):
+    """image_utils.py:66-82 (in place): uint8 HWC -> normalised float32 CHW tensor (one-hot for masks)."""
+    if (encoder, encoder_weights) != ('resnet101', 'imagenet'):
+        raise NotImplementedError('only the resnet101 / imagenet preprocessing the reference uses (image_utils.py:66)')
+    for key, im in images.items():
+        t = torch.as_tensor(np.ascontiguousarray(im)).cuda()
+        H, W = t.shape[:2]
+        if seg_mask:
+            images[key] = ops.scene_onehot_u8(t, H, W, H, W, 1.0, classes)
+        else:
+            images[key] = ops.scene_preprocess_u8(t, H, W, H, W, None, None, 1, SMP_MEAN, SMP_STD)[0]

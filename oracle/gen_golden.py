@@ -295,6 +295,27 @@ def gen_evaluate(ns):
              **rnd, **{'sd/' + k: v for k, v in sd.items()})
 
 
+def gen_preprocess():
+    """Scene-image preprocessing (image_utils.py:66-107) recorded from the installed cv2 + the published smp constants."""
+    import cv2
+    from oracle import preprocess_oracle as P
+    rng = np.random.RandomState(7)
+    out = {}
+    for tag, (H, W, f) in (('a', (97, 131, 0.33)), ('b', (64, 96, 0.25))):
+        img = rng.randint(0, 256, (H, W, 3)).astype(np.uint8)
+        r = cv2.resize(img, (0, 0), fx=f, fy=f, interpolation=cv2.INTER_AREA)
+        p = cv2.copyMakeBorder(r, 0, (-r.shape[0]) % 32, 0, (-r.shape[1]) % 32, cv2.BORDER_CONSTANT)
+        x = ((p / 255.0) - P.IMAGENET_MEAN) / P.IMAGENET_STD
+        out.update({f'img_{tag}': img, f'factor_{tag}': f, f'resized_{tag}': r,
+                    f'chw_{tag}': x.transpose(2, 0, 1).astype('float32')})
+    mask = rng.randint(0, 6, (97, 131)).astype(np.uint8)
+    m = cv2.resize(mask, (0, 0), fx=0.33, fy=0.33, interpolation=cv2.INTER_NEAREST)
+    m = cv2.copyMakeBorder(m, 0, (-m.shape[0]) % 32, 0, (-m.shape[1]) % 32, cv2.BORDER_CONSTANT)
+    out['mask'] = mask
+    out['onehot'] = np.stack([(m == v) for v in range(6)], axis=-1).transpose(2, 0, 1).astype('float32')
+    save('preprocess', **out)
+
+
 def gen_train(ns):
     """Two optimiser steps of the reference's train_epoch (train_epoch.py:8-136) with MoSA r=1 on stages 0-4:
     freeze policy of trainer.py:117,137-139, Adam(lr) + BCEWithLogitsLoss as trainer.py:197,206."""
@@ -353,6 +374,7 @@ def main(only=None):
     gen_embed_semantic(ns)
     gen_evaluate(ns)
     gen_train(ns)
+    gen_preprocess()
 
 
 if __name__ == '__main__':
