@@ -38,5 +38,28 @@ sig = torch.rand(3, H, W, device=dev)
 wp = torch.rand(20, 3, 2, device=dev) * 50
 cw = ops.cws_waypoint(sig, wp, torch.rand(3, 2, device=dev) * 50, 0.5, torch.full((20,), 6.0, device=dev), 2.0, True)
 ade, fde = ops.ade_fde(torch.rand(3, 30, 2, device=dev), torch.rand(20, 3, 30, 2, device=dev), torch.rand(20, 3, 2, 2, device=dev), 0.33)
+# round 2: row-marching conv (plain, padded output, multi-source + hoisted partial), fused conv + predictor + soft-argmax tail,
+# scene-image preprocessing
+xr = ops.tc_pack(torch.relu(torch.randn(3, 32, 34, 150, device=dev)))
+wr = torch.randn(32, 32, 3, 3, device=dev) * 0.1
+b32 = torch.randn(32, device=dev) * 0.1
+pkr = ops.tc_rowconv_pack_weights(wr, 32)
+yr = ops.tc_rowconv3x3(xr, pkr, b32, 32, True, pad_out=True)
+up = ops.tc_pack(torch.randn(6, 16, 34, 150, device=dev))
+wpl = ops.tc_pack(torch.rand(6, 2, 34, 150, device=dev))
+feat = ops.tc_pack(torch.relu(torch.randn(2, 32, 34, 150, device=dev)))
+w2 = torch.randn(32, 50, 3, 3, device=dev) * 0.1
+part = ops.tc_conv3x3_hilo([feat], ops.tc_pack_weights(w2[:, 16:48].contiguous(), [32]), 32, True).repeat_interleave(3)
+ym = ops.tc_rowconv3x3([up, wpl], ops.tc_rowconv_pack_weights_cat(w2, [(0, 16, 16), (48, 50, 16)]), b32, 32, True, partial=part)
+wp1 = torch.randn(30, 32, 1, 1, device=dev) * 0.5
+sa = ops.tc_rowconv3x3_pred_softargmax(xr, pkr, b32, 32, True, ops.tc_pack_weights(wp1, [32]), torch.zeros(32, device=dev), 30)
+from motion_style_transfer_b200.utils import image_utils as U  # noqa: E402
+import numpy as np  # noqa: E402
+img = np.random.RandomState(0).randint(0, 256, (97, 131, 3)).astype(np.uint8)
+pre = U.preprocess_scene_image(img, 0.33, 32)
+pre4 = U.preprocess_scene_image(img, 0.25, 32)
+msk = U.preprocess_scene_image(img[:, :, 0] % 6, 0.33, 32, seg_mask=True)
 torch.cuda.synchronize()
+print('sanitize_small r02: ok', float(ops.tc_unpack(yr).abs().sum()), float(ops.tc_unpack(ym).abs().sum()), float(sa.sum()),
+      float(pre.sum()), float(pre4.sum()), float(msk.sum()))
 print('sanitize_small: ok', float(ops.tc_unpack(out).abs().sum()), int(idx.sum()), float(cw.sum()), float(ade.sum()))
