@@ -420,8 +420,9 @@ def main():
     ap.add_argument('--profile-layers', default=None, help='write a per-layer timing table to this path')
     ap.add_argument('--no-graph', dest='graph', action='store_false',
                     help='issue every kernel from Python instead of replaying the captured CUDA graph')
-    ap.add_argument('--backend', default='bf16', choices=['bf16', 'fp32'],
-                    help='bf16 = tcgen05 tensor-core engine (default), fp32 = CUDA-core reference-grade engine')
+    ap.add_argument('--backend', default='bf16', choices=['bf16', 'fp32', 'bf16x3'],
+                    help='bf16 = tcgen05 tensor-core engine (default), fp32 = CUDA-core reference-grade engine, bf16x3 = '
+                         'split-bf16 tensor-core engine at the fp32 engine\'s parity (three MMAs per product)')
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', 0))

@@ -305,6 +305,29 @@ int ynet_tc_conv3x3_hilo(const ynet_tc_src* srcs_host, int32_t n_src, int32_t N,
                          const void* packed_weight, int32_t C_out, void* out_c8, int32_t C_out_pad, int32_t with_lo,
                          int32_t tune, void* stream);
 
+/* Split-bf16 ("bf16x3") engine: the <= 1e-3 parity mode of models/ynet.py:302-470 on the tensor cores (split_tc.cu).
+ * A float32 activation x travels as hi = bf16(x), lo = bf16(x - hi) in ONE tensor (N, 2*C_pad/8, H, W, 8): hi planes,
+ * then lo planes (C_pad = channels padded to 16).  y = W_hi x_hi + W_hi x_lo + W_lo x_hi (+ bias, ReLU in float32):
+ *   ynet_tc_conv3x3_split: per activation TWO ynet_tc_src entries -- {ptr, channels_pad = 2*C_pad} against the packed
+ *       [W_hi | W_hi] and {ptr, channels_pad = C_pad, same batch_stride} (the hi planes again) against W_lo -- so the
+ *       packed weight is ynet_tc_pack_weights over sources (2*C_pad, C_pad, ...); out_split: (N, 2*C_out_pad/8, H, W, 8).
+ *       Concat-on-write (torch.cat of ynet.py:466 / evaluate.py:259 without a copy): out_total_pad > 0 makes out_split a
+ *       wider activation (N, 2*out_total_pad/8, H, W, 8) of which this call fills channels [out_channel_off,
+ *       out_channel_off + C_out_pad) of both halves; ynet_split_pack_f32 takes the same pair.  0, 0 = a tensor of its own.
+ *       The 1x1 predictor (ynet.py:450-451) is ynet_tc_conv1x1_f32 over the same source pairs (float32 NCHW logits).
+ *   ynet_split_pack_f32 / ynet_split_unpack_f32: NCHW float32 <-> split planes (batch_stride in floats, 0 = broadcast);
+ *   ynet_split_maxpool2x2 (nn.MaxPool2d(2, 2), ynet.py:241-245), ynet_split_upsample2x (F.interpolate(scale_factor=2,
+ *       mode='bilinear', align_corners=False), ynet.py:463): read hi + lo, compute in float32, split again. */
+int ynet_tc_conv3x3_split(const ynet_tc_src* srcs_host, int32_t n_src, int32_t N, int32_t H, int32_t W,
+                          const void* packed_weight, const float* bias, int32_t C_out, int32_t relu, void* out_split,
+                          int32_t C_out_pad, int32_t out_total_pad, int32_t out_channel_off, int32_t tune, void* stream);
+int ynet_split_pack_f32(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, int64_t batch_stride, void* out_split,
+                        int32_t C_pad, int32_t out_total_pad, int32_t out_channel_off, void* stream);
+int ynet_split_unpack_f32(const void* x_split, int32_t N, int32_t C, int32_t C_pad, int32_t H, int32_t W, float* out,
+                          void* stream);
+int ynet_split_maxpool2x2(const void* x_split, int32_t N, int32_t C_pad, int32_t H, int32_t W, void* out_split, void* stream);
+int ynet_split_upsample2x(const void* x_split, int32_t N, int32_t C_pad, int32_t H, int32_t W, void* out_split, void* stream);
+
 /* The 1x1 predictor (ynet.py:450-451,469) on the tensor cores:
  *   ynet_tc_conv1x1_f32        -> float32 NCHW logits (goal decoder: sigmoid / sampling need the map);
  *   ynet_tc_conv1x1_softargmax -> predictor + SoftArgmax2D (ynet.py:582-583, softargmax.py:55-81) in one

@@ -90,6 +90,11 @@ _PROTOS = {
     'ynet_tc_conv3x3_pred_softargmax': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P, _L, _P]),
     'ynet_tc_pad_replicate': (c_int, [_P, _I, _I, _I, _I, _P, _P]),
     'ynet_tc_conv3x3_hilo': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P]),
+    'ynet_tc_conv3x3_split': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _I, _I, _I, _P]),
+    'ynet_split_pack_f32': (c_int, [_P, _I, _I, _I, _I, _L, _P, _I, _I, _I, _P]),
+    'ynet_split_unpack_f32': (c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    'ynet_split_maxpool2x2': (c_int, [_P, _I, _I, _I, _I, _P, _P]),
+    'ynet_split_upsample2x': (c_int, [_P, _I, _I, _I, _I, _P, _P]),
     'ynet_tc_rowconv_packed_weight_bytes': (_L, [_I]),
     'ynet_tc_rowconv_pack_weights': (c_int, [_P, _I, _I, _I, _P, _P]),
     'ynet_tc_rowconv3x3': (c_int, [POINTER(TcSrc), _I, POINTER(TcSrc), _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),

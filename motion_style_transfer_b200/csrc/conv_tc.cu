@@ -37,7 +37,7 @@ struct TcSrcDev {
   int off;          // 1: the tensor carries a one-pixel replicate-padded ring (dims H + 2, W + 2): shift the TMA box
   int pad_[3];
 };
-constexpr int TC_MAX_KB = 32;
+constexpr int TC_MAX_KB = 64;
 
 struct TcParams {
   TcSrcDev src[YNET_MAX_SOURCES];
@@ -46,9 +46,11 @@ struct TcParams {
   long long total_tiles;
   int kb_total;           // sum of kblocks
   int with_lo;            // EPI_HILO: also write the low halves
+  int hl_planes, hl_off;  // EPI_HILO: 8-channel planes per image of the output tensor (hi then lo halves) and the first hi
+                          // plane this conv writes (concat-on-write: the output may be a slice of a wider activation)
   int pad_out;            // EPI_C8: write (H + 2, W + 2) planes with a replicated one-pixel ring (input of an upconv)
-  uint32_t center_mask;   // bit kb: K block kb belongs to a centre-tap-only source
-  uint32_t quad_mask;     // bit kb: K block kb belongs to a 2x2-neighbourhood source: taps (0,0) (0,1) (1,0) (1,1) only
+  uint64_t center_mask;   // bit kb: K block kb belongs to a centre-tap-only source
+  uint64_t quad_mask;     // bit kb: K block kb belongs to a 2x2-neighbourhood source: taps (0,0) (0,1) (1,0) (1,1) only
   int w_total;            // bytes of the packed weights
   int wofs[TC_MAX_KB];    // byte offset of K block kb in the packed weights (9-tap and 1-tap blocks are mixed)
   int resident;           // weights resident in smem
@@ -145,8 +147,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err);
             unsigned char* st = s_stage + (size_t)stage * p.stage_bytes;
             const uint32_t fb = smem_u32(&full_bar[stage]);
-            const uint32_t wb = ((p.center_mask >> kb) & 1u) ? (uint32_t)(wblk_bytes / TAPS)
-                                : ((p.quad_mask >> kb) & 1u) ? (uint32_t)(4 * (wblk_bytes / TAPS))
+            const uint32_t wb = ((p.center_mask >> kb) & 1ull) ? (uint32_t)(wblk_bytes / TAPS)
+                                : ((p.quad_mask >> kb) & 1ull) ? (uint32_t)(4 * (wblk_bytes / TAPS))
                                                              : (uint32_t)wblk_bytes;
             mbar_expect_tx(fb, p.a_bytes + (p.resident ? 0u : wb));
             tma_load_4d(smem_u32(st), map, fb, 8 * (x0 - HALO + p.src[s].off), y0 - HALO + p.src[s].off, 2 * b, ns);
@@ -190,7 +192,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
           const uint32_t b_base = p.resident ? smem_u32(s_w + p.wofs[kb]) : smem_u32(st + p.a_bytes);
           uint32_t b_lo = ((b_base >> 4) & 0x3FFF) | b_lbo_field;
           const uint32_t acc_first = (kb > 0) ? 1u : 0u;
-          if (TAPS == 9 && ((p.center_mask >> kb) & 1u)) {
+          if (TAPS == 9 && ((p.center_mask >> kb) & 1ull)) {
             // hoisted partial sums: identity weights on the centre tap only
             const uint64_t bdesc = ((uint64_t)b_hi << 32) | b_lo;
 #pragma unroll
@@ -198,7 +200,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
               const uint64_t adesc = ((uint64_t)A_HI << 32) | (a_lo0 + (uint32_t)(BW + 1 + 8 * jj));
               tc_mma_bf16(d_tmem + (uint32_t)(jj * p.n_pad), adesc, bdesc, idesc, acc_first);
             }
-          } else if (TAPS == 9 && ((p.quad_mask >> kb) & 1u)) {
+          } else if (TAPS == 9 && ((p.quad_mask >> kb) & 1ull)) {
             // 2x2-neighbourhood planes (waypoint maps): the four taps anchored at (-1,-1) (-1,0) (0,-1) (0,0) cover
             // the 3x3 window; the packed weights hold exactly these four taps
 #pragma unroll
@@ -370,10 +372,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
                 ol.y = pack_bf16(lo[2], lo[3]);
                 ol.z = pack_bf16(lo[4], lo[5]);
                 ol.w = pack_bf16(lo[6], lo[7]);
-                const int planes = p.with_lo ? 2 * n_chunks : n_chunks;
-                __nv_bfloat16* dst = p.out + ((((size_t)n * planes + chunk) * p.H + y) * p.W + x) * 8;
+                __nv_bfloat16* dst = p.out + ((((size_t)n * p.hl_planes + p.hl_off + chunk) * p.H + y) * p.W + x) * 8;
                 *reinterpret_cast<uint4*>(dst) = o;
-                if (p.with_lo) *reinterpret_cast<uint4*>(dst + (size_t)n_chunks * p.H * p.W * 8) = ol;
+                if (p.with_lo) *reinterpret_cast<uint4*>(dst + (size_t)(p.hl_planes >> 1) * p.H * p.W * 8) = ol;
               }
             }
           } else if (EPI == EPI_NCHW_F32) {
@@ -572,7 +573,7 @@ tc_conv_pred_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
           const uint32_t a_lo0 = ((smem_u32(s_stage + (size_t)stage * p.stage_bytes) >> 4) & 0x3FFF) | A_LBO_FIELD;
           uint32_t b_lo = ((smem_u32(s_w + p.wofs[kb]) >> 4) & 0x3FFF) | b_lbo_field;
           const uint32_t acc_first = (kb > 0) ? 1u : 0u;
-          if ((p.center_mask >> kb) & 1u) {
+          if ((p.center_mask >> kb) & 1ull) {
             const uint64_t bdesc = ((uint64_t)b_hi << 32) | b_lo;
             {
               const uint64_t adesc = ((uint64_t)A_HI << 32) | (a_lo0 + (uint32_t)(BW + 1 + 8 * jj));
@@ -1598,7 +1599,7 @@ static void tc_dispatch(int j, unsigned grid, size_t smem, cudaStream_t st, cons
 // Shared launcher of the tcgen05 conv kernel.  taps = 9 (3x3, padding 1) or 1 (1x1); epi = EPI_*.
 static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N, int H, int W, const void* packed_weight,
                      const float* bias, int C_out, int relu, int C_out_pad, int tune, int taps, int epi, TcOut out,
-                     int* grid_out, void* stream) {
+                     int* grid_out, void* stream, int hl_total_pad = 0, int hl_channel_off = 0) {
   if (!(srcs && packed_weight && (bias || epi == EPI_HILO))) {
     set_error("%s: null pointer", who);
     return YNET_E_INVALID;
@@ -1694,8 +1695,8 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
     for (int b = 0; b < cp / 16; ++b) {
       p.wofs[kb_total + b] = w_total;
       w_total += (p.src[i].center ? 1 : (quad ? 4 : taps)) * 2 * C_out_pad * 16;
-      if (p.src[i].center) p.center_mask |= 1u << (kb_total + b);
-      if (quad) p.quad_mask |= 1u << (kb_total + b);
+      if (p.src[i].center) p.center_mask |= 1ull << (kb_total + b);
+      if (quad) p.quad_mask |= 1ull << (kb_total + b);
     }
     kb_total += cp / 16;
   }
@@ -1707,9 +1708,11 @@ static int tc_launch(const char* who, const ynet_tc_src* srcs, int n_src, int N,
   p.W = W;
   p.n_pad = C_out_pad;
   p.c_out = C_out;
-  p.relu = (epi == EPI_HILO) ? 0 : (relu & 1);
+  p.relu = relu & 1;
   p.pad_out = (epi == EPI_C8 && (relu & 2)) ? 1 : 0;
-  p.with_lo = (epi == EPI_HILO && relu == 2) ? 1 : 0;
+  p.with_lo = (epi == EPI_HILO && (relu & 2)) ? 1 : 0;
+  p.hl_planes = hl_total_pad > 0 ? 2 * hl_total_pad / 8 : (p.with_lo ? 2 : 1) * (C_out_pad / 8);
+  p.hl_off = hl_channel_off / 8;
   p.tiles_x = ceil_div(W, 8 * p.j);
   p.tiles_y = ceil_div(H, TC_TH);
   p.total_tiles = (long long)N * p.tiles_x * p.tiles_y;
@@ -1866,6 +1869,23 @@ int ynet_tc_conv3x3_hilo(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int3
   TcOut o{out_c8, nullptr, nullptr, nullptr};
   return tc_launch("ynet_tc_conv3x3_hilo", srcs, n_src, N, H, W, packed_weight, nullptr, C_out, with_lo ? 2 : 0, C_out_pad,
                    tune, 9, EPI_HILO, o, nullptr, stream);
+}
+
+// A full layer of the split-bf16 engine (split_tc.cu): conv over the sources (for an activation x: [x_hi | x_lo] against
+// [W_hi | W_hi], then the hi planes again against W_lo), + bias, ReLU, fp32 accumulator split into hi | lo planes.
+int ynet_tc_conv3x3_split(const ynet_tc_src* srcs, int32_t n_src, int32_t N, int32_t H, int32_t W, const void* packed_weight,
+                          const float* bias, int32_t C_out, int32_t relu, void* out_split, int32_t C_out_pad,
+                          int32_t out_total_pad, int32_t out_channel_off, int32_t tune, void* stream) {
+  YNET_CHECK_ARG(out_split != nullptr || N == 0, "null output");
+  YNET_CHECK_ARG(bias != nullptr, "null bias");
+  if (out_total_pad == 0) out_total_pad = C_out_pad;
+  YNET_CHECK_ARG(out_total_pad % 16 == 0 && out_channel_off % 16 == 0 && out_channel_off >= 0 &&
+                     out_channel_off + C_out_pad <= out_total_pad,
+                 "output slice outside the activation (multiples of 16)");
+  YNET_CHECK_ALIGN(out_split, 16);
+  TcOut o{out_split, nullptr, nullptr, nullptr};
+  return tc_launch("ynet_tc_conv3x3_split", srcs, n_src, N, H, W, packed_weight, bias, C_out, (relu ? 1 : 0) | 2, C_out_pad,
+                   tune, 9, EPI_HILO, o, nullptr, stream, out_total_pad, out_channel_off);
 }
 
 int ynet_tc_upconv_phase_weights(const float* weight, const float* bias, int32_t C_out, int32_t C_in, float* w_eff,

@@ -3,9 +3,9 @@
 Constructor arguments, attributes, the train/test/load/save methods, the freeze-policy DSL
 (``train_net`` / ``position`` / ``ynet_bias``), the checkpoint layout and the stdout formats scraped
 by the reference's log tools are preserved; the compute runs through libynet_b200.so.
-Data preparation (pandas / cv2 / segmentation preprocessing, trainer.py:518-584) is outside the hot
-path: ``prepare_data`` delegates to the reference's own ``utils.data_utils`` when it is importable,
-and ``train_prepared`` / ``test_prepared`` accept ready-made (images dict, DataLoader) pairs.
+``prepare_data`` (trainer.py:518-584) reads the scene images with cv2 and preprocesses them in one fused CUDA launch
+each; ``train_prepared`` / ``test_prepared`` / ``forward_test_prepared`` accept ready-made (images dict, DataLoader)
+pairs.
 """
 import os
 import pathlib
@@ -18,6 +18,7 @@ from torch.utils.data import DataLoader
 from tqdm import tqdm
 
 from .. import ops, parallel
+from ..engine import ChannelCat
 from ..autograd_engine import BCEWithLogitsLoss
 from ..utils.dataloader import SceneDataset, scene_collate
 from ..utils.evaluate import evaluate
@@ -313,8 +314,114 @@ class YNetTrainer:
         print(f'\nAverage performance (by {n_round}): \nTest ADE: {avg_ade} \nTest FDE: {avg_fde}')
         return avg_ade, avg_fde, list_metrics, list_trajs
 
+    # ------------------------------------------------------------------------------------------ saliency
     def forward_test(self, df_test, image_path, set_input, noisy_std_frac):
-        raise NotImplementedError('forward_test (saliency tooling, trainer.py:354-516) is outside the B200 hot path')
+        """trainer.py:354-355: one differentiable forward of one scene, for input-gradient (saliency) studies."""
+        p = self.params
+        test_images, test_loader, self.homo_mat = self.prepare_data(
+            df_test, image_path, p['dataset_name'], 'test', p['obs_len'], p['pred_len'], p['resize_factor'],
+            p.get('use_raw_data', False))
+        return self.forward_test_prepared(test_images, test_loader, set_input, noisy_std_frac)
+
+    def forward_test_prepared(self, test_images, test_loader, set_input, noisy_std_frac):
+        return self._forward_test(test_images, test_loader, set_input, noisy_std_frac, **self.params)
+
+    def _forward_test(self, test_images, test_loader, set_input, noisy_std_frac, decision, obs_len, pred_len, waypoints,
+                      kernlen, nsig, loss_scale, **kwargs):
+        """trainer.py:357-443.  ``decision`` = 'loss' -> (goal_loss, traj_loss, scene image[, noisy scene image]);
+        'map' -> (goal logits, trajectory logits, scene image[, noisy scene image, cat(semantic, observed maps)]).
+
+        Which tensor carries ``requires_grad`` follows the reference: the noisy copy of the scene image when noise goes
+        on the semantic input, else the scene image itself if 'scene' is in ``set_input``; noise on the semantic map /
+        the observed maps is added inside ``_forward_batch``.  (In the reference only ``noisy_std_frac=None`` with
+        ``decision='map'`` runs to the end -- 'loss' passes ``False`` as ``set_input`` (trainer.py:381-383, TypeError) and
+        the noisy branches return names that were never bound (trainer.py:436-440); here every combination returns what
+        those lines evidently meant.)"""
+        if decision not in ('loss', 'map'):
+            raise ValueError(f'No support for decision={decision}')
+        if len(test_loader) == 0:
+            raise ValueError('No data is provided')
+        if len(test_loader) != 1:
+            raise ValueError(f'Received more than 1 scene ({len(test_loader)})')
+        input_template = torch.Tensor(create_dist_mat(size=self.template_size)).to(self.device)
+        gt_template = torch.Tensor(create_gaussian_heatmap_template(
+            size=self.template_size, kernlen=kernlen, nsig=nsig, normalize=False)).to(self.device)
+        criterion = BCEWithLogitsLoss()
+        traj, _, scene_id = next(iter(test_loader))
+        scene_raw_img = test_images[scene_id].to(self.device).unsqueeze(0)
+        noisy_scene_img = None
+        fed = scene_raw_img
+        if noisy_std_frac is not None and 'semantic' in set_input:
+            std = float(noisy_std_frac * (scene_raw_img.max() - scene_raw_img.min()))
+            noisy_scene_img = scene_raw_img + scene_raw_img.new(scene_raw_img.size()).normal_(0, std)
+            noisy_scene_img.requires_grad = True
+            fed = noisy_scene_img
+        elif noisy_std_frac is None:
+            scene_raw_img.requires_grad = 'scene' in set_input
+        out = self._forward_batch(fed, traj, input_template, gt_template, criterion, obs_len, pred_len, waypoints,
+                                  loss_scale, self.device, set_input, noisy_std_frac, decision == 'map')
+        head = tuple(out[:2])
+        if noisy_std_frac is None:
+            return head + (scene_raw_img,)
+        if decision == 'loss':
+            return head + (scene_raw_img, noisy_scene_img)
+        return head + (scene_raw_img, noisy_scene_img, out[2] if len(out) > 2 else None)
+
+    def _forward_batch(self, scene_raw_img, traj, input_template, gt_template, criterion, obs_len, pred_len, waypoints,
+                       loss_scale, device, set_input=None, noisy_std_frac=None, return_pred_map=False):
+        """trainer.py:445-516: goal decoder on (semantic map, observed maps), trajectory decoder on the features plus
+        the AvgPool pyramid of the PREDICTED waypoint logits, BCE of both against the Gaussian ground-truth maps.
+
+        Runs on the differentiable executor (``autograd_engine``: conv forward / dgrad kernels of libynet_b200.so) as
+        soon as an input requires a gradient, so ``.backward()`` on the returned losses or maps reaches
+        ``scene_raw_img`` through the segmentation backbone.  Heat maps are rasterised on the device (constants)."""
+        model = self.model.to(self.device)
+        set_input = () if set_input is None else set_input
+        _, _, H, W = scene_raw_img.shape
+        traj = traj.to(device=self.device, dtype=torch.float32)
+        B = traj.shape[0]
+        observed_map = ops.rasterize_patches(input_template, traj[:, :obs_len].reshape(-1, 2), H, W).view(B, obs_len, H, W)
+        gt_future_map = ops.rasterize_patches(gt_template, traj[:, obs_len:].reshape(-1, 2), H, W).view(B, pred_len, H, W)
+        semantic_image = model.adapt_semantic(model.segmentation(scene_raw_img))     # (1, C, H, W): broadcast over agents
+
+        scene_in, motion_in = semantic_image, observed_map
+        noisy = False
+        if noisy_std_frac is not None and 'semantic' in set_input:
+            semantic_image = semantic_image.expand(B, -1, -1, -1)
+            std = float(noisy_std_frac * (semantic_image.detach().max() - semantic_image.detach().min()))
+            scene_in = semantic_image + semantic_image.new(semantic_image.size()).normal_(0, std)
+            scene_in.requires_grad_(True)
+            noisy = True
+        if 'traj' in set_input:
+            if noisy_std_frac is not None:
+                std = float(noisy_std_frac * (observed_map.max() - observed_map.min()))
+                motion_in = observed_map + observed_map.new(observed_map.size()).normal_(0, std)
+                motion_in.requires_grad_(True)
+                if scene_in is not semantic_image:
+                    # trainer.py:487-488: with both inputs noisy the reference feeds the noisy SEMANTIC map as the
+                    # motion input too; kept (it only type-checks when the two have the same channel count)
+                    motion_in = scene_in
+                noisy = True
+            else:
+                observed_map.requires_grad_(True)
+
+        features = model.pred_features(scene_in.float().contiguous(), motion_in.contiguous())
+        pred_goal_map = model.pred_goal(features)
+        goal_loss = criterion(pred_goal_map, gt_future_map) * loss_scale
+        pred_waypoint_map = pred_goal_map[:, waypoints]
+        # nn.AvgPool2d(2^i) of the predicted logits, differentiable (torch's pooling: this tool is not on the hot path)
+        pyr = [pred_waypoint_map] + [torch.nn.functional.avg_pool2d(pred_waypoint_map, 2 ** i, 2 ** i)
+                                     for i in range(1, len(features))]
+        traj_input = [ChannelCat(tuple(f) + (g.contiguous(),)) if isinstance(f, tuple) else ChannelCat((f, g.contiguous()))
+                      for f, g in zip(features, pyr)]
+        pred_traj_map = model.pred_traj(traj_input)
+        traj_loss = criterion(pred_traj_map, gt_future_map) * loss_scale
+        if return_pred_map:
+            if noisy:
+                sem = semantic_image if semantic_image.shape[0] == B else semantic_image.expand(B, -1, -1, -1)
+                return pred_goal_map, pred_traj_map, torch.cat([sem, observed_map], dim=1)
+            return pred_goal_map, pred_traj_map
+        return goal_loss, traj_loss
 
     # ------------------------------------------------------------------------------------------ data
     def prepare_data(self, df, image_path, dataset_name, mode, obs_len, pred_len, resize_factor, use_raw_data,

@@ -24,7 +24,7 @@ import torch.nn as nn
 
 from . import lora
 from .. import ops
-from ..engine import YNetEngine, YNetEngineTC, ChannelCat
+from ..engine import YNetEngine, YNetEngineSplit, YNetEngineTC, ChannelCat
 from ..utils.softargmax import SoftArgmax2D
 
 
@@ -298,8 +298,9 @@ class YNet(nn.Module):
 
     # ---- engine plumbing -------------------------------------------------------------------------
     def set_backend(self, backend):
-        """'fp32' = CUDA-core reference-grade engine (<= 1e-3 parity); 'bf16' = tcgen05 tensor-core engine."""
-        if backend not in ('fp32', 'bf16'):
+        """'fp32' = CUDA-core reference-grade engine (<= 1e-3 parity); 'bf16' = tcgen05 tensor-core engine;
+        'bf16x3' = split-bf16 tensor-core engine (<= 1e-3 parity, three MMAs per product)."""
+        if backend not in ('fp32', 'bf16', 'bf16x3'):
             raise ValueError(f'unknown backend {backend!r}')
         object.__setattr__(self, '_backend', backend)
         object.__setattr__(self, '_engine', None)
@@ -308,12 +309,23 @@ class YNet(nn.Module):
     @property
     def engine(self):
         if self._engine is None:
-            eng = YNetEngineTC(self) if self._backend == 'bf16' else YNetEngine(self)
+            eng = {'bf16': YNetEngineTC, 'bf16x3': YNetEngineSplit}.get(self._backend, YNetEngine)(self)
             object.__setattr__(self, '_engine', eng)
         return self._engine
 
-    def _training_graph(self):
-        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+    def _training_graph(self, *inputs):
+        """Differentiable executor (autograd_engine) when a parameter OR an input asks for gradients -- the latter is
+        the saliency path of trainer.py:354-516 (frozen weights, ``scene_raw_img.requires_grad = True``)."""
+        if not torch.is_grad_enabled():
+            return False
+        if any(p.requires_grad for p in self.parameters()):
+            return True
+
+        def walk(x):
+            if isinstance(x, torch.Tensor):
+                return x.requires_grad
+            return isinstance(x, (tuple, list)) and any(walk(t) for t in x)
+        return any(walk(x) for x in inputs)
 
     # ---- reference method set (ynet.py:551-600) ---------------------------------------------------
     def segmentation(self, image):
@@ -337,19 +349,19 @@ class YNet(nn.Module):
         return semantic_img       # ynet.py:554-559: identity unless a semantic adapter exists (it cannot, see __init__)
 
     def pred_features(self, scene_map, motion_map):
-        if self._training_graph():
+        if self._training_graph(scene_map, motion_map):
             from .. import autograd_engine
             return autograd_engine.pred_features(self, scene_map, motion_map)
         return self.engine.pred_features(scene_map, motion_map)
 
     def pred_goal(self, features):
-        if self._training_graph():
+        if self._training_graph(features):
             from .. import autograd_engine
             return autograd_engine.decoder_logits(self, self.goal_decoder, 'goal_decoder', features)
         return self.engine.decoder_logits(self.goal_decoder, 'goal_decoder', features)
 
     def pred_traj(self, features):
-        if self._training_graph():
+        if self._training_graph(features):
             from .. import autograd_engine
             return autograd_engine.decoder_logits(self, self.traj_decoder, 'traj_decoder', features)
         return self.engine.decoder_logits(self.traj_decoder, 'traj_decoder', features)

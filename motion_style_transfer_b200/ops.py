@@ -920,6 +920,174 @@ def tc_conv3x3_hilo(sources, packed_weight, C_out, with_lo=True):
     return C8(out, k * cp, 1, True)
 
 
+# ---- split-bf16 ("bf16x3") activations: the <= 1e-3 engine on the tensor cores (csrc/split_tc.cu) ---------------------
+class Split:
+    """float32 activation as hi = bf16(x), lo = bf16(x - hi): data (N, 2 * cp / 8, H, W, 8) bfloat16, hi planes then lo
+    planes, cp = pad16(C).  As a conv source a batch of 1 is broadcast and a divisor of N is read modulo (goal-major
+    stacking of the decoder passes, like the fp32 engine)."""
+
+    __slots__ = ('data', 'C', 'layout')
+    rep = 1
+
+    def __init__(self, data, C, layout=None):
+        # layout: [(C_i, cp_i)] of the activations concatenated inside (split_cat); their channels sit at sum(cp_<i)
+        self.data, self.C = data, C
+        self.layout = [(C, data.shape[1] * 4)] if layout is None else layout
+
+    N = property(lambda self: self.data.shape[0])
+    H = property(lambda self: self.data.shape[2])
+    W = property(lambda self: self.data.shape[3])
+    cp = property(lambda self: self.data.shape[1] * 4)
+
+
+def split_empty(N, layout, H, W, device):
+    """Uninitialised Split holding the channel concatenation ``layout`` = [(C_i, cp_i)]: the target of concat-on-write
+    (``into=`` of split_pack / tc_conv3x3_split), every slice of which must then be written."""
+    tot = sum(cp for _, cp in layout)
+    return Split(torch.empty(N, tot // 4, H, W, 8, dtype=torch.bfloat16, device=device), sum(c for c, _ in layout),
+                 list(layout))
+
+
+def split_pack(x, into=None):
+    """NCHW float32 (batch may be broadcast) -> Split; into = (Split buffer, channel offset): fill that slice instead."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
+        raise RuntimeError('split_pack: expected a 4-D float32 CUDA tensor')
+    if x.shape[0] > 1 and x.stride(0) == 0:
+        x = x[:1]
+    if not x[0].is_contiguous():
+        x = x.contiguous()
+    N, C, H, W = x.shape
+    cp = _pad16(C)
+    if into is None:
+        out, tot, off = torch.empty(N, cp // 4, H, W, 8, dtype=torch.bfloat16, device=x.device), 0, 0
+    else:
+        out, tot, off = into[0].data, into[0].cp, into[1]
+        if out.shape[0] != N or out.shape[2] != H or out.shape[3] != W:
+            raise ValueError('split_pack: the target activation has another shape')
+    with _timed('split_pack_kernel', 0, (4.0 * C + 4.0 * cp) * N * H * W):
+        check(_L().ynet_split_pack_f32(_ptr(x), N, C, H, W, x.stride(0) if N > 1 else C * H * W, _ptr(out), cp, tot, off,
+                                       _stream()), 'split_pack_f32')
+    _count()
+    return into[0] if into is not None else Split(out, C)
+
+
+def split_unpack(a):
+    out = torch.empty(a.N, a.C, a.H, a.W, dtype=torch.float32, device=a.data.device)
+    with _timed('split_unpack_kernel', 0, 8.0 * a.C * a.N * a.H * a.W):
+        check(_L().ynet_split_unpack_f32(_ptr(a.data), a.N, a.C, a.cp, a.H, a.W, _ptr(out), _stream()), 'split_unpack_f32')
+    _count()
+    return out
+
+
+def split_maxpool(a):
+    out = torch.empty(a.N, a.cp // 4, a.H // 2, a.W // 2, 8, dtype=torch.bfloat16, device=a.data.device)
+    with _timed('split_maxpool_kernel', 0, 5.0 * a.cp * a.N * a.H * a.W):
+        check(_L().ynet_split_maxpool2x2(_ptr(a.data), a.N, a.cp, a.H, a.W, _ptr(out), _stream()), 'split_maxpool2x2')
+    _count()
+    return Split(out, a.C)
+
+
+def split_upsample(a):
+    out = torch.empty(a.N, a.cp // 4, a.H * 2, a.W * 2, 8, dtype=torch.bfloat16, device=a.data.device)
+    with _timed('split_upsample_kernel', 0, 20.0 * a.cp * a.N * a.H * a.W):
+        check(_L().ynet_split_upsample2x(_ptr(a.data), a.N, a.cp, a.H, a.W, _ptr(out), _stream()), 'split_upsample2x')
+    _count()
+    return Split(out, a.C)
+
+
+def split_cat(parts, N=None):
+    """torch.cat along channels of Split activations (hi planes of all parts, then their lo planes).  Parts with a
+    smaller batch are tiled (``n % batch``: goal-major stacking)."""
+    N = max(p.N for p in parts) if N is None else N
+    his, los = [], []
+    for p in parts:
+        d = p.data if p.N == N else p.data.repeat(N // p.N, 1, 1, 1, 1)
+        k = d.shape[1] // 2
+        his.append(d[:, :k])
+        los.append(d[:, k:])
+    return Split(torch.cat(his + los, dim=1), sum(p.C for p in parts), [l for p in parts for l in p.layout])
+
+
+def split_pack_weights(weight_oihw, src_layouts):
+    """OIHW float32 weight (3x3 or 1x1), input channels = the concatenation of the sources' real channels.
+    src_layouts: per Split source its ``layout``.  Packed for the source pairs of ynet_tc_conv3x3_split: per source [W_hi | W_hi] over its
+    2 * sum(cp) stored channels, then W_lo over its sum(cp) hi channels."""
+    w = _req(weight_oihw, name='weight')
+    C_out, _, kh, kw = w.shape
+    w_hi = w.to(torch.bfloat16).to(torch.float32)
+    w_lo = w - w_hi                                   # rounded to bf16 by the packer: W = hi + lo to 2^-17
+    blocks, chans = [], []
+    c0 = 0
+    for layout in src_layouts:
+        tot = sum(cp for _, cp in layout)
+        a = torch.zeros(C_out, 2 * tot, kh, kw, dtype=torch.float32, device=w.device)
+        b = torch.zeros(C_out, tot, kh, kw, dtype=torch.float32, device=w.device)
+        o = 0
+        for C, cp in layout:
+            a[:, o:o + C] = w_hi[:, c0:c0 + C]
+            a[:, tot + o:tot + o + C] = w_hi[:, c0:c0 + C]
+            b[:, o:o + C] = w_lo[:, c0:c0 + C]
+            o += cp
+            c0 += C
+        blocks += [a, b]
+        chans += [2 * tot, tot]
+    if c0 != w.shape[1]:
+        raise ValueError(f'split_pack_weights: sources hold {c0} channels, the weight expects {w.shape[1]}')
+    return tc_pack_weights(torch.cat(blocks, dim=1).contiguous(), chans)
+
+
+def _split_src_array(sources, N):
+    arr = (_lib.TcSrc * (2 * len(sources)))()
+    for i, s in enumerate(sources):
+        for j, ch in enumerate((2 * s.cp, s.cp)):
+            e = arr[2 * i + j]
+            e.ptr = s.data.data_ptr()
+            e.channels_pad = ch
+            e.chunks_stored = ch // 8
+            e.batch_stride = 0 if (s.N == 1 and N > 1) else s.data.stride(0)
+            e.batch_mod = _tc_batch_mod(s, N)
+    return arr
+
+
+def tc_conv3x3_split(sources, packed_weight, bias_pad, C_out, relu, into=None):
+    """conv3x3(cat(sources)) + bias (+ReLU) on Split activations -> Split: three bf16 tcgen05 MMAs per product term.
+    into = (Split buffer, channel offset): write the result as that channel slice of a wider activation."""
+    if not 1 <= len(sources) <= 2:
+        raise ValueError('tc_conv3x3_split: one or two Split sources (concatenate more with split_cat)')
+    N = max(s.N for s in sources)
+    H, W = sources[0].H, sources[0].W
+    if any(s.H != H or s.W != W for s in sources):
+        raise ValueError('tc_conv3x3_split: sources must share the spatial size')
+    arr = _split_src_array(sources, N)
+    cpo = _pad16(C_out)
+    if into is None:
+        out, tot, off = torch.empty(N, cpo // 4, H, W, 8, dtype=torch.bfloat16, device=sources[0].data.device), 0, 0
+    else:
+        out, tot, off = into[0].data, into[0].cp, into[1]
+        if out.shape[0] != N or out.shape[2] != H or out.shape[3] != W:
+            raise ValueError('tc_conv3x3_split: the target activation has another shape')
+    cin = sum(s.cp for s in sources)
+    with _timed('tc_conv3x3_split_kernel', 3 * 2.0 * 9 * cin * C_out * H * W * N,
+                sum(4.0 * s.cp * min(s.N, N) for s in sources) * H * W + 4.0 * cpo * H * W * N,
+                tag=f'{cin}->{cpo}@{H}x{W} N={N}'):
+        check(_L().ynet_tc_conv3x3_split(arr, 2 * len(sources), N, H, W, _ptr(packed_weight), _ptr(bias_pad), C_out,
+                                         1 if relu else 0, _ptr(out), cpo, tot, off, 0, _stream()), 'tc_conv3x3_split')
+    _count()
+    return into[0] if into is not None else Split(out, C_out)
+
+
+def tc_conv1x1_split_f32(a, packed_weight, bias_pad, C_out):
+    """1x1 predictor on a Split activation -> float32 NCHW logits."""
+    out = torch.empty(a.N, C_out, a.H, a.W, dtype=torch.float32, device=a.data.device)
+    arr = _split_src_array([a], a.N)
+    with _timed('tc_conv_kernel<1x1,f32,split>', 3 * 2.0 * a.cp * C_out * a.H * a.W * a.N,
+                (4.0 * a.cp + 4.0 * C_out) * a.H * a.W * a.N):
+        check(_L().ynet_tc_conv1x1_f32(arr, 2, a.N, a.H, a.W, _ptr(packed_weight), _ptr(bias_pad), C_out, _ptr(out), 0,
+                                       _stream()), 'tc_conv1x1_f32')
+    _count()
+    return out
+
+
 def tc_pack_hoisted_weights(weight_oihw, parts):
     """Packed weights of a conv whose sources mix 3x3 inputs and hoisted partial sums.
 

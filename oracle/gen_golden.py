@@ -360,6 +360,46 @@ def gen_train(ns):
              **{'lastgrad/' + k: v for k, v in grads.items()})
 
 
+def gen_forward_batch(ns):
+    """The saliency forward of trainer.py:445-516 (``YNetTrainer._forward_batch``, unbound, on a stand-in ``self``):
+    logits of both decoders, both losses and the gradient of a fixed linear functional of the logits with respect to the
+    scene image (``set_input = ['scene', 'traj']``, no noise: the only configuration trainer.py:357-443 runs through)."""
+    if ns.trainer is None:
+        print('trainer not importable:', ns.trainer_error)
+        return
+    import types
+    c = dict(H=64, W=96, obs=5, pred=6, wps=[2, 5], B=3, resize=0.25, loss_scale=1000, kernlen=31, nsig=4)
+    m = build_ref_model(ns, c['obs'], c['pred'], len(c['wps']))
+    for p_ in m.parameters():
+        p_.requires_grad = False
+    sd0 = {k: v.detach().clone().numpy() for k, v in m.state_dict().items()}
+    scene = O.synthetic_scene(c['H'], c['W'], seed=0)
+    traj = torch.as_tensor(O.synthetic_tracks(c['B'], c['obs'] + c['pred'], c['H'], c['W'], seed=5), dtype=torch.float32)
+    size = int(4200 * c['resize'])
+    tmpl = torch.Tensor(ns.image_utils.create_dist_mat(size))
+    gt_tmpl = torch.Tensor(ns.image_utils.create_gaussian_heatmap_template(size=size, kernlen=c['kernlen'],
+                                                                           nsig=c['nsig'], normalize=False))
+    crit = torch.nn.BCEWithLogitsLoss()
+    me = types.SimpleNamespace(model=m, device='cpu')
+    fb = ns.trainer.YNetTrainer._forward_batch
+    img = scene.clone().unsqueeze(0).requires_grad_(True)
+    goal, trj = fb(me, img, traj, tmpl, gt_tmpl, crit, c['obs'], c['pred'], c['wps'], c['loss_scale'], 'cpu',
+                   ['scene', 'traj'], None, True)
+    g = torch.Generator().manual_seed(11)
+    r1 = torch.randn(goal.shape, generator=g)
+    r2 = torch.randn(trj.shape, generator=g)
+    ((goal * r1).sum() + (trj * r2).sum()).backward()
+    grad_maps = img.grad.detach().clone()
+    img2 = scene.clone().unsqueeze(0).requires_grad_(True)
+    gl, tl = fb(me, img2, traj, tmpl, gt_tmpl, crit, c['obs'], c['pred'], c['wps'], c['loss_scale'], 'cpu',
+                ['scene', 'traj'], None, False)
+    (gl + tl).backward()
+    save('forward_batch', scene=scene.numpy(), trajectory=traj.numpy(), template_size=size, cfg=np.array(repr(c)),
+         goal_map=goal.detach().numpy(), traj_map=trj.detach().numpy(), functional_seed=11,
+         grad_maps=grad_maps.numpy(), goal_loss=np.float32(gl.item()), traj_loss=np.float32(tl.item()),
+         grad_loss=img2.grad.detach().numpy(), **{'sd/' + k: v for k, v in sd0.items()})
+
+
 def main(only=None):
     torch.set_num_threads(1)     # reference's global-sum quirk depends on thread count (SURVEY 8)
     ns = ref_harness.load()
@@ -374,6 +414,7 @@ def main(only=None):
     gen_embed_semantic(ns)
     gen_evaluate(ns)
     gen_train(ns)
+    gen_forward_batch(ns)
     gen_preprocess()
 
 

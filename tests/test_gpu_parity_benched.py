@@ -106,7 +106,7 @@ def _decode_with_oracle_waypoints(ops, case, backend):
     return goal, trajs, ade, fde
 
 
-@pytest.mark.parametrize('backend', ['fp32', 'bf16'])
+@pytest.mark.parametrize('backend', ['fp32', 'bf16', 'bf16x3'])
 def test_full_width_416_decoder_with_oracle_waypoints(ops, full_case, backend):
     goal, trajs, ade, fde = _decode_with_oracle_waypoints(ops, full_case, backend)
     mid = full_case['mid']
@@ -117,12 +117,12 @@ def test_full_width_416_decoder_with_oracle_waypoints(ops, full_case, backend):
     fde_err = (fde.cpu() - full_case['fde']).abs().max().item()
     print(f'[{backend}] full width 416^2: goal logits rel {g_err:.2e}; decoded coordinates max |d| {coord_err:.4f} px '
           f'(mean {d.mean().item():.5f}); ADE diff {ade_err:.4f} px, FDE diff {fde_err:.5f} px (reported units)')
-    assert g_err < (1e-3 if backend == 'fp32' else 3e-2)
-    assert coord_err < (0.01 if backend == 'fp32' else BF16_COORD_TOL)
+    assert g_err < (1e-3 if backend != 'bf16' else 3e-2)
+    assert coord_err < (0.01 if backend != 'bf16' else BF16_COORD_TOL)
     assert ade_err < ADE_TOL and fde_err < ADE_TOL
 
 
-@pytest.mark.parametrize('backend', ['fp32', 'bf16'])
+@pytest.mark.parametrize('backend', ['fp32', 'bf16', 'bf16x3'])
 def test_full_width_416_forecast_batch_stage_by_stage(ops, full_case, backend):
     """The whole benchmarked body (sampling + k-means + CWS included) with the oracle's randoms, checked stage by stage.
 
@@ -165,6 +165,8 @@ def test_full_width_416_forecast_batch_stage_by_stage(ops, full_case, backend):
     print(f'[{backend} e2e] draws identical to the oracle\'s: {100 * same:.2f} %, mean displacement {disp:.4f} px')
     if backend == 'fp32':
         assert same > 0.995
+    elif backend == 'bf16x3':     # logits within ~1e-5 instead of 6e-7: about 1 % of the draws move by one raster bin
+        assert same > 0.98 and disp < 0.1
     else:
         assert disp < 4.0
     # (c) k-means on the product's own draws: kernel vs oracle, bit-exact
@@ -179,7 +181,7 @@ def test_full_width_416_forecast_batch_stage_by_stage(ops, full_case, backend):
     assert ade_err < 1.0
 
 
-@pytest.mark.parametrize('backend', ['fp32', 'bf16'])
+@pytest.mark.parametrize('backend', ['fp32', 'bf16', 'bf16x3'])
 def test_fixture_ind_long_decoder_with_reference_waypoints(ops, backend):
     """Live-reference fixture eval_ind_long_ttst_cws: the REFERENCE's waypoint samples through decode_trajectories;
     ADE (min over goals) and FDE must match the reference's within 0.05 px."""
@@ -205,7 +207,7 @@ def test_fixture_ind_long_decoder_with_reference_waypoints(ops, backend):
     print(f'[{backend}] fixture: ADE diff {ade_err:.4f}, FDE diff {fde_err:.5f}, best-trajectory max |d| {pred_err:.4f} '
           f'(reported px)')
     assert ade_err < ADE_TOL and fde_err < ADE_TOL
-    assert pred_err < (0.05 if backend == 'fp32' else 0.2)
+    assert pred_err < (0.05 if backend != 'bf16' else 0.2)
 
 
 def test_graph_replay_equals_eager_bf16(ops, full_case):
