@@ -379,6 +379,28 @@ int ynet_tc_rowconv3x3(const ynet_tc_src* srcs_host, int32_t n_src, const ynet_t
                        int32_t H, int32_t W, const void* packed_weight, const float* bias32, int32_t C_out, int32_t relu,
                        void* out_c8, int32_t C_out_pad, void* stream);
 int64_t ynet_tc_rowconv_softargmax_workspace_bytes(int32_t N, int32_t C_pred, int32_t W);
+/* The same with the waypoint channels of the trajectory decoder's input (evaluate.py:248-259: get_patch of the sampled
+ * waypoints, image_utils.py:40-63, and its AvgPool2d(2) level) taken STRAIGHT FROM THE DISTANCE TEMPLATE instead of being
+ * rasterised to HBM per image and read back: the kernel's TMA loads the window of every waypoint channel from bf16 C8
+ * planes of the template (a few MB, L2-resident, built once per template by ynet_tc_wp_template_c8) and the issuing
+ * thread zeroes the conv's padding pixels.  The waypoint source is the LAST 16-channel K block of the conv: channel c
+ * (n_ch <= 2) sits at K index 8 c -- pack the weights as two 8-channel sources -- and is bit-identical to the planes
+ * ynet_tc_rasterize_pyramid_c8 writes at that level (windows that leave the template read zero instead of clamping;
+ * the rasteriser's oob flag reports those).  n_src <= 2 tensor sources precede it.
+ *   ynet_tc_wp_template_c8: (th, tw) float32 template -> out_l0 (th, tw, 8) bf16, channel 0 = bf16(T), channels 1-7 zero;
+ *       out_l1 (4, th/2, tw/2, 8): plane 2 py + px at [i][j] = bf16(0.25 ((T[2i+py][2j+px] + T[2i+py][2j+px+1]) +
+ *       (T[2i+py+1][2j+px] + T[2i+py+1][2j+px+1]))), the AvgPool2d(2) of a window whose corner has parity (py, px). */
+typedef struct ynet_tc_wp_src {
+  const void* tmpl_c8;   /* out_l0 (level 0) or out_l1 (level 1) of ynet_tc_wp_template_c8                      */
+  const float* coords;   /* (N * n_ch, 2) float32 (x, y) at full resolution, rounded half-to-even like np.round */
+  int32_t th, tw;        /* size of the float32 template (even for level 1)                                     */
+  int32_t n_ch;          /* 1 or 2                                                                              */
+  int32_t level;         /* 0: the conv runs at the full resolution; 1: at half of it (2x2 average)             */
+} ynet_tc_wp_src;
+int ynet_tc_wp_template_c8(const float* tmpl, int32_t th, int32_t tw, void* out_l0, void* out_l1, void* stream);
+int ynet_tc_rowconv3x3_wp(const ynet_tc_src* srcs_host, int32_t n_src, const ynet_tc_src* partial_host,
+                          const ynet_tc_wp_src* wp_host, int32_t N, int32_t H, int32_t W, const void* packed_weight,
+                          const float* bias32, int32_t C_out, int32_t relu, void* out_c8, int32_t C_out_pad, void* stream);
 int ynet_tc_rowconv3x3_pred_softargmax(const ynet_tc_src* src_host, int32_t N, int32_t H, int32_t W,
                                        const void* packed_weight, const float* bias32, int32_t C_out, int32_t relu,
                                        const void* packed_pred_weight, const float* pred_bias, int32_t C_pred,

@@ -27,6 +27,11 @@ class TcSrc(Structure):
                 ('padded', c_int32), ('tap_mask', c_int32)]
 
 
+class TcWpSrc(Structure):
+    _fields_ = [('tmpl_c8', c_void_p), ('coords', c_void_p), ('th', c_int32), ('tw', c_int32), ('n_ch', c_int32),
+                ('level', c_int32)]
+
+
 class YnetError(RuntimeError):
     pass
 
@@ -98,6 +103,9 @@ _PROTOS = {
     'ynet_tc_rowconv_packed_weight_bytes': (_L, [_I]),
     'ynet_tc_rowconv_pack_weights': (c_int, [_P, _I, _I, _I, _P, _P]),
     'ynet_tc_rowconv3x3': (c_int, [POINTER(TcSrc), _I, POINTER(TcSrc), _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
+    'ynet_tc_wp_template_c8': (c_int, [_P, _I, _I, _P, _P, _P]),
+    'ynet_tc_rowconv3x3_wp': (c_int, [POINTER(TcSrc), _I, POINTER(TcSrc), POINTER(TcWpSrc), _I, _I, _I, _P, _P, _I, _I, _P, _I,
+                                      _P]),
     'ynet_tc_rowconv_softargmax_workspace_bytes': (_L, [_I, _I, _I]),
     'ynet_tc_rowconv3x3_pred_softargmax': (c_int, [POINTER(TcSrc), _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P, _L, _P]),
     'ynet_scene_preprocess_u8': (c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, POINTER(c_double),

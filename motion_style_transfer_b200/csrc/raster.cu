@@ -185,7 +185,8 @@ wp_pyramid_c8_kernel(const float* __restrict__ tmpl, int th, int tw, const float
     }
   }
   __syncthreads();
-  {  // level 0: 32 x 32, 4 pixels per thread
+  if (outs.p[0] != nullptr) {  // level 0: 32 x 32, 4 pixels per thread (null = level not wanted: the row-marching conv
+                               // gathers its waypoint planes itself, rowconv_tc.cu)
     uint4* o = outs.p[0] + (size_t)n * chunks * H * W;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -217,10 +218,12 @@ wp_pyramid_c8_kernel(const float* __restrict__ tmpl, int th, int tw, const float
       }
       const int h = H >> lvl, w = W >> lvl;
       const size_t pix = (size_t)((ty0 >> lvl) + y) * w + (tx0 >> lvl) + x;
-      uint4* o = outs.p[lvl] + (size_t)n * chunks * h * w;
-      o[pix] = pack8_bf16(f);
-      if (write_pad)
-        for (int k = 1; k < chunks; ++k) o[(size_t)k * h * w + pix] = zero;
+      if (outs.p[lvl] != nullptr) {
+        uint4* o = outs.p[lvl] + (size_t)n * chunks * h * w;
+        o[pix] = pack8_bf16(f);
+        if (write_pad)
+          for (int k = 1; k < chunks; ++k) o[(size_t)k * h * w + pix] = zero;
+      }
     }
   };
   if (n_levels <= 1) return;
@@ -252,6 +255,34 @@ wp_pyramid_c8_kernel(const float* __restrict__ tmpl, int th, int tw, const float
   }
 }
 
+
+// ---- the distance template as bf16 C8 planes (16 B per template pixel: channel 0 = value, 1-7 zero), so that the row-
+// marching conv's TMA can load a waypoint channel's window straight into its K-major operand chunk (rowconv_tc.cu):
+// level 0 as it is, level 1 as the four parity planes of the 2x2 average (same float32 arithmetic as the pyramid kernels)
+__global__ void __launch_bounds__(256)
+wp_template_c8_kernel(const float* __restrict__ tmpl, int th, int tw, uint4* __restrict__ l0, uint4* __restrict__ l1) {
+  const long long S = (long long)th * tw, S1 = (long long)(th / 2) * (tw / 2);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < S + 4 * S1; t += (long long)gridDim.x * blockDim.x) {
+    float v;
+    uint4* dst;
+    if (t < S) {
+      v = tmpl[t];
+      dst = l0 + t;
+    } else {
+      const long long r = t - S;
+      const int par = (int)(r / S1);
+      const long long q = r - par * S1;
+      const int i = (int)(q / (tw / 2)), j = (int)(q - (long long)i * (tw / 2));
+      const int y0 = min(2 * i + (par >> 1), th - 1), y1 = min(y0 + 1, th - 1);
+      const int x0 = min(2 * j + (par & 1), tw - 1), x1 = min(x0 + 1, tw - 1);
+      v = 0.25f * ((tmpl[(size_t)y0 * tw + x0] + tmpl[(size_t)y0 * tw + x1]) +
+                   (tmpl[(size_t)y1 * tw + x0] + tmpl[(size_t)y1 * tw + x1]));
+      dst = l1 + r;
+    }
+    const __nv_bfloat162 b = __floats2bfloat162_rn(v, 0.f);
+    *dst = make_uint4(*reinterpret_cast<const uint32_t*>(&b), 0u, 0u, 0u);
+  }
+}
 
 // ---- the same pyramid with 2x2-NEIGHBOURHOOD planes at the finest levels ---------------------------------------
 // The n_wp <= 2 waypoint channels leave six of the eight channels of the plane empty, and the conv spends nine MMAs per
@@ -554,9 +585,11 @@ int ynet_tc_rasterize_pyramid_c8(const float* tmpl, int32_t th, int32_t tw, cons
     for (int i = 0; i < 6; ++i) {
       o.p[i] = nullptr;
       if (i < n_levels) {
-        YNET_CHECK_ARG(outs_host[i] != nullptr, "null output level");
+        // a null level is skipped (plain layout only): ynet_tc_rowconv3x3_wp gathers the finest levels itself
+        YNET_CHECK_ARG(outs_host[i] != nullptr || (quad_levels == 0 && i < 5), "null output level");
         YNET_CHECK_ALIGN(outs_host[i], 16);
-        o.p[i] = reinterpret_cast<uint4*>(outs_host[i]) + (size_t)n0 * chunks * (H >> i) * (W >> i);
+        if (outs_host[i] != nullptr)
+          o.p[i] = reinterpret_cast<uint4*>(outs_host[i]) + (size_t)n0 * chunks * (H >> i) * (W >> i);
       }
     }
     dim3 grid(W / 32, H / 32, nn);
@@ -581,6 +614,19 @@ int ynet_tc_rasterize_pyramid_c8(const float* tmpl, int32_t th, int32_t tw, cons
 #undef YNET_WP_CASE
     YNET_LAUNCH_CHECK();
   }
+  return YNET_OK;
+}
+
+int ynet_tc_wp_template_c8(const float* tmpl, int32_t th, int32_t tw, void* out_l0, void* out_l1, void* stream) {
+  YNET_CHECK_ARG(tmpl && out_l0 && out_l1, "null pointer");
+  YNET_CHECK_ARG(th >= 2 && tw >= 2 && th % 2 == 0 && tw % 2 == 0, "template size must be even");
+  YNET_CHECK_ALIGN(out_l0, 16);
+  YNET_CHECK_ALIGN(out_l1, 16);
+  const long long total = 2LL * th * tw;
+  const long long blocks = (total + 255) / 256;
+  wp_template_c8_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, as_stream(stream)>>>(
+      tmpl, th, tw, reinterpret_cast<uint4*>(out_l0), reinterpret_cast<uint4*>(out_l1));
+  YNET_LAUNCH_CHECK();
   return YNET_OK;
 }
 

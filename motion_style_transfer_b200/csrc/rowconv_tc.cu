@@ -76,6 +76,11 @@ struct RcParams {
   int src_coff[3];             // first chunk slot of source s in the row buffer
   int src_bcast[3], src_mod[3];
   int zero_fill;               // some chunk slots are never written by TMA (K padding): zero the ring once
+  // waypoint source (ynet_tc_rowconv3x3_wp): the last K block is get_patch (image_utils.py:40-63) [+ one 2x2 AvgPool,
+  // evaluate.py:255-257] of the distance template, loaded by TMA straight from the template's bf16 C8 planes (L2-resident)
+  // instead of being rasterised to HBM per image and read back; channel c occupies chunk wp_coff + c (K index 8 c)
+  const float* wp_coords;      // (N * wp_nch, 2) = (x, y) at full resolution
+  int wp_nch, wp_level, wp_th, wp_tw, wp_coff;
   const uint4* part;           // hoisted partial sums (goal-loop hoisting, ynet_tc_conv3x3_hilo): bf16 C8, 4 chunks hi
   long long part_bs;           //   [+ 4 chunks lo], added by the epilogue before the activation; batch stride in uint4
   int part_mod, part_chunks;
@@ -161,6 +166,16 @@ __device__ __forceinline__ void rc_run(uint32_t tmem_base, uint32_t a_lo, uint32
       b += 3 * (RC_WBLK >> 4);
     }
   }
+}
+
+// Strip geometry of the WP kernels (ynet_tc_rowconv3x3_wp).  The waypoint K block comes from the TEMPLATE's planes, which
+// hold values where the conv's zero padding must be (x = -1, x = W).  TMA destinations are 128-byte (8-pixel) aligned,
+// so the first strip's window starts at x = -8 and the last strip's at x = W - 120: pixels 0-7 / 120-127 of those
+// windows lie outside the image and are written by a TMA load of zeros, the other 120 by a 120-pixel box of the template
+// (the tensor sources are zero-filled by their own out-of-bounds handling).  Interior strips: 128-pixel box, window
+// [126 s - 8, 126 s + 120).  The last strip overlaps its neighbours' windows; it alone writes the columns [W - 119, W).
+__device__ __forceinline__ int rc_wp_window(int s, int strips, int W) {
+  return s == 0 ? -8 : (s == strips - 1 ? W - 120 : RC_VW * s - 8);
 }
 
 // an INTERIOR input row (1 <= Y <= H - 2) whose running index g has g % 8 == POS.  bars = shared address of in_full[0];
@@ -269,7 +284,7 @@ __device__ __forceinline__ void rc_conv_issuer(const RcParams& p, uint32_t tmem_
       if (Y + 1 < H) mbar_wait(acc_empty + 8u * rc_slot(g + 1), (uint32_t)((((g + 1) >> 3) & 1) ^ 1), nullptr);
       mbar_wait(in_full + 8u * (uint32_t)stage, ph_in, nullptr);
       tc_fence_after();
-      // kernel rows kh_lo..kh_hi contribute (output row g + 1 - kh must exist).  The slots of rows g + 1, g, g - 1 are
+          // kernel rows kh_lo..kh_hi contribute (output row g + 1 - kh must exist).  The slots of rows g + 1, g, g - 1 are
       // consecutive except where the ring wraps: after kh = 0 when g % 8 == 7, after kh = 1 when g % 8 == 0.
       const int kh_lo = (Y + 1 < H) ? 0 : 1, kh_hi = (Y >= 1) ? 2 : 1;
       const int brk = (pos == RC_NS - 1) ? 1 : (pos == 0 ? 2 : 3);          // first kernel row of a second run
@@ -299,10 +314,14 @@ __device__ __forceinline__ void rc_conv_issuer(const RcParams& p, uint32_t tmem_
   }
 }
 
-template <bool FUSE>
+// WP: the LAST K block is the waypoint source (ynet_tc_rowconv3x3_wp, n_ch <= 2): mapw / mapw120 describe the template's
+// bf16 C8 planes with a 128- / 120-pixel box, mapz eight pixels of zeros.  A template parameter so that the plain kernels
+// carry none of its code.
+template <bool FUSE, bool WP = false>
 __global__ void __launch_bounds__(FUSE ? RC_THREADS_FUSED : RC_THREADS_PLAIN, FUSE ? 1 : 2)
 tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
-                  const __grid_constant__ CUtensorMap map2, const RcParams p) {
+                  const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap mapw,
+                  const __grid_constant__ CUtensorMap mapw120, const __grid_constant__ CUtensorMap mapz, const RcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -399,7 +418,23 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
           const int bm = p.src_mod[i];
           ns[i] = p.src_bcast[i] ? 0 : (bm > 0 ? n % bm : (bm < 0 ? n / (-bm) : n));
         }
-        const int c0 = 2 * (s * RC_VW - 1);                 // 8-byte elements: two per pixel
+        const int xw = WP ? rc_wp_window(s, p.strips, p.W) : s * RC_VW - 1;      // first pixel of the window
+        const int c0 = 2 * xw;                              // 8-byte elements: two per pixel
+        const int edge = WP ? (s == 0 ? 1 : (s == p.strips - 1 ? 2 : 0)) : 0;
+        int wrow[2] = {0, 0}, wcol[2] = {0, 0}, wpar[2] = {0, 0};
+        if (WP) {
+          // window of channel c in the template planes: level 0 T[yl + Y][xl + x]; level 1 the 2x2 average whose top-left
+          // corner is T[yl + 2Y][xl + 2x] = plane (yl & 1, xl & 1) at [(yl >> 1) + Y][(xl >> 1) + x]
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const size_t k = (size_t)n * p.wp_nch + min(c, p.wp_nch - 1);
+            const int yl = p.wp_th / 2 - __float2int_rn(__ldg(p.wp_coords + 2 * k + 1));     // half to even == np.round
+            const int xl = p.wp_tw / 2 - __float2int_rn(__ldg(p.wp_coords + 2 * k));
+            wpar[c] = p.wp_level ? ((yl & 1) * 2 + (xl & 1)) : 0;
+            wrow[c] = p.wp_level ? (yl >> 1) : yl;
+            wcol[c] = 2 * (p.wp_level ? (xl >> 1) : xl) + c0;
+          }
+        }
         for (int Y = 0; Y < p.H; ++Y) {
           mbar_wait(smem_u32(&in_empty[stage]), phase ^ 1, nullptr);
           const uint32_t fb = smem_u32(&in_full[stage]);
@@ -408,6 +443,22 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
           tma_load_4d(dst + (uint32_t)(p.src_coff[0] * RC_CHUNK_BYTES), &map0, fb, c0, Y, 0, ns[0]);
           if (p.n_src > 1) tma_load_4d(dst + (uint32_t)(p.src_coff[1] * RC_CHUNK_BYTES), &map1, fb, c0, Y, 0, ns[1]);
           if (p.n_src > 2) tma_load_4d(dst + (uint32_t)(p.src_coff[2] * RC_CHUNK_BYTES), &map2, fb, c0, Y, 0, ns[2]);
+          if (WP) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              if (c >= p.wp_nch) break;
+              const uint32_t d = dst + (uint32_t)((p.wp_coff + c) * RC_CHUNK_BYTES);
+              if (edge == 0) {
+                tma_load_4d(d, &mapw, fb, wcol[c], wrow[c] + Y, wpar[c], 0);
+              } else if (edge == 1) {        // window pixels 0-7 = x in [-8, 0): zeros; 8-127 = x in [0, 120)
+                tma_load_4d(d, &mapz, fb, 0, 0, 0, 0);
+                tma_load_4d(d + 128u, &mapw120, fb, wcol[c] + 16, wrow[c] + Y, wpar[c], 0);
+              } else {                       // window pixels 0-119 = x in [W - 120, W); 120-127 = x >= W: zeros
+                tma_load_4d(d, &mapw120, fb, wcol[c], wrow[c] + Y, wpar[c], 0);
+                tma_load_4d(d + 1920u, &mapz, fb, 0, 0, 0, 0);
+              }
+            }
+          }
           if (++stage == NSTG) {
             stage = 0;
             phase ^= 1;
@@ -439,8 +490,10 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     const int H = p.H;
     for (long long item = blockIdx.x; item < p.items; item += gridDim.x, g0 += H) {
       const int n = (int)(item / p.strips), s = (int)(item - (long long)n * p.strips);
-      const int x = s * RC_VW + m;
-      const bool live = m < RC_VW && x < p.W;
+      const int x = (WP ? rc_wp_window(s, p.strips, p.W) + 1 : s * RC_VW) + m;
+      // WP: the columns [W - 119, W) belong to the last strip alone (an interior strip sees template values, not zeros,
+      // beyond x = W - 1)
+      const bool live = m < RC_VW && x < p.W && (!WP || (x >= 0 && (s == p.strips - 1 || x < p.W - 119)));
       const int npart = p.part_mod > 0 ? n % p.part_mod : (p.part_mod < 0 ? n / (-p.part_mod) : n);
       const uint4* part_px = p.part + (size_t)npart * p.part_bs + x;
       const bool has_part = p.part != nullptr && live;
@@ -659,7 +712,7 @@ rc_pack_weights_kernel(const float* __restrict__ w, int C_out, int C_in, int kb,
 }
 
 static int rc_launch(const char* who, bool fuse, const ynet_tc_src* srcs, int n_src, const ynet_tc_src* partial, int N,
-                     int H, int W, RcParams& p, void* stream) {
+                     int H, int W, RcParams& p, void* stream, const ynet_tc_wp_src* wp = nullptr) {
   if (!(srcs && n_src >= 1 && n_src <= 3)) {
     set_error("%s: 1..3 conv sources", who);
     return YNET_E_INVALID;
@@ -718,6 +771,54 @@ static int rc_launch(const char* who, bool fuse, const ynet_tc_src* srcs, int n_
     stored_total += stored;
   }
   for (int i = n_src; i < 3; ++i) maps[i] = maps[0];
+  CUtensorMap mapw = maps[0], mapw120 = maps[0], mapz = maps[0];
+  if (wp != nullptr) {
+    if (fuse || !(wp->tmpl_c8 && wp->coords) || reinterpret_cast<uintptr_t>(wp->tmpl_c8) % 16 != 0 || wp->n_ch < 1 ||
+        wp->n_ch > 2 || wp->level < 0 || wp->level > 1 || n_src > 2 || wp->th < (H << wp->level) ||
+        wp->tw < (W << wp->level) || (wp->level == 1 && ((wp->th | wp->tw) & 1)) || W < 120) {
+      set_error("%s: waypoint source: 1 or 2 channels, level 0 or 1, (even-sized) template at least as large as the "
+                "full-resolution image, W >= 120", who);
+      return YNET_E_INVALID;
+    }
+    static void* zeros = nullptr;              // 128 bytes of zeros: the conv's padding pixels of the edge strips
+    if (zeros == nullptr) {
+      cudaError_t ze = cudaMalloc(&zeros, 256);
+      if (ze == cudaSuccess) ze = cudaMemset(zeros, 0, 256);
+      if (ze != cudaSuccess) return cuda_fail(ze, who);
+    }
+    // level 0: planes (1, th, tw); level 1: the four parity planes (4, th / 2, tw / 2) of ynet_tc_wp_template_c8
+    const cuuint64_t tH = (cuuint64_t)(wp->th >> wp->level), tW = (cuuint64_t)(wp->tw >> wp->level);
+    const cuuint64_t dims[4] = {tW * 2, tH, wp->level ? 4u : 1u, 1};
+    const cuuint64_t strides[3] = {tW * 16, tH * tW * 16, (wp->level ? 4u : 1u) * tH * tW * 16};
+    const cuuint32_t box[4] = {(cuuint32_t)RC_M * 2, 1, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&mapw, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(wp->tmpl_c8), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const cuuint32_t box120[4] = {120 * 2, 1, 1, 1};
+    if (r == CUDA_SUCCESS)
+      r = encode(&mapw120, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(wp->tmpl_c8), dims, strides, box120, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const cuuint64_t zdims[4] = {16, 1, 1, 1};
+    const cuuint64_t zstr[3] = {128, 128, 128};
+    const cuuint32_t zbox[4] = {16, 1, 1, 1};
+    if (r == CUDA_SUCCESS)
+      r = encode(&mapz, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, zeros, zdims, zstr, zbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("%s: cuTensorMapEncodeTiled failed (%d) for the template planes (%d x %d)", who, (int)r, wp->th, wp->tw);
+      return YNET_E_CUDA;
+    }
+    p.wp_coords = wp->coords;
+    p.wp_nch = wp->n_ch;
+    p.wp_level = wp->level;
+    p.wp_th = wp->th;
+    p.wp_tw = wp->tw;
+    p.wp_coff = chunks;
+    chunks += 2;                 // one 16-channel K block: channel c = K index 8 c (chunk wp_coff + c), the rest zero
+    stored_total += wp->n_ch;
+  }
   if (chunks / 2 > RC_MAX_KB) {
     set_error("%s: more than %d input channels", who, RC_MAX_KB * 16);
     return YNET_E_UNSUPPORTED;
@@ -743,7 +844,7 @@ static int rc_launch(const char* who, bool fuse, const ynet_tc_src* srcs, int n_
   p.W = W;
   p.kb = chunks / 2;
   p.chunks = chunks;
-  p.strips = ceil_div(W, RC_VW);
+  p.strips = (wp != nullptr) ? 2 + ceil_div(tmax(0, W - 238), RC_VW) : ceil_div(W, RC_VW);     // WP: see rc_wp_window
   p.items = (long long)N * p.strips;
   p.row_bytes = p.chunks * RC_CHUNK_BYTES;
   const size_t smem = (size_t)p.kb * 3 * RC_WBLK + (size_t)(fuse ? RC_STAGES_FUSED : RC_STAGES_PLAIN) * p.row_bytes + 1024 +
@@ -751,6 +852,8 @@ static int rc_launch(const char* who, bool fuse, const ynet_tc_src* srcs, int n_
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_rowconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc_rowconv_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(tc_rowconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, who);
@@ -765,9 +868,12 @@ static int rc_launch(const char* who, bool fuse, const ynet_tc_src* srcs, int n_
   const long long grid = tmin<long long>(p.items, (long long)sm_count() * per_sm);
   cudaStream_t st = as_stream(stream);
   if (fuse)
-    tc_rowconv_kernel<true><<<(unsigned)grid, RC_THREADS_FUSED, smem, st>>>(maps[0], maps[1], maps[2], p);
+    tc_rowconv_kernel<true><<<(unsigned)grid, RC_THREADS_FUSED, smem, st>>>(maps[0], maps[1], maps[2], mapw, mapw120, mapz, p);
   else
-    tc_rowconv_kernel<false><<<(unsigned)grid, RC_THREADS_PLAIN, smem, st>>>(maps[0], maps[1], maps[2], p);
+    if (wp != nullptr)
+      tc_rowconv_kernel<false, true><<<(unsigned)grid, RC_THREADS_PLAIN, smem, st>>>(maps[0], maps[1], maps[2], mapw, mapw120, mapz, p);
+    else
+      tc_rowconv_kernel<false><<<(unsigned)grid, RC_THREADS_PLAIN, smem, st>>>(maps[0], maps[1], maps[2], mapw, mapw120, mapz, p);
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) return cuda_fail(le, who);
   return YNET_OK;
@@ -814,6 +920,25 @@ int ynet_tc_rowconv3x3(const ynet_tc_src* srcs, int32_t n_src, const ynet_tc_src
   p.out = reinterpret_cast<__nv_bfloat16*>(out_c8);
   p.out_chunks = C_out_pad / 8;
   return rc_launch("ynet_tc_rowconv3x3", false, srcs, n_src, partial, N, H, W, p, stream);
+}
+
+int ynet_tc_rowconv3x3_wp(const ynet_tc_src* srcs, int32_t n_src, const ynet_tc_src* partial, const ynet_tc_wp_src* wp,
+                          int32_t N, int32_t H, int32_t W, const void* packed_weight, const float* bias32, int32_t C_out,
+                          int32_t relu, void* out_c8, int32_t C_out_pad, void* stream) {
+  YNET_CHECK_ARG(packed_weight && bias32 && wp && (out_c8 || N == 0), "null pointer");
+  YNET_CHECK_ARG(C_out > 0 && C_out <= RC_CO && C_out_pad % 16 == 0 && C_out_pad >= C_out && C_out_pad <= RC_CO, "C_out <= 32");
+  YNET_CHECK_ARG(n_src <= 2, "at most two tensor sources next to the waypoint source");
+  YNET_CHECK_ALIGN(packed_weight, 16);
+  YNET_CHECK_ALIGN(out_c8, 16);
+  RcParams p;
+  memset(&p, 0, sizeof(p));
+  p.w96 = reinterpret_cast<const unsigned char*>(packed_weight);
+  p.bias = bias32;
+  p.relu = relu & 1;
+  p.pad_out = (relu & 2) ? 1 : 0;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out_c8);
+  p.out_chunks = C_out_pad / 8;
+  return rc_launch("ynet_tc_rowconv3x3_wp", false, srcs, n_src, partial, N, H, W, p, stream, wp);
 }
 
 int64_t ynet_tc_rowconv_softargmax_workspace_bytes(int32_t N, int32_t C_pred, int32_t W) {

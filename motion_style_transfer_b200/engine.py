@@ -527,16 +527,34 @@ class YNetEngineTC(YNetEngine):
             out.append(self._partial(decoder.decoder[i][0], f'{key}.decoder.{i}.0', skip, c_up))
         return out
 
+    # The waypoint planes of the levels whose decoder.i.0 runs in the row-marching kernel are gathered by that kernel from
+    # the (L2-resident) distance template instead of being written by the rasteriser and read back (16 B/px each way).
+    wp_gather = os.environ.get('YNET_WP_GATHER', '1') == '1'
+
+    def _wp_gather_levels(self, dec, n_levels, n_wp):
+        if not (self.wp_gather and self.rowconv and self.hoist and n_wp <= 2 and self.im2col_levels == 0):
+            return 0
+        lazy = 0
+        for lvl in range(min(2, n_levels - 1)):
+            i = n_levels - 2 - lvl
+            if dec.decoder[i][0].weight.shape[0] > 32 or ops._pad16(dec.upsample_conv[i].weight.shape[0]) + 16 > 64:
+                break
+            lazy = lvl + 1
+        return lazy
+
     def _tconv_hoisted_row(self, module, key, up, partial, pyr_level, c_feat):
         """The same through the row-marching kernel: conv sources [up, waypoint planes] side by side on the K axis, the
         hoisted partial added in fp32 by the epilogue (no identity-weight MMAs)."""
         srcs = [up, pyr_level]
         ver = (module.weight._version, module.weight.data_ptr(), tuple(s.K_pad for s in srcs), c_feat,
-               _bias_version(module))
+               _bias_version(module), isinstance(pyr_level, ops.WpPlanes))
         hit = self._wcache.get(key + '#rowhoist')
         if hit is None or hit[0] != ver:
             w = module.weight.detach()
-            parts = [(0, up.C, up.K_pad), (up.C + c_feat, up.C + c_feat + pyr_level.C, pyr_level.K_pad)]
+            if isinstance(pyr_level, ops.WpPlanes):      # channel c of the template-loaded planes sits at K index 8 c
+                parts = [(0, up.C, up.K_pad)] + pyr_level.weight_parts(up.C + c_feat)
+            else:
+                parts = [(0, up.C, up.K_pad), (up.C + c_feat, up.C + c_feat + pyr_level.C, pyr_level.K_pad)]
             bias = torch.zeros(32, dtype=torch.float32, device=w.device)
             if module.bias is not None:
                 bias[:w.shape[0]] = module.bias.detach()
@@ -550,6 +568,8 @@ class YNetEngineTC(YNetEngine):
                 and ops.tc_rowconv_supported([up, pyr_level], module.weight.shape[0])
                 and partial.C_pad in (32, 64) and partial.H == up.H):
             return self._tconv_hoisted_row(module, key, up, partial, pyr_level, c_feat)
+        if isinstance(pyr_level, ops.WpPlanes):      # not taken by the row kernel after all: write the planes
+            pyr_level = pyr_level.materialize()
         layout, srcs, c = [], [], 0
         if up is not None:
             layout.append(('conv', (0, up.C)))
@@ -620,7 +640,8 @@ class YNetEngineTC(YNetEngine):
             quad = min(self.quad_levels, len(feats)) if (self.hoist and n_wp <= 2) else 0
             if self.rowconv and quad and dec.decoder[len(feats) - 2][0].weight.shape[0] <= 32:
                 quad = 0      # the finest level's input conv runs in the row-marching kernel, which takes plain planes
-            pyr = ops.tc_rasterize_pyramid(template, wp, nb * G, n_wp, H, W, len(feats), quad_levels=quad)
+            pyr = ops.tc_rasterize_pyramid(template, wp, nb * G, n_wp, H, W, len(feats), quad_levels=quad,
+                                           lazy_levels=0 if quad else self._wp_gather_levels(dec, len(feats), n_wp))
             if self.hoist and n_wp <= 3:
                 for lvl in range(min(self.im2col_levels, len(pyr))):
                     pyr[lvl] = ops.tc_rasterize_im2col(template, wp, nb * G, n_wp, H, W, lvl)

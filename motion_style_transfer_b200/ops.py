@@ -696,7 +696,50 @@ def tc_quad_weights(weight_oihw, c0, n_ch):
     return q
 
 
-def tc_rasterize_pyramid(template, coords, n_img, n_ch, H, W, n_levels, slot=0, quad_levels=0):
+_wp_template_cache = {}
+
+
+def tc_wp_template(template):
+    """bf16 C8 planes of the distance template for the row-marching conv's waypoint source (ynet_tc_wp_template_c8):
+    (level-0 planes (th, tw, 8), level-1 parity planes (4, th/2, tw/2, 8)); built once per template tensor."""
+    key = (template.data_ptr(), template._version, tuple(template.shape), template.device)
+    hit = _wp_template_cache.get(key)
+    if hit is None:
+        th, tw = template.shape
+        l0 = torch.empty(th, tw, 8, dtype=torch.bfloat16, device=template.device)
+        l1 = torch.empty(4, th // 2, tw // 2, 8, dtype=torch.bfloat16, device=template.device)
+        check(_L().ynet_tc_wp_template_c8(_ptr(template), th, tw, _ptr(l0), _ptr(l1), _stream()), 'tc_wp_template_c8')
+        _count()
+        if len(_wp_template_cache) > 8:
+            _wp_template_cache.clear()
+        hit = _wp_template_cache[key] = (l0, l1, template)       # (keeps the keyed tensor alive: no pointer reuse)
+    return hit[0], hit[1]
+
+
+class WpPlanes:
+    """Level ``level`` (0 or 1) of a waypoint pyramid that is NOT materialised: the row-marching conv loads it straight
+    from the distance template's bf16 planes (ynet_tc_rowconv3x3_wp).  Stands where the C8 planes of that level would:
+    (N, n_ch <= 2 channels, H, W) at the level's resolution, one 16-channel K block with channel c at K index 8 c."""
+
+    __slots__ = ('template', 'coords', 'N', 'C', 'level', 'H', 'W', 'planes')
+    rep, pad, center, taps, K_pad, C_pad = 1, 0, False, 0, 16, 8
+
+    def __init__(self, template, coords, N, C, level, H, W):
+        self.template, self.coords, self.N, self.C, self.level, self.H, self.W = template, coords, N, C, level, H, W
+        self.planes = tc_wp_template(template)[level]
+
+    def weight_parts(self, c0):
+        """tc_rowconv_pack_weights_cat parts of this source: its channels are input channels [c0, c0 + C) of the conv."""
+        return [(c0, c0 + 1, 16)] if self.C == 1 else [(c0, c0 + 1, 8), (c0 + 1, c0 + 2, 8)]
+
+    def materialize(self):
+        """The C8 planes of this level (what tc_rasterize_pyramid would have written)."""
+        return tc_rasterize_pyramid(self.template, self.coords, self.N, self.C, self.H << self.level, self.W << self.level,
+                                    self.level + 1, only_level=self.level)[self.level]
+
+
+def tc_rasterize_pyramid(template, coords, n_img, n_ch, H, W, n_levels, slot=0, quad_levels=0, lazy_levels=0,
+                         only_level=None):
     """get_patch + AvgPool pyramid of ``n_img x n_ch`` waypoint coordinates written straight as bf16 C8 planes
     (image_utils.py:40-63 + evaluate.py:255-257).  Returns n_levels C8 (n_img, ONE 8-channel plane, H>>l, W>>l):
     16 B per pixel; a conv pads the K block to 16 channels through the TMA zero fill (``C8.K_pad``).
@@ -709,17 +752,22 @@ def tc_rasterize_pyramid(template, coords, n_img, n_ch, H, W, n_levels, slot=0, 
     if coords.shape[0] != n_img * n_ch:
         raise ValueError(f'tc_rasterize_pyramid: expected {n_img * n_ch} coordinates, got {coords.shape[0]}')
     # n_ch <= 8 channels fit ONE 8-channel plane; the conv's TMA zero-fills the other plane of the 16-channel K block
-    bufs = [torch.empty(n_img, 1, H >> l, W >> l, 8, dtype=torch.bfloat16, device=template.device)
+    # lazy_levels (<= 2, n_ch <= 2): the finest levels come back as WpPlanes (gathered inside the row-marching conv)
+    # and are not written; only_level: write that level alone
+    lazy_levels = lazy_levels if (n_ch <= 2 and template.shape[0] % 2 == 0 and template.shape[1] % 2 == 0) else 0
+    skip = [(l < lazy_levels) or (only_level is not None and l != only_level) for l in range(n_levels)]
+    bufs = [None if skip[l] else torch.empty(n_img, 1, H >> l, W >> l, 8, dtype=torch.bfloat16, device=template.device)
             for l in range(n_levels)]
     write_pad = 0
-    outs = (ctypes.c_void_p * n_levels)(*[b.data_ptr() for b in bufs])
-    S = sum((H >> l) * (W >> l) for l in range(n_levels))
+    outs = (ctypes.c_void_p * n_levels)(*[None if b is None else b.data_ptr() for b in bufs])
+    S = sum((H >> l) * (W >> l) for l in range(n_levels) if not skip[l])
     with _timed('wp_pyramid_c8_kernel', 0, 16.0 * S * n_img):
         check(_L().ynet_tc_rasterize_pyramid_c8(_ptr(template), template.shape[0], template.shape[1], _ptr(coords), n_img,
                                                 n_ch, H, W, n_levels, outs, 8, write_pad, quad_levels, None, _stream()),
               'tc_rasterize_pyramid_c8')
     _count()
-    return [C8(b, 4 * n_ch, taps=TAPS_QUAD) if l < quad_levels else C8(b, n_ch) for l, b in enumerate(bufs)]
+    return [(WpPlanes(template, coords, n_img, n_ch, l, H >> l, W >> l) if l < lazy_levels else None) if b is None
+            else (C8(b, 4 * n_ch, taps=TAPS_QUAD) if l < quad_levels else C8(b, n_ch)) for l, b in enumerate(bufs)]
 
 
 def tc_pad_replicate(a):
@@ -1191,7 +1239,9 @@ def tc_rowconv_supported(a, C_out):
     srcs = a if isinstance(a, (list, tuple)) else [a]
     if not (1 <= len(srcs) <= 3) or C_out > 32:
         return False
-    for s in srcs:
+    for i, s in enumerate(srcs):
+        if isinstance(s, WpPlanes) and i == len(srcs) - 1 and 1 <= i <= 2 and s.W >= 120:
+            continue                 # loaded from the template planes: last source, behind one or two tensor sources
         if not isinstance(s, C8) or s.pad or s.center or s.taps:
             return False
     return (sum(s.K_pad for s in srcs) <= 64 and srcs[0].H >= 2
@@ -1237,6 +1287,7 @@ def tc_rowconv3x3(a, packed_weight, bias32, C_out, relu, pad_out=False, partial=
     """conv3x3 + bias (+ ReLU) with C_out <= 32 of one plain C8 source or a list of <= 3 (= channel concat) -> C8
     (see ynet_tc_rowconv3x3).  ``partial``: hoisted partial sums (tc_conv3x3_hilo output) added before the activation."""
     srcs = list(a) if isinstance(a, (list, tuple)) else [a]
+    wp = srcs.pop() if isinstance(srcs[-1], WpPlanes) else None      # waypoint planes gathered in the kernel
     N = max(s.N for s in srcs + ([partial] if partial is not None else []))
     H, W = srcs[0].H, srcs[0].W
     cp = _pad16(C_out)
@@ -1248,12 +1299,22 @@ def tc_rowconv3x3(a, packed_weight, bias32, C_out, relu, pad_out=False, partial=
         parr = _rowconv_srcs([partial], N)
         parr[0].channels_pad = partial.C_pad
         in_bytes += 2.0 * partial.C_pad * min(partial.data.shape[0], N) * H * W
-    k_pad = sum(s.K_pad for s in srcs)
-    tag = f'{k_pad}{"+P" if partial is not None else ""}->{cp}@{H}x{W} N={N}'
-    with _timed('tc_rowconv_kernel', 2.0 * 9 * sum(s.C for s in srcs) * C_out * H * W * N,
+    k_pad = sum(s.K_pad for s in srcs) + (16 if wp is not None else 0)
+    tag = f'{k_pad}{"+P" if partial is not None else ""}{"+W" if wp is not None else ""}->{cp}@{H}x{W} N={N}'
+    with _timed('tc_rowconv_kernel', 2.0 * 9 * (sum(s.C for s in srcs) + (wp.C if wp is not None else 0)) * C_out * H * W * N,
                 in_bytes + 2.0 * cp * H * W * N, tag=tag):
-        check(_L().ynet_tc_rowconv3x3(_rowconv_srcs(srcs, N), len(srcs), parr, N, H, W, _ptr(packed_weight), _ptr(bias32),
-                                      C_out, (1 if relu else 0) | (2 * po), _ptr(out), cp, _stream()), 'tc_rowconv3x3')
+        if wp is None:
+            check(_L().ynet_tc_rowconv3x3(_rowconv_srcs(srcs, N), len(srcs), parr, N, H, W, _ptr(packed_weight),
+                                          _ptr(bias32), C_out, (1 if relu else 0) | (2 * po), _ptr(out), cp, _stream()),
+                  'tc_rowconv3x3')
+        else:
+            if wp.N != N or wp.H != H or wp.W != W:
+                raise ValueError('tc_rowconv3x3: the waypoint planes cover another batch / resolution')
+            w = _lib.TcWpSrc(wp.planes.data_ptr(), wp.coords.data_ptr(), wp.template.shape[0], wp.template.shape[1],
+                             wp.C, wp.level)
+            check(_L().ynet_tc_rowconv3x3_wp(_rowconv_srcs(srcs, N), len(srcs), parr, ctypes.byref(w), N, H, W,
+                                             _ptr(packed_weight), _ptr(bias32), C_out, (1 if relu else 0) | (2 * po),
+                                             _ptr(out), cp, _stream()), 'tc_rowconv3x3_wp')
     _count()
     return C8(out, C_out, 1, False, po)
 

@@ -165,3 +165,44 @@ def test_rowconv_multi_source_with_hoisted_partial(ops):
     packed3 = ops.tc_rowconv_pack_weights_cat(w3.cuda(), [(0, 16, 16), (16, 24, a3.K_pad), (24, 26, a_wp.K_pad)])
     out3 = ops.tc_rowconv3x3([a_up, a3, a_wp], packed3, torch.zeros(32).cuda(), 24, False)
     assert rel_err(ops.tc_unpack(out3).cpu().numpy(), ref3.numpy()) < 5e-3
+
+
+@pytest.mark.parametrize('n_wp,level,H0,W0,N', [(2, 0, 64, 160, 3), (2, 1, 64, 288, 3), (1, 0, 32, 416, 2), (1, 1, 96, 480, 2),
+                                                (2, 0, 416, 416, 2), (2, 1, 416, 416, 2), (2, 0, 32, 128, 2), (2, 0, 32, 256, 2), (1, 1, 64, 512, 2)])
+def test_rowconv_gathered_waypoint_planes_bit_exact(ops, n_wp, level, H0, W0, N):
+    """ynet_tc_rowconv3x3_wp: the waypoint planes (get_patch, image_utils.py:40-63, + AvgPool2d(2), evaluate.py:255-257)
+    loaded by the kernel's TMA from the distance template's bf16 planes == the same conv reading the rasterised planes, bit for bit;
+    coordinates near the image border put zero-padded / clamped pixels in every strip."""
+    torch.manual_seed(5)
+    H, W = H0 >> level, W0 >> level
+    tmpl = ops.create_dist_template(3 * max(H0, W0), 'cuda')
+    coords = torch.stack([torch.rand(N * n_wp) * (W0 - 1), torch.rand(N * n_wp) * (H0 - 1)], 1)
+    coords[0] = torch.tensor([0.5, 1.5])                       # half-to-even rounding, window against the template edge
+    coords[-1] = torch.tensor([W0 - 1.0, H0 - 1.0])
+    coords = coords.cuda().contiguous()
+    planes = ops.tc_rasterize_pyramid(tmpl, coords, N, n_wp, H0, W0, level + 1)[level]
+    lazy = ops.tc_rasterize_pyramid(tmpl, coords, N, n_wp, H0, W0, level + 1, lazy_levels=level + 1)[level]
+    assert isinstance(lazy, ops.WpPlanes) and (lazy.H, lazy.W, lazy.N, lazy.C) == (H, W, N, n_wp)
+    # more than two waypoint channels are not gathered in the kernel: the planes are written as before
+    c3 = torch.rand(N * 3, 2).cuda() * 20
+    assert isinstance(ops.tc_rasterize_pyramid(tmpl, c3, N, 3, H0, W0, 2, lazy_levels=2)[0], ops.C8)
+    assert torch.equal(lazy.materialize().data, planes.data)
+    up = ops.tc_pack(bf16_exact(torch.randn(N, 16, H, W)).cuda())
+    w = bf16_exact(torch.randn(32, 16 + n_wp, 3, 3) * 0.1)
+    b = torch.randn(32) * 0.1
+    packed = ops.tc_rowconv_pack_weights_cat(w.cuda(), [(0, 16, 16), (16, 16 + n_wp, 16)])
+    packed_l = ops.tc_rowconv_pack_weights_cat(w.cuda(), [(0, 16, 16)] + lazy.weight_parts(16))    # channel c at K index 8 c
+    ref = ops.tc_rowconv3x3([up, planes], packed, _bias32(b), 32, True)
+    got = ops.tc_rowconv3x3([up, lazy], packed_l, _bias32(b), 32, True)
+    torch.cuda.synchronize()
+    assert torch.equal(got.data, ref.data)
+    # against torch on the float32 maps (bf16 operands, fp32 accumulation)
+    wmap = ops.tc_unpack(planes).cpu()
+    full = F.relu(F.conv2d(torch.cat([ops.tc_unpack(up).cpu(), wmap], 1), w, b, padding=1))
+    assert rel_err(ops.tc_unpack(got).cpu().numpy(), full.numpy()) < 5e-3
+    # with the hoisted partial sums and a second tensor source in front (decoder.i.0 of the trajectory decoder)
+    feat = ops.tc_pack(bf16_exact(torch.relu(torch.randn(N, 32, H, W))).cuda())
+    part = ops.tc_conv3x3_hilo([feat], ops.tc_pack_weights(bf16_exact(torch.randn(32, 32, 3, 3) * 0.05).cuda(), [32]), 32, False)
+    ref2 = ops.tc_rowconv3x3([up, planes], packed, _bias32(b), 32, True, pad_out=True, partial=part)
+    got2 = ops.tc_rowconv3x3([up, lazy], packed_l, _bias32(b), 32, True, pad_out=True, partial=part)
+    assert torch.equal(got2.data, ref2.data)

@@ -69,3 +69,23 @@ if MODE in ('both', 'l2'):
     S2 = HW * HW * nb * G
     timeit('row conv [up|P|wp] -> 32', lambda: ops.tc_rowconv3x3([up, wpl], packed2, bias, 32, True, partial=part),
            2.0 * 9 * 18 * 32 * S2, (32.0 + 16.0 + 64.0) * S2)
+
+if MODE in ('wp',):
+    # the same with the waypoint planes gathered inside the kernel (ynet_tc_rowconv3x3_wp)
+    G = 20
+    nb = N // G
+    up = ops.tc_pack(torch.randn(nb * G, 16, HW, HW, device='cuda'))
+    tmpl = ops.create_dist_template(int(2.5 * HW), 'cuda')
+    coords = (torch.rand(nb * G * 2, 2, device='cuda') * (HW - 1)).contiguous()
+    pyr = ops.tc_rasterize_pyramid(tmpl, coords, nb * G, 2, HW, HW, 1)
+    lazy = ops.tc_rasterize_pyramid(tmpl, coords, nb * G, 2, HW, HW, 1, lazy_levels=1)
+    feat = ops.tc_pack(torch.relu(torch.randn(nb, 32, HW, HW, device='cuda')))
+    w2 = torch.randn(32, 50, 3, 3, device='cuda') * 0.1
+    part = ops.tc_conv3x3_hilo([feat], ops.tc_pack_weights(w2[:, 16:48].contiguous(), [32]), 32, False).repeat_interleave(G)
+    packed2 = ops.tc_rowconv_pack_weights_cat(w2, [(0, 16, 16), (48, 50, 16)])
+    S2 = HW * HW * nb * G
+    timeit('row conv [up|P|wp planes]', lambda: ops.tc_rowconv3x3([up, pyr[0]], packed2, bias, 32, True, partial=part),
+           2.0 * 9 * 18 * 32 * S2, (32.0 + 16.0 + 64.0) * S2)
+    packed3 = ops.tc_rowconv_pack_weights_cat(w2, [(0, 16, 16)] + lazy[0].weight_parts(48))
+    timeit('row conv [up|P|wp template]', lambda: ops.tc_rowconv3x3([up, lazy[0]], packed3, bias, 32, True, partial=part),
+           2.0 * 9 * 18 * 32 * S2, (32.0 + 64.0) * S2)
