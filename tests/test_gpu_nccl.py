@@ -70,6 +70,9 @@ def test_sharded_evaluate_equals_single_process(pg):
     tmpl = torch.Tensor(create_dist_mat(size=1050))
     args = (m, loader, images, dev, 'sdd', None, tmpl, [2, 5], 'test', 20, 1, 5, 4, 0.25, 1.0, False, False, 0.01, None)
 
+    from motion_style_transfer_b200.utils import evaluate as ev
+    ev.RNG_MODE = 'host'
+
     def run():
         torch.manual_seed(100)            # every rank draws the SAME host randoms; shards take their rows
         np.random.seed(200)

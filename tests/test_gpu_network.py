@@ -192,11 +192,14 @@ def test_forecast_batch_golden(ops, name):
     np.testing.assert_allclose(res['fde'].cpu().numpy(), g['fde'], rtol=0, atol=0.05 if not c['ttst'] else 1.0)
 
 
-def test_evaluate_dropin_signature_against_fixture(ops):
-    """The 23-argument evaluate() with a DataLoader, seeded like the reference run that wrote the fixture."""
+def test_evaluate_dropin_signature_against_fixture(ops, monkeypatch):
+    """The 23-argument evaluate() with a DataLoader, seeded like the reference run that wrote the fixture
+    (RNG_MODE 'host': torch's / numpy's global generators consumed in the reference's order)."""
     import pandas as pd
     from torch.utils.data import DataLoader, Dataset
+    from motion_style_transfer_b200.utils import evaluate as ev
     from motion_style_transfer_b200.utils.evaluate import evaluate
+    monkeypatch.setattr(ev, 'RNG_MODE', 'host')
     g = load_golden('eval_sdd_short')
     c = eval_cfg(g)
     m = build_product_model(golden_state_dict(g), c['obs'], c['pred'], len(c['wps']))
@@ -306,3 +309,53 @@ def test_embed_network_against_reference_fixture(ops):
     for n, p in m.named_parameters():
         if 'embedding' in n:
             assert rel_err(p.grad.cpu().numpy(), g['grad/' + n]) < 2e-3, n
+
+
+def test_evaluate_device_rng_graph_equals_eager_and_is_seeded(ops, monkeypatch):
+    """evaluate() in its default mode (device generator; full batches replayed from ONE captured CUDA graph): the graph
+    path returns exactly what the eager launches return, a re-seeded repeat of the same call index reproduces it, the next
+    call draws other numbers, and a weight update is picked up (a new graph is captured)."""
+    import pandas as pd
+    from torch.utils.data import DataLoader, Dataset
+    from motion_style_transfer_b200.utils import evaluate as ev
+    g = load_golden('eval_ind_long_ttst_cws')
+    c = eval_cfg(g)
+    m = build_product_model(golden_state_dict(g), c['obs'], c['pred'], len(c['wps'])).set_backend('bf16')
+    traj = torch.from_numpy(g['trajectory'])
+    traj = torch.cat([traj + 0.37 * i for i in range(5)])[:9]            # 9 agents: four full batches of 2 and a tail of 1
+    B = traj.shape[0]
+
+    class OneScene(Dataset):
+        def __len__(self):
+            return 1
+
+        def __getitem__(self, i):
+            return traj, pd.DataFrame({'metaId': np.repeat(np.arange(B), traj.shape[1])}), 's0'
+
+    loader = DataLoader(OneScene(), batch_size=1, collate_fn=lambda b: (b[0][0], [b[0][1]], b[0][2]))
+    tmpl = torch.from_numpy(O.create_dist_mat(int(g['template_size'])).astype(np.float32))
+    images = {'s0': torch.from_numpy(g['scene'])}
+
+    def run(graph, call):
+        monkeypatch.setattr(ev, 'USE_GRAPH', graph)
+        monkeypatch.setattr(ev, '_eval_calls', call)
+        torch.manual_seed(7)
+        return ev.evaluate(m, loader, images, 'cuda', 'ind', None, tmpl, c['wps'], 'test', c['n_goal'], c['n_traj'], c['obs'],
+                           2, c['resize'], c['T'], c['ttst'], c['cws'], c['thr'], c['cwsp'], return_preds=True)
+
+    assert ev.RNG_MODE == 'device'
+    a = run(True, 0)
+    assert len(m.__dict__['_forecast_graphs']) == 1
+    b = run(False, 0)
+    assert np.array_equal(a[2].ade.values, b[2].ade.values) and np.array_equal(a[2].fde.values, b[2].fde.values)
+    assert np.array_equal(a[3]['prediction'], b[3]['prediction'])
+    a2 = run(True, 0)
+    assert np.array_equal(a[2].ade.values, a2[2].ade.values)
+    nxt = run(True, 1)                                                   # the next round draws other samples
+    assert not np.array_equal(a[2].fde.values, nxt[2].fde.values)
+    with torch.no_grad():
+        m.goal_decoder.predictor.bias.add_(0.5)
+    upd = run(True, 0)
+    assert len(m.__dict__['_forecast_graphs']) == 2
+    ref = run(False, 0)
+    assert np.array_equal(upd[2].ade.values, ref[2].ade.values)
