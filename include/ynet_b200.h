@@ -401,6 +401,24 @@ int ynet_tc_wp_template_c8(const float* tmpl, int32_t th, int32_t tw, void* out_
 int ynet_tc_rowconv3x3_wp(const ynet_tc_src* srcs_host, int32_t n_src, const ynet_tc_src* partial_host,
                           const ynet_tc_wp_src* wp_host, int32_t N, int32_t H, int32_t W, const void* packed_weight,
                           const float* bias32, int32_t C_out, int32_t relu, void* out_c8, int32_t C_out_pad, void* stream);
+/* A whole decoder block of the trajectory decoder in ONE kernel (ynet.py:466-468: decoder.i.0 + ReLU + decoder.i.2
+ * [+ ReLU]), and at the last level the predictor + SoftArgmax2D behind it (ynet.py:469 + 582-583): conv A =
+ * ynet_tc_rowconv3x3_wp (tensor sources + waypoint source + hoisted partial sums, 32 output channels, ReLU), whose rows
+ * stay in shared memory as the operand of conv B (32 -> C_out <= 32, packed with ynet_tc_rowconv_pack_weights over 32
+ * channels).  Neither the 32-channel activation between the convs nor (tail) conv B's output or the logits reach HBM.
+ * W >= 120.  relu bits as in ynet_tc_rowconv3x3 (they apply to conv B).  Workspace of the tail:
+ * ynet_tc_rowconv2_softargmax_workspace_bytes(N, C_pred, W); out (N, C_pred, 2) = (x, y). */
+int ynet_tc_rowconv2_wp(const ynet_tc_src* srcs_host, int32_t n_src, const ynet_tc_src* partial_host,
+                        const ynet_tc_wp_src* wp_host, int32_t N, int32_t H, int32_t W, const void* packed_weight_a,
+                        const float* bias32_a, const void* packed_weight_b, const float* bias32_b, int32_t C_out,
+                        int32_t relu, void* out_c8, int32_t C_out_pad, void* stream);
+int64_t ynet_tc_rowconv2_softargmax_workspace_bytes(int32_t N, int32_t C_pred, int32_t W);
+int ynet_tc_rowconv2_wp_pred_softargmax(const ynet_tc_src* srcs_host, int32_t n_src, const ynet_tc_src* partial_host,
+                                        const ynet_tc_wp_src* wp_host, int32_t N, int32_t H, int32_t W,
+                                        const void* packed_weight_a, const float* bias32_a, const void* packed_weight_b,
+                                        const float* bias32_b, int32_t relu_b, const void* packed_pred_weight,
+                                        const float* pred_bias, int32_t C_pred, float* out, void* workspace,
+                                        int64_t workspace_bytes, void* stream);
 int ynet_tc_rowconv3x3_pred_softargmax(const ynet_tc_src* src_host, int32_t N, int32_t H, int32_t W,
                                        const void* packed_weight, const float* bias32, int32_t C_out, int32_t relu,
                                        const void* packed_pred_weight, const float* pred_bias, int32_t C_pred,

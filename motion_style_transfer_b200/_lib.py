@@ -104,6 +104,11 @@ _PROTOS = {
     'ynet_tc_rowconv_pack_weights': (c_int, [_P, _I, _I, _I, _P, _P]),
     'ynet_tc_rowconv3x3': (c_int, [POINTER(TcSrc), _I, POINTER(TcSrc), _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
     'ynet_tc_wp_template_c8': (c_int, [_P, _I, _I, _P, _P, _P]),
+    'ynet_tc_rowconv2_wp': (c_int, [POINTER(TcSrc), _I, POINTER(TcSrc), POINTER(TcWpSrc), _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _I,
+                                    _P]),
+    'ynet_tc_rowconv2_softargmax_workspace_bytes': (_L, [_I, _I, _I]),
+    'ynet_tc_rowconv2_wp_pred_softargmax': (c_int, [POINTER(TcSrc), _I, POINTER(TcSrc), POINTER(TcWpSrc), _I, _I, _I, _P, _P, _P,
+                                                    _P, _I, _P, _P, _I, _P, _P, _L, _P]),
     'ynet_tc_rowconv3x3_wp': (c_int, [POINTER(TcSrc), _I, POINTER(TcSrc), POINTER(TcWpSrc), _I, _I, _I, _P, _P, _I, _I, _P, _I,
                                       _P]),
     'ynet_tc_rowconv_softargmax_workspace_bytes': (_L, [_I, _I, _I]),

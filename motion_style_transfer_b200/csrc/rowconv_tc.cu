@@ -132,7 +132,8 @@ __device__ __forceinline__ uint32_t pack_bf16_act(uint32_t lo, uint32_t hi) {
   return d;
 }
 
-__device__ __forceinline__ int rc_slot(int row) { return RC_NS - 1 - (row & (RC_NS - 1)); }
+template <int NS = RC_NS>
+__device__ __forceinline__ int rc_slot(int row) { return NS - 1 - (row & (NS - 1)); }
 
 // ---- single-thread issue paths with compile-time ring positions -----------------------------------------------------------
 // The issuing thread is a scalar instruction stream (~8 cycles per dependent instruction): at ~150 instructions per row it,
@@ -185,31 +186,31 @@ __device__ __forceinline__ int rc_wp_window(int s, int strips, int W) {
 // acc_full counts two arrivals.
 // pre: bit 0 = acc_empty of this row already seen complete, bit 1 = in_full (probed while this issuer's previous row was
 // issued); returns the same two bits for row g + 2 (probed before this row's MMAs are issued) when PROBE, else 0.
-template <int POS, int KB, bool PROBE, int ISS, int NSTG>
+template <int POS, int KB, bool PROBE, int ISS, int NSTG, int NS>
 __device__ __forceinline__ uint32_t rc_fast_row(uint32_t tmem_base, uint32_t a_base, uint32_t a_step, uint32_t w_lo0, int kbn,
                                                 uint32_t bars, int g, uint32_t pre) {
-  constexpr int S_UP = RC_NS - 1 - ((POS + 1) & (RC_NS - 1));      // slot of output row g + 1 (first written here)
-  constexpr int S_MID = RC_NS - 1 - POS;
-  constexpr int S_DN = RC_NS - 1 - ((POS + RC_NS - 1) & (RC_NS - 1));   // slot of output row g - 1 (completed here)
-  const uint32_t abars = bars + 16u * NSTG;                       // acc_full[0]; acc_empty[0] = abars + 8 * RC_NS
-  const uint32_t ph = (uint32_t)((g >> 3) & 1);                    // slot-ring turn of row g
+  constexpr int S_UP = NS - 1 - ((POS + 1) & (NS - 1));      // slot of output row g + 1 (first written here)
+  constexpr int S_MID = NS - 1 - POS;
+  constexpr int S_DN = NS - 1 - ((POS + NS - 1) & (NS - 1));   // slot of output row g - 1 (completed here)
+  const uint32_t abars = bars + 16u * NSTG;                       // acc_full[0]; acc_empty[0] = abars + 8 * NS
+  const uint32_t ph = (uint32_t)((g / NS) & 1);                    // slot-ring turn of row g
   const int stage = g & (NSTG - 1);
   const uint32_t ph_in = (uint32_t)((g / NSTG) & 1);
   if (!(pre & 1u))
-    mbar_wait(abars + 8u * (RC_NS + S_UP), (POS == RC_NS - 1) ? ph : (ph ^ 1u), nullptr);   // acc_empty[S_UP], use (g + 1) / 8
+    mbar_wait(abars + 8u * (NS + S_UP), (POS == NS - 1) ? ph : (ph ^ 1u), nullptr);   // acc_empty[S_UP], use (g + 1) / 8
   if (!(pre & 2u)) mbar_wait(bars + 8u * (uint32_t)stage, ph_in, nullptr);                   // in_full[stage]
   tc_fence_after();
   uint32_t nxt = 0;
   if (PROBE) {
-    constexpr int NP = (POS + ISS) & (RC_NS - 1);
-    constexpr int S_UPN = RC_NS - 1 - ((NP + 1) & (RC_NS - 1));
-    const uint32_t phn = (POS >= RC_NS - ISS) ? (ph ^ 1u) : ph;
+    constexpr int NP = (POS + ISS) & (NS - 1);
+    constexpr int S_UPN = NS - 1 - ((NP + 1) & (NS - 1));
+    const uint32_t phn = (POS >= NS - ISS) ? (ph ^ 1u) : ph;
     const int gn = g + ISS;
-    nxt = mbar_test(abars + 8u * (RC_NS + S_UPN), (NP == RC_NS - 1) ? phn : (phn ^ 1u)) |
+    nxt = mbar_test(abars + 8u * (NS + S_UPN), (NP == NS - 1) ? phn : (phn ^ 1u)) |
           (mbar_test(bars + 8u * (uint32_t)(gn & (NSTG - 1)), (uint32_t)((gn / NSTG) & 1)) << 1);
   }
   const uint32_t a_lo = a_base + (uint32_t)stage * a_step;
-  if (POS == RC_NS - 1) {          // the ring wraps between rows g + 1 and g
+  if (POS == NS - 1) {          // the ring wraps between rows g + 1 and g
     rc_run<0, 1, S_UP, KB>(tmem_base, a_lo, w_lo0, kbn);
     rc_run<1, 2, S_MID, KB>(tmem_base, a_lo, w_lo0, kbn);
   } else if (POS == 0) {           // ... between rows g and g - 1
@@ -225,72 +226,87 @@ __device__ __forceinline__ uint32_t rc_fast_row(uint32_t tmem_base, uint32_t a_b
 }
 
 // ISS = 2: issuer `who` (0 / 1) takes the input rows with g % 2 == who; ISS = 1: one issuer (who = 0) takes all rows
-template <int KB, int ISS, int NSTG>
-__device__ __forceinline__ void rc_conv_issuer(const RcParams& p, uint32_t tmem_base, uint32_t a_base, uint32_t w_lo0,
-                                               uint32_t bars, int who) {
-  const uint32_t a_step = (uint32_t)(p.row_bytes >> 4);
-  const int kbn = (p.dbg & 4) ? 1 : p.kb, H = p.H;
-  const uint32_t in_full = bars, in_empty = bars + 8u * NSTG, acc_full = bars + 16u * NSTG, acc_empty = acc_full + 8u * RC_NS;
+// NS = slots of the TMEM ring at tmem_base (8, or 4 in the two-conv kernel); a_step = bytes of one input row >> 4;
+// barrier block at `bars`: in_full[NSTG] in_empty[NSTG] acc_full[NS] acc_empty[NS]
+template <int KB, int ISS, int NSTG, int NS>
+__device__ __forceinline__ void rc_conv_issuer(int H, long long items, int kbn, uint32_t a_step, uint32_t tmem_base,
+                                               uint32_t a_base, uint32_t w_lo0, uint32_t bars, int who) {
+  const uint32_t in_full = bars, in_empty = bars + 8u * NSTG, acc_full = bars + 16u * NSTG, acc_empty = acc_full + 8u * NS;
   int g0 = 0;                                // running index of the strip's first row: slot ring and stage ring position
-  for (long long item = blockIdx.x; item < p.items; item += gridDim.x, g0 += H) {
+  for (long long item = blockIdx.x; item < items; item += gridDim.x, g0 += H) {
     for (int Y = (ISS == 2) ? ((g0 ^ who) & 1) : 0; Y < H; Y += ISS) {
       const int g = g0 + Y;
-      const int pos = g & (RC_NS - 1);
-      const uint32_t ph = (uint32_t)((g >> 3) & 1);
+      const int pos = g & (NS - 1);
+      const uint32_t ph = (uint32_t)((g / NS) & 1);
       const int stage = g & (NSTG - 1);
       const uint32_t ph_in = (uint32_t)((g / NSTG) & 1);
       const uint32_t a_lo = a_base + (uint32_t)stage * a_step;
       if (Y >= 1 && Y + 1 < H) {
-        if (pos == who && Y + RC_NS < H) {     // an aligned group of eight interior rows (this issuer's share of it):
+        if (pos == who && Y + NS < H) {     // an aligned group of eight interior rows (this issuer's share of it):
           uint32_t pre = 0;                    // straight-line code, barriers probed one row ahead
-          if (ISS == 1) {
-            pre = rc_fast_row<0, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, pre);
-            pre = rc_fast_row<1, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 1, pre);
-            pre = rc_fast_row<2, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 2, pre);
-            pre = rc_fast_row<3, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 3, pre);
-            pre = rc_fast_row<4, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 4, pre);
-            pre = rc_fast_row<5, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 5, pre);
-            pre = rc_fast_row<6, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 6, pre);
-            rc_fast_row<7, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 7, pre);
+          if constexpr (NS == 4) {
+            static_assert(NS != 4 || ISS == 1, "the four-slot ring is driven by one issuer");
+            pre = rc_fast_row<0, KB, true, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, pre);
+            pre = rc_fast_row<1, KB, true, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 1, pre);
+            pre = rc_fast_row<2, KB, true, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 2, pre);
+            rc_fast_row<3, KB, false, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 3, pre);
+          } else if (ISS == 1) {
+            pre = rc_fast_row<0, KB, true, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, pre);
+            pre = rc_fast_row<1, KB, true, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 1, pre);
+            pre = rc_fast_row<2, KB, true, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 2, pre);
+            pre = rc_fast_row<3, KB, true, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 3, pre);
+            pre = rc_fast_row<4, KB, true, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 4, pre);
+            pre = rc_fast_row<5, KB, true, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 5, pre);
+            pre = rc_fast_row<6, KB, true, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 6, pre);
+            rc_fast_row<7, KB, false, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 7, pre);
           } else if (who == 0) {
-            pre = rc_fast_row<0, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, pre);
-            pre = rc_fast_row<2, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 2, pre);
-            pre = rc_fast_row<4, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 4, pre);
-            rc_fast_row<6, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 6, pre);
+            pre = rc_fast_row<0, KB, true, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, pre);
+            pre = rc_fast_row<2, KB, true, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 2, pre);
+            pre = rc_fast_row<4, KB, true, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 4, pre);
+            rc_fast_row<6, KB, false, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 6, pre);
           } else {
-            pre = rc_fast_row<1, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, pre);
-            pre = rc_fast_row<3, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 2, pre);
-            pre = rc_fast_row<5, KB, true, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 4, pre);
-            rc_fast_row<7, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 6, pre);
+            pre = rc_fast_row<1, KB, true, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, pre);
+            pre = rc_fast_row<3, KB, true, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 2, pre);
+            pre = rc_fast_row<5, KB, true, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 4, pre);
+            rc_fast_row<7, KB, false, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g + 6, pre);
           }
-          Y += RC_NS - ISS;
+          Y += NS - ISS;
           continue;
         }
-        switch (pos) {
-          case 0: rc_fast_row<0, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
-          case 1: rc_fast_row<1, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
-          case 2: rc_fast_row<2, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
-          case 3: rc_fast_row<3, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
-          case 4: rc_fast_row<4, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
-          case 5: rc_fast_row<5, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
-          case 6: rc_fast_row<6, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
-          default: rc_fast_row<7, KB, false, ISS, NSTG>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+        if constexpr (NS == 4) {
+          switch (pos) {
+            case 0: rc_fast_row<0, KB, false, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+            case 1: rc_fast_row<1, KB, false, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+            case 2: rc_fast_row<2, KB, false, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+            default: rc_fast_row<3, KB, false, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+          }
+        } else {
+          switch (pos) {
+            case 0: rc_fast_row<0, KB, false, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+            case 1: rc_fast_row<1, KB, false, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+            case 2: rc_fast_row<2, KB, false, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+            case 3: rc_fast_row<3, KB, false, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+            case 4: rc_fast_row<4, KB, false, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+            case 5: rc_fast_row<5, KB, false, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+            case 6: rc_fast_row<6, KB, false, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+            default: rc_fast_row<7, KB, false, ISS, NSTG, NS>(tmem_base, a_base, a_step, w_lo0, kbn, bars, g, 0u); break;
+          }
         }
         continue;
       }
       // ---- first / last row of a strip: generic path (2 rows in H) ----
       // the slots this row writes FIRST must have been drained: row g + 1 (and row g at the top of a strip)
-      if (Y == 0) mbar_wait(acc_empty + 8u * rc_slot(g), ph ^ 1u, nullptr);
-      if (Y + 1 < H) mbar_wait(acc_empty + 8u * rc_slot(g + 1), (uint32_t)((((g + 1) >> 3) & 1) ^ 1), nullptr);
+      if (Y == 0) mbar_wait(acc_empty + 8u * rc_slot<NS>(g), ph ^ 1u, nullptr);
+      if (Y + 1 < H) mbar_wait(acc_empty + 8u * rc_slot<NS>(g + 1), (uint32_t)((((g + 1) / NS) & 1) ^ 1), nullptr);
       mbar_wait(in_full + 8u * (uint32_t)stage, ph_in, nullptr);
       tc_fence_after();
           // kernel rows kh_lo..kh_hi contribute (output row g + 1 - kh must exist).  The slots of rows g + 1, g, g - 1 are
       // consecutive except where the ring wraps: after kh = 0 when g % 8 == 7, after kh = 1 when g % 8 == 0.
       const int kh_lo = (Y + 1 < H) ? 0 : 1, kh_hi = (Y >= 1) ? 2 : 1;
-      const int brk = (pos == RC_NS - 1) ? 1 : (pos == 0 ? 2 : 3);          // first kernel row of a second run
+      const int brk = (pos == NS - 1) ? 1 : (pos == 0 ? 2 : 3);          // first kernel row of a second run
       auto issue = [&](int kh0, int len) {
         const uint32_t idesc = RC_IDESC0 | ((uint32_t)(len * (RC_CO >> 3)) << 17);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(rc_slot(g + 1 - kh0) * RC_CO);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(rc_slot<NS>(g + 1 - kh0) * RC_CO);
         uint32_t b_lo = w_lo0 + (uint32_t)(kh0 * RC_CO);
         uint32_t a = a_lo;
         for (int kb = 0; kb < kbn; ++kb) {
@@ -307,9 +323,9 @@ __device__ __forceinline__ void rc_conv_issuer(const RcParams& p, uint32_t tmem_
       const int b0 = max(brk, kh_lo);
       if (b0 <= kh_hi) issue(b0, kh_hi - b0 + 1);
       tc_commit(in_empty + 8u * (uint32_t)stage);
-      if (ISS == 2) tc_commit(acc_full + 8u * rc_slot(g));         // this issuer's share of output row g
-      if (Y >= 1) tc_commit(acc_full + 8u * rc_slot(g - 1));       // last contribution to output row g - 1
-      if (Y == H - 1) tc_commit(acc_full + 8u * rc_slot(g));       // no input row below: the last arrival comes from here
+      if (ISS == 2) tc_commit(acc_full + 8u * rc_slot<NS>(g));         // this issuer's share of output row g
+      if (Y >= 1) tc_commit(acc_full + 8u * rc_slot<NS>(g - 1));       // last contribution to output row g - 1
+      if (Y == H - 1) tc_commit(acc_full + 8u * rc_slot<NS>(g));       // no input row below: the last arrival comes from here
     }
   }
 }
@@ -475,10 +491,12 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
       constexpr uint32_t B_LBO = (uint32_t)((96 * 16) >> 4) << 16;
       const uint32_t w_lo0 = ((smem_u32(s_w) >> 4) & 0x3FFF) | B_LBO;
       const uint32_t a_base = ((smem_u32(s_in) >> 4) & 0x3FFF) | A_LBO;
+      const uint32_t a_step = (uint32_t)(p.row_bytes >> 4);
       if (p.kb == 2 && !(p.dbg & 4))
-        rc_conv_issuer<2, 1, NSTG>(p, tmem_base, a_base, w_lo0, smem_u32(in_full), warp - 1);
+        rc_conv_issuer<2, 1, NSTG, RC_NS>(p.H, p.items, 2, a_step, tmem_base, a_base, w_lo0, smem_u32(in_full), warp - 1);
       else
-        rc_conv_issuer<0, 1, NSTG>(p, tmem_base, a_base, w_lo0, smem_u32(in_full), warp - 1);
+        rc_conv_issuer<0, 1, NSTG, RC_NS>(p.H, p.items, (p.dbg & 4) ? 1 : p.kb, a_step, tmem_base, a_base, w_lo0,
+                                          smem_u32(in_full), warp - 1);
     }
   } else if (warp < W_EPI + RC_EPI_WARPS) {
     // ===================== conv epilogue: 2 sets x 4 warps; warp w owns TMEM lanes 32 (w % 4) .. +31 = pixels; set k
@@ -692,6 +710,510 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
   }
 }
 
+// ================================================================================================================
+// TWO stacked convs of a decoder block in one kernel (ynet.py:466-468: decoder.i.0 + ReLU + decoder.i.2 + ReLU), with the
+// predictor + SoftArgmax2D behind them at the last level (TAIL): the 32-channel activation between the two convs never
+// leaves the SM.  Conv A is the WP kernel above (sources [up, waypoint planes from the template], hoisted partial sums
+// added by its epilogue); its epilogue writes the bf16 row into a four-row shared-memory ring in the K-major operand
+// layout -- zeroed outside the image, which is conv B's padding -- and conv B marches over that ring exactly as conv A
+// marches over the TMA ring (same issuer code, other barriers).  Conv B's output lane m is pixel xw + 2 + m: 124 valid
+// pixels per strip.  TMEM: two rings of FOUR 32-column slots (A: columns 0-127, B: 128-255) + the two predictor
+// accumulators (256-511).  Warps: 0 TMA | 1 conv A issuer | 2 conv B issuer | 3 predictor issuer | 4-11 conv A epilogue |
+// 12-19 conv B epilogue (two sets of four each, alternating rows: one set's per-row latency chain of ~1 200 cycles --
+// barrier wake-ups, tcgen05.ld / st, proxy fence -- would bound the kernel) | 20-27 soft-argmax (two sets of four, 32
+// pixels per warp).
+// The hoisted partial sums (64 B per pixel) reach conv A's epilogue through their own TMA row ring: with ONE CTA per SM
+// and one epilogue warp set, per-lane global loads keep only 8 KB in flight per SM, and the kernel ran at the L2
+// round trip per row (3.7 ms per 320 images against 2.1 ms without the partial sums).  The producer thread drives the
+// input ring and the partial ring with two independent cursors (non-blocking barrier probes).
+constexpr int R2_NS = 4;                         // slots per accumulator ring
+constexpr int R2_NSTG = 8;                       // TMA ring of conv A's input rows
+constexpr int R2_NA = 4;                         // ring of conv A's output rows = conv B's input stages
+constexpr int R2_VW = 124;                       // valid output pixels per strip row
+constexpr int R2_NY = 2;                         // conv B -> predictor row ring (tail)
+constexpr int R2_PROW = 4 * RC_CHUNK_BYTES;      // one row of partial sums: [4 chunks (hi)][128 px][8 ch] bf16
+constexpr int R2_THREADS_TAIL = 32 * 28;
+constexpr int R2_THREADS_PLAIN = 32 * 20;
+constexpr int R2_SOFT_WARPS = 8;
+constexpr uint32_t R2_BCOL = 128;                // first TMEM column of conv B's ring
+
+struct Rc2Params {
+  RcParams a;                  // conv A: sources, waypoint source, partial sums, weights (w96), bias, geometry
+  const unsigned char* wb96;   // conv B weights [2][kw][2][96][8]
+  const float* bias_b;         // 32 floats
+  int relu_b;
+};
+
+// window start (x of input pixel 0) of strip s: see rc_wp_window; conv B's valid columns shrink the stride to 124
+__device__ __forceinline__ int rc2_window(int s, int strips, int W) {
+  return s == 0 ? -8 : (s == strips - 1 ? W - 120 : R2_VW * s - 8);
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* b) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "f"(b[0]), "f"(b[1]), "f"(b[2]), "f"(b[3]), "f"(b[4]), "f"(b[5]), "f"(b[6]), "f"(b[7]), "f"(b[8]), "f"(b[9]),
+      "f"(b[10]), "f"(b[11]), "f"(b[12]), "f"(b[13]), "f"(b[14]), "f"(b[15])
+      : "memory");
+}
+
+// soft-argmax of a 16-pixel row segment restricted to the columns [lo, hi)
+__device__ __forceinline__ void softargmax_row16_range(SoftState& st, const uint32_t (&v)[16], float bias, int x0, int y, int lo,
+                                                       int hi) {
+  uint32_t vm[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) vm[i] = (x0 + i >= lo && x0 + i < hi) ? v[i] : __float_as_uint(-1.0e30f);
+  softargmax_row16(st, vm, bias, x0, y);
+}
+
+template <bool TAIL>
+__global__ void __launch_bounds__(TAIL ? R2_THREADS_TAIL : R2_THREADS_PLAIN, 1)
+tc_rowconv2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                   const __grid_constant__ CUtensorMap mapw, const __grid_constant__ CUtensorMap mapw120,
+                   const __grid_constant__ CUtensorMap mapz, const __grid_constant__ CUtensorMap mapp, const Rc2Params pp) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const RcParams& p = pp.a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NTHREADS = TAIL ? R2_THREADS_TAIL : R2_THREADS_PLAIN;
+  constexpr int W_EPA = 4, W_EPB = 12, W_SOFT = 20;
+  constexpr int NPR = TAIL ? 8 : 4;                // rows of the partial-sum ring
+  constexpr int NS = TAIL ? R2_NS : 8;             // slots per accumulator ring: the tail shares the 512 columns with the predictor
+  constexpr uint32_t BCOL = TAIL ? R2_BCOL : 256u; // first column of conv B's ring
+
+  unsigned char* s_wa = smem;                                                   // kb * 3 * RC_WBLK
+  unsigned char* s_wb = s_wa + (size_t)p.kb * 3 * RC_WBLK;                      // 2 * 3 * RC_WBLK
+  unsigned char* s_in = s_wb + 2 * 3 * RC_WBLK;                                 // R2_NSTG * row_bytes (+ 1 KB slack)
+  unsigned char* s_a = s_in + (size_t)R2_NSTG * p.row_bytes + 1024;             // R2_NA * RC_YROW (+ 1 KB slack)
+  unsigned char* s_pr = s_a + R2_NA * RC_YROW + 1024;                           // NPR * R2_PROW
+  unsigned char* s_y = s_pr + NPR * R2_PROW;                                    // tail: R2_NY * RC_YROW
+  unsigned char* s_pw = s_y + (TAIL ? R2_NY * RC_YROW : 0);                     // tail: 2 * PR_WBLK_BYTES
+  float* s_bias = reinterpret_cast<float*>(s_pw + (TAIL ? 2 * PR_WBLK_BYTES : 0));   // [A: 32][B: 32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 64);
+  uint64_t* in_full = bars;                        // block A: in_full[8] in_empty[8] acca_full[4] acca_empty[4]
+  uint64_t* in_empty = in_full + R2_NSTG;
+  uint64_t* acca_full = in_empty + R2_NSTG;
+  uint64_t* acca_empty = acca_full + NS;
+  uint64_t* a_full = acca_empty + NS;           // block B: a_full[4] a_empty[4] accb_full[4] accb_empty[4]
+  uint64_t* a_empty = a_full + R2_NA;
+  uint64_t* accb_full = a_empty + R2_NA;
+  uint64_t* accb_empty = accb_full + NS;
+  uint64_t* y_full = accb_empty + NS;
+  uint64_t* y_empty = y_full + R2_NY;
+  uint64_t* p_full = y_empty + R2_NY;
+  uint64_t* p_empty = p_full + 2;
+  uint64_t* pr_full = p_empty + 2;
+  uint64_t* pr_empty = pr_full + NPR;
+  uint64_t* w_bar = pr_empty + NPR;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  if (TAIL) pred_stage_weights(s_pw, p.pw, p.kbp, p.pn_pad, threadIdx.x, NTHREADS);
+  if (threadIdx.x < 64) s_bias[threadIdx.x] = threadIdx.x < 32 ? p.bias[threadIdx.x] : pp.bias_b[threadIdx.x - 32];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < R2_NSTG; ++s) {
+      mbar_init(smem_u32(&in_full[s]), 1);
+      mbar_init(smem_u32(&in_empty[s]), 1);
+    }
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(smem_u32(&acca_full[s]), 1);
+      mbar_init(smem_u32(&acca_empty[s]), 4);
+      mbar_init(smem_u32(&accb_full[s]), 1);
+      mbar_init(smem_u32(&accb_empty[s]), 4);
+    }
+    for (int s = 0; s < R2_NA; ++s) {
+      mbar_init(smem_u32(&a_full[s]), 4);
+      mbar_init(smem_u32(&a_empty[s]), 1);
+    }
+    for (int s = 0; s < R2_NY; ++s) {
+      mbar_init(smem_u32(&y_full[s]), 4);
+      mbar_init(smem_u32(&y_empty[s]), 1);
+    }
+    for (int s = 0; s < NPR; ++s) {
+      mbar_init(smem_u32(&pr_full[s]), 1);
+      mbar_init(smem_u32(&pr_empty[s]), 4);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&p_full[s]), 1);
+      mbar_init(smem_u32(&p_empty[s]), R2_SOFT_WARPS / 2);
+    }
+    mbar_init(smem_u32(w_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  constexpr uint32_t TMEM_COLS = 512u;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {   // K-padding chunk slots of the TMA ring that no transaction writes, and the slack behind the rings, must read as zero
+    uint4* z = reinterpret_cast<uint4*>(s_in);
+    const int nz = (int)((s_pr - s_in) >> 4);
+    for (int i = threadIdx.x; i < nz; i += NTHREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  if ((warp >= W_EPA && warp < W_EPA + 4) || (warp >= W_EPB && warp < W_EPB + 4)) {   // both rings start out holding their bias
+    const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (warp >= W_EPB ? BCOL : 0u);
+    const float* b = s_bias + (warp >= W_EPB ? 32 : 0);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      tmem_st16(t_row + (uint32_t)(s * RC_CO), b);
+      tmem_st16(t_row + (uint32_t)(s * RC_CO + 16), b + 16);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    // ===================== TMA producer (conv A's input rows; see tc_rowconv_kernel<false, true>) =====================
+    if (elect_one()) {
+      const uint32_t wa = (uint32_t)(p.kb * 3 * RC_WBLK), wb = (uint32_t)(2 * 3 * RC_WBLK);
+      mbar_expect_tx(smem_u32(w_bar), wa + wb);
+      for (uint32_t off = 0; off < wa; off += 18432) bulk_load(smem_u32(s_wa + off), p.w96 + off, min(18432u, wa - off), smem_u32(w_bar));
+      bulk_load(smem_u32(s_wb), pp.wb96, wb, smem_u32(w_bar));
+      // two cursors over the same (item, row) sequence: conv A's input rows and the rows of partial sums
+      const bool has_part = p.part != nullptr && !(p.dbg & 8);
+      long long it_i = blockIdx.x, it_p = has_part ? (long long)blockIdx.x : p.items;
+      int Yi = 0, Yp = 0, st_i = 0, st_p = 0;
+      uint32_t ph_i = 0, ph_p = 0;
+      int ns[2] = {0, 0}, c0 = 0, edge = 0, wrow[2] = {0, 0}, wcol[2] = {0, 0}, wpar[2] = {0, 0};
+      int np_img = 0, c0p = 0;
+      bool new_i = true, new_p = true;
+      while (it_i < p.items || it_p < p.items) {
+        if (it_i < p.items) {
+          if (new_i) {
+            const int n = (int)(it_i / p.strips), s = (int)(it_i - (long long)n * p.strips);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int bm = p.src_mod[i];
+              ns[i] = p.src_bcast[i] ? 0 : (bm > 0 ? n % bm : (bm < 0 ? n / (-bm) : n));
+            }
+            c0 = 2 * rc2_window(s, p.strips, p.W);          // 8-byte elements: two per pixel
+            edge = s == 0 ? 1 : (s == p.strips - 1 ? 2 : 0);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const size_t k = (size_t)n * p.wp_nch + min(c, p.wp_nch - 1);
+              const int yl = p.wp_th / 2 - __float2int_rn(__ldg(p.wp_coords + 2 * k + 1));     // half to even == np.round
+              const int xl = p.wp_tw / 2 - __float2int_rn(__ldg(p.wp_coords + 2 * k));
+              wpar[c] = p.wp_level ? ((yl & 1) * 2 + (xl & 1)) : 0;
+              wrow[c] = p.wp_level ? (yl >> 1) : yl;
+              wcol[c] = 2 * (p.wp_level ? (xl >> 1) : xl) + c0;
+            }
+            new_i = false;
+          }
+          if (mbar_test(smem_u32(&in_empty[st_i]), ph_i ^ 1)) {
+            const uint32_t fb = smem_u32(&in_full[st_i]);
+            const uint32_t dst = smem_u32(s_in + (size_t)st_i * p.row_bytes);
+            mbar_expect_tx(fb, (uint32_t)(p.row_tx - ((p.dbg & 16) ? p.wp_nch * RC_CHUNK_BYTES : 0)));
+            tma_load_4d(dst + (uint32_t)(p.src_coff[0] * RC_CHUNK_BYTES), &map0, fb, c0, Yi, 0, ns[0]);
+            if (p.n_src > 1) tma_load_4d(dst + (uint32_t)(p.src_coff[1] * RC_CHUNK_BYTES), &map1, fb, c0, Yi, 0, ns[1]);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              if (c >= p.wp_nch || (p.dbg & 16)) break;
+              const uint32_t d = dst + (uint32_t)((p.wp_coff + c) * RC_CHUNK_BYTES);
+              if (edge == 0) {
+                tma_load_4d(d, &mapw, fb, wcol[c], wrow[c] + Yi, wpar[c], 0);
+              } else if (edge == 1) {
+                tma_load_4d(d, &mapz, fb, 0, 0, 0, 0);
+                tma_load_4d(d + 128u, &mapw120, fb, wcol[c] + 16, wrow[c] + Yi, wpar[c], 0);
+              } else {
+                tma_load_4d(d, &mapw120, fb, wcol[c], wrow[c] + Yi, wpar[c], 0);
+                tma_load_4d(d + 1920u, &mapz, fb, 0, 0, 0, 0);
+              }
+            }
+            if (++st_i == R2_NSTG) {
+              st_i = 0;
+              ph_i ^= 1;
+            }
+            if (++Yi == p.H) {
+              Yi = 0;
+              it_i += gridDim.x;
+              new_i = true;
+            }
+          }
+        }
+        if (it_p < p.items) {
+          if (new_p) {
+            const int n = (int)(it_p / p.strips), s = (int)(it_p - (long long)n * p.strips);
+            np_img = p.part_mod > 0 ? n % p.part_mod : (p.part_mod < 0 ? n / (-p.part_mod) : n);
+            c0p = 2 * rc2_window(s, p.strips, p.W);
+            new_p = false;
+          }
+          if (mbar_test(smem_u32(&pr_empty[st_p]), ph_p ^ 1)) {
+            const uint32_t fb = smem_u32(&pr_full[st_p]);
+            mbar_expect_tx(fb, (uint32_t)R2_PROW);
+            tma_load_4d(smem_u32(s_pr + (size_t)st_p * R2_PROW), &mapp, fb, c0p, Yp, 0, np_img);
+            if (++st_p == NPR) {
+              st_p = 0;
+              ph_p ^= 1;
+            }
+            if (++Yp == p.H) {
+              Yp = 0;
+              it_p += gridDim.x;
+              new_p = true;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ===================== conv A / conv B MMA issuers =====================
+    if (elect_one()) {
+      mbar_wait(smem_u32(w_bar), 0, nullptr);
+      constexpr uint32_t A_LBO = (uint32_t)(RC_CHUNK_BYTES >> 4) << 16;
+      constexpr uint32_t B_LBO = (uint32_t)((96 * 16) >> 4) << 16;
+      if (warp == 1) {
+        const uint32_t w_lo0 = ((smem_u32(s_wa) >> 4) & 0x3FFF) | B_LBO;
+        const uint32_t a_base = ((smem_u32(s_in) >> 4) & 0x3FFF) | A_LBO;
+        const uint32_t a_step = (uint32_t)(p.row_bytes >> 4);
+        if (p.kb == 2 && !(p.dbg & 4))
+          rc_conv_issuer<2, 1, R2_NSTG, NS>(p.H, p.items, 2, a_step, tmem_base, a_base, w_lo0, smem_u32(in_full), 0);
+        else
+          rc_conv_issuer<0, 1, R2_NSTG, NS>(p.H, p.items, (p.dbg & 4) ? 1 : p.kb, a_step, tmem_base, a_base, w_lo0,
+                                               smem_u32(in_full), 0);
+      } else {
+        const uint32_t w_lo0 = ((smem_u32(s_wb) >> 4) & 0x3FFF) | B_LBO;
+        const uint32_t a_base = ((smem_u32(s_a) >> 4) & 0x3FFF) | A_LBO;
+        rc_conv_issuer<2, 1, R2_NA, NS>(p.H, p.items, 2, (uint32_t)(RC_YROW >> 4), tmem_base + BCOL, a_base, w_lo0,
+                                           smem_u32(a_full), 0);
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== predictor MMA issuer (tail): D[channel, pixel] = Wp (M = 128, replicated) x row (N = 128) =====
+    if (TAIL && elect_one()) {
+      constexpr uint32_t IDESC_P = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      constexpr uint32_t P_HI = (uint32_t)(128 >> 4) | (1u << 14);
+      constexpr uint32_t P_LBO = (uint32_t)((RC_M * 16) >> 4) << 16;
+      const uint32_t pa_lo = ((smem_u32(s_pw) >> 4) & 0x3FFF) | P_LBO;
+      const uint32_t pb_lo = ((smem_u32(s_y) >> 4) & 0x3FFF) | P_LBO;
+      const uint32_t yf = smem_u32(y_full), ye = smem_u32(y_empty), pf = smem_u32(p_full), pe = smem_u32(p_empty);
+      const int kbpn = p.kbp;
+      uint32_t pre = 0;
+      long long total_rows = 0;
+      for (long long item = blockIdx.x; item < p.items; item += gridDim.x) total_rows += p.H;
+      for (long long gl = 0; gl < total_rows; ++gl) {
+        const int g = (int)gl;
+        const uint32_t b = (uint32_t)(g & (R2_NY - 1)), a = (uint32_t)(g & 1);
+        if (!(pre & 1u)) mbar_wait(pe + 8u * a, (uint32_t)(((g >> 1) & 1) ^ 1), nullptr);
+        if (!(pre & 2u)) mbar_wait(yf + 8u * b, (uint32_t)((g / R2_NY) & 1), nullptr);
+        tc_fence_after();
+        {
+          const int gn = g + 1;
+          pre = mbar_test(pe + 8u * (uint32_t)(gn & 1), (uint32_t)(((gn >> 1) & 1) ^ 1)) |
+                (mbar_test(yf + 8u * (uint32_t)(gn & (R2_NY - 1)), (uint32_t)((gn / R2_NY) & 1)) << 1);
+        }
+        const uint32_t d = tmem_base + RC_PACC + a * 128u;
+        const uint32_t bl = pb_lo + b * (uint32_t)(RC_YROW >> 4);
+        tc_mma_bf16(d, ((uint64_t)P_HI << 32) | pa_lo, ((uint64_t)P_HI << 32) | bl, IDESC_P, 0u);
+        if (kbpn > 1)
+          tc_mma_bf16(d, ((uint64_t)P_HI << 32) | (pa_lo + (uint32_t)(PR_WBLK_BYTES >> 4)),
+                      ((uint64_t)P_HI << 32) | (bl + (uint32_t)((2 * RC_M * 16) >> 4)), IDESC_P, 1u);
+        tc_commit(pf + 8u * a);
+        tc_commit(ye + 8u * b);
+      }
+    }
+  } else if (warp < W_EPB) {
+    // ===================== conv A epilogue: + partial sums, ReLU, zero outside the image -> row ring of conv B ==========
+    const int q = warp & 3, set = (warp - W_EPA) >> 2;
+    const int m = q * 32 + lane;                    // lane m = pixel xw + 1 + m
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    int g0 = 0;
+    const int H = p.H;
+    for (long long item = blockIdx.x; item < p.items; item += gridDim.x, g0 += H) {
+      const int n = (int)(item / p.strips), s = (int)(item - (long long)n * p.strips);
+      const int x = rc2_window(s, p.strips, p.W) + 1 + m;
+      const bool inside = x >= 0 && x < p.W;        // (lanes 126 / 127 hold garbage that conv B's valid lanes never read)
+      const bool has_part = p.part != nullptr && !(p.dbg & 8);
+      const int mp = min(m + 1, RC_M - 1);              // window pixel of this lane's output pixel in the partial-sum row
+      for (int Y = (g0 ^ set) & 1; Y < H; Y += 2) {          // this set's rows: g % 2 == set
+        const int g = g0 + Y;
+        const int sl = rc_slot<NS>(g);
+        mbar_wait(smem_u32(&acca_full[sl]), (uint32_t)((g / NS) & 1), nullptr);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(t_row + (uint32_t)(sl * RC_CO), v);
+        tmem_st16(t_row + (uint32_t)(sl * RC_CO), s_bias);
+        tmem_st16(t_row + (uint32_t)(sl * RC_CO + 16), s_bias + 16);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&acca_empty[sl]));
+        if (has_part) {              // + the agent's hoisted encoder-feature share of conv A (fp32 add), from its TMA ring
+          const int pb = g & (NPR - 1);
+          mbar_wait(smem_u32(&pr_full[pb]), (uint32_t)((g / NPR) & 1), nullptr);
+          const unsigned char* prow = s_pr + (size_t)pb * R2_PROW + mp * 16;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 h4 = *reinterpret_cast<const uint4*>(prow + c * RC_CHUNK_BYTES);
+            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              v[8 * c + 2 * k] = __float_as_uint(__uint_as_float(v[8 * c + 2 * k]) + __uint_as_float(hw[k] << 16));
+              v[8 * c + 2 * k + 1] =
+                  __float_as_uint(__uint_as_float(v[8 * c + 2 * k + 1]) + __uint_as_float(hw[k] & 0xFFFF0000u));
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&pr_empty[pb]));
+        }
+        uint4 o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          o[c].x = inside ? pack_bf16_act<true>(v[8 * c + 0], v[8 * c + 1]) : 0u;
+          o[c].y = inside ? pack_bf16_act<true>(v[8 * c + 2], v[8 * c + 3]) : 0u;
+          o[c].z = inside ? pack_bf16_act<true>(v[8 * c + 4], v[8 * c + 5]) : 0u;
+          o[c].w = inside ? pack_bf16_act<true>(v[8 * c + 6], v[8 * c + 7]) : 0u;
+        }
+        const int b = g & (R2_NA - 1);
+        if (lane == 0) mbar_wait(smem_u32(&a_empty[b]), (uint32_t)(((g / R2_NA) & 1) ^ 1), nullptr);
+        __syncwarp();
+        unsigned char* ab = s_a + (size_t)b * RC_YROW + m * 16;
+        if (!(p.dbg & 2)) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(ab + c * (RC_M * 16)) = o[c];
+        }
+        if (!(p.dbg & 16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&a_full[b]));
+      }
+    }
+  } else if (warp < W_SOFT) {
+    // ===================== conv B epilogue: ReLU -> predictor operand ring (tail) or the C8 planes (plain) ==============
+    const int q = warp & 3, set = (warp - W_EPB) >> 2;
+    const int m = q * 32 + lane;                    // lane m = pixel xw + 2 + m
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + BCOL;
+    int g0 = 0;
+    const int H = p.H;
+    for (long long item = blockIdx.x; item < p.items; item += gridDim.x, g0 += H) {
+      const int n = (int)(item / p.strips), s = (int)(item - (long long)n * p.strips);
+      const int x = rc2_window(s, p.strips, p.W) + 2 + m;
+      // the columns [W - 118, W) belong to the last strip alone (see tc_rowconv_kernel<false, true>)
+      const bool live = m < R2_VW && x >= 0 && x < p.W && (s == p.strips - 1 || x < p.W - 118);
+      for (int Y = (g0 ^ set) & 1; Y < H; Y += 2) {          // this set's rows: g % 2 == set
+        const int g = g0 + Y;
+        const int sl = rc_slot<NS>(g);
+        mbar_wait(smem_u32(&accb_full[sl]), (uint32_t)((g / NS) & 1), nullptr);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(t_row + (uint32_t)(sl * RC_CO), v);
+        tmem_st16(t_row + (uint32_t)(sl * RC_CO), s_bias + 32);
+        tmem_st16(t_row + (uint32_t)(sl * RC_CO + 16), s_bias + 48);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&accb_empty[sl]));
+        uint4 o[4];
+        if (pp.relu_b) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            o[c].x = pack_bf16_act<true>(v[8 * c + 0], v[8 * c + 1]);
+            o[c].y = pack_bf16_act<true>(v[8 * c + 2], v[8 * c + 3]);
+            o[c].z = pack_bf16_act<true>(v[8 * c + 4], v[8 * c + 5]);
+            o[c].w = pack_bf16_act<true>(v[8 * c + 6], v[8 * c + 7]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            o[c].x = pack_bf16_act<false>(v[8 * c + 0], v[8 * c + 1]);
+            o[c].y = pack_bf16_act<false>(v[8 * c + 2], v[8 * c + 3]);
+            o[c].z = pack_bf16_act<false>(v[8 * c + 4], v[8 * c + 5]);
+            o[c].w = pack_bf16_act<false>(v[8 * c + 6], v[8 * c + 7]);
+          }
+        }
+        if (TAIL) {
+          const int b = g & (R2_NY - 1);
+          if (lane == 0) mbar_wait(smem_u32(&y_empty[b]), (uint32_t)(((g / R2_NY) & 1) ^ 1), nullptr);
+          __syncwarp();
+          unsigned char* yb = s_y + (size_t)b * RC_YROW + m * 16;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(yb + c * (RC_M * 16)) = o[c];
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&y_full[b]));
+        } else if (live) {
+          const int po = p.pad_out;
+          const int Hp = p.H + 2 * po, Wp = p.W + 2 * po;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c >= p.out_chunks) break;
+            uint4* dst = reinterpret_cast<uint4*>(p.out) + (((size_t)n * p.out_chunks + c) * Hp + (Y + po)) * Wp + (x + po);
+            *dst = o[c];
+            if (po) {      // replicate the border pixels into the ring (input of the phase-decomposed upconv)
+              const int dyv = (Y == 0) ? -1 : ((Y == p.H - 1) ? 1 : 0);
+              const int dxv = (x == 0) ? -1 : ((x == p.W - 1) ? 1 : 0);
+              if (dyv != 0) dst[dyv * Wp] = o[c];
+              if (dxv != 0) dst[dxv] = o[c];
+              if (dyv != 0 && dxv != 0) dst[dyv * Wp + dxv] = o[c];
+            }
+          }
+        }
+      }
+    }
+  } else if (TAIL) {
+    // ===================== soft-argmax: 2 sets x 4 lane quadrants, 32 pixels per warp; TMEM lane = channel, column m of
+    // the accumulator = pixel xw + 2 + m; set k takes the rows with g % 2 == k (= predictor accumulator k) ==========
+    const int e = warp - W_SOFT;
+    const int q = warp & 3, set = e >> 2;
+    const int col0 = 32 * q;
+    const bool active = lane < p.c_pred;
+    const float bias = active ? p.pbias[lane] : 0.f;
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + RC_PACC + (uint32_t)(set * 128 + col0);
+    const uint32_t pf = smem_u32(&p_full[set]), pe = smem_u32(&p_empty[set]);
+    const int H = p.H, W = p.W;
+    int g0 = 0;
+    for (long long item = blockIdx.x; item < p.items; item += gridDim.x, g0 += H) {
+      const int n = (int)(item / p.strips), s = (int)(item - (long long)n * p.strips);
+      const int xs = rc2_window(s, p.strips, W) + 2;           // pixel of accumulator column 0
+      const int x0 = xs + col0;
+      const int lo = max(0, xs), hi = (s == p.strips - 1) ? min(W, xs + R2_VW) : min(W - 118, xs + R2_VW);
+      SoftState st{PR_NEG, 0.f, 0.f, 0.f};
+      const bool any0 = x0 < hi && x0 + 16 > lo, any1 = x0 + 16 < hi && x0 + 32 > lo;
+      const bool full0 = x0 >= lo && x0 + 16 <= hi, full1 = x0 + 16 >= lo && x0 + 32 <= hi;
+      for (int Y = (g0 ^ set) & 1; Y < H; Y += 2) {
+        const int g = g0 + Y;
+        mbar_wait(pf, (uint32_t)((g >> 1) & 1), nullptr);
+        if (!(any0 || any1)) {       // nothing to reduce in these columns, but the accumulator hand-shake goes on
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pe);
+          continue;
+        }
+        tc_fence_after();
+        uint32_t v0[16], v1[16];
+        tmem_ld16_nowait(t_addr, v0);
+        tmem_ld16_nowait(t_addr + 16u, v1);
+        tmem_ld_wait(v0);
+        tmem_ld_wait(v1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pe);      // the values are in registers: release the accumulator
+        if (p.dbg & 1) continue;
+        if (full0)
+          softargmax_row16(st, v0, bias, x0, Y);
+        else if (any0)
+          softargmax_row16_range(st, v0, bias, x0, Y, lo, hi);
+        if (full1)
+          softargmax_row16(st, v1, bias, x0 + 16, Y);
+        else if (any1)
+          softargmax_row16_range(st, v1, bias, x0 + 16, Y, lo, hi);
+      }
+      if (active) p.partial[((size_t)n * p.c_pred + lane) * p.slots + s * R2_SOFT_WARPS + e] = make_float4(st.m, st.s, st.sx, st.sy);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // weights OIHW f32 (C_out <= 32, C_in <= 64, 3, 3) -> [kb][kw][2 chunks][96 = kh * 32 + co][8 ch] bf16
 __global__ void __launch_bounds__(256)
 rc_pack_weights_kernel(const float* __restrict__ w, int C_out, int C_in, int kb, __nv_bfloat16* __restrict__ out) {
@@ -711,8 +1233,16 @@ rc_pack_weights_kernel(const float* __restrict__ w, int C_out, int C_in, int kb,
   }
 }
 
+struct Rc2Host {              // the second conv of tc_rowconv2_kernel
+  const void* wb96;
+  const float* bias_b;
+  int relu_b;
+  bool tail;
+};
+
 static int rc_launch(const char* who, bool fuse, const ynet_tc_src* srcs, int n_src, const ynet_tc_src* partial, int N,
-                     int H, int W, RcParams& p, void* stream, const ynet_tc_wp_src* wp = nullptr) {
+                     int H, int W, RcParams& p, void* stream, const ynet_tc_wp_src* wp = nullptr,
+                     const Rc2Host* two = nullptr) {
   if (!(srcs && n_src >= 1 && n_src <= 3)) {
     set_error("%s: 1..3 conv sources", who);
     return YNET_E_INVALID;
@@ -773,7 +1303,7 @@ static int rc_launch(const char* who, bool fuse, const ynet_tc_src* srcs, int n_
   for (int i = n_src; i < 3; ++i) maps[i] = maps[0];
   CUtensorMap mapw = maps[0], mapw120 = maps[0], mapz = maps[0];
   if (wp != nullptr) {
-    if (fuse || !(wp->tmpl_c8 && wp->coords) || reinterpret_cast<uintptr_t>(wp->tmpl_c8) % 16 != 0 || wp->n_ch < 1 ||
+    if ((fuse && two == nullptr) || !(wp->tmpl_c8 && wp->coords) || reinterpret_cast<uintptr_t>(wp->tmpl_c8) % 16 != 0 || wp->n_ch < 1 ||
         wp->n_ch > 2 || wp->level < 0 || wp->level > 1 || n_src > 2 || wp->th < (H << wp->level) ||
         wp->tw < (W << wp->level) || (wp->level == 1 && ((wp->th | wp->tw) & 1)) || W < 120) {
       set_error("%s: waypoint source: 1 or 2 channels, level 0 or 1, (even-sized) template at least as large as the "
@@ -829,7 +1359,7 @@ static int rc_launch(const char* who, bool fuse, const ynet_tc_src* srcs, int n_
   if (partial != nullptr) {
     const int pc = partial->channels_pad / 8;
     if (!partial->ptr || reinterpret_cast<uintptr_t>(partial->ptr) % 16 != 0 || !(pc == 4 || pc == 8) ||
-        partial->batch_stride <= 0 || fuse) {
+        partial->batch_stride <= 0 || (fuse && two == nullptr)) {
       set_error("%s: the partial-sum source must be a 32- or 64-channel (hi | lo) C8 tensor", who);
       return YNET_E_INVALID;
     }
@@ -845,8 +1375,65 @@ static int rc_launch(const char* who, bool fuse, const ynet_tc_src* srcs, int n_
   p.kb = chunks / 2;
   p.chunks = chunks;
   p.strips = (wp != nullptr) ? 2 + ceil_div(tmax(0, W - 238), RC_VW) : ceil_div(W, RC_VW);     // WP: see rc_wp_window
+  if (two != nullptr) p.strips = 2 + ceil_div(tmax(0, W - 236), R2_VW);                        // see rc2_window
   p.items = (long long)N * p.strips;
   p.row_bytes = p.chunks * RC_CHUNK_BYTES;
+  if (two != nullptr) {
+    if (wp == nullptr || n_src > 2) {
+      set_error("%s: the two-conv kernel takes one or two tensor sources and the waypoint source", who);
+      return YNET_E_INVALID;
+    }
+    Rc2Params pp;
+    pp.a = p;
+    pp.wb96 = reinterpret_cast<const unsigned char*>(two->wb96);
+    pp.bias_b = two->bias_b;
+    pp.relu_b = two->relu_b;
+    CUtensorMap mapp = maps[0];
+    if (partial != nullptr) {
+      if (p.part_chunks != 4) {
+        set_error("%s: the two-conv kernel takes hi-only partial sums (32 channels)", who);
+        return YNET_E_UNSUPPORTED;
+      }
+      const int bmod = partial->batch_mod;
+      const int nimg = bmod > 0 ? bmod : (bmod < 0 ? ceil_div(N, -bmod) : N);
+      const cuuint64_t dims[4] = {(cuuint64_t)W * 2, (cuuint64_t)H, 4, (cuuint64_t)nimg};
+      const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)partial->batch_stride * 2};
+      const cuuint32_t box[4] = {(cuuint32_t)RC_M * 2, 1, 4, 1};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = encode(&mapp, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(partial->ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("%s: cuTensorMapEncodeTiled failed (%d) for the partial sums", who, (int)r);
+        return YNET_E_CUDA;
+      }
+    }
+    const size_t smem2 = (size_t)p.kb * 3 * RC_WBLK + 2 * 3 * RC_WBLK + (size_t)R2_NSTG * p.row_bytes + 1024 +
+                         (size_t)R2_NA * RC_YROW + 1024 + (size_t)(two->tail ? 8 : 4) * R2_PROW +
+                         (two->tail ? (size_t)R2_NY * RC_YROW + 2 * PR_WBLK_BYTES : 0) + 64 * 4 + 80 * 8 + 16 + 1024;
+    static bool configured2 = false;
+    if (!configured2) {
+      cudaError_t e = cudaFuncSetAttribute(tc_rowconv2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(tc_rowconv2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, who);
+      configured2 = true;
+    }
+    if (smem2 > 226 * 1024) {
+      set_error("%s: layer does not fit shared memory", who);
+      return YNET_E_UNSUPPORTED;
+    }
+    const long long grid2 = tmin<long long>(p.items, (long long)sm_count());
+    if (two->tail)
+      tc_rowconv2_kernel<true><<<(unsigned)grid2, R2_THREADS_TAIL, smem2, as_stream(stream)>>>(maps[0], maps[1], mapw, mapw120,
+                                                                                              mapz, mapp, pp);
+    else
+      tc_rowconv2_kernel<false><<<(unsigned)grid2, R2_THREADS_PLAIN, smem2, as_stream(stream)>>>(maps[0], maps[1], mapw,
+                                                                                                mapw120, mapz, mapp, pp);
+    cudaError_t le2 = cudaGetLastError();
+    if (le2 != cudaSuccess) return cuda_fail(le2, who);
+    return YNET_OK;
+  }
   const size_t smem = (size_t)p.kb * 3 * RC_WBLK + (size_t)(fuse ? RC_STAGES_FUSED : RC_STAGES_PLAIN) * p.row_bytes + 1024 +
                       (fuse ? (size_t)RC_NY * RC_YROW + 2 * PR_WBLK_BYTES : 0) + 80 * 8 + 16 + 1024;
   static bool configured = false;
@@ -939,6 +1526,69 @@ int ynet_tc_rowconv3x3_wp(const ynet_tc_src* srcs, int32_t n_src, const ynet_tc_
   p.out = reinterpret_cast<__nv_bfloat16*>(out_c8);
   p.out_chunks = C_out_pad / 8;
   return rc_launch("ynet_tc_rowconv3x3_wp", false, srcs, n_src, partial, N, H, W, p, stream, wp);
+}
+
+int ynet_tc_rowconv2_wp(const ynet_tc_src* srcs, int32_t n_src, const ynet_tc_src* partial, const ynet_tc_wp_src* wp, int32_t N,
+                        int32_t H, int32_t W, const void* packed_weight_a, const float* bias32_a, const void* packed_weight_b,
+                        const float* bias32_b, int32_t C_out, int32_t relu, void* out_c8, int32_t C_out_pad, void* stream) {
+  YNET_CHECK_ARG(packed_weight_a && bias32_a && packed_weight_b && bias32_b && wp && (out_c8 || N == 0), "null pointer");
+  YNET_CHECK_ARG(C_out > 0 && C_out <= RC_CO && C_out_pad % 16 == 0 && C_out_pad >= C_out && C_out_pad <= RC_CO, "C_out <= 32");
+  YNET_CHECK_ALIGN(packed_weight_a, 16);
+  YNET_CHECK_ALIGN(packed_weight_b, 16);
+  YNET_CHECK_ALIGN(out_c8, 16);
+  RcParams p;
+  memset(&p, 0, sizeof(p));
+  p.w96 = reinterpret_cast<const unsigned char*>(packed_weight_a);
+  p.bias = bias32_a;
+  p.relu = 1;
+  p.pad_out = (relu & 2) ? 1 : 0;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out_c8);
+  p.out_chunks = C_out_pad / 8;
+  const Rc2Host two{packed_weight_b, bias32_b, relu & 1, false};
+  return rc_launch("ynet_tc_rowconv2_wp", false, srcs, n_src, partial, N, H, W, p, stream, wp, &two);
+}
+
+int64_t ynet_tc_rowconv2_softargmax_workspace_bytes(int32_t N, int32_t C_pred, int32_t W) {
+  if (N <= 0 || C_pred <= 0 || W < 120) return 0;
+  return (int64_t)N * C_pred * (2 + ceil_div(tmax(0, W - 236), R2_VW)) * R2_SOFT_WARPS * (int64_t)sizeof(float4);
+}
+
+int ynet_tc_rowconv2_wp_pred_softargmax(const ynet_tc_src* srcs, int32_t n_src, const ynet_tc_src* partial,
+                                        const ynet_tc_wp_src* wp, int32_t N, int32_t H, int32_t W, const void* packed_weight_a,
+                                        const float* bias32_a, const void* packed_weight_b, const float* bias32_b,
+                                        int32_t relu_b, const void* packed_pred_weight, const float* pred_bias, int32_t C_pred,
+                                        float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  YNET_CHECK_ARG(packed_weight_a && bias32_a && packed_weight_b && bias32_b && packed_pred_weight && pred_bias && wp &&
+                     (out || N == 0),
+                 "null pointer");
+  YNET_CHECK_ARG(C_pred > 0 && C_pred <= 32, "C_pred <= 32");
+  YNET_CHECK_ALIGN(packed_weight_a, 16);
+  YNET_CHECK_ALIGN(packed_weight_b, 16);
+  YNET_CHECK_ALIGN(packed_pred_weight, 16);
+  if (N == 0) return YNET_OK;
+  if (workspace == nullptr || workspace_bytes < ynet_tc_rowconv2_softargmax_workspace_bytes(N, C_pred, W) || W < 120) {
+    set_error("ynet_tc_rowconv2_wp_pred_softargmax: workspace too small (or W < 120)");
+    return YNET_E_WORKSPACE;
+  }
+  YNET_CHECK_ALIGN(workspace, 16);
+  RcParams p;
+  memset(&p, 0, sizeof(p));
+  p.w96 = reinterpret_cast<const unsigned char*>(packed_weight_a);
+  p.bias = bias32_a;
+  p.relu = 1;
+  p.pw = reinterpret_cast<const unsigned char*>(packed_pred_weight);
+  p.pbias = pred_bias;
+  p.partial = reinterpret_cast<float4*>(workspace);
+  p.c_pred = C_pred;
+  p.pn_pad = ceil_div(C_pred, 16) * 16;
+  p.kbp = 2;
+  p.slots = (2 + ceil_div(tmax(0, W - 236), R2_VW)) * R2_SOFT_WARPS;
+  const Rc2Host two{packed_weight_b, bias32_b, relu_b & 1, true};
+  int rc = rc_launch("ynet_tc_rowconv2_wp_pred_softargmax", true, srcs, n_src, partial, N, H, W, p, stream, wp, &two);
+  if (rc != YNET_OK) return rc;
+  cudaError_t le = pred_partial_finalize(p.partial, N * C_pred, p.slots, out, as_stream(stream));
+  if (le != cudaSuccess) return cuda_fail(le, "ynet_tc_rowconv2_wp_pred_softargmax");
+  return YNET_OK;
 }
 
 int64_t ynet_tc_rowconv_softargmax_workspace_bytes(int32_t N, int32_t C_pred, int32_t W) {

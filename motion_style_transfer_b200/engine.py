@@ -542,9 +542,8 @@ class YNetEngineTC(YNetEngine):
             lazy = lvl + 1
         return lazy
 
-    def _tconv_hoisted_row(self, module, key, up, partial, pyr_level, c_feat):
-        """The same through the row-marching kernel: conv sources [up, waypoint planes] side by side on the K axis, the
-        hoisted partial added in fp32 by the epilogue (no identity-weight MMAs)."""
+    def _rowhoist_params(self, module, key, up, pyr_level, c_feat):
+        """(packed weights, 32-float bias) of decoder.i.0 for the row kernels: sources [up, waypoint planes]."""
         srcs = [up, pyr_level]
         ver = (module.weight._version, module.weight.data_ptr(), tuple(s.K_pad for s in srcs), c_feat,
                _bias_version(module), isinstance(pyr_level, ops.WpPlanes))
@@ -560,7 +559,43 @@ class YNetEngineTC(YNetEngine):
                 bias[:w.shape[0]] = module.bias.detach()
             hit = (ver, ops.tc_rowconv_pack_weights_cat(w, parts), bias)
             self._wcache[key + '#rowhoist'] = hit
-        return ops.tc_rowconv3x3(srcs, hit[1], hit[2], module.weight.shape[0], True, partial=partial)
+        return hit[1], hit[2]
+
+    def _tconv_hoisted_row(self, module, key, up, partial, pyr_level, c_feat):
+        """The same through the row-marching kernel: conv sources [up, waypoint planes] side by side on the K axis, the
+        hoisted partial added in fp32 by the epilogue (no identity-weight MMAs)."""
+        packed, bias = self._rowhoist_params(module, key, up, pyr_level, c_feat)
+        return ops.tc_rowconv3x3([up, pyr_level], packed, bias, module.weight.shape[0], True, partial=partial)
+
+    # decoder.i.0 + decoder.i.2 (+ predictor + soft-argmax at the last level) in ONE kernel (tc_rowconv2_kernel): the
+    # 32-channel activation between the two convs of a block stays in shared memory
+    rowconv2 = os.environ.get('YNET_ROWCONV2', '1') == '1'
+    # ... and with the predictor + soft-argmax behind it.  Correct and tested, but measured slower than decoder.4.0 followed by
+    # the fused decoder.4.2 tail kernel (4.0-4.8 vs 2.9 ms per 320 images): with one 896-thread CTA per SM (72 registers per
+    # thread, 512 TMEM columns shared by two 4-slot rings and the predictor) the three MMA streams run at ~35 % of the
+    # tensor pipe's 720 cycles per row.  Off by default.
+    rowconv2_tail = os.environ.get('YNET_ROWCONV2_TAIL', '0') == '1'
+
+    def _block_fused(self, decoder, key, i, up, partial, pyr_level, c_feat, tail):
+        """The fused block, or None when it does not apply.  tail: predictor + SoftArgmax2D behind it -> (N, C_pred, 2)."""
+        c0, c2 = decoder.decoder[i][0], decoder.decoder[i][2]
+        if not (self.rowconv2 and self.rowconv and isinstance(pyr_level, ops.WpPlanes) and partial.C_pad in (32, 64)
+                and partial.H == up.H and ops.tc_rowconv2_supported([up, pyr_level], c0.weight.shape[0], c2.weight.shape[0])
+                and not _is_adapter_layer(c0) and not _is_adapter_layer(c2)):
+            return None
+        pa, ba = self._rowhoist_params(c0, f'{key}.decoder.{i}.0', up, pyr_level, c_feat)
+        pb, bb = self._rowconv_params(c2, f'{key}.decoder.{i}.2', 32)
+        if tail:
+            if not self.rowconv2_tail:
+                return None
+            pred = decoder.predictor
+            if pred.weight.shape[0] > 32 or c2.weight.shape[0] != 32 or up.K_pad > 16:
+                return None
+            ppacked, pbias = self._tc_params(pred, f'{key}.predictor', [32])
+            return ops.tc_rowconv2_wp_pred_softargmax([up, pyr_level], pa, ba, pb, bb, True, ppacked, pbias,
+                                                      pred.weight.shape[0], partial=partial)
+        return ops.tc_rowconv2_wp([up, pyr_level], pa, ba, pb, bb, c2.weight.shape[0], True,
+                                  pad_out=self._feeds_upconv(decoder, i), partial=partial)
 
     def _tconv_hoisted(self, module, key, up, partial, pyr_level, c_feat):
         """conv(cat(up, feature, waypoints)) with the feature share taken from ``partial``."""
@@ -604,9 +639,15 @@ class YNetEngineTC(YNetEngine):
         x = self._tconv(decoder.center[2], f'{key}.center.2', [x], True, self._feeds_upconv(decoder, -1))
         for i in range(len(partials) - 1):
             up = self._tupconv(decoder.upsample_conv[i], f'{key}.upsample_conv.{i}', [x])
+            last = i == len(partials) - 2
+            fused = self._block_fused(decoder, key, i, up, partials[i + 1], pyr_rev[i + 1], c_feats[i + 1], last and softargmax)
+            if fused is not None:
+                if last and softargmax:
+                    return fused
+                x = fused
+                continue
             x = self._tconv_hoisted(decoder.decoder[i][0], f'{key}.decoder.{i}.0', up, partials[i + 1], pyr_rev[i + 1],
                                     c_feats[i + 1])
-            last = i == len(partials) - 2
             if (last and softargmax and self._use_rowconv(decoder.decoder[i][2], [x]) and x.K_pad <= 32
                     and decoder.predictor.weight.shape[0] <= 32):
                 return self._conv_pred_softargmax_row(decoder.decoder[i][2], f'{key}.decoder.{i}.2', x, decoder.predictor,

@@ -1319,6 +1319,67 @@ def tc_rowconv3x3(a, packed_weight, bias32, C_out, relu, pad_out=False, partial=
     return C8(out, C_out, 1, False, po)
 
 
+def _rowconv2_args(srcs, partial):
+    srcs = list(srcs)
+    wp = srcs.pop()
+    if not isinstance(wp, WpPlanes) or not 1 <= len(srcs) <= 2:
+        raise ValueError('tc_rowconv2: sources = one or two C8 tensors followed by WpPlanes')
+    N = max(s.N for s in srcs + ([partial] if partial is not None else []))
+    H, W = srcs[0].H, srcs[0].W
+    if wp.N != N or wp.H != H or wp.W != W:
+        raise ValueError('tc_rowconv2: the waypoint planes cover another batch / resolution')
+    parr = None
+    in_bytes = sum(2.0 * s.C_pad * min(s.data.shape[0], N) for s in srcs) * H * W
+    if partial is not None:
+        parr = _rowconv_srcs([partial], N)
+        parr[0].channels_pad = partial.C_pad
+        in_bytes += 2.0 * partial.C_pad * min(partial.data.shape[0], N) * H * W
+    w = _lib.TcWpSrc(wp.planes.data_ptr(), wp.coords.data_ptr(), wp.template.shape[0], wp.template.shape[1], wp.C, wp.level)
+    k_pad = sum(s.K_pad for s in srcs) + 16
+    c_in = sum(s.C for s in srcs) + wp.C
+    return srcs, wp, w, parr, N, H, W, in_bytes, k_pad, c_in
+
+
+def tc_rowconv2_supported(srcs, C_mid, C_out):
+    """Can the two-conv row kernel take conv A's sources (C8 tensors + WpPlanes last) with 32 channels in between?"""
+    return (isinstance(srcs[-1], WpPlanes) and tc_rowconv_supported(srcs, C_mid) and C_mid == 32 and C_out <= 32
+            and srcs[0].W >= 120)
+
+
+def tc_rowconv2_wp(srcs, packed_a, bias32_a, packed_b, bias32_b, C_out, relu, pad_out=False, partial=None):
+    """conv3x3(cat(srcs)) + partial + ReLU -> conv3x3 (+ReLU) in one kernel (ynet_tc_rowconv2_wp) -> C8 (N, C_out)."""
+    srcs, wp, w, parr, N, H, W, in_bytes, k_pad, c_in = _rowconv2_args(srcs, partial)
+    cp = _pad16(C_out)
+    po = 1 if pad_out else 0
+    out = torch.empty(N, cp // 8, H + 2 * po, W + 2 * po, 8, dtype=torch.bfloat16, device=srcs[0].data.device)
+    tag = f'{k_pad}{"+P" if partial is not None else ""}+W->32->{cp}@{H}x{W} N={N}'
+    with _timed('tc_rowconv2_kernel', 2.0 * 9 * (c_in * 32 + 32 * C_out) * H * W * N, in_bytes + 2.0 * cp * H * W * N, tag=tag):
+        check(_L().ynet_tc_rowconv2_wp(_rowconv_srcs(srcs, N), len(srcs), parr, ctypes.byref(w), N, H, W, _ptr(packed_a),
+                                       _ptr(bias32_a), _ptr(packed_b), _ptr(bias32_b), C_out, (1 if relu else 0) | (2 * po),
+                                       _ptr(out), cp, _stream()), 'tc_rowconv2_wp')
+    _count()
+    return C8(out, C_out, 1, False, po)
+
+
+def tc_rowconv2_wp_pred_softargmax(srcs, packed_a, bias32_a, packed_b, bias32_b, relu_b, packed_pred, pred_bias_pad, C_pred,
+                                   partial=None):
+    """conv + partial + ReLU -> conv (+ReLU) -> 1x1 predictor -> SoftArgmax2D in one kernel -> (N, C_pred, 2)."""
+    srcs, wp, w, parr, N, H, W, in_bytes, k_pad, c_in = _rowconv2_args(srcs, partial)
+    out = torch.empty(N, C_pred, 2, dtype=torch.float32, device=srcs[0].data.device)
+    nb = _L().ynet_tc_rowconv2_softargmax_workspace_bytes(N, C_pred, W)
+    ws = _workspace(nb, out.device, 'tc_rowconv2_softargmax')
+    tag = f'{k_pad}{"+P" if partial is not None else ""}+W->32->32->{C_pred}@{H}x{W} N={N}'
+    with _timed('tc_rowconv2_kernel<pred,softargmax>', 2.0 * (9 * (c_in * 32 + 32 * 32) + 32 * C_pred) * H * W * N, in_bytes,
+                tag=tag):
+        check(_L().ynet_tc_rowconv2_wp_pred_softargmax(_rowconv_srcs(srcs, N), len(srcs), parr, ctypes.byref(w), N, H, W,
+                                                       _ptr(packed_a), _ptr(bias32_a), _ptr(packed_b), _ptr(bias32_b),
+                                                       1 if relu_b else 0, _ptr(packed_pred), _ptr(pred_bias_pad), C_pred,
+                                                       _ptr(out), _ptr(ws), ws.numel(), _stream()),
+              'tc_rowconv2_wp_pred_softargmax')
+    _count(2)
+    return out
+
+
 def tc_rowconv3x3_pred_softargmax(a, packed_weight, bias32, C_out, relu, packed_pred, pred_bias_pad, C_pred):
     """conv3x3 (+bias, +ReLU) -> 1x1 predictor -> SoftArgmax2D in one kernel: C8 (N, <= 64 ch) -> (N, C_pred, 2)."""
     out = torch.empty(a.N, C_pred, 2, dtype=torch.float32, device=a.data.device)

@@ -206,3 +206,57 @@ def test_rowconv_gathered_waypoint_planes_bit_exact(ops, n_wp, level, H0, W0, N)
     ref2 = ops.tc_rowconv3x3([up, planes], packed, _bias32(b), 32, True, pad_out=True, partial=part)
     got2 = ops.tc_rowconv3x3([up, lazy], packed_l, _bias32(b), 32, True, pad_out=True, partial=part)
     assert torch.equal(got2.data, ref2.data)
+
+
+@pytest.mark.parametrize('n_wp,level,H0,W0,N,G,c_up', [(2, 0, 64, 160, 4, 2, 16), (2, 1, 64, 416, 4, 2, 32), (1, 0, 32, 416, 2, 1, 16),
+                                                       (2, 0, 416, 416, 2, 2, 16), (2, 0, 64, 256, 6, 3, 16)])
+def test_rowconv2_block_equals_unfused_chain(ops, n_wp, level, H0, W0, N, G, c_up):
+    """ynet_tc_rowconv2_wp: decoder.i.0 (+ partial sums, ReLU) and decoder.i.2 in one kernel == the two row-kernel launches
+    with the activation round-tripping through HBM, bit for bit (same MMAs in the same order per output pixel); plain and
+    replicate-padded output; agent-major partial sums (image n reads partial n // G)."""
+    torch.manual_seed(6)
+    H, W = H0 >> level, W0 >> level
+    tmpl = ops.create_dist_template(3 * max(H0, W0), 'cuda')
+    coords = torch.stack([torch.rand(N * n_wp) * (W0 - 1), torch.rand(N * n_wp) * (H0 - 1)], 1)
+    coords[0] = torch.tensor([0.5, 1.5])
+    coords[-1] = torch.tensor([W0 - 1.0, H0 - 1.0])
+    coords = coords.cuda().contiguous()
+    lazy = ops.tc_rasterize_pyramid(tmpl, coords, N, n_wp, H0, W0, level + 1, lazy_levels=level + 1)[level]
+    up = ops.tc_pack(bf16_exact(torch.randn(N, c_up, H, W)).cuda())
+    feat = ops.tc_pack(bf16_exact(torch.relu(torch.randn(N // G, 32, H, W))).cuda())
+    wa = bf16_exact(torch.randn(32, c_up + 32 + n_wp, 3, 3) * 0.1)
+    ba, bb = torch.randn(32) * 0.1, torch.randn(32) * 0.1
+    wb = bf16_exact(torch.randn(32, 32, 3, 3) * 0.1)
+    part = ops.tc_conv3x3_hilo([feat], ops.tc_pack_weights(wa[:, c_up:c_up + 32].contiguous().cuda(), [32]), 32,
+                               False).repeat_interleave(G)
+    pa = ops.tc_rowconv_pack_weights_cat(wa.cuda(), [(0, c_up, c_up)] + lazy.weight_parts(c_up + 32))
+    pb = ops.tc_rowconv_pack_weights(wb.cuda(), 32)
+    assert ops.tc_rowconv2_supported([up, lazy], 32, 32)
+    mid = ops.tc_rowconv3x3([up, lazy], pa, _bias32(ba), 32, True, partial=part)
+    for pad_out in (False, True):
+        ref = ops.tc_rowconv3x3(mid, pb, _bias32(bb), 32, True, pad_out=pad_out)
+        got = ops.tc_rowconv2_wp([up, lazy], pa, _bias32(ba), pb, _bias32(bb), 32, True, pad_out=pad_out, partial=part)
+        torch.cuda.synchronize()
+        assert got.pad == ref.pad and torch.equal(got.data, ref.data)
+    # no ReLU behind conv B, fewer output channels, and a second launch on a clean accumulator ring
+    wb2 = bf16_exact(torch.randn(20, 32, 3, 3) * 0.1)
+    pb2 = ops.tc_rowconv_pack_weights(wb2.cuda(), 32)
+    ref2 = ops.tc_rowconv3x3(mid, pb2, _bias32(bb[:20]), 20, False)
+    got2 = ops.tc_rowconv2_wp([up, lazy], pa, _bias32(ba), pb2, _bias32(bb[:20]), 20, False, partial=part)
+    assert torch.equal(got2.data, ref2.data)
+    if c_up > 16:
+        return                     # (the tail kernel keeps an 8-row partial-sum ring: <= 32 input channels in conv A)
+    # tail: predictor + soft-argmax behind conv B (other strip partition of the sums: float32 order differs)
+    wp1 = bf16_exact(torch.randn(30, 32, 1, 1) * 0.5)
+    ppk = ops.tc_pack_weights(wp1.cuda(), [32])
+    pbias = torch.zeros(32)
+    pbias[:30] = torch.randn(30)
+    refs = ops.tc_rowconv3x3_pred_softargmax(mid, pb, _bias32(bb), 32, True, ppk, pbias.cuda(), 30)
+    gots = ops.tc_rowconv2_wp_pred_softargmax([up, lazy], pa, _bias32(ba), pb, _bias32(bb), True, ppk, pbias.cuda(), 30,
+                                              partial=part)
+    torch.cuda.synchronize()
+    assert gots.shape == (N, 30, 2)
+    np.testing.assert_allclose(gots.cpu().numpy(), refs.cpu().numpy(), rtol=0, atol=2e-3)
+    again = ops.tc_rowconv2_wp_pred_softargmax([up, lazy], pa, _bias32(ba), pb, _bias32(bb), True, ppk, pbias.cuda(), 30,
+                                               partial=part)
+    assert torch.equal(again, gots)

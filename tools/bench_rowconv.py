@@ -89,3 +89,24 @@ if MODE in ('wp',):
     packed3 = ops.tc_rowconv_pack_weights_cat(w2, [(0, 16, 16)] + lazy[0].weight_parts(48))
     timeit('row conv [up|P|wp template]', lambda: ops.tc_rowconv3x3([up, lazy[0]], packed3, bias, 32, True, partial=part),
            2.0 * 9 * 18 * 32 * S2, (32.0 + 64.0) * S2)
+
+if MODE in ('rc2',):
+    # decoder.4.0 + decoder.4.2 (+ predictor + soft-argmax) in one kernel against the separate launches
+    G = 20
+    nb = N // G
+    up = ops.tc_pack(torch.randn(nb * G, 16, HW, HW, device='cuda'))
+    tmpl = ops.create_dist_template(int(2.5 * HW), 'cuda')
+    coords = (torch.rand(nb * G * 2, 2, device='cuda') * (HW - 1)).contiguous()
+    lazy = ops.tc_rasterize_pyramid(tmpl, coords, nb * G, 2, HW, HW, 1, lazy_levels=1)[0]
+    feat = ops.tc_pack(torch.relu(torch.randn(nb, 32, HW, HW, device='cuda')))
+    w2 = torch.randn(32, 50, 3, 3, device='cuda') * 0.1
+    part = ops.tc_conv3x3_hilo([feat], ops.tc_pack_weights(w2[:, 16:48].contiguous(), [32]), 32, False).repeat_interleave(G)
+    pa = ops.tc_rowconv_pack_weights_cat(w2, [(0, 16, 16)] + lazy.weight_parts(48))
+    S2 = HW * HW * nb * G
+    fl = 2.0 * 9 * (18 * 32 + 32 * 32) * S2
+    timeit('L1 row conv [up|P|wp template]', lambda: ops.tc_rowconv3x3([up, lazy], pa, bias, 32, True, partial=part),
+           2.0 * 9 * 18 * 32 * S2, (32.0 + 64.0) * S2)
+    timeit('two-conv block -> HBM', lambda: ops.tc_rowconv2_wp([up, lazy], pa, bias, packed_row, bias, 32, True, partial=part),
+           fl, (32.0 + 64.0) * S2)
+    timeit('two-conv block + pred + softargmax', lambda: ops.tc_rowconv2_wp_pred_softargmax(
+        [up, lazy], pa, bias, packed_row, bias, True, ppacked, pb, 30, partial=part), fl + 2.0 * 32 * 30 * S2, 32.0 * S2)
