@@ -343,6 +343,8 @@ def run_finetune_mode(args, cfg, rank, world, dev):
     from motion_style_transfer_b200.utils.image_utils import create_dist_mat, create_gaussian_heatmap_template
     from motion_style_transfer_b200.utils.train_epoch import train_epoch
     model = build_model_state(cfg).to(dev)
+    if args.backend == 'bf16x3':          # forward + data-gradient convs on the tensor cores (split-bf16); default: fp32 kernels
+        model.set_backend('bf16x3')
     net = cfg.get('network', 'original')
     pos = cfg.get('position', [0, 1, 2, 3, 4])
     apply_freeze_policy(model, 'mosa_1', pos, net)
@@ -379,7 +381,7 @@ def run_finetune_mode(args, cfg, rank, world, dev):
         print(json.dumps({
             'metric': 'fine-tune optimiser steps/sec (train_epoch drop-in, MoSA r=1 adapters)', 'mode': 'finetune',
             'value': 1000.0 / ms, 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'bf16x3 (forward + dgrad), f32 (wgrad, Adam)' if args.backend == 'bf16x3' else 'f32',
             'data': 'synthetic',
             'config': {'workload': workload_name(args, cfg).replace(' eval,', ' fine-tune,'), 'agents_per_step': bs,
                        'steps_per_epoch': n_batches, 'trainable_floats': int(sum(q.numel() for q in trainable)),

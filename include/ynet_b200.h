@@ -323,6 +323,9 @@ int ynet_tc_conv3x3_split(const ynet_tc_src* srcs_host, int32_t n_src, int32_t N
                           int32_t C_out_pad, int32_t out_total_pad, int32_t out_channel_off, int32_t tune, void* stream);
 int ynet_split_pack_f32(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, int64_t batch_stride, void* out_split,
                         int32_t C_pad, int32_t out_total_pad, int32_t out_channel_off, void* stream);
+/* dy * (relu_out > 0) -> split planes: the ReLU backward folded into the split of a gradient (contiguous NCHW float32) */
+int ynet_split_pack_masked_f32(const float* x, const float* relu_out, int32_t N, int32_t C, int32_t H, int32_t W,
+                               void* out_split, int32_t C_pad, void* stream);
 int ynet_split_unpack_f32(const void* x_split, int32_t N, int32_t C, int32_t C_pad, int32_t H, int32_t W, float* out,
                           void* stream);
 int ynet_split_maxpool2x2(const void* x_split, int32_t N, int32_t C_pad, int32_t H, int32_t W, void* out_split, void* stream);

@@ -97,6 +97,7 @@ _PROTOS = {
     'ynet_tc_conv3x3_hilo': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P]),
     'ynet_tc_conv3x3_split': (c_int, [POINTER(TcSrc), _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _I, _I, _I, _P]),
     'ynet_split_pack_f32': (c_int, [_P, _I, _I, _I, _I, _L, _P, _I, _I, _I, _P]),
+    'ynet_split_pack_masked_f32': (c_int, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
     'ynet_split_unpack_f32': (c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
     'ynet_split_maxpool2x2': (c_int, [_P, _I, _I, _I, _I, _P, _P]),
     'ynet_split_upsample2x': (c_int, [_P, _I, _I, _I, _I, _P, _P]),

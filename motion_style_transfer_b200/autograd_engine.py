@@ -6,6 +6,8 @@ torch.autograd is plumbing here (graph bookkeeping, gradient accumulation of the
 tensors); conv forward / dgrad / wgrad, pool / bilinear backward, BCE and the LoRA gradient
 projection (dA = s B^T dM, dB = s dM A^T) are CUDA kernels.
 """
+import os
+
 import torch
 
 from . import ops
@@ -24,14 +26,76 @@ def _materialize(t, mode, N):
     return t
 
 
+# Tensor-core training convs (model.set_backend('bf16x3'), or YNET_TRAIN_TC=1): the forward conv and the data gradient of
+# every layer run as split-bf16 tcgen05 convs (three bf16 MMAs per product, fp32 accumulation: ~1e-5 of the fp32 result,
+# inside the fixture tolerances of tests/test_gpu_train.py) instead of the CUDA-core fp32 kernels; the weight gradient of
+# the few trainable (LoRA / adapter) layers stays on the fp32 wgrad kernel.  The autograd interface stays float32 NCHW:
+# operands are split on entry and results joined on exit (bandwidth-bound passes).
+TRAIN_TC = os.environ.get('YNET_TRAIN_TC', '0') == '1'
+_tc_wcache = {}
+
+
+def _tc_packed(key, ver, make):
+    if ver[0] is None:               # a temporary weight (adapter sum): its address may be recycled, never cache it
+        return make()
+    hit = _tc_wcache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    if len(_tc_wcache) > 512:
+        _tc_wcache.clear()
+    val = make()
+    _tc_wcache[key] = (ver, val)
+    return val
+
+
+def _tc_conv_forward(w_eff, wver, bias, relu, parts):
+    """conv3x3(cat(parts)) + bias (+ReLU): float32 NCHW parts (batch 1 = broadcast) -> float32 NCHW."""
+    from .engine import YNetEngineSplit
+    sp = [ops.split_pack(t) for t in parts]
+    sources, ranges = YNetEngineSplit._group(sp)
+    layouts = tuple(tuple(s.layout) for s in sources)
+    C_out = w_eff.shape[0]
+
+    def make():
+        idx = torch.cat([torch.arange(c0, c1, device=w_eff.device) for c0, c1 in ranges])
+        return ops.split_pack_weights(w_eff.index_select(1, idx).contiguous(), [s.layout for s in sources])
+    packed = _tc_packed(('f', None if wver is None else wver[0]), (wver, layouts, ranges), make)
+    bias_pad = torch.zeros(ops._pad16(C_out), dtype=torch.float32, device=w_eff.device)
+    if bias is not None:
+        bias_pad[:C_out] = bias
+    return ops.split_unpack(ops.tc_conv3x3_split(sources, packed, bias_pad, C_out, relu))
+
+
+def _tc_conv_dgrad(w_eff, wver, dy, relu_out):
+    """d/dx of conv3x3 (+ReLU): dy (masked by the activation) convolved with the flipped, transposed weight."""
+    dys = ops.split_pack_masked(dy, relu_out) if relu_out is not None else ops.split_pack(dy)
+    C_in = w_eff.shape[1]
+
+    def make():
+        w_t = w_eff.flip(2, 3).transpose(0, 1).contiguous()                 # (C_in, C_out, 3, 3)
+        return ops.split_pack_weights(w_t, [dys.layout])
+    packed = _tc_packed(('d', None if wver is None else wver[0]), (wver, tuple(dys.layout)), make)
+    zero = torch.zeros(ops._pad16(C_in), dtype=torch.float32, device=dy.device)
+    return ops.split_unpack(ops.tc_conv3x3_split([dys], packed, zero, C_in, False))
+
+
 class Conv3x3Fn(torch.autograd.Function):
     """conv3x3(cat(sources)) (+ReLU) with LoRA-folded weight; sources may be pooled / upsampled on load."""
 
     @staticmethod
     def forward(ctx, weight, bias, lora_A, lora_B, relu, modes, H, W, *sources):
         N = max(s.shape[0] for s in sources)
-        packed = ops.lora_fold(weight, lora_A, lora_B, packed=True)
-        y = ops.conv3x3_f32(list(zip(sources, modes)), packed, bias, relu, N, H, W)
+        ctx.tc = (TRAIN_TC and ops.tc_supported() and weight.shape[0] <= 256 and 3 * sum(
+            ops._pad16(s.shape[1]) for s in sources) // 16 <= 64)
+        if ctx.tc:
+            w_eff = ops.lora_fold(weight, lora_A, lora_B, packed=False)
+            ctx.wver = (weight.data_ptr(), weight._version, None if lora_A is None else lora_A._version,
+                        None if lora_B is None else lora_B._version) if weight.is_leaf else None
+            parts = [_materialize(s.contiguous(), m, 1) for s, m in zip(sources, modes)]
+            y = _tc_conv_forward(w_eff, ctx.wver, bias, relu, parts)
+        else:
+            packed = ops.lora_fold(weight, lora_A, lora_B, packed=True)
+            y = ops.conv3x3_f32(list(zip(sources, modes)), packed, bias, relu, N, H, W)
         ctx.relu, ctx.modes, ctx.N = relu, modes, N
         ctx.has_lora = lora_A is not None
         ctx.save_for_backward(weight, bias, lora_A, lora_B, y, *sources)
@@ -47,7 +111,7 @@ class Conv3x3Fn(torch.autograd.Function):
         d_sources = [None] * len(sources)
         if any(need[8:]):
             w_eff = ops.lora_fold(weight, lora_A, lora_B, packed=False)
-            dx = ops.conv3x3_dgrad_f32(dy, relu_out, w_eff)
+            dx = _tc_conv_dgrad(w_eff, ctx.wver, dy, relu_out) if ctx.tc else ops.conv3x3_dgrad_f32(dy, relu_out, w_eff)
             c0 = 0
             for i, (s, mode) in enumerate(zip(sources, ctx.modes)):
                 c1 = c0 + s.shape[1]

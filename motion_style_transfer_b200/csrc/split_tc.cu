@@ -50,8 +50,8 @@ inline unsigned split_grid(long long total) {
 
 // NCHW f32 -> split planes.  One thread = one pixel x one 8-channel chunk (two 16 B stores).
 __global__ void __launch_bounds__(256)
-split_pack_kernel(const float* __restrict__ x, int C, int H, int W, long long batch_stride, uint4* __restrict__ out, int chunks,
-                  int chunks_total, int chunk_off, long long total) {
+split_pack_kernel(const float* __restrict__ x, const float* __restrict__ mask, int C, int H, int W, long long batch_stride,
+                  uint4* __restrict__ out, int chunks, int chunks_total, int chunk_off, long long total) {
   const long long S = (long long)H * W;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const long long pix = t % S;
@@ -63,6 +63,8 @@ split_pack_kernel(const float* __restrict__ x, int C, int H, int W, long long ba
     for (int k = 0; k < 8; ++k) {
       const int c = chunk * 8 + k;
       f[k] = (c < C) ? __ldg(x + n * batch_stride + (long long)c * S + pix) : 0.f;
+      // ReLU backward folded into the split (train_epoch.py:109-110 through autograd): dy where the activation was positive
+      if (mask != nullptr && c < C && !(__ldg(mask + (n * C + c) * S + pix) > 0.f)) f[k] = 0.f;
     }
     split_store8(out + ((n * 2 * chunks_total + chunk_off + chunk) * S + pix), (long long)chunks_total * S, f);
   }
@@ -185,8 +187,23 @@ int ynet_split_pack_f32(const float* x, int32_t N, int32_t C, int32_t H, int32_t
   YNET_CHECK_ARG(x && out, "null pointer");
   YNET_CHECK_ALIGN(out, 16);
   const long long total = (long long)N * (C_pad / 8) * H * W;
-  split_pack_kernel<<<split_grid(total), 256, 0, as_stream(stream)>>>(x, C, H, W, batch_stride, reinterpret_cast<uint4*>(out),
-                                                                      C_pad / 8, out_total_pad / 8, out_channel_off / 8, total);
+  split_pack_kernel<<<split_grid(total), 256, 0, as_stream(stream)>>>(x, nullptr, C, H, W, batch_stride,
+                                                                      reinterpret_cast<uint4*>(out), C_pad / 8,
+                                                                      out_total_pad / 8, out_channel_off / 8, total);
+  YNET_LAUNCH_CHECK();
+  return YNET_OK;
+}
+
+int ynet_split_pack_masked_f32(const float* x, const float* relu_out, int32_t N, int32_t C, int32_t H, int32_t W, void* out,
+                               int32_t C_pad, void* stream) {
+  YNET_CHECK_ARG(N >= 0 && C > 0 && H > 0 && W > 0 && C_pad >= C && C_pad % 16 == 0, "bad shape (C_pad % 16 == 0)");
+  if (N == 0) return YNET_OK;
+  YNET_CHECK_ARG(x && relu_out && out, "null pointer");
+  YNET_CHECK_ALIGN(out, 16);
+  const long long total = (long long)N * (C_pad / 8) * H * W;
+  split_pack_kernel<<<split_grid(total), 256, 0, as_stream(stream)>>>(x, relu_out, C, H, W, (long long)C * H * W,
+                                                                      reinterpret_cast<uint4*>(out), C_pad / 8, C_pad / 8, 0,
+                                                                      total);
   YNET_LAUNCH_CHECK();
   return YNET_OK;
 }

@@ -19,6 +19,8 @@ The ``embed`` network (three conv + ReLU layers on the semantic map and on the o
 ynet.py:154-167,529-531) runs through the float32 conv kernel, forward and backward.  The ``semantic`` adapter
 (ynet.py:513-519) cannot be constructed in the reference itself (TypeError) and raises the same error here.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -304,6 +306,9 @@ class YNet(nn.Module):
             raise ValueError(f'unknown backend {backend!r}')
         object.__setattr__(self, '_backend', backend)
         object.__setattr__(self, '_engine', None)
+        # training graphs (autograd_engine): forward + data-gradient convs on the tensor cores with the split-bf16 engine
+        from .. import autograd_engine
+        autograd_engine.TRAIN_TC = backend == 'bf16x3' or os.environ.get('YNET_TRAIN_TC', '0') == '1'
         return self
 
     @property

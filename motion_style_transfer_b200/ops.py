@@ -1019,6 +1019,21 @@ def split_pack(x, into=None):
     return into[0] if into is not None else Split(out, C)
 
 
+def split_pack_masked(x, relu_out):
+    """dy * (relu_out > 0) -> Split (ReLU backward folded into the split of a gradient); contiguous NCHW float32."""
+    x, relu_out = _req(x, name='x'), _req(relu_out, name='relu_out')
+    if x.shape != relu_out.shape or x.dim() != 4:
+        raise ValueError('split_pack_masked: gradient and activation must share one 4-D shape')
+    N, C, H, W = x.shape
+    cp = _pad16(C)
+    out = torch.empty(N, cp // 4, H, W, 8, dtype=torch.bfloat16, device=x.device)
+    with _timed('split_pack_kernel', 0, (8.0 * C + 4.0 * cp) * N * H * W):
+        check(_L().ynet_split_pack_masked_f32(_ptr(x), _ptr(relu_out), N, C, H, W, _ptr(out), cp, _stream()),
+              'split_pack_masked_f32')
+    _count()
+    return Split(out, C)
+
+
 def split_unpack(a):
     out = torch.empty(a.N, a.C, a.H, a.W, dtype=torch.float32, device=a.data.device)
     with _timed('split_unpack_kernel', 0, 8.0 * a.C * a.N * a.H * a.W):
