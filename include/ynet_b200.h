@@ -435,12 +435,21 @@ int ynet_tc_rowconv3x3_pred_softargmax(const ynet_tc_src* src_host, int32_t N, i
  *     cvRound(size * f); area tables = cv::computeResizeAreaTab for scale 1 / f as CSR arrays (device) -- or int_scale > 0
  *     for an integer scale whose blocks fit (OpenCV's integer path).  out_chw (3, Hp, Wp) and / or out_u8_hwc (dh, dw, 3)
  *     (the resized image alone: the reference-named resize()).
+ * ynet_scene_preprocess_oriented_u8 (the image half of utils/data_utils.py::augment_data, 163-233): the
+ *     same chain applied to the augmented VIEW cv2.flip(cv2.rotate(img, ROTATE_90_COUNTERCLOCKWISE) x k, 1) with
+ *     orient = k + 4 * flip, read straight from the stored (H0, W0) image: the eight views of a scene cost one upload
+ *     and no rotated copies.  (dh, dw), the tables and (Hp, Wp) refer to the view (W0 x H0 for odd k).
  * ynet_scene_onehot_u8: segmentation masks: cv2.INTER_NEAREST -> zero pad -> one-hot float32 (classes, Hp, Wp).
  * ------------------------------------------------------------------------------------------- */
 int ynet_scene_preprocess_u8(const uint8_t* img_hwc, int32_t H, int32_t W, int32_t dh, int32_t dw, int32_t Hp, int32_t Wp,
                              const int32_t* xt_start, const int32_t* xt_src, const float* xt_w, const int32_t* yt_start,
                              const int32_t* yt_src, const float* yt_w, int32_t int_scale, const double* mean3_host,
                              const double* std3_host, float* out_chw, uint8_t* out_u8_hwc, void* stream);
+int ynet_scene_preprocess_oriented_u8(const uint8_t* img_hwc, int32_t H0, int32_t W0, int32_t orient, int32_t dh, int32_t dw,
+                                      int32_t Hp, int32_t Wp, const int32_t* xt_start, const int32_t* xt_src,
+                                      const float* xt_w, const int32_t* yt_start, const int32_t* yt_src, const float* yt_w,
+                                      int32_t int_scale, const double* mean3_host, const double* std3_host, float* out_chw,
+                                      uint8_t* out_u8_hwc, void* stream);
 int ynet_scene_onehot_u8(const uint8_t* mask, int32_t H, int32_t W, int32_t dh, int32_t dw, int32_t Hp, int32_t Wp,
                          double inv_factor, int32_t classes, float* out, void* stream);
 

@@ -116,6 +116,8 @@ _PROTOS = {
     'ynet_tc_rowconv3x3_pred_softargmax': (c_int, [POINTER(TcSrc), _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P, _L, _P]),
     'ynet_scene_preprocess_u8': (c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, POINTER(c_double),
                                          POINTER(c_double), _P, _P, _P]),
+    'ynet_scene_preprocess_oriented_u8': (c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, POINTER(c_double),
+                                                  POINTER(c_double), _P, _P, _P]),
     'ynet_scene_onehot_u8': (c_int, [_P, _I, _I, _I, _I, _I, _I, c_double, _I, _P, _P]),
     'ynet_bce_workspace_bytes': (_L, [_L]),
     'ynet_bce_logits_fwd_bwd': (c_int, [_P, _P, _L, _F, _P, _P, _P, _L, _P]),

@@ -429,7 +429,7 @@ class YNetTrainer:
         """trainer.py:518-584.  Scene images are read with cv2 (host I/O, data_utils.py:248-263) and go through ONE fused
         CUDA launch each -- resize (INTER_AREA) -> pad to a multiple of ``division_factor`` -> segmentation-backbone
         normalisation, bit-exact against the reference's cv2 / numpy chain (utils/image_utils.py); the
-        returned dict holds device tensors.  Augmentation (data_utils.py:115-233) is outside the hot path."""
+        returned dict holds device tensors.  ``augment`` (data_utils.py:115-233): see below."""
         import cv2
         from ..utils.image_utils import preprocess_scene_images
         dataset_name = dataset_name.lower()
@@ -438,9 +438,6 @@ class YNetTrainer:
             raise ValueError(f'{dataset_name} dataset is not supported')
         if dataset_name == 'eth':
             raise NotImplementedError('ETH/UCY homography path is outside the B200 hot path')
-        if augment:
-            raise NotImplementedError('data / image augmentation (data_utils.py:115-233) is outside the B200 hot path; '
-                                      'augment the DataFrame and the images beforehand and use train_prepared()')
         images_dict = {}
         for scene in df.sceneId.unique():
             if use_raw_data:
@@ -452,11 +449,22 @@ class YNetTrainer:
             if im is None:
                 raise FileNotFoundError(im_path)
             images_dict[scene] = im
-        print('No data and images augmentation')
+        if not augment:
+            print('No data and images augmentation')
+            preprocess_scene_images(images_dict, resize_factor, self.division_factor, seg_mask=False, device=self.device)
+        else:
+            # data_utils.py:163-233: x8 (three rotations, then the mirror image of all four).  The trajectories are
+            # transformed on the host in the reference's float64 arithmetic; the eight image views of a scene are read
+            # by the preprocessing kernel from ONE uploaded image (no rotated copies)
+            from ..utils.image_utils import augment_data, preprocess_scene_image
+            df, views = augment_data(df, images_dict)
+            stored = {scene: torch.as_tensor(im).to(self.device) for scene, im in images_dict.items()}
+            images_dict = {view: preprocess_scene_image(stored[base], resize_factor, self.division_factor, device=self.device,
+                                                        orient=orient) for view, (base, orient) in views.items()}
+            print('Augmented data and images')
         dataset = SceneDataset(df, resize=resize_factor, total_len=obs_len + pred_len)
         dataloader = DataLoader(dataset, batch_size=1, collate_fn=scene_collate, shuffle=(mode == 'train'),
                                 generator=parallel.shared_generator() if mode == 'train' else None)
-        preprocess_scene_images(images_dict, resize_factor, self.division_factor, seg_mask=False, device=self.device)
         return images_dict, dataloader, None
 
     # ------------------------------------------------------------------------------------------ checkpoints

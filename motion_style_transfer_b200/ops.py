@@ -149,9 +149,12 @@ def avgpool_pyramid(maps, n_levels):
 
 
 # ------------------------------------------------------------------------------------------------ 8f rank 2: scene images
-def scene_preprocess_u8(img_u8, dh, dw, Hp, Wp, xt, yt, int_scale, mean3=None, std3=None, want_chw=True, want_u8=False):
+def scene_preprocess_u8(img_u8, dh, dw, Hp, Wp, xt, yt, int_scale, mean3=None, std3=None, want_chw=True, want_u8=False,
+                        orient=0):
     """uint8 HWC CUDA image -> (float32 (3, Hp, Wp) normalised | None, uint8 (dh, dw, 3) resized | None).
-    xt / yt: (start, src, weight) CUDA tensors of cv::computeResizeAreaTab (None with int_scale > 0)."""
+    xt / yt: (start, src, weight) CUDA tensors of cv::computeResizeAreaTab (None with int_scale > 0).
+    orient = k + 4 * flip: the chain is applied to the augmented view cv2.flip(rot90 x k (img), 1) without materialising
+    it (data_utils.py:115-233); dh, dw, Hp, Wp and the tables then refer to the view."""
     img_u8 = _req(img_u8, torch.uint8, 'image')
     H, W, C = img_u8.shape
     if C != 3:
@@ -162,8 +165,8 @@ def scene_preprocess_u8(img_u8, dh, dw, Hp, Wp, xt, yt, int_scale, mean3=None, s
     sd = (ctypes.c_double * 3)(*std3) if std3 is not None else None
     tabs = [None] * 6 if int_scale else [_ptr(t) for t in (xt + yt)]
     with _timed('scene_preprocess_kernel', 0, 3.0 * H * W + 12.0 * Hp * Wp):
-        check(_L().ynet_scene_preprocess_u8(_ptr(img_u8), H, W, dh, dw, Hp, Wp, *tabs, int(int_scale), m, sd, _ptr(out),
-                                            _ptr(out8), _stream()), 'scene_preprocess_u8')
+        check(_L().ynet_scene_preprocess_oriented_u8(_ptr(img_u8), H, W, int(orient), dh, dw, Hp, Wp, *tabs, int(int_scale), m,
+                                                     sd, _ptr(out), _ptr(out8), _stream()), 'scene_preprocess_oriented_u8')
     _count()
     return out, out8
 

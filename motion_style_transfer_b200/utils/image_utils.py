@@ -211,20 +211,77 @@ def _device_tabs(H, W, dh, dw, scale, device):
     return hit
 
 
-def preprocess_scene_image(im, factor, division_factor=32, seg_mask=False, classes=6, device='cuda'):
+def preprocess_scene_image(im, factor, division_factor=32, seg_mask=False, classes=6, device='cuda', orient=0):
     """resize -> pad -> preprocess_image_for_segmentation of ONE scene image (trainer.py:578-582) in one launch:
-    uint8 (H, W, 3) numpy / tensor (or (H, W) mask with seg_mask) -> float32 (C, Hp, Wp) CUDA tensor."""
+    uint8 (H, W, 3) numpy / tensor (or (H, W) mask with seg_mask) -> float32 (C, Hp, Wp) CUDA tensor.
+    orient = k + 4 * flip: the same for the augmented view fliplr^flip(rot90^k(im)) (data_utils.py:115-233), read from
+    the stored image itself."""
     t = torch.as_tensor(np.ascontiguousarray(im) if isinstance(im, np.ndarray) else im)
     if t.dtype != torch.uint8:
         raise TypeError(f'scene images are uint8 (cv2.imread), got {t.dtype}')
     t = t.to(device).contiguous()
-    H, W = t.shape[:2]
+    H, W = (t.shape[1], t.shape[0]) if (orient & 1) else t.shape[:2]        # the view's size
     dh, dw, scale, isc = _resize_plan(H, W, factor)
     Hp, Wp = _ceil_to(dh, division_factor), _ceil_to(dw, division_factor)
     if seg_mask:
+        if orient:
+            raise NotImplementedError('augmented views of segmentation masks (ETH/UCY) are outside the B200 hot path')
         return ops.scene_onehot_u8(t, dh, dw, Hp, Wp, scale, classes)
     xt, yt = (None, None) if isc else _device_tabs(H, W, dh, dw, scale, t.device)
-    return ops.scene_preprocess_u8(t, dh, dw, Hp, Wp, xt, yt, isc, SMP_MEAN, SMP_STD)[0]
+    return ops.scene_preprocess_u8(t, dh, dw, Hp, Wp, xt, yt, isc, SMP_MEAN, SMP_STD, orient=orient)[0]
+
+
+AUGMENT_SUFFIX = {0: '', 1: '_rot90', 2: '_rot180', 3: '_rot270'}
+
+
+def augment_data(data, images):
+    """utils/data_utils.py::augment_data (163-233), the trajectory half: every scene three more times rotated
+    counter-clockwise by k * 90 degrees about the image centre (``rot``, 115-142), then all of those mirrored
+    horizontally (``fliplr``, 145-160): 8x the rows, new ``sceneId`` suffixes and ``metaId`` offsets as the reference
+    assigns them.  Same float64 numpy arithmetic as the reference (``np.dot(xy, R)`` with R from cos / sin of -k pi / 2),
+    so the coordinates are bit-identical.  ``images``: {sceneId: uint8 image as read from disk}.
+
+    Returns (augmented DataFrame, {augmented sceneId: (original sceneId, orient)}): the images themselves are NOT
+    rotated on the host -- ``preprocess_scene_image(..., orient=)`` reads the view from the stored image."""
+    import pandas as pd
+
+    def size(scene, k):
+        h, w = images[scene].shape[:2]
+        return (w, h) if k % 2 else (h, w)                 # (y0, x0) of the view after k rotations
+
+    views = {scene: (scene, 0) for scene in data.sceneId.unique()}
+    data_ = data.copy()
+    for k in (1, 2, 3):
+        meta_max = data['metaId'].max()
+        for scene in data_.sceneId.unique():
+            xy = data_[data_.sceneId == scene].copy()
+            y0, x0 = images[scene].shape[:2]
+            xy.loc()[:, 'x'] = xy['x'] - x0 / 2
+            xy.loc()[:, 'y'] = xy['y'] - y0 / 2
+            c, s = np.cos(-k * np.pi / 2), np.sin(-k * np.pi / 2)
+            xy.loc()[:, ['x', 'y']] = np.dot(xy[['x', 'y']], np.array([[c, s], [-s, c]]))
+            y1, x1 = size(scene, k)
+            xy.loc()[:, 'x'] = xy['x'] + x1 / 2
+            xy.loc()[:, 'y'] = xy['y'] + y1 / 2
+            xy['sceneId'] = scene + AUGMENT_SUFFIX[k]
+            xy['metaId'] = xy['metaId'] + meta_max + 1
+            views[scene + AUGMENT_SUFFIX[k]] = (scene, k)
+            data = pd.concat([data, xy], axis=0)
+    meta_max = data['metaId'].max()
+    for scene in data.sceneId.unique():
+        base, k = views[scene]
+        xy = data[data.sceneId == scene].copy()
+        y0, x0 = size(base, k)
+        xy.loc()[:, 'x'] = xy['x'] - x0 / 2
+        xy.loc()[:, 'y'] = xy['y'] - y0 / 2
+        xy.loc()[:, ['x', 'y']] = np.dot(xy[['x', 'y']], np.array([[-1, 0], [0, 1]]))
+        xy.loc()[:, 'x'] = xy['x'] + x0 / 2
+        xy.loc()[:, 'y'] = xy['y'] + y0 / 2
+        xy['sceneId'] = xy['sceneId'] + '_fliplr'
+        xy['metaId'] = xy['metaId'] + meta_max + 1
+        views[scene + '_fliplr'] = (base, k + 4)
+        data = pd.concat([data, xy], axis=0)
+    return data, views
 
 
 def preprocess_scene_images(images, factor, division_factor=32, seg_mask=False, classes=6, device='cuda'):

@@ -316,6 +316,53 @@ def gen_preprocess():
     save('preprocess', **out)
 
 
+def gen_augment(ns):
+    """utils/data_utils.py::augment_data (163-233) run LIVE on two synthetic scenes written to a temporary directory:
+    the augmented DataFrame (8x: three rotations, then the mirror image of all four) and, for every augmented scene, the
+    reference's rotated / flipped image pushed through resize -> pad -> normalise (cv2 + the published smp constants)."""
+    import importlib
+    import sys
+    import tempfile
+    import cv2
+    from oracle import preprocess_oracle as P
+    sys.path.insert(0, ref_harness.REF_PATH)
+    try:
+        du = importlib.import_module('utils.data_utils')
+    finally:
+        sys.path.remove(ref_harness.REF_PATH)
+    rng = np.random.RandomState(11)
+    sizes = {'sA': (60, 84), 's_B': (50, 50)}
+    f = 0.5
+    rows = []
+    with tempfile.TemporaryDirectory() as tmp:
+        out = {}
+        for scene, (H, W) in sizes.items():
+            img = rng.randint(0, 256, (H, W, 3)).astype(np.uint8)
+            os.makedirs(os.path.join(tmp, scene))
+            cv2.imwrite(os.path.join(tmp, scene, 'reference.png'), img)
+            out['img/' + scene] = img
+            for meta in range(2):
+                mid = len(rows) // 4
+                for t in range(4):
+                    rows.append(dict(frame=t, trackId=mid, x=float(rng.uniform(0, W)), y=float(rng.uniform(0, H)),
+                                     sceneId=scene, metaId=mid))
+        df = pd.DataFrame(rows)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            data, images = du.augment_data(df.copy(), image_path=tmp, images={}, image_file='reference.png')
+    out['in/x'], out['in/y'] = df.x.values, df.y.values
+    out['in/metaId'], out['in/sceneId'] = df.metaId.values.astype(np.int64), np.array(list(df.sceneId.values), dtype='U32')
+    out['out/x'], out['out/y'] = data.x.values, data.y.values
+    out['out/metaId'], out['out/sceneId'] = data.metaId.values.astype(np.int64), np.array(list(data.sceneId.values), dtype='U32')
+    out['out/frame'] = data.frame.values.astype(np.int64)
+    for key, im in images.items():
+        r = cv2.resize(im, (0, 0), fx=f, fy=f, interpolation=cv2.INTER_AREA)
+        pd_ = cv2.copyMakeBorder(r, 0, (-r.shape[0]) % 32, 0, (-r.shape[1]) % 32, cv2.BORDER_CONSTANT)
+        x = ((pd_ / 255.0) - P.IMAGENET_MEAN) / P.IMAGENET_STD
+        out['chw/' + key] = x.transpose(2, 0, 1).astype('float32')
+    save('augment', factor=f, **out)
+
+
 def gen_train(ns):
     """Two optimiser steps of the reference's train_epoch (train_epoch.py:8-136) with MoSA r=1 on stages 0-4:
     freeze policy of trainer.py:117,137-139, Adam(lr) + BCEWithLogitsLoss as trainer.py:197,206."""
@@ -415,6 +462,7 @@ def main(only=None):
     gen_evaluate(ns)
     gen_train(ns)
     gen_forward_batch(ns)
+    gen_augment(ns)
     gen_preprocess()
 
 
