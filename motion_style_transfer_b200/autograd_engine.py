@@ -7,6 +7,7 @@ tensors); conv forward / dgrad / wgrad, pool / bilinear backward, BCE and the Lo
 projection (dA = s B^T dM, dB = s dM A^T) are CUDA kernels.
 """
 import os
+import weakref
 
 import torch
 
@@ -35,20 +36,30 @@ TRAIN_TC = os.environ.get('YNET_TRAIN_TC', '0') == '1'
 _tc_wcache = {}
 
 
-def _tc_packed(key, ver, make):
-    if ver[0] is None:               # a temporary weight (adapter sum): its address may be recycled, never cache it
+def _select_executor(model):
+    """The conv kernels of the training graph follow the model's backend (called at every entry point below)."""
+    global TRAIN_TC
+    TRAIN_TC = getattr(model, '_backend', 'fp32') == 'bf16x3' or os.environ.get('YNET_TRAIN_TC', '0') == '1'
+
+
+def _tc_packed(kind, weight, ver, make):
+    """Packed split weights of a PARAMETER, cached per tensor object (weak reference: a new model whose parameter lands on
+    a recycled address must not hit) and version; temporaries (adapter sums) are packed every time."""
+    if weight is None:
         return make()
+    key = (kind, id(weight))
     hit = _tc_wcache.get(key)
-    if hit is not None and hit[0] == ver:
-        return hit[1]
+    if hit is not None and hit[0]() is weight and hit[1] == ver:
+        return hit[2]
     if len(_tc_wcache) > 512:
-        _tc_wcache.clear()
+        for k in [k for k, v in _tc_wcache.items() if v[0]() is None]:
+            del _tc_wcache[k]
     val = make()
-    _tc_wcache[key] = (ver, val)
+    _tc_wcache[key] = (weakref.ref(weight), ver, val)
     return val
 
 
-def _tc_conv_forward(w_eff, wver, bias, relu, parts):
+def _tc_conv_forward(w_eff, weight, wver, bias, relu, parts):
     """conv3x3(cat(parts)) + bias (+ReLU): float32 NCHW parts (batch 1 = broadcast) -> float32 NCHW."""
     from .engine import YNetEngineSplit
     sp = [ops.split_pack(t) for t in parts]
@@ -59,14 +70,14 @@ def _tc_conv_forward(w_eff, wver, bias, relu, parts):
     def make():
         idx = torch.cat([torch.arange(c0, c1, device=w_eff.device) for c0, c1 in ranges])
         return ops.split_pack_weights(w_eff.index_select(1, idx).contiguous(), [s.layout for s in sources])
-    packed = _tc_packed(('f', None if wver is None else wver[0]), (wver, layouts, ranges), make)
+    packed = _tc_packed('f', weight, (wver, layouts, ranges), make)
     bias_pad = torch.zeros(ops._pad16(C_out), dtype=torch.float32, device=w_eff.device)
     if bias is not None:
         bias_pad[:C_out] = bias
     return ops.split_unpack(ops.tc_conv3x3_split(sources, packed, bias_pad, C_out, relu))
 
 
-def _tc_conv_dgrad(w_eff, wver, dy, relu_out):
+def _tc_conv_dgrad(w_eff, weight, wver, dy, relu_out):
     """d/dx of conv3x3 (+ReLU): dy (masked by the activation) convolved with the flipped, transposed weight."""
     dys = ops.split_pack_masked(dy, relu_out) if relu_out is not None else ops.split_pack(dy)
     C_in = w_eff.shape[1]
@@ -74,7 +85,7 @@ def _tc_conv_dgrad(w_eff, wver, dy, relu_out):
     def make():
         w_t = w_eff.flip(2, 3).transpose(0, 1).contiguous()                 # (C_in, C_out, 3, 3)
         return ops.split_pack_weights(w_t, [dys.layout])
-    packed = _tc_packed(('d', None if wver is None else wver[0]), (wver, tuple(dys.layout)), make)
+    packed = _tc_packed('d', weight, (wver, tuple(dys.layout)), make)
     zero = torch.zeros(ops._pad16(C_in), dtype=torch.float32, device=dy.device)
     return ops.split_unpack(ops.tc_conv3x3_split([dys], packed, zero, C_in, False))
 
@@ -89,10 +100,10 @@ class Conv3x3Fn(torch.autograd.Function):
             ops._pad16(s.shape[1]) for s in sources) // 16 <= 64)
         if ctx.tc:
             w_eff = ops.lora_fold(weight, lora_A, lora_B, packed=False)
-            ctx.wver = (weight.data_ptr(), weight._version, None if lora_A is None else lora_A._version,
-                        None if lora_B is None else lora_B._version) if weight.is_leaf else None
+            ctx.wver = (weight._version, None if lora_A is None else (id(lora_A), lora_A._version),
+                        None if lora_B is None else (id(lora_B), lora_B._version))
             parts = [_materialize(s.contiguous(), m, 1) for s, m in zip(sources, modes)]
-            y = _tc_conv_forward(w_eff, ctx.wver, bias, relu, parts)
+            y = _tc_conv_forward(w_eff, weight if weight.is_leaf else None, ctx.wver, bias, relu, parts)
         else:
             packed = ops.lora_fold(weight, lora_A, lora_B, packed=True)
             y = ops.conv3x3_f32(list(zip(sources, modes)), packed, bias, relu, N, H, W)
@@ -111,7 +122,8 @@ class Conv3x3Fn(torch.autograd.Function):
         d_sources = [None] * len(sources)
         if any(need[8:]):
             w_eff = ops.lora_fold(weight, lora_A, lora_B, packed=False)
-            dx = _tc_conv_dgrad(w_eff, ctx.wver, dy, relu_out) if ctx.tc else ops.conv3x3_dgrad_f32(dy, relu_out, w_eff)
+            dx = (_tc_conv_dgrad(w_eff, weight if weight.is_leaf else None, ctx.wver, dy, relu_out) if ctx.tc
+                  else ops.conv3x3_dgrad_f32(dy, relu_out, w_eff))
             c0 = 0
             for i, (s, mode) in enumerate(zip(sources, ctx.modes)):
                 c1 = c0 + s.shape[1]
@@ -236,6 +248,7 @@ def _run_stages(stages, x_parts):
 
 
 def pred_features(model, scene_map, motion_map):
+    _select_executor(model)
     enc = model.encoder
     scene, motion = _parts(scene_map), _parts(motion_map)
     if model.network == 'fusion':
@@ -250,6 +263,7 @@ def pred_features(model, scene_map, motion_map):
 
 
 def decoder_logits(model, decoder, key, features):
+    _select_executor(model)
     feats = [_parts(f) for f in features][::-1]
     c = feats[0]
     H, W = c[0].shape[2], c[0].shape[3]

@@ -306,9 +306,7 @@ class YNet(nn.Module):
             raise ValueError(f'unknown backend {backend!r}')
         object.__setattr__(self, '_backend', backend)
         object.__setattr__(self, '_engine', None)
-        # training graphs (autograd_engine): forward + data-gradient convs on the tensor cores with the split-bf16 engine
-        from .. import autograd_engine
-        autograd_engine.TRAIN_TC = backend == 'bf16x3' or os.environ.get('YNET_TRAIN_TC', '0') == '1'
+        # (training graphs, autograd_engine: with 'bf16x3' the forward + data-gradient convs run on the tensor cores too)
         return self
 
     @property

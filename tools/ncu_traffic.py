@@ -13,8 +13,10 @@ import re
 import sys
 
 LABELS = [   # ops.py timing label <- ncu kernel name
-    ('tc_rowconv_kernel<pred,softargmax>', r'tc_rowconv_kernel<\(bool\)1>|tc_rowconv_kernel<true>|tc_rowconv_kernel<1>'),
-    ('tc_rowconv_kernel', r'tc_rowconv_kernel<\(bool\)0>|tc_rowconv_kernel<false>|tc_rowconv_kernel<0>'),
+    ('tc_rowconv2_kernel<pred,softargmax>', r'tc_rowconv2_kernel<\(bool\)1|tc_rowconv2_kernel<true|tc_rowconv2_kernel<1'),
+    ('tc_rowconv2_kernel', r'tc_rowconv2_kernel'),
+    ('tc_rowconv_kernel<pred,softargmax>', r'tc_rowconv_kernel<\(bool\)1|tc_rowconv_kernel<true|tc_rowconv_kernel<1'),
+    ('tc_rowconv_kernel', r'tc_rowconv_kernel<\(bool\)0|tc_rowconv_kernel<false|tc_rowconv_kernel<0'),
     ('tc_conv3x3_kernel', r'tc_conv_kernel<\d, 9, 0>'),
     ('tc_conv3x3_hilo_kernel', r'tc_conv_kernel<\d, 9, 4>'),
     ('tc_upconv3x3_kernel', r'tc_conv_kernel<\d, 9, 3>|upconv_ringfix'),

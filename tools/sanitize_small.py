@@ -59,7 +59,32 @@ img = np.random.RandomState(0).randint(0, 256, (97, 131, 3)).astype(np.uint8)
 pre = U.preprocess_scene_image(img, 0.33, 32)
 pre4 = U.preprocess_scene_image(img, 0.25, 32)
 msk = U.preprocess_scene_image(img[:, :, 0] % 6, 0.33, 32, seg_mask=True)
+# round 2, second half: waypoint planes from the template, two-conv block (plain + tail), split-bf16 engine ops and the
+# tensor-core training convs, oriented preprocessing, evaluate() through the cached graph
+H2, W2 = 64, 256
+coords2 = torch.stack([torch.rand(6 * 2) * (W2 - 1), torch.rand(6 * 2) * (H2 - 1)], 1).to(dev).contiguous()
+tmpl2 = ops.create_dist_template(3 * W2, dev)
+lazy = ops.tc_rasterize_pyramid(tmpl2, coords2, 6, 2, H2, W2, 2, lazy_levels=2)
+up2 = ops.tc_pack(torch.randn(6, 16, H2, W2, device=dev))
+feat2 = ops.tc_pack(torch.relu(torch.randn(2, 32, H2, W2, device=dev)))
+wa = torch.randn(32, 50, 3, 3, device=dev) * 0.1
+part2 = ops.tc_conv3x3_hilo([feat2], ops.tc_pack_weights(wa[:, 16:48].contiguous(), [32]), 32, False).repeat_interleave(3)
+pa = ops.tc_rowconv_pack_weights_cat(wa, [(0, 16, 16)] + lazy[0].weight_parts(48))
+y1 = ops.tc_rowconv3x3([up2, lazy[0]], pa, b32, 32, True, partial=part2)
+y2 = ops.tc_rowconv2_wp([up2, lazy[0]], pa, b32, pkr, b32, 32, True, pad_out=True, partial=part2)
+y3 = ops.tc_rowconv2_wp_pred_softargmax([up2, lazy[0]], pa, b32, pkr, b32, True, ops.tc_pack_weights(wp1, [32]),
+                                        torch.zeros(32, device=dev), 30, partial=part2)
+up1 = ops.tc_pack(torch.randn(6, 16, H2 // 2, W2 // 2, device=dev))
+y4 = ops.tc_rowconv3x3([up1, lazy[1]], pa, b32, 32, True)
+xs = ops.split_pack(torch.randn(3, 21, 20, 36, device=dev))
+ws = torch.randn(30, 21, 3, 3, device=dev) * 0.1
+ys = ops.tc_conv3x3_split([xs], ops.split_pack_weights(ws, [xs.layout]), torch.zeros(32, device=dev), 30, True)
+ys2 = ops.split_unpack(ops.split_upsample(ops.split_maxpool(ys)))
+ymask = ops.split_pack_masked(torch.randn(3, 30, 20, 36, device=dev), ops.split_unpack(ys))
+pre_o = U.preprocess_scene_image(img, 0.33, 32, orient=5)
 torch.cuda.synchronize()
+print('sanitize_small r02b: ok', float(ops.tc_unpack(y1).abs().sum()), float(ops.tc_unpack(y2).abs().sum()), float(y3.sum()),
+      float(ops.tc_unpack(y4).abs().sum()), float(ys2.abs().sum()), float(ops.split_unpack(ymask).abs().sum()), float(pre_o.sum()))
 print('sanitize_small r02: ok', float(ops.tc_unpack(yr).abs().sum()), float(ops.tc_unpack(ym).abs().sum()), float(sa.sum()),
       float(pre.sum()), float(pre4.sum()), float(msk.sum()))
 print('sanitize_small: ok', float(ops.tc_unpack(out).abs().sum()), int(idx.sum()), float(cw.sum()), float(ade.sum()))

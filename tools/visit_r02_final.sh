@@ -13,3 +13,8 @@ timeout 1200 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-roofline --torch-cuda-agents 0 > gpurun_out/ncu_traffic.log 2>&1; echo "ncu traffic exit $?"
 timeout 900 python bench.py --steps 20 --warmup 3 --profile-layers gpurun_out/layers_r02_final.json > gpurun_out/bench_r02_final.log 2>&1; echo "bench exit $?"
 tail -c 600 gpurun_out/bench_r02_final.log
+timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r02_reference.log 2>&1; echo "reference exit $?"
+timeout 900 python bench.py --backend bf16x3 --steps 5 --warmup 3 --no-cpu-baseline --torch-cuda-agents 0 > gpurun_out/bench_r02_bf16x3.log 2>&1; echo "bf16x3 exit $?"
+timeout 600 python bench.py --mode evaluate --agents 1024 --steps 3 --warmup 1 > gpurun_out/bench_r02_evaluate_1gpu.log 2>&1
+for B in fp32 bf16x3; do timeout 600 python bench.py --mode finetune --workload sdd_short --agents 30 --steps 3 --warmup 2 --backend $B > gpurun_out/bench_r02_finetune_sdd_1gpu_$B.log 2>&1; done
+for f in gpurun_out/bench_r02_reference.log gpurun_out/bench_r02_bf16x3.log gpurun_out/bench_r02_evaluate_1gpu.log gpurun_out/bench_r02_finetune_sdd_1gpu_fp32.log gpurun_out/bench_r02_finetune_sdd_1gpu_bf16x3.log; do echo "== $f"; grep "^{" $f | tail -n 1 | cut -c1-300; done

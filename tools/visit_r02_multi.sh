@@ -10,4 +10,5 @@ timeout 600 $TR bench.py --gpus $N --steps 10 --warmup 3 --no-roofline > gpurun_
 timeout 600 $TR bench.py --gpus $N --mode evaluate --agents 1024 --steps 3 --warmup 1 > gpurun_out/bench_r02_evaluate_${N}gpu.log 2>&1
 timeout 600 $TR bench.py --gpus $N --mode finetune --workload sdd_short --agents 30 --steps 3 --warmup 1 > gpurun_out/bench_r02_finetune_sdd_${N}gpu.log 2>&1
 timeout 600 $TR bench.py --gpus $N --mode finetune --workload ind_short_ynetmod --agents 30 --steps 3 --warmup 1 > gpurun_out/bench_r02_finetune_ynetmod_${N}gpu.log 2>&1
+timeout 600 $TR bench.py --gpus $N --mode finetune --workload sdd_short --agents 30 --steps 3 --warmup 1 --backend bf16x3 > gpurun_out/bench_r02_finetune_sdd_bf16x3_${N}gpu.log 2>&1
 for f in gpurun_out/bench_r02_*_${N}gpu.log; do echo "== $f"; grep "^{" $f | tail -n 1 | cut -c1-330; done
