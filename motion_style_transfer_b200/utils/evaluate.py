@@ -24,7 +24,13 @@ TTST_SAMPLES = 10000          # evaluate.py:138
 # reference consumes them: a seeded run reproduces the reference's CPU results draw for draw (eager launches).
 RNG_MODE = os.environ.get('YNET_EVAL_RNG', 'device')
 USE_GRAPH = os.environ.get('YNET_EVAL_GRAPH', '1') == '1'
-GRAPH_MIN_BATCHES = 3         # a capture costs three eager passes
+# A capture costs about three eager passes and a replay saves ~20 % of an eager batch, so a graph pays for itself after
+# ~14 full batches: a (scene size, batch shape) is captured when this call alone brings that many, or from the second
+# evaluate() call that meets it on (validation / test rounds revisit their scenes).  Graphs own their activation pools:
+# the least recently used ones are dropped beyond GRAPH_POOL_GB.
+GRAPH_MIN_BATCHES = 14
+GRAPH_MIN_BATCHES_SEEN = 3
+GRAPH_POOL_GB = float(os.environ.get('YNET_EVAL_GRAPH_GB', '48'))
 _eval_calls = 0
 # agent x goal decoder passes per launch (bounds activation memory: ~40 MB per pass at 416^2)
 MAX_STACKED_PASSES = int(os.environ.get('YNET_MAX_STACKED_PASSES', '640'))
@@ -219,7 +225,10 @@ def evaluate(model, val_loader, val_images, device, dataset_name, homo_mat, inpu
                 k_batch += 1
                 if graph is not None and e - b == batch_size:
                     graph.rng._epoch(device).fill_(stream + k_batch - 1)
+                    fresh = graph.graph is None
                     res = graph(scene_image, trajectory[b:e])
+                    if fresh:
+                        _trim_graph_cache(model, graph)
                     res = dict(res, ade=res['ade'].clone(), fde=res['fde'].clone())   # static buffers: next replay overwrites
                 else:
                     if eager_rng is not None:
@@ -285,20 +294,39 @@ def _cached_graph(model, weights_ver, n_full, input_template, scene_image, traj_
     (at most two: a graph owns its activation pool).  None when this call has too few full batches to repay a capture
     and nothing is cached yet."""
     cache = model.__dict__.setdefault('_forecast_graphs', {})
+    seen = model.__dict__.setdefault('_forecast_graph_seen', {})
     key = (weights_ver, getattr(model, '_backend', None), tuple(scene_image.shape), traj_shape, tuple(waypoints), n_goal,
            n_traj, obs_len, resize_factor, temperature, use_TTST, use_CWS, rel_thresh,
            None if CWS_params is None else tuple(sorted(CWS_params.items())), embed_motion,
            input_template.data_ptr(), tuple(input_template.shape))
-    hit = cache.get(key)
-    if hit is None:
-        if n_full < GRAPH_MIN_BATCHES:
-            return None
-        while len(cache) >= 2:
-            cache.pop(next(iter(cache)))
-        hit = cache[key] = GraphedForecaster(model, input_template, tuple(scene_image.shape), traj_shape, waypoints, n_goal,
-                                             n_traj, obs_len, resize_factor, temperature, use_TTST, use_CWS, rel_thresh,
-                                             CWS_params, seed=0x59E7, embed_motion=embed_motion)
+    hit = cache.pop(key, None)
+    if hit is not None:
+        cache[key] = hit                       # most recently used last
+        return hit
+    shape_key = key[1:]                         # (a weight update re-captures, it does not reset the count)
+    seen[shape_key] = seen.get(shape_key, 0) + 1
+    if n_full < (GRAPH_MIN_BATCHES_SEEN if seen[shape_key] > 1 else GRAPH_MIN_BATCHES):
+        return None
+    for k in [k for k in cache if k[1:] == shape_key]:       # graphs of this shape captured for older weights
+        del cache[k]
+    hit = GraphedForecaster(model, input_template, tuple(scene_image.shape), traj_shape, waypoints, n_goal, n_traj, obs_len,
+                            resize_factor, temperature, use_TTST, use_CWS, rel_thresh, CWS_params, seed=0x59E7,
+                            embed_motion=embed_motion)
+    cache[key] = hit
     return hit
+
+
+def _trim_graph_cache(model, keep):
+    """Drop least recently used graphs while their pools exceed GRAPH_POOL_GB (never the one in use)."""
+    cache = model.__dict__.get('_forecast_graphs', {})
+    total = sum(g.pool_bytes for g in cache.values())
+    for k in list(cache):
+        if total <= GRAPH_POOL_GB * 1e9:
+            break
+        if cache[k] is keep:
+            continue
+        total -= cache[k].pool_bytes
+        del cache[k]
 
 
 class GraphedForecaster:
@@ -325,6 +353,7 @@ class GraphedForecaster:
         self._embed_motion = embed_motion
         self.graph = None
         self.out = None
+        self.pool_bytes = 0
 
     def _run(self):
         self.rng.next_step(self.scene.device)
@@ -342,9 +371,11 @@ class GraphedForecaster:
                 self._run()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        before = torch.cuda.memory_reserved(self.scene.device)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = self._run()
+        self.pool_bytes = max(0, torch.cuda.memory_reserved(self.scene.device) - before)     # the graph's private pool
         self.rng.epoch.copy_(epoch0)
         return self
 
