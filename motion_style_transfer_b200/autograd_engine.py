@@ -34,6 +34,7 @@ def _materialize(t, mode, N):
 # operands are split on entry and results joined on exit (bandwidth-bound passes).
 TRAIN_TC = os.environ.get('YNET_TRAIN_TC', '0') == '1'
 _tc_wcache = {}
+_zero_bias = {}
 
 
 def _select_executor(model):
@@ -69,11 +70,12 @@ def _tc_conv_forward(w_eff, weight, wver, bias, relu, parts):
 
     def make():
         idx = torch.cat([torch.arange(c0, c1, device=w_eff.device) for c0, c1 in ranges])
-        return ops.split_pack_weights(w_eff.index_select(1, idx).contiguous(), [s.layout for s in sources])
-    packed = _tc_packed('f', weight, (wver, layouts, ranges), make)
-    bias_pad = torch.zeros(ops._pad16(C_out), dtype=torch.float32, device=w_eff.device)
-    if bias is not None:
-        bias_pad[:C_out] = bias
+        bias_pad = torch.zeros(ops._pad16(C_out), dtype=torch.float32, device=w_eff.device)
+        if bias is not None:
+            bias_pad[:C_out] = bias.detach()
+        return ops.split_pack_weights(w_eff.index_select(1, idx).contiguous(), [s.layout for s in sources]), bias_pad
+    bver = None if bias is None else (id(bias), bias._version)
+    packed, bias_pad = _tc_packed('f', weight, (wver, bver, layouts, ranges), make)
     return ops.split_unpack(ops.tc_conv3x3_split(sources, packed, bias_pad, C_out, relu))
 
 
@@ -86,7 +88,9 @@ def _tc_conv_dgrad(w_eff, weight, wver, dy, relu_out):
         w_t = w_eff.flip(2, 3).transpose(0, 1).contiguous()                 # (C_in, C_out, 3, 3)
         return ops.split_pack_weights(w_t, [dys.layout])
     packed = _tc_packed('d', weight, (wver, tuple(dys.layout)), make)
-    zero = torch.zeros(ops._pad16(C_in), dtype=torch.float32, device=dy.device)
+    zero = _zero_bias.get((dy.device, C_in))
+    if zero is None:
+        zero = _zero_bias[(dy.device, C_in)] = torch.zeros(ops._pad16(C_in), dtype=torch.float32, device=dy.device)
     return ops.split_unpack(ops.tc_conv3x3_split([dys], packed, zero, C_in, False))
 
 

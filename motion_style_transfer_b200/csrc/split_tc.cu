@@ -70,17 +70,24 @@ split_pack_kernel(const float* __restrict__ x, const float* __restrict__ mask, i
   }
 }
 
+// split planes -> NCHW f32.  One thread = one pixel x one 8-channel chunk: two 16 B loads, eight coalesced 4 B stores
+// (one per channel plane).
 __global__ void __launch_bounds__(256)
-split_unpack_kernel(const __nv_bfloat16* __restrict__ x, int C, int chunks, int H, int W, float* __restrict__ out,
-                    long long total) {
+split_unpack_kernel(const uint4* __restrict__ x, int C, int chunks, int H, int W, float* __restrict__ out, long long total) {
   const long long S = (long long)H * W;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int used = (C + 7) >> 3;               // chunks that hold real channels (total = N * used * S)
     const long long pix = t % S;
     const long long rest = t / S;
-    const int c = (int)(rest % C);
-    const long long n = rest / C;
-    const long long hi = (((n * 2 * chunks + (c >> 3)) * S) + pix) * 8 + (c & 7);
-    out[t] = __bfloat162float(x[hi]) + __bfloat162float(x[hi + (long long)chunks * S * 8]);
+    const int chunk = (int)(rest % used);
+    const long long n = rest / used;
+    float f[8];
+    split_load8(x + ((n * 2 * chunks + chunk) * S + pix), (long long)chunks * S, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = chunk * 8 + k;
+      if (c < C) out[(n * C + c) * S + pix] = f[k];
+    }
   }
 }
 
@@ -212,9 +219,9 @@ int ynet_split_unpack_f32(const void* x, int32_t N, int32_t C, int32_t C_pad, in
   YNET_CHECK_ARG(N >= 0 && C > 0 && H > 0 && W > 0 && C_pad >= C && C_pad % 16 == 0, "bad shape");
   if (N == 0) return YNET_OK;
   YNET_CHECK_ARG(x && out, "null pointer");
-  const long long total = (long long)N * C * H * W;
-  split_unpack_kernel<<<split_grid(total), 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), C,
-                                                                        C_pad / 8, H, W, out, total);
+  const long long total = (long long)N * ((C + 7) / 8) * H * W;
+  split_unpack_kernel<<<split_grid(total), 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(x), C, C_pad / 8, H, W,
+                                                                        out, total);
   YNET_LAUNCH_CHECK();
   return YNET_OK;
 }

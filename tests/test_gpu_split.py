@@ -43,6 +43,9 @@ def test_split_layout_roundtrip_pool_upsample(ops):
     up = ops.split_unpack(ops.split_upsample(ops.split_pack(x16.cuda()))).cpu()
     ref = F.interpolate(x16.double(), scale_factor=2, mode='bilinear', align_corners=False)
     assert rel_err(up.numpy(), ref.numpy()) < 2e-5
+    # fewer real channels than padded planes (C = 8 -> one used chunk of two), several images
+    x8 = torch.randn(3, 8, 6, 10)
+    assert ((ops.split_unpack(ops.split_pack(x8.cuda())).cpu() - x8).abs() <= 2.0 ** -16 * x8.abs()).all()
     # broadcast batch (stride 0) packs one image
     b = ops.split_pack(x[:1].cuda().expand(4, -1, -1, -1))
     assert b.N == 1
