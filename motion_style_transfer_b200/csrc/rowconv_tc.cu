@@ -31,6 +31,14 @@
 // accumulator (TMEM lane = channel, column = pixel) is reduced by eight soft-argmax warps straight from tcgen05.ld.
 // Both epilogues run as two warp sets that alternate rows, so the per-row latency chain (barrier wake-up, tcgen05.ld,
 // tcgen05.st) of one row overlaps the next row's.
+//
+// Round 2, second half (further down in this file):
+//  * WP kernels (ynet_tc_rowconv3x3_wp): the waypoint channels of the trajectory decoder's input are windows of the
+//    distance template, so their K block is loaded by TMA from bf16 planes of the TEMPLATE (L2-resident) instead of
+//    per-image planes in HBM; edge strips are aligned to 8 pixels so that the conv's zero padding is a TMA load of zeros.
+//  * tc_rowconv2_kernel (ynet_tc_rowconv2_wp*): decoder.i.0 and decoder.i.2 in one launch -- conv A's epilogue writes its
+//    row into a shared-memory ring that conv B marches over with the same issuer code (templated on the TMEM ring size);
+//    the hoisted partial sums arrive through their own TMA row ring.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -300,7 +308,7 @@ __device__ __forceinline__ void rc_conv_issuer(int H, long long items, int kbn, 
       if (Y + 1 < H) mbar_wait(acc_empty + 8u * rc_slot<NS>(g + 1), (uint32_t)((((g + 1) / NS) & 1) ^ 1), nullptr);
       mbar_wait(in_full + 8u * (uint32_t)stage, ph_in, nullptr);
       tc_fence_after();
-          // kernel rows kh_lo..kh_hi contribute (output row g + 1 - kh must exist).  The slots of rows g + 1, g, g - 1 are
+      // kernel rows kh_lo..kh_hi contribute (output row g + 1 - kh must exist).  The slots of rows g + 1, g, g - 1 are
       // consecutive except where the ring wraps: after kh = 0 when g % 8 == 7, after kh = 1 when g % 8 == 0.
       const int kh_lo = (Y + 1 < H) ? 0 : 1, kh_hi = (Y >= 1) ? 2 : 1;
       const int brk = (pos == NS - 1) ? 1 : (pos == 0 ? 2 : 3);          // first kernel row of a second run
