@@ -742,7 +742,7 @@ constexpr int R2_NY = 2;                         // conv B -> predictor row ring
 constexpr int R2_PROW = 4 * RC_CHUNK_BYTES;      // one row of partial sums: [4 chunks (hi)][128 px][8 ch] bf16
 constexpr int R2_THREADS_TAIL = 32 * 28;
 constexpr int R2_THREADS_PLAIN = 32 * 20;
-constexpr int R2_SOFT_WARPS = 8;
+constexpr int R2_SOFT_WARPS = 16;
 constexpr uint32_t R2_BCOL = 128;                // first TMEM column of conv B's ring
 
 struct Rc2Params {
@@ -774,6 +774,59 @@ __device__ __forceinline__ void softargmax_row16_range(SoftState& st, const uint
   softargmax_row16(st, vm, bias, x0, y);
 }
 
+// shared-memory accesses by 32-bit shared address (one register instead of a 64-bit generic pointer: the tail variant runs
+// 896 threads at 72 registers, and spilled loop state in the epilogues costs an L2 round trip per row)
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// 32 lanes x 32 columns <- 0: a drained accumulator slot is handed back zeroed (one operand register; the bias is added
+// by the epilogue, four channels at a time from shared memory, instead of living in 32 registers or in the slot)
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr),
+      "r"(0u)
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// 32 lanes x 16 columns <- 16 floats at shared address b (plain variant: the slot is handed back holding the bias, like
+// tc_rowconv_kernel's, which keeps the two-conv block bit-identical to the two separate launches)
+__device__ __forceinline__ void tmem_st16_s(uint32_t taddr, uint32_t b) {
+  const uint4 b0 = lds128(b), b1 = lds128(b + 16), b2 = lds128(b + 32), b3 = lds128(b + 48);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(b0.x), "r"(b0.y), "r"(b0.z), "r"(b0.w), "r"(b1.x), "r"(b1.y), "r"(b1.z), "r"(b1.w), "r"(b2.x), "r"(b2.y), "r"(b2.z),
+      "r"(b2.w), "r"(b3.x), "r"(b3.y), "r"(b3.z), "r"(b3.w)
+      : "memory");
+}
+template <bool ZERO>
+__device__ __forceinline__ void slot_reset(uint32_t taddr, uint32_t sbias) {
+  if (ZERO) {
+    tmem_zero32(taddr);
+  } else {
+    tmem_st16_s(taddr, sbias);
+    tmem_st16_s(taddr + 16, sbias + 64);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+}
+// v[8c .. 8c + 7] += the eight bias floats at shared address b
+__device__ __forceinline__ void add_bias8(uint32_t (&v)[32], int c, uint32_t b) {
+  const uint4 b0 = lds128(b), b1 = lds128(b + 16);
+  v[8 * c + 0] = __float_as_uint(__uint_as_float(v[8 * c + 0]) + __uint_as_float(b0.x));
+  v[8 * c + 1] = __float_as_uint(__uint_as_float(v[8 * c + 1]) + __uint_as_float(b0.y));
+  v[8 * c + 2] = __float_as_uint(__uint_as_float(v[8 * c + 2]) + __uint_as_float(b0.z));
+  v[8 * c + 3] = __float_as_uint(__uint_as_float(v[8 * c + 3]) + __uint_as_float(b0.w));
+  v[8 * c + 4] = __float_as_uint(__uint_as_float(v[8 * c + 4]) + __uint_as_float(b1.x));
+  v[8 * c + 5] = __float_as_uint(__uint_as_float(v[8 * c + 5]) + __uint_as_float(b1.y));
+  v[8 * c + 6] = __float_as_uint(__uint_as_float(v[8 * c + 6]) + __uint_as_float(b1.z));
+  v[8 * c + 7] = __float_as_uint(__uint_as_float(v[8 * c + 7]) + __uint_as_float(b1.w));
+}
+
 template <bool TAIL>
 __global__ void __launch_bounds__(TAIL ? R2_THREADS_TAIL : R2_THREADS_PLAIN, 1)
 tc_rowconv2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
@@ -784,7 +837,8 @@ tc_rowconv2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
   const RcParams& p = pp.a;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NTHREADS = TAIL ? R2_THREADS_TAIL : R2_THREADS_PLAIN;
-  constexpr int W_EPA = 4, W_EPB = 12, W_SOFT = 20;
+  constexpr int SETS = TAIL ? 1 : 2;               // epilogue warp sets per conv (tail: the thread budget goes to 16 soft-argmax warps)
+  constexpr int W_EPA = 4, W_EPB = W_EPA + 4 * SETS, W_SOFT = W_EPB + 4 * SETS;
   constexpr int NPR = TAIL ? 8 : 4;                // rows of the partial-sum ring
   constexpr int NS = TAIL ? R2_NS : 8;             // slots per accumulator ring: the tail shares the 512 columns with the predictor
   constexpr uint32_t BCOL = TAIL ? R2_BCOL : 256u; // first column of conv B's ring
@@ -864,15 +918,10 @@ tc_rowconv2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  if ((warp >= W_EPA && warp < W_EPA + 4) || (warp >= W_EPB && warp < W_EPB + 4)) {   // both rings start out holding their bias
+  if ((warp >= W_EPA && warp < W_EPA + 4) || (warp >= W_EPB && warp < W_EPB + 4)) {   // both rings start out zeroed (tail) / holding their bias (plain)
     const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (warp >= W_EPB ? BCOL : 0u);
-    const float* b = s_bias + (warp >= W_EPB ? 32 : 0);
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      tmem_st16(t_row + (uint32_t)(s * RC_CO), b);
-      tmem_st16(t_row + (uint32_t)(s * RC_CO + 16), b + 16);
-    }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    for (int s = 0; s < NS; ++s) slot_reset<TAIL>(t_row + (uint32_t)(s * RC_CO), smem_u32(s_bias) + (warp >= W_EPB ? 128u : 0u));
   }
   tc_fence_before();
   __syncthreads();
@@ -1031,34 +1080,35 @@ tc_rowconv2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     const int q = warp & 3, set = (warp - W_EPA) >> 2;
     const int m = q * 32 + lane;                    // lane m = pixel xw + 1 + m
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t bar0 = smem_u32(bars);
+    constexpr uint32_t B_ACCA_FULL = 8u * (2 * R2_NSTG), B_ACCA_EMPTY = B_ACCA_FULL + 8u * NS, B_A_FULL = B_ACCA_EMPTY + 8u * NS,
+                       B_A_EMPTY = B_A_FULL + 8u * R2_NA;
+    const uint32_t b_pr_full = smem_u32(pr_full), b_pr_empty = smem_u32(pr_empty);
+    const uint32_t sa_lane = smem_u32(s_a) + (uint32_t)(m * 16), sbias = smem_u32(s_bias);
+    const uint32_t spr_lane = smem_u32(s_pr) + (uint32_t)(min(m + 1, RC_M - 1) * 16);   // this lane's pixel in a partial-sum row
+    const bool has_part = p.part != nullptr && !(p.dbg & 8);
+    const int H = p.H, W = p.W, strips = p.strips, items = (int)p.items;
     int g0 = 0;
-    const int H = p.H;
-    for (long long item = blockIdx.x; item < p.items; item += gridDim.x, g0 += H) {
-      const int n = (int)(item / p.strips), s = (int)(item - (long long)n * p.strips);
-      const int x = rc2_window(s, p.strips, p.W) + 1 + m;
-      const bool inside = x >= 0 && x < p.W;        // (lanes 126 / 127 hold garbage that conv B's valid lanes never read)
-      const bool has_part = p.part != nullptr && !(p.dbg & 8);
-      const int mp = min(m + 1, RC_M - 1);              // window pixel of this lane's output pixel in the partial-sum row
-      for (int Y = (g0 ^ set) & 1; Y < H; Y += 2) {          // this set's rows: g % 2 == set
+    for (int item = blockIdx.x; item < items; item += gridDim.x, g0 += H) {
+      const int x = rc2_window(item % strips, strips, W) + 1 + m;
+      const bool inside = x >= 0 && x < W;          // (lanes 126 / 127 hold garbage that conv B's valid lanes never read)
+      for (int Y = (SETS == 2) ? ((g0 ^ set) & 1) : 0; Y < H; Y += SETS) {          // this set's rows: g % SETS == set
         const int g = g0 + Y;
-        const int sl = rc_slot<NS>(g);
-        mbar_wait(smem_u32(&acca_full[sl]), (uint32_t)((g / NS) & 1), nullptr);
+        const uint32_t sl = (uint32_t)rc_slot<NS>(g);
+        mbar_wait(bar0 + B_ACCA_FULL + 8u * sl, (uint32_t)((g / NS) & 1), nullptr);
         tc_fence_after();
         uint32_t v[32];
-        tmem_ld32(t_row + (uint32_t)(sl * RC_CO), v);
-        tmem_st16(t_row + (uint32_t)(sl * RC_CO), s_bias);
-        tmem_st16(t_row + (uint32_t)(sl * RC_CO + 16), s_bias + 16);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tmem_ld32(t_row + sl * RC_CO, v);
+        slot_reset<TAIL>(t_row + sl * RC_CO, sbias);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&acca_empty[sl]));
+        if (lane == 0) mbar_arrive(bar0 + B_ACCA_EMPTY + 8u * sl);
         if (has_part) {              // + the agent's hoisted encoder-feature share of conv A (fp32 add), from its TMA ring
-          const int pb = g & (NPR - 1);
-          mbar_wait(smem_u32(&pr_full[pb]), (uint32_t)((g / NPR) & 1), nullptr);
-          const unsigned char* prow = s_pr + (size_t)pb * R2_PROW + mp * 16;
+          const uint32_t pb = (uint32_t)(g & (NPR - 1));
+          mbar_wait(b_pr_full + 8u * pb, (uint32_t)((g / NPR) & 1), nullptr);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const uint4 h4 = *reinterpret_cast<const uint4*>(prow + c * RC_CHUNK_BYTES);
+            const uint4 h4 = lds128(spr_lane + pb * R2_PROW + (uint32_t)(c * RC_CHUNK_BYTES));
             const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -1068,27 +1118,26 @@ tc_rowconv2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
             }
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&pr_empty[pb]));
+          if (lane == 0) mbar_arrive(b_pr_empty + 8u * pb);
         }
-        uint4 o[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          o[c].x = inside ? pack_bf16_act<true>(v[8 * c + 0], v[8 * c + 1]) : 0u;
-          o[c].y = inside ? pack_bf16_act<true>(v[8 * c + 2], v[8 * c + 3]) : 0u;
-          o[c].z = inside ? pack_bf16_act<true>(v[8 * c + 4], v[8 * c + 5]) : 0u;
-          o[c].w = inside ? pack_bf16_act<true>(v[8 * c + 6], v[8 * c + 7]) : 0u;
-        }
-        const int b = g & (R2_NA - 1);
-        if (lane == 0) mbar_wait(smem_u32(&a_empty[b]), (uint32_t)(((g / R2_NA) & 1) ^ 1), nullptr);
+        const uint32_t b = (uint32_t)(g & (R2_NA - 1));
+        if (lane == 0) mbar_wait(bar0 + B_A_EMPTY + 8u * b, (uint32_t)(((g / R2_NA) & 1) ^ 1), nullptr);
         __syncwarp();
-        unsigned char* ab = s_a + (size_t)b * RC_YROW + m * 16;
         if (!(p.dbg & 2)) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(ab + c * (RC_M * 16)) = o[c];
+          for (int c = 0; c < 4; ++c) {
+            if (TAIL) add_bias8(v, c, sbias + (uint32_t)(c * 32));
+            uint4 o;
+            o.x = inside ? pack_bf16_act<true>(v[8 * c + 0], v[8 * c + 1]) : 0u;
+            o.y = inside ? pack_bf16_act<true>(v[8 * c + 2], v[8 * c + 3]) : 0u;
+            o.z = inside ? pack_bf16_act<true>(v[8 * c + 4], v[8 * c + 5]) : 0u;
+            o.w = inside ? pack_bf16_act<true>(v[8 * c + 6], v[8 * c + 7]) : 0u;
+            sts128(sa_lane + b * RC_YROW + (uint32_t)(c * (RC_M * 16)), o);
+          }
         }
         if (!(p.dbg & 16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&a_full[b]));
+        if (lane == 0) mbar_arrive(bar0 + B_A_FULL + 8u * b);
       }
     }
   } else if (warp < W_SOFT) {
@@ -1096,38 +1145,38 @@ tc_rowconv2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     const int q = warp & 3, set = (warp - W_EPB) >> 2;
     const int m = q * 32 + lane;                    // lane m = pixel xw + 2 + m
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + BCOL;
+    const uint32_t b_accb_full = smem_u32(accb_full), b_accb_empty = smem_u32(accb_empty);
+    const uint32_t b_y_full = smem_u32(y_full), b_y_empty = smem_u32(y_empty);
+    const uint32_t sy_lane = smem_u32(s_y) + (uint32_t)(m * 16), sbias = smem_u32(s_bias) + 128u;
+    const int H = p.H, W = p.W, strips = p.strips, items = (int)p.items;
+    const bool relu_b = pp.relu_b != 0;
     int g0 = 0;
-    const int H = p.H;
-    for (long long item = blockIdx.x; item < p.items; item += gridDim.x, g0 += H) {
-      const int n = (int)(item / p.strips), s = (int)(item - (long long)n * p.strips);
-      const int x = rc2_window(s, p.strips, p.W) + 2 + m;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, g0 += H) {
+      const int n = item / strips, s = item - n * strips;
+      const int x = rc2_window(s, strips, W) + 2 + m;
       // the columns [W - 118, W) belong to the last strip alone (see tc_rowconv_kernel<false, true>)
-      const bool live = m < R2_VW && x >= 0 && x < p.W && (s == p.strips - 1 || x < p.W - 118);
-      for (int Y = (g0 ^ set) & 1; Y < H; Y += 2) {          // this set's rows: g % 2 == set
+      const bool live = m < R2_VW && x >= 0 && x < W && (s == strips - 1 || x < W - 118);
+      for (int Y = (SETS == 2) ? ((g0 ^ set) & 1) : 0; Y < H; Y += SETS) {          // this set's rows: g % SETS == set
         const int g = g0 + Y;
-        const int sl = rc_slot<NS>(g);
-        mbar_wait(smem_u32(&accb_full[sl]), (uint32_t)((g / NS) & 1), nullptr);
+        const uint32_t sl = (uint32_t)rc_slot<NS>(g);
+        mbar_wait(b_accb_full + 8u * sl, (uint32_t)((g / NS) & 1), nullptr);
         tc_fence_after();
         uint32_t v[32];
-        tmem_ld32(t_row + (uint32_t)(sl * RC_CO), v);
-        tmem_st16(t_row + (uint32_t)(sl * RC_CO), s_bias + 32);
-        tmem_st16(t_row + (uint32_t)(sl * RC_CO + 16), s_bias + 48);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tmem_ld32(t_row + sl * RC_CO, v);
+        slot_reset<TAIL>(t_row + sl * RC_CO, sbias);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&accb_empty[sl]));
+        if (lane == 0) mbar_arrive(b_accb_empty + 8u * sl);
         uint4 o[4];
-        if (pp.relu_b) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 4; ++c) {
+          if (TAIL) add_bias8(v, c, sbias + (uint32_t)(c * 32));
+          if (relu_b) {
             o[c].x = pack_bf16_act<true>(v[8 * c + 0], v[8 * c + 1]);
             o[c].y = pack_bf16_act<true>(v[8 * c + 2], v[8 * c + 3]);
             o[c].z = pack_bf16_act<true>(v[8 * c + 4], v[8 * c + 5]);
             o[c].w = pack_bf16_act<true>(v[8 * c + 6], v[8 * c + 7]);
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          } else {
             o[c].x = pack_bf16_act<false>(v[8 * c + 0], v[8 * c + 1]);
             o[c].y = pack_bf16_act<false>(v[8 * c + 2], v[8 * c + 3]);
             o[c].z = pack_bf16_act<false>(v[8 * c + 4], v[8 * c + 5]);
@@ -1135,26 +1184,25 @@ tc_rowconv2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
           }
         }
         if (TAIL) {
-          const int b = g & (R2_NY - 1);
-          if (lane == 0) mbar_wait(smem_u32(&y_empty[b]), (uint32_t)(((g / R2_NY) & 1) ^ 1), nullptr);
+          const uint32_t b = (uint32_t)(g & (R2_NY - 1));
+          if (lane == 0) mbar_wait(b_y_empty + 8u * b, (uint32_t)(((g / R2_NY) & 1) ^ 1), nullptr);
           __syncwarp();
-          unsigned char* yb = s_y + (size_t)b * RC_YROW + m * 16;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(yb + c * (RC_M * 16)) = o[c];
+          for (int c = 0; c < 4; ++c) sts128(sy_lane + b * RC_YROW + (uint32_t)(c * (RC_M * 16)), o[c]);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&y_full[b]));
+          if (lane == 0) mbar_arrive(b_y_full + 8u * b);
         } else if (live) {
           const int po = p.pad_out;
-          const int Hp = p.H + 2 * po, Wp = p.W + 2 * po;
+          const int Hp = H + 2 * po, Wp = W + 2 * po;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if (c >= p.out_chunks) break;
             uint4* dst = reinterpret_cast<uint4*>(p.out) + (((size_t)n * p.out_chunks + c) * Hp + (Y + po)) * Wp + (x + po);
             *dst = o[c];
             if (po) {      // replicate the border pixels into the ring (input of the phase-decomposed upconv)
-              const int dyv = (Y == 0) ? -1 : ((Y == p.H - 1) ? 1 : 0);
-              const int dxv = (x == 0) ? -1 : ((x == p.W - 1) ? 1 : 0);
+              const int dyv = (Y == 0) ? -1 : ((Y == H - 1) ? 1 : 0);
+              const int dxv = (x == 0) ? -1 : ((x == W - 1) ? 1 : 0);
               if (dyv != 0) dst[dyv * Wp] = o[c];
               if (dxv != 0) dst[dxv] = o[c];
               if (dyv != 0 && dxv != 0) dst[dyv * Wp + dxv] = o[c];
@@ -1164,51 +1212,43 @@ tc_rowconv2_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
       }
     }
   } else if (TAIL) {
-    // ===================== soft-argmax: 2 sets x 4 lane quadrants, 32 pixels per warp; TMEM lane = channel, column m of
-    // the accumulator = pixel xw + 2 + m; set k takes the rows with g % 2 == k (= predictor accumulator k) ==========
+    // ===================== soft-argmax: 2 sets x 4 lane quadrants x 2 halves = 16 warps, 16 pixels each; TMEM lane =
+    // channel, column m of the accumulator = pixel xw + 2 + m; set k takes the rows with g % 2 == k ==========
     const int e = warp - W_SOFT;
-    const int q = warp & 3, set = e >> 2;
-    const int col0 = 32 * q;
+    const int q = warp & 3, set = (e >> 2) & 1, half = e >> 3;
+    const int col0 = 32 * q + 16 * half;
     const bool active = lane < p.c_pred;
     const float bias = active ? p.pbias[lane] : 0.f;
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + RC_PACC + (uint32_t)(set * 128 + col0);
     const uint32_t pf = smem_u32(&p_full[set]), pe = smem_u32(&p_empty[set]);
-    const int H = p.H, W = p.W;
+    const int H = p.H, W = p.W, strips = p.strips, items = (int)p.items;
     int g0 = 0;
-    for (long long item = blockIdx.x; item < p.items; item += gridDim.x, g0 += H) {
-      const int n = (int)(item / p.strips), s = (int)(item - (long long)n * p.strips);
-      const int xs = rc2_window(s, p.strips, W) + 2;           // pixel of accumulator column 0
+    for (int item = blockIdx.x; item < items; item += gridDim.x, g0 += H) {
+      const int n = item / strips, s = item - n * strips;
+      const int xs = rc2_window(s, strips, W) + 2;             // pixel of accumulator column 0
       const int x0 = xs + col0;
-      const int lo = max(0, xs), hi = (s == p.strips - 1) ? min(W, xs + R2_VW) : min(W - 118, xs + R2_VW);
+      const int lo = max(0, xs), hi = (s == strips - 1) ? min(W, xs + R2_VW) : min(W - 118, xs + R2_VW);
       SoftState st{PR_NEG, 0.f, 0.f, 0.f};
-      const bool any0 = x0 < hi && x0 + 16 > lo, any1 = x0 + 16 < hi && x0 + 32 > lo;
-      const bool full0 = x0 >= lo && x0 + 16 <= hi, full1 = x0 + 16 >= lo && x0 + 32 <= hi;
+      const bool any = x0 < hi && x0 + 16 > lo, full = x0 >= lo && x0 + 16 <= hi;
       for (int Y = (g0 ^ set) & 1; Y < H; Y += 2) {
         const int g = g0 + Y;
         mbar_wait(pf, (uint32_t)((g >> 1) & 1), nullptr);
-        if (!(any0 || any1)) {       // nothing to reduce in these columns, but the accumulator hand-shake goes on
+        if (!any) {                  // nothing to reduce in these columns, but the accumulator hand-shake goes on
           __syncwarp();
           if (lane == 0) mbar_arrive(pe);
           continue;
         }
         tc_fence_after();
-        uint32_t v0[16], v1[16];
-        tmem_ld16_nowait(t_addr, v0);
-        tmem_ld16_nowait(t_addr + 16u, v1);
-        tmem_ld_wait(v0);
-        tmem_ld_wait(v1);
+        uint32_t v[16];
+        tmem_ld16(t_addr, v);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(pe);      // the values are in registers: release the accumulator
         if (p.dbg & 1) continue;
-        if (full0)
-          softargmax_row16(st, v0, bias, x0, Y);
-        else if (any0)
-          softargmax_row16_range(st, v0, bias, x0, Y, lo, hi);
-        if (full1)
-          softargmax_row16(st, v1, bias, x0 + 16, Y);
-        else if (any1)
-          softargmax_row16_range(st, v1, bias, x0 + 16, Y, lo, hi);
+        if (full)
+          softargmax_row16(st, v, bias, x0, Y);
+        else
+          softargmax_row16_range(st, v, bias, x0, Y, lo, hi);
       }
       if (active) p.partial[((size_t)n * p.c_pred + lane) * p.slots + s * R2_SOFT_WARPS + e] = make_float4(st.m, st.s, st.sx, st.sy);
     }

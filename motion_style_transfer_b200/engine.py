@@ -571,9 +571,9 @@ class YNetEngineTC(YNetEngine):
     # 32-channel activation between the two convs of a block stays in shared memory
     rowconv2 = os.environ.get('YNET_ROWCONV2', '1') == '1'
     # ... and with the predictor + soft-argmax behind it.  Correct and tested, but measured slower than decoder.4.0 followed by
-    # the fused decoder.4.2 tail kernel (4.0-4.8 vs 2.9 ms per 320 images): with one 896-thread CTA per SM (72 registers per
-    # thread, 512 TMEM columns shared by two 4-slot rings and the predictor) the three MMA streams run at ~35 % of the
-    # tensor pipe's 720 cycles per row.  Off by default.
+    # the fused decoder.4.2 tail kernel (3.9 vs 2.9 ms per 320 images, after removing every register spill): with one
+    # 896-thread CTA per SM (72 registers per thread, 512 TMEM columns shared by two 4-slot rings and the predictor) the
+    # three MMA streams run at ~40 % of the tensor pipe's 720 cycles per row.  Off by default.
     rowconv2_tail = os.environ.get('YNET_ROWCONV2_TAIL', '0') == '1'
 
     def _block_fused(self, decoder, key, i, up, partial, pyr_level, c_feat, tail):
