@@ -185,7 +185,8 @@ def evaluate(model, val_loader, val_images, device, dataset_name, homo_mat, inpu
     device_rng = RNG_MODE == 'device'
     # 40-bit stream id of this call; batch k of the call draws from epoch stream + k + 1 of the generator, whether it is
     # replayed from a graph or issued eagerly (same kernels, same numbers)
-    stream = (((torch.initial_seed() * 0x9E3779B1) ^ (_eval_calls * 0x85EBCA77)) & 0xFFFFFFFFFF) << 20
+    stream = (((torch.initial_seed() * 0x9E3779B1) ^ (_eval_calls * 0x85EBCA77) ^ (parallel.world()[0] * 0xC2B2AE35))
+              & 0xFFFFFFFFFF) << 20            # (ranks of a sharded run draw from different streams)
     eager_rng = None
     if device_rng:
         from .image_utils import DeviceRng
