@@ -111,6 +111,10 @@ class ClockSampler:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
         time.sleep(0.15)
         self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)        # (its exit must not overlap the end-to-end loop that follows)
+        except Exception:
+            pass
         sm, mx, reasons = [], None, set()
         for ts, line in self.rows:
             if ts < t0 or ts > t1 + 0.2:
@@ -547,6 +551,11 @@ def main():
     value = traj_per_step / (ms_step / 1000)
 
     # ---- end to end through the public call with HOST buffers (H2D of inputs + D2H of metrics inside) -----
+    # (every step ends in a blocking D2H read, so a host-side pause lands in the measurement: no garbage collection inside
+    # the timed loop, and the clock sampler's nvidia-smi child has exited before it starts)
+    import gc
+    gc.collect()
+    gc.disable()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_marks, e2e_km = [], []
@@ -562,6 +571,7 @@ def main():
         e2e_km.append(int(km_mod.last_iters.max().item()) if km_mod.last_iters is not None else None)
     e3.record()
     barrier()
+    gc.enable()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3)) / args.steps
     e2e_value = traj_per_step / (ms_e2e / 1000)
     h2d = scene_host.numel() * 4 + traj_host[0].numel() * 4
