@@ -28,6 +28,12 @@ USE_GRAPH = os.environ.get('YNET_EVAL_GRAPH', '1') == '1'
 # ~14 full batches: a (scene size, batch shape) is captured when this call alone brings that many, or from the second
 # evaluate() call that meets it on (validation / test rounds revisit their scenes).  Graphs own their activation pools:
 # the least recently used ones are dropped beyond GRAPH_POOL_GB.
+# The reference's scripts evaluate 8-10 agents per batch (scripts/*/generalize.sh: batch_size=10): ten agents fill a B200 to
+# a quarter.  Agents are independent (evaluate.py:109-291 has no cross-agent term: `sampling` divides by the batch-wide sum,
+# which torch.multinomial's own per-row normalisation undoes), so with the device generator -- where no reference random
+# stream has to be reproduced -- evaluate() forecasts at least EVAL_MIN_BATCH agents per launch sequence, whatever
+# `batch_size` says.  'host' RNG mode and return_samples keep the caller's batches.
+EVAL_MIN_BATCH = int(os.environ.get('YNET_EVAL_MIN_BATCH', '128'))
 GRAPH_MIN_BATCHES = 14
 GRAPH_MIN_BATCHES_SEEN = 3
 GRAPH_POOL_GB = float(os.environ.get('YNET_EVAL_GRAPH_GB', '48'))
@@ -183,6 +189,8 @@ def evaluate(model, val_loader, val_images, device, dataset_name, homo_mat, inpu
     global _eval_calls
     _eval_calls += 1
     device_rng = RNG_MODE == 'device'
+    if device_rng and not return_samples:
+        batch_size = max(int(batch_size), EVAL_MIN_BATCH)
     # 40-bit stream id of this call; batch k of the call draws from epoch stream + k + 1 of the generator, whether it is
     # replayed from a graph or issued eagerly (same kernels, same numbers)
     stream = (((torch.initial_seed() * 0x9E3779B1) ^ (_eval_calls * 0x85EBCA77) ^ (parallel.world()[0] * 0xC2B2AE35))

@@ -344,6 +344,7 @@ def test_evaluate_device_rng_graph_equals_eager_and_is_seeded(ops, monkeypatch):
                            2, c['resize'], c['T'], c['ttst'], c['cws'], c['thr'], c['cwsp'], return_preds=True)
 
     assert ev.RNG_MODE == 'device'
+    monkeypatch.setattr(ev, 'EVAL_MIN_BATCH', 1)             # (default 128: small caller batches are merged)
     monkeypatch.setattr(ev, 'GRAPH_MIN_BATCHES', 3)          # (default 14: a capture must pay for itself)
     a = run(True, 0)
     assert len(m.__dict__['_forecast_graphs']) == 1
@@ -362,3 +363,44 @@ def test_evaluate_device_rng_graph_equals_eager_and_is_seeded(ops, monkeypatch):
     assert len(graphs) == 1 and graphs[0] is not first and graphs[0].pool_bytes >= 0      # re-captured for the new weights
     ref = run(False, 0)
     assert np.array_equal(upd[2].ade.values, ref[2].ade.values)
+
+
+def test_evaluate_merges_small_batches(ops, monkeypatch):
+    """evaluate(batch_size=2) with the device generator forecasts EVAL_MIN_BATCH agents per launch sequence: same per-agent
+    rows as one call with the large batch (same streams: the batches coincide), fewer launches than 2-agent batches."""
+    import pandas as pd
+    from torch.utils.data import DataLoader, Dataset
+    from motion_style_transfer_b200.utils import evaluate as ev
+    g = load_golden('eval_sdd_short')
+    c = eval_cfg(g)
+    m = build_product_model(golden_state_dict(g), c['obs'], c['pred'], len(c['wps'])).set_backend('bf16')
+    traj = torch.cat([torch.from_numpy(g['trajectory']) + 0.41 * i for i in range(4)])[:7]
+    B = traj.shape[0]
+
+    class OneScene(Dataset):
+        def __len__(self):
+            return 1
+
+        def __getitem__(self, i):
+            return traj, pd.DataFrame({'metaId': np.repeat(np.arange(B), traj.shape[1])}), 's0'
+
+    loader = DataLoader(OneScene(), batch_size=1, collate_fn=lambda b: (b[0][0], [b[0][1]], b[0][2]))
+    tmpl = torch.from_numpy(O.create_dist_mat(int(g['template_size'])).astype(np.float32))
+    images = {'s0': torch.from_numpy(g['scene'])}
+    monkeypatch.setattr(ev, 'USE_GRAPH', False)
+
+    def run(bs, min_batch):
+        monkeypatch.setattr(ev, 'EVAL_MIN_BATCH', min_batch)
+        monkeypatch.setattr(ev, '_eval_calls', 0)
+        torch.manual_seed(3)
+        l0 = ops.launch_count
+        out = ev.evaluate(m, loader, images, 'cuda', 'sdd', None, tmpl, c['wps'], 'test', c['n_goal'], c['n_traj'], c['obs'], bs,
+                          c['resize'], c['T'], c['ttst'], c['cws'], c['thr'], c['cwsp'])
+        return out, ops.launch_count - l0
+
+    run(B, 1)                                            # (weight packing, template planes, autotuning: one-time launches)
+    merged, n_merged = run(2, 128)
+    whole, n_whole = run(B, 1)
+    small, n_small = run(2, 1)
+    assert np.array_equal(merged[2].ade.values, whole[2].ade.values) and n_merged == n_whole
+    assert n_small > 2 * n_merged and len(small[2]) == B
