@@ -262,3 +262,34 @@ def test_rowconv2_block_equals_unfused_chain(ops, n_wp, level, H0, W0, N, G, c_u
     again = ops.tc_rowconv2_wp_pred_softargmax([up, lazy], pa, _bias32(ba), pb, _bias32(bb), True, ppk, pbias.cuda(), 30,
                                                partial=part)
     assert torch.equal(again, gots)
+
+
+@pytest.mark.parametrize('n_wp,H0,W0,N,mod', [(1, 32, 128, 4, 2), (2, 32, 128, 6, 3), (2, 64, 352, 4, 0)])
+def test_rowconv2_edge_geometry(ops, n_wp, H0, W0, N, mod):
+    """Two-conv block at the smallest width (two overlapping edge strips), with one waypoint channel, with a goal-major
+    partial-sum source (image n reads partial n % mod), and with an interior strip: always bit-identical to the two
+    launches, and within bf16 tolerance of torch on the same operands."""
+    torch.manual_seed(7)
+    tmpl = ops.create_dist_template(3 * max(H0, W0), 'cuda')
+    coords = torch.stack([torch.rand(N * n_wp) * (W0 - 1), torch.rand(N * n_wp) * (H0 - 1)], 1).cuda().contiguous()
+    lazy = ops.tc_rasterize_pyramid(tmpl, coords, N, n_wp, H0, W0, 1, lazy_levels=1)[0]
+    up = ops.tc_pack(bf16_exact(torch.randn(N, 16, H0, W0)).cuda())
+    wa = bf16_exact(torch.randn(32, 16 + 32 + n_wp, 3, 3) * 0.1)
+    wb = bf16_exact(torch.randn(32, 32, 3, 3) * 0.1)
+    ba, bb = torch.randn(32) * 0.1, torch.randn(32) * 0.1
+    n_part = mod if mod else N
+    feat = ops.tc_pack(bf16_exact(torch.relu(torch.randn(n_part, 32, H0, W0))).cuda())
+    part = ops.tc_conv3x3_hilo([feat], ops.tc_pack_weights(wa[:, 16:48].contiguous().cuda(), [32]), 32, False)
+    pa = ops.tc_rowconv_pack_weights_cat(wa.cuda(), [(0, 16, 16)] + lazy.weight_parts(48))
+    pb = ops.tc_rowconv_pack_weights(wb.cuda(), 32)
+    mid = ops.tc_rowconv3x3([up, lazy], pa, _bias32(ba), 32, True, partial=part)
+    ref = ops.tc_rowconv3x3(mid, pb, _bias32(bb), 32, True)
+    got = ops.tc_rowconv2_wp([up, lazy], pa, _bias32(ba), pb, _bias32(bb), 32, True, partial=part)
+    torch.cuda.synchronize()
+    assert torch.equal(got.data, ref.data)
+    # against torch on the unpacked operands (bf16 operands, fp32 accumulation, bf16 activation in between)
+    wmap = ops.tc_unpack(lazy.materialize()).cpu()
+    x = torch.cat([ops.tc_unpack(up).cpu(), ops.tc_unpack(feat).cpu().repeat(N // n_part, 1, 1, 1), wmap], 1)
+    y1 = bf16_exact(F.relu(F.conv2d(x, wa, ba, padding=1)))
+    y2 = F.relu(F.conv2d(y1, wb, bb, padding=1))
+    assert rel_err(ops.tc_unpack(got).cpu().numpy(), y2.numpy()) < 1.5e-2
