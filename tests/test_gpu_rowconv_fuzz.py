@@ -85,3 +85,38 @@ def test_waypoint_source_and_two_conv_random_shapes(ops, seed):
     got = ops.tc_rowconv2_wp([up, lazy], p_lazy, _b32(ba), pb, _b32(bb), cout, relu, pad_out=pad_out, partial=part)
     torch.cuda.synchronize()
     assert torch.equal(got.data, ref.data), (level, H0, W0, N, n_wp, c_up, cout, relu, pad_out)
+
+
+@pytest.mark.parametrize('seed', range(10))
+def test_split_conv_random_shapes(ops, seed):
+    """The split-bf16 conv (bf16x3 engine) against float64 torch: random part counts / channels / sizes / batch sharing."""
+    import torch.nn.functional as F
+    from motion_style_transfer_b200.engine import YNetEngineSplit
+    rng = np.random.RandomState(300 + seed)
+    n_parts = int(rng.randint(1, 4))
+    B = int(rng.randint(1, 4))
+    G = int(rng.randint(1, 4))
+    H, W = int(rng.randint(1, 40)), int(rng.randint(1, 70))
+    cins = [int(rng.randint(1, 70)) for _ in range(n_parts)]
+    cout = int(rng.randint(1, 130))
+    relu = bool(rng.randint(2))
+    torch.manual_seed(seed)
+    # part 0 covers all G * B images; later parts may be per-agent (B images, read modulo) or broadcast (1 image)
+    batches = [G * B] + [int(rng.choice([G * B, B, 1])) for _ in range(n_parts - 1)]
+    xs = [torch.randn(n, c, H, W) for n, c in zip(batches, cins)]
+    w = torch.randn(cout, sum(cins), 3, 3) * 0.1
+    b = torch.randn(cout)
+    full = [x if x.shape[0] == G * B else x.repeat(G * B // x.shape[0], 1, 1, 1) for x in xs]
+    ref = F.conv2d(torch.cat(full, 1).double(), w.double(), b.double(), padding=1)
+    ref = F.relu(ref) if relu else ref
+    parts = [ops.split_pack(x.cuda()) for x in xs]
+    sources, ranges = YNetEngineSplit._group(parts)
+    idx = torch.cat([torch.arange(c0, c1) for c0, c1 in ranges])
+    packed = ops.split_pack_weights(w[:, idx].contiguous().cuda(), [s.layout for s in sources])
+    bias = torch.zeros((cout + 15) // 16 * 16)
+    bias[:cout] = b
+    out = ops.tc_conv3x3_split(sources, packed, bias.cuda(), cout, relu)
+    torch.cuda.synchronize()
+    got = ops.split_unpack(out).cpu()
+    assert got.shape == ref.shape, (batches, cins, cout, H, W)
+    assert rel_err(got.numpy(), ref.numpy()) < 3e-5, (batches, cins, cout, H, W)
