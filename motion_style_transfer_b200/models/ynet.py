@@ -296,7 +296,10 @@ class YNet(nn.Module):
         self.softargmax_ = SoftArgmax2D(normalized_coordinates=False)
         self.encoder_channels = encoder_channels
         self._engine = None
-        self._backend = 'fp32'
+        # the reference's scripts never choose an engine: YNET_BACKEND selects it for unchanged train.py / test.py runs
+        self._backend = os.environ.get('YNET_BACKEND', 'fp32')
+        if self._backend not in ('fp32', 'bf16', 'bf16x3'):
+            raise ValueError(f"YNET_BACKEND={self._backend!r}: expected 'fp32', 'bf16x3' or 'bf16'")
 
     # ---- engine plumbing -------------------------------------------------------------------------
     def set_backend(self, backend):
