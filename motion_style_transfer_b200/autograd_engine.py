@@ -60,15 +60,16 @@ def _tc_packed(kind, weight, ver, make):
     return val
 
 
-def _tc_conv_forward(w_eff, weight, wver, bias, relu, parts):
-    """conv3x3(cat(parts)) + bias (+ReLU): float32 NCHW parts (batch 1 = broadcast) -> float32 NCHW."""
+def _tc_conv_forward(fold, C_out, weight, wver, bias, relu, parts):
+    """conv3x3(cat(parts)) + bias (+ReLU): float32 NCHW parts (batch 1 = broadcast) -> float32 NCHW.  ``fold()`` yields the
+    effective OIHW weight (LoRA folded); it only runs when the packed weights are not cached for this version."""
     from .engine import YNetEngineSplit
     sp = [ops.split_pack(t) for t in parts]
     sources, ranges = YNetEngineSplit._group(sp)
     layouts = tuple(tuple(s.layout) for s in sources)
-    C_out = w_eff.shape[0]
 
     def make():
+        w_eff = fold()
         idx = torch.cat([torch.arange(c0, c1, device=w_eff.device) for c0, c1 in ranges])
         bias_pad = torch.zeros(ops._pad16(C_out), dtype=torch.float32, device=w_eff.device)
         if bias is not None:
@@ -79,13 +80,12 @@ def _tc_conv_forward(w_eff, weight, wver, bias, relu, parts):
     return ops.split_unpack(ops.tc_conv3x3_split(sources, packed, bias_pad, C_out, relu))
 
 
-def _tc_conv_dgrad(w_eff, weight, wver, dy, relu_out):
+def _tc_conv_dgrad(fold, C_in, weight, wver, dy, relu_out):
     """d/dx of conv3x3 (+ReLU): dy (masked by the activation) convolved with the flipped, transposed weight."""
     dys = ops.split_pack_masked(dy, relu_out) if relu_out is not None else ops.split_pack(dy)
-    C_in = w_eff.shape[1]
 
     def make():
-        w_t = w_eff.flip(2, 3).transpose(0, 1).contiguous()                 # (C_in, C_out, 3, 3)
+        w_t = fold().flip(2, 3).transpose(0, 1).contiguous()                # (C_in, C_out, 3, 3)
         return ops.split_pack_weights(w_t, [dys.layout])
     packed = _tc_packed('d', weight, (wver, tuple(dys.layout)), make)
     zero = _zero_bias.get((dy.device, C_in))
@@ -103,11 +103,11 @@ class Conv3x3Fn(torch.autograd.Function):
         ctx.tc = (TRAIN_TC and ops.tc_supported() and weight.shape[0] <= 256 and 3 * sum(
             ops._pad16(s.shape[1]) for s in sources) // 16 <= 64)
         if ctx.tc:
-            w_eff = ops.lora_fold(weight, lora_A, lora_B, packed=False)
             ctx.wver = (weight._version, None if lora_A is None else (id(lora_A), lora_A._version),
                         None if lora_B is None else (id(lora_B), lora_B._version))
             parts = [_materialize(s.contiguous(), m, 1) for s, m in zip(sources, modes)]
-            y = _tc_conv_forward(w_eff, weight if weight.is_leaf else None, ctx.wver, bias, relu, parts)
+            y = _tc_conv_forward(lambda: ops.lora_fold(weight, lora_A, lora_B, packed=False), weight.shape[0],
+                                 weight if weight.is_leaf else None, ctx.wver, bias, relu, parts)
         else:
             packed = ops.lora_fold(weight, lora_A, lora_B, packed=True)
             y = ops.conv3x3_f32(list(zip(sources, modes)), packed, bias, relu, N, H, W)
@@ -125,9 +125,10 @@ class Conv3x3Fn(torch.autograd.Function):
         d_weight = d_bias = d_A = d_B = None
         d_sources = [None] * len(sources)
         if any(need[8:]):
-            w_eff = ops.lora_fold(weight, lora_A, lora_B, packed=False)
-            dx = (_tc_conv_dgrad(w_eff, weight if weight.is_leaf else None, ctx.wver, dy, relu_out) if ctx.tc
-                  else ops.conv3x3_dgrad_f32(dy, relu_out, w_eff))
+            def fold():
+                return ops.lora_fold(weight, lora_A, lora_B, packed=False)
+            dx = (_tc_conv_dgrad(fold, weight.shape[1], weight if weight.is_leaf else None, ctx.wver, dy, relu_out) if ctx.tc
+                  else ops.conv3x3_dgrad_f32(dy, relu_out, fold()))
             c0 = 0
             for i, (s, mode) in enumerate(zip(sources, ctx.modes)):
                 c1 = c0 + s.shape[1]
