@@ -38,6 +38,15 @@ GRAPH_MIN_BATCHES = 14
 GRAPH_MIN_BATCHES_SEEN = 3
 GRAPH_POOL_GB = float(os.environ.get('YNET_EVAL_GRAPH_GB', '48'))
 _eval_calls = 0
+
+
+def reset_rng_stream():
+    """Rewind the call counter of the device generator's stream id: the next evaluate() draws what the first one after
+    the same torch.manual_seed() drew (utils/data_utils.py::set_random_seeds calls this)."""
+    global _eval_calls
+    _eval_calls = 0
+
+
 # agent x goal decoder passes per launch (bounds activation memory: ~40 MB per pass at 416^2)
 MAX_STACKED_PASSES = int(os.environ.get('YNET_MAX_STACKED_PASSES', '640'))
 

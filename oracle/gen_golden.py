@@ -447,6 +447,170 @@ def gen_forward_batch(ns):
          grad_loss=img2.grad.detach().numpy(), **{'sd/' + k: v for k, v in sd0.items()})
 
 
+def _agents_frame(seed, n_agents=37, T=5):
+    rng = np.random.RandomState(seed)
+    ids = rng.permutation(200)[:n_agents]
+    rows = [dict(frame=t, trackId=int(m), x=float(rng.rand()), y=float(rng.rand()), sceneId='s%d' % (m % 3), metaId=int(m))
+            for m in ids for t in range(T)]
+    return pd.DataFrame(rows)
+
+
+def _xs(df):
+    return None if df is None else [float(v) for v in df.x.values]
+
+
+def _log_of_run(seed, exp, n_param, early, ade, fde, pre='ckpts/sdd__ynet__ped.pt', tuned=None):
+    """What one train.py / test.py run prints, reduced to the lines the scraper reads (models/trainer.py:203,280,344,351;
+    train.py:33; util.py:59)."""
+    s = str({'save_every_n': 121, 'resize_factor': 0.25, 'seed': seed, 'pretrained_ckpt': pre, 'tuned_ckpt': tuned,
+             'lr': 0.003}) + '\n'
+    if exp:
+        s += f'Experiment {exp} has started\n'
+    if n_param is not None:
+        s += 'The number of trainable parameters: {:d}\n'.format(n_param)
+    if early is not None:
+        s += f'Early stop at epoch {early}\n'
+    s += f'Round 0: \nTest ADE: {ade + 1} \nTest FDE: {fde + 1}\n'
+    s += f'\nAverage performance (by 3): \nTest ADE: {ade} \nTest FDE: {fde}\n'
+    return s
+
+
+def gen_scripts_host(ns):
+    """the host side of train.py / test.py run LIVE -- utils/data_utils.py:14-48,754-912,955-964 (splits,
+    sample limits, with numpy's global generator seeded), utils/parser.py, utils/util.py (names, parameter dictionaries)
+    and utils/extract_log.py (scraped CSVs).  One JSON file: inputs and the reference's outputs / printed lines."""
+    import contextlib
+    import io
+    import json
+    import tempfile
+    R, RU, RP, RX = ns.data_utils, ns.util, ns.parser, ns.extract_log
+    out = {}
+
+    def captured(fn, *a, **kw):
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf), warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            res = fn(*a, **kw)
+        return res, buf.getvalue()
+
+    frames = {'main': _agents_frame(0), 'Biker.pkl': _agents_frame(1), 'Car.pkl': _agents_frame(2, 20),
+              'train.pkl': _agents_frame(3, 30), 'val.pkl': _agents_frame(4, 8), 'test.pkl': _agents_frame(5, 9)}
+    out['frames'] = {k: v.to_dict(orient='list') for k, v in frames.items()}
+    df = frames['main']
+    out['split_by_ratio'] = []
+    for kw in [dict(val_split=0.1, test_split=0.2), dict(val_split=5, test_split=10, shuffle=True),
+               dict(val_split=0.1, test_split=12, share_val_test=True), dict(val_split=0, test_split=12, share_val_test=True),
+               dict(val_split=10, test_split=12, share_val_test=True, shuffle=True), dict(val_split=0.3),
+               dict(val_split=0.1, test_split=0.2, given_test_meta_ids=[3, 5, 7, 88])]:
+        np.random.seed(4)
+        call = dict(kw)
+        if 'given_test_meta_ids' in call:
+            call['given_test_meta_ids'] = np.array(call['given_test_meta_ids'])
+        parts, printed = captured(R.dataset_split_by_ratio, df, **call)
+        out['split_by_ratio'].append(dict(kw=kw, seed=4, parts=[_xs(p) for p in parts], printed=printed,
+                                          next_random=float(np.random.rand())))
+    np.random.seed(1)
+    out['limit_samples'] = dict(seed=1, num=3, batch_size=4, xs=_xs(R.limit_samples(df, 3, 4)),
+                                xs_ordered=_xs(R.limit_samples(df, 2, 4, False)))
+    out['downsample'] = dict(step=2, xs=_xs(R.downsample(df, 2)))
+    short = df.drop(index=[0, 1, 7, 30, 31, 32, 33])
+    out['filter_short'] = dict(dropped=[0, 1, 7, 30, 31, 32, 33], threshold=4, xs=_xs(R.filter_short_trajectories(short, 4)))
+    out['prepare'] = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, f in frames.items():
+            if name != 'main':
+                f.to_pickle(os.path.join(tmp, name))
+        two = ['Biker.pkl', 'Car.pkl']
+        for args in [('sequential', 4, 2, two, two, 0.1, [5, 6], False, False, 'train', True),
+                     ('sequential', 4, None, two[:1], two[:1], 0.1, [5], True, True, 'train', False),
+                     ('sequential', 4, None, None, two, 0.1, [5, 7], False, True, 'eval', False),
+                     ('predefined', 4, 2, None, None, None, None, True, False, 'train', False),
+                     ('predefined', 4, None, None, None, None, None, False, False, 'eval', True)]:
+            np.random.seed(7)
+            parts, printed = captured(R.prepare_dataeset, tmp, *args)
+            out['prepare'].append(dict(args=list(args), seed=7, parts=[_xs(p) for p in parts], printed=printed))
+        _, printed = captured(R.split_train_val_test_randomly, tmp, 'Biker.pkl', 0.1, 0.2, seed=3)
+        out['split_randomly'] = dict(val_split=0.1, test_split=0.2, seed=3, printed=printed, parts=[
+            _xs(pd.read_pickle(os.path.join(tmp, 'Biker', n + '.pkl'))) for n in ('train', 'val', 'test')])
+        sel, printed = captured(R.dataset_split_given_scenes, tmp, two, ['s1'])
+        out['given_scenes'] = dict(scenes=['s1'], xs=_xs(sel), printed=printed)
+    # flags, names
+    train_argv = [
+        '--fine_tune --config_filename sdd_shortterm_train.yaml --seed 3 --batch_size 10 --n_epoch 100 --n_early_stop 30 '
+        '--n_round 3 --dataset_path filter/shortterm/agent_type/deathCircle_0/Biker --network original --load_data predefined '
+        '--pretrained_ckpt ckpts/sdd__ynet__ped.pt --train_net mosa_1 --position 0 1 2 3 4 --ckpt_path ckpts/sdd/ped_to_biker '
+        '--n_train_batch 3 --lr 0.003 --steps 20 --smooth_val',
+        '--config_filename inD_longterm_train.yaml --dataset_path filter/longterm/agent_type/scene1 --network fusion '
+        '--n_fusion 2 --train_files car.pkl truck.pkl --val_files car.pkl truck.pkl --test_splits 10 20 --val_split 0.2 '
+        '--augment --ynet_bias --n_train_batch 0.5 --lr 0.00005 --n_epoch 50 --n_early_stop 300 --share_val_test --shuffle',
+        '--config_filename x.yaml --dataset_path a/b --network embed --train_net all --load_data predefined']
+    test_argv = ['--config_filename sdd_shortterm_eval.yaml --seed 2 --batch_size 10 --n_round 3 --dataset_path p/q --network '
+                 'original --load_data predefined --pretrained_ckpt ckpts/a__b__ped.pt --tuned_ckpt '
+                 'ckpts/x/Seed_1__p_q__mosa_1__Pos_0_1__TrN_20__lr_0.003__AUG__bias__original.pt']
+    out['parser'] = []
+    for is_train, argvs in ((True, train_argv), (False, test_argv)):
+        for argv in argvs:
+            a = RP.get_parser(is_train).parse_args(argv.split())
+            rec = dict(is_train=is_train, argv=argv, namespace=dict(vars(a)))
+            if is_train:
+                rec['experiment'] = {str(n): RU.get_experiment_name(a, n) for n in (17, 3)}
+            out['parser'].append(rec)
+    names = ['ckpts/x/Seed_1__p_q__mosa_1__Pos_0_1__TrN_20__lr_0.003__AUG__bias__original.pt',
+             'Seed_2__a__all__TrN_40__lr_0.00005__original.pt', 'Seed_1__p__encoder__TrN_10__original.pt']
+    out['ckpt_names'] = [dict(path=n, name=RU.get_ckpt_name(n), position=RU.get_position(n), position_str=RU.get_position(
+        n, return_list=False), train_net=RX.get_train_net(n), n_train=RX.get_n_train(n), lr=RX.get_lr(n),
+        bias=RX.get_bool_bias(n), aug=RX.get_bool_aug(n)) for n in names]
+    out['update_params'] = []
+    for pre in ('ckpts/sdd__ynet__ped.pt', 'ckpts/sdd__ynet__ped_embed.pt'):
+        base = {'pretrained_ckpt': pre, 'train_net': 'train', 'position': []}
+        out['update_params'].append(dict(tuned=names[0], params=base, updated=RU.update_params(names[0], base)))
+    out['ckpts_and_names'] = [dict(args=a, result=[list(r) for r in RU.get_ckpts_and_names(*a)]) for a in
+                              [(['a', 'b'], ['A', 'B'], None, [None]), (None, None, 'pre.pt', names[:2])]]
+    # get_params / get_image_and_data_path in a scratch working directory
+    with tempfile.TemporaryDirectory() as tmp:
+        for d in ('config', 'data/sdd/raw/annotations', 'data/sdd/p/q'):
+            os.makedirs(os.path.join(tmp, d))
+        yaml_text = ('save_every_n: 121\nresize_factor: 0.25\ndata_dir: data/\ndataset_name: sdd\nwaypoints:\n  - 11\n'
+                     'CWS_params: None\n')
+        with open(os.path.join(tmp, 'config', 'sdd_shortterm_eval.yaml'), 'w') as f:
+            f.write(yaml_text)
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            a = RP.get_parser(False).parse_args(test_argv[0].split())
+            params, printed = captured(RU.get_params, a)
+            out['get_params'] = dict(yaml=yaml_text, argv=test_argv[0], params=params, printed=printed,
+                                     paths=list(RU.get_image_and_data_path(params)))
+        finally:
+            os.chdir(cwd)
+    # logs -> CSV
+    tuned = names[0]
+    logs = {
+        'sdd_train': _log_of_run(1, 'Seed_1__p_q__mosa_1__Pos_0_1_2_3_4__TrN_30__lr_0.003__smooth__early_30__original', 8190,
+                                 41, 12.3456, 20.5)
+        + _log_of_run(2, 'Seed_2__p_q__all__TrN_20__lr_0.00005__AUG__bias__original', None, None, 11.0, 19.25)
+        + _log_of_run(3, 'Seed_3__p_q__encoder__TrN_10__fusion_2', 120, 7, 10.5, 18.0),
+        'sdd_eval': _log_of_run(1, None, None, None, 12.5, 20.5, tuned=tuned)
+        + _log_of_run(2, None, None, None, 13.5, 21.5, tuned='ckpts/x/Seed_2__p_q__all__TrN_40__original.pt'),
+    }
+    imp = ("{'save_every_n': 121, 'seed': 1, 'pretrained_ckpt': 'ckpts/pre.pt', 'tuned_ckpts': ['ckpts/t.pt'], 'x': 1}\n"
+           + ''.join(f'Replacing encoder.stages.{i}.0\n\nAverage performance (by 1): \nTest ADE: {10 + i}.5 \n'
+                     f'Test FDE: {20 + i}.25\n' for i in range(3)))
+    logs['sdd_imp'] = imp + imp.replace("'seed': 1", "'seed': 2")
+    out['logs'] = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, text in logs.items():
+            with open(os.path.join(tmp, name + '.out'), 'w') as f:
+                f.write(text)
+            captured(RX.extract_file, os.path.join(tmp, name + '.out'), os.path.join(tmp, 'csv'))
+            with open(os.path.join(tmp, 'csv', name + '.csv')) as f:
+                out['logs'][name] = dict(text=text, csv=f.read())
+    path = os.path.join(OUT, 'scripts_host.json')
+    with open(path, 'w') as f:
+        json.dump(out, f, indent=0, sort_keys=True)
+    print(f'scripts_host: {os.path.getsize(path) / 1024:.1f} KiB')
+
+
 def main(only=None):
     torch.set_num_threads(1)     # reference's global-sum quirk depends on thread count (SURVEY 8)
     ns = ref_harness.load()
@@ -463,6 +627,7 @@ def main(only=None):
     gen_train(ns)
     gen_forward_batch(ns)
     gen_augment(ns)
+    gen_scripts_host(ns)
     gen_preprocess()
 
 

@@ -79,6 +79,12 @@ def load():
             ns.train_epoch = None
             ns.trainer = None
             ns.trainer_error = repr(e)
+        for name in ('data_utils', 'util', 'parser', 'extract_log'):      # the scripts' host side
+            try:
+                setattr(ns, name, importlib.import_module('utils.' + name))
+            except Exception as e:  # pragma: no cover
+                setattr(ns, name, None)
+                setattr(ns, name + '_error', repr(e))
     finally:
         sys.path.remove(REF_PATH)
     _loaded['ns'] = ns

@@ -60,3 +60,15 @@ def build_adapter_model(g, device='cpu'):
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert not unexpected and all(not k.startswith('encoder.') for k in missing)
     return m.to(device).eval()
+
+
+class TinySeg(torch.nn.Module):
+    """Stand-in for the pickled smp U-Net the reference loads from ``<data_dir>/<dataset>/<dataset>_segmentation.pth``
+    (ynet.py:495-507): a whole pickled module, 3 -> n_classes channels at the input resolution."""
+
+    def __init__(self, n_classes=6):
+        super().__init__()
+        self.head = torch.nn.Conv2d(3, n_classes, 3, padding=1)
+
+    def forward(self, x):
+        return self.head(x)

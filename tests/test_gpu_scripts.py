@@ -1,0 +1,150 @@
+"""The reference's command lines end to end on the B200 path (SURVEY 8f rank 4 + 8b callers): a scratch working directory
+laid out like the reference's (``config/*.yaml``, ``data/sdd/raw/annotations/<scene>/video<k>/reference.jpg``, the pickled
+segmentation module, ``train.pkl / val.pkl / test.pkl``), then
+
+    train  (from scratch, 1 epoch)                          scripts/*/pretrain.sh
+    train  --fine_tune --train_net mosa_1 --init_check       scripts/*/tune_mosa.sh
+    test   --pretrained_ckpt ... --tuned_ckpt ...            scripts/*/generalize.sh, evaluate
+    extract_log on both logs
+
+and the numbers have to agree with each other: a freshly adapted model forecasts exactly what the pretrained one does
+(``--init_check``), the tuned checkpoint restored by ``test`` reproduces the ADE / FDE ``train`` printed for the same seed,
+and the scraper reads those numbers back.
+"""
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+import yaml
+
+pytestmark = pytest.mark.gpu
+
+CONFIG = dict(
+    save_every_n=121, resize_factor=0.25, viz_epoch=10, encoder_channels=[8, 8, 16, 16, 16], decoder_channels=[16, 16, 16, 8, 8],
+    waypoints=[5], temperature=1.0, n_semantic_classes=6, loss_scale=1000, kernlen=31, nsig=4, use_features_only=False,
+    e_unfreeze=10000, use_TTST=True, rel_threshold=0.01, use_CWS=False, CWS_params='None', obs_len=5, pred_len=6, n_goal=20,
+    n_traj=1, use_raw_data=True, data_dir='data/', dataset_name='sdd')
+DATASET_PATH = 'filter/agent_type/Biker'
+H0, W0 = 200, 264                                     # x 0.25 -> 50 x 66 -> padded to 64 x 96
+
+
+def _agents(rng, first_id, n, scenes):
+    rows = []
+    T = CONFIG['obs_len'] + CONFIG['pred_len']
+    for k in range(n):
+        start = rng.uniform([40, 40], [W0 - 120, H0 - 90])
+        step = rng.uniform([2, -3], [8, 6])
+        wobble = rng.normal(0, 0.6, (T, 2))
+        for t in range(T):
+            x, y = start + step * t + wobble[t]
+            rows.append(dict(frame=12 * t, trackId=first_id + k, x=float(x), y=float(y), sceneId=scenes[k % len(scenes)],
+                             metaId=first_id + k))
+    return pd.DataFrame(rows)
+
+
+@pytest.fixture()
+def workspace(tmp_path, monkeypatch, cuda_device):
+    import cv2
+    from helpers import TinySeg
+    rng = np.random.RandomState(0)
+    os.makedirs(tmp_path / 'config')
+    with open(tmp_path / 'config' / 'tiny.yaml', 'w') as f:
+        yaml.safe_dump(CONFIG, f, sort_keys=False)
+    scenes = ['sA_0', 'sB_1']
+    for scene in scenes:
+        name, idx = scene.split('_')
+        d = tmp_path / 'data' / 'sdd' / 'raw' / 'annotations' / name / f'video{idx}'
+        os.makedirs(d)
+        assert cv2.imwrite(str(d / 'reference.jpg'), rng.randint(0, 256, (H0, W0, 3)).astype(np.uint8))
+    torch.manual_seed(0)
+    torch.save(TinySeg(6), tmp_path / 'data' / 'sdd' / 'sdd_segmentation.pth')
+    d = tmp_path / 'data' / 'sdd' / DATASET_PATH
+    os.makedirs(d)
+    for name, first, n in (('train', 0, 12), ('val', 100, 4), ('test', 200, 6)):
+        _agents(rng, first, n, scenes).to_pickle(d / f'{name}.pkl')
+    monkeypatch.chdir(tmp_path)
+    return tmp_path
+
+
+COMMON = f'--config_filename tiny.yaml --dataset_path {DATASET_PATH} --network original --load_data predefined --batch_size 4'
+AVERAGE = r'Average performance \(by (\d+)\): \nTest ADE: ([\d\.]+) \nTest FDE: ([\d\.]+)'
+
+
+def test_pretrain_finetune_test_and_scrape(workspace, capsys):
+    from motion_style_transfer_b200 import train, test
+    from motion_style_transfer_b200.utils import extract_log
+    from motion_style_transfer_b200.utils.parser import get_parser
+
+    # ---- pretraining from scratch (train_net = 'train': everything but the segmentation module) -------------------
+    train.main(get_parser(True).parse_args(f'{COMMON} --seed 1 --n_epoch 1 --n_round 1 --ckpt_path ckpts/pre'.split()))
+    out = capsys.readouterr().out
+    assert 'Training from scratch' in out and 'Loading predefined train/val/test sets' in out
+    assert 'df_train: (132, 6); #=12' in out and 'df_val: (44, 6); #=4' in out and 'df_test: (66, 6); #=6' in out
+    experiment = re.search('Experiment (.*?) has started', out).group(1)
+    assert experiment == 'Seed_1__filter_agent_type_Biker__train__original'
+    pre = f'ckpts/pre/{experiment}.pt'
+    saved = torch.load(pre)
+    assert not any('segmentation' in k for k in saved) and 'encoder.stages.0.0.weight' in saved
+    assert os.path.exists(f'ckpts/pre/{experiment}_weights.pt')                 # best validation epoch (trainer.py:262-266)
+    n_all = int(re.search(r'The number of trainable parameters: (\d+)', out).group(1))
+    assert n_all == sum(v.numel() for k, v in saved.items())
+
+    # ---- MoSA fine-tuning on 2 batches of 4 agents, with the initialisation check --------------------------------
+    tune = (f'{COMMON} --fine_tune --seed 2 --n_epoch 3 --n_early_stop 30 --n_round 2 --pretrained_ckpt {pre} --train_net mosa_1 '
+            '--position 0 1 --ckpt_path ckpts/tuned --n_train_batch 2 --lr 0.003 --steps 2 --init_check')
+    train.main(get_parser(True).parse_args(tune.split()))
+    train_out = capsys.readouterr().out
+    assert 'Passed initialization check' in train_out and f'Loaded checkpoint {pre}' in train_out
+    assert 'df_train: (88, 6); #=8' in train_out
+    tuned_name = 'Seed_2__filter_agent_type_Biker__mosa_1__Pos_0_1__TrN_8__lr_0.003__original'   # (early stop 30 >= 3 epochs)
+    assert f'Experiment {tuned_name} has started' in train_out
+    tuned = f'ckpts/tuned/{tuned_name}.pt'
+    sd = torch.load(tuned)
+    assert sd and all('lora_' in k for k in sd)                                 # only the adapters are written
+    n_lora = int(re.search(r'The number of trainable parameters: (\d+)', train_out).group(1))
+    assert n_lora == sum(v.numel() for v in sd.values())
+    assert any(float(v.abs().max()) > 0 for k, v in sd.items() if 'lora_B' in k)   # training moved B away from zero
+    averages = re.findall(AVERAGE, train_out)
+    assert len(averages) == 3 and averages[0] == averages[1]                    # pretrained == freshly adapted, same seed
+    assert all(a[0] == '2' for a in averages)
+    assert len(re.findall(r'lr=0\.003\n', train_out)) == 2 and 'lr=0.0003' in train_out      # MultiStepLR(steps=[2], 0.1)
+
+    # ---- test.py: pretrained + separately saved tuned parameters --------------------------------------------------
+    test.main(get_parser(False).parse_args(
+        f'{COMMON} --seed 2 --n_round 2 --pretrained_ckpt {pre} --tuned_ckpt {tuned}'.split()))
+    eval_out = capsys.readouterr().out
+    assert f"['{pre}', '{tuned}'] ['OODG', 'mosa_1[0_1](8)']" in eval_out
+    evals = re.findall(AVERAGE, eval_out)
+    assert len(evals) == 1 and evals[0] == averages[2]          # same weights, same seed -> the numbers train printed
+    # ... and a whole checkpoint through --ckpts: the pretrained model's numbers (first average of the init check)
+    test.main(get_parser(False).parse_args(f'{COMMON} --seed 2 --n_round 2 --ckpts {pre} --ckpts_name pre'.split()))
+    assert re.findall(AVERAGE, capsys.readouterr().out) == [averages[0]]
+
+    # ---- scraper --------------------------------------------------------------------------------------------------
+    os.makedirs('logs')
+    for name, text in (('tiny_train', train_out), ('tiny_eval', eval_out)):
+        with open(f'logs/{name}.out', 'w') as f:
+            f.write(text)
+        extract_log.extract_file(f'logs/{name}.out', 'csv/log')
+    row = pd.read_csv('csv/log/tiny_train.csv', dtype={'position': str}).iloc[0]
+    assert (row.seed, row.train_net, row.n_train, str(row.position), row.n_param, row.n_epoch) == (2, 'mosa_1', 8, '0_1', n_lora, 99)
+    assert (row.ade, row.fde) == (float(averages[0][1]), float(averages[0][2]))   # the scraper takes the first average
+    assert row.experiment == tuned_name and row.pretrained_ckpt == f'{experiment}.pt' and not row.is_augment
+    row = pd.read_csv('csv/log/tiny_eval.csv', dtype={'position': str}).iloc[0]
+    assert (row.seed, row.train_net, row.n_train, str(row.position), float(row.lr)) == (2, 'mosa_1', 8, '0_1', 0.003)
+    assert (row.ade, row.fde) == (float(evals[0][1]), float(evals[0][2]))
+    assert row.tuned_ckpt == f'{tuned_name}.pt'
+
+
+def test_augmented_pretraining_epoch(workspace, capsys):
+    """``--augment`` (scripts/*/pretrain.sh): 8 views per scene through the oriented preprocessing launch."""
+    from motion_style_transfer_b200 import train
+    from motion_style_transfer_b200.utils.parser import get_parser
+    train.main(get_parser(True).parse_args(
+        f'{COMMON} --seed 1 --n_epoch 1 --n_round 1 --ckpt_path ckpts/aug --augment --backend bf16x3'.split()))
+    out = capsys.readouterr().out
+    assert 'Augmented data and images' in out and 'Best epoch at 0' in out
+    assert len(re.findall(AVERAGE, out)) == 1
