@@ -315,7 +315,8 @@ def _cached_graph(model, weights_ver, n_full, input_template, scene_image, traj_
     seen = model.__dict__.setdefault('_forecast_graph_seen', {})
     key = (weights_ver, getattr(model, '_backend', None), tuple(scene_image.shape), traj_shape, tuple(waypoints), n_goal,
            n_traj, obs_len, resize_factor, temperature, use_TTST, use_CWS, rel_thresh,
-           None if CWS_params is None else tuple(sorted(CWS_params.items())), embed_motion,
+           # (the reference's YAMLs ship ``CWS_params: None``, which YAML reads as the string 'None'; only read with use_CWS)
+           tuple(sorted(CWS_params.items())) if use_CWS and isinstance(CWS_params, dict) else None, embed_motion,
            input_template.data_ptr(), tuple(input_template.shape))
     hit = cache.pop(key, None)
     if hit is not None:
