@@ -91,6 +91,13 @@ def test_prepare_dataeset_and_file_splits(G, frames, tmp_path):
                           seed=c['seed'])
     assert printed == c['printed']
     assert [xs(pd.read_pickle(tmp_path / 'Biker' / f'{n}.pkl')) for n in ('train', 'val', 'test')] == c['parts']
+    # the command line of scripts/inD/preprocessing.sh writes the same three files
+    import shutil
+    from motion_style_transfer_b200.utils import split_dataset
+    shutil.rmtree(tmp_path / 'Biker')
+    captured(split_dataset.main, ['--data_dir', str(tmp_path), '--data_filename', 'Biker.pkl', '--val_split', str(c['val_split']),
+                                  '--test_split', str(c['test_split']), '--seed', str(c['seed'])])
+    assert [xs(pd.read_pickle(tmp_path / 'Biker' / f'{n}.pkl')) for n in ('train', 'val', 'test')] == c['parts']
     c = G['given_scenes']
     sel, printed = captured(D.dataset_split_given_scenes, str(tmp_path), ['Biker.pkl', 'Car.pkl'], c['scenes'])
     assert xs(sel) == c['xs'] and printed == c['printed']

@@ -45,26 +45,48 @@ def _agents(rng, first_id, n, scenes):
     return pd.DataFrame(rows)
 
 
-@pytest.fixture()
-def workspace(tmp_path, monkeypatch, cuda_device):
+def _make_workspace(root, config, scenes, image_dir, image_name, seg_name, pickles):
+    """config/tiny.yaml, one image per scene, the pickled segmentation module and the trajectory pickles."""
     import cv2
     from helpers import TinySeg
     rng = np.random.RandomState(0)
-    os.makedirs(tmp_path / 'config')
-    with open(tmp_path / 'config' / 'tiny.yaml', 'w') as f:
-        yaml.safe_dump(CONFIG, f, sort_keys=False)
-    scenes = ['sA_0', 'sB_1']
+    os.makedirs(root / 'config')
+    with open(root / 'config' / 'tiny.yaml', 'w') as f:
+        yaml.safe_dump(config, f, sort_keys=False)
+    data = root / 'data' / config['dataset_name']
     for scene in scenes:
-        name, idx = scene.split('_')
-        d = tmp_path / 'data' / 'sdd' / 'raw' / 'annotations' / name / f'video{idx}'
+        d = data / image_dir(scene)
         os.makedirs(d)
-        assert cv2.imwrite(str(d / 'reference.jpg'), rng.randint(0, 256, (H0, W0, 3)).astype(np.uint8))
+        assert cv2.imwrite(str(d / image_name), rng.randint(0, 256, (H0, W0, 3)).astype(np.uint8))
     torch.manual_seed(0)
-    torch.save(TinySeg(6), tmp_path / 'data' / 'sdd' / 'sdd_segmentation.pth')
-    d = tmp_path / 'data' / 'sdd' / DATASET_PATH
-    os.makedirs(d)
-    for name, first, n in (('train', 0, 12), ('val', 100, 4), ('test', 200, 6)):
-        _agents(rng, first, n, scenes).to_pickle(d / f'{name}.pkl')
+    torch.save(TinySeg(6), data / seg_name)
+    os.makedirs(data / DATASET_PATH)
+    for name, first, n in pickles:
+        _agents(rng, first, n, scenes).to_pickle(data / DATASET_PATH / f'{name}.pkl')
+
+
+def _sdd_raw_dir(scene):
+    name, idx = scene.split('_')
+    return os.path.join('raw', 'annotations', name, f'video{idx}')
+
+
+@pytest.fixture()
+def workspace(tmp_path, monkeypatch, cuda_device):
+    _make_workspace(tmp_path, CONFIG, ['sA_0', 'sB_1'], _sdd_raw_dir, 'reference.jpg', 'sdd_segmentation.pth',
+                    (('train', 0, 12), ('val', 100, 4), ('test', 200, 6)))
+    monkeypatch.chdir(tmp_path)
+    return tmp_path
+
+
+# inD layout (config/inD_longterm_eval.yaml: images/<scene>/reference.png, two waypoints, CWS parameters as a dictionary)
+CONFIG_IND = dict(CONFIG, waypoints=[2, 5], temperature=1.8, use_TTST=True, rel_threshold=0.002, use_CWS=True,
+                  CWS_params=dict(sigma_factor=6, ratio=2, rot=True), use_raw_data=False, dataset_name='inD-dataset-v1.0')
+
+
+@pytest.fixture()
+def workspace_ind(tmp_path, monkeypatch, cuda_device):
+    _make_workspace(tmp_path, CONFIG_IND, ['scene1'], lambda scene: os.path.join('images', scene), 'reference.png',
+                    'inD_segmentation.pth', (('car', 0, 16),))
     monkeypatch.chdir(tmp_path)
     return tmp_path
 
@@ -148,3 +170,51 @@ def test_augmented_pretraining_epoch(workspace, capsys):
     out = capsys.readouterr().out
     assert 'Augmented data and images' in out and 'Best epoch at 0' in out
     assert len(re.findall(AVERAGE, out)) == 1
+
+
+def test_ind_ynetmod_sequential_split_smoothed_validation_cws(workspace_ind, capsys):
+    """scripts/inD/scene1_car_to_truck/ynetmod/{pretrain,tune_mosa_A,generalize}.sh in small: Y-Net-Mod (``--network fusion
+    --n_fusion 2``), MoSA on the motion branch, one pickle split sequentially with a shared validation / test set,
+    validation smoothed over a window, evaluation with TTST + CWS."""
+    from motion_style_transfer_b200 import train, test
+    from motion_style_transfer_b200.utils import extract_log
+    from motion_style_transfer_b200.utils.parser import get_parser
+    common = (f'--config_filename tiny.yaml --dataset_path {DATASET_PATH} --network fusion --n_fusion 2 --batch_size 4 '
+              '--load_data sequential --val_files car.pkl --val_split 2 --test_splits 6 --share_val_test')
+    train.main(get_parser(True).parse_args(
+        f'{common} --train_files car.pkl --seed 1 --n_epoch 1 --n_round 1 --ckpt_path ckpts'.split()))
+    out = capsys.readouterr().out
+    assert "Split ['car.pkl'] given val_split=2.0, test_split=[6]" in out and 'Share validation and test set' in out
+    assert 'df_train: (110, 6); #=10' in out and 'df_val: (22, 6); #=2' in out and 'df_test: (66, 6); #=6' in out
+    pre_name = 'Seed_1__filter_agent_type_Biker_car__train__fusion_2'
+    assert f'Experiment {pre_name} has started' in out
+    pre = 'ckpts/inD__ynetmod__car.pt'
+    os.rename(f'ckpts/{pre_name}.pt', pre)
+
+    tune = (f'{common} --train_files car.pkl --fine_tune --seed 1 --n_epoch 5 --n_early_stop 3000 --n_round 2 --pretrained_ckpt {pre} '
+            '--train_net mosa_1 --position motion --ckpt_path ckpts/tuned --n_train_batch 2 --lr 0.001 --smooth_val --window_size 3 '
+            '--init_check')
+    train.main(get_parser(True).parse_args(tune.split()))
+    train_out = capsys.readouterr().out
+    tuned_name = 'Seed_1__filter_agent_type_Biker_car__mosa_1__Pos_motion__TrN_8__lr_0.001__smooth__fusion_2'
+    assert f'Experiment {tuned_name} has started' in train_out and 'Passed initialization check' in train_out
+    assert 'df_train: (88, 6); #=8' in train_out
+    assert re.search(r'Best epoch at [23]\n', train_out)       # the first smoothed value exists at epoch 3 (centre: 2)
+    sd = torch.load(f'ckpts/tuned/{tuned_name}.pt')
+    assert sd and all('lora_' in k and k.startswith('encoder.motion_stages.') for k in sd)
+    averages = re.findall(AVERAGE, train_out)
+    assert len(averages) == 3 and averages[0] == averages[1]
+
+    test.main(get_parser(False).parse_args(
+        f'{common} --seed 1 --n_round 2 --pretrained_ckpt {pre} --tuned_ckpt ckpts/tuned/{tuned_name}.pt'.split()))
+    eval_out = capsys.readouterr().out
+    assert "['OODG', 'mosa_1[motion](8)']" in eval_out and 'TTST setting: True' in eval_out
+    assert re.findall(AVERAGE, eval_out) == [averages[2]]
+
+    os.makedirs('logs')
+    with open('logs/ind_eval.out', 'w') as f:
+        f.write(eval_out)
+    extract_log.extract_file('logs/ind_eval.out', 'csv')
+    row = pd.read_csv('csv/ind_eval.csv', float_precision='round_trip').iloc[0]
+    assert (row.train_net, row.n_train, row.position, float(row.lr)) == ('mosa_1', 8, 'motion', 0.001)
+    assert (row.ade, row.fde) == (float(averages[2][1]), float(averages[2][2]))
