@@ -252,3 +252,22 @@ def test_set_random_seeds_rewinds_every_generator():
     b = (float(np.random.rand()), random.random(), float(torch.rand(1)), torch.initial_seed(), E._eval_calls)
     assert a == b and a[3] == 3 and a[4] == 0
     assert torch.backends.cudnn.deterministic and not torch.backends.cudnn.benchmark
+
+
+def test_write_files_and_round_means(tmp_path):
+    """evaluator/write_files.py and the per-agent mean over rounds of evaluator/evaluate_multickpts.py:50-57 (outputs of the
+    live reference for these inputs)."""
+    from motion_style_transfer_b200.evaluator import write_files as W
+    from motion_style_transfer_b200.evaluator.evaluate_multickpts import mean_over_rounds
+    W.write_csv(str(tmp_path / 'r'), 'a.csv', [1.23456, 2.5, 0.333333], [1, 2, 3])
+    assert (tmp_path / 'r' / 'a.csv').read_text() == '0.3333\n1.356\n1.2346\n2.5\n0.3333\n'
+    W.write_csv(str(tmp_path / 'r'), 'b.csv', [1.23456, 2.5, 0.333333], [1, 2, 3], 3.14159265)
+    assert (tmp_path / 'r' / 'b.csv').read_text() == '3.1416\n0.3333\n1.356\n1.2346\n2.5\n0.3333\n'
+    assert W.round_val(None) == 0.0 and W.round_val(2.0) == '2.0' and W.convert_to_str([1, 'a']) == [['1'], ['a']]
+    assert W.get_out_dir('o', 'a/b', 1, 'mosa', ['x.pkl', 'y.pkl'], ['t.pkl']) == 'o/a/b/t/x___y/mosa/1'
+    assert W.get_out_dir('o', 'a/b', 1, 'mosa', ['x.pkl']) == 'o/a/b/None/x/mosa/1'
+    rounds = [pd.DataFrame({'metaId': [3, 4], 'sceneId': ['s', 's'], 'ade': [1.0, 2.0], 'fde': [4.0, 8.0]}),
+              pd.DataFrame({'metaId': [3, 4], 'sceneId': ['s', 's'], 'ade': [3.0, 2.0], 'fde': [0.0, 4.0]})]
+    t = mean_over_rounds(rounds, 'A')
+    assert list(t.columns) == ['metaId', 'sceneId', 'ade_A', 'fde_A']
+    assert list(t.ade_A) == [2.0, 2.0] and list(t.fde_A) == [2.0, 6.0] and list(rounds[0].ade) == [1.0, 2.0]

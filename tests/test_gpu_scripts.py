@@ -160,6 +160,29 @@ def test_pretrain_finetune_test_and_scrape(workspace, capsys):
     assert (row.ade, row.fde) == (float(evals[0][1]), float(evals[0][2]))
     assert row.tuned_ckpt == f'{tuned_name}.pt'
 
+    # ---- evaluate_multickpts: per-agent table of both models under one seed, then the agents on which they differ most ----
+    from motion_style_transfer_b200.evaluator import evaluate_multickpts as multi
+    table = multi.main(multi.get_multickpts_parser().parse_args(
+        f'{COMMON} --seed 2 --n_round 2 --pretrained_ckpt {pre} --tuned_ckpts {tuned}'.split()))
+    out = capsys.readouterr().out
+    csv_path = 'csv/comparison/2__filter_agent_type_Biker/OODG_mosa_1[0_1](8)__N6_R2.csv'
+    assert f'Saved {csv_path}' in out and '====== Testing for mosa_1[0_1](8) ======' in out
+    saved = pd.read_csv(csv_path, float_precision='round_trip')
+    assert list(saved.columns) == ['metaId', 'sceneId', 'ade_OODG', 'fde_OODG', 'ade_mosa_1[0_1](8)', 'fde_mosa_1[0_1](8)']
+    assert sorted(saved.metaId) == list(range(200, 206)) and len(table) == 6
+    # paired samples: the column means are the numbers test.py printed for the two models under this seed
+    np.testing.assert_allclose(saved['ade_OODG'].mean(), float(averages[0][1]), rtol=1e-5)
+    np.testing.assert_allclose(saved['fde_mosa_1[0_1](8)'].mean(), float(evals[0][2]), rtol=1e-5)
+    multi.main(multi.get_multickpts_parser().parse_args(
+        f'{COMMON} --seed 2 --n_round 1 --ckpts {pre} --ckpts_name pre --result_path {csv_path} '
+        '--result_name ade_OODG__ade_mosa_1[0_1](8)__abs_diff --result_limited 2'.split()))
+    out = capsys.readouterr().out
+    worst = saved.assign(d=(saved['ade_OODG'] - saved['ade_mosa_1[0_1](8)']).abs()).sort_values('d', ascending=False).metaId[:2]
+    assert 'meta_ids_focus: #= 2' in out and 'df_test_limited: (22, 6); #=2' in out
+    assert sorted(pd.read_csv('csv/comparison/2__filter_agent_type_Biker/pre__N2_R1.csv').metaId) == sorted(worst)
+    with pytest.raises(NotImplementedError):
+        multi.main(multi.get_multickpts_parser().parse_args(f'{COMMON} --ckpts {pre} --ckpts_name pre --viz'.split()))
+
 
 def test_augmented_pretraining_epoch(workspace, capsys):
     """``--augment`` (scripts/*/pretrain.sh): 8 views per scene through the oriented preprocessing launch."""
