@@ -76,6 +76,11 @@ __device__ __forceinline__ unsigned long long km_pack(float x, float y) {
 // first version spent as many instructions on K select-adds per point as on the distances).  Bins are reduced per
 // CTA, exchanged through distributed shared memory (double-buffered by iteration parity: one cluster barrier per
 // iteration) and every CTA of the cluster recomputes the identical centre update.
+// Points per thread in flight: the argmin over the centres is a dependent compare-select chain per point; four independent
+// chains hide its latency at 16 warps per SM (14.4 -> 11.5 us per Lloyd iteration at 10 000 points, K = 19; the packed
+// FADD2 / FMUL2 form of the distance was tried on top and changed nothing: the loop is not bound by FP32 issue).
+constexpr int kKmUnroll = 4;
+
 template <int KMAX>
 __global__ void __launch_bounds__(kKmThreads)
 kmeans_kernel(const float* __restrict__ X, int N, int K, const int* __restrict__ init_idx,
@@ -146,29 +151,46 @@ kmeans_kernel(const float* __restrict__ X, int N, int K, const int* __restrict__
       sh.cnt[tid] = 0;
     }
     __syncthreads();
-    for (int i = tid; i < nloc; i += kKmThreads) {
-      const float2 pt = Xs[i];
-      float best = FLT_MAX;
-      int bk = 0;
+    // kKmUnroll points per thread at a time: their argmin chains are independent
+    for (int i = tid; i < nloc; i += kKmUnroll * kKmThreads) {
+      float2 pt[kKmUnroll];
+      float best[kKmUnroll];
+      int bk[kKmUnroll];
+#pragma unroll
+      for (int u = 0; u < kKmUnroll; ++u) {
+        const int iu = i + u * kKmThreads;
+        pt[u] = Xs[iu < nloc ? iu : i];
+        best[u] = FLT_MAX;
+        bk[u] = 0;
+      }
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
         if (k < K) {
-          const float dx = __fsub_rn(pt.x, cx[k]);
-          const float dy = __fsub_rn(pt.y, cy[k]);
-          const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-          if (d < best) {  // strict: first minimum wins (torch.argmin)
-            best = d;
-            bk = k;
+#pragma unroll
+          for (int u = 0; u < kKmUnroll; ++u) {
+            const float dx = __fsub_rn(pt[u].x, cx[k]);
+            const float dy = __fsub_rn(pt[u].y, cy[k]);
+            const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            if (d < best[u]) {  // strict: first minimum wins (torch.argmin)
+              best[u] = d;
+              bk[u] = k;
+            }
           }
         }
       }
-      if (assign != nullptr) assign[(size_t)b * N + i0 + i] = bk;
-      if (exact) {
-        acc[bk * kKmThreads + tid] += km_pack(pt.x, pt.y);
-      } else {
-        atomicAdd(&sh.sumx[bk], pt.x);
-        atomicAdd(&sh.sumy[bk], pt.y);
-        atomicAdd(&sh.cnt[bk], 1);
+#pragma unroll
+      for (int u = 0; u < kKmUnroll; ++u) {
+        const int iu = i + u * kKmThreads;
+        if (iu < nloc) {
+          if (assign != nullptr) assign[(size_t)b * N + i0 + iu] = bk[u];
+          if (exact) {
+            acc[bk[u] * kKmThreads + tid] += km_pack(pt[u].x, pt[u].y);
+          } else {
+            atomicAdd(&sh.sumx[bk[u]], pt[u].x);
+            atomicAdd(&sh.sumy[bk[u]], pt[u].y);
+            atomicAdd(&sh.cnt[bk[u]], 1);
+          }
+        }
       }
     }
     __syncthreads();
