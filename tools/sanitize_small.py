@@ -82,9 +82,16 @@ ys = ops.tc_conv3x3_split([xs], ops.split_pack_weights(ws, [xs.layout]), torch.z
 ys2 = ops.split_unpack(ops.split_upsample(ops.split_maxpool(ys)))
 ymask = ops.split_pack_masked(torch.randn(3, 30, 20, 36, device=dev), ops.split_unpack(ys))
 pre_o = U.preprocess_scene_image(img, 0.33, 32, orient=5)
+# k-means with four points per thread in flight: N not a multiple of 4 x 512, K at and below the template bounds, 2-CTA clusters
+for n_pts, k in ((10000, 19), (777, 5), (4100, 32)):
+    pts = torch.randint(0, 400, (3, n_pts, 2), device=dev).float()
+    init_idx = torch.stack([torch.randperm(n_pts, device=dev)[:k] for _ in range(3)]).int()
+    cen, _, n_it, _ = ops.kmeans_batched(pts, init_idx, torch.randint(0, n_pts, (3, 64), dtype=torch.int32, device=dev), 0.001, 40,
+                                         want_assign=True)
 torch.cuda.synchronize()
 print('sanitize_small r02b: ok', float(ops.tc_unpack(y1).abs().sum()), float(ops.tc_unpack(y2).abs().sum()), float(y3.sum()),
-      float(ops.tc_unpack(y4).abs().sum()), float(ys2.abs().sum()), float(ops.split_unpack(ymask).abs().sum()), float(pre_o.sum()))
+      float(ops.tc_unpack(y4).abs().sum()), float(ys2.abs().sum()), float(ops.split_unpack(ymask).abs().sum()), float(pre_o.sum()),
+      float(cen.sum()), int(n_it.max()))
 print('sanitize_small r02: ok', float(ops.tc_unpack(yr).abs().sum()), float(ops.tc_unpack(ym).abs().sum()), float(sa.sum()),
       float(pre.sum()), float(pre4.sum()), float(msk.sum()))
 print('sanitize_small: ok', float(ops.tc_unpack(out).abs().sum()), int(idx.sum()), float(cw.sum()), float(ade.sum()))
