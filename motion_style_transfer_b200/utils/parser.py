@@ -22,7 +22,7 @@ _DATA = [
     ('--show_details', _FLAG),
     # load_data == 'sequential'
     ('--val_split', dict(default=0.1, type=float)),
-    ('--test_splits', dict(help='The number of data left for testing for each val_file', **_multi(int))),
+    ('--test_splits', dict(help='agents held out for testing, one number per file of --val_files', **_multi(int))),
     ('--val_files', _multi(str)),
     ('--share_val_test', _FLAG),
 ]
@@ -39,13 +39,13 @@ _MODEL = [
     ('--swap_semantic', _FLAG),
     ('--position', _multi(str, default=[])),
     ('--ynet_bias', _FLAG),
-    ('--train_net', dict(default='train', type=str, help='Train which part of the network')),
+    ('--train_net', dict(default='train', type=str, help='which parameters train: all | train | encoder | mosa_<r> | serial* | parallel* | bias* | scene | motion | fusion ...')),
 ]
 _GENERAL = [
     ('--seed', dict(default=1, type=int)),
     ('--batch_size', dict(default=8, type=int)),
-    ('--gpu', dict(default=None, type=int, help='gpu id to use')),
-    ('--n_round', dict(default=1, type=int, help='number of rounds in stochastics eval process')),
+    ('--gpu', dict(default=None, type=int, help='CUDA_VISIBLE_DEVICES for this run')),
+    ('--n_round', dict(default=1, type=int, help='test rounds to average (TTST / CWS draw random numbers)')),
     ('--config_filename', dict(default=None, type=str)),
     ('--backend', dict(default=None, choices=['fp32', 'bf16x3', 'bf16'],
                        help='B200 engine (INTEGRATION.md section 2); default: YNET_BACKEND or fp32')),
@@ -55,7 +55,7 @@ _TRAIN = [
     ('--n_epoch', dict(default=100, type=int)),
     ('--n_early_stop', dict(default=300, type=int)),
     ('--n_train_batch', dict(default=None, type=float,
-                             help='Limited number of batches for each training agent (fine-tuning), None means no limit')),
+                             help='low-shot fine-tuning: train on this many batches of agents only (may be fractional)')),
     ('--lr', dict(default=0.0001, type=float)),
     ('--steps', _multi(int, default=[])),
     ('--lr_decay_ratio', dict(default=0.1)),

@@ -1,21 +1,26 @@
-"""``python -m motion_style_transfer_b200.utils.split_dataset --data_dir ... --data_filename pedestrian.pkl --val_split 0.1
---test_split 0.2 --seed 1`` (utils/split_dataset.py:1-19, used by scripts/inD/preprocessing.sh): writes the predefined
-train.pkl / val.pkl / test.pkl that ``--load_data predefined`` reads."""
+"""Random train / val / test split of one trajectory pickle, as a command (utils/split_dataset.py:1-19; called fifteen times
+by the reference's scripts/*/preprocessing.sh):
+
+    python -m motion_style_transfer_b200.utils.split_dataset --data_dir <dir> --data_filename pedestrian.pkl \\
+        --val_split 0.1 --test_split 0.2 --seed 1
+
+A split > 1 is a number of agents, otherwise a fraction.  Output: ``<dir>/pedestrian/{train,val,test}.pkl`` -- what
+``--load_data predefined`` reads (data_utils.split_train_val_test_randomly).
+"""
 import argparse
 
 from .data_utils import split_train_val_test_randomly
 
+_FLAGS = (('data_dir', str, None), ('data_filename', str, None), ('val_split', float, None), ('test_split', float, None),
+          ('seed', int, 1))
+
 
 def main(argv=None):
-    parser = argparse.ArgumentParser()
-    parser.add_argument('--data_dir', default=None, type=str,
-                        help='Path to the raw data, can be a subset of the entire dataset')
-    parser.add_argument('--data_filename', default=None, type=str)
-    parser.add_argument('--val_split', default=None, type=float)
-    parser.add_argument('--test_split', default=None, type=float)
-    parser.add_argument('--seed', default=1, type=int)
-    args = parser.parse_args(argv)
-    split_train_val_test_randomly(args.data_dir, args.data_filename, args.val_split, args.test_split, args.seed)
+    cli = argparse.ArgumentParser(description=__doc__.split('\n')[0])
+    for name, kind, default in _FLAGS:
+        cli.add_argument('--' + name, type=kind, default=default)
+    opt = cli.parse_args(argv)
+    split_train_val_test_randomly(opt.data_dir, opt.data_filename, opt.val_split, opt.test_split, opt.seed)
 
 
 if __name__ == '__main__':

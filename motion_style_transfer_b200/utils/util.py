@@ -69,38 +69,43 @@ def get_image_and_data_path(params):
     return image_path, data_path
 
 
+def _name_fields(ckpt_path):
+    """The fields of a checkpoint file name (grammar in the module docstring) that the helpers below need."""
+    name = ckpt_path.split('/')[-1]
+    position = name.split('Pos_')[-1].split('__')[0] if 'Pos' in name else None
+    return dict(name=name, train_net=name.split('__')[2], position=position)
+
+
 def get_position(ckpt_path, return_list=True):
-    """util.py:79-91: the ``Pos_0_1_2`` field of a checkpoint name -> '0_1_2' or ['0', '1', '2']; None without one."""
+    """util.py:79-91: the ``Pos_0_1_2`` field of a checkpoint name -> '0_1_2' or ['0', '1', '2']; None without one (or
+    without a path)."""
     if ckpt_path is None or 'Pos' not in ckpt_path:
         return None
     pos = ckpt_path.split('Pos_')[-1].split('__')[0]
     return pos.split('_') if return_list else pos
 
 
-def _n_train(ckpt_path):
-    return int(ckpt_path.split('TrN_')[-1].split('_')[0])
-
-
 def get_ckpt_name(ckpt_path):
-    """util.py:94-104: 'mosa_1[0_1_2](20)' / 'all(20)' -- the column name of a tuned checkpoint in result tables."""
-    name = ckpt_path.split('/')[-1]
-    train_net = name.split('__')[2]
-    where = f'[{get_position(name, return_list=False)}]' if 'Pos' in name else ''
-    return f'{train_net}{where}({_n_train(name)})'
+    """util.py:94-104: 'mosa_1[0_1_2](20)' / 'all(20)' -- the column name of a tuned checkpoint in result tables: what was
+    trained, where, on how many agents."""
+    f = _name_fields(ckpt_path)
+    n_train = int(f['name'].split('TrN_')[-1].split('_')[0])
+    where = '' if f['position'] is None else f"[{f['position']}]"
+    return f"{f['train_net']}{where}({n_train})"
 
 
 def update_params(ckpt_path, params):
-    """util.py:107-123: the constructor arguments a tuned checkpoint needs, read back from its file name."""
-    name = ckpt_path.split('/')[-1]
-    updated = params.copy()
-    updated['train_net'] = name.split('__')[2].split('.')[0]
+    """util.py:107-123: the constructor arguments a separately saved set of tuned parameters needs, read back from its file
+    name: ``train_net`` and ``position`` decide where the adapter tensors live in the module tree."""
+    f = _name_fields(ckpt_path)
+    updated = dict(params, train_net=f['train_net'].split('.')[0])
     base_arch = params['pretrained_ckpt'].split('_')[-1].split('.')[0]
     if base_arch == 'embed':
         updated['add_embedding'] = True
     elif 'fusion' in base_arch:       # (unreachable with the name grammar above: the last '_' field is the number)
         updated['n_fusion'] = int(base_arch.split('_')[-1])
-    if 'Pos' in name:
-        updated['position'] = get_position(name)
+    if f['position'] is not None:
+        updated['position'] = f['position'].split('_')
     return updated
 
 
