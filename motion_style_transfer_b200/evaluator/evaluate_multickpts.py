@@ -12,6 +12,7 @@ overlays, evaluator/visualization.py) is outside the path and refused.
 """
 import pathlib
 
+from .. import parallel
 from ..utils.data_utils import get_meta_ids_focus, prepare_dataeset, set_random_seeds
 from ..utils.parser import get_parser
 from ..utils.util import get_ckpts_and_names, get_image_and_data_path, get_params, restore_model
@@ -29,6 +30,7 @@ def mean_over_rounds(list_metrics, ckpt_name):
 def main(args):
     if args.viz:
         raise NotImplementedError('--viz draws matplotlib overlays (evaluator/visualization.py): not part of the B200 path')
+    parallel.init_from_env()           # under torchrun: one process per GPU, agents sharded (parallel.py)
     set_random_seeds(args.seed)
     params = get_params(args)
     image_path, data_path = get_image_and_data_path(params)

@@ -22,6 +22,27 @@ def world():
     return 0, 1
 
 
+def init_from_env(quiet=True):
+    """Join the process group ``torchrun`` describes (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* in the environment): NCCL with
+    one GPU per process, gloo without CUDA.  A no-op for a plain ``python`` launch or when a group exists already.  With
+    ``quiet`` the ranks other than 0 stop printing: every rank computes the same metrics, and the log scraper
+    (utils/extract_log.py) expects one run per parameter dictionary in a log.  Returns (rank, world_size)."""
+    import os
+    import sys
+    n = int(os.environ.get('WORLD_SIZE', '1'))
+    if n > 1 and dist.is_available() and not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if torch.cuda.is_available():
+            local = int(os.environ.get('LOCAL_RANK', os.environ.get('RANK', '0')))
+            torch.cuda.set_device(local)
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        else:
+            dist.init_process_group('gloo')
+        if quiet and dist.get_rank() != 0:
+            sys.stdout = open(os.devnull, 'w')
+    return world()
+
+
 def shard_bounds(n, rank=None, world_size=None):
     """Contiguous [lo, hi) of ``n`` agents owned by ``rank``: the first ``n % world`` ranks get one extra agent.
 

@@ -3,6 +3,7 @@ checkpoint (``--ckpts``) or of a pretrained checkpoint plus separately saved tun
 ``--tuned_ckpt``) on the held-out agents."""
 import time
 
+from . import parallel
 from .utils.data_utils import prepare_dataeset, set_random_seeds
 from .utils.parser import get_parser
 from .utils.util import get_ckpts_and_names, get_image_and_data_path, get_params, restore_model
@@ -10,6 +11,7 @@ from .utils.util import get_ckpts_and_names, get_image_and_data_path, get_params
 
 def main(args):
     tic = time.time()
+    parallel.init_from_env()           # under torchrun: one process per GPU, agents sharded (parallel.py)
     set_random_seeds(args.seed)
     params = get_params(args)
     image_path, data_path = get_image_and_data_path(params)

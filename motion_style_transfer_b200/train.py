@@ -9,6 +9,7 @@ from a directory that holds ``config/`` and ``data/``.  ``utils/extract_log.py``
 import os
 import time
 
+from . import parallel
 from .utils import data_utils, util
 from .utils.parser import get_parser
 
@@ -38,6 +39,7 @@ def _initialization_check(args, params, adapted, df_test, image_dir):
 
 def main(args):
     started = time.time()
+    parallel.init_from_env()           # under torchrun: one process per GPU, agents sharded (parallel.py)
     data_utils.set_random_seeds(args.seed)
     if args.gpu:                        # (as in the reference, device 0 needs no flag)
         os.environ['CUDA_VISIBLE_DEVICES'] = str(args.gpu)

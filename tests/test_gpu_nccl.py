@@ -143,3 +143,55 @@ def test_sharded_finetune_matches_single_process(pg):
         pg.all_reduce(lo, op=pg.ReduceOp.MIN)
         pg.all_reduce(hi, op=pg.ReduceOp.MAX)
         assert torch.equal(lo, hi), n
+
+
+def test_train_and_test_entry_points_under_torchrun(pg, monkeypatch):
+    """``torchrun -m motion_style_transfer_b200.train ...`` in small: every rank runs the same command line in one shared
+    working directory (rank 0 lays it out), agents of every batch are sharded, rank 0 alone writes the checkpoints -- and every
+    rank ends with the same adapter tensors, which ``test`` restores to the same ADE / FDE on every rank."""
+    import pathlib
+    import re
+    import shutil
+    import test_gpu_scripts as S
+    from motion_style_transfer_b200 import train, test
+    from motion_style_transfer_b200.utils.parser import get_parser
+    rank = pg.get_rank()
+    root = pathlib.Path(f"/tmp/ynet_scripts_{os.environ.get('MASTER_PORT', '0')}")
+    if rank == 0:
+        shutil.rmtree(root, ignore_errors=True)
+        os.makedirs(root)
+        S._make_workspace(root, S.CONFIG, ['sA_0', 'sB_1'], S._sdd_raw_dir, 'reference.jpg', 'sdd_segmentation.pth',
+                          (('train', 0, 12), ('val', 100, 4), ('test', 200, 6)))
+        # a "pretrained" checkpoint: random initialisation, everything but the segmentation module
+        from motion_style_transfer_b200.models.ynet import YNet
+        torch.manual_seed(5)
+        m = YNet(obs_len=5, pred_len=6, segmentation_model_fp=None, encoder_channels=[8, 8, 16, 16, 16],
+                 decoder_channels=[16, 16, 16, 8, 8], n_waypoints=1, train_net='train', position=[], network='original')
+        os.makedirs(root / 'ckpts')
+        torch.save(m.state_dict(), root / 'ckpts' / 'sdd__ynet__ped.pt')
+    pg.barrier()
+    monkeypatch.chdir(root)
+    try:
+        tune = (f'{S.COMMON} --fine_tune --seed 2 --n_epoch 2 --n_round 1 --pretrained_ckpt ckpts/sdd__ynet__ped.pt '
+                '--train_net mosa_1 --position 0 1 --ckpt_path ckpts/tuned --n_train_batch 2 --lr 0.003')
+        train.main(get_parser(True).parse_args(tune.split()))
+        pg.barrier()
+        tuned = 'ckpts/tuned/Seed_2__filter_agent_type_Biker__mosa_1__Pos_0_1__TrN_8__lr_0.003__original.pt'
+        sd = torch.load(tuned, map_location='cuda')
+        assert sd and all('lora_' in k for k in sd)
+        import contextlib
+        import io
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            test.main(get_parser(False).parse_args(
+                f'{S.COMMON} --seed 2 --n_round 1 --pretrained_ckpt ckpts/sdd__ynet__ped.pt --tuned_ckpt {tuned}'.split()))
+        ade, fde = (float(v) for v in re.findall(S.AVERAGE, buf.getvalue())[0][1:])
+        t = torch.tensor([ade, fde], device='cuda', dtype=torch.float64)
+        lo, hi = t.clone(), t.clone()
+        pg.all_reduce(lo, op=pg.ReduceOp.MIN)
+        pg.all_reduce(hi, op=pg.ReduceOp.MAX)
+        assert torch.equal(lo, hi) and ade > 0 and fde > 0
+    finally:
+        pg.barrier()
+        if rank == 0:
+            shutil.rmtree(root, ignore_errors=True)

@@ -140,3 +140,45 @@ def test_fixed_layout_loss_mean_and_shared_generator_gloo():
     res = _run(_layout_case)
     assert res[0][0] and res[1][0]
     assert res[0][1] == res[1][1]
+
+
+def _init_env_worker(rank, world, port, out_q):
+    """What torchrun gives a rank: only environment variables.  (Not via _worker: that one creates the group itself.)"""
+    import io
+    import sys
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR='127.0.0.1',
+                      MASTER_PORT=str(port))
+    try:
+        from motion_style_transfer_b200 import parallel
+        sys.stdout = buf = io.StringIO()
+        got = parallel.init_from_env()
+        muted = sys.stdout is not buf
+        again = parallel.init_from_env()                      # a second call joins nothing and changes nothing
+        t = torch.tensor([float(rank + 1)])
+        dist.all_reduce(t)
+        out_q.put((rank, dict(world=tuple(got), again=tuple(again), muted=muted, total=float(t), backend=dist.get_backend())))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # pragma: no cover
+        out_q.put((rank, repr(e)))
+        raise
+
+
+def test_init_from_env_joins_the_torchrun_group_gloo():
+    """The entry points (train / test / evaluate_multickpts) call parallel.init_from_env(): under torchrun it forms the group
+    from the environment (gloo here, NCCL with CUDA) and silences the ranks other than 0; a plain launch is untouched."""
+    from motion_style_transfer_b200 import parallel
+    assert parallel.init_from_env() == (0, 1) and not dist.is_initialized()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_init_env_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for r in range(2):
+        assert not isinstance(res[r], str), res[r]
+        assert res[r]['world'] == (r, 2) and res[r]['again'] == (r, 2) and res[r]['total'] == 3.0 and res[r]['backend'] == 'gloo'
+    assert res[0]['muted'] is False and res[1]['muted'] is True
