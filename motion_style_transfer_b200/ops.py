@@ -16,7 +16,15 @@ def _L():
     return _lib.load()
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+_cur_device = getattr(torch._C, '_cuda_getDevice', None)
+
+
 def _stream():
+    """cudaStream_t of torch's current stream.  The raw accessor: building a torch.cuda.Stream object per launch
+    (``torch.cuda.current_stream()``) cost 10-17 us each, ~4 ms of the ~390 launches of a fine-tuning step."""
+    if _raw_stream is not None and _cur_device is not None:
+        return ctypes.c_void_p(_raw_stream(_cur_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

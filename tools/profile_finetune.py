@@ -37,3 +37,24 @@ with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA, to
     epoch(3)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=25, max_name_column_width=60))
+
+if os.environ.get('HOST_PROFILE', '0') == '1':
+    # where the host time of a step goes (the bf16x3 step is issue-bound: ~24 ms of Python against ~18 ms of kernels)
+    import cProfile
+    import pstats
+    import time
+    t0 = time.perf_counter()
+    for e in range(4, 7):
+        epoch(e)
+    t_issue = (time.perf_counter() - t0) / 3
+    torch.cuda.synchronize()
+    print(f'host issue time per epoch (1 step of 10 agents): {1000 * t_issue:.2f} ms')
+    pr = cProfile.Profile()
+    pr.enable()
+    for e in range(7, 10):
+        epoch(e)
+    pr.disable()
+    torch.cuda.synchronize()
+    st = pstats.Stats(pr)
+    st.sort_stats('tottime').print_stats(35)
+    st.sort_stats('cumulative').print_stats(45)
