@@ -129,7 +129,7 @@ class ClockSampler:
                 if val.lower().startswith('active'):
                     reasons.add(name)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons),
-                    samples=len(sm))
+                    samples=len(sm), sm_min_mhz=float(min(sm)) if sm else None)
 
 
 def _reference_evaluate(model_state, cfg, B, device, seeds, ns):
@@ -369,6 +369,9 @@ def run_finetune_mode(args, cfg, rank, world, dev):
 
     for e in range(max(1, args.warmup)):
         epoch(e)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
+    t_wall0 = time.time()
     times, out = [], None
     for it in range(args.steps):
         if world > 1:
@@ -381,9 +384,12 @@ def run_finetune_mode(args, cfg, rank, world, dev):
         torch.cuda.synchronize()
         times.append(_dist_max(e0.elapsed_time(e1), world, dev) / n_batches)
     ms = sum(times) / len(times)
+    clocks = sampler.stop(t_wall0, time.time()) if sampler else None
+    mem = torch.cuda.memory_stats(dev)
     if rank == 0:
         print(json.dumps({
             'metric': 'fine-tune optimiser steps/sec (train_epoch drop-in, MoSA r=1 adapters)', 'mode': 'finetune',
+            'clocks': clocks, 'mem': {k: mem.get(k, 0) for k in ('num_alloc_retries', 'num_device_alloc', 'num_device_free')},
             'value': 1000.0 / ms, 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'bf16x3 (forward + dgrad), f32 (wgrad, Adam)' if args.backend == 'bf16x3' else 'f32',
             'data': 'synthetic',
