@@ -304,11 +304,28 @@ int ynet_bce_logits_fwd_bwd(const float* logits, const float* target, int64_t n,
   return YNET_OK;
 }
 
+// The scratch of the fp32 data gradient comes from the device's stream-ordered pool.  By default that pool hands unused
+// memory back to the OS at every synchronisation point (release threshold 0), so the ~200 MB masked-gradient buffer was
+// unmapped at each epoch-end read of the loss and mapped again by the next step: single steps of 100-840 ms in a run of
+// 48 ms steps (profiles/finetune_fp32_excursions_r02.log).  Told once per device to keep what it has.
+static void keep_pool_memory() {
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done[dev] = true;
+}
+
 int ynet_conv3x3_dgrad_f32(const float* dy, const float* relu_out, int32_t N, int32_t H, int32_t W, const float* weight,
                            int32_t C_out, int32_t C_in, float* dx, void* stream) {
   YNET_CHECK_ARG(dy && weight && dx, "null pointer");
   YNET_CHECK_ARG(N > 0 && H > 0 && W > 0 && C_out > 0 && C_in > 0, "bad shape");
   cudaStream_t st = as_stream(stream);
+  keep_pool_memory();
   float* packed = nullptr;
   float* masked = nullptr;
   cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&packed), (size_t)C_out * C_in * 9 * sizeof(float), st);
