@@ -627,7 +627,7 @@ def main(only=None):
     gen_train(ns)
     gen_forward_batch(ns)
     gen_augment(ns)
-    gen_scripts_host(ns)
+    gen_scripts_host(ref_harness.load_scripts_host())
     gen_preprocess()
 
 

@@ -79,13 +79,21 @@ def load():
             ns.train_epoch = None
             ns.trainer = None
             ns.trainer_error = repr(e)
-        for name in ('data_utils', 'util', 'parser', 'extract_log'):      # the scripts' host side
-            try:
-                setattr(ns, name, importlib.import_module('utils.' + name))
-            except Exception as e:  # pragma: no cover
-                setattr(ns, name, None)
-                setattr(ns, name + '_error', repr(e))
     finally:
         sys.path.remove(REF_PATH)
     _loaded['ns'] = ns
+    return ns
+
+
+def load_scripts_host():
+    """``load()`` plus the host side of the reference's scripts: ``utils.data_utils``, ``utils.util``,
+    ``utils.parser``, ``utils.extract_log``.  Kept out of ``load()``: the reference arm of bench.py does not need them."""
+    ns = load()
+    if getattr(ns, 'data_utils', None) is None:
+        sys.path.insert(0, REF_PATH)
+        try:
+            for name in ('data_utils', 'util', 'parser', 'extract_log'):
+                setattr(ns, name, importlib.import_module('utils.' + name))
+        finally:
+            sys.path.remove(REF_PATH)
     return ns
