@@ -60,6 +60,20 @@ def _tc_packed(kind, weight, ver, make):
     return val
 
 
+_range_idx_cache = {}
+
+
+def _range_index(ranges, device):
+    """arange over the concatenated channel ranges, cached (built once per layer instead of once per optimiser step)."""
+    key = (tuple(ranges), str(device))
+    hit = _range_idx_cache.get(key)
+    if hit is None:
+        if len(_range_idx_cache) > 256:
+            _range_idx_cache.clear()
+        hit = _range_idx_cache[key] = torch.cat([torch.arange(c0, c1, device=device) for c0, c1 in ranges])
+    return hit
+
+
 def _tc_conv_forward(fold, C_out, weight, wver, bias, relu, parts):
     """conv3x3(cat(parts)) + bias (+ReLU): float32 NCHW parts (batch 1 = broadcast) -> float32 NCHW.  ``fold()`` yields the
     effective OIHW weight (LoRA folded); it only runs when the packed weights are not cached for this version."""
@@ -70,7 +84,7 @@ def _tc_conv_forward(fold, C_out, weight, wver, bias, relu, parts):
 
     def make():
         w_eff = fold()
-        idx = torch.cat([torch.arange(c0, c1, device=w_eff.device) for c0, c1 in ranges])
+        idx = _range_index(ranges, w_eff.device)
         bias_pad = torch.zeros(ops._pad16(C_out), dtype=torch.float32, device=w_eff.device)
         if bias is not None:
             bias_pad[:C_out] = bias.detach()

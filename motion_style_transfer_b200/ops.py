@@ -1082,32 +1082,46 @@ def split_cat(parts, N=None):
     return Split(torch.cat(his + los, dim=1), sum(p.C for p in parts), [l for p in parts for l in p.layout])
 
 
+_split_sel_cache = {}
+
+
+def _split_weight_select(src_layouts, c_in, device):
+    """For the channel-concatenation [W_hi (c_in) | W_lo (c_in) | one zero channel]: the gather index that lays the input
+    channels out as ynet_tc_conv3x3_split reads them -- per source [hi | hi] over its 2 * sum(cp) stored channels, then lo
+    over its sum(cp) hi channels, every part padded to its cp -- and the channel count of each of those blocks.  Cached
+    per layout: fine-tuning re-packs the adapted layers' weights after every optimiser step."""
+    key = (tuple(tuple(tuple(e) for e in layout) for layout in src_layouts), c_in, str(device))
+    hit = _split_sel_cache.get(key)
+    if hit is None:
+        zero = 2 * c_in
+        sel, chans, c0 = [], [], 0
+        for layout in src_layouts:
+            hi, lo = [], []
+            for C, cp in layout:
+                hi += list(range(c0, c0 + C)) + [zero] * (cp - C)
+                lo += list(range(c_in + c0, c_in + c0 + C)) + [zero] * (cp - C)
+                c0 += C
+            sel += hi + hi + lo
+            chans += [2 * len(hi), len(hi)]
+        if c0 != c_in:
+            raise ValueError(f'split_pack_weights: sources hold {c0} channels, the weight expects {c_in}')
+        if len(_split_sel_cache) > 256:
+            _split_sel_cache.clear()
+        hit = _split_sel_cache[key] = (torch.tensor(sel, dtype=torch.long, device=device), chans)
+    return hit
+
+
 def split_pack_weights(weight_oihw, src_layouts):
     """OIHW float32 weight (3x3 or 1x1), input channels = the concatenation of the sources' real channels.
     src_layouts: per Split source its ``layout``.  Packed for the source pairs of ynet_tc_conv3x3_split: per source [W_hi | W_hi] over its
     2 * sum(cp) stored channels, then W_lo over its sum(cp) hi channels."""
     w = _req(weight_oihw, name='weight')
-    C_out, _, kh, kw = w.shape
+    C_out, c_in, kh, kw = w.shape
+    sel, chans = _split_weight_select(src_layouts, c_in, w.device)
     w_hi = w.to(torch.bfloat16).to(torch.float32)
     w_lo = w - w_hi                                   # rounded to bf16 by the packer: W = hi + lo to 2^-17
-    blocks, chans = [], []
-    c0 = 0
-    for layout in src_layouts:
-        tot = sum(cp for _, cp in layout)
-        a = torch.zeros(C_out, 2 * tot, kh, kw, dtype=torch.float32, device=w.device)
-        b = torch.zeros(C_out, tot, kh, kw, dtype=torch.float32, device=w.device)
-        o = 0
-        for C, cp in layout:
-            a[:, o:o + C] = w_hi[:, c0:c0 + C]
-            a[:, tot + o:tot + o + C] = w_hi[:, c0:c0 + C]
-            b[:, o:o + C] = w_lo[:, c0:c0 + C]
-            o += cp
-            c0 += C
-        blocks += [a, b]
-        chans += [2 * tot, tot]
-    if c0 != w.shape[1]:
-        raise ValueError(f'split_pack_weights: sources hold {c0} channels, the weight expects {w.shape[1]}')
-    return tc_pack_weights(torch.cat(blocks, dim=1).contiguous(), chans)
+    wcat = torch.cat([w_hi, w_lo, w.new_zeros(C_out, 1, kh, kw)], dim=1)
+    return tc_pack_weights(wcat.index_select(1, sel), chans)
 
 
 def _split_src_array(sources, N):
