@@ -16,7 +16,9 @@ same order as the reference, so a seeded run selects the same agents.  What diff
     the grouping column to the function), so those two are pinned against ``oracle/data_oracle.py`` (per-agent loops
     restating `:51-112`) instead of the live reference; the others are pinned against the live reference.
 
-The analysis half of the reference file (variation-factor tables and plots, `:279-751`) is not part of the path.
+Of the analysis half of the reference file (`:279-751`) the velocity / acceleration variation factors and the per-agent-type
+datasets (what ``utils/sdd_dataset.py`` / ``inD_dataset.py`` / ``filter_dataset.py`` need to go from the raw recordings to
+the pickles above) are here; neighbour-distance factors, range datasets and the plots are not.
 """
 import os
 import pathlib
@@ -117,6 +119,98 @@ def create_images_dict(unique_scene, image_path, image_file='reference.jpg', use
 def load_images(scenes, image_path, image_file='reference.jpg'):
     """data_utils.py:266-276."""
     return create_images_dict(set(scenes) if isinstance(scenes, list) else scenes, image_path, image_file)
+
+
+# ------------------------------------------------------------------------------------------ variation factors (279-357)
+_REDUCE = {'max': np.max, 'avg': np.mean, 'min': np.min, 'tot': np.sum,
+           'abs+max': lambda a, axis: np.max(np.abs(a), axis=axis), 'abs+avg': lambda a, axis: np.mean(np.abs(a), axis=axis),
+           'abs+min': lambda a, axis: np.mean(np.abs(a), axis=axis)}        # ('abs+min' is a mean in the reference, :351-352)
+
+
+def aggregate_per_varf_value(df, varf, obs_len):
+    """data_utils.py:293-357: one statistic per agent, ``varf = '<op>_<attr>'`` with attr = vel (speed between consecutive
+    rows / frame step) or acc (difference of consecutive speeds / frame step), taken over the first ``obs_len`` rows (all rows
+    if falsy) and reduced by op (max / avg / min / tot / abs+...).  Returns the frame [metaId, <varf>, label], agents in
+    ascending metaId.  All agents at once on an (agents, rows) array -- the data are windowed, every agent has the same
+    number of rows -- instead of a Python function per agent.  The neighbour-distance factors (dist, den*) are not built."""
+    op, attr = varf.split('_')
+    if attr not in ('vel', 'acc'):
+        raise NotImplementedError(f'variation factor {varf!r}: only the velocity / acceleration factors are built')
+    if op not in _REDUCE:
+        raise ValueError(f'Cannot compute {op} operation')
+    order, starts, counts = _grouped_positions(df)
+    if len(counts) == 0 or (counts != counts[0]).any():
+        raise ValueError('aggregate_per_varf_value: every agent needs the same number of rows (windowed data)')
+    T = int(counts[0])
+    take = df.iloc[order]
+    x, y = take['x'].to_numpy().reshape(-1, T), take['y'].to_numpy().reshape(-1, T)
+    frame = take['frame'].to_numpy().reshape(-1, T)
+    label = take['label'].to_numpy().reshape(-1, T)
+    step = frame[:, 1:] - frame[:, :-1]
+    assert (step == step[:, :1]).all() and (label == label[:, :1]).all()     # the reference's sanity checks (:306-313)
+    step = step[:, :1].astype(np.float64) if step.dtype.kind != 'f' else step[:, :1]
+    n = obs_len if obs_len else T
+    vel = np.sqrt((x[:, :n - 1] - x[:, 1:n]) ** 2 + (y[:, :n - 1] - y[:, 1:n]) ** 2) / step
+    seq = vel if attr == 'vel' else (vel[:, :n - 2] - vel[:, 1:n - 1]) / step
+    stats = _REDUCE[op](np.ascontiguousarray(seq), axis=1)
+    meta = take['metaId'].to_numpy().reshape(-1, T)[:, 0]
+    return pd.DataFrame({'metaId': meta, varf: stats, 'label': label[:, 0]})
+
+
+def get_varf_table(df, varf_list, obs_len):
+    """data_utils.py:279-290: [metaId, label, sceneId, scene, <varf>...], one row per agent."""
+    print('Computing variation fatcor by obs_len' if obs_len else 'Computing variation fatcor by obs_len + pred_len')
+    table = df.groupby(['metaId', 'label', 'sceneId']).size().reset_index()[['metaId', 'label', 'sceneId']]
+    table['scene'] = table.sceneId.apply(lambda s: s.split('_')[0])
+    for varf in varf_list:
+        table = table.merge(aggregate_per_varf_value(df, varf, obs_len)[['metaId', varf]], on='metaId')
+    return table
+
+
+# ------------------------------------------------------------------------------------------ datasets per agent type (367-413)
+def convert_df_to_dict(df_gb):
+    """data_utils.py:367-373: {group: {'metaId': [...], 'sceneId': [...], 'label': [...]}}, one entry per agent."""
+    out = {}
+    for key in df_gb.groups.keys():
+        agents = df_gb.get_group(key)[['metaId', 'sceneId', 'label']].drop_duplicates()
+        assert agents.metaId.nunique() == agents.shape[0]
+        out[key] = agents.to_dict('list')
+    return out
+
+
+def create_dataset_by_agent_type(df, labels, out_dir, statistic_only, same_group_size=False, selected_scenes=None):
+    """data_utils.py:376-413: ``<out_dir>/<label>.pkl`` per agent type, or with ``selected_scenes``
+    ``<out_dir>/<scene>/<label>.pkl`` per scene plus ``<out_dir>/<scene>__<scene>.../<label>.pkl`` for their union -- the
+    directories ``--dataset_path filter/.../agent_type/<scene>/`` of the training scripts point at."""
+    if same_group_size:
+        raise NotImplementedError('same_group_size (data_utils.py:468-517) has no caller in the reference')
+    pathlib.Path(out_dir).mkdir(parents=True, exist_ok=True)
+    df_label = df[df.label.isin(labels)]
+    groups = df_label.groupby(by='label', dropna=True)
+    rows_per_agent = df_label[df_label.metaId == df_label.metaId.unique()[0]].shape[0]
+    n_agents = groups.count()['metaId'] / rows_per_agent
+    print('Statistics:\n', n_agents)
+    print('# total:', n_agents.sum())
+    if statistic_only:
+        return
+    for agent, group in convert_df_to_dict(groups).items():
+        rows = df_label[df_label.metaId.isin(group['metaId'])]
+        if selected_scenes is None:
+            rows.to_pickle(os.path.join(out_dir, f'{agent}.pkl'))
+            continue
+        parts = []
+        for scene_id in selected_scenes:
+            scene_dir = os.path.join(out_dir, scene_id)
+            pathlib.Path(scene_dir).mkdir(parents=True, exist_ok=True)
+            part = rows[rows.sceneId == scene_id]
+            parts.append(part)
+            print(f'scene_id = {scene_id}, label = {agent}, #= {part.metaId.unique().shape[0]}')
+            part.to_pickle(os.path.join(scene_dir, f'{agent}.pkl'))
+        union_dir = os.path.join(out_dir, '__'.join(selected_scenes))
+        pathlib.Path(union_dir).mkdir(parents=True, exist_ok=True)
+        union = pd.concat(parts, axis=0)
+        print(f'scene_id = {selected_scenes}, label = {agent}, #= {union.metaId.unique().shape[0]}')
+        union.to_pickle(os.path.join(union_dir, f'{agent}.pkl'))
 
 
 # ------------------------------------------------------------------------------------------ splits (754-912, 955-964)

@@ -611,6 +611,84 @@ def gen_scripts_host(ns):
     print(f'scripts_host: {os.path.getsize(path) / 1024:.1f} KiB')
 
 
+VARFS = ['avg_vel', 'max_acc', 'abs+max_acc', 'min_vel', 'tot_vel', 'abs+min_acc', 'max_vel', 'avg_acc']
+
+
+def _frame_arrays(prefix, df):
+    out = {}
+    for col in df.columns:
+        v = df[col].to_numpy()
+        out[f'{prefix}/{col}'] = np.array(list(v), dtype='U32') if v.dtype.kind in 'OUT' or str(df[col].dtype).startswith(
+            ('str', 'object')) else v
+    out[f'{prefix}/__columns__'] = np.array(list(df.columns), dtype='U32')
+    return out
+
+
+def gen_raw_datasets(ns):
+    """The converters from the raw recordings (utils/sdd_dataset.py, inD_dataset.py, filter_dataset.py; data_utils.py:279-413)
+    run LIVE on the synthetic recordings of oracle/synth_raw.py: the raw frames, the variation-factor table and the
+    per-agent-type datasets.  ``load_and_window_*`` of the reference cannot run here (pandas 3, see oracle/data_oracle.py):
+    the windowed frame the later stages are fed is the restatement's (oracle/data_oracle.py) and is stored with the fixture."""
+    import contextlib
+    import importlib
+    import io
+    import sys
+    import tempfile
+    from oracle import data_oracle, synth_raw
+    sys.path.insert(0, ref_harness.REF_PATH)
+    try:
+        RS = importlib.import_module('utils.sdd_dataset')
+        RI = importlib.import_module('utils.inD_dataset')
+        RF = importlib.import_module('utils.filter_dataset')
+    finally:
+        sys.path.remove(ref_harness.REF_PATH)
+    R = ns.data_utils
+    out = {}
+
+    def quiet(fn, *a, **kw):
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf), warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            res = fn(*a, **kw)
+        return res, buf.getvalue()
+
+    with tempfile.TemporaryDirectory() as tmp:
+        synth_raw.write_sdd(tmp, seed=0)
+        raw = RS.load_raw_sdd(tmp)
+        out.update(_frame_arrays('sdd/raw', raw))
+        # sdd_dataset.py:44-50 with the two functions the reference cannot run replaced by their per-agent restatement
+        w = data_oracle.split_fragmented(raw)
+        w = R.downsample(w, step=12)
+        w = R.filter_short_trajectories(w, threshold=10)
+        w = data_oracle.sliding_window(w, window_size=10, stride=10)
+        out.update(_frame_arrays('sdd/window', w))
+        for obs in (4, 0):
+            table, printed = quiet(R.get_varf_table, w, VARFS, obs)
+            out.update(_frame_arrays(f'sdd/varf{obs}', table))
+            out[f'sdd/varf{obs}/__printed__'] = np.array(printed)
+        for tag, sel in (('all', None), ('sel', ['bookstore_0', 'coupa_3'])):
+            d = os.path.join(tmp, 'agent_' + tag)
+            _, printed = quiet(R.create_dataset_by_agent_type, w, ['Biker', 'Pedestrian'], d, False, selected_scenes=sel)
+            files = sorted(os.path.relpath(os.path.join(dp, f), d) for dp, _, fs in os.walk(d) for f in fs)
+            out[f'sdd/agent_{tag}/files'] = np.array(files, dtype='U64')
+            out[f'sdd/agent_{tag}/printed'] = np.array(printed)
+            for f in files:
+                out[f'sdd/agent_{tag}/{f}'] = pd.read_pickle(os.path.join(d, f)).index.to_numpy()
+        _, printed = quiet(R.create_dataset_by_agent_type, w, ['Pedestrian'], os.path.join(tmp, 'stat'), True)
+        out['sdd/agent_stat/printed'] = np.array(printed)
+        table.to_pickle(os.path.join(tmp, 'varf.pkl'))
+        w[w.label == 'Pedestrian'].to_pickle(os.path.join(tmp, 'ped.pkl'))
+        lo, hi = float(table.avg_vel.quantile(0.3)), float(table.avg_vel.quantile(0.8))
+        _, printed = quiet(RF.filter_by_avg_vel, os.path.join(tmp, 'ped.pkl'), os.path.join(tmp, 'varf.pkl'), lo, hi)
+        out['sdd/filter/bounds'] = np.array([lo, hi])
+        out['sdd/filter/printed'] = np.array(printed)
+        out['sdd/filter/index'] = pd.read_pickle(os.path.join(tmp, 'ped_filter.pkl')).index.to_numpy()
+    with tempfile.TemporaryDirectory() as tmp:
+        synth_raw.write_ind(tmp, seed=1)
+        out.update(_frame_arrays('ind/raw', RI.load_raw_inD(tmp, recordings=['00', '07'])))
+    save('raw_datasets', **out)
+
+
 def main(only=None):
     torch.set_num_threads(1)     # reference's global-sum quirk depends on thread count (SURVEY 8)
     ns = ref_harness.load()
@@ -628,6 +706,7 @@ def main(only=None):
     gen_forward_batch(ns)
     gen_augment(ns)
     gen_scripts_host(ref_harness.load_scripts_host())
+    gen_raw_datasets(ref_harness.load_scripts_host())
     gen_preprocess()
 
 

@@ -1,0 +1,141 @@
+"""From the raw recordings to the pickles the path starts from (the reference's utils/sdd_dataset.py, inD_dataset.py,
+filter_dataset.py and data_utils.py:279-413), against ``tests/golden/raw_datasets.npz`` recorded from the LIVE reference on
+the synthetic recordings of oracle/synth_raw.py (oracle/gen_golden.py::gen_raw_datasets).  Float columns are compared bit
+for bit."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import load_golden
+
+
+def quiet(fn, *a, **kw):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        res = fn(*a, **kw)
+    return res, buf.getvalue()
+
+
+def check_frame(g, prefix, df):
+    cols = [str(c) for c in g[f'{prefix}/__columns__']]
+    assert list(df.columns) == cols, prefix
+    for c in cols:
+        want = g[f'{prefix}/{c}']
+        got = df[c].to_numpy()
+        if want.dtype.kind == 'U':
+            assert list(map(str, got)) == list(want), (prefix, c)
+        else:
+            assert np.array_equal(got, want), (prefix, c)
+
+
+def frame_of(g, prefix):
+    cols = [str(c) for c in g[f'{prefix}/__columns__']]
+    return pd.DataFrame({c: (g[f'{prefix}/{c}'].astype(object) if g[f'{prefix}/{c}'].dtype.kind == 'U' else g[f'{prefix}/{c}'])
+                         for c in cols})
+
+
+@pytest.fixture(scope='module')
+def G():
+    return load_golden('raw_datasets')
+
+
+def test_sdd_raw_window_varf_agent_type_filter(G, tmp_path):
+    from oracle import synth_raw
+    from motion_style_transfer_b200.utils import data_utils as D, filter_dataset as F, sdd_dataset as S
+    synth_raw.write_sdd(str(tmp_path), seed=0)
+    raw = S.load_raw_sdd(str(tmp_path))
+    check_frame(G, 'sdd/raw', raw)
+    # the first annotation line of every file is consumed as a header (reference quirk, kept): 3 files, 3 rows short
+    n_lines = sum(len(open(os.path.join(dp, f)).read().splitlines()) for dp, _, fs in os.walk(tmp_path) for f in fs)
+    assert len(raw) == n_lines - 3 - 3 * 6 and set(raw.label) == {'Pedestrian', 'Biker', 'Cart'}        # 6 lost boxes per file
+    w = S.load_and_window_sdd(str(tmp_path), step=12, window_size=10, stride=10)
+    check_frame(G, 'sdd/window', w)
+    assert (w.groupby('metaId').size() == 10).all() and (w.groupby('metaId').frame.diff().dropna() == 12).all()
+    for obs in (4, 0):
+        table, printed = quiet(D.get_varf_table, w, [str(v) for v in G[f'sdd/varf{obs}/__columns__'][4:]], obs)
+        check_frame(G, f'sdd/varf{obs}', table)
+        assert printed == str(G[f'sdd/varf{obs}/__printed__'])
+    with pytest.raises(NotImplementedError):
+        D.aggregate_per_varf_value(w, 'min_dist', 4)
+    with pytest.raises(ValueError, match='Cannot compute'):
+        D.aggregate_per_varf_value(w, 'median_vel', 4)
+    for tag, sel in (('all', None), ('sel', ['bookstore_0', 'coupa_3'])):
+        d = tmp_path / f'agent_{tag}'
+        _, printed = quiet(D.create_dataset_by_agent_type, w, ['Biker', 'Pedestrian'], str(d), False, selected_scenes=sel)
+        assert printed == str(G[f'sdd/agent_{tag}/printed'])
+        files = sorted(os.path.relpath(os.path.join(dp, f), d) for dp, _, fs in os.walk(d) for f in fs)
+        assert files == [str(f) for f in G[f'sdd/agent_{tag}/files']]
+        for f in files:
+            part = pd.read_pickle(d / f)
+            assert np.array_equal(part.index.to_numpy(), G[f'sdd/agent_{tag}/{f}'])
+            assert set(part.label) == {os.path.basename(f)[:-4]}
+    _, printed = quiet(D.create_dataset_by_agent_type, w, ['Pedestrian'], str(tmp_path / 'stat'), True)
+    assert printed == str(G['sdd/agent_stat/printed']) and not os.listdir(tmp_path / 'stat')
+    with pytest.raises(NotImplementedError):
+        D.create_dataset_by_agent_type(w, ['Pedestrian'], str(tmp_path / 'x'), False, same_group_size=True)
+    table.to_pickle(tmp_path / 'varf.pkl')
+    w[w.label == 'Pedestrian'].to_pickle(tmp_path / 'ped.pkl')
+    lo, hi = G['sdd/filter/bounds']
+    _, printed = quiet(F.main, ['--data_path', str(tmp_path / 'ped.pkl'), '--varf_path', str(tmp_path / 'varf.pkl'),
+                                '--lower_bound', repr(float(lo)), '--upper_bound', repr(float(hi))])
+    assert printed == str(G['sdd/filter/printed'])
+    assert np.array_equal(pd.read_pickle(tmp_path / 'ped_filter.pkl').index.to_numpy(), G['sdd/filter/index'])
+
+
+def test_sdd_command_line_end_to_end(tmp_path):
+    """``python -m ...utils.sdd_dataset --varf agent_type`` then ``split_dataset`` then ``prepare_dataeset``: raw recordings
+    to the frames a training run loads, with the training window (obs + pred rows per agent)."""
+    from oracle import synth_raw
+    from motion_style_transfer_b200.utils import data_utils as D, sdd_dataset as S, split_dataset
+    raw_dir, filt = tmp_path / 'raw', tmp_path / 'filter'
+    synth_raw.write_sdd(str(raw_dir), seed=2)
+    df, printed = quiet(S.main, ['--raw_data_dir', str(raw_dir), '--additional_data_dir', str(raw_dir), '--filter_data_dir',
+                                 str(filt), '--window_size', '10', '--stride', '5', '--obs_len', '4', '--varf', 'agent_type',
+                                 '--labels', 'Pedestrian', 'Biker', '--selected_scenes', 'bookstore_0', 'bookstore_1'])
+    assert 'Loaded raw dataset' in printed and 'Saved variation factor data to' in printed
+    assert os.path.exists(raw_dir / 'data_8_12_2_5fps.pkl') and os.path.exists(raw_dir / 'varf_8_12_2_5fps.pkl')
+    varf = pd.read_pickle(raw_dir / 'varf_8_12_2_5fps.pkl')
+    assert list(varf.columns) == ['metaId', 'label', 'sceneId', 'scene', 'avg_vel', 'max_acc'] and len(varf) == df.metaId.nunique()
+    both = filt / 'agent_type' / 'bookstore_0__bookstore_1'
+    assert sorted(os.listdir(both)) == ['Biker.pkl', 'Pedestrian.pkl']
+    # --reload reads the pickle back instead of the raw files
+    _, printed = quiet(S.main, ['--raw_data_dir', str(raw_dir), '--filter_data_dir', str(filt), '--reload', '--varf',
+                                'agent_type', '--labels', 'Biker', '--statistic_only'])
+    assert 'Reloaded raw dataset' in printed and 'Statistics' in printed
+    with pytest.raises(NotImplementedError):
+        quiet(S.main, ['--raw_data_dir', str(raw_dir), '--filter_data_dir', str(filt), '--reload', '--varf', 'avg_vel'])
+    quiet(split_dataset.main, ['--data_dir', str(both), '--data_filename', 'Pedestrian.pkl', '--val_split', '0.2', '--test_split',
+                               '0.2', '--seed', '1'])
+    (tr, va, te), _ = quiet(D.prepare_dataeset, str(both / 'Pedestrian'), 'predefined', 4, None, None, None, None, None, False,
+                            False, 'train')
+    n = pd.read_pickle(both / 'Pedestrian.pkl').metaId.nunique()
+    assert tr.metaId.nunique() + va.metaId.nunique() + te.metaId.nunique() == n and te.metaId.nunique() == int(0.2 * n)
+    from motion_style_transfer_b200.utils.dataloader import SceneDataset
+    ds = SceneDataset(tr, resize=0.25, total_len=10)
+    assert sum(t.shape[0] for t in ds.trajectories) == tr.metaId.nunique() and ds.trajectories[0].shape[1:] == (10, 2)
+
+
+def test_ind_raw_and_window(G, tmp_path):
+    from oracle import data_oracle, synth_raw
+    from motion_style_transfer_b200.utils import inD_dataset as I
+    synth_raw.write_ind(str(tmp_path), seed=1)
+    raw = I.load_raw_inD(str(tmp_path), recordings=['00', '07'])
+    check_frame(G, 'ind/raw', raw)
+    assert (raw.x >= 0).all() and (raw.y >= 0).all() and set(raw.label) == {'car', 'pedestrian', 'truck_bus', 'bicycle'}
+    assert I._recordings([1]) == ['%02d' % r for r in range(7)] and len(I._recordings([1, 2, 3, 4])) == 33
+    # windowing (inD_dataset.py:73-100) needs all 33 recordings by default: only the two written ones here
+    synth_raw.write_ind(str(tmp_path / 'all'), seed=3, recordings=['%02d' % r for r in range(33)])
+    w = I.load_and_window_inD(25, 8, 8, scenes=[1, 4], path=str(tmp_path / 'all'))
+    assert list(w.columns) == ['trackId', 'frame', 'x', 'y', 'sceneId', 'metaId', 'label', 'recId']
+    assert set(w.sceneId) == {'scene1', 'scene4'} and set(w[w.sceneId == 'scene4'].recId) == {'30', '31', '32'}
+    assert (w.groupby('metaId').size() == 8).all()
+    # metres -> pixels with the constants as the reference's code applies them
+    base = I.load_raw_inD(str(tmp_path / 'all'), scenes=[1, 4])
+    from motion_style_transfer_b200.utils.data_utils import downsample, filter_short_trajectories
+    ref = data_oracle.sliding_window(filter_short_trajectories(downsample(base, 25), 8), 8, 8)
+    scale = np.where(ref.sceneId.isin(I._recordings([1])), 0.0127 * 12, 0.00814 * 12)
+    assert np.array_equal(w.x.to_numpy(), ref.x.to_numpy() / scale) and np.array_equal(w.y.to_numpy(), ref.y.to_numpy() / scale)
