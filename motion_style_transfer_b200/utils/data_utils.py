@@ -18,7 +18,7 @@ same order as the reference, so a seeded run selects the same agents.  What diff
 
 Of the analysis half of the reference file (`:279-751`) the velocity / acceleration variation factors and the per-agent-type
 datasets (what ``utils/sdd_dataset.py`` / ``inD_dataset.py`` / ``filter_dataset.py`` need to go from the raw recordings to
-the pickles above) are here; neighbour-distance factors, range datasets and the plots are not.
+the pickles above) and the datasets by factor range are here; neighbour-distance factors and the plots are not.
 """
 import os
 import pathlib
@@ -211,6 +211,47 @@ def create_dataset_by_agent_type(df, labels, out_dir, statistic_only, same_group
         union = pd.concat(parts, axis=0)
         print(f'scene_id = {selected_scenes}, label = {agent}, #= {union.metaId.unique().shape[0]}')
         union.to_pickle(os.path.join(union_dir, f'{agent}.pkl'))
+
+
+def add_range_column(df, varf, varf_ranges, obs_len, inclusive='both'):
+    """data_utils.py:359-364: column ``<varf>_range`` = '<lo>_<hi>' of the range the agent's factor falls into (a later
+    range wins where ranges overlap, agents outside every range get NaN).  The merge renumbers the index."""
+    stats = aggregate_per_varf_value(df, varf, obs_len)
+    for lo, hi in varf_ranges:
+        stats.loc[stats[varf].between(lo, hi, inclusive=inclusive), f'{varf}_range'] = f'{lo}_{hi}'
+    return df.merge(stats[['metaId', f'{varf}_range']], on='metaId')
+
+
+def create_dataset_given_range(df, varf, varf_ranges, labels, out_dir, obs_len, statistic_only, inclusive='both',
+                               same_group_size=False):
+    """data_utils.py:415-465: one pickle per range of a variation factor, ``<out_dir>/<lo>_<hi>.pkl`` (``varf_ranges`` a
+    list of tuples, one factor) or per combination of ranges of several factors, ``<lo>_<hi>__<lo>_<hi>.pkl``
+    (``varf_ranges`` a list of lists of tuples).  The 'Statistics' lines print what the reference prints (the number of
+    distinct group sizes)."""
+    if same_group_size:
+        raise NotImplementedError('same_group_size (data_utils.py:468-517) has no caller in the reference')
+    pathlib.Path(out_dir).mkdir(parents=True, exist_ok=True)
+    df_label = df[df.label.isin(labels)]
+    if isinstance(varf_ranges[0], tuple):
+        varf = varf[0]
+        df_label = add_range_column(df_label, varf, varf_ranges, obs_len, inclusive=inclusive)
+        column = f'{varf}_range'
+    elif isinstance(varf_ranges[0], list):
+        for f, r in zip(varf, varf_ranges):
+            df_label = add_range_column(df_label, f, r, obs_len, inclusive=inclusive)
+        column = '__'.join(varf) + '_range'
+        complete = ~df_label.isna().any(axis=1)
+        df_label.loc[complete, column] = df_label.loc[complete, [f + '_range' for f in varf]].agg('__'.join, axis=1)
+    else:
+        raise ValueError(f'Cannot process {varf}.')
+    groups = df_label.groupby(by=column, dropna=True)
+    n_sizes = groups.count()['metaId'].unique().shape[0]
+    print('Statistics:\n', n_sizes)
+    print('# total:', n_sizes)
+    if statistic_only:
+        return
+    for name, group in convert_df_to_dict(groups).items():
+        df_label[df_label.metaId.isin(group['metaId'])].to_pickle(os.path.join(out_dir, f'{name}.pkl'))
 
 
 # ------------------------------------------------------------------------------------------ splits (754-912, 955-964)

@@ -6,7 +6,7 @@ import os
 
 import pandas as pd
 
-from .data_utils import create_dataset_by_agent_type, get_varf_table
+from .data_utils import create_dataset_by_agent_type, create_dataset_given_range, get_varf_table
 
 VARF_HELP = ("Variation factors from: 'avg_vel', 'max_vel', 'avg_acc', 'max_acc', 'abs+max_acc', 'abs+avg_acc', "
              "'agent_type' (the neighbour-distance factors 'min_dist', 'avg_den*' are not built)")
@@ -52,9 +52,14 @@ def build(args, load_and_window):
         print(f'Saved variation factor data to {varf_path}')
     if args.varf is None:
         return df
-    if args.varf != ['agent_type']:
-        raise NotImplementedError('datasets by variation-factor range (data_utils.py:415-465) are not built; '
-                                  'utils/filter_dataset.py filters an agent-type dataset by one factor')
-    create_dataset_by_agent_type(df, args.labels, os.path.join(args.filter_data_dir, 'agent_type'),
-                                 statistic_only=args.statistic_only, selected_scenes=args.selected_scenes)
+    if args.varf == ['agent_type']:
+        create_dataset_by_agent_type(df, args.labels, os.path.join(args.filter_data_dir, 'agent_type'),
+                                     statistic_only=args.statistic_only, selected_scenes=args.selected_scenes)
+    else:
+        if any('dist' in f or 'den' in f for f in args.varf):
+            raise NotImplementedError('neighbour-distance variation factors (data_utils.py:520-540) are not built')
+        out_dir = os.path.join(args.filter_data_dir, '__'.join(args.varf), '_'.join(args.labels))
+        create_dataset_given_range(df, args.varf, args.varf_ranges, args.labels, out_dir, obs_len=args.obs_len,
+                                   statistic_only=args.statistic_only)
+    print(f'Created dataset: \nVariation factor = {args.varf} \nAgents = {args.labels}')
     return df

@@ -106,8 +106,8 @@ def test_sdd_command_line_end_to_end(tmp_path):
     _, printed = quiet(S.main, ['--raw_data_dir', str(raw_dir), '--filter_data_dir', str(filt), '--reload', '--varf',
                                 'agent_type', '--labels', 'Biker', '--statistic_only'])
     assert 'Reloaded raw dataset' in printed and 'Statistics' in printed
-    with pytest.raises(NotImplementedError):
-        quiet(S.main, ['--raw_data_dir', str(raw_dir), '--filter_data_dir', str(filt), '--reload', '--varf', 'avg_vel'])
+    with pytest.raises(NotImplementedError):            # neighbour distances are not built
+        quiet(S.main, ['--raw_data_dir', str(raw_dir), '--filter_data_dir', str(filt), '--reload', '--varf', 'avg_den50'])
     quiet(split_dataset.main, ['--data_dir', str(both), '--data_filename', 'Pedestrian.pkl', '--val_split', '0.2', '--test_split',
                                '0.2', '--seed', '1'])
     (tr, va, te), _ = quiet(D.prepare_dataeset, str(both / 'Pedestrian'), 'predefined', 4, None, None, None, None, None, False,
@@ -139,3 +139,58 @@ def test_ind_raw_and_window(G, tmp_path):
     ref = data_oracle.sliding_window(filter_short_trajectories(downsample(base, 25), 8), 8, 8)
     scale = np.where(ref.sceneId.isin(I._recordings([1])), 0.0127 * 12, 0.00814 * 12)
     assert np.array_equal(w.x.to_numpy(), ref.x.to_numpy() / scale) and np.array_equal(w.y.to_numpy(), ref.y.to_numpy() / scale)
+
+
+def test_range_datasets_and_generate_varf(G, tmp_path):
+    """``--varf avg_vel`` (data_utils.py:359-364, 415-465).  ``add_range_column`` is compared with the live reference when it
+    is there; ``create_dataset_given_range`` of the reference raises at its own statistics line (`:452`, ``.sum()`` of an
+    int) before it writes anything, so the files are checked against the factor table itself."""
+    from motion_style_transfer_b200.utils import data_utils as D, generate_varf, sdd_dataset as S
+    w = frame_of(G, 'sdd/window')
+    table, _ = quiet(D.get_varf_table, w, ['avg_vel', 'max_acc'], 4)
+    ranges = [(0.4, 1.0), (1.0, 1.5), (1.4, 2.5)]
+    for inclusive in ('both', 'left', 'neither'):
+        got = D.add_range_column(w, 'avg_vel', ranges, 4, inclusive=inclusive)
+        assert list(got.columns) == list(w.columns) + ['avg_vel_range'] and len(got) == len(w)
+        try:
+            from oracle import ref_harness
+            ref = ref_harness.load_scripts_host().data_utils.add_range_column(w, 'avg_vel', ranges, 4, inclusive=inclusive)
+            pd.testing.assert_frame_equal(ref, got)
+        except (ImportError, RuntimeError):         # no reference tree (GPU box): the hand check below still runs
+            pass
+    got = D.add_range_column(w, 'avg_vel', ranges, 4)
+    v = table.set_index('metaId').avg_vel
+    want = {m: ('1.4_2.5' if 1.4 <= x <= 2.5 else '1.0_1.5' if 1.0 <= x <= 1.5 else '0.4_1.0') for m, x in v.items()}   # later wins
+    assert all(want[m] == r for m, r in zip(got.metaId, got.avg_vel_range))
+    out = tmp_path / 'avg_vel' / 'Biker_Pedestrian'
+    _, printed = quiet(D.create_dataset_given_range, w, ['avg_vel'], ranges, ['Biker', 'Pedestrian'], str(out), 4, False)
+    assert printed.startswith('Statistics:\n') and '# total:' in printed
+    assert sorted(os.listdir(out)) == ['0.4_1.0.pkl', '1.0_1.5.pkl', '1.4_2.5.pkl']
+    labels = w.drop_duplicates('metaId').set_index('metaId').label
+    seen = set()
+    for name in os.listdir(out):
+        part = pd.read_pickle(out / name)
+        ids = set(part.metaId)
+        assert ids == {m for m in want if want[m] == name[:-4] and labels[m] in ('Biker', 'Pedestrian')} and not (ids & seen)
+        assert (part.groupby('metaId').size() == 10).all()
+        seen |= ids
+    # two factors: one pickle per combination of ranges, agents outside a range of either factor in none
+    out2 = tmp_path / 'two'
+    quiet(D.create_dataset_given_range, w, ['avg_vel', 'max_acc'], [[(0.0, 1.2), (1.2, 3.0)], [(-1.0, 0.005), (0.005, 1.0)]],
+          ['Biker', 'Pedestrian', 'Cart'], str(out2), 4, False)
+    files = sorted(os.listdir(out2))
+    assert set(files) <= {f'{a}__{b}.pkl' for a in ('0.0_1.2', '1.2_3.0') for b in ('-1.0_0.005', '0.005_1.0')} and len(files) >= 3
+    assert sum(pd.read_pickle(out2 / f).metaId.nunique() for f in files) == w.metaId.nunique()
+    with pytest.raises(NotImplementedError):
+        D.create_dataset_given_range(w, ['avg_vel'], ranges, ['Biker'], str(out), 4, True, same_group_size=True)
+    # the command lines: sdd_dataset --reload --varf avg_vel ..., generate_varf
+    w.to_pickle(tmp_path / 'Biker.pkl')
+    _, printed = quiet(S.main, ['--reload', '--raw_data_dir', str(tmp_path), '--raw_data_filename', 'Biker.pkl', '--varf', 'avg_vel',
+                                '--labels', 'Biker', '--filter_data_dir', str(tmp_path / 'f'), '--obs_len', '4'])
+    assert "Variation factor = ['avg_vel']" in printed and sorted(os.listdir(tmp_path / 'f' / 'avg_vel' / 'Biker')) == ['0.5_3.5.pkl']
+    _, printed = quiet(generate_varf.main, ['--raw_data_dir', str(tmp_path), '--raw_data_filename', 'Biker.pkl', '--additional_data_dir',
+                                            str(tmp_path), '--obs_len', '4'])
+    saved = pd.read_pickle(tmp_path / 'df_varfs.pkl')
+    assert list(saved.columns) == ['metaId', 'label', 'sceneId', 'scene', 'avg_vel'] and np.array_equal(saved.avg_vel, table.avg_vel)
+    with pytest.raises(NotImplementedError):
+        quiet(S.main, ['--reload', '--raw_data_dir', str(tmp_path), '--raw_data_filename', 'Biker.pkl', '--varf', 'min_dist'])
