@@ -10,8 +10,9 @@ import pandas as pd
 SDD_LABELS = ['Pedestrian', 'Biker', 'Cart', 'Pedestrian', 'Biker']
 
 
-def write_sdd(root, seed=0):
-    """3 videos, 5 tracks each, 280-520 frames at 30 fps; track 1 has a frame gap, track 2 a run of lost boxes."""
+def write_sdd(root, seed=0, start=(100, 900), speed_x=(0.3, 2.0), speed_y=(-1.0, 1.0)):
+    """3 videos, 5 tracks each, 280-520 frames at 30 fps; track 1 has a frame gap, track 2 a run of lost boxes.  (The
+    defaults are the fixture's; narrower ``start`` / ``speed_*`` keep the tracks inside a small image.)"""
     rng = np.random.RandomState(seed)
     for scene, videos in (('bookstore', [0, 1]), ('coupa', [3])):
         for v in videos:
@@ -20,8 +21,8 @@ def write_sdd(root, seed=0):
             rows = []
             for tid, label in enumerate(SDD_LABELS):
                 f0, n = int(rng.randint(0, 50)), int(rng.randint(280, 520))
-                x, y = rng.uniform(100, 900, 2)
-                vx, vy = rng.uniform(0.3, 2.0), rng.uniform(-1.0, 1.0)
+                x, y = rng.uniform(start[0], start[1], 2)
+                vx, vy = rng.uniform(*speed_x), rng.uniform(*speed_y)
                 for k in range(n):
                     frame = f0 + k + (40 if (tid == 1 and k > 250) else 0)
                     x += vx + rng.normal(0, 0.2)

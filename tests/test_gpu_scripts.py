@@ -241,3 +241,43 @@ def test_ind_ynetmod_sequential_split_smoothed_validation_cws(workspace_ind, cap
     row = pd.read_csv('csv/ind_eval.csv', float_precision='round_trip').iloc[0]
     assert (row.train_net, row.n_train, row.position, float(row.lr)) == ('mosa_1', 8, 'motion', 0.001)
     assert (row.ade, row.fde) == (float(averages[2][1]), float(averages[2][2]))
+
+
+def test_raw_recordings_to_trained_model(tmp_path, monkeypatch, capsys, cuda_device):
+    """The whole journey of scripts/sdd/preprocessing.sh + pretrain.sh in small: raw ``annotations.txt`` files -> ``sdd_dataset``
+    (split at gaps, downsample, window, per-agent-type pickles, factor table) -> ``split_dataset`` -> ``train`` from scratch on
+    the B200 path, with the scene images beside the annotations as in the SDD download."""
+    import cv2
+    from helpers import TinySeg
+    from oracle import synth_raw
+    from motion_style_transfer_b200 import train
+    from motion_style_transfer_b200.utils import sdd_dataset, split_dataset
+    from motion_style_transfer_b200.utils.parser import get_parser
+    raw = tmp_path / 'data' / 'sdd' / 'raw'
+    synth_raw.write_sdd(str(raw), seed=4, start=(250, 600), speed_x=(0.2, 0.9), speed_y=(-0.4, 0.4))    # x < 910, y < 600
+    rng = np.random.RandomState(1)
+    for dp, _, files in os.walk(raw / 'annotations'):
+        if 'annotations.txt' in files:
+            assert cv2.imwrite(os.path.join(dp, 'reference.jpg'), rng.randint(0, 256, (640, 960, 3)).astype(np.uint8))
+    torch.manual_seed(0)
+    torch.save(TinySeg(6), tmp_path / 'data' / 'sdd' / 'sdd_segmentation.pth')
+    os.makedirs(tmp_path / 'config')
+    with open(tmp_path / 'config' / 'tiny.yaml', 'w') as f:
+        yaml.safe_dump(CONFIG, f, sort_keys=False)
+    monkeypatch.chdir(tmp_path)
+    sdd_dataset.main('--raw_data_dir data/sdd/raw --additional_data_dir data/sdd/raw --filter_data_dir data/sdd/filter/shortterm '
+                     '--window_size 11 --stride 11 --obs_len 5 --varf agent_type --labels Pedestrian Biker'.split())
+    split_dataset.main('--data_dir data/sdd/filter/shortterm/agent_type --data_filename Pedestrian.pkl --val_split 0.2 '
+                       '--test_split 0.2 --seed 1'.split())
+    out = capsys.readouterr().out
+    assert '# data = 16' in out and '# train = 10' in out and '# val = 3' in out and '# test = 3' in out
+    train.main(get_parser(True).parse_args(
+        '--config_filename tiny.yaml --dataset_path filter/shortterm/agent_type/Pedestrian --network original --load_data '
+        'predefined --batch_size 4 --seed 1 --n_epoch 2 --n_round 1 --ckpt_path ckpts'.split()))
+    out = capsys.readouterr().out
+    assert 'df_train: (110, 8); #=10' in out and 'df_test: (33, 8); #=3' in out       # (+ label, frame_diff columns)
+    ade, fde = (float(v) for v in re.findall(AVERAGE, out)[0][1:])
+    assert np.isfinite(ade) and np.isfinite(fde) and 0 < ade < 2000
+    epochs = re.findall(r'Epoch (\d+): \tTrain \(Top-1\) ADE: ([\d\.]+) FDE: ([\d\.]+) \t\tVal \(Top-k\) ADE: ([\d\.]+)', out)
+    assert [e[0] for e in epochs] == ['0', '1']
+    assert os.path.exists('ckpts/Seed_1__filter_shortterm_agent_type_Pedestrian__train__original.pt')
